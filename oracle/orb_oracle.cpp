@@ -1,0 +1,850 @@
+/*
+ * orb_oracle.cpp — CPU ORACLE for the ORB front end.  TEST INFRASTRUCTURE ONLY.
+ *
+ * A from-scratch restatement of the reference's algorithm (caomw/ORBSLAM_jpMiniPC,
+ * ORB-SLAM v1) for the path the B200 product accelerates.  Every function cites the
+ * reference file:line it follows.  The OpenCV primitives the reference calls
+ * (resize, copyMakeBorder, FAST, KeyPointsFilter::retainBest, GaussianBlur,
+ * fastAtan2, cvRound, gemm) live in an un-vendored third party (OpenCV, unpinned
+ * `find_package(OpenCV REQUIRED)`, reference CMakeLists.txt:19); they are restated
+ * here to the semantics of OpenCV 4.13.0 as observable through python cv2 in the
+ * build container and pinned by tests/test_oracle_vs_cv2.py + tests/golden/.
+ *
+ * Build: g++ -O3 -march=x86-64-v3 -ffp-contract=off (no FMA contraction: every fused
+ * multiply-add that is part of the spec is written as an explicit fmaf()).
+ * std::nth_element of this toolchain's libstdc++ (GCC 13) is part of the spec
+ * (it defines which tied keypoints survive retainBest and in what order).
+ */
+#include "orb_oracle.h"
+
+#include <algorithm>
+#include <climits>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+const int PATCH_SIZE = 31;       /* src/ORBextractor.cc:75 */
+const int HALF_PATCH_SIZE = 15;  /* :76 */
+const int EDGE_THRESHOLD = 16;   /* :77 */
+
+const int8_t kPattern[1024] = {
+#include "orb_pattern.inc"
+};
+
+/* cvRound = round-half-even (SSE cvtsd2si under the default rounding mode) */
+inline int cv_round(double v) { return (int)lrint(v); }
+inline int cv_roundf(float v) { return (int)lrintf(v); }
+inline int cv_floor(double v) { int i = (int)v; return i - (i > v); }
+inline int cv_ceil(double v) { int i = (int)v; return i + (i < v); }
+inline uint8_t sat_u8(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+
+struct KP { float x, y, size, angle, response; int octave, class_id; };
+struct RespGreater { bool operator()(const KP& a, const KP& b) const { return a.response > b.response; } };
+
+/* ---------------------------------------------------------------- resize ---
+ * cv::resize(src,dst,sz,0,0,INTER_LINEAR) for CV_8UC1 (reference call site
+ * src/ORBextractor.cc:800).  OpenCV: inv_scale = (double)dsize/ssize,
+ * scale = 1./inv_scale; per destination column fx=(float)((dx+0.5)*scale-0.5),
+ * sx=floor(fx), fx-=sx, clamped at both ends; 11-bit fixed-point coefficients
+ * (saturate_cast<short>(f*2048) = round-half-even); horizontal pass in int32,
+ * vertical pass (((b0*(S0>>4))>>16)+((b1*(S1>>4))>>16)+2)>>2.  Rows are clipped
+ * (not re-weighted) in the vertical direction. */
+void resize_linear_u8(const uint8_t* src, int sw, int sh, int sstride,
+                      uint8_t* dst, int dw, int dh, int dstride)
+{
+    const double inv_sx = (double)dw / sw, inv_sy = (double)dh / sh;
+    const double scale_x = 1. / inv_sx, scale_y = 1. / inv_sy;
+    std::vector<int> xofs(dw), yofs(dh);
+    std::vector<short> alpha(2 * dw), beta(2 * dh);
+    for (int dx = 0; dx < dw; dx++) {
+        float fx = (float)((dx + 0.5) * scale_x - 0.5);
+        int sx = cv_floor(fx);
+        fx -= sx;
+        if (sx < 0) { fx = 0; sx = 0; }
+        if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+        xofs[dx] = sx;
+        alpha[2 * dx] = (short)cv_roundf((1.f - fx) * 2048);
+        alpha[2 * dx + 1] = (short)cv_roundf(fx * 2048);
+    }
+    for (int dy = 0; dy < dh; dy++) {
+        float fy = (float)((dy + 0.5) * scale_y - 0.5);
+        int sy = cv_floor(fy);
+        fy -= sy;
+        yofs[dy] = sy;
+        beta[2 * dy] = (short)cv_roundf((1.f - fy) * 2048);
+        beta[2 * dy + 1] = (short)cv_roundf(fy * 2048);
+    }
+    std::vector<int> r0(dw), r1(dw);
+    for (int dy = 0; dy < dh; dy++) {
+        int sy0 = std::min(std::max(yofs[dy], 0), sh - 1);
+        int sy1 = std::min(std::max(yofs[dy] + 1, 0), sh - 1);
+        const uint8_t* S0 = src + (size_t)sy0 * sstride;
+        const uint8_t* S1 = src + (size_t)sy1 * sstride;
+        for (int dx = 0; dx < dw; dx++) {
+            int sx = xofs[dx];
+            int sx1 = std::min(sx + 1, sw - 1);
+            int a0 = alpha[2 * dx], a1 = alpha[2 * dx + 1];
+            r0[dx] = S0[sx] * a0 + S0[sx1] * a1;
+            r1[dx] = S1[sx] * a0 + S1[sx1] * a1;
+        }
+        int b0 = beta[2 * dy], b1 = beta[2 * dy + 1];
+        uint8_t* D = dst + (size_t)dy * dstride;
+        for (int dx = 0; dx < dw; dx++)
+            D[dx] = sat_u8((((b0 * (r0[dx] >> 4)) >> 16) + ((b1 * (r1[dx] >> 4)) >> 16) + 2) >> 2);
+    }
+}
+
+/* copyMakeBorder(..., BORDER_REFLECT_101) in place on a padded plane whose
+ * interior is already filled (reference src/ORBextractor.cc:806,814). */
+inline int reflect101(int p, int len)
+{
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) { if (p < 0) p = -p; else p = 2 * len - 2 - p; }
+    return p;
+}
+void border_reflect101(uint8_t* plane, int w, int h, int stride, int b)
+{
+    for (int y = 0; y < h; y++) {
+        uint8_t* row = plane + (size_t)(y + b) * stride + b;
+        for (int x = -b; x < 0; x++) row[x] = row[reflect101(x, w)];
+        for (int x = w; x < w + b; x++) row[x] = row[reflect101(x, w)];
+    }
+    for (int y = -b; y < h + b; y++) {
+        if (y >= 0 && y < h) continue;
+        int sy = reflect101(y, h);
+        memcpy(plane + (size_t)(y + b) * stride, plane + (size_t)(sy + b) * stride, w + 2 * b);
+    }
+}
+
+/* ------------------------------------------------------------------ FAST ---
+ * cv::FAST(img, kps, th, nonmaxSuppression=true), TYPE_9_16 (reference call
+ * sites src/ORBextractor.cc:607,613).  Ring order = OpenCV's 16-pixel Bresenham
+ * circle.  corner <=> some 9 contiguous ring pixels all darker than p-th or all
+ * brighter than p+th.  Score (OpenCV cornerScore<16>) = max over the 16 arcs of
+ * min(|diff| over the arc, signed) - 1, independent of th for corners.  NMS:
+ * keep iff score > all 8 neighbours' scores (non-corners and the 3-px margin
+ * count 0).  Output in raster order, coordinates local to img. */
+const int kRing[16][2] = { {0,3},{1,3},{2,2},{3,1},{3,0},{3,-1},{2,-2},{1,-3},
+                           {0,-3},{-1,-3},{-2,-2},{-3,-1},{-3,0},{-3,1},{-2,2},{-1,3} };
+
+inline int fast_score_px(const uint8_t* p, const int* ofs, int th)
+{
+    /* quick reject (same idea as OpenCV's table test): every 9-arc of the ring contains
+     * one pixel of each opposite pair, so a corner needs, for every pair, a member that is
+     * darker than v-th (bit 1) or brighter than v+th (bit 2), consistently. */
+    const int v = p[0], lo = v - th, hi = v + th;
+#define CLS(k) ((p[ofs[k]] < lo ? 1 : 0) | (p[ofs[k]] > hi ? 2 : 0))
+    int m = CLS(0) | CLS(8);
+    if (!m) return INT_MIN;
+    m &= CLS(4) | CLS(12);
+    if (!m) return INT_MIN;
+    m &= CLS(2) | CLS(10);
+    m &= CLS(6) | CLS(14);
+    if (!m) return INT_MIN;
+#undef CLS
+    int d[32];
+    for (int k = 0; k < 16; k++) d[k] = d[k + 16] = v - p[ofs[k]];
+    /* max over 16 arcs of min over 9 contiguous (darker ring) and of min of -d (brighter ring) */
+    int best = INT_MIN;
+    int m2[24], M2[24];
+    for (int k = 0; k < 24; k++) { m2[k] = std::min(d[k], d[k + 1]); M2[k] = std::max(d[k], d[k + 1]); }
+    for (int k = 0; k < 16; k++) {
+        int mn = std::min(std::min(m2[k], m2[k + 2]), std::min(m2[k + 4], m2[k + 6]));
+        int mx = std::max(std::max(M2[k], M2[k + 2]), std::max(M2[k + 4], M2[k + 6]));
+        mn = std::min(mn, d[k + 8]); mx = std::max(mx, d[k + 8]);
+        best = std::max(best, std::max(mn, -mx));
+    }
+    return best;   /* corner at threshold th  <=>  best > th ; response = best-1 */
+}
+
+int fast9_nms(const uint8_t* img, int w, int h, int stride, int th, std::vector<KP>& out)
+{
+    out.clear();
+    if (w < 7 || h < 7) return 0;
+    int ofs[16];
+    for (int k = 0; k < 16; k++) ofs[k] = kRing[k][1] * stride + kRing[k][0];
+    std::vector<uint8_t> sc((size_t)w * h, 0);
+    for (int y = 3; y < h - 3; y++)
+        for (int x = 3; x < w - 3; x++) {
+            int b = fast_score_px(img + (size_t)y * stride + x, ofs, th);
+            if (b > th) sc[(size_t)y * w + x] = (uint8_t)(b - 1);
+        }
+    for (int y = 3; y < h - 3; y++)
+        for (int x = 3; x < w - 3; x++) {
+            int s = sc[(size_t)y * w + x];
+            if (!s) continue;
+            const uint8_t* r = &sc[(size_t)y * w + x];
+            if (s > r[-1] && s > r[1] && s > r[-w - 1] && s > r[-w] && s > r[-w + 1] &&
+                s > r[w - 1] && s > r[w] && s > r[w + 1]) {
+                KP k; k.x = (float)x; k.y = (float)y; k.size = 7.f; k.angle = -1.f;
+                k.response = (float)s; k.octave = 0; k.class_id = -1;
+                out.push_back(k);
+            }
+        }
+    return (int)out.size();
+}
+
+/* KeyPointsFilter::retainBest(v, n) of OpenCV 4.x followed by the reference's
+ * `if(size>n) resize(n)` (src/ORBextractor.cc:683-685, :699-700): the survivors are
+ * the first n elements after std::nth_element(begin, begin+n-1, end, response>). */
+void retain_best(std::vector<KP>& v, int n)
+{
+    if (n >= 0 && v.size() > (size_t)n) {
+        if (n == 0) { v.clear(); return; }
+        std::nth_element(v.begin(), v.begin() + n - 1, v.end(), RespGreater());
+        float amb = v[n - 1].response;
+        std::vector<KP>::iterator new_end =
+            std::partition(v.begin() + n, v.end(), [amb](const KP& k) { return k.response >= amb; });
+        v.resize(new_end - v.begin());
+    }
+    if ((int)v.size() > n) v.resize(n);
+}
+
+/* cv::fastAtan2(y,x) (degrees, OpenCV 4.x scalar atan_f32), called from IC_Angle
+ * src/ORBextractor.cc:150.  Every operation rounded to FP32, no FMA. */
+float fast_atan2(float y, float x)
+{
+    const float scale = (float)(180 / M_PI);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale;
+    const float p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+    float ax = std::fabs(x), ay = std::fabs(y), a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = ax / (ay + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+/* IC_Angle, src/ORBextractor.cc:124-151 */
+float ic_angle(const uint8_t* center, int step, const int* umax)
+{
+    int m_01 = 0, m_10 = 0;
+    for (int u = -HALF_PATCH_SIZE; u <= HALF_PATCH_SIZE; ++u) m_10 += u * center[u];
+    for (int v = 1; v <= HALF_PATCH_SIZE; ++v) {
+        int v_sum = 0, d = umax[v];
+        for (int u = -d; u <= d; ++u) {
+            int val_plus = center[u + v * step], val_minus = center[u - v * step];
+            v_sum += (val_plus - val_minus);
+            m_10 += u * (val_plus + val_minus);
+        }
+        m_01 += v * v_sum;
+    }
+    return fast_atan2((float)m_01, (float)m_10);
+}
+
+/* computeOrbDescriptor, src/ORBextractor.cc:155-194.  cos/sin: the reference's
+ * cosf/sinf (libm-variant dependent in the last bit) are pinned to correctly
+ * rounded single precision computed through double. */
+void rbrief(const uint8_t* center, int step, float angle_deg, uint8_t* desc)
+{
+    const float factorPI = (float)(M_PI / 180.f);        /* :154 */
+    float angle = angle_deg * factorPI;                   /* :159 */
+    float a = (float)cos((double)angle), b = (float)sin((double)angle);
+    const int8_t* pat = kPattern;
+    for (int i = 0; i < 32; ++i, pat += 32) {
+        int val = 0;
+        for (int k = 0; k < 8; k++) {
+            float x0 = pat[4 * k], y0 = pat[4 * k + 1], x1 = pat[4 * k + 2], y1 = pat[4 * k + 3];
+            int t0 = center[cv_roundf(x0 * b + y0 * a) * step + cv_roundf(x0 * a - y0 * b)];
+            int t1 = center[cv_roundf(x1 * b + y1 * a) * step + cv_roundf(x1 * a - y1 * b)];
+            val |= (t0 < t1) << k;
+        }
+        desc[i] = (uint8_t)val;
+    }
+}
+
+/* GaussianBlur(m, m, Size(7,7), 2, 2, BORDER_REFLECT_101), src/ORBextractor.cc:760,
+ * applied to the level ROI of a padded plane: reads the real border (== reflect-101),
+ * writes only the ROI.  src points at the ROI origin inside the padded plane. */
+const uint32_t kGaussBits[7] = { 0x3d8fafb1u, 0x3e06387eu, 0x3e434a39u, 0x3e5d4ae0u,
+                                 0x3e434a39u, 0x3e06387eu, 0x3d8fafb1u };
+void gaussian_blur7(const uint8_t* src, int w, int h, int stride, uint8_t* dst, int dstride, int variant)
+{
+    if (variant == ORC_BLUR_F32_SEPFILTER) {
+        float k[7];
+        memcpy(k, kGaussBits, sizeof k);
+        std::vector<float> R((size_t)(h + 6) * w);
+        for (int y = -3; y < h + 3; y++) {
+            const uint8_t* S = src + (ptrdiff_t)y * stride;
+            float* r = &R[(size_t)(y + 3) * w];
+            for (int x = 0; x < w; x++) {
+                float s = 0.f;
+                for (int i = 0; i < 7; i++) s = fmaf((float)S[x + i - 3], k[i], s);
+                r[x] = s;
+            }
+        }
+        for (int y = 0; y < h; y++) {
+            uint8_t* D = dst + (size_t)y * dstride;
+            for (int x = 0; x < w; x++) {
+                const float* c = &R[(size_t)(y + 3) * w + x];
+                float s = k[3] * c[0];
+                for (int d = 1; d <= 3; d++) s = fmaf(c[(ptrdiff_t)d * w] + c[-(ptrdiff_t)d * w], k[3 + d], s);
+                D[x] = sat_u8((int)lrintf(s));
+            }
+        }
+        return;
+    }
+    static const int t256[7] = { 18, 34, 48, 56, 48, 34, 18 };
+    static const int t257[7] = { 18, 34, 49, 55, 49, 34, 18 };
+    const int* t = variant == ORC_BLUR_FIXED_256 ? t256 : t257;
+    std::vector<int> R((size_t)(h + 6) * w);
+    for (int y = -3; y < h + 3; y++) {
+        const uint8_t* S = src + (ptrdiff_t)y * stride;
+        for (int x = 0; x < w; x++) {
+            int s = 0;
+            for (int i = 0; i < 7; i++) s += S[x + i - 3] * t[i];
+            R[(size_t)(y + 3) * w + x] = s;
+        }
+    }
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int s = 0;
+            for (int i = 0; i < 7; i++) s += R[(size_t)(y + i) * w + x] * t[i];
+            dst[(size_t)y * dstride + x] = sat_u8((s + (1 << 15)) >> 16);
+        }
+}
+
+} // namespace
+
+/* ================================================================ extractor */
+struct orc_extractor {
+    int nfeatures; double scaleFactor; int nlevels, scoreType, fastTh, blurVariant;
+    std::vector<float> mvScaleFactor, mvInvScaleFactor;
+    std::vector<int> mnFeaturesPerLevel, umax;
+    struct Level {
+        int w = 0, h = 0, stride = 0, nDesired = 0, cols = 0, rows = 0, cellW = 0, cellH = 0, nfCell = 0, nKept = 0;
+        std::vector<uint8_t> plane, blurred;
+        std::vector<int> candCell, candX, candY, candScore, nTotal, nRetain;
+    };
+    std::vector<Level> lv;
+};
+
+extern "C" {
+
+orc_extractor* orc_extractor_create(int nfeatures, float scale_factor, int nlevels,
+                                    int score_type, int fast_th, int blur_variant)
+{
+    /* src/ORBextractor.cc:457-511 */
+    orc_extractor* e = new orc_extractor;
+    e->nfeatures = nfeatures; e->scaleFactor = scale_factor; e->nlevels = nlevels;
+    e->scoreType = score_type; e->fastTh = fast_th; e->blurVariant = blur_variant;
+    e->mvScaleFactor.resize(nlevels); e->mvInvScaleFactor.resize(nlevels);
+    e->mvScaleFactor[0] = 1;
+    for (int i = 1; i < nlevels; i++) e->mvScaleFactor[i] = (float)(e->mvScaleFactor[i - 1] * e->scaleFactor);
+    float invScaleFactor = (float)(1.0f / e->scaleFactor);
+    e->mvInvScaleFactor[0] = 1;
+    for (int i = 1; i < nlevels; i++) e->mvInvScaleFactor[i] = e->mvInvScaleFactor[i - 1] * invScaleFactor;
+
+    e->mnFeaturesPerLevel.resize(nlevels);
+    float factor = (float)(1.0 / e->scaleFactor);
+    float nDesired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int level = 0; level < nlevels - 1; level++) {
+        e->mnFeaturesPerLevel[level] = cv_roundf(nDesired);
+        sum += e->mnFeaturesPerLevel[level];
+        nDesired *= factor;
+    }
+    e->mnFeaturesPerLevel[nlevels - 1] = std::max(nfeatures - sum, 0);
+
+    e->umax.assign(HALF_PATCH_SIZE + 1, 0);
+    int v, v0, vmax = cv_floor(HALF_PATCH_SIZE * sqrtf(2.f) / 2 + 1);
+    int vmin = cv_ceil(HALF_PATCH_SIZE * sqrtf(2.f) / 2);
+    const double hp2 = HALF_PATCH_SIZE * HALF_PATCH_SIZE;
+    for (v = 0; v <= vmax; ++v) e->umax[v] = cv_round(sqrt(hp2 - v * v));
+    for (v = HALF_PATCH_SIZE, v0 = 0; v >= vmin; --v) {
+        while (e->umax[v0] == e->umax[v0 + 1]) ++v0;
+        e->umax[v] = v0;
+        ++v0;
+    }
+    e->lv.resize(nlevels);
+    return e;
+}
+
+void orc_extractor_destroy(orc_extractor* e) { delete e; }
+
+int orc_extract(orc_extractor* e, const uint8_t* img, int w, int h, int stride,
+                orc_keypoint* kps, uint8_t* desc, int cap, int* n)
+{
+    *n = 0;
+    if (!img || w <= 0 || h <= 0) return 0;             /* empty image: silent return, :721-722 */
+    const int nlevels = e->nlevels, B = EDGE_THRESHOLD;
+
+    /* ---- ComputePyramid, :781-822 (mask pyramid is never consumed, see :601-607) ---- */
+    for (int level = 0; level < nlevels; ++level) {
+        orc_extractor::Level& L = e->lv[level];
+        float scale = e->mvInvScaleFactor[level];
+        L.w = cv_roundf((float)w * scale); L.h = cv_roundf((float)h * scale);
+        if (L.w < 1 || L.h < 1) return -2;
+        L.stride = L.w + 2 * B;
+        L.plane.assign((size_t)L.stride * (L.h + 2 * B), 0);
+        uint8_t* roi = &L.plane[(size_t)B * L.stride + B];
+        if (level != 0) {
+            orc_extractor::Level& P = e->lv[level - 1];
+            resize_linear_u8(&P.plane[(size_t)B * P.stride + B], P.w, P.h, P.stride, roi, L.w, L.h, L.stride);
+        } else {
+            for (int y = 0; y < h; y++) memcpy(roi + (size_t)y * L.stride, img + (size_t)y * stride, w);
+        }
+        border_reflect101(L.plane.data(), L.w, L.h, L.stride, B);
+    }
+
+    /* ---- ComputeKeyPoints, :522-707 ---- */
+    std::vector<std::vector<KP> > allKeypoints(nlevels);
+    float imageRatio = (float)e->lv[0].w / e->lv[0].h;
+    for (int level = 0; level < nlevels; ++level) {
+        orc_extractor::Level& L = e->lv[level];
+        const int nDesiredFeatures = e->mnFeaturesPerLevel[level];
+        const int levelCols = (int)sqrtf((float)nDesiredFeatures / (5 * imageRatio));
+        const int levelRows = (int)(imageRatio * levelCols);
+        L.nDesired = nDesiredFeatures; L.cols = levelCols; L.rows = levelRows;
+        L.candCell.clear(); L.candX.clear(); L.candY.clear(); L.candScore.clear();
+        if (levelCols < 1 || levelRows < 1) return -2;   /* reference divides by zero here */
+
+        const int minBorderX = EDGE_THRESHOLD, minBorderY = minBorderX;
+        const int maxBorderX = L.w - EDGE_THRESHOLD, maxBorderY = L.h - EDGE_THRESHOLD;
+        const int W = maxBorderX - minBorderX, H = maxBorderY - minBorderY;
+        const int cellW = (int)ceilf((float)W / levelCols);
+        const int cellH = (int)ceilf((float)H / levelRows);
+        const int nCells = levelRows * levelCols;
+        const int nfeaturesCell = (int)ceilf((float)nDesiredFeatures / nCells);
+        L.cellW = cellW; L.cellH = cellH; L.nfCell = nfeaturesCell;
+
+        std::vector<std::vector<std::vector<KP> > > cellKeyPoints(levelRows, std::vector<std::vector<KP> >(levelCols));
+        std::vector<std::vector<int> > nToRetain(levelRows, std::vector<int>(levelCols, 0));
+        std::vector<std::vector<int> > nTotal(levelRows, std::vector<int>(levelCols, 0));
+        std::vector<std::vector<char> > bNoMore(levelRows, std::vector<char>(levelCols, 0));
+        std::vector<int> iniXCol(levelCols, 0), iniYRow(levelRows, 0);
+        int nNoMore = 0, nToDistribute = 0;
+
+        const uint8_t* roi = &L.plane[(size_t)B * L.stride + B];
+        float hY = (float)(cellH + 6);
+        for (int i = 0; i < levelRows; i++) {
+            const float iniY = (float)(minBorderY + i * cellH - 3);
+            iniYRow[i] = (int)iniY;
+            if (i == levelRows - 1) {
+                hY = maxBorderY + 3 - iniY;
+                if (hY <= 0) continue;
+            }
+            float hX = (float)(cellW + 6);
+            for (int j = 0; j < levelCols; j++) {
+                float iniX;
+                if (i == 0) { iniX = (float)(minBorderX + j * cellW - 3); iniXCol[j] = (int)iniX; }
+                else iniX = (float)iniXCol[j];
+                if (j == levelCols - 1) {
+                    hX = maxBorderX + 3 - iniX;
+                    if (hX <= 0) continue;
+                }
+                /* Mat::rowRange/colRange on the ROI: the reference throws if the cell leaves it */
+                int x0 = (int)iniX, x1 = (int)(iniX + hX), y0 = (int)iniY, y1 = (int)(iniY + hY);
+                if (x0 < 0 || y0 < 0 || x1 > L.w || y1 > L.h || x1 < x0 || y1 < y0) return -2;
+                const uint8_t* cellImage = roi + (size_t)y0 * L.stride + x0;
+                std::vector<KP>& kc = cellKeyPoints[i][j];
+                fast9_nms(cellImage, x1 - x0, y1 - y0, L.stride, e->fastTh, kc);      /* :607 */
+                if (kc.size() <= 3) { kc.clear(); fast9_nms(cellImage, x1 - x0, y1 - y0, L.stride, 7, kc); } /* :609-614 */
+                /* HARRIS_SCORE (:616-620) is not on the accelerated path */
+                for (size_t k = 0; k < kc.size(); k++) {
+                    L.candCell.push_back(i * levelCols + j); L.candX.push_back((int)kc[k].x);
+                    L.candY.push_back((int)kc[k].y); L.candScore.push_back((int)kc[k].response);
+                }
+                const int nKeys = (int)kc.size();
+                nTotal[i][j] = nKeys;
+                if (nKeys > nfeaturesCell) { nToRetain[i][j] = nfeaturesCell; bNoMore[i][j] = 0; }
+                else { nToRetain[i][j] = nKeys; nToDistribute += nfeaturesCell - nKeys; bNoMore[i][j] = 1; nNoMore++; }
+            }
+        }
+        /* quota redistribution, :644-670 */
+        while (nToDistribute > 0 && nNoMore < nCells) {
+            int nNewFeaturesCell = nfeaturesCell + (int)ceilf((float)nToDistribute / (nCells - nNoMore));
+            nToDistribute = 0;
+            for (int i = 0; i < levelRows; i++)
+                for (int j = 0; j < levelCols; j++)
+                    if (!bNoMore[i][j]) {
+                        if (nTotal[i][j] > nNewFeaturesCell) { nToRetain[i][j] = nNewFeaturesCell; bNoMore[i][j] = 0; }
+                        else {
+                            nToRetain[i][j] = nTotal[i][j];
+                            nToDistribute += nNewFeaturesCell - nTotal[i][j];
+                            bNoMore[i][j] = 1; nNoMore++;
+                        }
+                    }
+        }
+        L.nTotal.clear(); L.nRetain.clear();
+        for (int i = 0; i < levelRows; i++) for (int j = 0; j < levelCols; j++) {
+            L.nTotal.push_back(nTotal[i][j]); L.nRetain.push_back(nToRetain[i][j]);
+        }
+
+        std::vector<KP>& keypoints = allKeypoints[level];
+        const int scaledPatchSize = (int)(PATCH_SIZE * e->mvScaleFactor[level]);       /* :675 */
+        for (int i = 0; i < levelRows; i++)
+            for (int j = 0; j < levelCols; j++) {
+                std::vector<KP>& keysCell = cellKeyPoints[i][j];
+                retain_best(keysCell, nToRetain[i][j]);                                 /* :683-685 */
+                for (size_t k = 0; k < keysCell.size(); k++) {
+                    keysCell[k].x += iniXCol[j]; keysCell[k].y += iniYRow[i];
+                    keysCell[k].octave = level; keysCell[k].size = (float)scaledPatchSize;
+                    keypoints.push_back(keysCell[k]);
+                }
+            }
+        if ((int)keypoints.size() > nDesiredFeatures) retain_best(keypoints, nDesiredFeatures); /* :697-701 */
+        L.nKept = (int)keypoints.size();
+    }
+    /* orientations on the un-blurred planes, :705-706 */
+    for (int level = 0; level < nlevels; ++level) {
+        orc_extractor::Level& L = e->lv[level];
+        const uint8_t* roi = &L.plane[(size_t)B * L.stride + B];
+        for (KP& k : allKeypoints[level])
+            k.angle = ic_angle(roi + (size_t)cv_roundf(k.y) * L.stride + cv_roundf(k.x), L.stride, e->umax.data());
+    }
+
+    /* ---- operator() tail, :733-778 ---- */
+    int nkeypoints = 0;
+    for (int level = 0; level < nlevels; ++level) nkeypoints += (int)allKeypoints[level].size();
+    if (nkeypoints > cap) { *n = nkeypoints; return -3; }
+    int offset = 0;
+    for (int level = 0; level < nlevels; ++level) {
+        orc_extractor::Level& L = e->lv[level];
+        std::vector<KP>& keypoints = allKeypoints[level];
+        L.blurred = L.plane;
+        if (keypoints.empty()) continue;
+        gaussian_blur7(&L.plane[(size_t)B * L.stride + B], L.w, L.h, L.stride,
+                       &L.blurred[(size_t)B * L.stride + B], L.stride, e->blurVariant);
+        const uint8_t* roi = &L.blurred[(size_t)B * L.stride + B];
+        for (size_t i = 0; i < keypoints.size(); i++) {
+            const KP& k = keypoints[i];
+            rbrief(roi + (size_t)cv_roundf(k.y) * L.stride + cv_roundf(k.x), L.stride, k.angle,
+                   desc + (size_t)(offset + i) * 32);
+        }
+        if (level != 0) {
+            float scale = e->mvScaleFactor[level];
+            for (KP& k : keypoints) { k.x *= scale; k.y *= scale; }
+        }
+        for (size_t i = 0; i < keypoints.size(); i++) memcpy(&kps[offset + i], &keypoints[i], sizeof(KP));
+        offset += (int)keypoints.size();
+    }
+    *n = nkeypoints;
+    return 0;
+}
+
+int orc_nlevels(const orc_extractor* e) { return e->nlevels; }
+float orc_scale_factor(const orc_extractor* e, int l) { return e->mvScaleFactor[l]; }
+float orc_inv_scale_factor(const orc_extractor* e, int l) { return e->mvInvScaleFactor[l]; }
+int orc_features_per_level(const orc_extractor* e, int l) { return e->mnFeaturesPerLevel[l]; }
+const int* orc_umax(const orc_extractor* e) { return e->umax.data(); }
+int orc_level_info(const orc_extractor* e, int l, int* info)
+{
+    const orc_extractor::Level& L = e->lv[l];
+    int v[10] = { L.w, L.h, L.stride, L.nDesired, L.cols, L.rows, L.cellW, L.cellH, L.nfCell, L.nKept };
+    memcpy(info, v, sizeof v);
+    return 0;
+}
+const uint8_t* orc_level_plane(const orc_extractor* e, int l, int blurred)
+{
+    return blurred ? e->lv[l].blurred.data() : e->lv[l].plane.data();
+}
+int orc_level_candidates(const orc_extractor* e, int l, int cap, int* cell, int* x, int* y, int* score)
+{
+    const orc_extractor::Level& L = e->lv[l];
+    int n = (int)L.candCell.size();
+    if (n > cap) return -n;
+    for (int i = 0; i < n; i++) { cell[i] = L.candCell[i]; x[i] = L.candX[i]; y[i] = L.candY[i]; score[i] = L.candScore[i]; }
+    return n;
+}
+int orc_level_quota(const orc_extractor* e, int l, int* ntotal, int* nretain)
+{
+    const orc_extractor::Level& L = e->lv[l];
+    for (size_t i = 0; i < L.nTotal.size(); i++) { ntotal[i] = L.nTotal[i]; nretain[i] = L.nRetain[i]; }
+    return (int)L.nTotal.size();
+}
+
+/* ---- primitives ---- */
+void orc_resize_linear_u8(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int dstride)
+{ resize_linear_u8(src, sw, sh, sstride, dst, dw, dh, dstride); }
+void orc_border_reflect101(uint8_t* plane, int w, int h, int stride, int border)
+{ border_reflect101(plane, w, h, stride, border); }
+int orc_fast9_nms(const uint8_t* img, int w, int h, int stride, int th, int cap, int* x, int* y, int* score)
+{
+    std::vector<KP> v;
+    int n = fast9_nms(img, w, h, stride, th, v);
+    if (n > cap) return -n;
+    for (int i = 0; i < n; i++) { x[i] = (int)v[i].x; y[i] = (int)v[i].y; score[i] = (int)v[i].response; }
+    return n;
+}
+float orc_fast_atan2(float y, float x) { return fast_atan2(y, x); }
+void orc_gaussian_blur7(const uint8_t* src, int w, int h, int stride, uint8_t* dst, int dstride, int variant)
+{ gaussian_blur7(src, w, h, stride, dst, dstride, variant); }
+void orc_nth_element_desc(float* resp, int32_t* idx, int n, int nth)
+{
+    std::vector<KP> v(n);
+    for (int i = 0; i < n; i++) { v[i].response = resp[i]; v[i].class_id = idx[i]; }
+    std::nth_element(v.begin(), v.begin() + nth, v.end(), RespGreater());
+    for (int i = 0; i < n; i++) { resp[i] = v[i].response; idx[i] = v[i].class_id; }
+}
+int orc_retain_best(float* resp, int32_t* idx, int n, int npoints)
+{
+    std::vector<KP> v(n);
+    for (int i = 0; i < n; i++) { v[i].response = resp[i]; v[i].class_id = idx[i]; }
+    retain_best(v, npoints);
+    for (size_t i = 0; i < v.size(); i++) { resp[i] = v[i].response; idx[i] = v[i].class_id; }
+    return (int)v.size();
+}
+float orc_ic_angle(const uint8_t* center, int stride)
+{
+    static const int um[16] = { 15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3 };
+    return ic_angle(center, stride, um);
+}
+void orc_rbrief(const uint8_t* center, int stride, float angle_deg, uint8_t* desc32)
+{ rbrief(center, stride, angle_deg, desc32); }
+
+/* ================================================================== matcher */
+/* ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:1794-1810 (bit-hack popcount) */
+int orc_descriptor_distance(const uint8_t* a, const uint8_t* b)
+{
+    int dist = 0;
+    for (int i = 0; i < 8; i++) {
+        uint32_t x, y;
+        memcpy(&x, a + 4 * i, 4); memcpy(&y, b + 4 * i, 4);
+        unsigned int v = x ^ y;
+        v = v - ((v >> 1) & 0x55555555);
+        v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+        dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+    }
+    return dist;
+}
+static inline int dist_popcnt(const uint8_t* a, const uint8_t* b)
+{
+    uint64_t x[4], y[4];
+    memcpy(x, a, 32); memcpy(y, b, 32);
+    return __builtin_popcountll(x[0] ^ y[0]) + __builtin_popcountll(x[1] ^ y[1]) +
+           __builtin_popcountll(x[2] ^ y[2]) + __builtin_popcountll(x[3] ^ y[3]);
+}
+
+/* best / second-best sequential scan with strict '<' (src/ORBmatcher.cc:197-222) */
+void orc_knn2(const uint8_t* q, int nq, const uint8_t* db, int64_t ndb,
+              int32_t* idx1, int32_t* d1, int32_t* d2, int use_popcnt)
+{
+    for (int i = 0; i < nq; i++) {
+        int best1 = INT_MAX, best2 = INT_MAX, bi = -1;
+        const uint8_t* qi = q + (size_t)i * 32;
+        for (int64_t j = 0; j < ndb; j++) {
+            int dist = use_popcnt ? dist_popcnt(qi, db + (size_t)j * 32) : orc_descriptor_distance(qi, db + (size_t)j * 32);
+            if (dist < best1) { best2 = best1; best1 = dist; bi = (int)j; }
+            else if (dist < best2) best2 = dist;
+        }
+        idx1[i] = bi; d1[i] = best1; d2[i] = best2;
+    }
+}
+
+/* acceptance of src/ORBmatcher.cc:224-226: best<=th && (float)best < nnratio*(float)second */
+int orc_match_ratio(const int32_t* idx1, const int32_t* d1, const int32_t* d2, int nq,
+                    float nnratio, int th, int32_t* match)
+{
+    int n = 0;
+    for (int i = 0; i < nq; i++) {
+        match[i] = -1;
+        if (idx1[i] >= 0 && d1[i] <= th && (float)d1[i] < nnratio * (float)d2[i]) { match[i] = idx1[i]; n++; }
+    }
+    return n;
+}
+
+/* grid fill src/Frame.cc:109-123, PosInGrid :267-277 (round = half away from zero) */
+void orc_frame_grid(const orc_keypoint* kps, int n, int min_x, int max_x, int min_y, int max_y,
+                    int32_t* cell_start, int32_t* cell_items)
+{
+    const int GC = 64, GR = 48;
+    const float invW = (float)GC / (float)(max_x - min_x), invH = (float)GR / (float)(max_y - min_y);
+    std::vector<std::vector<int> > g(GC * GR);
+    for (int i = 0; i < n; i++) {
+        int px = (int)roundf((kps[i].x - min_x) * invW);
+        int py = (int)roundf((kps[i].y - min_y) * invH);
+        if (px < 0 || px >= GC || py < 0 || py >= GR) continue;
+        g[px * GR + py].push_back(i);
+    }
+    int o = 0;
+    for (int c = 0; c < GC * GR; c++) {
+        cell_start[c] = o;
+        for (int v : g[c]) cell_items[o++] = v;
+    }
+    cell_start[GC * GR] = o;
+}
+
+/* Frame::GetFeaturesInArea, src/Frame.cc:200-265 */
+int orc_features_in_area(const orc_frame* f, float x, float y, float r, int minLevel, int maxLevel,
+                         int32_t* out, int cap)
+{
+    const int GC = 64, GR = 48;
+    const float invW = (float)GC / (float)(f->max_x - f->min_x), invH = (float)GR / (float)(f->max_y - f->min_y);
+    int n = 0;
+    int nMinCellX = (int)floorf((x - f->min_x - r) * invW);
+    nMinCellX = std::max(0, nMinCellX);
+    if (nMinCellX >= GC) return 0;
+    int nMaxCellX = (int)ceilf((x - f->min_x + r) * invW);
+    nMaxCellX = std::min(GC - 1, nMaxCellX);
+    if (nMaxCellX < 0) return 0;
+    int nMinCellY = (int)floorf((y - f->min_y - r) * invH);
+    nMinCellY = std::max(0, nMinCellY);
+    if (nMinCellY >= GR) return 0;
+    int nMaxCellY = (int)ceilf((y - f->min_y + r) * invH);
+    nMaxCellY = std::min(GR - 1, nMaxCellY);
+    if (nMaxCellY < 0) return 0;
+    bool bCheckLevels = true, bSameLevel = false;
+    if (minLevel == -1 && maxLevel == -1) bCheckLevels = false;
+    else if (minLevel == maxLevel) bSameLevel = true;
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+            int c = ix * GR + iy;
+            for (int j = f->cell_start[c]; j < f->cell_start[c + 1]; j++) {
+                int id = f->cell_items[j];
+                const orc_keypoint& kp = f->kps[id];
+                if (bCheckLevels && !bSameLevel) { if (kp.octave < minLevel || kp.octave > maxLevel) continue; }
+                else if (bSameLevel) { if (kp.octave != minLevel) continue; }
+                if (std::fabs(kp.x - x) > r || std::fabs(kp.y - y) > r) continue;
+                if (n < cap) out[n] = id;
+                n++;
+            }
+        }
+    return n;
+}
+
+/* ORBmatcher::ComputeThreeMaxima, src/ORBmatcher.cc:1748-1789 */
+void orc_three_maxima(const int* hs, int L, int* i1, int* i2, int* i3)
+{
+    int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+    for (int i = 0; i < L; i++) {
+        const int s = hs[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) ind3 = -1;
+    *i1 = ind1; *i2 = ind2; *i3 = ind3;
+}
+
+static int rot_bin(float a_from, float a_to)
+{
+    /* src/ORBmatcher.cc:1583-1588 / :234-239; factor = 1/HISTO_LENGTH (sic) */
+    const float factor = 1.0f / 30;
+    float rot = a_from - a_to;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)roundf(rot * factor);
+    if (bin == 30) bin = 0;
+    return bin;
+}
+
+/* ORBmatcher::SearchByProjection(Frame&, const Frame&, float), src/ORBmatcher.cc:1507-1620.
+ * Rcw*x3Dw+tcw is one cv::gemm on CV_32F 3x3 * 3x1 (+C): OpenCV's small-matrix branch sums the
+ * three products in FP32 and adds the translation in double (pinned via cv2.gemm, see tests). */
+int orc_search_by_projection(const orc_frame* cur, const orc_frame* last, const uint8_t* last_has_mp,
+                             const uint8_t* last_outlier, const float* last_xyz, const float* T,
+                             float th, int check_ori, int32_t* match_cur)
+{
+    const int HISTO_LENGTH = 30, TH_HIGH = 100;
+    int nmatches = 0;
+    std::vector<int> rotHist[30];
+    std::vector<float> sf(cur->nlevels);
+    sf[0] = 1.0f;
+    for (int i = 1; i < cur->nlevels; i++) sf[i] = sf[i - 1] * cur->scale_factor;  /* src/Frame.cc:95-103 */
+    std::vector<int32_t> cand(cur->n > 0 ? cur->n : 1);
+    for (int i = 0; i < last->n; i++) {
+        if (!last_has_mp[i] || last_outlier[i]) continue;
+        const float X = last_xyz[3 * i], Y = last_xyz[3 * i + 1], Z = last_xyz[3 * i + 2];
+        float c[3];
+        for (int r = 0; r < 3; r++) {
+            float t0 = T[4 * r + 0] * X + T[4 * r + 1] * Y + T[4 * r + 2] * Z;
+            c[r] = (float)((double)t0 * 1.0 + (double)T[4 * r + 3] * 1.0);
+        }
+        const float xc = c[0], yc = c[1];
+        const float invzc = (float)(1.0 / c[2]);
+        float u = cur->fx * xc * invzc + cur->cx;
+        float v = cur->fy * yc * invzc + cur->cy;
+        if (u < cur->min_x || u > cur->max_x) continue;
+        if (v < cur->min_y || v > cur->max_y) continue;
+        int oct = last->kps[i].octave;
+        float radius = th * sf[oct];
+        int nc = orc_features_in_area(cur, u, v, radius, oct - 1, oct + 1, cand.data(), cur->n);
+        if (nc == 0) continue;
+        const uint8_t* dMP = last->desc + (size_t)i * 32;
+        int bestDist = INT_MAX, bestIdx2 = -1;
+        for (int k = 0; k < nc; k++) {
+            int i2 = cand[k];
+            if (match_cur[i2] >= 0) continue;
+            int dist = orc_descriptor_distance(dMP, cur->desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            match_cur[bestIdx2] = i;
+            nmatches++;
+            if (check_ori) rotHist[rot_bin(last->kps[i].angle, cur->kps[bestIdx2].angle)].push_back(bestIdx2);
+        }
+    }
+    if (check_ori) {
+        int hs[30], i1, i2, i3;
+        for (int i = 0; i < HISTO_LENGTH; i++) hs[i] = (int)rotHist[i].size();
+        orc_three_maxima(hs, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != i1 && i != i2 && i != i3)
+                for (int id : rotHist[i]) { match_cur[id] = -1; nmatches--; }
+    }
+    return nmatches;
+}
+
+/* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...), src/ORBmatcher.cc:155-284 */
+int orc_search_by_bow(const orc_featvec* kfv, const uint8_t* kf_desc, const orc_keypoint* kf_kps,
+                      const uint8_t* kf_mp_valid, int n_kf,
+                      const orc_featvec* ffv, const uint8_t* f_desc, const orc_keypoint* f_kps, int n_f,
+                      float nnratio, int check_ori, int32_t* match_f)
+{
+    (void)n_kf;
+    const int HISTO_LENGTH = 30, TH_LOW = 50;
+    for (int i = 0; i < n_f; i++) match_f[i] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[30];
+    int a = 0, b = 0;
+    while (a < kfv->nnodes && b < ffv->nnodes) {
+        if (kfv->node_id[a] == ffv->node_id[b]) {
+            for (int ik = kfv->start[a]; ik < kfv->start[a + 1]; ik++) {
+                const int realIdxKF = kfv->items[ik];
+                if (!kf_mp_valid[realIdxKF]) continue;
+                const uint8_t* dKF = kf_desc + (size_t)realIdxKF * 32;
+                int bestDist1 = INT_MAX, bestIdxF = -1, bestDist2 = INT_MAX;
+                for (int jf = ffv->start[b]; jf < ffv->start[b + 1]; jf++) {
+                    const int realIdxF = ffv->items[jf];
+                    if (match_f[realIdxF] >= 0) continue;
+                    const int dist = orc_descriptor_distance(dKF, f_desc + (size_t)realIdxF * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 <= TH_LOW && (float)bestDist1 < nnratio * (float)bestDist2) {
+                    match_f[bestIdxF] = realIdxKF;
+                    if (check_ori) rotHist[rot_bin(kf_kps[realIdxKF].angle, f_kps[bestIdxF].angle)].push_back(bestIdxF);
+                    nmatches++;
+                }
+            }
+            a++; b++;
+        } else if (kfv->node_id[a] < ffv->node_id[b]) {
+            while (a < kfv->nnodes && kfv->node_id[a] < ffv->node_id[b]) a++;     /* lower_bound */
+        } else {
+            while (b < ffv->nnodes && ffv->node_id[b] < kfv->node_id[a]) b++;
+        }
+    }
+    if (check_ori) {
+        int hs[30], i1, i2, i3;
+        for (int i = 0; i < HISTO_LENGTH; i++) hs[i] = (int)rotHist[i].size();
+        orc_three_maxima(hs, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == i1 || i == i2 || i == i3) continue;
+            for (int id : rotHist[i]) { match_f[id] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
+} // extern "C"

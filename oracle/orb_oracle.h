@@ -1,0 +1,119 @@
+/*
+ * orb_oracle.h — C API of the CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * The oracle is a from-scratch CPU restatement of the reference's ORB front end
+ * (caomw/ORBSLAM_jpMiniPC: src/ORBextractor.cc, src/ORBmatcher.cc, src/Frame.cc)
+ * with the OpenCV primitives the reference calls re-implemented to OpenCV-4.13
+ * semantics.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load it.  The product (liborb_b200.so) never does.
+ *
+ * PARITY PIN: the reference has no tests or golden vectors of its own and cannot be
+ * compiled in the build container (needs ROS + OpenCV C++).  The oracle is therefore
+ * pinned against the real OpenCV (python cv2 4.13.0) primitive by primitive and
+ * through cv2.ORB known-answer tests (tests/golden/, tests/test_oracle_vs_cv2.py).
+ */
+#ifndef ORB_ORACLE_H
+#define ORB_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* bit-compatible with cv::KeyPoint (28 B) */
+typedef struct orc_keypoint {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} orc_keypoint;
+
+enum { ORC_BLUR_F32_SEPFILTER = 0,   /* OpenCV 4.13, non-isolated sub-matrix (what the reference hits) */
+       ORC_BLUR_FIXED_256 = 1,       /* OpenCV 4.x bit-exact fixed-point path (contiguous Mat)          */
+       ORC_BLUR_FIXED_257 = 2 };     /* OpenCV 2.4-era 8-bit fixed-point taps (sum 257)                 */
+
+typedef struct orc_extractor orc_extractor;
+
+/* ORBextractor::ORBextractor, src/ORBextractor.cc:457-511 */
+orc_extractor* orc_extractor_create(int nfeatures, float scale_factor, int nlevels,
+                                    int score_type, int fast_th, int blur_variant);
+void orc_extractor_destroy(orc_extractor*);
+
+/* ORBextractor::operator(), src/ORBextractor.cc:718-779.  Returns 0, or <0 on error
+ * (-2: geometry the reference itself would throw on, -3: capacity). */
+int orc_extract(orc_extractor*, const uint8_t* img, int w, int h, int stride,
+                orc_keypoint* kps, uint8_t* desc, int cap, int* n);
+
+/* constant tables / per-level geometry (valid after a call to orc_extract) */
+int   orc_nlevels(const orc_extractor*);
+float orc_scale_factor(const orc_extractor*, int level);
+float orc_inv_scale_factor(const orc_extractor*, int level);
+int   orc_features_per_level(const orc_extractor*, int level);
+const int* orc_umax(const orc_extractor*);                 /* 16 ints */
+/* info[0..9] = w,h,stride(padded),nDesired,gridCols,gridRows,cellW,cellH,nfeaturesCell,nKept */
+int   orc_level_info(const orc_extractor*, int level, int* info);
+/* padded plane (w+32)x(h+32); blurred=0: as FAST/IC_Angle saw it, 1: after the in-place blur */
+const uint8_t* orc_level_plane(const orc_extractor*, int level, int blurred);
+/* candidates that entered retainBest (after the th=7 fallback), cell row-major then raster:
+ * arrays of capacity cap; returns count (or -needed).  x,y are cell-local. */
+int   orc_level_candidates(const orc_extractor*, int level, int cap, int* cell, int* x, int* y, int* score);
+/* per-cell nTotal / nToRetain, gridRows*gridCols ints each */
+int   orc_level_quota(const orc_extractor*, int level, int* ntotal, int* nretain);
+
+/* ---- primitives, exposed so each can be checked against cv2 on its own ---- */
+void  orc_resize_linear_u8(const uint8_t* src, int sw, int sh, int sstride,
+                           uint8_t* dst, int dw, int dh, int dstride);
+void  orc_border_reflect101(uint8_t* plane, int w, int h, int stride, int border); /* plane = padded origin */
+/* cv::FAST(img, kps, th, true) TYPE_9_16; returns count; x/y/score arrays capacity cap */
+int   orc_fast9_nms(const uint8_t* img, int w, int h, int stride, int th, int cap, int* x, int* y, int* score);
+float orc_fast_atan2(float y, float x);
+void  orc_gaussian_blur7(const uint8_t* src_padded_roi, int w, int h, int stride, uint8_t* dst, int dstride, int variant);
+/* std::nth_element(first, first+nth, last, response >) over (resp, idx) pairs — permutes both arrays */
+void  orc_nth_element_desc(float* resp, int32_t* idx, int n, int nth);
+/* KeyPointsFilter::retainBest + the reference's resize(n): returns new count */
+int   orc_retain_best(float* resp, int32_t* idx, int n, int npoints);
+float orc_ic_angle(const uint8_t* center, int stride);
+void  orc_rbrief(const uint8_t* center, int stride, float angle_deg, uint8_t* desc32);
+
+/* ---- matcher ---- */
+/* ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:1794-1810 */
+int   orc_descriptor_distance(const uint8_t* a, const uint8_t* b);
+/* best / second-best scan (pattern src/ORBmatcher.cc:197-222) over all db rows, no claims */
+void  orc_knn2(const uint8_t* q, int nq, const uint8_t* db, int64_t ndb,
+               int32_t* idx1, int32_t* d1, int32_t* d2, int use_popcnt);
+/* ratio/threshold acceptance: SearchByBoW form (src/ORBmatcher.cc:224-226) */
+int   orc_match_ratio(const int32_t* idx1, const int32_t* d1, const int32_t* d2, int nq,
+                      float nnratio, int th, int32_t* match);
+
+/* Frame grid: src/Frame.cc:109-123 (fill) + :267-277 (PosInGrid).  CSR over 64x48 cells,
+ * cell id = ix*48+iy.  cell_start has 64*48+1 entries, cell_items capacity n. */
+typedef struct orc_frame {
+    int n;
+    const orc_keypoint* kps;       /* mvKeysUn (== mvKeys, zero distortion) */
+    const uint8_t* desc;           /* n x 32 */
+    float fx, fy, cx, cy;
+    int min_x, max_x, min_y, max_y;  /* mnMinX.. (0,w,0,h for zero distortion, src/Frame.cc:342-348) */
+    int nlevels; float scale_factor; /* mnScaleLevels, mfScaleFactor (src/Frame.cc:92-103) */
+    const int32_t* cell_start; const int32_t* cell_items;
+} orc_frame;
+void  orc_frame_grid(const orc_keypoint* kps, int n, int min_x, int max_x, int min_y, int max_y,
+                     int32_t* cell_start, int32_t* cell_items);
+/* Frame::GetFeaturesInArea, src/Frame.cc:200-265; returns count */
+int   orc_features_in_area(const orc_frame* f, float x, float y, float r, int min_level, int max_level,
+                           int32_t* out, int cap);
+/* ORBmatcher::SearchByProjection(Frame&,const Frame&,float), src/ORBmatcher.cc:1507-1620.
+ * last_has_mp / last_outlier: per last-frame feature; last_xyz: world position of its map point.
+ * match_cur[i2] in/out: index of the last-frame feature whose map point claimed keypoint i2, or -1. */
+int   orc_search_by_projection(const orc_frame* cur, const orc_frame* last, const uint8_t* last_has_mp,
+                               const uint8_t* last_outlier, const float* last_xyz, const float* Tcw16,
+                               float th, int check_ori, int32_t* match_cur);
+/* ORBmatcher::SearchByBoW(KeyFrame*,Frame&,...), src/ORBmatcher.cc:155-284.  FeatureVectors as CSR:
+ * node ids ascending, per node the feature indices in insertion (ascending) order. */
+typedef struct orc_featvec { int nnodes; const int32_t* node_id; const int32_t* start; const int32_t* items; } orc_featvec;
+int   orc_search_by_bow(const orc_featvec* kf_fv, const uint8_t* kf_desc, const orc_keypoint* kf_kps,
+                        const uint8_t* kf_mp_valid, int n_kf,
+                        const orc_featvec* f_fv, const uint8_t* f_desc, const orc_keypoint* f_kps, int n_f,
+                        float nnratio, int check_ori, int32_t* match_f);
+void  orc_three_maxima(const int* hist_sizes, int L, int* ind1, int* ind2, int* ind3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

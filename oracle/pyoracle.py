@@ -1,0 +1,306 @@
+"""ctypes binding of the CPU oracle (oracle/liborb_oracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module; the product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liborb_oracle.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+BLUR_F32, BLUR_FIXED_256, BLUR_FIXED_257 = 0, 1, 2
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "orb_oracle.cpp")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "clean", "all"])
+    return _SO
+
+
+class _Frame(C.Structure):
+    _fields_ = [("n", C.c_int), ("kps", C.c_void_p), ("desc", C.c_void_p),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("min_x", C.c_int), ("max_x", C.c_int), ("min_y", C.c_int), ("max_y", C.c_int),
+                ("nlevels", C.c_int), ("scale_factor", C.c_float),
+                ("cell_start", C.c_void_p), ("cell_items", C.c_void_p)]
+
+
+class _FeatVec(C.Structure):
+    _fields_ = [("nnodes", C.c_int), ("node_id", C.c_void_p), ("start", C.c_void_p), ("items", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.orc_extractor_create.restype = C.c_void_p
+        L.orc_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_extractor_destroy.argtypes = [C.c_void_p]
+        L.orc_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_int, C.POINTER(C.c_int)]
+        L.orc_scale_factor.restype = C.c_float
+        L.orc_scale_factor.argtypes = [C.c_void_p, C.c_int]
+        L.orc_inv_scale_factor.restype = C.c_float
+        L.orc_inv_scale_factor.argtypes = [C.c_void_p, C.c_int]
+        L.orc_features_per_level.argtypes = [C.c_void_p, C.c_int]
+        L.orc_umax.restype = C.POINTER(C.c_int)
+        L.orc_umax.argtypes = [C.c_void_p]
+        L.orc_level_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_level_plane.restype = C.c_void_p
+        L.orc_level_plane.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_level_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4
+        L.orc_level_quota.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_resize_linear_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_border_reflect101.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_fast9_nms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 3
+        L.orc_fast_atan2.restype = C.c_float
+        L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orc_gaussian_blur7.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.orc_nth_element_desc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.orc_retain_best.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.orc_ic_angle.restype = C.c_float
+        L.orc_ic_angle.argtypes = [C.c_void_p, C.c_int]
+        L.orc_rbrief.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p]
+        L.orc_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_knn2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_match_ratio.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
+        L.orc_frame_grid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_features_in_area.argtypes = [C.POINTER(_Frame), C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_int]
+        L.orc_search_by_projection.argtypes = [C.POINTER(_Frame), C.POINTER(_Frame), C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p]
+        L.orc_search_by_bow.argtypes = [C.POINTER(_FeatVec), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.POINTER(_FeatVec), C.c_void_p, C.c_void_p, C.c_int,
+                                        C.c_float, C.c_int, C.c_void_p]
+        L.orc_three_maxima.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 3
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OracleExtractor:
+    """ORB_SLAM::ORBextractor restated on the CPU (reference include/ORBextractor.h:32-77)."""
+    HARRIS_SCORE, FAST_SCORE = 0, 1
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, scoreType=1, fastTh=20, blur=BLUR_F32):
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self._h = lib().orc_extractor_create(nfeatures, scaleFactor, nlevels, scoreType, fastTh, blur)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_extractor_destroy(self._h)
+            self._h = None
+
+    def __call__(self, image, mask=None):
+        image = np.asarray(image)
+        if image.size == 0:
+            return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        assert image.dtype == np.uint8 and image.ndim == 2 and image.strides[1] == 1
+        h, w = image.shape
+        cap = self.nfeatures + 64
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        rc = lib().orc_extract(self._h, _p(image), w, h, image.strides[0], _p(kps), _p(desc), cap, C.byref(n))
+        if rc != 0:
+            raise RuntimeError("orc_extract failed: %d" % rc)
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def scale_factors(self):
+        return np.array([lib().orc_scale_factor(self._h, l) for l in range(self.nlevels)], np.float32)
+
+    def inv_scale_factors(self):
+        return np.array([lib().orc_inv_scale_factor(self._h, l) for l in range(self.nlevels)], np.float32)
+
+    def features_per_level(self):
+        return [lib().orc_features_per_level(self._h, l) for l in range(self.nlevels)]
+
+    def umax(self):
+        p = lib().orc_umax(self._h)
+        return [p[i] for i in range(16)]
+
+    def level_info(self, level):
+        info = np.zeros(10, np.int32)
+        lib().orc_level_info(self._h, level, _p(info))
+        return dict(zip(["w", "h", "stride", "nDesired", "cols", "rows", "cellW", "cellH", "nfCell", "nKept"],
+                        [int(v) for v in info]))
+
+    def level_plane(self, level, blurred=False):
+        i = self.level_info(level)
+        ptr = lib().orc_level_plane(self._h, level, int(blurred))
+        buf = (C.c_uint8 * (i["stride"] * (i["h"] + 32))).from_address(ptr)
+        return np.frombuffer(buf, np.uint8).reshape(i["h"] + 32, i["stride"]).copy()
+
+    def level_candidates(self, level):
+        cap = 1 << 20
+        a = [np.zeros(cap, np.int32) for _ in range(4)]
+        n = lib().orc_level_candidates(self._h, level, cap, *[_p(x) for x in a])
+        assert n >= 0
+        return [x[:n].copy() for x in a]
+
+    def level_quota(self, level):
+        i = self.level_info(level)
+        nt = np.zeros(i["cols"] * i["rows"], np.int32)
+        nr = np.zeros_like(nt)
+        lib().orc_level_quota(self._h, level, _p(nt), _p(nr))
+        return nt, nr
+
+
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dw)
+    return dst
+
+
+def border_reflect101(img, b=16):
+    h, w = img.shape
+    plane = np.zeros((h + 2 * b, w + 2 * b), np.uint8)
+    plane[b:b + h, b:b + w] = img
+    lib().orc_border_reflect101(_p(plane), w, h, w + 2 * b, b)
+    return plane
+
+
+def fast9_nms(img, th):
+    assert img.dtype == np.uint8 and img.strides[1] == 1
+    cap = max(16, img.shape[0] * img.shape[1] // 4 + 16)
+    x, y, s = (np.zeros(cap, np.int32) for _ in range(3))
+    n = lib().orc_fast9_nms(_p(img), img.shape[1], img.shape[0], img.strides[0], th, cap, _p(x), _p(y), _p(s))
+    assert n >= 0
+    return x[:n].copy(), y[:n].copy(), s[:n].copy()
+
+
+def fast_atan2(y, x):
+    return lib().orc_fast_atan2(float(y), float(x))
+
+
+def gaussian_blur7(padded, b, variant=BLUR_F32):
+    """padded: (h+2b, w+2b) plane with a reflect-101 border (b>=3); returns the blurred (h, w) ROI."""
+    padded = np.ascontiguousarray(padded, np.uint8)
+    h, w = padded.shape[0] - 2 * b, padded.shape[1] - 2 * b
+    dst = np.zeros((h, w), np.uint8)
+    roi = padded.ctypes.data + b * padded.strides[0] + b
+    lib().orc_gaussian_blur7(C.c_void_p(roi), w, h, padded.strides[0], _p(dst), w, variant)
+    return dst
+
+
+def nth_element_desc(resp, nth):
+    r = np.ascontiguousarray(resp, np.float32).copy()
+    idx = np.arange(len(r), dtype=np.int32)
+    lib().orc_nth_element_desc(_p(r), _p(idx), len(r), nth)
+    return r, idx
+
+
+def retain_best(resp, n):
+    r = np.ascontiguousarray(resp, np.float32).copy()
+    idx = np.arange(len(r), dtype=np.int32)
+    m = lib().orc_retain_best(_p(r), _p(idx), len(r), n)
+    return r[:m], idx[:m]
+
+
+def ic_angle(padded, x, y):
+    padded = np.ascontiguousarray(padded, np.uint8)
+    return lib().orc_ic_angle(C.c_void_p(padded.ctypes.data + y * padded.strides[0] + x), padded.strides[0])
+
+
+def rbrief(padded, x, y, angle_deg):
+    padded = np.ascontiguousarray(padded, np.uint8)
+    d = np.zeros(32, np.uint8)
+    lib().orc_rbrief(C.c_void_p(padded.ctypes.data + y * padded.strides[0] + x), padded.strides[0],
+                     float(angle_deg), _p(d))
+    return d
+
+
+def descriptor_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return lib().orc_descriptor_distance(_p(a), _p(b))
+
+
+def knn2(q, db, use_popcnt=True):
+    q = np.ascontiguousarray(q, np.uint8)
+    db = np.ascontiguousarray(db, np.uint8)
+    nq = q.shape[0]
+    idx1, d1, d2 = (np.zeros(nq, np.int32) for _ in range(3))
+    lib().orc_knn2(_p(q), nq, _p(db), db.shape[0], _p(idx1), _p(d1), _p(d2), int(use_popcnt))
+    return idx1, d1, d2
+
+
+def match_ratio(idx1, d1, d2, nnratio, th):
+    m = np.zeros(len(idx1), np.int32)
+    n = lib().orc_match_ratio(_p(idx1), _p(d1), _p(d2), len(idx1), nnratio, th, _p(m))
+    return m, n
+
+
+class OracleFrame:
+    """The slice of ORB_SLAM::Frame the matcher reads (reference src/Frame.cc:56-128)."""
+
+    def __init__(self, kps, desc, w, h, fx, fy, cx, cy, nlevels=8, scale_factor=1.2):
+        self.kps = np.ascontiguousarray(kps, KP_DTYPE)
+        self.desc = np.ascontiguousarray(desc, np.uint8)
+        self.n = len(self.kps)
+        self.cell_start = np.zeros(64 * 48 + 1, np.int32)
+        self.cell_items = np.zeros(max(self.n, 1), np.int32)
+        lib().orc_frame_grid(_p(self.kps), self.n, 0, w, 0, h, _p(self.cell_start), _p(self.cell_items))
+        self.c = _Frame(self.n, self.kps.ctypes.data, self.desc.ctypes.data, fx, fy, cx, cy, 0, w, 0, h,
+                        nlevels, scale_factor, self.cell_start.ctypes.data, self.cell_items.ctypes.data)
+
+    def features_in_area(self, x, y, r, min_level=-1, max_level=-1):
+        out = np.zeros(max(self.n, 1), np.int32)
+        n = lib().orc_features_in_area(C.byref(self.c), x, y, r, min_level, max_level, _p(out), len(out))
+        return out[:n].copy()
+
+
+def search_by_projection(cur, last, last_has_mp, last_outlier, last_xyz, Tcw, th, check_ori=True, match_cur=None):
+    if match_cur is None:
+        match_cur = np.full(cur.n, -1, np.int32)
+    has = np.ascontiguousarray(last_has_mp, np.uint8)
+    out = np.ascontiguousarray(last_outlier, np.uint8)
+    xyz = np.ascontiguousarray(last_xyz, np.float32)
+    T = np.ascontiguousarray(Tcw, np.float32).reshape(16)
+    n = lib().orc_search_by_projection(C.byref(cur.c), C.byref(last.c), _p(has), _p(out), _p(xyz), _p(T),
+                                       th, int(check_ori), _p(match_cur))
+    return n, match_cur
+
+
+def _fv(node_id, start, items):
+    node_id = np.ascontiguousarray(node_id, np.int32)
+    start = np.ascontiguousarray(start, np.int32)
+    items = np.ascontiguousarray(items, np.int32)
+    return _FeatVec(len(node_id), node_id.ctypes.data, start.ctypes.data, items.ctypes.data), (node_id, start, items)
+
+
+def search_by_bow(kf_fv, kf_desc, kf_kps, kf_mp_valid, f_fv, f_desc, f_kps, nnratio, check_ori=True):
+    a, keep_a = _fv(*kf_fv)
+    b, keep_b = _fv(*f_fv)
+    kf_desc = np.ascontiguousarray(kf_desc, np.uint8)
+    f_desc = np.ascontiguousarray(f_desc, np.uint8)
+    kf_kps = np.ascontiguousarray(kf_kps, KP_DTYPE)
+    f_kps = np.ascontiguousarray(f_kps, KP_DTYPE)
+    valid = np.ascontiguousarray(kf_mp_valid, np.uint8)
+    m = np.full(len(f_kps), -1, np.int32)
+    n = lib().orc_search_by_bow(C.byref(a), _p(kf_desc), _p(kf_kps), _p(valid), len(kf_kps),
+                                C.byref(b), _p(f_desc), _p(f_kps), len(f_kps), nnratio, int(check_ori), _p(m))
+    return n, m
+
+
+def three_maxima(sizes):
+    s = np.ascontiguousarray(sizes, np.int32)
+    i1, i2, i3 = C.c_int(), C.c_int(), C.c_int()
+    lib().orc_three_maxima(_p(s), len(s), C.byref(i1), C.byref(i2), C.byref(i3))
+    return i1.value, i2.value, i3.value
