@@ -1,0 +1,171 @@
+/*
+ * orb_b200.h — C ABI of liborb_b200.so: the B200-native (sm_100a) ORB front end.
+ *
+ * Drop-in boundary for ONE path of caomw/ORBSLAM_jpMiniPC (ORB-SLAM v1): ORB extraction and
+ * binary-descriptor matching.  The reference has no FFI layer of its own; the boundary is the
+ * two C++ classes ORB_SLAM::ORBextractor (include/ORBextractor.h:32-77, called from
+ * src/Frame.cc:60) and ORB_SLAM::ORBmatcher (include/ORBmatcher.h:37-107).  Each entry point
+ * below names the reference symbol it replaces.  include/ORBextractor.h and
+ * include/ORBmatcher.h in this repo are header-only C++ shims with the reference's class
+ * names and call signatures on top of this ABI.
+ *
+ * Conventions: plain pointers and sizes, opaque handle, int status (0 = ok, <0 = error, see
+ * orb_error_string), no exceptions cross the ABI, caller owns all output buffers.  Image,
+ * keypoint and descriptor pointers may be HOST or DEVICE pointers unless a function says
+ * otherwise (detected with cudaPointerGetAttributes); the *_device entry points take device
+ * pointers only, enqueue on the given stream and do not synchronise.
+ * Every function fails with ORB_ERR_CUDA when no CUDA device is usable: there is no CPU path.
+ */
+#ifndef ORB_B200_H
+#define ORB_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* bit-compatible with cv::KeyPoint (28 bytes; also the record the reference fork serialises,
+ * include/SaveLoadWorld.h:1408-1424) */
+typedef struct orb_keypoint {
+    float x, y;        /* pt, level-0 image coordinates (src/ORBextractor.cc:769-775) */
+    float size;        /* (int)(31*scale[level])       (:675,692) */
+    float angle;       /* degrees [0,360), IC_Angle    (:124-151) */
+    float response;    /* FAST-9/16 score               (:607,613) */
+    int32_t octave;    /* pyramid level                 (:691) */
+    int32_t class_id;  /* -1 */
+} orb_keypoint;
+
+enum {
+    ORB_OK = 0,
+    ORB_ERR_INVALID = -1,      /* bad argument */
+    ORB_ERR_GEOMETRY = -2,     /* cell grid the reference itself cannot process (it throws / divides by 0) */
+    ORB_ERR_CAPACITY = -3,     /* caller buffer or context limit (max_w/max_h/max_batch/cap) too small */
+    ORB_ERR_CUDA = -4,         /* CUDA runtime error or no device; details via orb_last_cuda_error */
+    ORB_ERR_UNSUPPORTED = -5   /* e.g. HARRIS_SCORE (src/ORBextractor.cc:616-620, off the accelerated path) */
+};
+enum { ORB_HARRIS_SCORE = 0, ORB_FAST_SCORE = 1 };   /* include/ORBextractor.h:37 */
+
+typedef struct orb_ctx orb_ctx;
+
+const char* orb_error_string(int status);
+const char* orb_last_cuda_error(void);
+int         orb_abi_version(void);
+
+/* ---------------------------------------------------------------- extraction ----------
+ * ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, scoreType, fastTh)
+ * (src/ORBextractor.cc:457-511).  A context is stateful and not re-entrant, like the
+ * reference object (pyramid buffers are members, include/ORBextractor.h:74-75): use one
+ * context per calling thread.  max_w/max_h/max_batch size the device buffers. */
+orb_ctx* orb_create(int device, int nfeatures, float scale_factor, int nlevels, int score_type,
+                    int fast_th, int max_w, int max_h, int max_batch);
+void     orb_destroy(orb_ctx*);
+int      orb_nlevels(const orb_ctx*);          /* ORBextractor::GetLevels()      include/ORBextractor.h:47 */
+float    orb_scale_factor(const orb_ctx*);     /* ORBextractor::GetScaleFactor() include/ORBextractor.h:50 */
+int      orb_keypoint_capacity(const orb_ctx*);/* rows to allocate per image: sum of per-level quotas */
+
+/* ORBextractor::operator()(image, mask, keypoints, descriptors), src/ORBextractor.cc:718-779.
+ * The mask is a no-op in the reference (built at :791-810 but never handed to FAST, :601-607),
+ * so it is not part of the ABI.  img: 8-bit gray, row stride in bytes.  Empty image
+ * (img==NULL or w/h <= 0) -> *n = 0, ORB_OK (the reference returns silently, :721-722).
+ * kps[cap], desc[cap*32]; *n receives the keypoint count. */
+int orb_extract(orb_ctx*, const uint8_t* img, int w, int h, int stride,
+                orb_keypoint* kps, uint8_t* desc, int cap, int* n);
+
+/* nimg frames of the same shape, frame i at imgs + i*frame_pitch (bytes).  Outputs for frame i
+ * at kps + i*cap and desc + i*cap*32; counts[i] = its keypoint count.  Frames are independent
+ * (this is what is sharded across GPUs); internally processed in chunks of max_batch with
+ * copies and kernels overlapped on two streams when the buffers are host memory. */
+int orb_extract_batch(orb_ctx*, const uint8_t* imgs, int nimg, int w, int h, int stride, size_t frame_pitch,
+                      orb_keypoint* kps, uint8_t* desc, int cap, int32_t* counts);
+/* device pointers only, nimg <= max_batch, asynchronous on `stream` (a cudaStream_t). */
+int orb_extract_batch_device(orb_ctx*, const uint8_t* d_imgs, int nimg, int w, int h, int stride, size_t frame_pitch,
+                             orb_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts, void* stream);
+/* kernels launched by the last orb_extract* call on this context (for bench accounting) */
+int orb_last_launch_count(const orb_ctx*);
+
+/* test / inspection hooks (valid after an extract call; frame < nimg of that call's last chunk):
+ * info[0..9] = w,h,stride,nDesired,gridCols,gridRows,cellW,cellH,nfeaturesCell,nKept */
+int orb_debug_level_info(orb_ctx*, int frame, int level, int32_t* info);
+/* copies the padded (h+32) x stride plane to host memory `out`; which: 0 un-blurred, 1 blurred ROI
+ * (its 16-px border is undefined: descriptors read the un-blurred border, src/ORBextractor.cc:760) */
+int orb_debug_level_plane(orb_ctx*, int frame, int level, int which, uint8_t* out, size_t out_bytes);
+
+/* ------------------------------------------------------------------ matching ---------- */
+/* ORBmatcher::DescriptorDistance(a, b), src/ORBmatcher.cc:1794-1810 (two 32-byte host rows). */
+int orb_descriptor_distance(const uint8_t* a, const uint8_t* b);
+
+/* Brute-force best / second-best over ALL db rows with the reference's scan semantics
+ * (src/ORBmatcher.cc:197-222): idx1 = lowest index attaining the minimum, d1 = that distance,
+ * d2 = second order statistic of the distance multiset (ties with d1 count).  ndb == 0 ->
+ * idx1 = -1, d1 = d2 = INT32_MAX.  q[nq*32], db[ndb*32]. */
+int orb_hamming_knn2(orb_ctx*, const uint8_t* q, int nq, const uint8_t* db, int64_t ndb,
+                     int32_t* idx1, int32_t* d1, int32_t* d2);
+/* npairs independent (q, db) blocks laid out back to back (block p at q + p*nq*32, db + p*ndb*32);
+ * device pointers, asynchronous.  idx_base is added to every idx1 >= 0 (global index of a DB shard). */
+int orb_hamming_knn2_device(orb_ctx*, const uint8_t* d_q, int nq, const uint8_t* d_db, int64_t ndb, int npairs,
+                            int32_t idx_base, int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, void* stream);
+/* Exact merge of per-shard results: parts[s] = (idx1, d1, d2) of shard s, each
+ * nq int32 laid out as parts[(s*3+k)*nq + i].  best = lexicographic min of (d1, idx1);
+ * second = 2nd smallest of the multiset union {d1_s, d2_s}.  Device pointers, asynchronous. */
+int orb_knn2_merge_device(orb_ctx*, const int32_t* d_parts, int nparts, int nq,
+                          int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, void* stream);
+/* acceptance test of src/ORBmatcher.cc:224-226: d1 <= th && (float)d1 < nnratio*(float)d2.
+ * match[i] = idx1[i] or -1; returns the number of matches in *nmatches.  Host or device pointers. */
+int orb_match_ratio(orb_ctx*, const int32_t* idx1, const int32_t* d1, const int32_t* d2, int nq,
+                    float nnratio, int th, int32_t* match, int* nmatches);
+
+/* The slice of ORB_SLAM::Frame the matcher reads (src/Frame.cc:56-128, include/Frame.h). */
+typedef struct orb_frame_view {
+    int32_t n;                     /* Frame::N */
+    const orb_keypoint* kps;       /* mvKeysUn (== mvKeys: configs use zero distortion, src/Frame.cc:291-295) */
+    const uint8_t* desc;           /* mDescriptors, n x 32 */
+    float fx, fy, cx, cy;          /* Frame::fx.. (src/Frame.cc:80-83) */
+    int32_t min_x, max_x, min_y, max_y;   /* mnMinX.. (src/Frame.cc:342-348) */
+    int32_t nlevels; float scale_factor;  /* mnScaleLevels, mfScaleFactor (src/Frame.cc:92-93) */
+    const int32_t* cell_start;     /* 64*48+1: CSR of mGrid, cell id = ix*48+iy (include/Frame.h:35-36,90) */
+    const int32_t* cell_items;     /* keypoint indices in insertion order */
+} orb_frame_view;
+enum { ORB_GRID_COLS = 64, ORB_GRID_ROWS = 48 };
+
+/* Grid assignment of src/Frame.cc:109-123 with PosInGrid :267-277.  Host or device pointers
+ * (all of one kind).  cell_start[64*48+1], cell_items[n]. */
+int orb_frame_grid_build(orb_ctx*, const orb_keypoint* kps, int n, int min_x, int max_x, int min_y, int max_y,
+                         int32_t* cell_start, int32_t* cell_items);
+
+/* ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, float th),
+ * src/ORBmatcher.cc:1507-1620, constructed as ORBmatcher(nnratio, checkOri).  All pointers
+ * inside the views and the arrays below are HOST pointers or all DEVICE pointers.
+ * last_has_mp[i] != 0 <=> LastFrame.mvpMapPoints[i] != NULL; last_outlier = mvbOutlier;
+ * last_xyz[3*i..] = pMP->GetWorldPos(); Tcw = CurrentFrame.mTcw row-major 4x4.
+ * match_cur[i2] (in/out, cur->n entries) = index i of the last-frame feature whose map point is
+ * assigned to CurrentFrame.mvpMapPoints[i2], or -1.  *nmatches = the reference's return value. */
+int orb_search_by_projection(orb_ctx*, const orb_frame_view* cur, const orb_frame_view* last,
+                             const uint8_t* last_has_mp, const uint8_t* last_outlier, const float* last_xyz,
+                             const float* Tcw16, float th, int check_ori, int32_t* match_cur, int* nmatches);
+
+/* DBoW2::FeatureVector as CSR (Thirdparty/DBoW2/DBoW2/FeatureVector.cpp:31-45): node ids ascending,
+ * per node the feature indices in insertion order. */
+typedef struct orb_featvec_view {
+    int32_t nnodes; const int32_t* node_id; const int32_t* start; const int32_t* items;
+} orb_featvec_view;
+/* ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches),
+ * src/ORBmatcher.cc:155-284 (candidate scoring; the vocabulary transform that produces the
+ * FeatureVectors is out of scope).  kf_mp_valid[i] != 0 <=> KF feature i has a live map point.
+ * match_f[n_f] out = KF feature index matched to frame feature, or -1. */
+int orb_search_by_bow(orb_ctx*, const orb_featvec_view* kf_fv, const uint8_t* kf_desc, const orb_keypoint* kf_kps,
+                      const uint8_t* kf_mp_valid, int n_kf,
+                      const orb_featvec_view* f_fv, const uint8_t* f_desc, const orb_keypoint* f_kps, int n_f,
+                      float nnratio, int check_ori, int32_t* match_f, int* nmatches);
+
+/* pinned host memory helpers (page-locked buffers make the host<->device copies asynchronous) */
+void* orb_host_alloc(size_t bytes);
+void  orb_host_free(void* p);
+
+/* register-resident __popc micro-benchmark: measured POPC32 rate of this GPU in G ops/s
+ * (the integer-pipe roofline denominator for the matcher) */
+int orb_measure_popc_peak(orb_ctx*, double* gpopc_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

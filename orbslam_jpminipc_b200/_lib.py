@@ -1,0 +1,113 @@
+"""ctypes loader for liborb_b200.so (the C ABI declared in include/orb_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is usable the
+import / first call raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "liborb_b200.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+ORB_OK, ORB_ERR_INVALID, ORB_ERR_GEOMETRY, ORB_ERR_CAPACITY, ORB_ERR_CUDA, ORB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+GRID_COLS, GRID_ROWS = 64, 48
+
+# every symbol include/orb_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "orb_error_string", "orb_last_cuda_error", "orb_abi_version", "orb_create", "orb_destroy", "orb_nlevels",
+    "orb_scale_factor", "orb_keypoint_capacity", "orb_extract", "orb_extract_batch", "orb_extract_batch_device",
+    "orb_last_launch_count", "orb_debug_level_info", "orb_debug_level_plane", "orb_descriptor_distance",
+    "orb_hamming_knn2", "orb_hamming_knn2_device", "orb_knn2_merge_device", "orb_match_ratio",
+    "orb_frame_grid_build", "orb_search_by_projection", "orb_search_by_bow", "orb_host_alloc", "orb_host_free",
+    "orb_measure_popc_peak",
+]
+
+
+class FrameView(C.Structure):
+    _fields_ = [("n", C.c_int32), ("kps", C.c_void_p), ("desc", C.c_void_p),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("min_x", C.c_int32), ("max_x", C.c_int32), ("min_y", C.c_int32), ("max_y", C.c_int32),
+                ("nlevels", C.c_int32), ("scale_factor", C.c_float),
+                ("cell_start", C.c_void_p), ("cell_items", C.c_void_p)]
+
+
+class FeatVecView(C.Structure):
+    _fields_ = [("nnodes", C.c_int32), ("node_id", C.c_void_p), ("start", C.c_void_p), ("items", C.c_void_p)]
+
+
+class OrbError(RuntimeError):
+    def __init__(self, status, where):
+        self.status = status
+        L = lib()
+        msg = L.orb_error_string(status).decode()
+        if status == ORB_ERR_CUDA:
+            msg += " [" + L.orb_last_cuda_error().decode() + "]"
+        super().__init__("%s: %s (%d)" % (where, msg, status))
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError("liborb_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "or `make -C orbslam_jpminipc_b200/csrc`); there is no CPU fallback")
+    L = C.CDLL(SO_PATH)
+    vp, i32, f32, i64, sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
+    L.orb_error_string.restype = C.c_char_p
+    L.orb_error_string.argtypes = [i32]
+    L.orb_last_cuda_error.restype = C.c_char_p
+    L.orb_create.restype = vp
+    L.orb_create.argtypes = [i32, i32, f32, i32, i32, i32, i32, i32, i32]
+    L.orb_destroy.argtypes = [vp]
+    L.orb_nlevels.argtypes = [vp]
+    L.orb_scale_factor.restype = f32
+    L.orb_scale_factor.argtypes = [vp]
+    L.orb_keypoint_capacity.argtypes = [vp]
+    L.orb_extract.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, C.POINTER(C.c_int)]
+    L.orb_extract_batch.argtypes = [vp, vp, i32, i32, i32, i32, sz, vp, vp, i32, vp]
+    L.orb_extract_batch_device.argtypes = [vp, vp, i32, i32, i32, i32, sz, vp, vp, i32, vp, vp]
+    L.orb_last_launch_count.argtypes = [vp]
+    L.orb_debug_level_info.argtypes = [vp, i32, i32, vp]
+    L.orb_debug_level_plane.argtypes = [vp, i32, i32, i32, vp, sz]
+    L.orb_descriptor_distance.argtypes = [vp, vp]
+    L.orb_hamming_knn2.argtypes = [vp, vp, i32, vp, i64, vp, vp, vp]
+    L.orb_hamming_knn2_device.argtypes = [vp, vp, i32, vp, i64, i32, i32, vp, vp, vp, vp]
+    L.orb_knn2_merge_device.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
+    L.orb_match_ratio.argtypes = [vp, vp, vp, vp, i32, f32, i32, vp, C.POINTER(C.c_int)]
+    L.orb_frame_grid_build.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]
+    L.orb_search_by_projection.argtypes = [vp, C.POINTER(FrameView), C.POINTER(FrameView), vp, vp, vp, vp,
+                                           f32, i32, vp, C.POINTER(C.c_int)]
+    L.orb_search_by_bow.argtypes = [vp, C.POINTER(FeatVecView), vp, vp, vp, i32,
+                                    C.POINTER(FeatVecView), vp, vp, i32, f32, i32, vp, C.POINTER(C.c_int)]
+    L.orb_host_alloc.restype = vp
+    L.orb_host_alloc.argtypes = [sz]
+    L.orb_host_free.argtypes = [vp]
+    L.orb_measure_popc_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+def check(status, where):
+    if status != ORB_OK:
+        raise OrbError(status, where)
+
+
+def ptr(a):
+    """numpy array -> host pointer, torch tensor -> its data pointer, int -> as is."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(a.data_ptr())      # torch tensor

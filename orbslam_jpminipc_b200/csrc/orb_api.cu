@@ -1,0 +1,428 @@
+// orb_api.cu — C ABI (include/orb_b200.h): context, device buffers, extraction entry points.
+#include "orb_internal.h"
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+thread_local std::string g_last_cuda_error;
+
+int orb_cuda_fail(cudaError_t e, const char* what)
+{
+    g_last_cuda_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return ORB_ERR_CUDA;
+}
+
+template <typename T>
+static int ensure(T*& p, size_t& cap, size_t bytes)
+{
+    if (bytes <= cap && p) return ORB_OK;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    ORB_CUDA(cudaMalloc((void**)&p, std::max<size_t>(bytes, 256)));
+    cap = std::max<size_t>(bytes, 256);
+    return ORB_OK;
+}
+
+static bool is_device_ptr(const void* p)
+{
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// (re)build the geometry for this image shape and make sure every device buffer can hold nimg frames
+static int prepare(orb_ctx* c, int w, int h, int nimg)
+{
+    ORB_CUDA(cudaSetDevice(c->device));
+    const bool rebuild = !(c->plan_valid && c->plan.w == w && c->plan.h == h);
+    if (rebuild) {
+        int rc = orb_build_plan(c, w, h);
+        if (rc != ORB_OK) return rc;
+        size_t dummy = sizeof(Plan);
+        if (!c->d_plan) { size_t z = 0; rc = ensure(c->d_plan, z, sizeof(Plan)); if (rc) return rc; }
+        (void)dummy;
+        rc = ensure(c->d_cells, c->cap_cells, c->cells.size() * sizeof(CellGeom)); if (rc) return rc;
+        rc = ensure(c->d_tiles_fast, c->cap_tiles_fast, c->tiles_fast.size() * sizeof(Tile)); if (rc) return rc;
+        rc = ensure(c->d_tiles_blur, c->cap_tiles_blur, c->tiles_blur.size() * sizeof(Tile)); if (rc) return rc;
+        rc = ensure(c->d_xtab, c->cap_xtab, c->xtab.size() * sizeof(int2)); if (rc) return rc;
+        rc = ensure(c->d_ytab, c->cap_ytab, c->ytab.size() * sizeof(int2)); if (rc) return rc;
+        ORB_CUDA(cudaDeviceSynchronize());       // nothing in flight may still read the old tables
+        ORB_CUDA(cudaMemcpy(c->d_plan, &c->plan, sizeof(Plan), cudaMemcpyHostToDevice));
+        ORB_CUDA(cudaMemcpy(c->d_cells, c->cells.data(), c->cells.size() * sizeof(CellGeom), cudaMemcpyHostToDevice));
+        ORB_CUDA(cudaMemcpy(c->d_tiles_fast, c->tiles_fast.data(), c->tiles_fast.size() * sizeof(Tile), cudaMemcpyHostToDevice));
+        ORB_CUDA(cudaMemcpy(c->d_tiles_blur, c->tiles_blur.data(), c->tiles_blur.size() * sizeof(Tile), cudaMemcpyHostToDevice));
+        if (!c->xtab.empty()) ORB_CUDA(cudaMemcpy(c->d_xtab, c->xtab.data(), c->xtab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        if (!c->ytab.empty()) ORB_CUDA(cudaMemcpy(c->d_ytab, c->ytab.data(), c->ytab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        int maxcap = 0;
+        for (int l = 0; l < c->plan.nlevels; l++) maxcap = std::max(maxcap, c->plan.L[l].lvl_cap);
+        if ((size_t)maxcap * 8 > 200 * 1024) return ORB_ERR_CAPACITY;
+        rc = orb_select_smem_setup(std::max(maxcap * 8, 1024)); if (rc) return rc;
+        c->plan_valid = true;
+    }
+    const Plan& P = c->plan;
+    const size_t B = (size_t)std::min(std::max(nimg, 1), c->max_batch);
+    int rc;
+    rc = ensure(c->d_planes, c->planes_bytes, B * P.frame_bytes); if (rc) return rc;
+    rc = ensure(c->d_work, c->work_bytes, B * P.frame_bytes); if (rc) return rc;
+    rc = ensure(c->d_cand, c->cand_bytes, B * (size_t)P.cand_total * 4); if (rc) return rc;
+    rc = ensure(c->d_ntotal, c->ntotal_bytes, B * (size_t)P.ncells * 4); if (rc) return rc;
+    rc = ensure(c->d_lvl, c->lvl_bytes, B * (size_t)P.lvl_total * 8); if (rc) return rc;
+    return ORB_OK;
+}
+
+extern "C" {
+
+const char* orb_error_string(int s)
+{
+    switch (s) {
+    case ORB_OK: return "ok";
+    case ORB_ERR_INVALID: return "invalid argument";
+    case ORB_ERR_GEOMETRY: return "cell grid geometry the reference cannot process";
+    case ORB_ERR_CAPACITY: return "buffer or context capacity exceeded";
+    case ORB_ERR_CUDA: return "CUDA error / no usable device";
+    case ORB_ERR_UNSUPPORTED: return "unsupported option";
+    default: return "unknown status";
+    }
+}
+const char* orb_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+int orb_abi_version(void) { return 1; }
+
+orb_ctx* orb_create(int device, int nfeatures, float scale_factor, int nlevels, int score_type,
+                    int fast_th, int max_w, int max_h, int max_batch)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        g_last_cuda_error = "orb_create: no usable CUDA device (this library has no CPU path)";
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (score_type != ORB_FAST_SCORE || max_w < 1 || max_h < 1 || max_batch < 1 || fast_th < 1 || fast_th > 254) {
+        g_last_cuda_error = "orb_create: invalid or unsupported argument (HARRIS_SCORE is not accelerated)";
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { orb_cuda_fail(cudaGetLastError(), "cudaSetDevice"); return nullptr; }
+    orb_ctx* c = new orb_ctx;
+    c->device = device; c->nfeatures = nfeatures; c->scale_factor_f = scale_factor; c->nlevels = nlevels;
+    c->score_type = score_type; c->fast_th = fast_th; c->max_w = max_w; c->max_h = max_h; c->max_batch = max_batch;
+    if (orb_build_tables(c) != ORB_OK || orb_upload_constants(c->umax) != ORB_OK) { delete c; return nullptr; }
+    bool ok = cudaMalloc((void**)&c->d_nkept, sizeof(int) * ORB_MAX_LEVELS * max_batch) == cudaSuccess &&
+              cudaMalloc((void**)&c->d_status, sizeof(int)) == cudaSuccess &&
+              cudaMemset(c->d_status, 0, sizeof(int)) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; i++) {
+        ok = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok) { orb_cuda_fail(cudaGetLastError(), "orb_create allocations"); orb_destroy(c); return nullptr; }
+    return c;
+}
+
+void orb_destroy(orb_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    void* ptrs[] = { c->d_plan, c->d_cells, c->d_tiles_fast, c->d_tiles_blur, c->d_xtab, c->d_ytab, c->d_planes, c->d_work,
+                     c->d_cand, c->d_ntotal, c->d_lvl, c->d_nkept, c->d_status, c->d_src[0], c->d_src[1], c->d_kps[0],
+                     c->d_kps[1], c->d_desc[0], c->d_desc[1], c->d_counts[0], c->d_counts[1], c->d_knn_part, c->d_match_scratch };
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < 2; i++) {
+        if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+        if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
+    }
+    delete c;
+}
+
+int orb_nlevels(const orb_ctx* c) { return c ? c->nlevels : 0; }
+float orb_scale_factor(const orb_ctx* c) { return c ? (float)c->scaleFactor : 0.f; }
+int orb_keypoint_capacity(const orb_ctx* c)
+{
+    if (!c) return 0;
+    int s = 0;
+    for (int v : c->mnFeaturesPerLevel) s += v;
+    return s;
+}
+int orb_last_launch_count(const orb_ctx* c) { return c ? c->last_launches : 0; }
+
+int orb_extract_batch_device(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w, int h, int stride, size_t frame_pitch,
+                             orb_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts, void* stream)
+{
+    if (!c || !d_kps || !d_desc || !d_counts || cap < 1 || nimg < 0) return ORB_ERR_INVALID;
+    if (nimg == 0) return ORB_OK;
+    if (!d_imgs || w <= 0 || h <= 0) {              // empty image: no keypoints (src/ORBextractor.cc:721-722)
+        ORB_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * nimg, (cudaStream_t)stream));
+        return ORB_OK;
+    }
+    if (nimg > c->max_batch) return ORB_ERR_CAPACITY;
+    if (stride < w) return ORB_ERR_INVALID;
+    int rc = prepare(c, w, h, nimg);
+    if (rc != ORB_OK) return rc;
+    c->last_nimg = nimg;
+    return orb_launch_extract(c, d_imgs, nimg, w, h, stride, frame_pitch, d_kps, d_desc, cap, d_counts, (cudaStream_t)stream);
+}
+
+int orb_extract_batch(orb_ctx* c, const uint8_t* imgs, int nimg, int w, int h, int stride, size_t frame_pitch,
+                      orb_keypoint* kps, uint8_t* desc, int cap, int32_t* counts)
+{
+    if (!c || !kps || !desc || !counts || cap < 1 || nimg < 0) return ORB_ERR_INVALID;
+    if (nimg == 0) return ORB_OK;
+    if (!imgs || w <= 0 || h <= 0) { for (int i = 0; i < nimg; i++) counts[i] = 0; return ORB_OK; }
+    if (stride < w || frame_pitch < (size_t)stride * (h - 1) + w) return ORB_ERR_INVALID;
+    ORB_CUDA(cudaSetDevice(c->device));
+    const bool dev_in = is_device_ptr(imgs), dev_out = is_device_ptr(kps);
+    if (dev_out != is_device_ptr(desc) || dev_out != is_device_ptr(counts)) return ORB_ERR_INVALID;
+    int rc = prepare(c, w, h, nimg);
+    if (rc != ORB_OK) return rc;
+    const int B = std::min(nimg, c->max_batch);
+    const size_t src_chunk = (size_t)B * frame_pitch;
+    for (int i = 0; i < 2; i++) {
+        if (!dev_in) { rc = ensure(c->d_src[i], c->src_bytes[i], src_chunk); if (rc) return rc; }
+        if (!dev_out) {
+            rc = ensure(c->d_kps[i], c->kps_bytes[i], (size_t)B * cap * sizeof(orb_keypoint)); if (rc) return rc;
+            rc = ensure(c->d_desc[i], c->desc_bytes[i], (size_t)B * cap * 32); if (rc) return rc;
+            rc = ensure(c->d_counts[i], c->counts_bytes[i], (size_t)B * sizeof(int32_t)); if (rc) return rc;
+        }
+    }
+    ORB_CUDA(cudaMemsetAsync(c->d_status, 0, sizeof(int), c->streams[0]));
+    ORB_CUDA(cudaStreamSynchronize(c->streams[0]));
+    int launches = 0, k = 0;
+    cudaEvent_t prev_kernels = nullptr;
+    for (int f0 = 0; f0 < nimg; f0 += B, k++) {
+        const int n = std::min(B, nimg - f0), slot = k & 1;
+        cudaStream_t s = c->streams[slot];
+        if (k >= 2) ORB_CUDA(cudaStreamSynchronize(s));          // slot buffers free again
+        const uint8_t* d_in = imgs + (size_t)f0 * frame_pitch;
+        if (!dev_in) {
+            ORB_CUDA(cudaMemcpyAsync(c->d_src[slot], d_in, (size_t)(n - 1) * frame_pitch + (size_t)stride * (h - 1) + w,
+                                     cudaMemcpyHostToDevice, s));
+            d_in = c->d_src[slot];
+        }
+        orb_keypoint* o_k = dev_out ? kps + (size_t)f0 * cap : c->d_kps[slot];
+        uint8_t* o_d = dev_out ? desc + (size_t)f0 * cap * 32 : c->d_desc[slot];
+        int32_t* o_c = dev_out ? counts + f0 : c->d_counts[slot];
+        if (prev_kernels) ORB_CUDA(cudaStreamWaitEvent(s, prev_kernels, 0));   // work buffers are shared between slots
+        rc = orb_launch_extract(c, d_in, n, w, h, stride, frame_pitch, o_k, o_d, cap, o_c, s);
+        if (rc != ORB_OK) return rc;
+        launches += c->last_launches;
+        ORB_CUDA(cudaEventRecord(c->ev_free[slot], s));
+        prev_kernels = c->ev_free[slot];
+        if (!dev_out) {
+            ORB_CUDA(cudaMemcpyAsync(kps + (size_t)f0 * cap, o_k, (size_t)n * cap * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, s));
+            ORB_CUDA(cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, o_d, (size_t)n * cap * 32, cudaMemcpyDeviceToHost, s));
+            ORB_CUDA(cudaMemcpyAsync(counts + f0, o_c, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        }
+        c->last_nimg = n;
+    }
+    ORB_CUDA(cudaStreamSynchronize(c->streams[0]));
+    ORB_CUDA(cudaStreamSynchronize(c->streams[1]));
+    c->last_launches = launches;
+    int st = 0;
+    ORB_CUDA(cudaMemcpy(&st, c->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st != 0) return st;
+    if (!dev_out) for (int i = 0; i < nimg; i++) if (counts[i] > cap) { counts[i] = cap; return ORB_ERR_CAPACITY; }
+    return ORB_OK;
+}
+
+int orb_extract(orb_ctx* c, const uint8_t* img, int w, int h, int stride,
+                orb_keypoint* kps, uint8_t* desc, int cap, int* n)
+{
+    if (!n) return ORB_ERR_INVALID;
+    *n = 0;
+    if (!img || w <= 0 || h <= 0) return c ? ORB_OK : ORB_ERR_INVALID;
+    if (is_device_ptr(kps)) return ORB_ERR_INVALID;      // single-image call reports n on the host
+    int32_t cnt = 0;
+    int rc = orb_extract_batch(c, img, 1, w, h, stride, (size_t)stride * h, kps, desc, cap, &cnt);
+    *n = cnt;
+    return rc;
+}
+
+int orb_debug_level_info(orb_ctx* c, int frame, int level, int32_t* info)
+{
+    if (!c || !c->plan_valid || level < 0 || level >= c->plan.nlevels || frame < 0 || frame >= c->last_nimg) return ORB_ERR_INVALID;
+    const LevelGeom& L = c->plan.L[level];
+    int nk = 0;
+    ORB_CUDA(cudaSetDevice(c->device));
+    ORB_CUDA(cudaDeviceSynchronize());
+    ORB_CUDA(cudaMemcpy(&nk, c->d_nkept + frame * c->plan.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    int v[10] = { L.w, L.h, L.stride, L.nDesired, L.cols, L.rows, L.cellW, L.cellH, L.nfCell, nk };
+    memcpy(info, v, sizeof v);
+    return ORB_OK;
+}
+
+int orb_debug_level_plane(orb_ctx* c, int frame, int level, int which, uint8_t* out, size_t out_bytes)
+{
+    if (!c || !c->plan_valid || level < 0 || level >= c->plan.nlevels || frame < 0 || frame >= c->last_nimg) return ORB_ERR_INVALID;
+    const LevelGeom& L = c->plan.L[level];
+    const size_t bytes = (size_t)L.stride * L.prows;
+    if (out_bytes < bytes) return ORB_ERR_CAPACITY;
+    ORB_CUDA(cudaSetDevice(c->device));
+    ORB_CUDA(cudaDeviceSynchronize());
+    const uint8_t* src = (which ? c->d_work : c->d_planes) + (size_t)frame * c->plan.frame_bytes + L.plane_off;
+    ORB_CUDA(cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
+    return ORB_OK;
+}
+
+/* ------------------------------------------------------------------ matching */
+int orb_descriptor_distance(const uint8_t* a, const uint8_t* b)
+{
+    // ORBmatcher::DescriptorDistance is a static 32-byte helper on host rows (src/ORBmatcher.cc:1794-1810)
+    int d = 0;
+    for (int i = 0; i < 4; i++) {
+        uint64_t x, y;
+        memcpy(&x, a + 8 * i, 8); memcpy(&y, b + 8 * i, 8);
+        d += __builtin_popcountll(x ^ y);
+    }
+    return d;
+}
+
+// scratch for host-pointer matcher calls
+static int match_scratch(orb_ctx* c, size_t bytes)
+{
+    if (bytes <= c->match_scratch_bytes && c->d_match_scratch) return ORB_OK;
+    ORB_CUDA(cudaDeviceSynchronize());
+    if (c->d_match_scratch) cudaFree(c->d_match_scratch);
+    c->d_match_scratch = nullptr; c->match_scratch_bytes = 0;
+    ORB_CUDA(cudaMalloc(&c->d_match_scratch, bytes));
+    c->match_scratch_bytes = bytes;
+    return ORB_OK;
+}
+static inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+int orb_hamming_knn2_device(orb_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_db, int64_t ndb, int npairs,
+                            int32_t idx_base, int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, void* stream)
+{
+    if (!c || nq < 0 || ndb < 0 || npairs < 1 || !d_idx1 || !d_d1 || !d_d2) return ORB_ERR_INVALID;
+    if (nq == 0) return ORB_OK;
+    if (!d_q || (ndb > 0 && !d_db)) return ORB_ERR_INVALID;
+    if (((uintptr_t)d_q | (uintptr_t)d_db) & 15) return ORB_ERR_INVALID;     // bulk copies need 16-byte alignment
+    ORB_CUDA(cudaSetDevice(c->device));
+    return orb_launch_knn2(c, d_q, nq, d_db, ndb, npairs, idx_base, d_idx1, d_d1, d_d2, (cudaStream_t)stream);
+}
+
+int orb_hamming_knn2(orb_ctx* c, const uint8_t* q, int nq, const uint8_t* db, int64_t ndb,
+                     int32_t* idx1, int32_t* d1, int32_t* d2)
+{
+    if (!c || nq < 0 || ndb < 0 || !idx1 || !d1 || !d2) return ORB_ERR_INVALID;
+    if (nq == 0) return ORB_OK;
+    ORB_CUDA(cudaSetDevice(c->device));
+    const bool dq = is_device_ptr(q), ddb = is_device_ptr(db), dout = is_device_ptr(idx1);
+    cudaStream_t s = c->streams[0];
+    const size_t qb = al256((size_t)nq * 32), dbb = al256((size_t)ndb * 32), ob = al256((size_t)nq * 4);
+    int rc = match_scratch(c, (dq ? 0 : qb) + (ddb ? 0 : dbb) + (dout ? 0 : 3 * ob) + 256);
+    if (rc) return rc;
+    uint8_t* p = (uint8_t*)c->d_match_scratch;
+    const uint8_t* d_q = q; const uint8_t* d_db = db;
+    if (!dq) { ORB_CUDA(cudaMemcpyAsync(p, q, (size_t)nq * 32, cudaMemcpyHostToDevice, s)); d_q = p; p += qb; }
+    if (!ddb) { if (ndb) ORB_CUDA(cudaMemcpyAsync(p, db, (size_t)ndb * 32, cudaMemcpyHostToDevice, s)); d_db = p; p += dbb; }
+    int32_t *o0 = idx1, *o1 = d1, *o2 = d2;
+    if (!dout) { o0 = (int32_t*)p; o1 = (int32_t*)(p + ob); o2 = (int32_t*)(p + 2 * ob); }
+    rc = orb_hamming_knn2_device(c, d_q, nq, d_db, ndb, 1, 0, o0, o1, o2, s);
+    if (rc) return rc;
+    if (!dout) {
+        ORB_CUDA(cudaMemcpyAsync(idx1, o0, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+        ORB_CUDA(cudaMemcpyAsync(d1, o1, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+        ORB_CUDA(cudaMemcpyAsync(d2, o2, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    }
+    ORB_CUDA(cudaStreamSynchronize(s));
+    return ORB_OK;
+}
+
+int orb_knn2_merge_device(orb_ctx* c, const int32_t* d_parts, int nparts, int nq,
+                          int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, void* stream)
+{
+    if (!c || !d_parts || nparts < 1 || nq < 0) return ORB_ERR_INVALID;
+    if (nq == 0) return ORB_OK;
+    ORB_CUDA(cudaSetDevice(c->device));
+    return orb_launch_knn2_merge(d_parts, nparts, nq, d_idx1, d_d1, d_d2, (cudaStream_t)stream);
+}
+
+int orb_match_ratio(orb_ctx* c, const int32_t* idx1, const int32_t* d1, const int32_t* d2, int nq,
+                    float nnratio, int th, int32_t* match, int* nmatches)
+{
+    if (!c || nq < 0 || !match || !nmatches) return ORB_ERR_INVALID;
+    *nmatches = 0;
+    if (nq == 0) return ORB_OK;
+    ORB_CUDA(cudaSetDevice(c->device));
+    const bool din = is_device_ptr(idx1), dout = is_device_ptr(match);
+    cudaStream_t s = c->streams[0];
+    const size_t ob = al256((size_t)nq * 4);
+    int rc = match_scratch(c, 4 * ob + 256);
+    if (rc) return rc;
+    uint8_t* p = (uint8_t*)c->d_match_scratch;
+    int* d_cnt = (int*)p; p += 256;
+    const int32_t *i0 = idx1, *i1 = d1, *i2 = d2;
+    if (!din) {
+        ORB_CUDA(cudaMemcpyAsync(p, idx1, (size_t)nq * 4, cudaMemcpyHostToDevice, s));
+        ORB_CUDA(cudaMemcpyAsync(p + ob, d1, (size_t)nq * 4, cudaMemcpyHostToDevice, s));
+        ORB_CUDA(cudaMemcpyAsync(p + 2 * ob, d2, (size_t)nq * 4, cudaMemcpyHostToDevice, s));
+        i0 = (int32_t*)p; i1 = (int32_t*)(p + ob); i2 = (int32_t*)(p + 2 * ob);
+    }
+    int32_t* om = dout ? match : (int32_t*)(p + 3 * ob);
+    rc = orb_launch_match_ratio(i0, i1, i2, nq, nnratio, th, om, d_cnt, s);
+    if (rc) return rc;
+    if (!dout) ORB_CUDA(cudaMemcpyAsync(match, om, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaMemcpyAsync(nmatches, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaStreamSynchronize(s));
+    return ORB_OK;
+}
+
+int orb_frame_grid_build(orb_ctx* c, const orb_keypoint* kps, int n, int min_x, int max_x, int min_y, int max_y,
+                         int32_t* cell_start, int32_t* cell_items)
+{
+    if (!c || n < 0 || !cell_start || (n > 0 && (!kps || !cell_items)) || max_x <= min_x || max_y <= min_y) return ORB_ERR_INVALID;
+    ORB_CUDA(cudaSetDevice(c->device));
+    const int NC = ORB_GRID_COLS * ORB_GRID_ROWS + 1;
+    cudaStream_t s = c->streams[0];
+    if (is_device_ptr(cell_start)) {
+        int rc = orb_launch_grid_build(kps, n, min_x, max_x, min_y, max_y, cell_start, cell_items, s);
+        if (rc) return rc;
+        ORB_CUDA(cudaStreamSynchronize(s));
+        return ORB_OK;
+    }
+    const size_t kb = al256((size_t)std::max(n, 1) * sizeof(orb_keypoint)), sb = al256((size_t)NC * 4), ib = al256((size_t)std::max(n, 1) * 4);
+    int rc = match_scratch(c, kb + sb + ib);
+    if (rc) return rc;
+    uint8_t* p = (uint8_t*)c->d_match_scratch;
+    if (n) ORB_CUDA(cudaMemcpyAsync(p, kps, (size_t)n * sizeof(orb_keypoint), cudaMemcpyHostToDevice, s));
+    rc = orb_launch_grid_build((orb_keypoint*)p, n, min_x, max_x, min_y, max_y, (int32_t*)(p + kb), (int32_t*)(p + kb + sb), s);
+    if (rc) return rc;
+    ORB_CUDA(cudaMemcpyAsync(cell_start, p + kb, (size_t)NC * 4, cudaMemcpyDeviceToHost, s));
+    if (n) ORB_CUDA(cudaMemcpyAsync(cell_items, p + kb + sb, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaStreamSynchronize(s));
+    return ORB_OK;
+}
+
+int orb_search_by_projection(orb_ctx* c, const orb_frame_view* cur, const orb_frame_view* last,
+                             const uint8_t* last_has_mp, const uint8_t* last_outlier, const float* last_xyz,
+                             const float* Tcw16, float th, int check_ori, int32_t* match_cur, int* nmatches)
+{
+    (void)c; (void)cur; (void)last; (void)last_has_mp; (void)last_outlier; (void)last_xyz; (void)Tcw16; (void)th;
+    (void)check_ori; (void)match_cur; (void)nmatches;
+    return ORB_ERR_UNSUPPORTED;
+}
+
+int orb_search_by_bow(orb_ctx* c, const orb_featvec_view* kf_fv, const uint8_t* kf_desc, const orb_keypoint* kf_kps,
+                      const uint8_t* kf_mp_valid, int n_kf,
+                      const orb_featvec_view* f_fv, const uint8_t* f_desc, const orb_keypoint* f_kps, int n_f,
+                      float nnratio, int check_ori, int32_t* match_f, int* nmatches)
+{
+    (void)c; (void)kf_fv; (void)kf_desc; (void)kf_kps; (void)kf_mp_valid; (void)n_kf; (void)f_fv; (void)f_desc;
+    (void)f_kps; (void)n_f; (void)nnratio; (void)check_ori; (void)match_f; (void)nmatches;
+    return ORB_ERR_UNSUPPORTED;
+}
+
+int orb_measure_popc_peak(orb_ctx* c, double* gpopc_per_s)
+{
+    if (!c || !gpopc_per_s) return ORB_ERR_INVALID;
+    ORB_CUDA(cudaSetDevice(c->device));
+    return orb_launch_popc_bench(gpopc_per_s, c->streams[0]);
+}
+
+void* orb_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { orb_cuda_fail(cudaGetLastError(), "cudaMallocHost"); return nullptr; }
+    return p;
+}
+void orb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+} // extern "C"

@@ -1,0 +1,130 @@
+// orb_internal.h — shared host/device structures of liborb_b200 (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/orb_b200.h"
+
+#define ORB_MAX_LEVELS 16
+#define ORB_MAX_GRID 96            // max grid cols / rows per level
+#define ORB_MAX_CELLS_LEVEL 256    // one select-CTA thread per cell
+#define ORB_EDGE 16                // EDGE_THRESHOLD, reference src/ORBextractor.cc:77
+#define ORB_TILE_W 64
+#define ORB_TILE_H 32
+
+// Geometry of one pyramid level for one image shape (reference src/ORBextractor.cc:527-547,:786).
+struct LevelGeom {
+    int w, h;              // level ROI size
+    int stride;            // padded row pitch in bytes (w+32 rounded up to 16)
+    int prows;             // h + 32
+    int plane_off;         // byte offset of the padded plane inside a frame block
+    int nDesired, cols, rows, cellW, cellH, nfCell;
+    int xend, yend;        // FAST detection region is [16,xend) x [16,yend) in ROI coordinates
+    int cell_base;         // first cell of this level in the frame-wide cell arrays
+    int ncells;
+    int lvl_base, lvl_cap; // per-level keypoint list (u64 records) inside the frame's list block
+    int patch_size;        // (int)(31*scale)
+    float scale;           // mvScaleFactor[level]
+    int xtab_off, ytab_off;// offsets into the resize coefficient tables (int2 entries)
+    int kp_base;           // prefix of nDesired over levels (unused slots stay empty)
+};
+
+struct Plan {
+    int nlevels, w, h;
+    int frame_bytes;       // bytes of one frame's padded pyramid (multiple of 256)
+    int ncells;            // cells per frame, all levels
+    int cand_total;        // candidate slots per frame (u32 records)
+    int lvl_total;         // level-list slots per frame (u64 records)
+    int kp_cap;            // sum of nDesired
+    int fast_th, th_lo;
+    int ntiles_fast, ntiles_blur;
+    LevelGeom L[ORB_MAX_LEVELS];
+};
+
+// One FAST detection cell (reference src/ORBextractor.cc:560-599): detection rectangle in ROI
+// coordinates, the cell image origin (iniX, iniY) and where its candidates live.
+struct CellGeom {
+    int x0, x1, y0, y1;    // detection rect [x0,x1) x [y0,y1)
+    int inix, iniy;        // cell image origin (x0-3, y0-3 for every processed cell)
+    int cand_off, cand_cap;
+    int level, idx;        // idx = i*cols + j
+    int skipped, pad;      // skipped: the reference `continue`s before FAST (:570,:594); its quota state stays open
+};
+
+struct Tile { int level, x0, y0, pad; };
+
+struct orb_ctx {
+    int device = 0;
+    int nfeatures = 0, nlevels = 0, score_type = 1, fast_th = 20;
+    float scale_factor_f = 1.2f;
+    double scaleFactor = 1.2;
+    int max_w = 0, max_h = 0, max_batch = 0;
+    std::vector<float> mvScaleFactor, mvInvScaleFactor;
+    std::vector<int> mnFeaturesPerLevel;
+    int umax[16];
+
+    // current plan (rebuilt when the image shape changes)
+    Plan plan{};
+    bool plan_valid = false;
+    std::vector<CellGeom> cells;
+    std::vector<Tile> tiles_fast, tiles_blur;
+    std::vector<int2> xtab, ytab;
+
+    // device buffers
+    Plan* d_plan = nullptr;
+    CellGeom* d_cells = nullptr;
+    Tile* d_tiles_fast = nullptr; Tile* d_tiles_blur = nullptr;
+    int2* d_xtab = nullptr; int2* d_ytab = nullptr;
+    size_t cap_cells = 0, cap_tiles_fast = 0, cap_tiles_blur = 0, cap_xtab = 0, cap_ytab = 0;
+    uint8_t* d_planes = nullptr;  size_t planes_bytes = 0;
+    uint8_t* d_work = nullptr;    size_t work_bytes = 0;     // NMS score map, then blurred planes
+    uint32_t* d_cand = nullptr;   size_t cand_bytes = 0;
+    int* d_ntotal = nullptr;      size_t ntotal_bytes = 0;
+    unsigned long long* d_lvl = nullptr; size_t lvl_bytes = 0;
+    int* d_nkept = nullptr;
+    int* d_status = nullptr;
+    // staging for host-pointer calls (two slots for copy/compute overlap)
+    uint8_t* d_src[2] = { nullptr, nullptr };  size_t src_bytes[2] = { 0, 0 };
+    size_t kps_bytes[2] = { 0, 0 }, desc_bytes[2] = { 0, 0 }, counts_bytes[2] = { 0, 0 };
+    orb_keypoint* d_kps[2] = { nullptr, nullptr };
+    uint8_t* d_desc[2] = { nullptr, nullptr };
+    int32_t* d_counts[2] = { nullptr, nullptr };
+    cudaStream_t streams[2] = { nullptr, nullptr };
+    cudaEvent_t ev_free[2] = { nullptr, nullptr };
+    int last_launches = 0;
+    int last_nimg = 0;
+    // matcher scratch
+    int32_t* d_knn_part = nullptr; size_t knn_part_bytes = 0;
+    void* d_match_scratch = nullptr; size_t match_scratch_bytes = 0;
+};
+
+// status helpers
+extern thread_local std::string g_last_cuda_error;
+int orb_cuda_fail(cudaError_t e, const char* what);
+#define ORB_CUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return orb_cuda_fail(e__, #x); } while (0)
+
+// orb_plan.cu
+int orb_build_tables(orb_ctx* c);
+int orb_build_plan(orb_ctx* c, int w, int h);
+// orb_extract.cu
+int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w, int h, int stride, size_t frame_pitch,
+                       orb_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts, cudaStream_t s);
+int orb_upload_constants(const int* umax);
+int orb_select_smem_setup(int max_bytes);
+// orb_match.cu
+int orb_launch_knn2(orb_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_db, int64_t ndb, int npairs, int32_t idx_base,
+                    int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, cudaStream_t s);
+int orb_launch_knn2_merge(const int32_t* d_parts, int nparts, int nq, int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, cudaStream_t s);
+int orb_launch_match_ratio(const int32_t* idx1, const int32_t* d1, const int32_t* d2, int nq, float nnratio, int th,
+                           int32_t* match, int* d_count, cudaStream_t s);
+int orb_launch_grid_build(const orb_keypoint* kps, int n, int min_x, int max_x, int min_y, int max_y,
+                          int32_t* cell_start, int32_t* cell_items, cudaStream_t s);
+int orb_launch_search_by_projection(orb_ctx* c, const orb_frame_view* cur, const orb_frame_view* last,
+                                    const uint8_t* last_has_mp, const uint8_t* last_outlier, const float* last_xyz,
+                                    const float* T16_host, float th, int check_ori, int32_t* match_cur, int* d_nmatches, cudaStream_t s);
+int orb_launch_search_by_bow(orb_ctx* c, const orb_featvec_view* kf_fv, const uint8_t* kf_desc, const orb_keypoint* kf_kps,
+                             const uint8_t* kf_mp_valid, const orb_featvec_view* f_fv, const uint8_t* f_desc,
+                             const orb_keypoint* f_kps, int n_f, float nnratio, int check_ori, int32_t* match_f,
+                             int* d_nmatches, cudaStream_t s);
+int orb_launch_popc_bench(double* gpopc, cudaStream_t s);

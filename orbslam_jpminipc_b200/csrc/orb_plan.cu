@@ -1,0 +1,168 @@
+// orb_plan.cu — host-side geometry: scale tables, per-level quotas, cell grid, resize
+// coefficient tables and tile lists for one image shape.  Mirrors what the reference computes
+// in ORBextractor::ORBextractor (src/ORBextractor.cc:457-511), ComputePyramid (:781-822) and
+// the head of ComputeKeyPoints (:527-599); cv::resize's INTER_LINEAR 8-bit coefficient recipe
+// is restated from OpenCV 4.x ("K1").
+#include "orb_internal.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+static inline int cvRoundF(float v) { return (int)lrintf(v); }
+static inline int cvFloorD(double v) { int i = (int)v; return i - (i > v); }
+static inline int cvCeilD(double v) { int i = (int)v; return i + (i < v); }
+
+int orb_build_tables(orb_ctx* c)
+{
+    const int nlevels = c->nlevels;
+    if (nlevels < 1 || nlevels > ORB_MAX_LEVELS || c->nfeatures < 1) return ORB_ERR_INVALID;
+    c->scaleFactor = (double)c->scale_factor_f;                    // member is a double holding the float
+    c->mvScaleFactor.assign(nlevels, 1.f);
+    c->mvInvScaleFactor.assign(nlevels, 1.f);
+    for (int i = 1; i < nlevels; i++) c->mvScaleFactor[i] = (float)(c->mvScaleFactor[i - 1] * c->scaleFactor);
+    const float invScale = (float)(1.0f / c->scaleFactor);
+    for (int i = 1; i < nlevels; i++) c->mvInvScaleFactor[i] = c->mvInvScaleFactor[i - 1] * invScale;
+
+    c->mnFeaturesPerLevel.assign(nlevels, 0);
+    const float factor = (float)(1.0 / c->scaleFactor);
+    float nDesired = c->nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; l++) {
+        c->mnFeaturesPerLevel[l] = cvRoundF(nDesired);
+        sum += c->mnFeaturesPerLevel[l];
+        nDesired *= factor;
+    }
+    c->mnFeaturesPerLevel[nlevels - 1] = std::max(c->nfeatures - sum, 0);
+
+    // circular patch row extents for the intensity centroid (:495-510)
+    int umax[17] = { 0 };
+    const int HP = 15;
+    int v, v0, vmax = cvFloorD(HP * sqrtf(2.f) / 2 + 1), vmin = cvCeilD(HP * sqrtf(2.f) / 2);
+    for (v = 0; v <= vmax; ++v) umax[v] = (int)lrint(sqrt((double)HP * HP - v * v));
+    for (v = HP, v0 = 0; v >= vmin; --v) {
+        while (umax[v0] == umax[v0 + 1]) ++v0;
+        umax[v] = v0;
+        ++v0;
+    }
+    memcpy(c->umax, umax, sizeof(int) * 16);
+    return ORB_OK;
+}
+
+// INTER_LINEAR 8U coefficients for one axis: entry = { s0 | s1<<16 , c0 | c1<<16 } (c as int16)
+static void axis_table(int ssize, int dsize, bool clamp_frac, std::vector<int2>& out)
+{
+    const double inv_scale = (double)dsize / ssize;
+    const double scale = 1. / inv_scale;
+    for (int d = 0; d < dsize; d++) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = cvFloorD(f);
+        f -= s;
+        int s0, s1;
+        if (clamp_frac) {                       // x axis: the fraction is zeroed at the borders
+            if (s < 0) { f = 0; s = 0; }
+            if (s >= ssize - 1) { f = 0; s = ssize - 1; }
+            s0 = s; s1 = std::min(s + 1, ssize - 1);
+        } else {                                // y axis: row indices are clipped, weights kept
+            s0 = std::min(std::max(s, 0), ssize - 1);
+            s1 = std::min(std::max(s + 1, 0), ssize - 1);
+        }
+        short c0 = (short)cvRoundF((1.f - f) * 2048), c1 = (short)cvRoundF(f * 2048);
+        int2 e;
+        e.x = (s0 & 0xffff) | (s1 << 16);
+        e.y = ((int)(unsigned short)c0) | ((int)(unsigned short)c1 << 16);
+        out.push_back(e);
+    }
+}
+
+int orb_build_plan(orb_ctx* c, int w, int h)
+{
+    if (c->plan_valid && c->plan.w == w && c->plan.h == h) return ORB_OK;
+    c->plan_valid = false;
+    if (w < 1 || h < 1 || w > 32767 || h > 32767) return ORB_ERR_INVALID;
+    if (w > c->max_w || h > c->max_h) return ORB_ERR_CAPACITY;
+    Plan& P = c->plan;
+    memset(&P, 0, sizeof(P));
+    P.nlevels = c->nlevels; P.w = w; P.h = h;
+    P.fast_th = c->fast_th; P.th_lo = std::min(c->fast_th, 7);
+    c->cells.clear(); c->tiles_fast.clear(); c->tiles_blur.clear(); c->xtab.clear(); c->ytab.clear();
+
+    int off = 0, cand = 0, lvl = 0, kp = 0;
+    const float imageRatio = (float)w / h;                                   // :527
+    for (int l = 0; l < P.nlevels; l++) {
+        LevelGeom& L = P.L[l];
+        const float scale = c->mvInvScaleFactor[l];
+        L.w = cvRoundF((float)w * scale); L.h = cvRoundF((float)h * scale);   // :786
+        if (L.w < 1 || L.h < 1) return ORB_ERR_GEOMETRY;
+        L.stride = (L.w + 2 * ORB_EDGE + 15) & ~15;
+        L.prows = L.h + 2 * ORB_EDGE;
+        L.plane_off = off;
+        off += (L.stride * L.prows + 255) & ~255;
+        L.scale = c->mvScaleFactor[l];
+        L.patch_size = (int)(31 * c->mvScaleFactor[l]);                       // :675
+        L.xtab_off = (int)c->xtab.size(); L.ytab_off = (int)c->ytab.size();
+        if (l > 0) {
+            axis_table(P.L[l - 1].w, L.w, true, c->xtab);
+            axis_table(P.L[l - 1].h, L.h, false, c->ytab);
+        }
+        // cell grid (:531-547)
+        L.nDesired = c->mnFeaturesPerLevel[l];
+        L.cols = (int)sqrtf((float)L.nDesired / (5 * imageRatio));
+        L.rows = (int)(imageRatio * L.cols);
+        if (L.cols < 1 || L.rows < 1) return ORB_ERR_GEOMETRY;               // reference divides by zero
+        if (L.cols > ORB_MAX_GRID || L.rows > ORB_MAX_GRID || L.cols * L.rows > ORB_MAX_CELLS_LEVEL) return ORB_ERR_CAPACITY;
+        const int minB = ORB_EDGE, maxBX = L.w - ORB_EDGE, maxBY = L.h - ORB_EDGE;
+        const int W = maxBX - minB, H = maxBY - minB;
+        L.cellW = (int)ceilf((float)W / L.cols);
+        L.cellH = (int)ceilf((float)H / L.rows);
+        L.ncells = L.cols * L.rows;
+        L.nfCell = (int)ceilf((float)L.nDesired / L.ncells);
+        L.cell_base = (int)c->cells.size();
+        L.xend = minB; L.yend = minB;
+        for (int i = 0; i < L.rows; i++) {
+            const int iniY = minB + i * L.cellH - 3;
+            int hY = L.cellH + 6;
+            if (i == L.rows - 1) hY = maxBY + 3 - iniY;
+            for (int j = 0; j < L.cols; j++) {
+                const int iniX = minB + j * L.cellW - 3;
+                int hX = L.cellW + 6;
+                if (j == L.cols - 1) hX = maxBX + 3 - iniX;
+                CellGeom g;
+                g.level = l; g.idx = i * L.cols + j;
+                g.inix = iniX; g.iniy = iniY; g.pad = 0;
+                g.skipped = (hX <= 0 || hY <= 0) ? 1 : 0;
+                if (hX <= 0 || hY <= 0) {                  // skipped cell (:570,:594): never produces keypoints
+                    g.x0 = g.x1 = g.y0 = g.y1 = 0;
+                } else {
+                    // Mat::rowRange/colRange on the level ROI throws when the cell leaves it
+                    if (iniX < 0 || iniY < 0 || iniX + hX > L.w || iniY + hY > L.h) return ORB_ERR_GEOMETRY;
+                    g.x0 = iniX + 3; g.x1 = iniX + hX - 3; g.y0 = iniY + 3; g.y1 = iniY + hY - 3;
+                    if (g.x1 < g.x0) g.x1 = g.x0;          // cell image narrower than 7 px: FAST finds nothing
+                    if (g.y1 < g.y0) g.y1 = g.y0;
+                    if (g.x1 - g.x0 + 6 > 4095 || g.y1 - g.y0 + 6 > 4095) return ORB_ERR_CAPACITY;  // 12-bit cell-local coords
+                }
+                g.cand_off = cand;
+                g.cand_cap = ((g.x1 - g.x0 + 1) / 2) * ((g.y1 - g.y0 + 1) / 2);   // strict 8-neighbour NMS bound
+                cand += g.cand_cap;
+                if (g.x1 > g.x0 && g.y1 > g.y0) { L.xend = std::max(L.xend, g.x1); L.yend = std::max(L.yend, g.y1); }
+                c->cells.push_back(g);
+            }
+        }
+        L.lvl_base = lvl;
+        L.lvl_cap = L.nDesired + L.ncells + (L.ncells * L.ncells) / 2 + 64;
+        lvl += L.lvl_cap;
+        L.kp_base = kp;
+        kp += L.nDesired;
+        for (int y = minB; y < L.yend; y += ORB_TILE_H)
+            for (int x = minB; x < L.xend; x += ORB_TILE_W) c->tiles_fast.push_back(Tile{ l, x, y, 0 });
+        for (int y = 0; y < L.h; y += ORB_TILE_H)
+            for (int x = 0; x < L.w; x += ORB_TILE_W) c->tiles_blur.push_back(Tile{ l, x, y, 0 });
+    }
+    P.frame_bytes = off;
+    P.ncells = (int)c->cells.size();
+    P.cand_total = cand;
+    P.lvl_total = lvl;
+    P.kp_cap = kp;
+    P.ntiles_fast = (int)c->tiles_fast.size();
+    P.ntiles_blur = (int)c->tiles_blur.size();
+    return ORB_OK;   // device upload happens in orb_api.cu
+}

@@ -1,0 +1,89 @@
+"""ORBextractor — python mirror of ORB_SLAM::ORBextractor (reference include/ORBextractor.h:32-77)
+on top of the C ABI.  Same constructor arguments, same call: extractor(image, mask) -> (keypoints,
+descriptors); keypoints is a numpy record array bit-compatible with cv::KeyPoint, descriptors is
+N x 32 uint8.  All compute happens in liborb_b200.so on the GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import KP_DTYPE, check, lib, ptr
+
+
+class ORBextractor:
+    HARRIS_SCORE, FAST_SCORE = 0, 1
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, scoreType=1, fastTh=20,
+                 device=0, max_width=1920, max_height=1200, max_batch=64):
+        self.nfeatures, self.nlevels, self.device = nfeatures, nlevels, device
+        self.max_batch = max_batch
+        self._h = lib().orb_create(device, nfeatures, scaleFactor, nlevels, scoreType, fastTh,
+                                   max_width, max_height, max_batch)
+        if not self._h:
+            raise RuntimeError("orb_create failed: " + lib().orb_last_cuda_error().decode())
+        self.capacity = lib().orb_keypoint_capacity(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orb_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def GetLevels(self):
+        return lib().orb_nlevels(self._h)
+
+    def GetScaleFactor(self):
+        return lib().orb_scale_factor(self._h)
+
+    # ORBextractor::operator()(image, mask, keypoints, descriptors)
+    def __call__(self, image, mask=None):
+        image = np.asarray(image)
+        if image.size == 0:
+            return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        assert image.dtype == np.uint8 and image.ndim == 2 and image.strides[1] == 1, "CV_8UC1 expected"
+        h, w = image.shape
+        cap = self.capacity
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        check(lib().orb_extract(self._h, ptr(image), w, h, image.strides[0], ptr(kps), ptr(desc), cap, C.byref(n)),
+              "orb_extract")
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, images):
+        """images: (n, h, w) uint8 host array -> list of (keypoints, descriptors)."""
+        images = np.ascontiguousarray(images, np.uint8)
+        n, h, w = images.shape
+        cap = self.capacity
+        kps = np.zeros((n, cap), KP_DTYPE)
+        desc = np.zeros((n, cap, 32), np.uint8)
+        counts = np.zeros(n, np.int32)
+        check(lib().orb_extract_batch(self._h, ptr(images), n, w, h, w, h * w, ptr(kps), ptr(desc), cap, ptr(counts)),
+              "orb_extract_batch")
+        return [(kps[i, :counts[i]].copy(), desc[i, :counts[i]].copy()) for i in range(n)]
+
+    def extract_batch_device(self, d_images, d_kps, d_desc, d_counts, stream=0):
+        """Device-resident batch (torch CUDA tensors or raw device pointers); asynchronous on `stream`.
+        d_images: (n, h, w) uint8; d_kps: (n, cap, 7) int32/float32 view of orb_keypoint; d_desc: (n, cap, 32) uint8."""
+        n, h, w = d_images.shape
+        cap = d_desc.shape[1]
+        check(lib().orb_extract_batch_device(self._h, ptr(d_images), n, w, h, w, h * w, ptr(d_kps), ptr(d_desc), cap,
+                                             ptr(d_counts), C.c_void_p(stream)), "orb_extract_batch_device")
+
+    def last_launch_count(self):
+        return lib().orb_last_launch_count(self._h)
+
+    # inspection hooks used by the parity tests
+    def level_info(self, level, frame=0):
+        info = np.zeros(10, np.int32)
+        check(lib().orb_debug_level_info(self._h, frame, level, ptr(info)), "orb_debug_level_info")
+        return dict(zip(["w", "h", "stride", "nDesired", "cols", "rows", "cellW", "cellH", "nfCell", "nKept"],
+                        [int(v) for v in info]))
+
+    def level_plane(self, level, blurred=False, frame=0):
+        i = self.level_info(level, frame)
+        buf = np.zeros((i["h"] + 32, i["stride"]), np.uint8)
+        check(lib().orb_debug_level_plane(self._h, frame, level, int(blurred), ptr(buf), buf.nbytes), "orb_debug_level_plane")
+        return buf[:, :i["w"] + 32].copy()

@@ -1,0 +1,107 @@
+"""ORBmatcher / Frame — python mirrors of ORB_SLAM::ORBmatcher (reference include/ORBmatcher.h:37-107)
+and of the slice of ORB_SLAM::Frame the matcher reads (include/Frame.h, src/Frame.cc:56-128), on top
+of the C ABI.  All compute happens in liborb_b200.so on the GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import (GRID_COLS, GRID_ROWS, KP_DTYPE, FeatVecView, FrameView, check, lib, ptr)
+from .extractor import ORBextractor
+
+
+class Frame:
+    """Keypoints + descriptors + the 64x48 lookup grid (src/Frame.cc:109-123), zero distortion
+    (mvKeysUn == mvKeys, image bounds = image rectangle, src/Frame.cc:291-295,:342-348)."""
+
+    def __init__(self, ctx, kps, desc, width, height, fx, fy, cx, cy, nlevels=8, scale_factor=1.2):
+        self.kps = np.ascontiguousarray(kps, KP_DTYPE)
+        self.desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        self.N = len(self.kps)
+        self.width, self.height = width, height
+        self.fx, self.fy, self.cx, self.cy = fx, fy, cx, cy
+        self.nlevels, self.scale_factor = nlevels, scale_factor
+        self.cell_start = np.zeros(GRID_COLS * GRID_ROWS + 1, np.int32)
+        self.cell_items = np.zeros(max(self.N, 1), np.int32)
+        h = ctx._h if hasattr(ctx, "_h") else ctx
+        check(lib().orb_frame_grid_build(h, ptr(self.kps), self.N, 0, width, 0, height,
+                                         ptr(self.cell_start), ptr(self.cell_items)), "orb_frame_grid_build")
+
+    def view(self):
+        return FrameView(self.N, self.kps.ctypes.data, self.desc.ctypes.data, self.fx, self.fy, self.cx, self.cy,
+                         0, self.width, 0, self.height, self.nlevels, self.scale_factor,
+                         self.cell_start.ctypes.data, self.cell_items.ctypes.data)
+
+
+class ORBmatcher:
+    TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30       # src/ORBmatcher.cc:40-42
+
+    def __init__(self, nnratio=0.6, checkOri=True, extractor=None, device=0):
+        self.mfNNratio, self.mbCheckOrientation = float(nnratio), bool(checkOri)
+        self._own = None
+        if extractor is None:                             # the matcher only needs a context (streams, scratch)
+            extractor = self._own = ORBextractor(device=device, max_width=64, max_height=64, max_batch=1)
+        self._ex = extractor
+        self._h = extractor._h
+
+    @staticmethod
+    def DescriptorDistance(a, b):
+        a = np.ascontiguousarray(a, np.uint8).reshape(32)
+        b = np.ascontiguousarray(b, np.uint8).reshape(32)
+        return lib().orb_descriptor_distance(ptr(a), ptr(b))
+
+    def knn2(self, q, db):
+        """best / second-best over all db rows (scan semantics of src/ORBmatcher.cc:197-222)."""
+        q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+        db = np.ascontiguousarray(db, np.uint8).reshape(-1, 32)
+        nq = len(q)
+        idx1, d1, d2 = (np.zeros(nq, np.int32) for _ in range(3))
+        check(lib().orb_hamming_knn2(self._h, ptr(q), nq, ptr(db), len(db), ptr(idx1), ptr(d1), ptr(d2)), "orb_hamming_knn2")
+        return idx1, d1, d2
+
+    def match_ratio(self, idx1, d1, d2, th=None):
+        th = self.TH_LOW if th is None else th
+        m = np.zeros(len(idx1), np.int32)
+        n = C.c_int(0)
+        a, b, c = (np.ascontiguousarray(v, np.int32) for v in (idx1, d1, d2))
+        check(lib().orb_match_ratio(self._h, ptr(a), ptr(b), ptr(c), len(a), self.mfNNratio, th, ptr(m), C.byref(n)),
+              "orb_match_ratio")
+        return m, n.value
+
+    def SearchByProjection(self, CurrentFrame, LastFrame, th, last_has_mp, last_outlier, last_xyz, Tcw, match_cur=None):
+        """ORBmatcher::SearchByProjection(Frame&, const Frame&, float) (src/ORBmatcher.cc:1507-1620).
+        Returns (nmatches, match_cur) with match_cur[i2] = last-frame feature index or -1."""
+        if match_cur is None:
+            match_cur = np.full(CurrentFrame.N, -1, np.int32)
+        has = np.ascontiguousarray(last_has_mp, np.uint8)
+        out = np.ascontiguousarray(last_outlier, np.uint8)
+        xyz = np.ascontiguousarray(last_xyz, np.float32)
+        T = np.ascontiguousarray(Tcw, np.float32).reshape(16)
+        cur, last = CurrentFrame.view(), LastFrame.view()
+        n = C.c_int(0)
+        check(lib().orb_search_by_projection(self._h, C.byref(cur), C.byref(last), ptr(has), ptr(out), ptr(xyz), ptr(T),
+                                             th, int(self.mbCheckOrientation), ptr(match_cur), C.byref(n)),
+              "orb_search_by_projection")
+        return n.value, match_cur
+
+    def SearchByBoW(self, kf_featvec, kf_desc, kf_kps, kf_mp_valid, f_featvec, f_desc, f_kps):
+        """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) scoring (src/ORBmatcher.cc:155-284).
+        featvec = (node_id, start, items) CSR arrays.  Returns (nmatches, match_f)."""
+        keep = []
+
+        def fv(t):
+            arrs = [np.ascontiguousarray(a, np.int32) for a in t]
+            keep.append(arrs)
+            return FeatVecView(len(arrs[0]), arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data)
+        a, b = fv(kf_featvec), fv(f_featvec)
+        kf_desc = np.ascontiguousarray(kf_desc, np.uint8)
+        f_desc = np.ascontiguousarray(f_desc, np.uint8)
+        kf_kps = np.ascontiguousarray(kf_kps, KP_DTYPE)
+        f_kps = np.ascontiguousarray(f_kps, KP_DTYPE)
+        valid = np.ascontiguousarray(kf_mp_valid, np.uint8)
+        m = np.full(len(f_kps), -1, np.int32)
+        n = C.c_int(0)
+        check(lib().orb_search_by_bow(self._h, C.byref(a), ptr(kf_desc), ptr(kf_kps), ptr(valid), len(kf_kps),
+                                      C.byref(b), ptr(f_desc), ptr(f_kps), len(f_kps), self.mfNNratio,
+                                      int(self.mbCheckOrientation), ptr(m), C.byref(n)), "orb_search_by_bow")
+        return n.value, m

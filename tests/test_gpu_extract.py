@@ -1,0 +1,118 @@
+"""GPU parity tests (run on the B200 box): the CUDA extractor through the C ABI against the CPU
+oracle and against the golden fixtures generated from real OpenCV.  Integer outputs bit-exact;
+angles must agree within 1e-4 rad (north_star) — we additionally expect bit equality."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ANGLE_TOL_RAD = 1e-4
+
+
+def _bits(a):
+    return np.asarray(a, np.float32).view(np.uint32)
+
+
+def _same(kps, desc, rk, rd, what=""):
+    assert len(kps) == len(rk), (what, len(kps), len(rk))
+    for f in ("x", "y", "size", "response"):
+        assert np.array_equal(_bits(kps[f]), _bits(rk[f])), (what, f)
+    assert np.array_equal(kps["octave"], rk["octave"]) and np.all(kps["class_id"] == -1), what
+    if len(kps):
+        dang = np.abs(kps["angle"].astype(np.float64) - rk["angle"].astype(np.float64))
+        dang = np.minimum(dang, 360 - dang) * np.pi / 180
+        assert dang.max() < ANGLE_TOL_RAD, (what, dang.max())
+        assert np.array_equal(_bits(kps["angle"]), _bits(rk["angle"])), (what, "angle bits")
+    assert np.array_equal(desc, rd), what
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import orbslam_jpminipc_b200 as p
+    return p
+
+
+@pytest.fixture(scope="module")
+def po():
+    from oracle import pyoracle
+    return pyoracle
+
+
+@pytest.mark.parametrize("name", ["e2e_320x240_n300", "e2e_640x480_n1000", "e2e_620x188_n700"])
+def test_golden_frames(pkg, name):
+    d = np.load(os.path.join(G, name + ".npz"))
+    img = d["img"]
+    ex = pkg.ORBextractor(int(d["nfeatures"]), 1.2, 8, 1, 20, max_width=img.shape[1], max_height=img.shape[0], max_batch=2)
+    kps, desc = ex(img)
+    _same(kps, desc, d["kps"], d["desc"], name)
+    for l in (1, 4):
+        info = ex.level_info(l)
+        assert np.array_equal(ex.level_plane(l, False), d["L%d_plane" % l])
+        got = ex.level_plane(l, True)[16:16 + info["h"], 16:16 + info["w"]]
+        assert np.array_equal(got, d["L%d_blur" % l][16:-16, 16:-16])
+    ex.close()
+
+
+@pytest.mark.parametrize("shape,nf", [((480, 640), 1000), ((480, 752), 1000), ((376, 1241), 2000), ((480, 640), 2000),
+                                      ((300, 301), 500), ((97, 203), 150)])
+def test_vs_oracle_shapes(pkg, po, shape, nf):
+    from orbslam_jpminipc_b200.synth import synth_frame
+    h, w = shape
+    ex = pkg.ORBextractor(nf, 1.2, 8, 1, 20, max_width=w, max_height=h, max_batch=4)
+    orc = po.OracleExtractor(nf, 1.2, 8, 1, 20)
+    for seed in (1000, 1001, 1002):
+        img = synth_frame(h, w, seed, quadrants=(seed != 1001))
+        kps, desc = ex(img)
+        rk, rd = orc(img)
+        _same(kps, desc, rk, rd, (shape, nf, seed))
+        for l in range(8):
+            assert ex.level_info(l)["nKept"] == orc.level_info(l)["nKept"]
+            assert np.array_equal(ex.level_plane(l), orc.level_plane(l)), (shape, l)
+    ex.close()
+
+
+def test_batch_equals_single_and_chunks(pkg, po):
+    from orbslam_jpminipc_b200.synth import synth_frames
+    frames = synth_frames(7, 240, 320, seed0=4000)
+    ex = pkg.ORBextractor(400, 1.2, 8, 1, 20, max_width=320, max_height=240, max_batch=3)   # 3 chunks: 3+3+1
+    orc = po.OracleExtractor(400, 1.2, 8, 1, 20)
+    res = ex.extract_batch(frames)
+    for i, (kps, desc) in enumerate(res):
+        rk, rd = orc(frames[i])
+        _same(kps, desc, rk, rd, ("batch", i))
+    ex.close()
+
+
+def test_other_parameters(pkg, po):
+    from orbslam_jpminipc_b200.synth import synth_frame
+    img = synth_frame(360, 480, 5000)
+    for nf, sf, nl, th in [(800, 1.2, 8, 12), (600, 1.5, 5, 20), (500, 1.1, 6, 5), (1200, 1.2, 4, 30)]:
+        ex = pkg.ORBextractor(nf, sf, nl, 1, th, max_width=480, max_height=360, max_batch=1)
+        kps, desc = ex(img)
+        rk, rd = po.OracleExtractor(nf, sf, nl, 1, th)(img)
+        _same(kps, desc, rk, rd, (nf, sf, nl, th))
+        ex.close()
+
+
+def test_strided_input_and_edge_cases(pkg, po):
+    from orbslam_jpminipc_b200.synth import synth_frame
+    big = synth_frame(300, 500, 6000)
+    view = big[10:250, 20:340]                       # non-contiguous rows (stride 500)
+    ex = pkg.ORBextractor(300, 1.2, 8, 1, 20, max_width=320, max_height=240, max_batch=1)
+    kps, desc = ex(view)
+    rk, rd = po.OracleExtractor(300, 1.2, 8, 1, 20)(np.ascontiguousarray(view))
+    _same(kps, desc, rk, rd, "strided")
+    k, d = ex(np.zeros((0, 0), np.uint8))            # empty image: silent, no keypoints
+    assert len(k) == 0 and d.shape == (0, 32)
+    k, d = ex(np.full((240, 320), 9, np.uint8))      # flat image: no corners
+    assert len(k) == 0
+    with pytest.raises(pkg.OrbError):                # larger than the context was sized for
+        ex(np.zeros((241, 320), np.uint8))
+    ex.close()
+    tiny = pkg.ORBextractor(10, 1.2, 8, 1, 20, max_width=100, max_height=100, max_batch=1)
+    with pytest.raises(pkg.OrbError):                # grid with zero columns: the reference divides by zero
+        tiny(np.zeros((100, 100), np.uint8))
+    tiny.close()
