@@ -82,6 +82,13 @@ int orb_extract_batch_device(orb_ctx*, const uint8_t* d_imgs, int nimg, int w, i
                              orb_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts, void* stream);
 /* kernels launched by the last orb_extract* call on this context (for bench accounting) */
 int orb_last_launch_count(const orb_ctx*);
+/* per-stage device timing of the extraction pipeline (CUDA events recorded on the launching stream
+ * between the stages).  orb_profile_read synchronises, returns the milliseconds summed per stage over
+ * the extract launches since the last read (ms[ORB_NSTAGES]) and how many launches that was. */
+enum { ORB_NSTAGES = 7 };   /* level0, resize, fast_nms, cell_compact, select, blur, describe */
+int orb_profile_enable(orb_ctx*, int on);
+int orb_profile_read(orb_ctx*, double* ms, int* ncalls);
+const char* orb_profile_stage_name(int stage);
 
 /* test / inspection hooks (valid after an extract call; frame < nimg of that call's last chunk):
  * info[0..9] = w,h,stride,nDesired,gridCols,gridRows,cellW,cellH,nfeaturesCell,nKept */

@@ -125,6 +125,8 @@ void orb_destroy(orb_ctx* c)
                      c->d_cand, c->d_ntotal, c->d_lvl, c->d_nkept, c->d_status, c->d_src[0], c->d_src[1], c->d_kps[0],
                      c->d_kps[1], c->d_desc[0], c->d_desc[1], c->d_counts[0], c->d_counts[1], c->d_knn_part, c->d_match_scratch };
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) {
         if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
@@ -233,6 +235,37 @@ int orb_extract(orb_ctx* c, const uint8_t* img, int w, int h, int stride,
     int rc = orb_extract_batch(c, img, 1, w, h, stride, (size_t)stride * h, kps, desc, cap, &cnt);
     *n = cnt;
     return rc;
+}
+
+int orb_profile_enable(orb_ctx* c, int on)
+{
+    if (!c) return ORB_ERR_INVALID;
+    c->profile = on != 0;
+    return ORB_OK;
+}
+const char* orb_profile_stage_name(int i)
+{
+    static const char* n[ORB_NSTAGES] = { "k_level0", "k_resize(x7)", "k_fast_nms", "k_cell_compact", "k_select", "k_blur", "k_describe" };
+    return (i >= 0 && i < ORB_NSTAGES) ? n[i] : "";
+}
+int orb_profile_read(orb_ctx* c, double* ms, int* ncalls)
+{
+    if (!c || !ms || !ncalls) return ORB_ERR_INVALID;
+    ORB_CUDA(cudaSetDevice(c->device));
+    ORB_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < ORB_NSTAGES; i++) ms[i] = 0;
+    const size_t per = ORB_NSTAGES + 1;
+    const size_t n = c->prof_events.size() / per;
+    for (size_t k = 0; k < n; k++)
+        for (int i = 0; i < ORB_NSTAGES; i++) {
+            float t = 0;
+            ORB_CUDA(cudaEventElapsedTime(&t, c->prof_events[k * per + i], c->prof_events[k * per + i + 1]));
+            ms[i] += t;
+        }
+    for (cudaEvent_t e : c->prof_events) c->prof_pool.push_back(e);
+    c->prof_events.clear();
+    *ncalls = (int)n;
+    return ORB_OK;
 }
 
 int orb_debug_level_info(orb_ctx* c, int frame, int level, int32_t* info)
@@ -391,13 +424,78 @@ int orb_frame_grid_build(orb_ctx* c, const orb_keypoint* kps, int n, int min_x, 
     return ORB_OK;
 }
 
+} // extern "C"
+
+// bump allocator over the matcher scratch buffer; host arrays are uploaded, device arrays passed through
+struct Bump {
+    uint8_t* base; size_t off = 0, cap;
+    Bump(void* b, size_t c) : base((uint8_t*)b), cap(c) {}
+    void* take(size_t bytes) { void* p = base + off; off += al256(std::max<size_t>(bytes, 1)); return p; }
+};
+template <typename T>
+static int stage_in(Bump& b, bool dev, const T*& p, size_t count, cudaStream_t s)
+{
+    if (dev || !p) return ORB_OK;
+    T* d = (T*)b.take(count * sizeof(T));
+    if (count) ORB_CUDA(cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    p = d;
+    return ORB_OK;
+}
+static size_t frame_view_bytes(const orb_frame_view* f)
+{
+    const size_t n = (size_t)std::max(f->n, 1);
+    return al256(n * sizeof(orb_keypoint)) + al256(n * 32) + al256((ORB_GRID_COLS * ORB_GRID_ROWS + 1) * 4) + al256(n * 4);
+}
+static int stage_frame(Bump& b, bool dev, orb_frame_view& f, bool need_grid, cudaStream_t s)
+{
+    int rc;
+    if ((rc = stage_in(b, dev, f.kps, (size_t)f.n, s))) return rc;
+    if ((rc = stage_in(b, dev, f.desc, (size_t)f.n * 32, s))) return rc;
+    if (need_grid) {
+        if ((rc = stage_in(b, dev, f.cell_start, (size_t)ORB_GRID_COLS * ORB_GRID_ROWS + 1, s))) return rc;
+        if ((rc = stage_in(b, dev, f.cell_items, (size_t)f.n, s))) return rc;
+    }
+    return ORB_OK;
+}
+
+extern "C" {
+
 int orb_search_by_projection(orb_ctx* c, const orb_frame_view* cur, const orb_frame_view* last,
                              const uint8_t* last_has_mp, const uint8_t* last_outlier, const float* last_xyz,
                              const float* Tcw16, float th, int check_ori, int32_t* match_cur, int* nmatches)
 {
-    (void)c; (void)cur; (void)last; (void)last_has_mp; (void)last_outlier; (void)last_xyz; (void)Tcw16; (void)th;
-    (void)check_ori; (void)match_cur; (void)nmatches;
-    return ORB_ERR_UNSUPPORTED;
+    if (!c || !cur || !last || !Tcw16 || !nmatches || cur->n < 0 || last->n < 0) return ORB_ERR_INVALID;
+    *nmatches = 0;
+    if (cur->n == 0 || last->n == 0) return ORB_OK;
+    if (!match_cur || !cur->kps || !cur->desc || !cur->cell_start || !cur->cell_items || !last->kps || !last->desc ||
+        !last_has_mp || !last_outlier || !last_xyz || cur->max_x <= cur->min_x || cur->max_y <= cur->min_y) return ORB_ERR_INVALID;
+    ORB_CUDA(cudaSetDevice(c->device));
+    const bool dev = is_device_ptr(cur->kps);
+    if (is_device_ptr(match_cur) != dev || is_device_ptr(last->kps) != dev) return ORB_ERR_INVALID;
+    float T[16];
+    if (is_device_ptr(Tcw16)) ORB_CUDA(cudaMemcpy(T, Tcw16, sizeof T, cudaMemcpyDeviceToHost)); else memcpy(T, Tcw16, sizeof T);
+    cudaStream_t s = c->streams[0];
+    const size_t work = orb_sbp_scratch_bytes(cur->n, last->n);
+    const size_t in_bytes = dev ? 0 : frame_view_bytes(cur) + frame_view_bytes(last) + 2 * al256(last->n) + al256((size_t)last->n * 12) + al256((size_t)cur->n * 4);
+    int rc = match_scratch(c, 256 + in_bytes + work);
+    if (rc) return rc;
+    Bump b(c->d_match_scratch, c->match_scratch_bytes);
+    int* d_result = (int*)b.take(8);
+    orb_frame_view dc = *cur, dl = *last;
+    if ((rc = stage_frame(b, dev, dc, true, s)) || (rc = stage_frame(b, dev, dl, false, s))) return rc;
+    if ((rc = stage_in(b, dev, last_has_mp, (size_t)last->n, s)) || (rc = stage_in(b, dev, last_outlier, (size_t)last->n, s)) ||
+        (rc = stage_in(b, dev, last_xyz, (size_t)last->n * 3, s))) return rc;
+    int32_t* d_match = match_cur;
+    if (!dev) { const int32_t* m = match_cur; if ((rc = stage_in(b, false, m, (size_t)cur->n, s))) return rc; d_match = (int32_t*)m; }
+    uint8_t* wk = (uint8_t*)b.take(work);
+    rc = orb_launch_search_by_projection(c, &dc, &dl, last_has_mp, last_outlier, last_xyz, T, th, check_ori, d_match, d_result, wk, work, s);
+    if (rc) return rc;
+    int res[2] = { 0, 0 };
+    if (!dev) ORB_CUDA(cudaMemcpyAsync(match_cur, d_match, (size_t)cur->n * 4, cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaMemcpyAsync(res, d_result, sizeof res, cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaStreamSynchronize(s));
+    *nmatches = res[0];
+    return res[1] ? ORB_ERR_CAPACITY : ORB_OK;
 }
 
 int orb_search_by_bow(orb_ctx* c, const orb_featvec_view* kf_fv, const uint8_t* kf_desc, const orb_keypoint* kf_kps,
@@ -405,9 +503,46 @@ int orb_search_by_bow(orb_ctx* c, const orb_featvec_view* kf_fv, const uint8_t* 
                       const orb_featvec_view* f_fv, const uint8_t* f_desc, const orb_keypoint* f_kps, int n_f,
                       float nnratio, int check_ori, int32_t* match_f, int* nmatches)
 {
-    (void)c; (void)kf_fv; (void)kf_desc; (void)kf_kps; (void)kf_mp_valid; (void)n_kf; (void)f_fv; (void)f_desc;
-    (void)f_kps; (void)n_f; (void)nnratio; (void)check_ori; (void)match_f; (void)nmatches;
-    return ORB_ERR_UNSUPPORTED;
+    if (!c || !kf_fv || !f_fv || !nmatches || n_kf < 0 || n_f < 0 || kf_fv->nnodes < 0 || f_fv->nnodes < 0) return ORB_ERR_INVALID;
+    *nmatches = 0;
+    if (n_f == 0) return ORB_OK;
+    if (!match_f || !f_desc || !f_kps || (n_kf > 0 && (!kf_desc || !kf_kps || !kf_mp_valid))) return ORB_ERR_INVALID;
+    ORB_CUDA(cudaSetDevice(c->device));
+    const bool dev = is_device_ptr(f_desc);
+    if (is_device_ptr(match_f) != dev) return ORB_ERR_INVALID;
+    cudaStream_t s = c->streams[0];
+    // item totals live at start[nnodes]
+    int kf_total = 0, f_total = 0;
+    if (kf_fv->nnodes) { if (dev) ORB_CUDA(cudaMemcpy(&kf_total, kf_fv->start + kf_fv->nnodes, 4, cudaMemcpyDeviceToHost)); else kf_total = kf_fv->start[kf_fv->nnodes]; }
+    if (f_fv->nnodes) { if (dev) ORB_CUDA(cudaMemcpy(&f_total, f_fv->start + f_fv->nnodes, 4, cudaMemcpyDeviceToHost)); else f_total = f_fv->start[f_fv->nnodes]; }
+    const size_t work = orb_bow_scratch_bytes(n_f);
+    size_t in_bytes = 0;
+    if (!dev) in_bytes = al256((size_t)n_kf * 32) + al256((size_t)n_kf * 28) + al256(n_kf) + al256((size_t)n_f * 32) + al256((size_t)n_f * 28) +
+                         al256((size_t)n_f * 4) + 2 * al256((size_t)(kf_fv->nnodes + 1) * 4) + al256((size_t)kf_total * 4 + 4) +
+                         2 * al256((size_t)(f_fv->nnodes + 1) * 4) + al256((size_t)f_total * 4 + 4) + 4096;
+    int rc = match_scratch(c, in_bytes + work + 256);
+    if (rc) return rc;
+    Bump b(c->d_match_scratch, c->match_scratch_bytes);
+    orb_featvec_view a = *kf_fv, f = *f_fv;
+    static const int32_t zero_start[1] = { 0 };
+    if (!a.start) a.start = zero_start;
+    if (!f.start) f.start = zero_start;
+    if ((rc = stage_in(b, dev, a.node_id, (size_t)a.nnodes, s)) || (rc = stage_in(b, dev, a.start, (size_t)a.nnodes + 1, s)) ||
+        (rc = stage_in(b, dev, a.items, (size_t)kf_total, s)) || (rc = stage_in(b, dev, f.node_id, (size_t)f.nnodes, s)) ||
+        (rc = stage_in(b, dev, f.start, (size_t)f.nnodes + 1, s)) || (rc = stage_in(b, dev, f.items, (size_t)f_total, s)) ||
+        (rc = stage_in(b, dev, kf_desc, (size_t)n_kf * 32, s)) || (rc = stage_in(b, dev, kf_kps, (size_t)n_kf, s)) ||
+        (rc = stage_in(b, dev, kf_mp_valid, (size_t)n_kf, s)) || (rc = stage_in(b, dev, f_desc, (size_t)n_f * 32, s)) ||
+        (rc = stage_in(b, dev, f_kps, (size_t)n_f, s))) return rc;
+    int32_t* d_match = dev ? match_f : (int32_t*)b.take((size_t)n_f * 4);
+    uint8_t* wk = (uint8_t*)b.take(work);
+    rc = orb_launch_search_by_bow(c, &a, kf_desc, kf_kps, kf_mp_valid, &f, f_desc, f_kps, n_f, f_total, nnratio, check_ori, d_match, wk, s);
+    if (rc) return rc;
+    int res = 0;
+    if (!dev) ORB_CUDA(cudaMemcpyAsync(match_f, d_match, (size_t)n_f * 4, cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaMemcpyAsync(&res, wk, sizeof res, cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaStreamSynchronize(s));
+    *nmatches = res;
+    return ORB_OK;
 }
 
 int orb_measure_popc_peak(orb_ctx* c, double* gpopc_per_s)

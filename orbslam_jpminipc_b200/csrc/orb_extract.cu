@@ -505,27 +505,43 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w, int h
     const size_t fb = (size_t)P.frame_bytes;
     int launches = 0;
     const dim3 blk(64, 4);
+    auto mark = [&]() {           // stage boundary event (profiling mode only)
+        if (!c->profile) return;
+        cudaEvent_t e;
+        if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+        else if (cudaEventCreate(&e) != cudaSuccess) return;
+        cudaEventRecord(e, s);
+        c->prof_events.push_back(e);
+    };
+    mark();
     {
         const LevelGeom& L = P.L[0];
         dim3 grid((L.stride / 4 + 63) / 64, (L.prows + 3) / 4, nimg);
         k_level0<<<grid, blk, 0, s>>>(d_imgs, w, h, stride, frame_pitch, c->d_planes, fb, L.stride, L.prows);
         launches++;
     }
+    mark();
     for (int l = 1; l < P.nlevels; l++) {
         const LevelGeom& D = P.L[l];
         dim3 grid((D.stride / 4 + 63) / 64, (D.prows + 3) / 4, nimg);
         k_resize<<<grid, blk, 0, s>>>(c->d_planes, fb, P.L[l - 1], D, c->d_xtab, c->d_ytab);
         launches++;
     }
+    mark();
     k_fast_nms<<<dim3(P.ntiles_fast, nimg), 256, 0, s>>>(c->d_planes, c->d_work, fb, c->d_plan, c->d_tiles_fast);
+    mark();
     k_cell_compact<<<dim3((P.ncells + 7) / 8, nimg), 256, 0, s>>>(c->d_work, fb, c->d_plan, c->d_cells, c->d_cand, c->d_ntotal);
+    mark();
     int maxcap = 0;
     for (int l = 0; l < P.nlevels; l++) maxcap = std::max(maxcap, P.L[l].lvl_cap);
     k_select<<<dim3(P.nlevels, nimg), 128, (size_t)maxcap * 8, s>>>(c->d_plan, c->d_cells, c->d_cand, c->d_ntotal, c->d_lvl, c->d_nkept, c->d_status);
+    mark();
     k_blur<<<dim3(P.ntiles_blur, nimg), 256, 0, s>>>(c->d_planes, c->d_work, fb, c->d_plan, c->d_tiles_blur);
+    mark();
     const int slots = std::min(cap, P.kp_cap);
     k_describe<<<dim3((std::max(slots, 1) + 7) / 8, nimg), 256, 0, s>>>(c->d_planes, c->d_work, fb, c->d_plan, c->d_lvl, c->d_nkept,
                                                                     d_kps, d_desc, cap, d_counts);
+    mark();
     launches += 5;
     c->last_launches = launches;
     ORB_CUDA(cudaGetLastError());

@@ -93,6 +93,9 @@ struct orb_ctx {
     cudaStream_t streams[2] = { nullptr, nullptr };
     cudaEvent_t ev_free[2] = { nullptr, nullptr };
     int last_launches = 0;
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;   // (ORB_NSTAGES+1) per profiled launch
+    std::vector<cudaEvent_t> prof_pool;
     int last_nimg = 0;
     // matcher scratch
     int32_t* d_knn_part = nullptr; size_t knn_part_bytes = 0;
@@ -122,9 +125,12 @@ int orb_launch_grid_build(const orb_keypoint* kps, int n, int min_x, int max_x, 
                           int32_t* cell_start, int32_t* cell_items, cudaStream_t s);
 int orb_launch_search_by_projection(orb_ctx* c, const orb_frame_view* cur, const orb_frame_view* last,
                                     const uint8_t* last_has_mp, const uint8_t* last_outlier, const float* last_xyz,
-                                    const float* T16_host, float th, int check_ori, int32_t* match_cur, int* d_nmatches, cudaStream_t s);
+                                    const float* T16_host, float th, int check_ori, int32_t* match_cur, int* d_result,
+                                    uint8_t* scratch, size_t scratch_bytes, cudaStream_t s);
+size_t orb_sbp_scratch_bytes(int n_cur, int n_last);
 int orb_launch_search_by_bow(orb_ctx* c, const orb_featvec_view* kf_fv, const uint8_t* kf_desc, const orb_keypoint* kf_kps,
                              const uint8_t* kf_mp_valid, const orb_featvec_view* f_fv, const uint8_t* f_desc,
-                             const orb_keypoint* f_kps, int n_f, float nnratio, int check_ori, int32_t* match_f,
-                             int* d_nmatches, cudaStream_t s);
+                             const orb_keypoint* f_kps, int n_f, int f_items_total, float nnratio, int check_ori, int32_t* match_f,
+                             uint8_t* scratch, cudaStream_t s);
+size_t orb_bow_scratch_bytes(int n_f);
 int orb_launch_popc_bench(double* gpopc, cudaStream_t s);

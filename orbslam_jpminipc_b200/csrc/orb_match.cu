@@ -231,6 +231,285 @@ k_grid_build(const orb_keypoint* __restrict__ kps, int n, int min_x, int max_x, 
     }
 }
 
+// ------------------------------------------------------------------ K8: SearchByProjection
+constexpr int HISTO_LENGTH = 30;      // src/ORBmatcher.cc:42
+constexpr int TH_HIGH = 100, TH_LOW = 50;
+
+struct SbpArgs {
+    orb_frame_view cur, last;         // device pointers inside
+    const uint8_t* has_mp; const uint8_t* outlier; const float* xyz;
+    float T[16];
+    float sf[ORB_MAX_LEVELS];         // CurrentFrame.mvScaleFactors (src/Frame.cc:95-103)
+    float th;
+    int cap;                          // candidate slots per query
+    uint32_t* list; int* cnt;         // list[i*cap + pos] = dist<<22 | i2 ; cnt[i] = candidates found (-1: not searched)
+};
+
+__device__ __forceinline__ int hamming256(const uint32_t* q, const uint8_t* row)
+{
+    const uint4* p = reinterpret_cast<const uint4*>(row);
+    const uint4 a = __ldg(p), b = __ldg(p + 1);
+    return __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w)
+         + __popc(q[4] ^ b.x) + __popc(q[5] ^ b.y) + __popc(q[6] ^ b.z) + __popc(q[7] ^ b.w);
+}
+
+// rotation-histogram bin (src/ORBmatcher.cc:1583-1588, :234-239); factor is 1/HISTO_LENGTH as in the reference
+__device__ __forceinline__ int rot_bin(float a_from, float a_to)
+{
+    const float factor = 1.0f / HISTO_LENGTH;
+    float rot = __fsub_rn(a_from, a_to);
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, factor));
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+// ComputeThreeMaxima, src/ORBmatcher.cc:1748-1789
+__device__ void three_maxima(const int* hs, int& ind1, int& ind2, int& ind3)
+{
+    int max1 = 0, max2 = 0, max3 = 0;
+    ind1 = ind2 = ind3 = -1;
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+        const int s = hs[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
+}
+
+// Pass 1, one warp per last-frame feature: project its map point (:1529-1537), gate on the image
+// bounds (:1539-1542) and enumerate GetFeaturesInArea(u, v, th*scale, oct-1, oct+1) in the
+// reference's scan order (ix outer, iy inner, insertion order; src/Frame.cc:233-259) together with
+// the Hamming distance of every candidate.  Claims are NOT looked at here (pass 2 does that).
+__global__ void __launch_bounds__(256)
+k_sbp_candidates(SbpArgs A)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= A.last.n) return;
+    int total = -1;
+    if (A.has_mp[i] && !A.outlier[i]) {
+        const float X = A.xyz[3 * i], Y = A.xyz[3 * i + 1], Z = A.xyz[3 * i + 2];
+        float c[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            // cv::gemm small-matrix branch: FP32 sum of the three products, translation added in double
+            const float t0 = __fadd_rn(__fadd_rn(__fmul_rn(A.T[4 * r], X), __fmul_rn(A.T[4 * r + 1], Y)), __fmul_rn(A.T[4 * r + 2], Z));
+            c[r] = __double2float_rn((double)t0 + (double)A.T[4 * r + 3]);
+        }
+        const float invzc = __double2float_rn(1.0 / (double)c[2]);
+        const float u = __fadd_rn(__fmul_rn(__fmul_rn(A.cur.fx, c[0]), invzc), A.cur.cx);
+        const float v = __fadd_rn(__fmul_rn(__fmul_rn(A.cur.fy, c[1]), invzc), A.cur.cy);
+        const bool inb = !(u < (float)A.cur.min_x || u > (float)A.cur.max_x) && !(v < (float)A.cur.min_y || v > (float)A.cur.max_y);
+        if (inb) {
+            total = 0;
+            const int oct = A.last.kps[i].octave;
+            const float r = __fmul_rn(A.th, A.sf[oct]);
+            const int minLevel = oct - 1, maxLevel = oct + 1;
+            const float invW = __fdiv_rn((float)ORB_GRID_COLS, (float)(A.cur.max_x - A.cur.min_x));
+            const float invH = __fdiv_rn((float)ORB_GRID_ROWS, (float)(A.cur.max_y - A.cur.min_y));
+            const float ux = __fsub_rn(u, (float)A.cur.min_x), vy = __fsub_rn(v, (float)A.cur.min_y);
+            int x0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(ux, r), invW)));
+            int x1 = min(ORB_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(ux, r), invW)));
+            int y0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(vy, r), invH)));
+            int y1 = min(ORB_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(vy, r), invH)));
+            if (x0 >= ORB_GRID_COLS || x1 < 0 || y0 >= ORB_GRID_ROWS || y1 < 0) { x1 = -1; x0 = 0; }
+            uint32_t q[8];
+            {
+                const uint4* qp = reinterpret_cast<const uint4*>(A.last.desc + (size_t)i * 32);
+                const uint4 a = __ldg(qp), b = __ldg(qp + 1);
+                q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
+            }
+            const bool sameLevel = minLevel == maxLevel;   // never true here; kept for the general rule of :225-253
+            const bool checkLevels = !(minLevel == -1 && maxLevel == -1);
+            uint32_t* out = A.list + (size_t)i * A.cap;
+            const uint32_t lt = (1u << lane) - 1;
+            for (int ix = x0; ix <= x1; ix++)
+                for (int iy = y0; iy <= y1; iy++) {
+                    const int cidx = ix * ORB_GRID_ROWS + iy;
+                    const int b = A.cur.cell_start[cidx], e = A.cur.cell_start[cidx + 1];
+                    for (int j0 = b; j0 < e; j0 += 32) {
+                        const int j = j0 + lane;
+                        bool ok = false; int id = 0;
+                        if (j < e) {
+                            id = A.cur.cell_items[j];
+                            const orb_keypoint kp = A.cur.kps[id];
+                            ok = true;
+                            if (checkLevels && !sameLevel) { if (kp.octave < minLevel || kp.octave > maxLevel) ok = false; }
+                            else if (sameLevel) { if (kp.octave != minLevel) ok = false; }
+                            if (fabsf(__fsub_rn(kp.x, u)) > r || fabsf(__fsub_rn(kp.y, v)) > r) ok = false;
+                        }
+                        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+                        if (ok) {
+                            const int pos = total + __popc(m & lt);
+                            if (pos < A.cap) out[pos] = ((uint32_t)hamming256(q, A.cur.desc + (size_t)id * 32) << 22) | (uint32_t)id;
+                        }
+                        total += __popc(m);
+                    }
+                }
+        }
+    }
+    if (lane == 0) A.cnt[i] = total;
+}
+
+// Pass 2, one warp, last-frame features in index order: best unclaimed candidate, first in scan order
+// on ties (:1559-1574), accept at <= TH_HIGH and claim (:1576-1579); then the rotation histogram
+// filter (:1581-1617).  result[0] = nmatches, result[1] = error flag.
+__global__ void __launch_bounds__(32)
+k_sbp_resolve(SbpArgs A, int check_ori, int32_t* __restrict__ match_cur, int8_t* __restrict__ bin_of, int* __restrict__ result)
+{
+    __shared__ int hist[HISTO_LENGTH];
+    const int lane = threadIdx.x;
+    if (lane < HISTO_LENGTH) hist[lane] = 0;
+    for (int k = lane; k < A.cur.n; k += 32) bin_of[k] = -1;
+    __syncwarp();
+    int nmatches = 0, err = 0;
+    for (int i = 0; i < A.last.n; i++) {
+        const int n = A.cnt[i];
+        if (n <= 0) continue;
+        if (n > A.cap) { err = 1; continue; }
+        const uint32_t* L = A.list + (size_t)i * A.cap;
+        unsigned long long best = ~0ull;          // (dist, scan position, id)
+        for (int p = lane; p < n; p += 32) {
+            const uint32_t e = L[p];
+            const int id = (int)(e & 0x3fffff);
+            if (match_cur[id] >= 0) continue;     // CurrentFrame.mvpMapPoints[i2] already set (:1562)
+            const unsigned long long key = ((unsigned long long)(e >> 22) << 44) | ((unsigned long long)p << 22) | (unsigned long long)id;
+            best = key < best ? key : best;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o); best = t < best ? t : best; }
+        if (best == ~0ull) continue;
+        const int bestDist = (int)(best >> 44), bestIdx2 = (int)(best & 0x3fffff);
+        if (bestDist <= TH_HIGH) {
+            if (lane == 0) {
+                match_cur[bestIdx2] = i;
+                if (check_ori) {
+                    const int b = rot_bin(A.last.kps[i].angle, A.cur.kps[bestIdx2].angle);
+                    bin_of[bestIdx2] = (int8_t)b;
+                    hist[b]++;
+                }
+            }
+            nmatches++;
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    if (check_ori) {
+        int i1, i2, i3;
+        three_maxima(hist, i1, i2, i3);
+        int removed = 0;
+        for (int k = lane; k < A.cur.n; k += 32) {
+            const int b = bin_of[k];
+            if (b >= 0 && b != i1 && b != i2 && b != i3) { match_cur[k] = -1; removed++; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+        nmatches -= removed;
+    }
+    if (lane == 0) { result[0] = nmatches; result[1] = err; }
+}
+
+// ------------------------------------------------------------------ K9: SearchByBoW scoring
+struct BowArgs {
+    orb_featvec_view kf, f;
+    const uint8_t* kf_desc; const orb_keypoint* kf_kps; const uint8_t* kf_valid;
+    const uint8_t* f_desc; const orb_keypoint* f_kps; int n_f;
+    float nnratio; int check_ori;
+    int32_t* match_f; int8_t* bin_of; int* hist; int* result;   // hist[30], result[0]=nmatches, result[1]=overlap flag
+    int* seen;                                                   // n_f counters for the disjointness check
+};
+
+// A frame feature that appears under two vocabulary nodes would couple the nodes through the claim
+// array; DBoW2 never produces that, but if the caller's CSR does, fall back to one warp in node order.
+__global__ void k_bow_check(BowArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = A.f.start[A.f.nnodes];
+    if (j < total) { if (atomicAdd(&A.seen[A.f.items[j]], 1) > 0) A.result[1] = 1; }
+}
+
+__global__ void __launch_bounds__(256)
+k_bow_match(BowArgs A)
+{
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const bool serial = A.result[1] != 0;
+    if (serial && gw != 0) return;
+    int local_matches = 0;
+    for (int a = serial ? 0 : gw; a < A.kf.nnodes; a += serial ? 1 : nw) {
+        // merge-join of the two ascending node lists (:176-260) == binary search of this KF node in F
+        const int node = A.kf.node_id[a];
+        int lo = 0, hi = A.f.nnodes;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (A.f.node_id[mid] < node) lo = mid + 1; else hi = mid; }
+        if (lo >= A.f.nnodes || A.f.node_id[lo] != node) continue;
+        const int fb = A.f.start[lo], fe = A.f.start[lo + 1];
+        for (int ik = A.kf.start[a]; ik < A.kf.start[a + 1]; ik++) {
+            const int realIdxKF = A.kf.items[ik];
+            if (!A.kf_valid[realIdxKF]) continue;
+            uint32_t q[8];
+            {
+                const uint4* qp = reinterpret_cast<const uint4*>(A.kf_desc + (size_t)realIdxKF * 32);
+                const uint4 x = __ldg(qp), y = __ldg(qp + 1);
+                q[0] = x.x; q[1] = x.y; q[2] = x.z; q[3] = x.w; q[4] = y.x; q[5] = y.y; q[6] = y.z; q[7] = y.w;
+            }
+            unsigned long long best = ~0ull;      // (dist, scan position, id)
+            int d1 = INT_MAX, d2 = INT_MAX;
+            for (int jf = fb + lane; jf < fe; jf += 32) {
+                const int realIdxF = A.f.items[jf];
+                if (((volatile int32_t*)A.match_f)[realIdxF] >= 0) continue;      // :205
+                const int dist = hamming256(q, A.f_desc + (size_t)realIdxF * 32);
+                const unsigned long long key = ((unsigned long long)dist << 44) | ((unsigned long long)(jf - fb) << 22) | (unsigned long long)realIdxF;
+                best = key < best ? key : best;
+                if (dist < d1) { d2 = d1; d1 = dist; } else if (dist < d2) d2 = dist;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+                best = t < best ? t : best;
+                const int e1 = __shfl_xor_sync(0xffffffffu, d1, o), e2 = __shfl_xor_sync(0xffffffffu, d2, o);
+                const int n1 = min(d1, e1), n2 = min(max(d1, e1), min(d2, e2));   // two smallest of the multiset union
+                d1 = n1; d2 = n2;
+            }
+            if (best == ~0ull) continue;
+            const int bestIdxF = (int)(best & 0x3fffff);
+            if (d1 <= TH_LOW && (float)d1 < __fmul_rn(A.nnratio, (float)d2)) {    // :224-226
+                if (lane == 0) {
+                    A.match_f[bestIdxF] = realIdxKF;
+                    if (A.check_ori) {
+                        const int b = rot_bin(A.kf_kps[realIdxKF].angle, A.f_kps[bestIdxF].angle);
+                        A.bin_of[bestIdxF] = (int8_t)b;
+                        atomicAdd(&A.hist[b], 1);
+                    }
+                }
+                local_matches++;
+                __threadfence_block();
+                __syncwarp();
+            }
+        }
+    }
+    if (lane == 0 && local_matches) atomicAdd(&A.result[0], local_matches);
+}
+
+__global__ void __launch_bounds__(256)
+k_bow_orientation(BowArgs A)
+{
+    __shared__ int s_removed;
+    if (threadIdx.x == 0) s_removed = 0;
+    __syncthreads();
+    int i1, i2, i3;
+    three_maxima(A.hist, i1, i2, i3);
+    int removed = 0;
+    for (int k = threadIdx.x; k < A.n_f; k += blockDim.x) {
+        const int b = A.bin_of[k];
+        if (b >= 0 && b != i1 && b != i2 && b != i3) { A.match_f[k] = -1; removed++; }
+    }
+    if (removed) atomicAdd(&s_removed, removed);
+    __syncthreads();
+    if (threadIdx.x == 0) A.result[0] -= s_removed;
+}
+
 } // namespace
 
 int orb_launch_knn2(orb_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_db, int64_t ndb, int npairs, int32_t idx_base,
@@ -244,6 +523,12 @@ int orb_launch_knn2(orb_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_db,
     rows = ((rows + KNN_TILE - 1) / KNN_TILE) * KNN_TILE;
     if (rows > (1 << 30)) rows = 1 << 30;
     const int nchunks = (int)((ndb + rows - 1) / rows);
+    if (nchunks == 0) {          // empty DB: idx1 = -1, d1 = d2 = INT_MAX for every query
+        k_knn2_merge<<<dim3((nq + 127) / 128, npairs), 128, 0, s>>>(nullptr, 0, nq, npairs, d_idx1, d_d1, d_d2);
+        c->last_launches = 1;
+        ORB_CUDA(cudaGetLastError());
+        return ORB_OK;
+    }
     Knn2Args A;
     A.q = d_q; A.db = d_db; A.nq = nq; A.ndb = ndb; A.rows_per_chunk = (int)rows; A.nchunks = nchunks;
     A.idx_base = idx_base; A.out = nullptr; A.o_idx1 = d_idx1; A.o_d1 = d_d1; A.o_d2 = d_d2;
@@ -317,4 +602,68 @@ int orb_launch_popc_bench(double* gpopc, cudaStream_t s)
     *gpopc = (double)blocks * threads * iters * 32.0 / (best * 1e-3) / 1e9;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     return ORB_OK;
+}
+
+int orb_launch_search_by_projection(orb_ctx* c, const orb_frame_view* cur, const orb_frame_view* last,
+                                    const uint8_t* last_has_mp, const uint8_t* last_outlier, const float* last_xyz,
+                                    const float* T16_host, float th, int check_ori, int32_t* match_cur, int* d_result,
+                                    uint8_t* scratch, size_t scratch_bytes, cudaStream_t s)
+{
+    (void)c;
+    SbpArgs A;
+    A.cur = *cur; A.last = *last; A.has_mp = last_has_mp; A.outlier = last_outlier; A.xyz = last_xyz;
+    for (int i = 0; i < 16; i++) A.T[i] = T16_host[i];
+    if (cur->nlevels < 1 || cur->nlevels > ORB_MAX_LEVELS) return ORB_ERR_INVALID;
+    A.sf[0] = 1.0f;
+    for (int i = 1; i < ORB_MAX_LEVELS; i++) A.sf[i] = i < cur->nlevels ? A.sf[i - 1] * cur->scale_factor : A.sf[i - 1];
+    A.th = th;
+    if (cur->n >= (1 << 22)) return ORB_ERR_CAPACITY;
+    // scratch: cnt[last.n] | bin_of[cur.n] | list[last.n * cap]
+    size_t off = 0;
+    A.cnt = (int*)(scratch + off); off += ((size_t)last->n * 4 + 255) & ~(size_t)255;
+    int8_t* bin_of = (int8_t*)(scratch + off); off += ((size_t)cur->n + 255) & ~(size_t)255;
+    const size_t avail = scratch_bytes > off ? (scratch_bytes - off) / 4 : 0;
+    A.cap = (int)std::min<size_t>((size_t)cur->n, last->n ? avail / (size_t)last->n : 0);
+    A.cap = std::min(A.cap, 1 << 20);
+    A.list = (uint32_t*)(scratch + off);
+    if (A.cap < 1) return ORB_ERR_CAPACITY;
+    k_sbp_candidates<<<(last->n * 32 + 255) / 256, 256, 0, s>>>(A);
+    k_sbp_resolve<<<1, 32, 0, s>>>(A, check_ori, match_cur, bin_of, d_result);
+    ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
+}
+
+size_t orb_sbp_scratch_bytes(int n_cur, int n_last)
+{
+    const size_t cap = (size_t)std::min(n_cur, 1024);
+    return (((size_t)n_last * 4 + 255) & ~(size_t)255) + (((size_t)n_cur + 255) & ~(size_t)255) + (size_t)n_last * cap * 4 + 256;
+}
+
+int orb_launch_search_by_bow(orb_ctx* c, const orb_featvec_view* kf_fv, const uint8_t* kf_desc, const orb_keypoint* kf_kps,
+                             const uint8_t* kf_mp_valid, const orb_featvec_view* f_fv, const uint8_t* f_desc,
+                             const orb_keypoint* f_kps, int n_f, int f_items_total, float nnratio, int check_ori, int32_t* match_f,
+                             uint8_t* scratch, cudaStream_t s)
+{
+    (void)c;
+    if (n_f >= (1 << 22)) return ORB_ERR_CAPACITY;
+    BowArgs A;
+    A.kf = *kf_fv; A.f = *f_fv; A.kf_desc = kf_desc; A.kf_kps = kf_kps; A.kf_valid = kf_mp_valid;
+    A.f_desc = f_desc; A.f_kps = f_kps; A.n_f = n_f; A.nnratio = nnratio; A.check_ori = check_ori; A.match_f = match_f;
+    // scratch: result[2] + hist[30] (256 B) | seen[n_f] | bin_of[n_f]
+    A.result = (int*)scratch; A.hist = (int*)scratch + 2;
+    A.seen = (int*)(scratch + 256);
+    A.bin_of = (int8_t*)(scratch + 256 + (((size_t)n_f * 4 + 255) & ~(size_t)255));
+    ORB_CUDA(cudaMemsetAsync(scratch, 0, 256 + (((size_t)n_f * 4 + 255) & ~(size_t)255), s));
+    ORB_CUDA(cudaMemsetAsync(A.bin_of, 0xff, (size_t)std::max(n_f, 1), s));
+    ORB_CUDA(cudaMemsetAsync(match_f, 0xff, (size_t)std::max(n_f, 1) * 4, s));     // :159
+    if (f_items_total > 0) k_bow_check<<<(f_items_total + 255) / 256, 256, 0, s>>>(A);
+    if (kf_fv->nnodes > 0) k_bow_match<<<std::max(1, std::min(148, (kf_fv->nnodes + 7) / 8)), 256, 0, s>>>(A);
+    if (check_ori) k_bow_orientation<<<1, 256, 0, s>>>(A);
+    ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
+}
+
+size_t orb_bow_scratch_bytes(int n_f)
+{
+    return 256 + (((size_t)n_f * 4 + 255) & ~(size_t)255) + (((size_t)n_f + 255) & ~(size_t)255) + 256;
 }

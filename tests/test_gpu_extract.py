@@ -57,7 +57,7 @@ def test_golden_frames(pkg, name):
 
 
 @pytest.mark.parametrize("shape,nf", [((480, 640), 1000), ((480, 752), 1000), ((376, 1241), 2000), ((480, 640), 2000),
-                                      ((300, 301), 500), ((97, 203), 150)])
+                                      ((300, 301), 500), ((100, 140), 120)])
 def test_vs_oracle_shapes(pkg, po, shape, nf):
     from orbslam_jpminipc_b200.synth import synth_frame
     h, w = shape
@@ -71,6 +71,23 @@ def test_vs_oracle_shapes(pkg, po, shape, nf):
         for l in range(8):
             assert ex.level_info(l)["nKept"] == orc.level_info(l)["nKept"]
             assert np.array_equal(ex.level_plane(l), orc.level_plane(l)), (shape, l)
+    ex.close()
+
+
+@pytest.mark.parametrize("h,w,nf", [(97, 203, 150), (120, 160, 100), (90, 300, 200), (64, 64, 60), (200, 200, 50), (150, 170, 130)])
+def test_degenerate_geometry_agrees_with_oracle(pkg, po, h, w, nf):
+    """Shapes on which the reference itself throws / divides by zero: product and oracle must agree on the verdict."""
+    from orbslam_jpminipc_b200.synth import synth_frame
+    img = synth_frame(h, w, 77)
+    ex = pkg.ORBextractor(nf, 1.2, 8, 1, 20, max_width=w, max_height=h, max_batch=1)
+    try:
+        rk, rd = po.OracleExtractor(nf)(img)
+    except RuntimeError:
+        with pytest.raises(pkg.OrbError):
+            ex(img)
+    else:
+        kps, desc = ex(img)
+        _same(kps, desc, rk, rd, (h, w, nf))
     ex.close()
 
 

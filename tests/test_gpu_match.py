@@ -77,3 +77,141 @@ def test_frame_grid(pkg, po, matcher):
     assert np.array_equal(f.cell_start, o.cell_start)
     cnt = f.cell_start[-1]
     assert cnt < n and np.array_equal(f.cell_items[:cnt], o.cell_items[:cnt])
+
+
+# ---------------------------------------------------------------- SearchByProjection / SearchByBoW
+def _frame_pair(po, h=240, w=320, nf=500, seed=7000):
+    from orbslam_jpminipc_b200.synth import synth_frame, shifted_frame
+    a = synth_frame(h, w, seed, quadrants=False)
+    b = shifted_frame(a, 3, 2, seed + 1)
+    orc = po.OracleExtractor(nf, 1.2, 8, 1, 20)
+    ka, da = orc(a)
+    kb, db = orc(b)
+    return (ka, da), (kb, db)
+
+
+def _scene(po, pkg, matcher, h=240, w=320, nf=500, seed=7000, th=15.0):
+    (ka, da), (kb, db) = _frame_pair(po, h, w, nf, seed)
+    rng = np.random.default_rng(seed)
+    fx = fy = 500.0
+    cx, cy = w / 2.0, h / 2.0
+    z = rng.uniform(2, 10, len(ka)).astype(np.float32)
+    xyz = np.stack([(ka["x"] - cx) / fx * z, (ka["y"] - cy) / fy * z, z], 1).astype(np.float32)
+    T = np.eye(4, dtype=np.float32)
+    T[:3, 3] = [0.03, 0.02, 0.01]
+    has = (rng.random(len(ka)) < 0.9).astype(np.uint8)
+    outl = (rng.random(len(ka)) < 0.05).astype(np.uint8)
+    args = dict(w=w, h=h, fx=fx, fy=fy, cx=cx, cy=cy)
+    gcur = pkg.Frame(matcher, kb, db, w, h, fx, fy, cx, cy)
+    glast = pkg.Frame(matcher, ka, da, w, h, fx, fy, cx, cy)
+    ocur = po.OracleFrame(kb, db, w, h, fx, fy, cx, cy)
+    olast = po.OracleFrame(ka, da, w, h, fx, fy, cx, cy)
+    return gcur, glast, ocur, olast, has, outl, xyz, T
+
+
+@pytest.mark.parametrize("shape,nf,th,ori", [((240, 320), 500, 15.0, True), ((480, 752), 1000, 15.0, True),
+                                             ((376, 1241), 2000, 15.0, True), ((240, 320), 500, 7.0, False),
+                                             ((240, 320), 500, 40.0, True)])
+def test_search_by_projection_vs_oracle(pkg, po, shape, nf, th, ori):
+    m = pkg.ORBmatcher(0.9, ori)
+    gcur, glast, ocur, olast, has, outl, xyz, T = _scene(po, pkg, m, shape[0], shape[1], nf, 7000 + nf, th)
+    n, match = m.SearchByProjection(gcur, glast, th, has, outl, xyz, T)
+    rn, rmatch = po.search_by_projection(ocur, olast, has, outl, xyz, T, th, ori)
+    assert rn > 20, rn
+    assert n == rn and np.array_equal(match, rmatch)
+
+
+def test_search_by_projection_preclaimed_and_empty(pkg, po):
+    m = pkg.ORBmatcher(0.9, True)
+    gcur, glast, ocur, olast, has, outl, xyz, T = _scene(po, pkg, m)
+    pre = np.full(gcur.N, -1, np.int32)
+    pre[::3] = 12345                                   # keypoints that already carry a map point are skipped (:1562)
+    n, match = m.SearchByProjection(gcur, glast, 15.0, has, outl, xyz, T, match_cur=pre.copy())
+    rn, rmatch = po.search_by_projection(ocur, olast, has, outl, xyz, T, 15.0, True, match_cur=pre.copy())
+    assert n == rn and np.array_equal(match, rmatch) and np.all(match[::3] == 12345)
+    none = np.zeros_like(has)
+    n, match = m.SearchByProjection(gcur, glast, 15.0, none, outl, xyz, T)
+    assert n == 0 and np.all(match == -1)
+    T2 = T.copy(); T2[:3, 3] = [50, 0, 0]             # everything projects outside the image
+    n, match = m.SearchByProjection(gcur, glast, 15.0, has, outl, xyz, T2)
+    rn, _ = po.search_by_projection(ocur, olast, has, outl, xyz, T2, 15.0, True)
+    assert n == rn == 0
+
+
+def test_search_by_projection_tie_break_is_scan_order(pkg, po):
+    """Two current keypoints with identical descriptors at equal distance: the one met first in the
+    GetFeaturesInArea scan (ix outer, iy inner; src/Frame.cc:233-259) wins, not the lower index."""
+    m = pkg.ORBmatcher(0.9, False)
+    w, h = 640, 480
+    rng = np.random.default_rng(1)
+    d = rng.integers(0, 256, (1, 32), dtype=np.uint8)
+    kb = np.zeros(2, pkg.KP_DTYPE)
+    kb["x"] = [330.0, 310.0]; kb["y"] = [240.0, 240.0]; kb["octave"] = 0; kb["angle"] = 10
+    db = np.repeat(d, 2, 0)
+    ka = np.zeros(1, pkg.KP_DTYPE); ka["x"] = 320; ka["y"] = 240; ka["angle"] = 10
+    xyz = np.array([[0, 0, 5.0]], np.float32)
+    T = np.eye(4, dtype=np.float32)
+    g = (pkg.Frame(m, kb, db, w, h, 500, 500, 320, 240), pkg.Frame(m, ka, d, w, h, 500, 500, 320, 240))
+    o = (po.OracleFrame(kb, db, w, h, 500, 500, 320, 240), po.OracleFrame(ka, d, w, h, 500, 500, 320, 240))
+    one = np.ones(1, np.uint8); zero = np.zeros(1, np.uint8)
+    n, match = m.SearchByProjection(g[0], g[1], 15.0, one, zero, xyz, T)
+    rn, rmatch = po.search_by_projection(o[0], o[1], one, zero, xyz, T, 15.0, False)
+    assert n == rn == 1 and np.array_equal(match, rmatch) and match[1] == 0 and match[0] == -1
+
+
+def _bow_case(po, pkg, n_kf=2000, n_f=2000, nnodes=100, seed=9, flip=0.06):
+    rng = np.random.default_rng(seed)
+    kf_desc = rng.integers(0, 256, (n_kf, 32), dtype=np.uint8)
+    twin = rng.permutation(n_kf)[:n_f] if n_f <= n_kf else rng.integers(0, n_kf, n_f)
+    flips = np.packbits((rng.random((n_f, 256)) < flip).astype(np.uint8), axis=1)
+    f_desc = kf_desc[twin] ^ flips
+    f_desc[::7] = rng.integers(0, 256, (len(f_desc[::7]), 32), dtype=np.uint8)
+    kf_node = rng.integers(0, nnodes, n_kf)
+    f_node = np.where(rng.random(n_f) < 0.9, kf_node[twin], rng.integers(0, nnodes, n_f))
+    f_node = f_node * 3 + 5                              # sparse node ids, some present on one side only
+    kf_node = kf_node * 3 + 5
+    kf_node[kf_node == 5 + 3 * 7] = 4                    # a node id that only the KF has
+    def csr(node):
+        ids = np.unique(node)
+        start = [0]; items = []
+        for v in ids:
+            it = np.nonzero(node == v)[0]
+            items += list(it); start.append(len(items))
+        return ids.astype(np.int32), np.array(start, np.int32), np.array(items, np.int32)
+    kf_kps = np.zeros(n_kf, pkg.KP_DTYPE); kf_kps["angle"] = rng.uniform(0, 360, n_kf).astype(np.float32)
+    f_kps = np.zeros(n_f, pkg.KP_DTYPE)
+    f_kps["angle"] = np.where(rng.random(n_f) < 0.8, kf_kps["angle"][twin] - 20 + rng.normal(0, 6, n_f),
+                              rng.uniform(0, 360, n_f)).astype(np.float32) % 360
+    valid = (rng.random(n_kf) < 0.8).astype(np.uint8)
+    return csr(kf_node), kf_desc, kf_kps, valid, csr(f_node), f_desc, f_kps
+
+
+@pytest.mark.parametrize("n_kf,n_f,nnodes,ori", [(2000, 2000, 100, True), (500, 700, 10, True), (300, 200, 1, False), (64, 64, 40, True)])
+def test_search_by_bow_vs_oracle(pkg, po, n_kf, n_f, nnodes, ori):
+    m = pkg.ORBmatcher(0.75, ori)
+    case = _bow_case(po, pkg, n_kf, n_f, nnodes, seed=n_kf + nnodes)
+    n, match = m.SearchByBoW(*case)
+    rn, rmatch = po.search_by_bow(*case, 0.75, ori)
+    assert rn > 5
+    assert n == rn and np.array_equal(match, rmatch)
+
+
+def test_search_by_bow_overlapping_nodes_serial_path(pkg, po):
+    """A frame feature listed under two nodes couples the nodes through the claim array: must still equal the sequential scan."""
+    m = pkg.ORBmatcher(0.75, True)
+    kfv, kd, kk, valid, ffv, fd, fk = _bow_case(po, pkg, 400, 400, 8, seed=3)
+    ids, start, items = ffv
+    items2 = np.concatenate([items, items[:50]])            # last node additionally lists the first 50 items
+    start2 = start.copy(); start2[-1] = len(items2)
+    ffv2 = (ids, start2, items2.astype(np.int32))
+    n, match = m.SearchByBoW(kfv, kd, kk, valid, ffv2, fd, fk)
+    rn, rmatch = po.search_by_bow(kfv, kd, kk, valid, ffv2, fd, fk, 0.75, True)
+    assert n == rn and np.array_equal(match, rmatch)
+
+
+def test_three_maxima_rule(po):
+    assert po.three_maxima([0] * 30) == (-1, -1, -1)
+    h = [0] * 30; h[3] = 100; h[5] = 9; h[7] = 50
+    assert po.three_maxima(h) == (3, 7, -1)                 # max3 < 0.1*max1 dropped
+    h[5] = 10
+    assert po.three_maxima(h) == (3, 7, 5)
