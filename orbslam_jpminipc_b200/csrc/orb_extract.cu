@@ -25,126 +25,189 @@ __device__ __forceinline__ int reflect101(int p, int len)
 }
 
 // ------------------------------------------------------------------ K0
+// Level 0: copy the caller's image into the ROI of the padded plane (the 16-px reflect-101 frame
+// of every level is written afterwards by k_border).  4 pixels per thread.
 __global__ void __launch_bounds__(256)
-k_level0(const uint8_t* __restrict__ src, int w, int h, int sstride, size_t spitch,
-         uint8_t* __restrict__ planes, size_t fbytes, int pstride, int prows)
+k_level0(const uint8_t* __restrict__ src, int w, int h, int sstride, size_t spitch, int aligned4,
+         uint8_t* __restrict__ planes, size_t fbytes, int pstride)
 {
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int f = blockIdx.z;
-    if (x4 >= pstride || y >= prows) return;
-    const uint8_t* S = src + (size_t)f * spitch + (size_t)reflect101(y - ORB_EDGE, h) * sstride;
-    uint32_t v = 0;
+    if (x4 >= w || y >= h) return;
+    const uint8_t* S = src + (size_t)f * spitch + (size_t)y * sstride + x4;
+    uint32_t v;
+    if (aligned4 && x4 + 3 < w) v = __ldg(reinterpret_cast<const uint32_t*>(S));
+    else {
+        v = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int x = x4 + k;
-        const uint32_t px = (x < w + 2 * ORB_EDGE) ? __ldg(S + reflect101(x - ORB_EDGE, w)) : 0u;
-        v |= px << (8 * k);
+        for (int k = 0; k < 4; k++) if (x4 + k < w) v |= (uint32_t)__ldg(S + k) << (8 * k);
     }
-    *reinterpret_cast<uint32_t*>(planes + (size_t)f * fbytes + (size_t)y * pstride + x4) = v;
+    // bytes past the right ROI edge (w not a multiple of 4) fall into the border and are rewritten by k_border
+    *reinterpret_cast<uint32_t*>(planes + (size_t)f * fbytes + (size_t)(y + ORB_EDGE) * pstride + ORB_EDGE + x4) = v;
 }
 
 // ------------------------------------------------------------------ K1
-// Each thread produces 4 horizontally adjacent pixels of the PADDED destination plane; border
-// pixels evaluate the resize at their reflected coordinate, which is what copyMakeBorder copies.
+// cv::resize(prev ROI -> this ROI, INTER_LINEAR), 8-bit fixed-point recipe (DESIGN.md "K1").
+// One CTA per 64x16 output tile: the source footprint is staged in shared memory with coalesced
+// 32-bit loads, the horizontal pass runs once per source row (shared by the two output rows that
+// use it), then the vertical pass writes 4 pixels per thread.
+constexpr int RT_W = 64, RT_H = 16;
+
 __global__ void __launch_bounds__(256)
 k_resize(uint8_t* __restrict__ planes, size_t fbytes, LevelGeom S, LevelGeom D,
-         const int2* __restrict__ xtab, const int2* __restrict__ ytab)
+         const int2* __restrict__ xtab, const int2* __restrict__ ytab, int src_words, int src_rows)
 {
-    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int f = blockIdx.z;
-    if (x4 >= D.stride || y >= D.prows) return;
+    extern __shared__ uint32_t rs_sm[];
+    uint32_t* simg = rs_sm;                                        // src_rows x src_words
+    int* Hs = reinterpret_cast<int*>(rs_sm + ((src_rows * src_words + 3) & ~3));  // src_rows x RT_W, 16-byte aligned
+    const int tid = threadIdx.x, f = blockIdx.y;
+    const int tiles_x = (D.w + RT_W - 1) / RT_W;
+    const int by = blockIdx.x / tiles_x, bx = blockIdx.x - by * tiles_x;
+    const int x0 = bx * RT_W, y0 = by * RT_H;
+    const int tw = min(RT_W, D.w - x0), thh = min(RT_H, D.h - y0);
+    const int2* xt = xtab + D.xtab_off + x0;
+    const int2* yt = ytab + D.ytab_off + y0;
+    const int sx_lo = (__ldg(&xt[0]).x & 0xffff) & ~3, sx_hi = __ldg(&xt[tw - 1]).x >> 16;
+    const int sy_lo = __ldg(&yt[0]).x & 0xffff, sy_hi = __ldg(&yt[thh - 1]).x >> 16;
+    const int nw = (sx_hi - sx_lo) / 4 + 1, nr = sy_hi - sy_lo + 1;
     uint8_t* base = planes + (size_t)f * fbytes;
     const uint8_t* sroi = base + S.plane_off + (size_t)ORB_EDGE * S.stride + ORB_EDGE;
-    const int2 yt = __ldg(ytab + D.ytab_off + reflect101(y - ORB_EDGE, D.h));
-    const uint8_t* S0 = sroi + (size_t)(yt.x & 0xffff) * S.stride;
-    const uint8_t* S1 = sroi + (size_t)(yt.x >> 16) * S.stride;
-    const int b0 = (short)(yt.y & 0xffff), b1 = (short)(yt.y >> 16);
+    for (int i = tid; i < nr * nw; i += 256) {
+        const int r = i / nw, c = i - r * nw;
+        simg[r * src_words + c] = *reinterpret_cast<const uint32_t*>(sroi + (size_t)(sy_lo + r) * S.stride + sx_lo + 4 * c);
+    }
+    __syncthreads();
+    {   // horizontal pass: S[sx0]*a0 + S[sx1]*a1 for every staged source row
+        const int dx = tid & 63;
+        if (dx < tw) {
+            const int2 e = __ldg(&xt[dx]);
+            const int c0 = (e.x & 0xffff) - sx_lo, c1 = (e.x >> 16) - sx_lo;
+            const int a0 = (short)(e.y & 0xffff), a1 = (short)(e.y >> 16);
+            const uint8_t* sb = reinterpret_cast<const uint8_t*>(simg);
+            for (int r = tid >> 6; r < nr; r += 4)
+                Hs[r * RT_W + dx] = sb[r * src_words * 4 + c0] * a0 + sb[r * src_words * 4 + c1] * a1;
+        }
+    }
+    __syncthreads();
+    {   // vertical pass: (((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2
+        const int ry = tid >> 4, gx = (tid & 15) * 4;
+        if (ry < thh && gx < tw) {
+            const int2 e = __ldg(&yt[ry]);
+            const int r0 = (e.x & 0xffff) - sy_lo, r1 = (e.x >> 16) - sy_lo;
+            const int b0 = (short)(e.y & 0xffff), b1 = (short)(e.y >> 16);
+            const int4 h0 = *reinterpret_cast<const int4*>(Hs + r0 * RT_W + gx);
+            const int4 h1 = *reinterpret_cast<const int4*>(Hs + r1 * RT_W + gx);
+            auto mix = [&](int s0, int s1) {
+                const int o = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+                return (uint32_t)min(max(o, 0), 255);
+            };
+            const uint32_t v = mix(h0.x, h1.x) | (mix(h0.y, h1.y) << 8) | (mix(h0.z, h1.z) << 16) | (mix(h0.w, h1.w) << 24);
+            // bytes past the right ROI edge fall into the border and are rewritten by k_border
+            *reinterpret_cast<uint32_t*>(base + D.plane_off + (size_t)(y0 + ry + ORB_EDGE) * D.stride + ORB_EDGE + x0 + gx) = v;
+        }
+    }
+}
+
+// copyMakeBorder(..., 16, BORDER_REFLECT_101) for every level of every frame in one launch
+// (reference src/ORBextractor.cc:806,814).  Only blur and the descriptor sampler read the frame;
+// resize, FAST and IC_Angle stay inside the ROI.  One thread per 32-bit word of the frame region.
+__global__ void __launch_bounds__(256)
+k_border(uint8_t* __restrict__ planes, size_t fbytes, const Plan* __restrict__ plan)
+{
+    int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= plan->border_total) return;
+    int l = 0;
+    while (l + 1 < plan->nlevels && item >= plan->L[l + 1].border_base) l++;
+    const LevelGeom& L = plan->L[l];
+    item -= L.border_base;
+    const int wpr = L.stride >> 2;                      // words per padded row
+    const int band = ORB_EDGE * wpr;                    // words in the top (or bottom) band
+    const int rw0 = (ORB_EDGE + L.w) >> 2;              // first word that contains right-frame pixels
+    const int side = 4 + (wpr - rw0);                   // frame words per middle row
+    int py, wx;
+    if (item < band) { py = item / wpr; wx = item - py * wpr; }
+    else if (item < 2 * band) { item -= band; py = item / wpr; wx = item - py * wpr; py += ORB_EDGE + L.h; }
+    else { item -= 2 * band; py = item / side; wx = item - py * side; py += ORB_EDGE; if (wx >= 4) wx = rw0 + (wx - 4); }
+    uint8_t* plane = planes + (size_t)blockIdx.y * fbytes + L.plane_off;
+    const uint8_t* srow = plane + (size_t)(reflect101(py - ORB_EDGE, L.h) + ORB_EDGE) * L.stride + ORB_EDGE;
     uint32_t v = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int x = x4 + k;
-        uint32_t px = 0;
-        if (x < D.w + 2 * ORB_EDGE) {
-            const int2 xt = __ldg(xtab + D.xtab_off + reflect101(x - ORB_EDGE, D.w));
-            const int sx0 = xt.x & 0xffff, sx1 = xt.x >> 16;
-            const int a0 = (short)(xt.y & 0xffff), a1 = (short)(xt.y >> 16);
-            const int r0 = S0[sx0] * a0 + S0[sx1] * a1;
-            const int r1 = S1[sx0] * a0 + S1[sx1] * a1;
-            int o = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
-            px = (uint32_t)min(max(o, 0), 255);
-        }
-        v |= px << (8 * k);
+        const int px = wx * 4 + k;
+        if (px < L.w + 2 * ORB_EDGE) v |= (uint32_t)srow[reflect101(px - ORB_EDGE, L.w)] << (8 * k);
     }
-    *reinterpret_cast<uint32_t*>(base + D.plane_off + (size_t)y * D.stride + x4) = v;
+    *reinterpret_cast<uint32_t*>(plane + (size_t)py * L.stride + wx * 4) = v;
 }
 
 // ------------------------------------------------------------------ K2
+// FAST-9/16 + per-cell NMS on a 64x32 tile.  Arithmetic is packed two pixels per register in
+// unsigned 16-bit lanes so the 9-of-16 arc tests run on VIMNMX3.U16x2 (3-input min/max):
+//   bright strength = max_k( min of ring[k..k+8] ) - v,   dark strength = v - min_k( max of ring[k..k+8] )
+// corner at threshold t  <=>  max(bright, dark) > t ;  OpenCV's response = that maximum - 1.
 constexpr int FT_W = ORB_TILE_W, FT_H = ORB_TILE_H;
-constexpr int FI_W = FT_W + 8, FI_H = FT_H + 8;       // image tile: 3 (ring) + 1 (NMS) px halo
-constexpr int FS_W = FT_W + 4, FS_H = FT_H + 2;       // score tile: 1 px halo (row pitch padded to 68)
+constexpr int FIW = 20, FI_H = FT_H + 8;   // image tile: 20 words (cols x0-8..x0+71) x rows y0-4..y0+35
+constexpr int FSW = 18, FS_H = FT_H + 2;   // score tile: 18 words (cols x0-4..x0+67) x rows y0-1..y0+32
+constexpr int FAST_THREADS = 320;
 
-// FAST-9/16 corner strength at p: max over the 16 arcs of 9 contiguous ring pixels of
-// min(v - ring) (dark arc) and min(ring - v) (bright arc).  corner at threshold t <=> result > t;
-// OpenCV's response is result-1.  Returns <= th when the quick test proves "not a corner".
-__device__ __forceinline__ int fast_strength(const uint8_t* p, int th)
+__device__ __forceinline__ uint32_t lo16x2(uint32_t w) { return __byte_perm(w, 0, 0x4140); }   // bytes 0,1 -> u16 lanes
+__device__ __forceinline__ uint32_t hi16x2(uint32_t w) { return __byte_perm(w, 0, 0x4342); }   // bytes 2,3 -> u16 lanes
+
+// ring[k] packed for two pixels -> (max over arcs of arc-min, min over arcs of arc-max), packed
+__device__ __forceinline__ void arc_minmax(const uint32_t (&r)[16], uint32_t& Mn, uint32_t& Mx)
 {
-    const int v = p[0];
-    int d[16];
-    d[0] = v - p[3 * FI_W];      d[8] = v - p[-3 * FI_W];
-    d[4] = v - p[3];             d[12] = v - p[-3];
-    // every 9-arc contains one of each opposite pair: need |d| > th on both tested pairs
-    if (max(abs(d[0]), abs(d[8])) <= th || max(abs(d[4]), abs(d[12])) <= th) return 0;
-    d[1] = v - p[3 * FI_W + 1];  d[2] = v - p[2 * FI_W + 2];   d[3] = v - p[FI_W + 3];
-    d[5] = v - p[-FI_W + 3];     d[6] = v - p[-2 * FI_W + 2];  d[7] = v - p[-3 * FI_W + 1];
-    d[9] = v - p[-3 * FI_W - 1]; d[10] = v - p[-2 * FI_W - 2]; d[11] = v - p[-FI_W - 3];
-    d[13] = v - p[FI_W - 3];     d[14] = v - p[2 * FI_W - 2];  d[15] = v - p[3 * FI_W - 1];
-    int mn2[16], mx2[16], mn4[16], mx4[16];
+    uint32_t a[16], b[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) { mn2[k] = min(d[k], d[(k + 1) & 15]); mx2[k] = max(d[k], d[(k + 1) & 15]); }
+    for (int k = 0; k < 16; k++) a[k] = __vimin3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
 #pragma unroll
-    for (int k = 0; k < 16; k++) { mn4[k] = min(mn2[k], mn2[(k + 2) & 15]); mx4[k] = max(mx2[k], mx2[(k + 2) & 15]); }
-    int best = -256, worst = 256;
+    for (int k = 0; k < 16; k++) b[k] = __vimin3_u16x2(a[k], a[(k + 3) & 15], a[(k + 6) & 15]);      // min of 9 contiguous
+    Mn = __vimax3_u16x2(__vimax3_u16x2(b[0], b[1], b[2]), __vimax3_u16x2(b[3], b[4], b[5]), __vimax3_u16x2(b[6], b[7], b[8]));
+    Mn = __vimax3_u16x2(Mn, __vimax3_u16x2(b[9], b[10], b[11]), __vimax3_u16x2(b[12], b[13], b[14]));
+    Mn = __vmaxu2(Mn, b[15]);
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
-        const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
-        best = max(best, mn9);
-        worst = min(worst, mx9);
-    }
-    return max(best, -worst);
+    for (int k = 0; k < 16; k++) a[k] = __vimax3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; k++) b[k] = __vimax3_u16x2(a[k], a[(k + 3) & 15], a[(k + 6) & 15]);      // max of 9 contiguous
+    Mx = __vimin3_u16x2(__vimin3_u16x2(b[0], b[1], b[2]), __vimin3_u16x2(b[3], b[4], b[5]), __vimin3_u16x2(b[6], b[7], b[8]));
+    Mx = __vimin3_u16x2(Mx, __vimin3_u16x2(b[9], b[10], b[11]), __vimin3_u16x2(b[12], b[13], b[14]));
+    Mx = __vminu2(Mx, b[15]);
 }
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ uint32_t score_of(int v, int mn, int mx, int th)
+{
+    const int s = max(mn - v, v - mx);
+    return s > th ? (uint32_t)(s - 1) : 0u;
+}
+
+__global__ void __launch_bounds__(FAST_THREADS)
 k_fast_nms(const uint8_t* __restrict__ planes, uint8_t* __restrict__ nms, size_t fbytes,
            const Plan* __restrict__ plan, const Tile* __restrict__ tiles)
 {
-    __shared__ __align__(16) uint8_t img[FI_H * FI_W];
-    __shared__ __align__(16) uint8_t sc[FS_H * FS_W];
-    __shared__ short colcell[FS_W], rowcell[FS_H];
+    __shared__ __align__(16) uint32_t img[FI_H * FIW];
+    __shared__ __align__(16) uint32_t sc[FS_H * FSW];
+    __shared__ short colcell[FSW * 4], rowcell[FS_H];
+    __shared__ __align__(4) uint8_t m_in[FSW * 4], m_l[FSW * 4], m_r[FSW * 4];
     const Tile t = tiles[blockIdx.x];
     const LevelGeom& L = plan->L[t.level];
     const int f = blockIdx.y, tid = threadIdx.x;
     const uint8_t* plane = planes + (size_t)f * fbytes + L.plane_off;
     const int th = plan->th_lo;
 
-    // image tile, origin (x0-4, y0-4) in ROI coords = (+16,+16) in padded coords; 32-bit loads
-    {
-        const int px0 = t.x0 - 4 + ORB_EDGE, py0 = t.y0 - 4 + ORB_EDGE;
-        for (int i = tid; i < FI_H * (FI_W / 4); i += 256) {
-            const int r = i / (FI_W / 4), cw = i - r * (FI_W / 4);
+    {   // image tile, origin (x0-8, y0-4) in ROI coordinates (+16 in padded coordinates; word aligned)
+        const int px0 = t.x0 - 8 + ORB_EDGE, py0 = t.y0 - 4 + ORB_EDGE;
+        for (int i = tid; i < FI_H * FIW; i += FAST_THREADS) {
+            const int r = i / FIW, cw = i - r * FIW;
             const int py = py0 + r, px = px0 + cw * 4;
             uint32_t v = 0;
             if (py < L.prows && px + 3 < L.stride) v = __ldg(reinterpret_cast<const uint32_t*>(plane + (size_t)py * L.stride + px));
-            reinterpret_cast<uint32_t*>(img)[i] = v;
+            img[i] = v;
         }
     }
-    // cell id of each score-tile column / row (-1: outside every detection rectangle)
-    if (tid < FS_W) {
-        const int x = t.x0 - 1 + tid;
+    // detection-cell id of every score-tile column / row (-1: outside every detection rectangle)
+    if (tid < FSW * 4) {
+        const int x = t.x0 - 4 + tid;
         int c = -1;
-        if (x >= ORB_EDGE && tid < FT_W + 2) {
+        if (x >= ORB_EDGE) {
             c = (x - ORB_EDGE) / L.cellW;
             if (c >= L.cols - 1) { c = L.cols - 1; if (x >= L.w - ORB_EDGE) c = -1; }
         }
@@ -159,39 +222,94 @@ k_fast_nms(const uint8_t* __restrict__ planes, uint8_t* __restrict__ nms, size_t
         rowcell[i] = (short)c;
     }
     __syncthreads();
-    // corner strength for the (FT_H+2) x (FT_W+2) positions
-    for (int i = tid; i < FS_H * (FT_W + 2); i += 256) {
-        const int r = i / (FT_W + 2), c = i - r * (FT_W + 2);
-        int s = 0;
-        if (colcell[c] >= 0 && rowcell[r] >= 0) {
-            s = fast_strength(img + (r + 3) * FI_W + (c + 3), th);
-            s = s > th ? s - 1 : 0;
-        }
-        sc[r * FS_W + c] = (uint8_t)s;
+    if (tid < FSW * 4) {          // byte masks: in region / left neighbour in same cell / right neighbour in same cell
+        const int c = colcell[tid];
+        m_in[tid] = c >= 0 ? 0xff : 0;
+        m_l[tid] = (tid > 0 && c >= 0 && colcell[tid - 1] == c) ? 0xff : 0;
+        m_r[tid] = (tid < FSW * 4 - 1 && c >= 0 && colcell[tid + 1] == c) ? 0xff : 0;
     }
     __syncthreads();
-    // NMS restricted to the pixel's own cell; 4 pixels per thread, one 32-bit store
-    uint8_t* out = nms + (size_t)f * fbytes + L.plane_off;
-    for (int i = tid; i < FT_H * (FT_W / 4); i += 256) {
-        const int r = i / (FT_W / 4), c4 = (i - r * (FT_W / 4)) * 4;
-        uint32_t v = 0;
-        const int rc = rowcell[r + 1];
+
+    // ---- corner strength: one task = 4 horizontally adjacent pixels ----
+    for (int task = tid; task < FS_H * FSW; task += FAST_THREADS) {
+        const int r = task / FSW, g = task - r * FSW;
+        const uint32_t cm = reinterpret_cast<const uint32_t*>(m_in)[g];
+        uint32_t outw = 0;
+        if (cm != 0 && rowcell[r] >= 0) {
+            const uint32_t* ip = img + r * FIW + g;              // rows r..r+6 (y-3..y+3), words g..g+2
+            uint32_t w0[7], w1[7], w2[7];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int c = c4 + k;
-            const uint8_t* q = sc + (r + 1) * FS_W + (c + 1);
-            const int s = q[0];
-            if (s == 0) continue;
-            const int cc = colcell[c + 1];
-            const bool l = colcell[c] == cc, rt = colcell[c + 2] == cc;
-            const bool u = rowcell[r] == rc, dn = rowcell[r + 2] == rc;
-            bool keep = true;
-            keep = keep && !(l && q[-1] >= s) && !(rt && q[1] >= s);
-            keep = keep && !(u && (q[-FS_W] >= s || (l && q[-FS_W - 1] >= s) || (rt && q[-FS_W + 1] >= s)));
-            keep = keep && !(dn && (q[FS_W] >= s || (l && q[FS_W - 1] >= s) || (rt && q[FS_W + 1] >= s)));
-            if (keep) v |= (uint32_t)s << (8 * k);
+            for (int q = 0; q < 7; q++) { w0[q] = ip[q * FIW]; w1[q] = ip[q * FIW + 1]; w2[q] = ip[q * FIW + 2]; }
+            // the 16 ring positions as 4-byte windows (pixel x..x+3 shifted by dx) in OpenCV's ring order
+            uint32_t rw[16];
+            rw[0]  = w1[6];                                   // ( 0, 3)
+            rw[1]  = __funnelshift_r(w1[6], w2[6], 8);        // ( 1, 3)
+            rw[2]  = __funnelshift_r(w1[5], w2[5], 16);       // ( 2, 2)
+            rw[3]  = __funnelshift_r(w1[4], w2[4], 24);       // ( 3, 1)
+            rw[4]  = __funnelshift_r(w1[3], w2[3], 24);       // ( 3, 0)
+            rw[5]  = __funnelshift_r(w1[2], w2[2], 24);       // ( 3,-1)
+            rw[6]  = __funnelshift_r(w1[1], w2[1], 16);       // ( 2,-2)
+            rw[7]  = __funnelshift_r(w1[0], w2[0], 8);        // ( 1,-3)
+            rw[8]  = w1[0];                                   // ( 0,-3)
+            rw[9]  = __funnelshift_r(w0[0], w1[0], 24);       // (-1,-3)
+            rw[10] = __funnelshift_r(w0[1], w1[1], 16);       // (-2,-2)
+            rw[11] = __funnelshift_r(w0[2], w1[2], 8);        // (-3,-1)
+            rw[12] = __funnelshift_r(w0[3], w1[3], 8);        // (-3, 0)
+            rw[13] = __funnelshift_r(w0[4], w1[4], 8);        // (-3, 1)
+            rw[14] = __funnelshift_r(w0[5], w1[5], 16);       // (-2, 2)
+            rw[15] = __funnelshift_r(w0[6], w1[6], 24);       // (-1, 3)
+            const uint32_t cw = w1[3];
+            uint32_t ring[16], Mn, Mx;
+#pragma unroll
+            for (int k = 0; k < 16; k++) ring[k] = lo16x2(rw[k]);
+            arc_minmax(ring, Mn, Mx);
+            outw = score_of(cw & 0xff, Mn & 0xffff, Mx & 0xffff, th) | (score_of((cw >> 8) & 0xff, Mn >> 16, Mx >> 16, th) << 8);
+#pragma unroll
+            for (int k = 0; k < 16; k++) ring[k] = hi16x2(rw[k]);
+            arc_minmax(ring, Mn, Mx);
+            outw |= (score_of((cw >> 16) & 0xff, Mn & 0xffff, Mx & 0xffff, th) << 16) | (score_of(cw >> 24, Mn >> 16, Mx >> 16, th) << 24);
+            outw &= cm;
         }
-        const int py = t.y0 + r + ORB_EDGE, px = t.x0 + c4 + ORB_EDGE;
+        sc[task] = outw;
+    }
+    __syncthreads();
+
+    // ---- NMS restricted to the pixel's own cell: one task = 4 output pixels, one 32-bit store ----
+    uint8_t* out = nms + (size_t)f * fbytes + L.plane_off;
+    for (int task = tid; task < FT_H * (FT_W / 4); task += FAST_THREADS) {
+        const int ro = task / (FT_W / 4), go = task - ro * (FT_W / 4);
+        const int r = ro + 1, g = go + 1;
+        const uint32_t* sp = sc + r * FSW + g;
+        const uint32_t c = sp[0];
+        uint32_t v = 0;
+        if (c) {
+            const uint32_t ml = reinterpret_cast<const uint32_t*>(m_l)[g], mr = reinterpret_cast<const uint32_t*>(m_r)[g];
+            const int rc = rowcell[r];
+            const bool up = rowcell[r - 1] == rc, dn = rowcell[r + 1] == rc;
+            uint32_t nb[8];
+            nb[0] = __funnelshift_r(sp[-1], c, 24) & ml;
+            nb[1] = __funnelshift_r(c, sp[1], 8) & mr;
+            const uint32_t ul = sp[-FSW - 1], uc = sp[-FSW], ur = sp[-FSW + 1];
+            nb[2] = up ? uc : 0u;
+            nb[3] = up ? (__funnelshift_r(ul, uc, 24) & ml) : 0u;
+            nb[4] = up ? (__funnelshift_r(uc, ur, 8) & mr) : 0u;
+            const uint32_t dl = sp[FSW - 1], dc = sp[FSW], dr = sp[FSW + 1];
+            nb[5] = dn ? dc : 0u;
+            nb[6] = dn ? (__funnelshift_r(dl, dc, 24) & ml) : 0u;
+            nb[7] = dn ? (__funnelshift_r(dc, dr, 8) & mr) : 0u;
+            uint32_t mlo = __vimax3_u16x2(__vimax3_u16x2(lo16x2(nb[0]), lo16x2(nb[1]), lo16x2(nb[2])),
+                                          __vimax3_u16x2(lo16x2(nb[3]), lo16x2(nb[4]), lo16x2(nb[5])),
+                                          __vmaxu2(lo16x2(nb[6]), lo16x2(nb[7])));
+            uint32_t mhi = __vimax3_u16x2(__vimax3_u16x2(hi16x2(nb[0]), hi16x2(nb[1]), hi16x2(nb[2])),
+                                          __vimax3_u16x2(hi16x2(nb[3]), hi16x2(nb[4]), hi16x2(nb[5])),
+                                          __vmaxu2(hi16x2(nb[6]), hi16x2(nb[7])));
+            const uint32_t s0 = c & 0xff, s1 = (c >> 8) & 0xff, s2 = (c >> 16) & 0xff, s3 = c >> 24;
+            if (s0 > (mlo & 0xffff)) v |= s0;            // strictly greater than all 8 neighbours; s == 0 never passes
+            if (s1 > (mlo >> 16)) v |= s1 << 8;
+            if (s2 > (mhi & 0xffff)) v |= s2 << 16;
+            if (s3 > (mhi >> 16)) v |= s3 << 24;
+        }
+        const int py = t.y0 + ro + ORB_EDGE, px = t.x0 + go * 4 + ORB_EDGE;
         if (py < L.prows && px + 3 < L.stride)
             *reinterpret_cast<uint32_t*>(out + (size_t)py * L.stride + px) = v;
     }
@@ -200,9 +318,10 @@ k_fast_nms(const uint8_t* __restrict__ planes, uint8_t* __restrict__ nms, size_t
 // ------------------------------------------------------------------ K3
 // One warp per (frame, cell): scans the cell's detection rectangle of the NMS map in raster
 // order and appends survivors with ballot/popc prefix sums, so the list order is exactly the
-// order cv::FAST emits (y, then x).  Then applies the reference's fallback: if fewer than 4
-// survive at fastTh the cell is re-detected at threshold 7 (src/ORBextractor.cc:609-614) —
-// both sets are sub-sequences of the th_lo list ("one-pass fallback").
+// order cv::FAST emits (y, then x).  Each lane reads 4 pixels (one 32-bit word) per step.  Then
+// applies the reference's fallback: if fewer than 4 survive at fastTh the cell is re-detected at
+// threshold 7 (src/ORBextractor.cc:609-614) — both sets are sub-sequences of the th_lo list
+// ("one-pass fallback").
 // record = score<<24 | y_local<<12 | x_local   (cell-image coordinates, as cv::FAST reports)
 __global__ void __launch_bounds__(256)
 k_cell_compact(const uint8_t* __restrict__ nms, size_t fbytes, const Plan* __restrict__ plan,
@@ -218,18 +337,35 @@ k_cell_compact(const uint8_t* __restrict__ nms, size_t fbytes, const Plan* __res
     const int thP = plan->fast_th;
     int count = 0, nP = 0, n7 = 0;
     const uint32_t lt = (1u << lane) - 1;
+    const int xa = g.x0 & ~3;
     for (int y = g.y0; y < g.y1; y++) {
         const uint8_t* row = map + (size_t)y * L.stride;
-        for (int xb = g.x0; xb < g.x1; xb += 32) {
-            const int x = xb + lane;
-            const int s = x < g.x1 ? row[x] : 0;
-            const uint32_t m = __ballot_sync(0xffffffffu, s > 0);
-            if (s > 0) out[count + __popc(m & lt)] = ((uint32_t)s << 24) | ((uint32_t)(y - g.iniy) << 12) | (uint32_t)(x - g.inix);
-            count += __popc(m);
-            nP += __popc(__ballot_sync(0xffffffffu, s >= thP));
-            n7 += __popc(__ballot_sync(0xffffffffu, s >= 7));
+        for (int xb = xa; xb < g.x1; xb += 128) {
+            const int x = xb + 4 * lane;
+            uint32_t wv = 0;
+            if (x < g.x1) wv = *reinterpret_cast<const uint32_t*>(row + x);
+            uint32_t s[4];
+            bool nz[4];
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                s[b] = (wv >> (8 * b)) & 0xff;
+                if (x + b < g.x0 || x + b >= g.x1) s[b] = 0;
+                nz[b] = s[b] != 0;
+                nP += (int)s[b] >= thP;
+                n7 += s[b] >= 7;
+            }
+            const uint32_t m0 = __ballot_sync(0xffffffffu, nz[0]), m1 = __ballot_sync(0xffffffffu, nz[1]);
+            const uint32_t m2 = __ballot_sync(0xffffffffu, nz[2]), m3 = __ballot_sync(0xffffffffu, nz[3]);
+            if ((m0 | m1 | m2 | m3) == 0) continue;
+            int pos = count + __popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt);
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                if (nz[b]) out[pos++] = (s[b] << 24) | ((uint32_t)(y - g.iniy) << 12) | (uint32_t)(x + b - g.inix);
+            count += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
         }
     }
+    nP = __reduce_add_sync(0xffffffffu, nP);
+    n7 = __reduce_add_sync(0xffffffffu, n7);
     const int thr = nP > 3 ? thP : 7;
     const int want = nP > 3 ? nP : n7;
     if (want < count) {           // drop the weaker corners, keeping raster order (in place, warp-synchronous)
@@ -324,15 +460,25 @@ k_select(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells, uint
 // 7x7 sigma=2 Gaussian, the FP32 separable path OpenCV 4.x takes for an 8-bit non-isolated
 // sub-matrix (DESIGN.md "K5"): row pass s = fma(I[x+i-3], k[i], s) from s = 0, column pass
 // s = k3*R[y]; s = fma(R[y+d]+R[y-d], k[3+d], s), d = 1..3; round-half-even, saturate.
-constexpr int BT_W = ORB_TILE_W, BT_H = ORB_TILE_H;
-constexpr int BI_W = BT_W + 8, BI_H = BT_H + 6;      // input tile: 3 px halo (4 on x for alignment)
+// The order of the FMAs is part of the result, so the kernel keeps it; what it avoids are the
+// slow conversion instructions: u8 -> f32 is PRMT into the mantissa of 2^23 followed by an exact
+// FADD, f32 -> u8 is the 1.5*2^23 magic add (round-to-nearest-even by the FP adder).
+constexpr int BT_W = ORB_BLUR_TILE_W, BT_H = ORB_BLUR_TILE_H;   // 64 x 56 outputs per CTA
+constexpr int BIW = 18;                       // input tile words per row: cols x0-4 .. x0+67
+constexpr int BI_H = BT_H + 6;                // rows y0-3 .. y0+BT_H+2
+
+__device__ __forceinline__ float u8f(uint32_t w, int j)     // byte j of w as float, no I2F
+{
+    const uint32_t sel = 0x7440u | (uint32_t)j;
+    return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, sel)), 8388608.0f);
+}
 
 __global__ void __launch_bounds__(256)
 k_blur(const uint8_t* __restrict__ planes, uint8_t* __restrict__ blurred, size_t fbytes,
        const Plan* __restrict__ plan, const Tile* __restrict__ tiles)
 {
-    __shared__ __align__(16) uint8_t img[BI_H * BI_W];
-    __shared__ float rowp[BI_H * BT_W];
+    __shared__ __align__(16) uint32_t img[BI_H * BIW];
+    __shared__ __align__(16) float rowp[BI_H * BT_W];
     const float k0 = __uint_as_float(0x3d8fafb1u), k1 = __uint_as_float(0x3e06387eu),
                 k2 = __uint_as_float(0x3e434a39u), k3 = __uint_as_float(0x3e5d4ae0u);
     const Tile t = tiles[blockIdx.x];
@@ -341,41 +487,66 @@ k_blur(const uint8_t* __restrict__ planes, uint8_t* __restrict__ blurred, size_t
     const uint8_t* plane = planes + (size_t)f * fbytes + L.plane_off;
     {
         const int px0 = t.x0 - 4 + ORB_EDGE, py0 = t.y0 - 3 + ORB_EDGE;
-        for (int i = tid; i < BI_H * (BI_W / 4); i += 256) {
-            const int r = i / (BI_W / 4), cw = i - r * (BI_W / 4);
+        for (int i = tid; i < BI_H * BIW; i += 256) {
+            const int r = i / BIW, cw = i - r * BIW;
             const int py = py0 + r, px = px0 + cw * 4;
             uint32_t v = 0;
             if (py < L.prows && px + 3 < L.stride) v = __ldg(reinterpret_cast<const uint32_t*>(plane + (size_t)py * L.stride + px));
-            reinterpret_cast<uint32_t*>(img)[i] = v;
+            img[i] = v;
         }
     }
     __syncthreads();
-    for (int i = tid; i < BI_H * BT_W; i += 256) {
-        const int r = i / BT_W, c = i - r * BT_W;
-        const uint8_t* p = img + r * BI_W + c + 1;          // p[0] = column c-3
-        float s = __fmul_rn((float)p[0], k0);
-        s = fmaf((float)p[1], k1, s); s = fmaf((float)p[2], k2, s); s = fmaf((float)p[3], k3, s);
-        s = fmaf((float)p[4], k2, s); s = fmaf((float)p[5], k1, s); s = fmaf((float)p[6], k0, s);
-        rowp[i] = s;
-    }
-    __syncthreads();
-    uint8_t* out = blurred + (size_t)f * fbytes + L.plane_off;
-    for (int i = tid; i < BT_H * (BT_W / 4); i += 256) {
-        const int r = i / (BT_W / 4), c4 = (i - r * (BT_W / 4)) * 4;
-        uint32_t v = 0;
+    // row pass: one task = 8 adjacent outputs of one row (needs input bytes 8*seg+1 .. 8*seg+14 of the tile row)
+    for (int task = tid; task < BI_H * (BT_W / 8); task += 256) {
+        const int r = task >> 3, seg = task & 7;
+        const uint2* ip = reinterpret_cast<const uint2*>(img + r * BIW + 2 * seg);
+        const uint2 a = ip[0], b = ip[1];
+        float v[14];
+        v[0] = u8f(a.x, 1); v[1] = u8f(a.x, 2); v[2] = u8f(a.x, 3);
+        v[3] = u8f(a.y, 0); v[4] = u8f(a.y, 1); v[5] = u8f(a.y, 2); v[6] = u8f(a.y, 3);
+        v[7] = u8f(b.x, 0); v[8] = u8f(b.x, 1); v[9] = u8f(b.x, 2); v[10] = u8f(b.x, 3);
+        v[11] = u8f(b.y, 0); v[12] = u8f(b.y, 1); v[13] = u8f(b.y, 2);
+        float o[8];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const float* q = rowp + (r + 3) * BT_W + c4 + k;
-            float s = __fmul_rn(k3, q[0]);
-            s = fmaf(__fadd_rn(q[BT_W], q[-BT_W]), k2, s);
-            s = fmaf(__fadd_rn(q[2 * BT_W], q[-2 * BT_W]), k1, s);
-            s = fmaf(__fadd_rn(q[3 * BT_W], q[-3 * BT_W]), k0, s);
-            const int o = min(max(__float2int_rn(s), 0), 255);
-            v |= (uint32_t)o << (8 * k);
+        for (int q = 0; q < 8; q++) {
+            float s = __fmul_rn(v[q], k0);
+            s = fmaf(v[q + 1], k1, s); s = fmaf(v[q + 2], k2, s); s = fmaf(v[q + 3], k3, s);
+            s = fmaf(v[q + 4], k2, s); s = fmaf(v[q + 5], k1, s); s = fmaf(v[q + 6], k0, s);
+            o[q] = s;
         }
-        const int y = t.y0 + r, x = t.x0 + c4;
-        if (y < L.h && x < L.w)      // pixels past the ROI edge land in the border, which is never read from here
-            *reinterpret_cast<uint32_t*>(out + (size_t)(y + ORB_EDGE) * L.stride + x + ORB_EDGE) = v;
+        float4* op = reinterpret_cast<float4*>(rowp + r * BT_W + 8 * seg);
+        op[0] = make_float4(o[0], o[1], o[2], o[3]);
+        op[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+    __syncthreads();
+    // column pass: one task = 4 columns x 4 rows of outputs (10 row-pass rows, float4 loads)
+    uint8_t* out = blurred + (size_t)f * fbytes + L.plane_off;
+    for (int task = tid; task < (BT_W / 4) * (BT_H / 4); task += 256) {
+        const int cg = task & 15, rg = task >> 4;
+        const float4* rp = reinterpret_cast<const float4*>(rowp + (rg * 4) * BT_W + cg * 4);
+        float4 R[10];
+#pragma unroll
+        for (int q = 0; q < 10; q++) R[q] = rp[q * (BT_W / 4)];
+        const int x = t.x0 + cg * 4;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int y = t.y0 + rg * 4 + q;
+            uint32_t w = 0;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+#define RV(i) (e == 0 ? R[i].x : e == 1 ? R[i].y : e == 2 ? R[i].z : R[i].w)
+                float s = __fmul_rn(k3, RV(q + 3));
+                s = fmaf(__fadd_rn(RV(q + 4), RV(q + 2)), k2, s);
+                s = fmaf(__fadd_rn(RV(q + 5), RV(q + 1)), k1, s);
+                s = fmaf(__fadd_rn(RV(q + 6), RV(q)), k0, s);
+#undef RV
+                // rint via the 1.5*2^23 magic constant (0 <= s < 2^22), then saturate to 255
+                const uint32_t iv = min(__float_as_uint(__fadd_rn(s, 12582912.0f)) & 0x3ffu, 255u);
+                w |= iv << (8 * e);
+            }
+            if (y < L.h && x < L.w)      // bytes past the ROI edge land in the border of the blurred plane, which is never read
+                *reinterpret_cast<uint32_t*>(out + (size_t)(y + ORB_EDGE) * L.stride + x + ORB_EDGE) = w;
+        }
     }
 }
 
@@ -516,19 +687,23 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w, int h
     mark();
     {
         const LevelGeom& L = P.L[0];
-        dim3 grid((L.stride / 4 + 63) / 64, (L.prows + 3) / 4, nimg);
-        k_level0<<<grid, blk, 0, s>>>(d_imgs, w, h, stride, frame_pitch, c->d_planes, fb, L.stride, L.prows);
+        dim3 grid((w + 255) / 256, (h + 3) / 4, nimg);
+        const int aligned4 = (((uintptr_t)d_imgs | (uintptr_t)stride | (uintptr_t)frame_pitch) & 3) == 0;
+        k_level0<<<grid, blk, 0, s>>>(d_imgs, w, h, stride, frame_pitch, aligned4, c->d_planes, fb, L.stride);
         launches++;
     }
     mark();
     for (int l = 1; l < P.nlevels; l++) {
         const LevelGeom& D = P.L[l];
-        dim3 grid((D.stride / 4 + 63) / 64, (D.prows + 3) / 4, nimg);
-        k_resize<<<grid, blk, 0, s>>>(c->d_planes, fb, P.L[l - 1], D, c->d_xtab, c->d_ytab);
+        const int tiles = ((D.w + RT_W - 1) / RT_W) * ((D.h + RT_H - 1) / RT_H);
+        const size_t sm = ((((size_t)c->rs_rows[l] * c->rs_words[l] + 3) & ~(size_t)3) + (size_t)c->rs_rows[l] * RT_W) * 4;
+        k_resize<<<dim3(tiles, nimg), 256, sm, s>>>(c->d_planes, fb, P.L[l - 1], D, c->d_xtab, c->d_ytab, c->rs_words[l], c->rs_rows[l]);
         launches++;
     }
+    k_border<<<dim3((P.border_total + 255) / 256, nimg), 256, 0, s>>>(c->d_planes, fb, c->d_plan);
+    launches++;
     mark();
-    k_fast_nms<<<dim3(P.ntiles_fast, nimg), 256, 0, s>>>(c->d_planes, c->d_work, fb, c->d_plan, c->d_tiles_fast);
+    k_fast_nms<<<dim3(P.ntiles_fast, nimg), FAST_THREADS, 0, s>>>(c->d_planes, c->d_work, fb, c->d_plan, c->d_tiles_fast);
     mark();
     k_cell_compact<<<dim3((P.ncells + 7) / 8, nimg), 256, 0, s>>>(c->d_work, fb, c->d_plan, c->d_cells, c->d_cand, c->d_ntotal);
     mark();
@@ -545,6 +720,12 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w, int h
     launches += 5;
     c->last_launches = launches;
     ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
+}
+
+int orb_resize_smem_setup(int max_bytes)
+{
+    ORB_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
     return ORB_OK;
 }
 

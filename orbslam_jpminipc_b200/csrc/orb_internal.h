@@ -12,6 +12,8 @@
 #define ORB_EDGE 16                // EDGE_THRESHOLD, reference src/ORBextractor.cc:77
 #define ORB_TILE_W 64
 #define ORB_TILE_H 32
+#define ORB_BLUR_TILE_W 64
+#define ORB_BLUR_TILE_H 56
 
 // Geometry of one pyramid level for one image shape (reference src/ORBextractor.cc:527-547,:786).
 struct LevelGeom {
@@ -28,6 +30,7 @@ struct LevelGeom {
     float scale;           // mvScaleFactor[level]
     int xtab_off, ytab_off;// offsets into the resize coefficient tables (int2 entries)
     int kp_base;           // prefix of nDesired over levels (unused slots stay empty)
+    int border_base;       // first k_border work item of this level
 };
 
 struct Plan {
@@ -39,6 +42,7 @@ struct Plan {
     int kp_cap;            // sum of nDesired
     int fast_th, th_lo;
     int ntiles_fast, ntiles_blur;
+    int border_total;      // k_border work items (32-bit words of all frame regions) per image
     LevelGeom L[ORB_MAX_LEVELS];
 };
 
@@ -70,6 +74,7 @@ struct orb_ctx {
     std::vector<CellGeom> cells;
     std::vector<Tile> tiles_fast, tiles_blur;
     std::vector<int2> xtab, ytab;
+    int rs_words[ORB_MAX_LEVELS] = { 0 }, rs_rows[ORB_MAX_LEVELS] = { 0 };   // k_resize source footprint per level
 
     // device buffers
     Plan* d_plan = nullptr;
@@ -115,6 +120,7 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w, int h
                        orb_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts, cudaStream_t s);
 int orb_upload_constants(const int* umax);
 int orb_select_smem_setup(int max_bytes);
+int orb_resize_smem_setup(int max_bytes);
 // orb_match.cu
 int orb_launch_knn2(orb_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_db, int64_t ndb, int npairs, int32_t idx_base,
                     int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, cudaStream_t s);

@@ -86,7 +86,7 @@ int orb_build_plan(orb_ctx* c, int w, int h)
     P.fast_th = c->fast_th; P.th_lo = std::min(c->fast_th, 7);
     c->cells.clear(); c->tiles_fast.clear(); c->tiles_blur.clear(); c->xtab.clear(); c->ytab.clear();
 
-    int off = 0, cand = 0, lvl = 0, kp = 0;
+    int off = 0, cand = 0, lvl = 0, kp = 0, border = 0;
     const float imageRatio = (float)w / h;                                   // :527
     for (int l = 0; l < P.nlevels; l++) {
         LevelGeom& L = P.L[l];
@@ -103,7 +103,22 @@ int orb_build_plan(orb_ctx* c, int w, int h)
         if (l > 0) {
             axis_table(P.L[l - 1].w, L.w, true, c->xtab);
             axis_table(P.L[l - 1].h, L.h, false, c->ytab);
+            // largest source footprint of a 64x16 output tile (k_resize shared-memory staging)
+            int mw = 1, mr = 1;
+            for (int x0 = 0; x0 < L.w; x0 += 64) {
+                const int x1 = std::min(x0 + 64, L.w) - 1;
+                const int lo = (c->xtab[L.xtab_off + x0].x & 0xffff) & ~3, hi = c->xtab[L.xtab_off + x1].x >> 16;
+                mw = std::max(mw, (hi - lo) / 4 + 1);
+            }
+            for (int y0 = 0; y0 < L.h; y0 += 16) {
+                const int y1 = std::min(y0 + 16, L.h) - 1;
+                mr = std::max(mr, (c->ytab[L.ytab_off + y1].x >> 16) - (c->ytab[L.ytab_off + y0].x & 0xffff) + 1);
+            }
+            c->rs_words[l] = mw; c->rs_rows[l] = mr;
+            if (((size_t)mr * mw + (size_t)mr * 64) * 4 > 200 * 1024) return ORB_ERR_CAPACITY;
         }
+        L.border_base = border;
+        border += 2 * ORB_EDGE * (L.stride / 4) + L.h * (4 + L.stride / 4 - (ORB_EDGE + L.w) / 4);
         // cell grid (:531-547)
         L.nDesired = c->mnFeaturesPerLevel[l];
         L.cols = (int)sqrtf((float)L.nDesired / (5 * imageRatio));
@@ -154,14 +169,15 @@ int orb_build_plan(orb_ctx* c, int w, int h)
         kp += L.nDesired;
         for (int y = minB; y < L.yend; y += ORB_TILE_H)
             for (int x = minB; x < L.xend; x += ORB_TILE_W) c->tiles_fast.push_back(Tile{ l, x, y, 0 });
-        for (int y = 0; y < L.h; y += ORB_TILE_H)
-            for (int x = 0; x < L.w; x += ORB_TILE_W) c->tiles_blur.push_back(Tile{ l, x, y, 0 });
+        for (int y = 0; y < L.h; y += ORB_BLUR_TILE_H)
+            for (int x = 0; x < L.w; x += ORB_BLUR_TILE_W) c->tiles_blur.push_back(Tile{ l, x, y, 0 });
     }
     P.frame_bytes = off;
     P.ncells = (int)c->cells.size();
     P.cand_total = cand;
     P.lvl_total = lvl;
     P.kp_cap = kp;
+    P.border_total = border;
     P.ntiles_fast = (int)c->tiles_fast.size();
     P.ntiles_blur = (int)c->tiles_blur.size();
     return ORB_OK;   // device upload happens in orb_api.cu
