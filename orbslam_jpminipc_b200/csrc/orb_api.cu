@@ -55,8 +55,8 @@ static int prepare(orb_ctx* c, int w, int h, int nimg)
         if (!c->ytab.empty()) ORB_CUDA(cudaMemcpy(c->d_ytab, c->ytab.data(), c->ytab.size() * sizeof(int2), cudaMemcpyHostToDevice));
         int maxcap = 0;
         for (int l = 0; l < c->plan.nlevels; l++) maxcap = std::max(maxcap, c->plan.L[l].lvl_cap);
-        if ((size_t)maxcap * 8 > 200 * 1024) return ORB_ERR_CAPACITY;
-        rc = orb_select_smem_setup(std::max(maxcap * 8, 1024)); if (rc) return rc;
+        if ((size_t)maxcap * 8 > 170 * 1024) return ORB_ERR_CAPACITY;
+        rc = orb_select_smem_setup(maxcap * 8 + 6144 * 4 + 1024); if (rc) return rc;
         size_t rsm = 1024;
         for (int l = 1; l < c->plan.nlevels; l++) rsm = std::max(rsm, ((size_t)c->rs_rows[l] * c->rs_words[l] + 4 + (size_t)c->rs_rows[l] * 64) * 4);
         rc = orb_resize_smem_setup((int)rsm); if (rc) return rc;

@@ -49,63 +49,62 @@ k_level0(const uint8_t* __restrict__ src, int w, int h, int sstride, size_t spit
 
 // ------------------------------------------------------------------ K1
 // cv::resize(prev ROI -> this ROI, INTER_LINEAR), 8-bit fixed-point recipe (DESIGN.md "K1").
-// One CTA per 64x16 output tile: the source footprint is staged in shared memory with coalesced
-// 32-bit loads, the horizontal pass runs once per source row (shared by the two output rows that
-// use it), then the vertical pass writes 4 pixels per thread.
-constexpr int RT_W = 64, RT_H = 16;
+// A thread owns 4 adjacent output columns (their source offsets and weights stay in registers) and
+// walks down RS_ROWS output rows; the horizontal pass of a source row is kept in registers and
+// reused when the next output row needs the same source row (at scale 1.2 that is 4 rows in 5).
+constexpr int RS_ROWS = 8;
 
 __global__ void __launch_bounds__(256)
 k_resize(uint8_t* __restrict__ planes, size_t fbytes, LevelGeom S, LevelGeom D,
-         const int2* __restrict__ xtab, const int2* __restrict__ ytab, int src_words, int src_rows)
+         const int2* __restrict__ xtab, const int2* __restrict__ ytab)
 {
-    extern __shared__ uint32_t rs_sm[];
-    uint32_t* simg = rs_sm;                                        // src_rows x src_words
-    int* Hs = reinterpret_cast<int*>(rs_sm + ((src_rows * src_words + 3) & ~3));  // src_rows x RT_W, 16-byte aligned
-    const int tid = threadIdx.x, f = blockIdx.y;
-    const int tiles_x = (D.w + RT_W - 1) / RT_W;
-    const int by = blockIdx.x / tiles_x, bx = blockIdx.x - by * tiles_x;
-    const int x0 = bx * RT_W, y0 = by * RT_H;
-    const int tw = min(RT_W, D.w - x0), thh = min(RT_H, D.h - y0);
-    const int2* xt = xtab + D.xtab_off + x0;
-    const int2* yt = ytab + D.ytab_off + y0;
-    const int sx_lo = (__ldg(&xt[0]).x & 0xffff) & ~3, sx_hi = __ldg(&xt[tw - 1]).x >> 16;
-    const int sy_lo = __ldg(&yt[0]).x & 0xffff, sy_hi = __ldg(&yt[thh - 1]).x >> 16;
-    const int nw = (sx_hi - sx_lo) / 4 + 1, nr = sy_hi - sy_lo + 1;
+    const int gx = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;          // first of 4 output columns
+    const int y0 = (blockIdx.y * 4 + (threadIdx.x >> 6)) * RS_ROWS;     // first output row of this thread
+    const int f = blockIdx.z;
+    if (gx >= D.w || y0 >= D.h) return;
     uint8_t* base = planes + (size_t)f * fbytes;
     const uint8_t* sroi = base + S.plane_off + (size_t)ORB_EDGE * S.stride + ORB_EDGE;
-    for (int i = tid; i < nr * nw; i += 256) {
-        const int r = i / nw, c = i - r * nw;
-        simg[r * src_words + c] = *reinterpret_cast<const uint32_t*>(sroi + (size_t)(sy_lo + r) * S.stride + sx_lo + 4 * c);
+    int c0[4], c1[4], a0[4], a1[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int2 e = __ldg(xtab + D.xtab_off + min(gx + k, D.w - 1));
+        c0[k] = e.x & 0xffff; c1[k] = e.x >> 16;
+        a0[k] = (short)(e.y & 0xffff); a1[k] = (short)(e.y >> 16);
     }
-    __syncthreads();
-    {   // horizontal pass: S[sx0]*a0 + S[sx1]*a1 for every staged source row
-        const int dx = tid & 63;
-        if (dx < tw) {
-            const int2 e = __ldg(&xt[dx]);
-            const int c0 = (e.x & 0xffff) - sx_lo, c1 = (e.x >> 16) - sx_lo;
-            const int a0 = (short)(e.y & 0xffff), a1 = (short)(e.y >> 16);
-            const uint8_t* sb = reinterpret_cast<const uint8_t*>(simg);
-            for (int r = tid >> 6; r < nr; r += 4)
-                Hs[r * RT_W + dx] = sb[r * src_words * 4 + c0] * a0 + sb[r * src_words * 4 + c1] * a1;
+    auto hrow = [&](int sy, int (&H)[4]) {          // S[sx0]*a0 + S[sx1]*a1
+        const uint8_t* r = sroi + (size_t)sy * S.stride;
+#pragma unroll
+        for (int k = 0; k < 4; k++) H[k] = r[c0[k]] * a0[k] + r[c1[k]] * a1[k];
+    };
+    int id0 = -1, id1 = -1, H0[4], H1[4];
+    uint8_t* drow = base + D.plane_off + (size_t)(y0 + ORB_EDGE) * D.stride + ORB_EDGE + gx;
+    const int yend = min(y0 + RS_ROWS, D.h);
+    for (int y = y0; y < yend; y++, drow += D.stride) {
+        const int2 e = __ldg(ytab + D.ytab_off + y);
+        const int s0 = e.x & 0xffff, s1 = e.x >> 16;
+        const int b0 = (short)(e.y & 0xffff), b1 = (short)(e.y >> 16);
+        if (s0 != id0) {
+            if (s0 == id1) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) H0[k] = H1[k];
+            } else hrow(s0, H0);
+            id0 = s0;
         }
-    }
-    __syncthreads();
-    {   // vertical pass: (((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2
-        const int ry = tid >> 4, gx = (tid & 15) * 4;
-        if (ry < thh && gx < tw) {
-            const int2 e = __ldg(&yt[ry]);
-            const int r0 = (e.x & 0xffff) - sy_lo, r1 = (e.x >> 16) - sy_lo;
-            const int b0 = (short)(e.y & 0xffff), b1 = (short)(e.y >> 16);
-            const int4 h0 = *reinterpret_cast<const int4*>(Hs + r0 * RT_W + gx);
-            const int4 h1 = *reinterpret_cast<const int4*>(Hs + r1 * RT_W + gx);
-            auto mix = [&](int s0, int s1) {
-                const int o = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
-                return (uint32_t)min(max(o, 0), 255);
-            };
-            const uint32_t v = mix(h0.x, h1.x) | (mix(h0.y, h1.y) << 8) | (mix(h0.z, h1.z) << 16) | (mix(h0.w, h1.w) << 24);
-            // bytes past the right ROI edge fall into the border and are rewritten by k_border
-            *reinterpret_cast<uint32_t*>(base + D.plane_off + (size_t)(y0 + ry + ORB_EDGE) * D.stride + ORB_EDGE + x0 + gx) = v;
+        if (s1 != id1) {
+            if (s1 == id0) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) H1[k] = H0[k];
+            } else hrow(s1, H1);
+            id1 = s1;
         }
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {          // (((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2
+            const int o = (((b0 * (H0[k] >> 4)) >> 16) + ((b1 * (H1[k] >> 4)) >> 16) + 2) >> 2;
+            v |= (uint32_t)min(max(o, 0), 255) << (8 * k);
+        }
+        // bytes past the right ROI edge fall into the border and are rewritten by k_border
+        *reinterpret_cast<uint32_t*>(drow) = v;
     }
 }
 
@@ -392,18 +391,22 @@ k_cell_compact(const uint8_t* __restrict__ nms, size_t fbytes, const Plan* __res
 // its own list in parallel; the survivors are concatenated in cell order, converted to level
 // coordinates, and capped to nDesired by a second introselect (:697-701).
 // level record = score<<32 | y<<16 | x  (level ROI coordinates)
+constexpr int SEL_STAGE = 6144;     // candidate records staged in shared memory per (frame, level)
+
 __global__ void __launch_bounds__(128)
 k_select(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells, uint32_t* __restrict__ cand,
          const int* __restrict__ ntotal, unsigned long long* __restrict__ lvl, int* __restrict__ nkept,
          int* __restrict__ status)
 {
-    extern __shared__ unsigned long long s_list[];
+    extern __shared__ unsigned long long s_list[];            // lvl_cap records, then SEL_STAGE u32 records
     __shared__ int s_total[ORB_MAX_CELLS_LEVEL], s_retain[ORB_MAX_CELLS_LEVEL], s_off[ORB_MAX_CELLS_LEVEL + 1];
+    __shared__ int s_coff[ORB_MAX_CELLS_LEVEL + 1];
     const int level = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
     const LevelGeom& L = plan->L[level];
     const int nCells = L.ncells;
     const CellGeom* cg = cells + L.cell_base;
     const int* nt = ntotal + (size_t)f * plan->ncells + L.cell_base;
+    uint32_t* s_cand = reinterpret_cast<uint32_t*>(s_list + plan->sel_list_cap);
     for (int c = tid; c < nCells; c += blockDim.x) s_total[c] = nt[c];
     __syncthreads();
     if (tid == 0) {
@@ -426,18 +429,36 @@ k_select(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells, uint
                 else { s_retain[c] = s_total[c]; nToDistribute += nNew - s_total[c]; noMore[c] = 1; nNoMore++; }
             }
         }
-        int o = 0;
-        for (int c = 0; c < nCells; c++) { s_off[c] = o; o += s_retain[c]; }
-        s_off[nCells] = o;
+        int o = 0, co = 0;
+        for (int c = 0; c < nCells; c++) {
+            s_off[c] = o; o += s_retain[c];
+            // only cells that really run the selection are staged
+            s_coff[c] = co; if (s_total[c] > s_retain[c] && s_retain[c] > 0) co += s_total[c];
+        }
+        s_off[nCells] = o; s_coff[nCells] = co;
         if (o > L.lvl_cap) { atomicExch(status, ORB_ERR_CAPACITY); s_off[nCells] = -1; }
     }
     __syncthreads();
     int total = s_off[nCells];
     if (total < 0) { if (tid == 0) nkept[f * plan->nlevels + level] = 0; return; }
+    const bool staged = s_coff[nCells] <= SEL_STAGE;
+    uint32_t* gbase = cand + (size_t)f * plan->cand_total;
+    if (staged) {          // coalesced copy of the lists that need a selection into shared memory
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int c = warp; c < nCells; c += 4) {
+            const int n = s_coff[c + 1] - s_coff[c];
+            const uint32_t* src = gbase + cg[c].cand_off;
+            for (int k = lane; k < n; k += 32) s_cand[s_coff[c] + k] = src[k];
+        }
+        __syncthreads();
+    }
     for (int c = tid; c < nCells; c += blockDim.x) {
         const int n = s_total[c], keep = s_retain[c];
-        uint32_t* v = cand + (size_t)f * plan->cand_total + cg[c].cand_off;
-        if (n > keep && keep > 0) orbsel::nth_element(v, n, keep - 1, orbsel::KeyGreater<uint32_t, 24>());
+        uint32_t* v = gbase + cg[c].cand_off;
+        if (n > keep && keep > 0) {
+            if (staged) v = s_cand + s_coff[c];
+            orbsel::nth_element(v, n, keep - 1, orbsel::KeyGreater<uint32_t, 24>());
+        }
         const int ix = cg[c].inix, iy = cg[c].iniy;
         for (int k = 0; k < keep; k++) {
             const uint32_t r = v[k];
@@ -551,9 +572,11 @@ k_blur(const uint8_t* __restrict__ planes, uint8_t* __restrict__ blurred, size_t
 }
 
 // ------------------------------------------------------------------ K6
-__constant__ int8_t c_pattern[1024] = {
+const int8_t h_pattern[1024] = {
 #include "orb_pattern.inc"
 };
+// rBRIEF pattern transposed for the warp: entry [(2*k+e)*32 + lane] = sample e of test k of descriptor byte `lane`
+__device__ float2 g_pattern_t[16 * 32];
 __constant__ int c_umax[16];
 
 // cv::fastAtan2 (degrees), every operation individually rounded to FP32 (no contraction)
@@ -579,6 +602,12 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
     return a;
 }
 
+// cvRound for |v| < 2^22 without the slow F2I: the 1.5*2^23 magic add rounds to nearest-even
+__device__ __forceinline__ int rint_magic(float v)
+{
+    return (int)__float_as_uint(__fadd_rn(v, 12582912.0f)) - 0x4B400000;
+}
+
 // One warp per output keypoint slot.  Lanes 0..30 own patch column u = lane-15 for the moments;
 // lane i then owns descriptor byte i (8 tests, 16 rotated samples).
 __global__ void __launch_bounds__(256)
@@ -586,40 +615,41 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
            const Plan* __restrict__ plan, const unsigned long long* __restrict__ lvl, const int* __restrict__ nkept,
            orb_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int cap, int32_t* __restrict__ counts)
 {
-    __shared__ int8_t s_pat[1024];
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_pat[i] = c_pattern[i];
-    __syncthreads();
     const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.y;
     const int nl = plan->nlevels;
-    const int* nk = nkept + f * nl;
-    int level = -1, idx = 0, acc = 0;
-    for (int l = 0; l < nl; l++) {
-        const int n = nk[l];
-        if (level < 0 && slot < acc + n) { level = l; idx = slot - acc; }
-        acc += n;
-    }
-    if (slot == 0 && lane == 0) counts[f] = acc;        // > cap means the caller's buffers truncated the output
-    if (level < 0 || slot >= cap) return;
+    // per-level keypoint counts: lane l holds level l, prefix by shuffles
+    const int mycnt = lane < nl ? nkept[f * nl + lane] : 0;
+    int incl = mycnt;
+#pragma unroll
+    for (int o = 1; o < ORB_MAX_LEVELS; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(0xffffffffu, incl, ORB_MAX_LEVELS - 1);
+    if (slot == 0 && lane == 0) counts[f] = total;        // > cap means the caller's buffers truncated the output
+    if (slot >= total || slot >= cap) return;
+    const unsigned below = __ballot_sync(0xffffffffu, lane < nl && incl <= slot);
+    const int level = __popc(below);
+    const int idx = slot - (__shfl_sync(0xffffffffu, incl, level) - __shfl_sync(0xffffffffu, mycnt, level));
     const LevelGeom& L = plan->L[level];
+    const int stride = L.stride;
     const unsigned long long rec = lvl[(size_t)f * plan->lvl_total + L.lvl_base + idx];
     const int x = (int)(rec & 0xffff), y = (int)((rec >> 16) & 0xffff), score = (int)(rec >> 32);
-    const uint8_t* roi = planes + (size_t)f * fbytes + L.plane_off + (size_t)ORB_EDGE * L.stride + ORB_EDGE;
-    const uint8_t* broi = blurred + (size_t)f * fbytes + L.plane_off + (size_t)ORB_EDGE * L.stride + ORB_EDGE;
-    const uint8_t* center = roi + (size_t)y * L.stride + x;
+    const uint8_t* roi = planes + (size_t)f * fbytes + L.plane_off + (size_t)ORB_EDGE * stride + ORB_EDGE;
+    const ptrdiff_t bdelta = blurred - planes;             // same layout in both buffers
+    const uint8_t* center = roi + (size_t)y * stride + x;
 
     // IC_Angle (:124-151): m10 = sum u*I, m01 = sum v*I over the radius-15 disc
     int m10 = 0, m01 = 0;
-    const int u = lane - 15;
     if (lane < 31) {
-        const int au = abs(u);
+        const int u = lane - 15, au = abs(u);
+        int colsum = 0;
 #pragma unroll
         for (int v = -15; v <= 15; v++) {
             if (au <= c_umax[v < 0 ? -v : v]) {
-                const int val = center[v * L.stride + u];
-                m10 += u * val; m01 += v * val;
+                const int val = center[v * stride + u];
+                colsum += val; m01 += v * val;
             }
         }
+        m10 = u * colsum;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
@@ -631,22 +661,21 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
     float a, b;
     if (lane == 0) { a = (float)cos((double)arad); b = (float)sin((double)arad); }
     a = __shfl_sync(0xffffffffu, a, 0); b = __shfl_sync(0xffffffffu, b, 0);
-    const int8_t* pat = s_pat + lane * 32;
+    const float2* pat = g_pattern_t + lane;
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         int t[2];
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-            const float px = (float)pat[4 * k + 2 * e], py = (float)pat[4 * k + 2 * e + 1];
-            const int iy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
-            const int ix = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+            const float2 p = __ldg(pat + (2 * k + e) * 32);
+            const int iy = rint_magic(__fadd_rn(__fmul_rn(p.x, b), __fmul_rn(p.y, a)));
+            const int ix = rint_magic(__fsub_rn(__fmul_rn(p.x, a), __fmul_rn(p.y, b)));
             const int sx = x + ix, sy = y + iy;
             // the in-place blur only rewrites the ROI: samples that fall into the 16-px border
             // read the un-blurred reflected pixels (:760)
-            const bool inside = sx >= 0 && sx < L.w && sy >= 0 && sy < L.h;
-            const uint8_t* base = inside ? broi : roi;
-            t[e] = base[(ptrdiff_t)sy * L.stride + sx];
+            const bool inside = (unsigned)sx < (unsigned)L.w && (unsigned)sy < (unsigned)L.h;
+            t[e] = roi[(ptrdiff_t)sy * stride + sx + (inside ? bdelta : (ptrdiff_t)0)];
         }
         val |= (t[0] < t[1]) << k;
     }
@@ -666,6 +695,14 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
 int orb_upload_constants(const int* umax)
 {
     ORB_CUDA(cudaMemcpyToSymbol(c_umax, umax, sizeof(int) * 16));
+    float2 t[16 * 32];
+    for (int lane = 0; lane < 32; lane++)
+        for (int k = 0; k < 8; k++)
+            for (int e = 0; e < 2; e++) {
+                const int8_t* p = h_pattern + lane * 32 + 4 * k + 2 * e;
+                t[(2 * k + e) * 32 + lane] = make_float2((float)p[0], (float)p[1]);
+            }
+    ORB_CUDA(cudaMemcpyToSymbol(g_pattern_t, t, sizeof t));
     return ORB_OK;
 }
 
@@ -695,9 +732,8 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w, int h
     mark();
     for (int l = 1; l < P.nlevels; l++) {
         const LevelGeom& D = P.L[l];
-        const int tiles = ((D.w + RT_W - 1) / RT_W) * ((D.h + RT_H - 1) / RT_H);
-        const size_t sm = ((((size_t)c->rs_rows[l] * c->rs_words[l] + 3) & ~(size_t)3) + (size_t)c->rs_rows[l] * RT_W) * 4;
-        k_resize<<<dim3(tiles, nimg), 256, sm, s>>>(c->d_planes, fb, P.L[l - 1], D, c->d_xtab, c->d_ytab, c->rs_words[l], c->rs_rows[l]);
+        dim3 grid((D.w + 255) / 256, (D.h + 4 * RS_ROWS - 1) / (4 * RS_ROWS), nimg);
+        k_resize<<<grid, 256, 0, s>>>(c->d_planes, fb, P.L[l - 1], D, c->d_xtab, c->d_ytab);
         launches++;
     }
     k_border<<<dim3((P.border_total + 255) / 256, nimg), 256, 0, s>>>(c->d_planes, fb, c->d_plan);
@@ -709,7 +745,7 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w, int h
     mark();
     int maxcap = 0;
     for (int l = 0; l < P.nlevels; l++) maxcap = std::max(maxcap, P.L[l].lvl_cap);
-    k_select<<<dim3(P.nlevels, nimg), 128, (size_t)maxcap * 8, s>>>(c->d_plan, c->d_cells, c->d_cand, c->d_ntotal, c->d_lvl, c->d_nkept, c->d_status);
+    k_select<<<dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s>>>(c->d_plan, c->d_cells, c->d_cand, c->d_ntotal, c->d_lvl, c->d_nkept, c->d_status);
     mark();
     k_blur<<<dim3(P.ntiles_blur, nimg), 256, 0, s>>>(c->d_planes, c->d_work, fb, c->d_plan, c->d_tiles_blur);
     mark();
@@ -723,11 +759,7 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w, int h
     return ORB_OK;
 }
 
-int orb_resize_smem_setup(int max_bytes)
-{
-    ORB_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
-    return ORB_OK;
-}
+int orb_resize_smem_setup(int max_bytes) { (void)max_bytes; return ORB_OK; }
 
 int orb_select_smem_setup(int max_bytes)
 {

@@ -42,6 +42,7 @@ struct Plan {
     int kp_cap;            // sum of nDesired
     int fast_th, th_lo;
     int ntiles_fast, ntiles_blur;
+    int sel_list_cap;      // max lvl_cap over levels (k_select shared-memory list)
     int border_total;      // k_border work items (32-bit words of all frame regions) per image
     LevelGeom L[ORB_MAX_LEVELS];
 };

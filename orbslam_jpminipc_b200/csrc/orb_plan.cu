@@ -178,6 +178,8 @@ int orb_build_plan(orb_ctx* c, int w, int h)
     P.lvl_total = lvl;
     P.kp_cap = kp;
     P.border_total = border;
+    P.sel_list_cap = 0;
+    for (int l = 0; l < P.nlevels; l++) P.sel_list_cap = std::max(P.sel_list_cap, P.L[l].lvl_cap);
     P.ntiles_fast = (int)c->tiles_fast.size();
     P.ntiles_blur = (int)c->tiles_blur.size();
     return ORB_OK;   // device upload happens in orb_api.cu
