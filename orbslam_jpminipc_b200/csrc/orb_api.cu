@@ -12,6 +12,52 @@ int orb_cuda_fail(cudaError_t e, const char* what)
     return ORB_ERR_CUDA;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// (re)encode the per-level descriptors over the pyramid buffer: dims {stride, prows, frames}, box {bw, bh, 1}
+int orb_build_tmaps(orb_ctx* c, int nframes)
+{
+    if (c->tm_base == c->d_planes && c->tm_frames == nframes && c->tm_w == c->plan.w && c->tm_h == c->plan.h) return ORB_OK;
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { g_last_cuda_error = "cuTensorMapEncodeTiled entry point not available"; return ORB_ERR_CUDA; }
+    const Plan& P = c->plan;
+    for (int l = 0; l < P.nlevels; l++) {
+        const LevelGeom& L = P.L[l];
+        cuuint64_t dims[3] = { (cuuint64_t)L.stride, (cuuint64_t)L.prows, (cuuint64_t)nframes };
+        cuuint64_t strides[2] = { (cuuint64_t)L.stride, (cuuint64_t)P.frame_bytes };
+        cuuint32_t estr[3] = { 1, 1, 1 };
+        cuuint32_t box_fast[3] = { 96, ORB_TILE_H + 8, 1 };
+        cuuint32_t box_blur[3] = { 96, ORB_BLUR_TILE_H + 6, 1 };
+        void* base = c->d_planes + L.plane_off;
+        CUresult r1 = enc(&c->tm_fast.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box_fast, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CUresult r2 = enc(&c->tm_blur.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box_blur, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+            g_last_cuda_error = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r1) + "," + std::to_string((int)r2) + ")";
+            return ORB_ERR_CUDA;
+        }
+    }
+    c->tm_base = c->d_planes; c->tm_frames = nframes; c->tm_w = P.w; c->tm_h = P.h;
+    return ORB_OK;
+}
+
 template <typename T>
 static int ensure(T*& p, size_t& cap, size_t bytes)
 {
@@ -38,9 +84,7 @@ static int prepare(orb_ctx* c, int w, int h, int nimg)
     if (rebuild) {
         int rc = orb_build_plan(c, w, h);
         if (rc != ORB_OK) return rc;
-        size_t dummy = sizeof(Plan);
         if (!c->d_plan) { size_t z = 0; rc = ensure(c->d_plan, z, sizeof(Plan)); if (rc) return rc; }
-        (void)dummy;
         rc = ensure(c->d_cells, c->cap_cells, c->cells.size() * sizeof(CellGeom)); if (rc) return rc;
         rc = ensure(c->d_tiles_fast, c->cap_tiles_fast, c->tiles_fast.size() * sizeof(Tile)); if (rc) return rc;
         rc = ensure(c->d_tiles_blur, c->cap_tiles_blur, c->tiles_blur.size() * sizeof(Tile)); if (rc) return rc;
@@ -70,7 +114,8 @@ static int prepare(orb_ctx* c, int w, int h, int nimg)
     rc = ensure(c->d_cand, c->cand_bytes, B * (size_t)P.cand_total * 4); if (rc) return rc;
     rc = ensure(c->d_ntotal, c->ntotal_bytes, B * (size_t)P.ncells * 4); if (rc) return rc;
     rc = ensure(c->d_lvl, c->lvl_bytes, B * (size_t)P.lvl_total * 8); if (rc) return rc;
-    return ORB_OK;
+    // descriptors span the whole allocation (capacity in frames), so they survive smaller batches
+    return orb_build_tmaps(c, (int)(c->planes_bytes / P.frame_bytes));
 }
 
 extern "C" {
@@ -107,10 +152,11 @@ orb_ctx* orb_create(int device, int nfeatures, float scale_factor, int nlevels, 
     orb_ctx* c = new orb_ctx;
     c->device = device; c->nfeatures = nfeatures; c->scale_factor_f = scale_factor; c->nlevels = nlevels;
     c->score_type = score_type; c->fast_th = fast_th; c->max_w = max_w; c->max_h = max_h; c->max_batch = max_batch;
+    cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (orb_build_tables(c) != ORB_OK || orb_upload_constants(c->umax) != ORB_OK) { delete c; return nullptr; }
     bool ok = cudaMalloc((void**)&c->d_nkept, sizeof(int) * ORB_MAX_LEVELS * max_batch) == cudaSuccess &&
-              cudaMalloc((void**)&c->d_status, sizeof(int)) == cudaSuccess &&
-              cudaMemset(c->d_status, 0, sizeof(int)) == cudaSuccess;
+              cudaMalloc((void**)&c->d_status, 4 * sizeof(int)) == cudaSuccess &&     // [0] status, [1..] work counters
+              cudaMemset(c->d_status, 0, 4 * sizeof(int)) == cudaSuccess;
     for (int i = 0; i < 2 && ok; i++) {
         ok = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming) == cudaSuccess;

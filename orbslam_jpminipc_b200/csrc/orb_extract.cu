@@ -145,7 +145,7 @@ k_border(uint8_t* __restrict__ planes, size_t fbytes, const Plan* __restrict__ p
 //   bright strength = max_k( min of ring[k..k+8] ) - v,   dark strength = v - min_k( max of ring[k..k+8] )
 // corner at threshold t  <=>  max(bright, dark) > t ;  OpenCV's response = that maximum - 1.
 constexpr int FT_W = ORB_TILE_W, FT_H = ORB_TILE_H;
-constexpr int FIW = 20, FI_H = FT_H + 8;   // image tile: 20 words (cols x0-8..x0+71) x rows y0-4..y0+35
+constexpr int FIW = 24, FI_H = FT_H + 8;   // image tile: 24 words (cols x0-16..x0+79) x rows y0-4..y0+35; TMA needs a 16-byte aligned x origin
 constexpr int FSW = 18, FS_H = FT_H + 2;   // score tile: 18 words (cols x0-4..x0+67) x rows y0-1..y0+32
 constexpr int FAST_THREADS = 320;
 
@@ -172,145 +172,216 @@ __device__ __forceinline__ void arc_minmax(const uint32_t (&r)[16], uint32_t& Mn
     Mx = __vminu2(Mx, b[15]);
 }
 
-__device__ __forceinline__ uint32_t score_of(int v, int mn, int mx, int th)
+// packed epilogue for two pixels: strength = max(Mn - v, v - Mx) per s16 lane, response = strength-1 where
+// strength > th, else 0.  v2/Mn/Mx are u16x2 (values 0..255); returns the two responses in the low bytes of each lane.
+__device__ __forceinline__ uint32_t score2(uint32_t v2, uint32_t Mn, uint32_t Mx, uint32_t neg_th2, int th_m1)
 {
-    const int s = max(mn - v, v - mx);
-    return s > th ? (uint32_t)(s - 1) : 0u;
+    const uint32_t negv = __vneg2(v2), negMx = __vneg2(Mx);
+    const uint32_t dark = __vadd2(v2, negMx);                         // v - Mx  (may be negative)
+    const uint32_t T = __viaddmax_s16x2(Mn, negv, dark);              // max(Mn - v, v - Mx)
+    const uint32_t q = __viaddmax_s16x2_relu(T, neg_th2, 0u);         // max(T - th, 0)
+    const uint32_t m = __vmins2(q, 0x00010001u);                 // 1 where corner
+    return m * (uint32_t)th_m1 + q;                                   // T - 1 where corner (lanes cannot carry)
 }
 
-__global__ void __launch_bounds__(FAST_THREADS)
-k_fast_nms(const uint8_t* __restrict__ planes, uint8_t* __restrict__ nms, size_t fbytes,
-           const Plan* __restrict__ plan, const Tile* __restrict__ tiles)
+// ---- TMA / mbarrier helpers (tile loads run on the copy engine and overlap the previous tile's math) ----
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
 {
-    __shared__ __align__(16) uint32_t img[FI_H * FIW];
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// 3-D tiled TMA load (x, y, frame) -> shared memory, completion on the mbarrier (SASS: UTMALDG)
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int x, int y, int z, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_addr(dst)), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(smem_addr(bar)) : "memory");
+}
+
+// Persistent kernel: each CTA walks (tile, frame) work items; the image tile of item i+1 is fetched by
+// TMA into the other shared-memory buffer while item i is being scored.
+__global__ void __launch_bounds__(FAST_THREADS, 3)
+k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, size_t fbytes,
+           const Plan* __restrict__ plan, const Tile* __restrict__ tiles, int ntiles, int total, int* __restrict__ work_counter)
+{
+    __shared__ __align__(128) uint32_t img2[2][FI_H * FIW];
+    __shared__ int s_next[2];
     __shared__ __align__(16) uint32_t sc[FS_H * FSW];
     __shared__ short colcell[FSW * 4], rowcell[FS_H];
     __shared__ __align__(4) uint8_t m_in[FSW * 4], m_l[FSW * 4], m_r[FSW * 4];
-    const Tile t = tiles[blockIdx.x];
-    const LevelGeom& L = plan->L[t.level];
-    const int f = blockIdx.y, tid = threadIdx.x;
-    const uint8_t* plane = planes + (size_t)f * fbytes + L.plane_off;
+    __shared__ __align__(8) uint64_t bar[2];
+    const int tid = threadIdx.x;
     const int th = plan->th_lo;
+    const uint32_t neg_th2 = __vneg2((uint32_t)th * 0x00010001u);
+    const int th_m1 = th - 1;
+    constexpr uint32_t TILE_BYTES = FI_H * FIW * 4;
 
-    {   // image tile, origin (x0-8, y0-4) in ROI coordinates (+16 in padded coordinates; word aligned)
-        const int px0 = t.x0 - 8 + ORB_EDGE, py0 = t.y0 - 4 + ORB_EDGE;
-        for (int i = tid; i < FI_H * FIW; i += FAST_THREADS) {
-            const int r = i / FIW, cw = i - r * FIW;
-            const int py = py0 + r, px = px0 + cw * 4;
+    auto issue = [&](int item, int buf) {      // one thread: arm the barrier, start the copy
+        const int ti = item % ntiles, fr = item / ntiles;
+        const Tile t = tiles[ti];
+        mbar_expect_tx(&bar[buf], TILE_BYTES);
+        tma_load_3d(&img2[buf][0], &tm.m[t.level], t.x0 - 16 + ORB_EDGE, t.y0 - 4 + ORB_EDGE, fr, &bar[buf]);
+    };
+    if (tid == 0) {
+        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // dynamic work distribution: items differ a lot in cost (flat areas are rejected early)
+    int item = blockIdx.x;
+    if (tid == 0 && item < total) issue(item, 0);
+
+    for (int it = 0; item < total; it++) {
+        const int buf = it & 1;
+        const int ti = item % ntiles, f = item / ntiles;
+        const Tile t = tiles[ti];
+        const LevelGeom& L = plan->L[t.level];
+        // claim + prefetch the next item; its buffer was last read before the post-scoring barrier of the previous iteration
+        if (tid == 0) {
+            const int nxt = atomicAdd(work_counter, 1) + (int)gridDim.x;
+            s_next[buf] = nxt;
+            if (nxt < total) issue(nxt, buf ^ 1);
+        }
+
+        // detection-cell id of every score-tile column / row (-1: outside every detection rectangle)
+        if (tid < FSW * 4) {
+            const int x = t.x0 - 4 + tid;
+            int c = -1;
+            if (x >= ORB_EDGE) {
+                c = (x - ORB_EDGE) / L.cellW;
+                if (c >= L.cols - 1) { c = L.cols - 1; if (x >= L.w - ORB_EDGE) c = -1; }
+            }
+            colcell[tid] = (short)c;
+        } else if (tid >= 128 && tid < 128 + FS_H) {
+            const int i = tid - 128, y = t.y0 - 1 + i;
+            int c = -1;
+            if (y >= ORB_EDGE) {
+                c = (y - ORB_EDGE) / L.cellH;
+                if (c >= L.rows - 1) { c = L.rows - 1; if (y >= L.h - ORB_EDGE) c = -1; }
+            }
+            rowcell[i] = (short)c;
+        }
+        __syncthreads();
+        if (tid < FSW * 4) {          // byte masks: in region / left neighbour in same cell / right neighbour in same cell
+            const int c = colcell[tid];
+            m_in[tid] = c >= 0 ? 0xff : 0;
+            m_l[tid] = (tid > 0 && c >= 0 && colcell[tid - 1] == c) ? 0xff : 0;
+            m_r[tid] = (tid < FSW * 4 - 1 && c >= 0 && colcell[tid + 1] == c) ? 0xff : 0;
+        }
+        mbar_wait(&bar[buf], (uint32_t)((it >> 1) & 1));      // image tile has landed
+        __syncthreads();
+        const uint32_t* img = img2[buf];
+
+        // ---- corner strength: one task = 4 horizontally adjacent pixels ----
+        for (int task = tid; task < FS_H * FSW; task += FAST_THREADS) {
+            const int r = task / FSW, g = task - r * FSW;
+            const uint32_t cm = reinterpret_cast<const uint32_t*>(m_in)[g];
+            uint32_t outw = 0;
+            if (cm != 0 && rowcell[r] >= 0) {
+                const uint32_t* ip = img + r * FIW + g + 2;          // rows r..r+6 (y-3..y+3), words of cols x-4..x+7
+                uint32_t w0[7], w1[7], w2[7];
+#pragma unroll
+                for (int q = 0; q < 7; q++) { w0[q] = ip[q * FIW]; w1[q] = ip[q * FIW + 1]; w2[q] = ip[q * FIW + 2]; }
+                // Ring sample k for pixels (x, x+1) resp. (x+2, x+3), packed as two u16 lanes holding value*257
+                // (byte duplicated): one PRMT straight from the two source words, order preserving.
+#define RPAIR(A, B, o, hi) __byte_perm(A, B, (hi) ? ((((o) + 3) << 12) | (((o) + 3) << 8) | (((o) + 2) << 4) | ((o) + 2)) \
+                                                   : ((((o) + 1) << 12) | (((o) + 1) << 8) | ((o) << 4) | (o)))
+#define RING_ALL(hi, R)                                                                      \
+                R[0]  = RPAIR(w1[6], w2[6], 0, hi);  R[1]  = RPAIR(w1[6], w2[6], 1, hi);     \
+                R[2]  = RPAIR(w1[5], w2[5], 2, hi);  R[3]  = RPAIR(w1[4], w2[4], 3, hi);     \
+                R[4]  = RPAIR(w1[3], w2[3], 3, hi);  R[5]  = RPAIR(w1[2], w2[2], 3, hi);     \
+                R[6]  = RPAIR(w1[1], w2[1], 2, hi);  R[7]  = RPAIR(w1[0], w2[0], 1, hi);     \
+                R[8]  = RPAIR(w1[0], w2[0], 0, hi);  R[9]  = RPAIR(w0[0], w1[0], 3, hi);     \
+                R[10] = RPAIR(w0[1], w1[1], 2, hi);  R[11] = RPAIR(w0[2], w1[2], 1, hi);     \
+                R[12] = RPAIR(w0[3], w1[3], 1, hi);  R[13] = RPAIR(w0[4], w1[4], 1, hi);     \
+                R[14] = RPAIR(w0[5], w1[5], 2, hi);  R[15] = RPAIR(w0[6], w1[6], 3, hi);
+                const uint32_t cw = w1[3];
+                const uint32_t vlo = lo16x2(cw), vhi = hi16x2(cw);
+                uint32_t ring[16], Mn, Mx;
+                RING_ALL(0, ring)
+                // quick reject (exact): every 9-arc contains two ring-adjacent compass points (0,4,8,12), so a
+                // corner needs such a pair both brighter than v+th or both darker than v-th.
+                const uint32_t h0 = RPAIR(w1[6], w2[6], 0, 1), h4 = RPAIR(w1[3], w2[3], 3, 1);
+                const uint32_t h8 = RPAIR(w1[0], w2[0], 0, 1), h12 = RPAIR(w0[3], w1[3], 1, 1);
+                bool any;
+                {
+                    const uint32_t n0 = ring[0], n4 = ring[4], n8 = ring[8], n12 = ring[12];
+                    const uint32_t bl = __vmaxu2(__vmaxu2(__vminu2(n0, n4), __vminu2(n4, n8)), __vmaxu2(__vminu2(n8, n12), __vminu2(n12, n0)));
+                    const uint32_t dl = __vminu2(__vminu2(__vmaxu2(n0, n4), __vmaxu2(n4, n8)), __vminu2(__vmaxu2(n8, n12), __vmaxu2(n12, n0)));
+                    const uint32_t bh = __vmaxu2(__vmaxu2(__vminu2(h0, h4), __vminu2(h4, h8)), __vmaxu2(__vminu2(h8, h12), __vminu2(h12, h0)));
+                    const uint32_t dh = __vminu2(__vminu2(__vmaxu2(h0, h4), __vmaxu2(h4, h8)), __vminu2(__vmaxu2(h8, h12), __vmaxu2(h12, h0)));
+                    any = (score2(vlo, __byte_perm(bl, 0, 0x4240), __byte_perm(dl, 0, 0x4240), neg_th2, th_m1) |
+                           score2(vhi, __byte_perm(bh, 0, 0x4240), __byte_perm(dh, 0, 0x4240), neg_th2, th_m1)) != 0;
+                }
+                if (any) {
+                    arc_minmax(ring, Mn, Mx);
+                    const uint32_t slo = score2(vlo, __byte_perm(Mn, 0, 0x4240), __byte_perm(Mx, 0, 0x4240), neg_th2, th_m1);
+                    RING_ALL(1, ring)
+                    arc_minmax(ring, Mn, Mx);
+                    const uint32_t shi = score2(vhi, __byte_perm(Mn, 0, 0x4240), __byte_perm(Mx, 0, 0x4240), neg_th2, th_m1);
+                    outw = __byte_perm(slo, shi, 0x6420) & cm;              // low byte of each of the four lanes
+                }
+#undef RING_ALL
+#undef RPAIR
+            }
+            sc[task] = outw;
+        }
+        __syncthreads();
+
+        // ---- NMS restricted to the pixel's own cell: one task = 4 output pixels, one 32-bit store ----
+        uint8_t* out = nms + (size_t)f * fbytes + L.plane_off;
+        for (int task = tid; task < FT_H * (FT_W / 4); task += FAST_THREADS) {
+            const int ro = task / (FT_W / 4), go = task - ro * (FT_W / 4);
+            const int r = ro + 1, g = go + 1;
+            const uint32_t* sp = sc + r * FSW + g;
+            const uint32_t c = sp[0];
             uint32_t v = 0;
-            if (py < L.prows && px + 3 < L.stride) v = __ldg(reinterpret_cast<const uint32_t*>(plane + (size_t)py * L.stride + px));
-            img[i] = v;
+            if (c) {
+                const uint32_t ml = reinterpret_cast<const uint32_t*>(m_l)[g], mr = reinterpret_cast<const uint32_t*>(m_r)[g];
+                const int rc = rowcell[r];
+                const bool up = rowcell[r - 1] == rc, dn = rowcell[r + 1] == rc;
+                uint32_t nb[8];
+                nb[0] = __funnelshift_r(sp[-1], c, 24) & ml;
+                nb[1] = __funnelshift_r(c, sp[1], 8) & mr;
+                const uint32_t ul = sp[-FSW - 1], uc = sp[-FSW], ur = sp[-FSW + 1];
+                nb[2] = up ? uc : 0u;
+                nb[3] = up ? (__funnelshift_r(ul, uc, 24) & ml) : 0u;
+                nb[4] = up ? (__funnelshift_r(uc, ur, 8) & mr) : 0u;
+                const uint32_t dl = sp[FSW - 1], dc = sp[FSW], dr = sp[FSW + 1];
+                nb[5] = dn ? dc : 0u;
+                nb[6] = dn ? (__funnelshift_r(dl, dc, 24) & ml) : 0u;
+                nb[7] = dn ? (__funnelshift_r(dc, dr, 8) & mr) : 0u;
+                uint32_t mlo = __vimax3_u16x2(__vimax3_u16x2(lo16x2(nb[0]), lo16x2(nb[1]), lo16x2(nb[2])),
+                                              __vimax3_u16x2(lo16x2(nb[3]), lo16x2(nb[4]), lo16x2(nb[5])),
+                                              __vmaxu2(lo16x2(nb[6]), lo16x2(nb[7])));
+                uint32_t mhi = __vimax3_u16x2(__vimax3_u16x2(hi16x2(nb[0]), hi16x2(nb[1]), hi16x2(nb[2])),
+                                              __vimax3_u16x2(hi16x2(nb[3]), hi16x2(nb[4]), hi16x2(nb[5])),
+                                              __vmaxu2(hi16x2(nb[6]), hi16x2(nb[7])));
+                const uint32_t s0 = c & 0xff, s1 = (c >> 8) & 0xff, s2 = (c >> 16) & 0xff, s3 = c >> 24;
+                if (s0 > (mlo & 0xffff)) v |= s0;            // strictly greater than all 8 neighbours; s == 0 never passes
+                if (s1 > (mlo >> 16)) v |= s1 << 8;
+                if (s2 > (mhi & 0xffff)) v |= s2 << 16;
+                if (s3 > (mhi >> 16)) v |= s3 << 24;
+            }
+            const int py = t.y0 + ro + ORB_EDGE, px = t.x0 + go * 4 + ORB_EDGE;
+            if (py < L.prows && px + 3 < L.stride)
+                *reinterpret_cast<uint32_t*>(out + (size_t)py * L.stride + px) = v;
         }
-    }
-    // detection-cell id of every score-tile column / row (-1: outside every detection rectangle)
-    if (tid < FSW * 4) {
-        const int x = t.x0 - 4 + tid;
-        int c = -1;
-        if (x >= ORB_EDGE) {
-            c = (x - ORB_EDGE) / L.cellW;
-            if (c >= L.cols - 1) { c = L.cols - 1; if (x >= L.w - ORB_EDGE) c = -1; }
-        }
-        colcell[tid] = (short)c;
-    } else if (tid >= 128 && tid < 128 + FS_H) {
-        const int i = tid - 128, y = t.y0 - 1 + i;
-        int c = -1;
-        if (y >= ORB_EDGE) {
-            c = (y - ORB_EDGE) / L.cellH;
-            if (c >= L.rows - 1) { c = L.rows - 1; if (y >= L.h - ORB_EDGE) c = -1; }
-        }
-        rowcell[i] = (short)c;
-    }
-    __syncthreads();
-    if (tid < FSW * 4) {          // byte masks: in region / left neighbour in same cell / right neighbour in same cell
-        const int c = colcell[tid];
-        m_in[tid] = c >= 0 ? 0xff : 0;
-        m_l[tid] = (tid > 0 && c >= 0 && colcell[tid - 1] == c) ? 0xff : 0;
-        m_r[tid] = (tid < FSW * 4 - 1 && c >= 0 && colcell[tid + 1] == c) ? 0xff : 0;
-    }
-    __syncthreads();
-
-    // ---- corner strength: one task = 4 horizontally adjacent pixels ----
-    for (int task = tid; task < FS_H * FSW; task += FAST_THREADS) {
-        const int r = task / FSW, g = task - r * FSW;
-        const uint32_t cm = reinterpret_cast<const uint32_t*>(m_in)[g];
-        uint32_t outw = 0;
-        if (cm != 0 && rowcell[r] >= 0) {
-            const uint32_t* ip = img + r * FIW + g;              // rows r..r+6 (y-3..y+3), words g..g+2
-            uint32_t w0[7], w1[7], w2[7];
-#pragma unroll
-            for (int q = 0; q < 7; q++) { w0[q] = ip[q * FIW]; w1[q] = ip[q * FIW + 1]; w2[q] = ip[q * FIW + 2]; }
-            // the 16 ring positions as 4-byte windows (pixel x..x+3 shifted by dx) in OpenCV's ring order
-            uint32_t rw[16];
-            rw[0]  = w1[6];                                   // ( 0, 3)
-            rw[1]  = __funnelshift_r(w1[6], w2[6], 8);        // ( 1, 3)
-            rw[2]  = __funnelshift_r(w1[5], w2[5], 16);       // ( 2, 2)
-            rw[3]  = __funnelshift_r(w1[4], w2[4], 24);       // ( 3, 1)
-            rw[4]  = __funnelshift_r(w1[3], w2[3], 24);       // ( 3, 0)
-            rw[5]  = __funnelshift_r(w1[2], w2[2], 24);       // ( 3,-1)
-            rw[6]  = __funnelshift_r(w1[1], w2[1], 16);       // ( 2,-2)
-            rw[7]  = __funnelshift_r(w1[0], w2[0], 8);        // ( 1,-3)
-            rw[8]  = w1[0];                                   // ( 0,-3)
-            rw[9]  = __funnelshift_r(w0[0], w1[0], 24);       // (-1,-3)
-            rw[10] = __funnelshift_r(w0[1], w1[1], 16);       // (-2,-2)
-            rw[11] = __funnelshift_r(w0[2], w1[2], 8);        // (-3,-1)
-            rw[12] = __funnelshift_r(w0[3], w1[3], 8);        // (-3, 0)
-            rw[13] = __funnelshift_r(w0[4], w1[4], 8);        // (-3, 1)
-            rw[14] = __funnelshift_r(w0[5], w1[5], 16);       // (-2, 2)
-            rw[15] = __funnelshift_r(w0[6], w1[6], 24);       // (-1, 3)
-            const uint32_t cw = w1[3];
-            uint32_t ring[16], Mn, Mx;
-#pragma unroll
-            for (int k = 0; k < 16; k++) ring[k] = lo16x2(rw[k]);
-            arc_minmax(ring, Mn, Mx);
-            outw = score_of(cw & 0xff, Mn & 0xffff, Mx & 0xffff, th) | (score_of((cw >> 8) & 0xff, Mn >> 16, Mx >> 16, th) << 8);
-#pragma unroll
-            for (int k = 0; k < 16; k++) ring[k] = hi16x2(rw[k]);
-            arc_minmax(ring, Mn, Mx);
-            outw |= (score_of((cw >> 16) & 0xff, Mn & 0xffff, Mx & 0xffff, th) << 16) | (score_of(cw >> 24, Mn >> 16, Mx >> 16, th) << 24);
-            outw &= cm;
-        }
-        sc[task] = outw;
-    }
-    __syncthreads();
-
-    // ---- NMS restricted to the pixel's own cell: one task = 4 output pixels, one 32-bit store ----
-    uint8_t* out = nms + (size_t)f * fbytes + L.plane_off;
-    for (int task = tid; task < FT_H * (FT_W / 4); task += FAST_THREADS) {
-        const int ro = task / (FT_W / 4), go = task - ro * (FT_W / 4);
-        const int r = ro + 1, g = go + 1;
-        const uint32_t* sp = sc + r * FSW + g;
-        const uint32_t c = sp[0];
-        uint32_t v = 0;
-        if (c) {
-            const uint32_t ml = reinterpret_cast<const uint32_t*>(m_l)[g], mr = reinterpret_cast<const uint32_t*>(m_r)[g];
-            const int rc = rowcell[r];
-            const bool up = rowcell[r - 1] == rc, dn = rowcell[r + 1] == rc;
-            uint32_t nb[8];
-            nb[0] = __funnelshift_r(sp[-1], c, 24) & ml;
-            nb[1] = __funnelshift_r(c, sp[1], 8) & mr;
-            const uint32_t ul = sp[-FSW - 1], uc = sp[-FSW], ur = sp[-FSW + 1];
-            nb[2] = up ? uc : 0u;
-            nb[3] = up ? (__funnelshift_r(ul, uc, 24) & ml) : 0u;
-            nb[4] = up ? (__funnelshift_r(uc, ur, 8) & mr) : 0u;
-            const uint32_t dl = sp[FSW - 1], dc = sp[FSW], dr = sp[FSW + 1];
-            nb[5] = dn ? dc : 0u;
-            nb[6] = dn ? (__funnelshift_r(dl, dc, 24) & ml) : 0u;
-            nb[7] = dn ? (__funnelshift_r(dc, dr, 8) & mr) : 0u;
-            uint32_t mlo = __vimax3_u16x2(__vimax3_u16x2(lo16x2(nb[0]), lo16x2(nb[1]), lo16x2(nb[2])),
-                                          __vimax3_u16x2(lo16x2(nb[3]), lo16x2(nb[4]), lo16x2(nb[5])),
-                                          __vmaxu2(lo16x2(nb[6]), lo16x2(nb[7])));
-            uint32_t mhi = __vimax3_u16x2(__vimax3_u16x2(hi16x2(nb[0]), hi16x2(nb[1]), hi16x2(nb[2])),
-                                          __vimax3_u16x2(hi16x2(nb[3]), hi16x2(nb[4]), hi16x2(nb[5])),
-                                          __vmaxu2(hi16x2(nb[6]), hi16x2(nb[7])));
-            const uint32_t s0 = c & 0xff, s1 = (c >> 8) & 0xff, s2 = (c >> 16) & 0xff, s3 = c >> 24;
-            if (s0 > (mlo & 0xffff)) v |= s0;            // strictly greater than all 8 neighbours; s == 0 never passes
-            if (s1 > (mlo >> 16)) v |= s1 << 8;
-            if (s2 > (mhi & 0xffff)) v |= s2 << 16;
-            if (s3 > (mhi >> 16)) v |= s3 << 24;
-        }
-        const int py = t.y0 + ro + ORB_EDGE, px = t.x0 + go * 4 + ORB_EDGE;
-        if (py < L.prows && px + 3 < L.stride)
-            *reinterpret_cast<uint32_t*>(out + (size_t)py * L.stride + px) = v;
+        __syncthreads();       // masks / score tile are rewritten by the next item
+        item = s_next[buf];
     }
 }
 
@@ -739,7 +810,12 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w, int h
     k_border<<<dim3((P.border_total + 255) / 256, nimg), 256, 0, s>>>(c->d_planes, fb, c->d_plan);
     launches++;
     mark();
-    k_fast_nms<<<dim3(P.ntiles_fast, nimg), FAST_THREADS, 0, s>>>(c->d_planes, c->d_work, fb, c->d_plan, c->d_tiles_fast);
+    {
+        const int total = P.ntiles_fast * nimg;
+        const int grid = std::min(total, c->num_sms * 3);
+        cudaMemsetAsync(c->d_status + 1, 0, sizeof(int), s);
+        k_fast_nms<<<grid, FAST_THREADS, 0, s>>>(c->tm_fast, c->d_work, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total, c->d_status + 1);
+    }
     mark();
     k_cell_compact<<<dim3((P.ncells + 7) / 8, nimg), 256, 0, s>>>(c->d_work, fb, c->d_plan, c->d_cells, c->d_cand, c->d_ntotal);
     mark();

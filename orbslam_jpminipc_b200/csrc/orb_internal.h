@@ -1,5 +1,6 @@
 // orb_internal.h — shared host/device structures of liborb_b200 (not part of the public ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
@@ -59,6 +60,9 @@ struct CellGeom {
 
 struct Tile { int level, x0, y0, pad; };
 
+// one TMA descriptor per pyramid level: u8 tensor (x = padded row bytes, y = padded rows, z = frame)
+struct TmapSet { CUtensorMap m[ORB_MAX_LEVELS]; };
+
 struct orb_ctx {
     int device = 0;
     int nfeatures = 0, nlevels = 0, score_type = 1, fast_th = 20;
@@ -99,6 +103,9 @@ struct orb_ctx {
     cudaStream_t streams[2] = { nullptr, nullptr };
     cudaEvent_t ev_free[2] = { nullptr, nullptr };
     int last_launches = 0;
+    TmapSet tm_fast{}, tm_blur{};          // boxes: FAST image tile / blur input tile
+    const uint8_t* tm_base = nullptr; int tm_frames = 0; int tm_w = 0, tm_h = 0;
+    int num_sms = 148;
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;   // (ORB_NSTAGES+1) per profiled launch
     std::vector<cudaEvent_t> prof_pool;
@@ -120,6 +127,7 @@ int orb_build_plan(orb_ctx* c, int w, int h);
 int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w, int h, int stride, size_t frame_pitch,
                        orb_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts, cudaStream_t s);
 int orb_upload_constants(const int* umax);
+int orb_build_tmaps(orb_ctx* c, int nframes);
 int orb_select_smem_setup(int max_bytes);
 int orb_resize_smem_setup(int max_bytes);
 // orb_match.cu
