@@ -555,9 +555,11 @@ k_select(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells, uint
 // The order of the FMAs is part of the result, so the kernel keeps it; what it avoids are the
 // slow conversion instructions: u8 -> f32 is PRMT into the mantissa of 2^23 followed by an exact
 // FADD, f32 -> u8 is the 1.5*2^23 magic add (round-to-nearest-even by the FP adder).
-constexpr int BT_W = ORB_BLUR_TILE_W, BT_H = ORB_BLUR_TILE_H;   // 64 x 56 outputs per CTA
-constexpr int BIW = 18;                       // input tile words per row: cols x0-4 .. x0+67
+constexpr int BT_W = ORB_BLUR_TILE_W, BT_H = ORB_BLUR_TILE_H;   // 64 x 56 outputs per work item
+constexpr int BIW = 24;                       // input tile words per row: padded cols x0 .. x0+95 (16-byte aligned TMA origin)
 constexpr int BI_H = BT_H + 6;                // rows y0-3 .. y0+BT_H+2
+constexpr int BI_BYTES = BI_H * BIW * 4;      // 5952
+constexpr int BI_BUF = (BI_BYTES + 127) & ~127;
 
 __device__ __forceinline__ float u8f(uint32_t w, int j)     // byte j of w as float, no I2F
 {
@@ -565,80 +567,98 @@ __device__ __forceinline__ float u8f(uint32_t w, int j)     // byte j of w as fl
     return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, sel)), 8388608.0f);
 }
 
+// Persistent kernel, same pipeline shape as k_fast_nms: TMA fetches the input tile of the next work
+// item while the current one runs its row and column passes.
 __global__ void __launch_bounds__(256)
-k_blur(const uint8_t* __restrict__ planes, uint8_t* __restrict__ blurred, size_t fbytes,
-       const Plan* __restrict__ plan, const Tile* __restrict__ tiles)
+k_blur(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ blurred, size_t fbytes,
+       const Plan* __restrict__ plan, const Tile* __restrict__ tiles, int ntiles, int total, int* __restrict__ work_counter)
 {
-    __shared__ __align__(16) uint32_t img[BI_H * BIW];
+    __shared__ __align__(128) uint8_t img2[2][BI_BUF];
     __shared__ __align__(16) float rowp[BI_H * BT_W];
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ int s_next[2];
     const float k0 = __uint_as_float(0x3d8fafb1u), k1 = __uint_as_float(0x3e06387eu),
                 k2 = __uint_as_float(0x3e434a39u), k3 = __uint_as_float(0x3e5d4ae0u);
-    const Tile t = tiles[blockIdx.x];
-    const LevelGeom& L = plan->L[t.level];
-    const int f = blockIdx.y, tid = threadIdx.x;
-    const uint8_t* plane = planes + (size_t)f * fbytes + L.plane_off;
-    {
-        const int px0 = t.x0 - 4 + ORB_EDGE, py0 = t.y0 - 3 + ORB_EDGE;
-        for (int i = tid; i < BI_H * BIW; i += 256) {
-            const int r = i / BIW, cw = i - r * BIW;
-            const int py = py0 + r, px = px0 + cw * 4;
-            uint32_t v = 0;
-            if (py < L.prows && px + 3 < L.stride) v = __ldg(reinterpret_cast<const uint32_t*>(plane + (size_t)py * L.stride + px));
-            img[i] = v;
-        }
+    const int tid = threadIdx.x;
+    auto issue = [&](int item, int buf) {
+        const int ti = item % ntiles, fr = item / ntiles;
+        const Tile t = tiles[ti];
+        mbar_expect_tx(&bar[buf], BI_BYTES);
+        tma_load_3d(&img2[buf][0], &tm.m[t.level], t.x0, t.y0 - 3 + ORB_EDGE, fr, &bar[buf]);   // padded x0 = ROI x0 - 16
+    };
+    if (tid == 0) {
+        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // row pass: one task = 8 adjacent outputs of one row (needs input bytes 8*seg+1 .. 8*seg+14 of the tile row)
-    for (int task = tid; task < BI_H * (BT_W / 8); task += 256) {
-        const int r = task >> 3, seg = task & 7;
-        const uint2* ip = reinterpret_cast<const uint2*>(img + r * BIW + 2 * seg);
-        const uint2 a = ip[0], b = ip[1];
-        float v[14];
-        v[0] = u8f(a.x, 1); v[1] = u8f(a.x, 2); v[2] = u8f(a.x, 3);
-        v[3] = u8f(a.y, 0); v[4] = u8f(a.y, 1); v[5] = u8f(a.y, 2); v[6] = u8f(a.y, 3);
-        v[7] = u8f(b.x, 0); v[8] = u8f(b.x, 1); v[9] = u8f(b.x, 2); v[10] = u8f(b.x, 3);
-        v[11] = u8f(b.y, 0); v[12] = u8f(b.y, 1); v[13] = u8f(b.y, 2);
-        float o[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            float s = __fmul_rn(v[q], k0);
-            s = fmaf(v[q + 1], k1, s); s = fmaf(v[q + 2], k2, s); s = fmaf(v[q + 3], k3, s);
-            s = fmaf(v[q + 4], k2, s); s = fmaf(v[q + 5], k1, s); s = fmaf(v[q + 6], k0, s);
-            o[q] = s;
+    int item = blockIdx.x;
+    if (tid == 0 && item < total) issue(item, 0);
+    for (int it = 0; item < total; it++) {
+        const int buf = it & 1;
+        const int ti = item % ntiles, f = item / ntiles;
+        const Tile t = tiles[ti];
+        const LevelGeom& L = plan->L[t.level];
+        if (tid == 0) {
+            const int nxt = atomicAdd(work_counter, 1) + (int)gridDim.x;
+            s_next[buf] = nxt;
+            if (nxt < total) issue(nxt, buf ^ 1);
         }
-        float4* op = reinterpret_cast<float4*>(rowp + r * BT_W + 8 * seg);
-        op[0] = make_float4(o[0], o[1], o[2], o[3]);
-        op[1] = make_float4(o[4], o[5], o[6], o[7]);
-    }
-    __syncthreads();
-    // column pass: one task = 4 columns x 4 rows of outputs (10 row-pass rows, float4 loads)
-    uint8_t* out = blurred + (size_t)f * fbytes + L.plane_off;
-    for (int task = tid; task < (BT_W / 4) * (BT_H / 4); task += 256) {
-        const int cg = task & 15, rg = task >> 4;
-        const float4* rp = reinterpret_cast<const float4*>(rowp + (rg * 4) * BT_W + cg * 4);
-        float4 R[10];
+        mbar_wait(&bar[buf], (uint32_t)((it >> 1) & 1));
+        const uint32_t* img = reinterpret_cast<const uint32_t*>(img2[buf]);
+        // row pass: one task = 8 adjacent outputs of one row; ROI column x0+c sits at tile byte 16+c
+        for (int task = tid; task < BI_H * (BT_W / 8); task += 256) {
+            const int r = task >> 3, seg = task & 7;
+            const uint32_t* ip = img + r * BIW + 3 + 2 * seg;          // bytes 12+8seg .. 27+8seg
+            const uint32_t ax = ip[0], ay = ip[1], bx = ip[2], by = ip[3];
+            float v[14];
+            v[0] = u8f(ax, 1); v[1] = u8f(ax, 2); v[2] = u8f(ax, 3);
+            v[3] = u8f(ay, 0); v[4] = u8f(ay, 1); v[5] = u8f(ay, 2); v[6] = u8f(ay, 3);
+            v[7] = u8f(bx, 0); v[8] = u8f(bx, 1); v[9] = u8f(bx, 2); v[10] = u8f(bx, 3);
+            v[11] = u8f(by, 0); v[12] = u8f(by, 1); v[13] = u8f(by, 2);
+            float o[8];
 #pragma unroll
-        for (int q = 0; q < 10; q++) R[q] = rp[q * (BT_W / 4)];
-        const int x = t.x0 + cg * 4;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int y = t.y0 + rg * 4 + q;
-            uint32_t w = 0;
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-#define RV(i) (e == 0 ? R[i].x : e == 1 ? R[i].y : e == 2 ? R[i].z : R[i].w)
-                float s = __fmul_rn(k3, RV(q + 3));
-                s = fmaf(__fadd_rn(RV(q + 4), RV(q + 2)), k2, s);
-                s = fmaf(__fadd_rn(RV(q + 5), RV(q + 1)), k1, s);
-                s = fmaf(__fadd_rn(RV(q + 6), RV(q)), k0, s);
-#undef RV
-                // rint via the 1.5*2^23 magic constant (0 <= s < 2^22), then saturate to 255
-                const uint32_t iv = min(__float_as_uint(__fadd_rn(s, 12582912.0f)) & 0x3ffu, 255u);
-                w |= iv << (8 * e);
+            for (int q = 0; q < 8; q++) {
+                float s = __fmul_rn(v[q], k0);
+                s = fmaf(v[q + 1], k1, s); s = fmaf(v[q + 2], k2, s); s = fmaf(v[q + 3], k3, s);
+                s = fmaf(v[q + 4], k2, s); s = fmaf(v[q + 5], k1, s); s = fmaf(v[q + 6], k0, s);
+                o[q] = s;
             }
-            if (y < L.h && x < L.w)      // bytes past the ROI edge land in the border of the blurred plane, which is never read
-                *reinterpret_cast<uint32_t*>(out + (size_t)(y + ORB_EDGE) * L.stride + x + ORB_EDGE) = w;
+            float4* op = reinterpret_cast<float4*>(rowp + r * BT_W + 8 * seg);
+            op[0] = make_float4(o[0], o[1], o[2], o[3]);
+            op[1] = make_float4(o[4], o[5], o[6], o[7]);
         }
+        __syncthreads();
+        // column pass: one task = 4 columns x 4 rows of outputs (10 row-pass rows, float4 loads)
+        uint8_t* out = blurred + (size_t)f * fbytes + L.plane_off;
+        for (int task = tid; task < (BT_W / 4) * (BT_H / 4); task += 256) {
+            const int cg = task & 15, rg = task >> 4;
+            const float4* rp = reinterpret_cast<const float4*>(rowp + (rg * 4) * BT_W + cg * 4);
+            float4 R[10];
+#pragma unroll
+            for (int q = 0; q < 10; q++) R[q] = rp[q * (BT_W / 4)];
+            const int x = t.x0 + cg * 4;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int y = t.y0 + rg * 4 + q;
+                uint32_t w = 0;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+#define RV(i) (e == 0 ? R[i].x : e == 1 ? R[i].y : e == 2 ? R[i].z : R[i].w)
+                    float s = __fmul_rn(k3, RV(q + 3));
+                    s = fmaf(__fadd_rn(RV(q + 4), RV(q + 2)), k2, s);
+                    s = fmaf(__fadd_rn(RV(q + 5), RV(q + 1)), k1, s);
+                    s = fmaf(__fadd_rn(RV(q + 6), RV(q)), k0, s);
+#undef RV
+                    // rint via the 1.5*2^23 magic constant (0 <= s < 2^22), then saturate to 255
+                    const uint32_t iv = min(__float_as_uint(__fadd_rn(s, 12582912.0f)) & 0x3ffu, 255u);
+                    w |= iv << (8 * e);
+                }
+                if (y < L.h && x < L.w)      // bytes past the ROI edge land in the border of the blurred plane, which is never read
+                    *reinterpret_cast<uint32_t*>(out + (size_t)(y + ORB_EDGE) * L.stride + x + ORB_EDGE) = w;
+            }
+        }
+        __syncthreads();          // rowp and the other image buffer are reused by the next item
+        item = s_next[buf];
     }
 }
 
@@ -823,7 +843,12 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w, int h
     for (int l = 0; l < P.nlevels; l++) maxcap = std::max(maxcap, P.L[l].lvl_cap);
     k_select<<<dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s>>>(c->d_plan, c->d_cells, c->d_cand, c->d_ntotal, c->d_lvl, c->d_nkept, c->d_status);
     mark();
-    k_blur<<<dim3(P.ntiles_blur, nimg), 256, 0, s>>>(c->d_planes, c->d_work, fb, c->d_plan, c->d_tiles_blur);
+    {
+        const int total = P.ntiles_blur * nimg;
+        const int grid = std::min(total, c->num_sms * 4);
+        cudaMemsetAsync(c->d_status + 2, 0, sizeof(int), s);
+        k_blur<<<grid, 256, 0, s>>>(c->tm_blur, c->d_work, fb, c->d_plan, c->d_tiles_blur, P.ntiles_blur, total, c->d_status + 2);
+    }
     mark();
     const int slots = std::min(cap, P.kp_cap);
     k_describe<<<dim3((std::max(slots, 1) + 7) / 8, nimg), 256, 0, s>>>(c->d_planes, c->d_work, fb, c->d_plan, c->d_lvl, c->d_nkept,
