@@ -111,6 +111,7 @@ static int prepare(orb_ctx* c, int w, int h, int nimg)
     int rc;
     rc = ensure(c->d_planes, c->planes_bytes, B * P.frame_bytes); if (rc) return rc;
     rc = ensure(c->d_work, c->work_bytes, B * P.frame_bytes); if (rc) return rc;
+    rc = ensure(c->d_blur, c->blur_bytes, B * P.frame_bytes); if (rc) return rc;
     rc = ensure(c->d_cand, c->cand_bytes, B * (size_t)P.cand_total * 4); if (rc) return rc;
     rc = ensure(c->d_ntotal, c->ntotal_bytes, B * (size_t)P.ncells * 4); if (rc) return rc;
     rc = ensure(c->d_lvl, c->lvl_bytes, B * (size_t)P.lvl_total * 8); if (rc) return rc;
@@ -161,6 +162,9 @@ orb_ctx* orb_create(int device, int nfeatures, float scale_factor, int nlevels, 
         ok = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming) == cudaSuccess;
     }
+    ok = ok && cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { orb_cuda_fail(cudaGetLastError(), "orb_create allocations"); orb_destroy(c); return nullptr; }
     return c;
 }
@@ -171,9 +175,12 @@ void orb_destroy(orb_ctx* c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     void* ptrs[] = { c->d_plan, c->d_cells, c->d_tiles_fast, c->d_tiles_blur, c->d_xtab, c->d_ytab, c->d_planes, c->d_work,
-                     c->d_cand, c->d_ntotal, c->d_lvl, c->d_nkept, c->d_status, c->d_src[0], c->d_src[1], c->d_kps[0],
+                     c->d_blur, c->d_cand, c->d_ntotal, c->d_lvl, c->d_nkept, c->d_status, c->d_src[0], c->d_src[1], c->d_kps[0],
                      c->d_kps[1], c->d_desc[0], c->d_desc[1], c->d_counts[0], c->d_counts[1], c->d_knn_part, c->d_match_scratch };
     for (void* p : ptrs) if (p) cudaFree(p);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) {
@@ -338,7 +345,7 @@ int orb_debug_level_plane(orb_ctx* c, int frame, int level, int which, uint8_t* 
     if (out_bytes < bytes) return ORB_ERR_CAPACITY;
     ORB_CUDA(cudaSetDevice(c->device));
     ORB_CUDA(cudaDeviceSynchronize());
-    const uint8_t* src = (which ? c->d_work : c->d_planes) + (size_t)frame * c->plan.frame_bytes + L.plane_off;
+    const uint8_t* src = (which ? c->d_blur : c->d_planes) + (size_t)frame * c->plan.frame_bytes + L.plane_off;
     ORB_CUDA(cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
     return ORB_OK;
 }

@@ -829,6 +829,16 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w, int h
     }
     k_border<<<dim3((P.border_total + 255) / 256, nimg), 256, 0, s>>>(c->d_planes, fb, c->d_plan);
     launches++;
+    // k_blur only needs the finished pyramid: outside profiling mode it runs on a second stream,
+    // concurrently with FAST -> compaction -> selection (the selection kernel is latency bound and
+    // leaves most of the machine idle); k_describe joins both.
+    const bool fork = !c->profile;
+    auto launch_blur = [&](cudaStream_t bs) {
+        const int total = P.ntiles_blur * nimg;
+        const int grid = std::min(total, c->num_sms * 4);
+        cudaMemsetAsync(c->d_status + 2, 0, sizeof(int), bs);
+        k_blur<<<grid, 256, 0, bs>>>(c->tm_blur, c->d_blur, fb, c->d_plan, c->d_tiles_blur, P.ntiles_blur, total, c->d_status + 2);
+    };
     mark();
     {
         const int total = P.ntiles_fast * nimg;
@@ -838,20 +848,20 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w, int h
     }
     mark();
     k_cell_compact<<<dim3((P.ncells + 7) / 8, nimg), 256, 0, s>>>(c->d_work, fb, c->d_plan, c->d_cells, c->d_cand, c->d_ntotal);
-    mark();
-    int maxcap = 0;
-    for (int l = 0; l < P.nlevels; l++) maxcap = std::max(maxcap, P.L[l].lvl_cap);
-    k_select<<<dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s>>>(c->d_plan, c->d_cells, c->d_cand, c->d_ntotal, c->d_lvl, c->d_nkept, c->d_status);
-    mark();
-    {
-        const int total = P.ntiles_blur * nimg;
-        const int grid = std::min(total, c->num_sms * 4);
-        cudaMemsetAsync(c->d_status + 2, 0, sizeof(int), s);
-        k_blur<<<grid, 256, 0, s>>>(c->tm_blur, c->d_work, fb, c->d_plan, c->d_tiles_blur, P.ntiles_blur, total, c->d_status + 2);
+    if (fork) {          // blur starts when compaction is done, i.e. next to the selection kernel
+        ORB_CUDA(cudaEventRecord(c->ev_fork, s));
+        ORB_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+        launch_blur(c->aux_stream);
+        ORB_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
     }
     mark();
+    k_select<<<dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s>>>(c->d_plan, c->d_cells, c->d_cand, c->d_ntotal, c->d_lvl, c->d_nkept, c->d_status);
+    mark();
+    if (fork) ORB_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
+    else launch_blur(s);
+    mark();
     const int slots = std::min(cap, P.kp_cap);
-    k_describe<<<dim3((std::max(slots, 1) + 7) / 8, nimg), 256, 0, s>>>(c->d_planes, c->d_work, fb, c->d_plan, c->d_lvl, c->d_nkept,
+    k_describe<<<dim3((std::max(slots, 1) + 7) / 8, nimg), 256, 0, s>>>(c->d_planes, c->d_blur, fb, c->d_plan, c->d_lvl, c->d_nkept,
                                                                     d_kps, d_desc, cap, d_counts);
     mark();
     launches += 5;

@@ -88,7 +88,9 @@ struct orb_ctx {
     int2* d_xtab = nullptr; int2* d_ytab = nullptr;
     size_t cap_cells = 0, cap_tiles_fast = 0, cap_tiles_blur = 0, cap_xtab = 0, cap_ytab = 0;
     uint8_t* d_planes = nullptr;  size_t planes_bytes = 0;
-    uint8_t* d_work = nullptr;    size_t work_bytes = 0;     // NMS score map, then blurred planes
+    uint8_t* d_work = nullptr;    size_t work_bytes = 0;     // NMS score map
+    uint8_t* d_blur = nullptr;    size_t blur_bytes = 0;     // blurred ROIs (own buffer: k_blur overlaps compaction/selection)
+    cudaStream_t aux_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint32_t* d_cand = nullptr;   size_t cand_bytes = 0;
     int* d_ntotal = nullptr;      size_t ntotal_bytes = 0;
     unsigned long long* d_lvl = nullptr; size_t lvl_bytes = 0;
