@@ -30,6 +30,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# rank 0 prints exactly one JSON line on stdout: keep NCCL's version banner out of it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 W, H, NFEAT, NLEVELS, SCALE, FAST_TH = 752, 480, 1000, 8, 1.2, 20
 METRIC = "ORB frames/sec (752x480 EuRoC-shaped synthetic frames, 1000 kp, 8 levels, scale 1.2)"

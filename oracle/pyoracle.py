@@ -304,3 +304,24 @@ def three_maxima(sizes):
     i1, i2, i3 = C.c_int(), C.c_int(), C.c_int()
     lib().orc_three_maxima(_p(s), len(s), C.byref(i1), C.byref(i2), C.byref(i3))
     return i1.value, i2.value, i3.value
+
+
+def merge_best2(parts):
+    """Exact merge of per-shard (idx1, d1, d2) triples, shards in ascending global-index order
+    (SURVEY.md §8e): best = first strict minimum, second = 2nd smallest of the multiset union.
+    parts: int array [nshards, 3, nq] -> (idx1, d1, d2)."""
+    parts = np.asarray(parts)
+    nq = parts.shape[2]
+    I, D1, D2 = np.full(nq, -1, np.int32), np.full(nq, 2**31 - 1, np.int32), np.full(nq, 2**31 - 1, np.int32)
+    for s in range(parts.shape[0]):
+        pi, p1, p2 = parts[s]
+        for i in range(nq):
+            if pi[i] < 0:
+                continue
+            if p1[i] < D1[i]:
+                D2[i] = D1[i]; D1[i] = p1[i]; I[i] = pi[i]
+            elif p1[i] < D2[i]:
+                D2[i] = p1[i]
+            if p2[i] < D2[i]:
+                D2[i] = p2[i]
+    return I, D1, D2

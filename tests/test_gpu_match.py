@@ -215,3 +215,59 @@ def test_three_maxima_rule(po):
     assert po.three_maxima(h) == (3, 7, -1)                 # max3 < 0.1*max1 dropped
     h[5] = 10
     assert po.three_maxima(h) == (3, 7, 5)
+
+
+def test_sharded_merge_kernel_equals_single_scan(pkg, po, matcher):
+    """k_knn2_merge over emulated shards (one GPU, several row ranges) == one scan over the whole DB."""
+    import ctypes as C
+    import torch
+    from orbslam_jpminipc_b200._lib import check, lib, ptr
+    from orbslam_jpminipc_b200.sharding import shard_range
+    from orbslam_jpminipc_b200.synth import synth_descriptors
+    db, q = synth_descriptors(30011, 500, dup_frac=0.02)
+    dev = torch.device("cuda", 0)
+    d_db, d_q = torch.from_numpy(db).to(dev), torch.from_numpy(q).to(dev)
+    nq, world = len(q), 5
+    allp = torch.zeros((world, 3, nq), dtype=torch.int32, device=dev)
+    L = lib()
+    st = torch.cuda.current_stream().cuda_stream
+    for r in range(world):
+        lo, hi = shard_range(len(db), r, world)
+        p = allp[r]
+        check(L.orb_hamming_knn2_device(matcher._h, ptr(d_q), nq, C.c_void_p(d_db.data_ptr() + lo * 32), hi - lo, 1, lo,
+                                        C.c_void_p(p.data_ptr()), C.c_void_p(p.data_ptr() + 4 * nq), C.c_void_p(p.data_ptr() + 8 * nq),
+                                        C.c_void_p(st)), "knn2 shard")
+    out = torch.zeros((3, nq), dtype=torch.int32, device=dev)
+    check(L.orb_knn2_merge_device(matcher._h, ptr(allp), world, nq, C.c_void_p(out.data_ptr()), C.c_void_p(out.data_ptr() + 4 * nq),
+                                  C.c_void_p(out.data_ptr() + 8 * nq), C.c_void_p(st)), "merge")
+    torch.cuda.synchronize()
+    ref = po.knn2(q, db)
+    got = out.cpu().numpy()
+    assert all(np.array_equal(got[k], ref[k]) for k in range(3))
+    assert all(np.array_equal(a, b) for a, b in zip(po.merge_best2(allp.cpu().numpy()), ref))
+
+
+def test_cpp_shim_program(pkg, po, tmp_path):
+    """The header-only C++ shims (include/ORBextractor.h, include/ORBmatcher.h) through a compiled host program."""
+    import os
+    import subprocess
+    from orbslam_jpminipc_b200.synth import synth_frame
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "test_shim")
+    libdir = os.path.join(root, "orbslam_jpminipc_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(root, "tests", "cpp", "test_shim.cpp"),
+                           "-L" + libdir, "-lorb_b200", "-Wl,-rpath," + libdir])
+    img = synth_frame(240, 320, 8100)
+    raw, out = str(tmp_path / "f.raw"), str(tmp_path / "o.bin")
+    img.tofile(raw)
+    subprocess.check_call([exe, raw, "320", "240", "300", out])
+    buf = open(out, "rb").read()
+    n, nmatch = np.frombuffer(buf[:8], np.int32)
+    kps = np.frombuffer(buf[8:8 + 28 * n], pkg.KP_DTYPE)
+    desc = np.frombuffer(buf[8 + 28 * n:8 + 60 * n], np.uint8).reshape(n, 32)
+    match = np.frombuffer(buf[8 + 60 * n:], np.int32)
+    rk, rd = po.OracleExtractor(300)(img)
+    assert n == len(rk) and np.array_equal(kps.view(np.uint8), rk.view(np.uint8)) and np.array_equal(desc, rd)
+    i1, d1, d2 = po.knn2(rd, rd)
+    rm, rn = po.match_ratio(i1, d1, d2, np.float32(0.9), 50)
+    assert nmatch == rn and np.array_equal(match, rm)
