@@ -112,6 +112,7 @@ static int prepare(orb_ctx* c, int w, int h, int nimg)
     rc = ensure(c->d_planes, c->planes_bytes, B * P.frame_bytes); if (rc) return rc;
     rc = ensure(c->d_work, c->work_bytes, B * P.frame_bytes); if (rc) return rc;
     rc = ensure(c->d_blur, c->blur_bytes, B * P.frame_bytes); if (rc) return rc;
+    rc = ensure(c->d_bitmap, c->bitmap_bytes, B * (size_t)std::max(P.bm_total, 256)); if (rc) return rc;
     rc = ensure(c->d_cand, c->cand_bytes, B * (size_t)P.cand_total * 4); if (rc) return rc;
     rc = ensure(c->d_ntotal, c->ntotal_bytes, B * (size_t)P.ncells * 4); if (rc) return rc;
     rc = ensure(c->d_lvl, c->lvl_bytes, B * (size_t)P.lvl_total * 8); if (rc) return rc;
@@ -175,7 +176,7 @@ void orb_destroy(orb_ctx* c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     void* ptrs[] = { c->d_plan, c->d_cells, c->d_tiles_fast, c->d_tiles_blur, c->d_xtab, c->d_ytab, c->d_planes, c->d_work,
-                     c->d_blur, c->d_cand, c->d_ntotal, c->d_lvl, c->d_nkept, c->d_status, c->d_src[0], c->d_src[1], c->d_kps[0],
+                     c->d_blur, c->d_bitmap, c->d_cand, c->d_ntotal, c->d_lvl, c->d_nkept, c->d_status, c->d_src[0], c->d_src[1], c->d_kps[0],
                      c->d_kps[1], c->d_desc[0], c->d_desc[1], c->d_counts[0], c->d_counts[1], c->d_knn_part, c->d_match_scratch };
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);

@@ -147,7 +147,11 @@ k_border(uint8_t* __restrict__ planes, size_t fbytes, const Plan* __restrict__ p
 constexpr int FT_W = ORB_TILE_W, FT_H = ORB_TILE_H;
 constexpr int FIW = 24, FI_H = FT_H + 8;   // image tile: 24 words (cols x0-16..x0+79) x rows y0-4..y0+35; TMA needs a 16-byte aligned x origin
 constexpr int FSW = 18, FS_H = FT_H + 2;   // score tile: 18 words (cols x0-4..x0+67) x rows y0-1..y0+32
-constexpr int FAST_THREADS = 320;
+#ifndef ORB_FAST_THREADS
+#define ORB_FAST_THREADS 128      // measured on B200: 320x3 1.75 ms, 256x4 1.56, 128x8 1.46, 64x16 1.43 per 256 frames
+#define ORB_FAST_CTAS 8
+#endif
+constexpr int FAST_THREADS = ORB_FAST_THREADS, FAST_CTAS = ORB_FAST_CTAS;
 
 __device__ __forceinline__ uint32_t lo16x2(uint32_t w) { return __byte_perm(w, 0, 0x4140); }   // bytes 0,1 -> u16 lanes
 __device__ __forceinline__ uint32_t hi16x2(uint32_t w) { return __byte_perm(w, 0, 0x4342); }   // bytes 2,3 -> u16 lanes
@@ -213,8 +217,8 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
 
 // Persistent kernel: each CTA walks (tile, frame) work items; the image tile of item i+1 is fetched by
 // TMA into the other shared-memory buffer while item i is being scored.
-__global__ void __launch_bounds__(FAST_THREADS, 3)
-k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, size_t fbytes,
+__global__ void __launch_bounds__(FAST_THREADS, FAST_CTAS)
+k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_t* __restrict__ bitmap, size_t fbytes,
            const Plan* __restrict__ plan, const Tile* __restrict__ tiles, int ntiles, int total, int* __restrict__ work_counter)
 {
     __shared__ __align__(128) uint32_t img2[2][FI_H * FIW];
@@ -257,29 +261,31 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, size_t
         }
 
         // detection-cell id of every score-tile column / row (-1: outside every detection rectangle)
-        if (tid < FSW * 4) {
-            const int x = t.x0 - 4 + tid;
-            int c = -1;
-            if (x >= ORB_EDGE) {
-                c = (x - ORB_EDGE) / L.cellW;
-                if (c >= L.cols - 1) { c = L.cols - 1; if (x >= L.w - ORB_EDGE) c = -1; }
+        for (int i = tid; i < FSW * 4 + FS_H; i += FAST_THREADS) {
+            if (i < FSW * 4) {
+                const int x = t.x0 - 4 + i;
+                int c = -1;
+                if (x >= ORB_EDGE) {
+                    c = (x - ORB_EDGE) / L.cellW;
+                    if (c >= L.cols - 1) { c = L.cols - 1; if (x >= L.w - ORB_EDGE) c = -1; }
+                }
+                colcell[i] = (short)c;
+            } else {
+                const int r = i - FSW * 4, y = t.y0 - 1 + r;
+                int c = -1;
+                if (y >= ORB_EDGE) {
+                    c = (y - ORB_EDGE) / L.cellH;
+                    if (c >= L.rows - 1) { c = L.rows - 1; if (y >= L.h - ORB_EDGE) c = -1; }
+                }
+                rowcell[r] = (short)c;
             }
-            colcell[tid] = (short)c;
-        } else if (tid >= 128 && tid < 128 + FS_H) {
-            const int i = tid - 128, y = t.y0 - 1 + i;
-            int c = -1;
-            if (y >= ORB_EDGE) {
-                c = (y - ORB_EDGE) / L.cellH;
-                if (c >= L.rows - 1) { c = L.rows - 1; if (y >= L.h - ORB_EDGE) c = -1; }
-            }
-            rowcell[i] = (short)c;
         }
         __syncthreads();
-        if (tid < FSW * 4) {          // byte masks: in region / left neighbour in same cell / right neighbour in same cell
-            const int c = colcell[tid];
-            m_in[tid] = c >= 0 ? 0xff : 0;
-            m_l[tid] = (tid > 0 && c >= 0 && colcell[tid - 1] == c) ? 0xff : 0;
-            m_r[tid] = (tid < FSW * 4 - 1 && c >= 0 && colcell[tid + 1] == c) ? 0xff : 0;
+        for (int i = tid; i < FSW * 4; i += FAST_THREADS) {   // byte masks: in region / left, right neighbour in same cell
+            const int c = colcell[i];
+            m_in[i] = c >= 0 ? 0xff : 0;
+            m_l[i] = (i > 0 && c >= 0 && colcell[i - 1] == c) ? 0xff : 0;
+            m_r[i] = (i < FSW * 4 - 1 && c >= 0 && colcell[i + 1] == c) ? 0xff : 0;
         }
         mbar_wait(&bar[buf], (uint32_t)((it >> 1) & 1));      // image tile has landed
         __syncthreads();
@@ -341,44 +347,61 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, size_t
         }
         __syncthreads();
 
-        // ---- NMS restricted to the pixel's own cell: one task = 4 output pixels, one 32-bit store ----
+        // ---- NMS restricted to the pixel's own cell: one task = 16 output pixels (four words): one 128-bit store
+        //      of responses to the score map and one 16-bit store to the survivor bitmap ----
         uint8_t* out = nms + (size_t)f * fbytes + L.plane_off;
-        for (int task = tid; task < FT_H * (FT_W / 4); task += FAST_THREADS) {
-            const int ro = task / (FT_W / 4), go = task - ro * (FT_W / 4);
-            const int r = ro + 1, g = go + 1;
-            const uint32_t* sp = sc + r * FSW + g;
-            const uint32_t c = sp[0];
-            uint32_t v = 0;
-            if (c) {
-                const uint32_t ml = reinterpret_cast<const uint32_t*>(m_l)[g], mr = reinterpret_cast<const uint32_t*>(m_r)[g];
-                const int rc = rowcell[r];
-                const bool up = rowcell[r - 1] == rc, dn = rowcell[r + 1] == rc;
-                uint32_t nb[8];
-                nb[0] = __funnelshift_r(sp[-1], c, 24) & ml;
-                nb[1] = __funnelshift_r(c, sp[1], 8) & mr;
-                const uint32_t ul = sp[-FSW - 1], uc = sp[-FSW], ur = sp[-FSW + 1];
-                nb[2] = up ? uc : 0u;
-                nb[3] = up ? (__funnelshift_r(ul, uc, 24) & ml) : 0u;
-                nb[4] = up ? (__funnelshift_r(uc, ur, 8) & mr) : 0u;
-                const uint32_t dl = sp[FSW - 1], dc = sp[FSW], dr = sp[FSW + 1];
-                nb[5] = dn ? dc : 0u;
-                nb[6] = dn ? (__funnelshift_r(dl, dc, 24) & ml) : 0u;
-                nb[7] = dn ? (__funnelshift_r(dc, dr, 8) & mr) : 0u;
-                uint32_t mlo = __vimax3_u16x2(__vimax3_u16x2(lo16x2(nb[0]), lo16x2(nb[1]), lo16x2(nb[2])),
-                                              __vimax3_u16x2(lo16x2(nb[3]), lo16x2(nb[4]), lo16x2(nb[5])),
-                                              __vmaxu2(lo16x2(nb[6]), lo16x2(nb[7])));
-                uint32_t mhi = __vimax3_u16x2(__vimax3_u16x2(hi16x2(nb[0]), hi16x2(nb[1]), hi16x2(nb[2])),
-                                              __vimax3_u16x2(hi16x2(nb[3]), hi16x2(nb[4]), hi16x2(nb[5])),
-                                              __vmaxu2(hi16x2(nb[6]), hi16x2(nb[7])));
-                const uint32_t s0 = c & 0xff, s1 = (c >> 8) & 0xff, s2 = (c >> 16) & 0xff, s3 = c >> 24;
-                if (s0 > (mlo & 0xffff)) v |= s0;            // strictly greater than all 8 neighbours; s == 0 never passes
-                if (s1 > (mlo >> 16)) v |= s1 << 8;
-                if (s2 > (mhi & 0xffff)) v |= s2 << 16;
-                if (s3 > (mhi >> 16)) v |= s3 << 24;
+        uint8_t* bm = bitmap + (size_t)f * plan->bm_total + L.bm_off;
+        for (int task = tid; task < FT_H * (FT_W / 16); task += FAST_THREADS) {
+            const int ro = task >> 2, q4 = task & 3;
+            const int r = ro + 1;
+            const int rc = rowcell[r];
+            const bool up = rowcell[r - 1] == rc, dn = rowcell[r + 1] == rc;
+            uint32_t vv[4];
+            uint32_t bits = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int g = q4 * 4 + j + 1;
+                const uint32_t* sp = sc + r * FSW + g;
+                const uint32_t c = sp[0];
+                uint32_t v = 0;
+                if (c) {
+                    const uint32_t ml = reinterpret_cast<const uint32_t*>(m_l)[g], mr = reinterpret_cast<const uint32_t*>(m_r)[g];
+                    uint32_t nb[8];
+                    nb[0] = __funnelshift_r(sp[-1], c, 24) & ml;
+                    nb[1] = __funnelshift_r(c, sp[1], 8) & mr;
+                    const uint32_t ul = sp[-FSW - 1], uc = sp[-FSW], ur = sp[-FSW + 1];
+                    nb[2] = up ? uc : 0u;
+                    nb[3] = up ? (__funnelshift_r(ul, uc, 24) & ml) : 0u;
+                    nb[4] = up ? (__funnelshift_r(uc, ur, 8) & mr) : 0u;
+                    const uint32_t dl = sp[FSW - 1], dc = sp[FSW], dr = sp[FSW + 1];
+                    nb[5] = dn ? dc : 0u;
+                    nb[6] = dn ? (__funnelshift_r(dl, dc, 24) & ml) : 0u;
+                    nb[7] = dn ? (__funnelshift_r(dc, dr, 8) & mr) : 0u;
+                    const uint32_t mlo = __vimax3_u16x2(__vimax3_u16x2(lo16x2(nb[0]), lo16x2(nb[1]), lo16x2(nb[2])),
+                                                        __vimax3_u16x2(lo16x2(nb[3]), lo16x2(nb[4]), lo16x2(nb[5])),
+                                                        __vmaxu2(lo16x2(nb[6]), lo16x2(nb[7])));
+                    const uint32_t mhi = __vimax3_u16x2(__vimax3_u16x2(hi16x2(nb[0]), hi16x2(nb[1]), hi16x2(nb[2])),
+                                                        __vimax3_u16x2(hi16x2(nb[3]), hi16x2(nb[4]), hi16x2(nb[5])),
+                                                        __vmaxu2(hi16x2(nb[6]), hi16x2(nb[7])));
+                    const uint32_t s0 = c & 0xff, s1 = (c >> 8) & 0xff, s2 = (c >> 16) & 0xff, s3 = c >> 24;
+                    // strictly greater than all 8 neighbours; s == 0 never passes
+                    if (s0 > (mlo & 0xffff)) { v |= s0; bits |= 1u << (4 * j); }
+                    if (s1 > (mlo >> 16)) { v |= s1 << 8; bits |= 2u << (4 * j); }
+                    if (s2 > (mhi & 0xffff)) { v |= s2 << 16; bits |= 4u << (4 * j); }
+                    if (s3 > (mhi >> 16)) { v |= s3 << 24; bits |= 8u << (4 * j); }
+                }
+                vv[j] = v;
             }
-            const int py = t.y0 + ro + ORB_EDGE, px = t.x0 + go * 4 + ORB_EDGE;
-            if (py < L.prows && px + 3 < L.stride)
-                *reinterpret_cast<uint32_t*>(out + (size_t)py * L.stride + px) = v;
+            const int py = t.y0 + ro + ORB_EDGE, px = t.x0 + q4 * 16 + ORB_EDGE;
+            if (py < L.prows && px + 15 < L.stride)
+                *reinterpret_cast<uint4*>(out + (size_t)py * L.stride + px) = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+            else if (py < L.prows) {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (px + 4 * j + 3 < L.stride) *reinterpret_cast<uint32_t*>(out + (size_t)py * L.stride + px + 4 * j) = vv[j];
+            }
+            // bitmap: bit i of row y (ROI) = ROI column 16+i ; tiles start at ROI x0 = 16 + 64k
+            *reinterpret_cast<uint16_t*>(bm + (size_t)(t.y0 + ro - ORB_EDGE) * L.bm_pitch + ((t.x0 - ORB_EDGE) >> 3) + q4 * 2) = (uint16_t)bits;
         }
         __syncthreads();       // masks / score tile are rewritten by the next item
         item = s_next[buf];
@@ -394,7 +417,7 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, size_t
 // ("one-pass fallback").
 // record = score<<24 | y_local<<12 | x_local   (cell-image coordinates, as cv::FAST reports)
 __global__ void __launch_bounds__(256)
-k_cell_compact(const uint8_t* __restrict__ nms, size_t fbytes, const Plan* __restrict__ plan,
+k_cell_compact(const uint8_t* __restrict__ nms, const uint8_t* __restrict__ bitmap, size_t fbytes, const Plan* __restrict__ plan,
                const CellGeom* __restrict__ cells, uint32_t* __restrict__ cand, int* __restrict__ ntotal)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -403,39 +426,48 @@ k_cell_compact(const uint8_t* __restrict__ nms, size_t fbytes, const Plan* __res
     const CellGeom g = cells[warp];
     const LevelGeom& L = plan->L[g.level];
     const uint8_t* map = nms + (size_t)f * fbytes + L.plane_off + (size_t)ORB_EDGE * L.stride + ORB_EDGE;
+    const uint32_t* bm = reinterpret_cast<const uint32_t*>(bitmap + (size_t)f * plan->bm_total + L.bm_off);
     uint32_t* out = cand + (size_t)f * plan->cand_total + g.cand_off;
     const int thP = plan->fast_th;
     int count = 0, nP = 0, n7 = 0;
-    const uint32_t lt = (1u << lane) - 1;
-    const int xa = g.x0 & ~3;
-    for (int y = g.y0; y < g.y1; y++) {
-        const uint8_t* row = map + (size_t)y * L.stride;
-        for (int xb = xa; xb < g.x1; xb += 128) {
-            const int x = xb + 4 * lane;
-            uint32_t wv = 0;
-            if (x < g.x1) wv = *reinterpret_cast<const uint32_t*>(row + x);
-            uint32_t s[4];
-            bool nz[4];
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                s[b] = (wv >> (8 * b)) & 0xff;
-                if (x + b < g.x0 || x + b >= g.x1) s[b] = 0;
-                nz[b] = s[b] != 0;
-                nP += (int)s[b] >= thP;
-                n7 += s[b] >= 7;
-            }
-            const uint32_t m0 = __ballot_sync(0xffffffffu, nz[0]), m1 = __ballot_sync(0xffffffffu, nz[1]);
-            const uint32_t m2 = __ballot_sync(0xffffffffu, nz[2]), m3 = __ballot_sync(0xffffffffu, nz[3]);
-            if ((m0 | m1 | m2 | m3) == 0) continue;
-            int pos = count + __popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt);
-#pragma unroll
-            for (int b = 0; b < 4; b++)
-                if (nz[b]) out[pos++] = (s[b] << 24) | ((uint32_t)(y - g.iniy) << 12) | (uint32_t)(x + b - g.inix);
-            count += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+    // The rectangle is walked as (row, 32-pixel bitmap word) items in raster order; a lane owns one item per step.
+    const int b0 = g.x0 - ORB_EDGE, b1 = g.x1 - ORB_EDGE;            // bit range [b0, b1) of a bitmap row
+    const int w0 = b0 >> 5, wpr = b1 > b0 ? ((b1 - 1) >> 5) - w0 + 1 : 0;
+    const int nitems = (g.y1 - g.y0) * wpr;
+    const int pitchw = L.bm_pitch >> 2;
+    for (int i0 = 0; i0 < nitems; i0 += 32) {
+        const int i = i0 + lane;
+        uint32_t word = 0;
+        int y = 0, xbase = 0;
+        if (i < nitems) {
+            const int rr = i / wpr, wi = i - rr * wpr;
+            y = g.y0 + rr;
+            word = bm[(size_t)(y - ORB_EDGE) * pitchw + w0 + wi];
+            const int bit0 = (w0 + wi) << 5;                         // bit index of the word's LSB
+            if (bit0 < b0) word &= 0xffffffffu << (b0 - bit0);
+            if (bit0 + 32 > b1) word &= 0xffffffffu >> (bit0 + 32 - b1);
+            xbase = bit0 + ORB_EDGE;                                 // ROI x of the word's LSB
         }
+        const int cnt = __popc(word);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int tv = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += tv; }
+        int pos = count + incl - cnt;
+        const uint8_t* row = map + (size_t)y * L.stride;
+        while (word) {
+            const int b = __ffs(word) - 1;
+            word &= word - 1;
+            const int x = xbase + b;
+            const uint32_t s = row[x];
+            nP += (int)s >= thP;
+            n7 += s >= 7;
+            out[pos++] = (s << 24) | ((uint32_t)(y - g.iniy) << 12) | (uint32_t)(x - g.inix);
+        }
+        count += __shfl_sync(0xffffffffu, incl, 31);
     }
     nP = __reduce_add_sync(0xffffffffu, nP);
     n7 = __reduce_add_sync(0xffffffffu, n7);
+    const uint32_t lt = (1u << lane) - 1;
     const int thr = nP > 3 ? thP : 7;
     const int want = nP > 3 ? nP : n7;
     if (want < count) {           // drop the weaker corners, keeping raster order (in place, warp-synchronous)
@@ -842,12 +874,12 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w, int h
     mark();
     {
         const int total = P.ntiles_fast * nimg;
-        const int grid = std::min(total, c->num_sms * 3);
+        const int grid = std::min(total, c->num_sms * FAST_CTAS);
         cudaMemsetAsync(c->d_status + 1, 0, sizeof(int), s);
-        k_fast_nms<<<grid, FAST_THREADS, 0, s>>>(c->tm_fast, c->d_work, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total, c->d_status + 1);
+        k_fast_nms<<<grid, FAST_THREADS, 0, s>>>(c->tm_fast, c->d_work, c->d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total, c->d_status + 1);
     }
     mark();
-    k_cell_compact<<<dim3((P.ncells + 7) / 8, nimg), 256, 0, s>>>(c->d_work, fb, c->d_plan, c->d_cells, c->d_cand, c->d_ntotal);
+    k_cell_compact<<<dim3((P.ncells + 7) / 8, nimg), 256, 0, s>>>(c->d_work, c->d_bitmap, fb, c->d_plan, c->d_cells, c->d_cand, c->d_ntotal);
     if (fork) {          // blur starts when compaction is done, i.e. next to the selection kernel
         ORB_CUDA(cudaEventRecord(c->ev_fork, s));
         ORB_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));

@@ -32,6 +32,7 @@ struct LevelGeom {
     int xtab_off, ytab_off;// offsets into the resize coefficient tables (int2 entries)
     int kp_base;           // prefix of nDesired over levels (unused slots stay empty)
     int border_base;       // first k_border work item of this level
+    int bm_off, bm_pitch;  // NMS-survivor bitmap of this level: byte offset in the frame's bitmap block, row pitch in bytes (bit i = ROI x 16+i)
 };
 
 struct Plan {
@@ -43,6 +44,7 @@ struct Plan {
     int kp_cap;            // sum of nDesired
     int fast_th, th_lo;
     int ntiles_fast, ntiles_blur;
+    int bm_total;          // bitmap bytes per frame
     int sel_list_cap;      // max lvl_cap over levels (k_select shared-memory list)
     int border_total;      // k_border work items (32-bit words of all frame regions) per image
     LevelGeom L[ORB_MAX_LEVELS];
@@ -91,6 +93,7 @@ struct orb_ctx {
     uint8_t* d_work = nullptr;    size_t work_bytes = 0;     // NMS score map
     uint8_t* d_blur = nullptr;    size_t blur_bytes = 0;     // blurred ROIs (own buffer: k_blur overlaps compaction/selection)
     cudaStream_t aux_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    uint8_t* d_bitmap = nullptr;  size_t bitmap_bytes = 0;   // 1 bit per detection pixel: NMS survivor
     uint32_t* d_cand = nullptr;   size_t cand_bytes = 0;
     int* d_ntotal = nullptr;      size_t ntotal_bytes = 0;
     unsigned long long* d_lvl = nullptr; size_t lvl_bytes = 0;

@@ -86,7 +86,7 @@ int orb_build_plan(orb_ctx* c, int w, int h)
     P.fast_th = c->fast_th; P.th_lo = std::min(c->fast_th, 7);
     c->cells.clear(); c->tiles_fast.clear(); c->tiles_blur.clear(); c->xtab.clear(); c->ytab.clear();
 
-    int off = 0, cand = 0, lvl = 0, kp = 0, border = 0;
+    int off = 0, cand = 0, lvl = 0, kp = 0, border = 0, bm = 0;
     const float imageRatio = (float)w / h;                                   // :527
     for (int l = 0; l < P.nlevels; l++) {
         LevelGeom& L = P.L[l];
@@ -162,6 +162,9 @@ int orb_build_plan(orb_ctx* c, int w, int h)
                 c->cells.push_back(g);
             }
         }
+        L.bm_pitch = ((std::max(L.xend - ORB_EDGE, 0) + 63) / 64) * 8;          // whole 64-px tiles, 8 bytes each
+        L.bm_off = bm;
+        bm += ((L.bm_pitch * std::max(((L.yend - ORB_EDGE + ORB_TILE_H - 1) / ORB_TILE_H) * ORB_TILE_H, 0) + 255) & ~255);
         L.lvl_base = lvl;
         L.lvl_cap = L.nDesired + L.ncells + (L.ncells * L.ncells) / 2 + 64;
         lvl += L.lvl_cap;
@@ -178,6 +181,7 @@ int orb_build_plan(orb_ctx* c, int w, int h)
     P.lvl_total = lvl;
     P.kp_cap = kp;
     P.border_total = border;
+    P.bm_total = bm;
     P.sel_list_cap = 0;
     for (int l = 0; l < P.nlevels; l++) P.sel_list_cap = std::max(P.sel_list_cap, P.L[l].lvl_cap);
     P.ntiles_fast = (int)c->tiles_fast.size();
