@@ -49,6 +49,12 @@ int orb_build_tmaps(orb_ctx* c, int nframes)
         CUresult r2 = enc(&c->tm_blur.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box_blur, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (l + 1 < P.nlevels && r1 == CUDA_SUCCESS) {       // source descriptor for the resize that produces level l+1
+            cuuint32_t box_rs[3] = { (cuuint32_t)c->rs_box_w[l + 1], (cuuint32_t)c->rs_box_h[l + 1], 1 };
+            r1 = enc(&c->tm_resize.m[l + 1], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box_rs, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
         if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
             g_last_cuda_error = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r1) + "," + std::to_string((int)r2) + ")";
             return ORB_ERR_CUDA;
@@ -102,7 +108,7 @@ static int prepare(orb_ctx* c, int w, int h, int nimg)
         if ((size_t)maxcap * 8 > 170 * 1024) return ORB_ERR_CAPACITY;
         rc = orb_select_smem_setup(maxcap * 8 + 6144 * 4 + 1024); if (rc) return rc;
         size_t rsm = 1024;
-        for (int l = 1; l < c->plan.nlevels; l++) rsm = std::max(rsm, ((size_t)c->rs_rows[l] * c->rs_words[l] + 4 + (size_t)c->rs_rows[l] * 64) * 4);
+        for (int l = 1; l < c->plan.nlevels; l++) rsm = std::max(rsm, (size_t)2 * (((size_t)c->rs_box_w[l] * c->rs_box_h[l] + 127) & ~(size_t)127));
         rc = orb_resize_smem_setup((int)rsm); if (rc) return rc;
         c->plan_valid = true;
     }
@@ -157,8 +163,8 @@ orb_ctx* orb_create(int device, int nfeatures, float scale_factor, int nlevels, 
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (orb_build_tables(c) != ORB_OK || orb_upload_constants(c->umax) != ORB_OK) { delete c; return nullptr; }
     bool ok = cudaMalloc((void**)&c->d_nkept, sizeof(int) * ORB_MAX_LEVELS * max_batch) == cudaSuccess &&
-              cudaMalloc((void**)&c->d_status, 4 * sizeof(int)) == cudaSuccess &&     // [0] status, [1..] work counters
-              cudaMemset(c->d_status, 0, 4 * sizeof(int)) == cudaSuccess;
+              cudaMalloc((void**)&c->d_status, 32 * sizeof(int)) == cudaSuccess &&     // [0] status, [1..] work counters
+              cudaMemset(c->d_status, 0, 32 * sizeof(int)) == cudaSuccess;
     for (int i = 0; i < 2 && ok; i++) {
         ok = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming) == cudaSuccess;

@@ -81,7 +81,7 @@ struct orb_ctx {
     std::vector<CellGeom> cells;
     std::vector<Tile> tiles_fast, tiles_blur;
     std::vector<int2> xtab, ytab;
-    int rs_words[ORB_MAX_LEVELS] = { 0 }, rs_rows[ORB_MAX_LEVELS] = { 0 };   // k_resize source footprint per level
+    int rs_box_w[ORB_MAX_LEVELS] = { 0 }, rs_box_h[ORB_MAX_LEVELS] = { 0 };   // k_resize TMA box (source footprint of a 128x64 tile)
 
     // device buffers
     Plan* d_plan = nullptr;
@@ -108,7 +108,7 @@ struct orb_ctx {
     cudaStream_t streams[2] = { nullptr, nullptr };
     cudaEvent_t ev_free[2] = { nullptr, nullptr };
     int last_launches = 0;
-    TmapSet tm_fast{}, tm_blur{};          // boxes: FAST image tile / blur input tile
+    TmapSet tm_fast{}, tm_blur{}, tm_resize{};   // boxes: FAST image tile / blur input tile / resize source footprint (map l reads level l-1)
     const uint8_t* tm_base = nullptr; int tm_frames = 0; int tm_w = 0, tm_h = 0;
     int num_sms = 148;
     bool profile = false;

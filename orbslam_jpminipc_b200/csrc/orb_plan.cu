@@ -103,19 +103,19 @@ int orb_build_plan(orb_ctx* c, int w, int h)
         if (l > 0) {
             axis_table(P.L[l - 1].w, L.w, true, c->xtab);
             axis_table(P.L[l - 1].h, L.h, false, c->ytab);
-            // largest source footprint of a 64x16 output tile (k_resize shared-memory staging)
-            int mw = 1, mr = 1;
-            for (int x0 = 0; x0 < L.w; x0 += 64) {
-                const int x1 = std::min(x0 + 64, L.w) - 1;
-                const int lo = (c->xtab[L.xtab_off + x0].x & 0xffff) & ~3, hi = c->xtab[L.xtab_off + x1].x >> 16;
-                mw = std::max(mw, (hi - lo) / 4 + 1);
+            // largest source footprint of a 128x64 output tile, from a 16-byte aligned origin (k_resize TMA box)
+            int mw = 16, mr = 1;
+            for (int x0 = 0; x0 < L.w; x0 += 128) {
+                const int x1 = std::min(x0 + 128, L.w) - 1;
+                const int lo = (c->xtab[L.xtab_off + x0].x & 0xffff) & ~15, hi = c->xtab[L.xtab_off + x1].x >> 16;
+                mw = std::max(mw, hi - lo + 1);
             }
-            for (int y0 = 0; y0 < L.h; y0 += 16) {
-                const int y1 = std::min(y0 + 16, L.h) - 1;
+            for (int y0 = 0; y0 < L.h; y0 += 64) {
+                const int y1 = std::min(y0 + 64, L.h) - 1;
                 mr = std::max(mr, (c->ytab[L.ytab_off + y1].x >> 16) - (c->ytab[L.ytab_off + y0].x & 0xffff) + 1);
             }
-            c->rs_words[l] = mw; c->rs_rows[l] = mr;
-            if (((size_t)mr * mw + (size_t)mr * 64) * 4 > 200 * 1024) return ORB_ERR_CAPACITY;
+            c->rs_box_w[l] = (mw + 15) & ~15; c->rs_box_h[l] = mr;
+            if (c->rs_box_w[l] > 256 || mr > 256) return ORB_ERR_CAPACITY;      // TMA box limit (scale factors above ~1.9)
         }
         L.border_base = border;
         border += 2 * ORB_EDGE * (L.stride / 4) + L.h * (4 + L.stride / 4 - (ORB_EDGE + L.w) / 4);
