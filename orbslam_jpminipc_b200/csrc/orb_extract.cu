@@ -189,7 +189,7 @@ k_resize(const __grid_constant__ CUtensorMap tm, uint8_t* __restrict__ planes, s
 // resize, FAST and IC_Angle stay inside the ROI.  One thread per 32-bit word of the frame region
 // (a warp-per-row variant measured slower: 0.51 vs 0.45 ms for resize+border per 256 frames).
 __global__ void __launch_bounds__(256)
-k_border(uint8_t* __restrict__ planes, size_t fbytes, const Plan* __restrict__ plan)
+k_border(uint8_t* __restrict__ planes, uint8_t* __restrict__ blurred, size_t fbytes, const Plan* __restrict__ plan)
 {
     int item = blockIdx.x * blockDim.x + threadIdx.x;
     if (item >= plan->border_total) return;
@@ -214,6 +214,9 @@ k_border(uint8_t* __restrict__ planes, size_t fbytes, const Plan* __restrict__ p
         if (px < L.w + 2 * ORB_EDGE) v |= (uint32_t)srow[reflect101(px - ORB_EDGE, L.w)] << (8 * k);
     }
     *reinterpret_cast<uint32_t*>(plane + (size_t)py * L.stride + wx * 4) = v;
+    // the in-place blur of the reference leaves the frame un-blurred (:760): give the blurred buffer the same frame so
+    // that the descriptor sampler reads one buffer only (k_blur later rewrites exactly the ROI bytes)
+    *reinterpret_cast<uint32_t*>(blurred + (size_t)blockIdx.y * fbytes + L.plane_off + (size_t)py * L.stride + wx * 4) = v;
 }
 
 // ------------------------------------------------------------------ K2
@@ -735,8 +738,11 @@ k_blur(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ blurred, size_t
                     const uint32_t iv = min(__float_as_uint(__fadd_rn(s, 12582912.0f)) & 0x3ffu, 255u);
                     w |= iv << (8 * e);
                 }
-                if (y < L.h && x < L.w)      // bytes past the ROI edge land in the border of the blurred plane, which is never read
-                    *reinterpret_cast<uint32_t*>(out + (size_t)(y + ORB_EDGE) * L.stride + x + ORB_EDGE) = w;
+                if (y < L.h && x < L.w) {    // exactly the ROI bytes: the frame of the blurred buffer holds the un-blurred reflection
+                    uint8_t* o = out + (size_t)(y + ORB_EDGE) * L.stride + x + ORB_EDGE;
+                    if (x + 3 < L.w) *reinterpret_cast<uint32_t*>(o) = w;
+                    else for (int e = 0; x + e < L.w; e++) o[e] = (uint8_t)(w >> (8 * e));
+                }
             }
         }
         __syncthreads();          // rowp and the other image buffer are reused by the next item
@@ -750,6 +756,7 @@ const int8_t h_pattern[1024] = {
 };
 // rBRIEF pattern transposed for the warp: entry [(2*k+e)*32 + lane] = sample e of test k of descriptor byte `lane`
 __device__ float2 g_pattern_t[16 * 32];
+__device__ uint32_t g_rowmask[32];      // IC_Angle disc: bit (v+15) of entry `lane` set iff |lane-15| <= umax[|v|]
 __constant__ int c_umax[16];
 
 // cv::fastAtan2 (degrees), every operation individually rounded to FP32 (no contraction)
@@ -806,19 +813,21 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
     const int stride = L.stride;
     const unsigned long long rec = lvl[(size_t)f * plan->lvl_total + L.lvl_base + idx];
     const int x = (int)(rec & 0xffff), y = (int)((rec >> 16) & 0xffff), score = (int)(rec >> 32);
-    const uint8_t* roi = planes + (size_t)f * fbytes + L.plane_off + (size_t)ORB_EDGE * stride + ORB_EDGE;
-    const ptrdiff_t bdelta = blurred - planes;             // same layout in both buffers
-    const uint8_t* center = roi + (size_t)y * stride + x;
+    const size_t poff = (size_t)f * fbytes + L.plane_off + (size_t)(ORB_EDGE + y) * stride + ORB_EDGE + x;
+    const uint8_t* center = planes + poff;                  // un-blurred plane: orientation
+    const uint8_t* bcenter = blurred + poff;                // blurred ROI + un-blurred frame: descriptor
 
-    // IC_Angle (:124-151): m10 = sum u*I, m01 = sum v*I over the radius-15 disc
+    // IC_Angle (:124-151): m10 = sum u*I, m01 = sum v*I over the radius-15 disc; lane = column u
     int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int u = lane - 15, au = abs(u);
+    {
+        const int u = lane - 15;
+        const uint32_t rows = g_rowmask[lane];              // bit (v+15): |u| <= umax[|v|]
+        const uint8_t* p = center + u - 15 * stride;
         int colsum = 0;
 #pragma unroll
-        for (int v = -15; v <= 15; v++) {
-            if (au <= c_umax[v < 0 ? -v : v]) {
-                const int val = center[v * stride + u];
+        for (int v = -15; v <= 15; v++, p += stride) {
+            if ((rows >> (v + 15)) & 1) {
+                const int val = *p;
                 colsum += val; m01 += v * val;
             }
         }
@@ -832,9 +841,11 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
     const float factorPI = (float)(3.14159265358979323846 / 180.f);
     const float arad = __fmul_rn(angle, factorPI);
     float a, b;
-    if (lane == 0) { a = (float)cos((double)arad); b = (float)sin((double)arad); }
+    if (lane == 0) { double sd, cd; sincos((double)arad, &sd, &cd); a = (float)cd; b = (float)sd; }
     a = __shfl_sync(0xffffffffu, a, 0); b = __shfl_sync(0xffffffffu, b, 0);
     const float2* pat = g_pattern_t + lane;
+    // offset = cvRound(y')*stride + cvRound(x'); the 1.5*2^23 magic add leaves the rounded integer in the mantissa
+    const uint32_t magic_fix = 0u - 0x4B400000u * (uint32_t)(stride + 1);      // modulo-2^32 arithmetic, exact for the in-range result
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -842,13 +853,9 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
 #pragma unroll
         for (int e = 0; e < 2; e++) {
             const float2 p = __ldg(pat + (2 * k + e) * 32);
-            const int iy = rint_magic(__fadd_rn(__fmul_rn(p.x, b), __fmul_rn(p.y, a)));
-            const int ix = rint_magic(__fsub_rn(__fmul_rn(p.x, a), __fmul_rn(p.y, b)));
-            const int sx = x + ix, sy = y + iy;
-            // the in-place blur only rewrites the ROI: samples that fall into the 16-px border
-            // read the un-blurred reflected pixels (:760)
-            const bool inside = (unsigned)sx < (unsigned)L.w && (unsigned)sy < (unsigned)L.h;
-            t[e] = roi[(ptrdiff_t)sy * stride + sx + (inside ? bdelta : (ptrdiff_t)0)];
+            const uint32_t yb = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(p.x, b), __fmul_rn(p.y, a)), 12582912.0f));
+            const uint32_t xb = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(p.x, a), __fmul_rn(p.y, b)), 12582912.0f));
+            t[e] = bcenter[(int)(yb * (uint32_t)stride + xb + magic_fix)];
         }
         val |= (t[0] < t[1]) << k;
     }
@@ -876,6 +883,13 @@ int orb_upload_constants(const int* umax)
                 t[(2 * k + e) * 32 + lane] = make_float2((float)p[0], (float)p[1]);
             }
     ORB_CUDA(cudaMemcpyToSymbol(g_pattern_t, t, sizeof t));
+    uint32_t rm[32];
+    for (int lane = 0; lane < 32; lane++) {
+        rm[lane] = 0;
+        const int au = lane < 31 ? (lane > 15 ? lane - 15 : 15 - lane) : 99;
+        for (int v = -15; v <= 15; v++) if (au <= umax[v < 0 ? -v : v]) rm[lane] |= 1u << (v + 15);
+    }
+    ORB_CUDA(cudaMemcpyToSymbol(g_rowmask, rm, sizeof rm));
     return ORB_OK;
 }
 
@@ -913,7 +927,7 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w, int h
                                                bufb, nimg, c->d_status + 4 + l);
         launches++;
     }
-    k_border<<<dim3((P.border_total + 255) / 256, nimg), 256, 0, s>>>(c->d_planes, fb, c->d_plan);
+    k_border<<<dim3((P.border_total + 255) / 256, nimg), 256, 0, s>>>(c->d_planes, c->d_blur, fb, c->d_plan);
     launches++;
     // k_blur only needs the finished pyramid: outside profiling mode it runs on a second stream,
     // concurrently with FAST -> compaction -> selection (the selection kernel is latency bound and
