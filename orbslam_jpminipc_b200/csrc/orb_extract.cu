@@ -893,7 +893,7 @@ int orb_upload_constants(const int* umax)
     return ORB_OK;
 }
 
-int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w, int h, int stride, size_t frame_pitch,
+int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, int w, int h, int stride, size_t frame_pitch,
                        orb_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts, cudaStream_t s)
 {
     const Plan& P = c->plan;
@@ -913,7 +913,7 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w, int h
         const LevelGeom& L = P.L[0];
         dim3 grid((w + 255) / 256, (h + 3) / 4, nimg);
         const int aligned4 = (((uintptr_t)d_imgs | (uintptr_t)stride | (uintptr_t)frame_pitch) & 3) == 0;
-        k_level0<<<grid, blk, 0, s>>>(d_imgs, w, h, stride, frame_pitch, aligned4, c->d_planes, fb, L.stride);
+        k_level0<<<grid, blk, 0, s>>>(d_imgs, w, h, stride, frame_pitch, aligned4, W.d_planes, fb, L.stride);
         launches++;
     }
     mark();
@@ -922,12 +922,12 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w, int h
         const int tiles = ((D.w + RT_W - 1) / RT_W) * ((D.h + RT_H - 1) / RT_H) * nimg;
         const int bufb = (c->rs_box_w[l] * c->rs_box_h[l] + 127) & ~127;
         const int grid = std::min(tiles, c->num_sms * 4);
-        cudaMemsetAsync(c->d_status + 4 + l, 0, sizeof(int), s);
-        k_resize<<<grid, 256, 2 * bufb, s>>>(c->tm_resize.m[l], c->d_planes, fb, D, c->d_xtab, c->d_ytab, c->rs_box_w[l], c->rs_box_h[l],
-                                               bufb, nimg, c->d_status + 4 + l);
+        cudaMemsetAsync(W.d_counters + 4 + l, 0, sizeof(int), s);
+        k_resize<<<grid, 256, 2 * bufb, s>>>(W.tm_resize.m[l], W.d_planes, fb, D, c->d_xtab, c->d_ytab, c->rs_box_w[l], c->rs_box_h[l],
+                                               bufb, nimg, W.d_counters + 4 + l);
         launches++;
     }
-    k_border<<<dim3((P.border_total + 255) / 256, nimg), 256, 0, s>>>(c->d_planes, c->d_blur, fb, c->d_plan);
+    k_border<<<dim3((P.border_total + 255) / 256, nimg), 256, 0, s>>>(W.d_planes, W.d_blur, fb, c->d_plan);
     launches++;
     // k_blur only needs the finished pyramid: outside profiling mode it runs on a second stream,
     // concurrently with FAST -> compaction -> selection (the selection kernel is latency bound and
@@ -935,33 +935,38 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w, int h
     const bool fork = !c->profile;
     auto launch_blur = [&](cudaStream_t bs) {
         const int total = P.ntiles_blur * nimg;
-        const int grid = std::min(total, c->num_sms * 4);
-        cudaMemsetAsync(c->d_status + 2, 0, sizeof(int), bs);
-        k_blur<<<grid, 256, 0, bs>>>(c->tm_blur, c->d_blur, fb, c->d_plan, c->d_tiles_blur, P.ntiles_blur, total, c->d_status + 2);
+        const int grid = std::min(total, c->num_sms * c->blur_ctas);
+        cudaMemsetAsync(W.d_counters + 2, 0, sizeof(int), bs);
+        k_blur<<<grid, 256, 0, bs>>>(W.tm_blur, W.d_blur, fb, c->d_plan, c->d_tiles_blur, P.ntiles_blur, total, W.d_counters + 2);
     };
+    if (fork && c->fork_early) {          // blur next to FAST: FAST saturates the ALU pipe and leaves the FMA pipe idle
+        ORB_CUDA(cudaEventRecord(W.ev_fork, s));
+        ORB_CUDA(cudaStreamWaitEvent(W.aux_stream, W.ev_fork, 0));
+    }
     mark();
     {
         const int total = P.ntiles_fast * nimg;
-        const int grid = std::min(total, c->num_sms * FAST_CTAS);
-        cudaMemsetAsync(c->d_status + 1, 0, sizeof(int), s);
-        k_fast_nms<<<grid, FAST_THREADS, 0, s>>>(c->tm_fast, c->d_work, c->d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total, c->d_status + 1);
+        const int grid = std::min(total, c->num_sms * (fork && c->fork_early ? c->fast_ctas : FAST_CTAS));
+        cudaMemsetAsync(W.d_counters + 1, 0, sizeof(int), s);
+        k_fast_nms<<<grid, FAST_THREADS, 0, s>>>(W.tm_fast, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total, W.d_counters + 1);
+    }
+    if (fork && c->fork_early) { launch_blur(W.aux_stream); ORB_CUDA(cudaEventRecord(W.ev_join, W.aux_stream)); }
+    mark();
+    k_cell_compact<<<dim3((P.ncells + 7) / 8, nimg), 256, 0, s>>>(W.d_work, W.d_bitmap, fb, c->d_plan, c->d_cells, W.d_cand, W.d_ntotal);
+    if (fork && !c->fork_early) {          // blur starts when compaction is done, i.e. next to the selection kernel
+        ORB_CUDA(cudaEventRecord(W.ev_fork, s));
+        ORB_CUDA(cudaStreamWaitEvent(W.aux_stream, W.ev_fork, 0));
+        launch_blur(W.aux_stream);
+        ORB_CUDA(cudaEventRecord(W.ev_join, W.aux_stream));
     }
     mark();
-    k_cell_compact<<<dim3((P.ncells + 7) / 8, nimg), 256, 0, s>>>(c->d_work, c->d_bitmap, fb, c->d_plan, c->d_cells, c->d_cand, c->d_ntotal);
-    if (fork) {          // blur starts when compaction is done, i.e. next to the selection kernel
-        ORB_CUDA(cudaEventRecord(c->ev_fork, s));
-        ORB_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
-        launch_blur(c->aux_stream);
-        ORB_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
-    }
+    k_select<<<dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s>>>(c->d_plan, c->d_cells, W.d_cand, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status);
     mark();
-    k_select<<<dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s>>>(c->d_plan, c->d_cells, c->d_cand, c->d_ntotal, c->d_lvl, c->d_nkept, c->d_status);
-    mark();
-    if (fork) ORB_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
+    if (fork) ORB_CUDA(cudaStreamWaitEvent(s, W.ev_join, 0));
     else launch_blur(s);
     mark();
     const int slots = std::min(cap, P.kp_cap);
-    k_describe<<<dim3((std::max(slots, 1) + 7) / 8, nimg), 256, 0, s>>>(c->d_planes, c->d_blur, fb, c->d_plan, c->d_lvl, c->d_nkept,
+    k_describe<<<dim3((std::max(slots, 1) + 7) / 8, nimg), 256, 0, s>>>(W.d_planes, W.d_blur, fb, c->d_plan, W.d_lvl, W.d_nkept,
                                                                     d_kps, d_desc, cap, d_counts);
     mark();
     launches += 5;

@@ -65,6 +65,22 @@ struct Tile { int level, x0, y0, pad; };
 // one TMA descriptor per pyramid level: u8 tensor (x = padded row bytes, y = padded rows, z = frame)
 struct TmapSet { CUtensorMap m[ORB_MAX_LEVELS]; };
 
+// per-stream work buffers of the extraction pipeline
+struct WorkSet {
+    uint8_t* d_planes = nullptr;  size_t planes_bytes = 0;     // un-blurred padded pyramids
+    uint8_t* d_work = nullptr;    size_t work_bytes = 0;       // NMS score map
+    uint8_t* d_blur = nullptr;    size_t blur_bytes = 0;       // blurred ROIs + un-blurred frame
+    uint8_t* d_bitmap = nullptr;  size_t bitmap_bytes = 0;     // 1 bit per detection pixel: NMS survivor
+    uint32_t* d_cand = nullptr;   size_t cand_bytes = 0;
+    int* d_ntotal = nullptr;      size_t ntotal_bytes = 0;
+    unsigned long long* d_lvl = nullptr; size_t lvl_bytes = 0;
+    int* d_nkept = nullptr;       size_t nkept_bytes = 0;
+    int* d_counters = nullptr;    size_t counters_bytes = 0;   // dynamic tile-queue counters (32 ints)
+    TmapSet tm_fast{}, tm_blur{}, tm_resize{};                 // boxes: FAST tile / blur tile / resize source footprint (map l reads level l-1)
+    const uint8_t* tm_base = nullptr; int tm_frames = 0, tm_w = 0, tm_h = 0;
+    cudaStream_t aux_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+};
+
 struct orb_ctx {
     int device = 0;
     int nfeatures = 0, nlevels = 0, score_type = 1, fast_th = 20;
@@ -83,22 +99,18 @@ struct orb_ctx {
     std::vector<int2> xtab, ytab;
     int rs_box_w[ORB_MAX_LEVELS] = { 0 }, rs_box_h[ORB_MAX_LEVELS] = { 0 };   // k_resize TMA box (source footprint of a 128x64 tile)
 
-    // device buffers
+    // device tables (shared by both work sets)
     Plan* d_plan = nullptr;
     CellGeom* d_cells = nullptr;
     Tile* d_tiles_fast = nullptr; Tile* d_tiles_blur = nullptr;
     int2* d_xtab = nullptr; int2* d_ytab = nullptr;
     size_t cap_cells = 0, cap_tiles_fast = 0, cap_tiles_blur = 0, cap_xtab = 0, cap_ytab = 0;
-    uint8_t* d_planes = nullptr;  size_t planes_bytes = 0;
-    uint8_t* d_work = nullptr;    size_t work_bytes = 0;     // NMS score map
-    uint8_t* d_blur = nullptr;    size_t blur_bytes = 0;     // blurred ROIs (own buffer: k_blur overlaps compaction/selection)
-    cudaStream_t aux_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    uint8_t* d_bitmap = nullptr;  size_t bitmap_bytes = 0;   // 1 bit per detection pixel: NMS survivor
-    uint32_t* d_cand = nullptr;   size_t cand_bytes = 0;
-    int* d_ntotal = nullptr;      size_t ntotal_bytes = 0;
-    unsigned long long* d_lvl = nullptr; size_t lvl_bytes = 0;
-    int* d_nkept = nullptr;
-    int* d_status = nullptr;
+    int* d_status = nullptr;          // error flag raised by kernels
+    // two independent sets of work buffers: two chunks (or the two halves of one device batch) run on two streams
+    // so that one half's latency-bound selection overlaps the other half's FAST / blur
+    WorkSet ws[2];
+    cudaEvent_t ev_user = nullptr, ev_half[2] = { nullptr, nullptr };
+    int last_n0 = 0, last_n1 = 0;     // frames handled by ws[0] / ws[1] in the last launch (debug getters)
     // staging for host-pointer calls (two slots for copy/compute overlap)
     uint8_t* d_src[2] = { nullptr, nullptr };  size_t src_bytes[2] = { 0, 0 };
     size_t kps_bytes[2] = { 0, 0 }, desc_bytes[2] = { 0, 0 }, counts_bytes[2] = { 0, 0 };
@@ -108,9 +120,9 @@ struct orb_ctx {
     cudaStream_t streams[2] = { nullptr, nullptr };
     cudaEvent_t ev_free[2] = { nullptr, nullptr };
     int last_launches = 0;
-    TmapSet tm_fast{}, tm_blur{}, tm_resize{};   // boxes: FAST image tile / blur input tile / resize source footprint (map l reads level l-1)
-    const uint8_t* tm_base = nullptr; int tm_frames = 0; int tm_w = 0, tm_h = 0;
     int num_sms = 148;
+    int split_device = 0;
+    int fork_early = 0, fast_ctas = 6, blur_ctas = 4;      // stream-overlap tuning (ORB_FORK_EARLY / ORB_FAST_CTAS_FORK / ORB_BLUR_CTAS env)
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;   // (ORB_NSTAGES+1) per profiled launch
     std::vector<cudaEvent_t> prof_pool;
@@ -129,10 +141,10 @@ int orb_cuda_fail(cudaError_t e, const char* what);
 int orb_build_tables(orb_ctx* c);
 int orb_build_plan(orb_ctx* c, int w, int h);
 // orb_extract.cu
-int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w, int h, int stride, size_t frame_pitch,
+int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, int w, int h, int stride, size_t frame_pitch,
                        orb_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts, cudaStream_t s);
 int orb_upload_constants(const int* umax);
-int orb_build_tmaps(orb_ctx* c, int nframes);
+int orb_build_tmaps(orb_ctx* c, WorkSet& W, int nframes);
 int orb_select_smem_setup(int max_bytes);
 int orb_resize_smem_setup(int max_bytes);
 // orb_match.cu
