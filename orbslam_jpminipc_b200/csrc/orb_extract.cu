@@ -191,32 +191,50 @@ k_resize(const __grid_constant__ CUtensorMap tm, uint8_t* __restrict__ planes, s
 __global__ void __launch_bounds__(256)
 k_border(uint8_t* __restrict__ planes, uint8_t* __restrict__ blurred, size_t fbytes, const Plan* __restrict__ plan)
 {
-    int item = blockIdx.x * blockDim.x + threadIdx.x;
-    if (item >= plan->border_total) return;
-    int l = 0;
-    while (l + 1 < plan->nlevels && item >= plan->L[l + 1].border_base) l++;
+    // blockIdx.y = frame * nlevels + level; blockIdx.x walks the level's frame words (levels with fewer words exit)
+    const int l = blockIdx.y % plan->nlevels, f = blockIdx.y / plan->nlevels;
     const LevelGeom& L = plan->L[l];
-    item -= L.border_base;
+    int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= L.border_items) return;
+    const int w = L.w, h = L.h;
     const int wpr = L.stride >> 2;                      // words per padded row
     const int band = ORB_EDGE * wpr;                    // words in the top (or bottom) band
-    const int rw0 = (ORB_EDGE + L.w) >> 2;              // first word that contains right-frame pixels
+    const int rw0 = (ORB_EDGE + w) >> 2;                // first word that contains right-frame pixels
     const int side = 4 + (wpr - rw0);                   // frame words per middle row
     int py, wx;
-    if (item < band) { py = item / wpr; wx = item - py * wpr; }
-    else if (item < 2 * band) { item -= band; py = item / wpr; wx = item - py * wpr; py += ORB_EDGE + L.h; }
-    else { item -= 2 * band; py = item / side; wx = item - py * side; py += ORB_EDGE; if (wx >= 4) wx = rw0 + (wx - 4); }
-    uint8_t* plane = planes + (size_t)blockIdx.y * fbytes + L.plane_off;
-    const uint8_t* srow = plane + (size_t)(reflect101(py - ORB_EDGE, L.h) + ORB_EDGE) * L.stride + ORB_EDGE;
+    if (item < 2 * band) {                              // float reciprocal division is exact here (item < 2^23)
+        const int bi = item >= band;
+        if (bi) item -= band;
+        py = __float2int_rz(__fdividef((float)item + 0.5f, (float)wpr));
+        wx = item - py * wpr;
+        if (bi) py += ORB_EDGE + h;
+    } else {
+        item -= 2 * band;
+        py = __float2int_rz(__fdividef((float)item + 0.5f, (float)side));
+        wx = item - py * side;
+        py += ORB_EDGE;
+        if (wx >= 4) wx = rw0 + (wx - 4);
+    }
+    const size_t poff = (size_t)f * fbytes + L.plane_off;
+    int sy = py - ORB_EDGE;
+    if (sy < 0) sy = -sy; else if (sy >= h) sy = 2 * h - 2 - sy;
+    if ((unsigned)sy >= (unsigned)h) sy = reflect101(sy, h);            // only for ROIs lower than the frame
+    const uint8_t* srow = planes + poff + (size_t)(sy + ORB_EDGE) * L.stride + ORB_EDGE;
     uint32_t v = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int px = wx * 4 + k;
-        if (px < L.w + 2 * ORB_EDGE) v |= (uint32_t)srow[reflect101(px - ORB_EDGE, L.w)] << (8 * k);
+        int x = wx * 4 + k - ORB_EDGE;                  // ROI column of this byte
+        if (x < w + ORB_EDGE) {
+            if (x < 0) x = -x; else if (x >= w) x = 2 * w - 2 - x;
+            if ((unsigned)x >= (unsigned)w) x = reflect101(x, w);       // only for ROIs narrower than the frame
+            v |= (uint32_t)srow[x] << (8 * k);
+        }
     }
-    *reinterpret_cast<uint32_t*>(plane + (size_t)py * L.stride + wx * 4) = v;
+    const size_t o = poff + (size_t)py * L.stride + wx * 4;
+    *reinterpret_cast<uint32_t*>(planes + o) = v;
     // the in-place blur of the reference leaves the frame un-blurred (:760): give the blurred buffer the same frame so
     // that the descriptor sampler reads one buffer only (k_blur later rewrites exactly the ROI bytes)
-    *reinterpret_cast<uint32_t*>(blurred + (size_t)blockIdx.y * fbytes + L.plane_off + (size_t)py * L.stride + wx * 4) = v;
+    *reinterpret_cast<uint32_t*>(blurred + o) = v;
 }
 
 // ------------------------------------------------------------------ K2
@@ -927,7 +945,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
                                                bufb, nimg, W.d_counters + 4 + l);
         launches++;
     }
-    k_border<<<dim3((P.border_total + 255) / 256, nimg), 256, 0, s>>>(W.d_planes, W.d_blur, fb, c->d_plan);
+    k_border<<<dim3((P.L[0].border_items + 255) / 256, nimg * P.nlevels), 256, 0, s>>>(W.d_planes, W.d_blur, fb, c->d_plan);
     launches++;
     // k_blur only needs the finished pyramid: outside profiling mode it runs on a second stream,
     // concurrently with FAST -> compaction -> selection (the selection kernel is latency bound and

@@ -32,6 +32,7 @@ struct LevelGeom {
     int xtab_off, ytab_off;// offsets into the resize coefficient tables (int2 entries)
     int kp_base;           // prefix of nDesired over levels (unused slots stay empty)
     int border_base;       // first k_border work item of this level
+    int border_items;      // 32-bit words of this level's 16-px frame
     int bm_off, bm_pitch;  // NMS-survivor bitmap of this level: byte offset in the frame's bitmap block, row pitch in bytes (bit i = ROI x 16+i)
 };
 

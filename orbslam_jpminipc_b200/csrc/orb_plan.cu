@@ -118,7 +118,8 @@ int orb_build_plan(orb_ctx* c, int w, int h)
             if (c->rs_box_w[l] > 256 || mr > 256) return ORB_ERR_CAPACITY;      // TMA box limit (scale factors above ~1.9)
         }
         L.border_base = border;
-        border += 2 * ORB_EDGE * (L.stride / 4) + L.h * (4 + L.stride / 4 - (ORB_EDGE + L.w) / 4);
+        L.border_items = 2 * ORB_EDGE * (L.stride / 4) + L.h * (4 + L.stride / 4 - (ORB_EDGE + L.w) / 4);
+        border += L.border_items;
         // cell grid (:531-547)
         L.nDesired = c->mnFeaturesPerLevel[l];
         L.cols = (int)sqrtf((float)L.nDesired / (5 * imageRatio));
