@@ -130,48 +130,52 @@ void border_reflect101(uint8_t* plane, int w, int h, int stride, int b)
 const int kRing[16][2] = { {0,3},{1,3},{2,2},{3,1},{3,0},{3,-1},{2,-2},{1,-3},
                            {0,-3},{-1,-3},{-2,-2},{-3,-1},{-3,0},{-3,1},{-2,2},{-1,3} };
 
-inline int fast_score_px(const uint8_t* p, const int* ofs, int th)
+/* One image row of corner strengths, written so that the compiler vectorises over x (uint8 min/max):
+ *   bright = max_k min(ring[k..k+8]) - v,  dark = v - min_k max(ring[k..k+8]),  strength = max(bright, dark)
+ * which equals OpenCV's cornerScore<16> + 1 for corners (strength > th  <=>  corner at threshold th). */
+static void fast_strength_row(const uint8_t* row, int stride, int x0, int x1, int th, uint8_t* out /* [x0,x1) */)
 {
-    /* quick reject (same idea as OpenCV's table test): every 9-arc of the ring contains
-     * one pixel of each opposite pair, so a corner needs, for every pair, a member that is
-     * darker than v-th (bit 1) or brighter than v+th (bit 2), consistently. */
-    const int v = p[0], lo = v - th, hi = v + th;
-#define CLS(k) ((p[ofs[k]] < lo ? 1 : 0) | (p[ofs[k]] > hi ? 2 : 0))
-    int m = CLS(0) | CLS(8);
-    if (!m) return INT_MIN;
-    m &= CLS(4) | CLS(12);
-    if (!m) return INT_MIN;
-    m &= CLS(2) | CLS(10);
-    m &= CLS(6) | CLS(14);
-    if (!m) return INT_MIN;
-#undef CLS
-    int d[32];
-    for (int k = 0; k < 16; k++) d[k] = d[k + 16] = v - p[ofs[k]];
-    /* max over 16 arcs of min over 9 contiguous (darker ring) and of min of -d (brighter ring) */
-    int best = INT_MIN;
-    int m2[24], M2[24];
-    for (int k = 0; k < 24; k++) { m2[k] = std::min(d[k], d[k + 1]); M2[k] = std::max(d[k], d[k + 1]); }
+    enum { MAXW = 4096 };
+    alignas(64) uint8_t a[16][MAXW], bmin[MAXW], bmax[MAXW];
+    const int n = x1 - x0;
+    const uint8_t* r[16];
+    for (int k = 0; k < 16; k++) r[k] = row + kRing[k][1] * stride + kRing[k][0] + x0;
     for (int k = 0; k < 16; k++) {
-        int mn = std::min(std::min(m2[k], m2[k + 2]), std::min(m2[k + 4], m2[k + 6]));
-        int mx = std::max(std::max(M2[k], M2[k + 2]), std::max(M2[k + 4], M2[k + 6]));
-        mn = std::min(mn, d[k + 8]); mx = std::max(mx, d[k + 8]);
-        best = std::max(best, std::max(mn, -mx));
+        const uint8_t* __restrict__ p0 = r[k]; const uint8_t* __restrict__ p1 = r[(k + 1) & 15]; const uint8_t* __restrict__ p2 = r[(k + 2) & 15];
+        uint8_t* __restrict__ o = a[k];
+        for (int x = 0; x < n; x++) { uint8_t m = p0[x] < p1[x] ? p0[x] : p1[x]; o[x] = m < p2[x] ? m : p2[x]; }
     }
-    return best;   /* corner at threshold th  <=>  best > th ; response = best-1 */
+    for (int x = 0; x < n; x++) bmin[x] = 0;
+    for (int k = 0; k < 16; k++) {
+        const uint8_t* __restrict__ p0 = a[k]; const uint8_t* __restrict__ p1 = a[(k + 3) & 15]; const uint8_t* __restrict__ p2 = a[(k + 6) & 15];
+        uint8_t* __restrict__ o = bmin;
+        for (int x = 0; x < n; x++) { uint8_t m = p0[x] < p1[x] ? p0[x] : p1[x]; m = m < p2[x] ? m : p2[x]; o[x] = o[x] > m ? o[x] : m; }
+    }
+    for (int k = 0; k < 16; k++) {
+        const uint8_t* __restrict__ p0 = r[k]; const uint8_t* __restrict__ p1 = r[(k + 1) & 15]; const uint8_t* __restrict__ p2 = r[(k + 2) & 15];
+        uint8_t* __restrict__ o = a[k];
+        for (int x = 0; x < n; x++) { uint8_t m = p0[x] > p1[x] ? p0[x] : p1[x]; o[x] = m > p2[x] ? m : p2[x]; }
+    }
+    for (int x = 0; x < n; x++) bmax[x] = 255;
+    for (int k = 0; k < 16; k++) {
+        const uint8_t* __restrict__ p0 = a[k]; const uint8_t* __restrict__ p1 = a[(k + 3) & 15]; const uint8_t* __restrict__ p2 = a[(k + 6) & 15];
+        uint8_t* __restrict__ o = bmax;
+        for (int x = 0; x < n; x++) { uint8_t m = p0[x] > p1[x] ? p0[x] : p1[x]; m = m > p2[x] ? m : p2[x]; o[x] = o[x] < m ? o[x] : m; }
+    }
+    const uint8_t* v = row + x0;
+    for (int x = 0; x < n; x++) {
+        const int s = std::max((int)bmin[x] - (int)v[x], (int)v[x] - (int)bmax[x]);
+        out[x] = (uint8_t)(s > th ? s - 1 : 0);
+    }
 }
 
 int fast9_nms(const uint8_t* img, int w, int h, int stride, int th, std::vector<KP>& out)
 {
     out.clear();
-    if (w < 7 || h < 7) return 0;
-    int ofs[16];
-    for (int k = 0; k < 16; k++) ofs[k] = kRing[k][1] * stride + kRing[k][0];
+    if (w < 7 || h < 7 || w > 4096) return 0;
     std::vector<uint8_t> sc((size_t)w * h, 0);
     for (int y = 3; y < h - 3; y++)
-        for (int x = 3; x < w - 3; x++) {
-            int b = fast_score_px(img + (size_t)y * stride + x, ofs, th);
-            if (b > th) sc[(size_t)y * w + x] = (uint8_t)(b - 1);
-        }
+        fast_strength_row(img + (size_t)y * stride, stride, 3, w - 3, th, &sc[(size_t)y * w + 3]);
     for (int y = 3; y < h - 3; y++)
         for (int x = 3; x < w - 3; x++) {
             int s = sc[(size_t)y * w + x];
@@ -273,23 +277,34 @@ void gaussian_blur7(const uint8_t* src, int w, int h, int stride, uint8_t* dst, 
     if (variant == ORC_BLUR_F32_SEPFILTER) {
         float k[7];
         memcpy(k, kGaussBits, sizeof k);
+        /* loops run over x innermost so the compiler vectorises them; every pixel still sees the taps in
+         * the order i = 0..6 (row pass) and centre, +-1, +-2, +-3 (column pass), each step one fused multiply-add */
         std::vector<float> R((size_t)(h + 6) * w);
         for (int y = -3; y < h + 3; y++) {
-            const uint8_t* S = src + (ptrdiff_t)y * stride;
-            float* r = &R[(size_t)(y + 3) * w];
-            for (int x = 0; x < w; x++) {
-                float s = 0.f;
-                for (int i = 0; i < 7; i++) s = fmaf((float)S[x + i - 3], k[i], s);
-                r[x] = s;
+            const uint8_t* __restrict__ S = src + (ptrdiff_t)y * stride;
+            float* __restrict__ r = &R[(size_t)(y + 3) * w];
+            for (int x = 0; x < w; x++) r[x] = (float)S[x - 3] * k[0];
+            for (int i = 1; i < 7; i++) {
+                const float ki = k[i];
+                for (int x = 0; x < w; x++) r[x] = fmaf((float)S[x + i - 3], ki, r[x]);
             }
         }
+        std::vector<float> acc(w);
         for (int y = 0; y < h; y++) {
-            uint8_t* D = dst + (size_t)y * dstride;
+            uint8_t* __restrict__ D = dst + (size_t)y * dstride;
+            const float* __restrict__ c = &R[(size_t)(y + 3) * w];
+            float* __restrict__ s = acc.data();
+            for (int x = 0; x < w; x++) s[x] = k[3] * c[x];
+            for (int d = 1; d <= 3; d++) {
+                const float* __restrict__ p = c + (ptrdiff_t)d * w;
+                const float* __restrict__ m = c - (ptrdiff_t)d * w;
+                const float kd = k[3 + d];
+                for (int x = 0; x < w; x++) s[x] = fmaf(p[x] + m[x], kd, s[x]);
+            }
             for (int x = 0; x < w; x++) {
-                const float* c = &R[(size_t)(y + 3) * w + x];
-                float s = k[3] * c[0];
-                for (int d = 1; d <= 3; d++) s = fmaf(c[(ptrdiff_t)d * w] + c[-(ptrdiff_t)d * w], k[3 + d], s);
-                D[x] = sat_u8((int)lrintf(s));
+                float v = nearbyintf(s[x]);
+                v = v < 0.f ? 0.f : (v > 255.f ? 255.f : v);
+                D[x] = (uint8_t)(int)v;
             }
         }
         return;
