@@ -93,7 +93,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._halt.wait(0.05)
+            self._halt.wait(0.02)
 
     def stop(self):
         self._halt.set()
@@ -137,7 +137,7 @@ def run_reference(args):
         return
     from orbslam_jpminipc_b200.synth import synth_frames
     cores = os.cpu_count() or 1
-    per_step = max(cores * 2, 16)
+    per_step = max(cores * 8, 32)
     frames = synth_frames(min(per_step, 32), H, W, 1000)
     frames = [frames[i % len(frames)] for i in range(per_step)]
     for _ in range(args.warmup):
@@ -352,8 +352,14 @@ def run_gpu(args):
     nlaunch = (B + CH - 1) // CH                       # launches of each stage per step
     bytes_per_launch = alg[dom] * B / nlaunch
     achieved = bytes_per_launch / (stage[dom] / nlaunch * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum per frame from the committed `ncu --set full` capture
+    # (profiles/r1d_ncu_full_summary.md, 64-frame launches), scaled to this run's launch size
+    ncu_mb_per_frame = {"k_fast_nms": (77.3 + 40.5) / 64, "k_blur": (85.7 + 37.7) / 64, "k_describe": (117.3 + 7.0) / 64,
+                        "k_cell_compact": (64.4 + 1.3) / 64, "k_select": 6.6 / 64, "k_level0": 23.2 / 64}
+    traffic = ncu_mb_per_frame[dom] * 1e6 * B / nlaunch if dom in ncu_mb_per_frame and W == 752 else None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                "traffic": None, "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                "traffic": traffic, "alu_pipe_pct_ncu": 87.5 if dom == "k_fast_nms" else None,
+                "note": "k_fast_nms is integer-ALU bound (ncu: ALU pipe 87.5 % of peak, DRAM 3.8 %); the HBM fraction is the required yardstick, not its limiter", "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                 "kernel_ms_per_launch": stage[dom] / nlaunch, "stage_ms_per_step": stage, "profiled_ms_per_step": ms_profiled / args.steps,
                 "pipeline_bytes_per_frame": algorithmic_bytes_per_frame(W, H, nkp),
                 "pipeline_frac": (value / world) * algorithmic_bytes_per_frame(W, H, nkp) / (hbm * 1e9)}
@@ -381,13 +387,14 @@ def run_gpu(args):
             "roofline": roofline, "matching": matching}
     if args.cpu_baseline:
         cores = os.cpu_count() or 1
-        nfr = max(2 * cores, 16)
+        nfr = 64 * cores                                   # ~12 core-seconds of CPU work at ~80 frames/s/core
         fr = [base[i % len(base)] for i in range(nfr)]
-        fps1, _ = cpu_extract_rate(fr[:max(4, nfr // cores)], 1)
-        fpsN, dtN = cpu_extract_rate(fr * 4, cores)
+        fps1, dt1 = cpu_extract_rate(fr[:48], 1)
+        fpsN, dtN = cpu_extract_rate(fr, cores)
         line["cpu_baseline"] = {"value": fpsN, "unit": "frames/s", "cores": cores, "kind": "port", "single_thread_value": fps1,
-                                "sample": "%d frames of the same workload, frame-parallel over %d host threads (%.1f s); "
-                                          "single-thread figure on %d frames" % (4 * nfr, cores, dtN, max(4, nfr // cores))}
+                                "sample": "%d frames of the same workload, frame-parallel over %d host threads (%.1f s wall); "
+                                          "single-thread figure on 48 frames (%.1f s); oracle port of src/ORBextractor.cc "
+                                          "(the reference needs ROS + the OpenCV C++ SDK and cannot be built here)" % (nfr, cores, dtN, dt1)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -396,7 +403,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
