@@ -210,6 +210,7 @@ void orb_destroy(orb_ctx* c)
     for (cudaEvent_t e : c->ev_half) if (e) cudaEventDestroy(e);
     void* ptrs[] = { c->d_plan, c->d_cells, c->d_tiles_fast, c->d_tiles_blur, c->d_xtab, c->d_ytab, c->d_status, c->d_src[0], c->d_src[1], c->d_kps[0],
                      c->d_kps[1], c->d_desc[0], c->d_desc[1], c->d_counts[0], c->d_counts[1], c->d_knn_part, c->d_match_scratch };
+    if (c->h_match_arena) cudaFreeHost(c->h_match_arena);
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
@@ -422,8 +423,16 @@ int orb_descriptor_distance(const uint8_t* a, const uint8_t* b)
 }
 
 // scratch for host-pointer matcher calls
-static int match_scratch(orb_ctx* c, size_t bytes)
+static int match_scratch(orb_ctx* c, size_t bytes, size_t arena_bytes = 0)
 {
+    if (arena_bytes > c->match_arena_bytes || !c->h_match_arena) {
+        ORB_CUDA(cudaDeviceSynchronize());
+        if (c->h_match_arena) cudaFreeHost(c->h_match_arena);
+        c->h_match_arena = nullptr; c->match_arena_bytes = 0;
+        const size_t want = std::max<size_t>(arena_bytes, 1 << 20);
+        ORB_CUDA(cudaMallocHost((void**)&c->h_match_arena, want));
+        c->match_arena_bytes = want;
+    }
     if (bytes <= c->match_scratch_bytes && c->d_match_scratch) return ORB_OK;
     ORB_CUDA(cudaDeviceSynchronize());
     if (c->d_match_scratch) cudaFree(c->d_match_scratch);
@@ -541,17 +550,26 @@ int orb_frame_grid_build(orb_ctx* c, const orb_keypoint* kps, int n, int min_x, 
 } // extern "C"
 
 // bump allocator over the matcher scratch buffer; host arrays are uploaded, device arrays passed through
+// Host inputs are first gathered in a pinned arena that mirrors the scratch layout and then go up in ONE copy.
 struct Bump {
-    uint8_t* base; size_t off = 0, cap;
-    Bump(void* b, size_t c) : base((uint8_t*)b), cap(c) {}
+    uint8_t* base; uint8_t* hbase; size_t off = 0, cap, staged = 0;
+    Bump(void* b, void* h, size_t c) : base((uint8_t*)b), hbase((uint8_t*)h), cap(c) {}
     void* take(size_t bytes) { void* p = base + off; off += al256(std::max<size_t>(bytes, 1)); return p; }
+    int flush(cudaStream_t s)
+    {
+        if (staged) ORB_CUDA(cudaMemcpyAsync(base, hbase, staged, cudaMemcpyHostToDevice, s));
+        return ORB_OK;
+    }
 };
 template <typename T>
 static int stage_in(Bump& b, bool dev, const T*& p, size_t count, cudaStream_t s)
 {
+    (void)s;
     if (dev || !p) return ORB_OK;
+    const size_t o = b.off;
     T* d = (T*)b.take(count * sizeof(T));
-    if (count) ORB_CUDA(cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    if (count) memcpy(b.hbase + o, p, count * sizeof(T));
+    b.staged = b.off;
     p = d;
     return ORB_OK;
 }
@@ -591,9 +609,9 @@ int orb_search_by_projection(orb_ctx* c, const orb_frame_view* cur, const orb_fr
     cudaStream_t s = c->streams[0];
     const size_t work = orb_sbp_scratch_bytes(cur->n, last->n);
     const size_t in_bytes = dev ? 0 : frame_view_bytes(cur) + frame_view_bytes(last) + 2 * al256(last->n) + al256((size_t)last->n * 12) + al256((size_t)cur->n * 4);
-    int rc = match_scratch(c, 256 + in_bytes + work);
+    int rc = match_scratch(c, 256 + in_bytes + work, 256 + in_bytes + 4096);
     if (rc) return rc;
-    Bump b(c->d_match_scratch, c->match_scratch_bytes);
+    Bump b(c->d_match_scratch, c->h_match_arena, c->match_scratch_bytes);
     int* d_result = (int*)b.take(8);
     orb_frame_view dc = *cur, dl = *last;
     if ((rc = stage_frame(b, dev, dc, true, s)) || (rc = stage_frame(b, dev, dl, false, s))) return rc;
@@ -602,6 +620,7 @@ int orb_search_by_projection(orb_ctx* c, const orb_frame_view* cur, const orb_fr
     int32_t* d_match = match_cur;
     if (!dev) { const int32_t* m = match_cur; if ((rc = stage_in(b, false, m, (size_t)cur->n, s))) return rc; d_match = (int32_t*)m; }
     uint8_t* wk = (uint8_t*)b.take(work);
+    if ((rc = b.flush(s))) return rc;
     rc = orb_launch_search_by_projection(c, &dc, &dl, last_has_mp, last_outlier, last_xyz, T, th, check_ori, d_match, d_result, wk, work, s);
     if (rc) return rc;
     int res[2] = { 0, 0 };
@@ -634,9 +653,9 @@ int orb_search_by_bow(orb_ctx* c, const orb_featvec_view* kf_fv, const uint8_t* 
     if (!dev) in_bytes = al256((size_t)n_kf * 32) + al256((size_t)n_kf * 28) + al256(n_kf) + al256((size_t)n_f * 32) + al256((size_t)n_f * 28) +
                          al256((size_t)n_f * 4) + 2 * al256((size_t)(kf_fv->nnodes + 1) * 4) + al256((size_t)kf_total * 4 + 4) +
                          2 * al256((size_t)(f_fv->nnodes + 1) * 4) + al256((size_t)f_total * 4 + 4) + 4096;
-    int rc = match_scratch(c, in_bytes + work + 256);
+    int rc = match_scratch(c, in_bytes + work + 256, in_bytes + 4096);
     if (rc) return rc;
-    Bump b(c->d_match_scratch, c->match_scratch_bytes);
+    Bump b(c->d_match_scratch, c->h_match_arena, c->match_scratch_bytes);
     orb_featvec_view a = *kf_fv, f = *f_fv;
     static const int32_t zero_start[1] = { 0 };
     if (!a.start) a.start = zero_start;
@@ -649,6 +668,7 @@ int orb_search_by_bow(orb_ctx* c, const orb_featvec_view* kf_fv, const uint8_t* 
         (rc = stage_in(b, dev, f_kps, (size_t)n_f, s))) return rc;
     int32_t* d_match = dev ? match_f : (int32_t*)b.take((size_t)n_f * 4);
     uint8_t* wk = (uint8_t*)b.take(work);
+    if ((rc = b.flush(s))) return rc;
     rc = orb_launch_search_by_bow(c, &a, kf_desc, kf_kps, kf_mp_valid, &f, f_desc, f_kps, n_f, f_total, nnratio, check_ori, d_match, wk, s);
     if (rc) return rc;
     int res = 0;

@@ -131,6 +131,7 @@ struct orb_ctx {
     // matcher scratch
     int32_t* d_knn_part = nullptr; size_t knn_part_bytes = 0;
     void* d_match_scratch = nullptr; size_t match_scratch_bytes = 0;
+    uint8_t* h_match_arena = nullptr; size_t match_arena_bytes = 0;   // pinned mirror of the input part of the scratch: one H2D per call
 };
 
 // status helpers

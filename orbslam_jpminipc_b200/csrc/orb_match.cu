@@ -176,29 +176,27 @@ k_grid_build(const orb_keypoint* __restrict__ kps, int n, int min_x, int max_x, 
              int32_t* __restrict__ cell_start, int32_t* __restrict__ cell_items)
 {
     extern __shared__ unsigned short s_cell[];            // n entries
-    __shared__ int s_cnt[ORB_GRID_COLS * ORB_GRID_ROWS];
+    __shared__ int s_cnt[ORB_GRID_COLS * ORB_GRID_ROWS];  // histogram, then running fill position
     __shared__ int s_warp[32];
     const int NC = ORB_GRID_COLS * ORB_GRID_ROWS;
     const int tid = threadIdx.x;
     const float invW = __fdiv_rn((float)ORB_GRID_COLS, (float)(max_x - min_x));
     const float invH = __fdiv_rn((float)ORB_GRID_ROWS, (float)(max_y - min_y));
+    for (int c = tid; c < NC; c += blockDim.x) s_cnt[c] = 0;
+    __syncthreads();
     for (int i = tid; i < n; i += blockDim.x) {
         const int px = (int)roundf(__fmul_rn(__fsub_rn(kps[i].x, (float)min_x), invW));
         const int py = (int)roundf(__fmul_rn(__fsub_rn(kps[i].y, (float)min_y), invH));
         const bool ok = !(px < 0 || px >= ORB_GRID_COLS || py < 0 || py >= ORB_GRID_ROWS);
-        s_cell[i] = ok ? (unsigned short)(px * ORB_GRID_ROWS + py) : (unsigned short)0xffff;
+        const int c = px * ORB_GRID_ROWS + py;
+        s_cell[i] = ok ? (unsigned short)c : (unsigned short)0xffff;
+        if (ok) atomicAdd(&s_cnt[c], 1);
     }
     __syncthreads();
-    // 3 cells per thread: count
+    // block exclusive scan of the histogram (each thread owns 3 consecutive cells)
     int cnt[3];
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const int c = tid * 3 + k;
-        int v = 0;
-        if (c < NC) for (int i = 0; i < n; i++) v += (s_cell[i] == c);
-        cnt[k] = v;
-    }
-    // block exclusive scan over threads (each owns 3 consecutive cells)
+    for (int k = 0; k < 3; k++) cnt[k] = s_cnt[tid * 3 + k];
     const int mine = cnt[0] + cnt[1] + cnt[2];
     int incl = mine;
 #pragma unroll
@@ -216,17 +214,26 @@ k_grid_build(const orb_keypoint* __restrict__ kps, int n, int min_x, int max_x, 
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         const int c = tid * 3 + k;
-        if (c < NC) { cell_start[c] = base; s_cnt[c] = base; }
+        cell_start[c] = base; s_cnt[c] = base;
         base += cnt[k];
     }
     if (tid == 1023) cell_start[NC] = base;
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const int c = tid * 3 + k;
-        if (c < NC && cnt[k]) {
-            int o = s_cnt[c];
-            for (int i = 0; i < n; i++) if (s_cell[i] == c) cell_items[o++] = i;
+    // stable placement in ascending keypoint index (the reference push_backs in index order): one warp walks the
+    // keypoints 32 at a time; lanes of the same cell rank themselves with match_any
+    if (tid < 32) {
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + tid;
+            const unsigned c = i < n ? s_cell[i] : 0xffffu;
+            const unsigned same = __match_any_sync(0xffffffffu, c);
+            if (c != 0xffffu) {
+                const int rank = __popc(same & ((1u << tid) - 1));
+                const int pos = s_cnt[c] + rank;
+                cell_items[pos] = i;
+                __syncwarp(same);
+                if (rank == 0) s_cnt[c] += __popc(same);
+            }
+            __syncwarp();
         }
     }
 }
@@ -353,62 +360,81 @@ k_sbp_candidates(SbpArgs A)
     if (lane == 0) A.cnt[i] = total;
 }
 
-// Pass 2, one warp, last-frame features in index order: best unclaimed candidate, first in scan order
-// on ties (:1559-1574), accept at <= TH_HIGH and claim (:1576-1579); then the rotation histogram
-// filter (:1581-1617).  result[0] = nmatches, result[1] = error flag.
-__global__ void __launch_bounds__(32)
-k_sbp_resolve(SbpArgs A, int check_ori, int32_t* __restrict__ match_cur, int8_t* __restrict__ bin_of, int* __restrict__ result)
+// Pass 2, one CTA.  The reference walks the last-frame features in index order and lets each take its best
+// still-unclaimed candidate (first in scan order on ties, :1559-1574; accepted at <= TH_HIGH and then claimed,
+// :1576-1579).  That greedy order is reproduced without a serial walk by iterating to the unique fixed point of
+//     choice[i] = best candidate of i that no j < i currently chooses
+// (owner[c] = min{ j : choice[j] == c } is rebuilt every round with atomicMin).  Feature 0 is final after round 1
+// and feature i one round after all j < i are, so the fixed point IS the sequential result; collisions are rare
+// and it takes 2-4 rounds in practice.  Then the rotation histogram filter (:1581-1617).
+// result[0] = nmatches, result[1] = error flag.
+__global__ void __launch_bounds__(1024)
+k_sbp_resolve(SbpArgs A, int check_ori, int32_t* __restrict__ match_cur, int8_t* __restrict__ bin_of, int* __restrict__ owner,
+              int* __restrict__ choice, int* __restrict__ result)
 {
     __shared__ int hist[HISTO_LENGTH];
-    const int lane = threadIdx.x;
-    if (lane < HISTO_LENGTH) hist[lane] = 0;
-    for (int k = lane; k < A.cur.n; k += 32) bin_of[k] = -1;
-    __syncwarp();
-    int nmatches = 0, err = 0;
-    for (int i = 0; i < A.last.n; i++) {
-        const int n = A.cnt[i];
-        if (n <= 0) continue;
-        if (n > A.cap) { err = 1; continue; }
-        const uint32_t* L = A.list + (size_t)i * A.cap;
-        unsigned long long best = ~0ull;          // (dist, scan position, id)
-        for (int p = lane; p < n; p += 32) {
-            const uint32_t e = L[p];
-            const int id = (int)(e & 0x3fffff);
-            if (match_cur[id] >= 0) continue;     // CurrentFrame.mvpMapPoints[i2] already set (:1562)
-            const unsigned long long key = ((unsigned long long)(e >> 22) << 44) | ((unsigned long long)p << 22) | (unsigned long long)id;
-            best = key < best ? key : best;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o); best = t < best ? t : best; }
-        if (best == ~0ull) continue;
-        const int bestDist = (int)(best >> 44), bestIdx2 = (int)(best & 0x3fffff);
-        if (bestDist <= TH_HIGH) {
-            if (lane == 0) {
-                match_cur[bestIdx2] = i;
-                if (check_ori) {
-                    const int b = rot_bin(A.last.kps[i].angle, A.cur.kps[bestIdx2].angle);
-                    bin_of[bestIdx2] = (int8_t)b;
-                    hist[b]++;
-                }
+    __shared__ int s_changed, s_err, s_cnt, s_rounds;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int n1 = A.last.n, n2 = A.cur.n;
+    if (tid < HISTO_LENGTH) hist[tid] = 0;
+    if (tid == 0) { s_err = 0; s_cnt = 0; s_rounds = 0; }
+    for (int i = tid; i < n1; i += nt) choice[i] = -1;
+    for (int k = tid; k < n2; k += nt) bin_of[k] = -1;
+    __syncthreads();
+    for (int round = 0; round <= n1; round++) {
+        for (int k = tid; k < n2; k += nt) owner[k] = INT_MAX;
+        if (tid == 0) s_changed = 0;
+        __syncthreads();
+        for (int i = tid; i < n1; i += nt) { const int c = choice[i]; if (c >= 0) atomicMin(&owner[c], i); }
+        __syncthreads();
+        for (int i = tid; i < n1; i += nt) {
+            const int n = A.cnt[i];
+            if (n <= 0) continue;
+            if (n > A.cap) { s_err = 1; continue; }
+            const uint32_t* L = A.list + (size_t)i * A.cap;
+            uint32_t best = 0xffffffffu;          // dist<<22 | id ; scan position is the iteration order
+            for (int p = 0; p < n; p++) {
+                const uint32_t e = L[p];
+                const int id = (int)(e & 0x3fffff);
+                if (match_cur[id] >= 0) continue;                 // CurrentFrame.mvpMapPoints[i2] was set before the call (:1562)
+                if (owner[id] < i) continue;                      // claimed by an earlier feature
+                if ((e >> 22) < (best >> 22)) best = e;           // strict '<': first in scan order wins
             }
-            nmatches++;
-            __syncwarp();
+            const int c = (best != 0xffffffffu && (int)(best >> 22) <= TH_HIGH) ? (int)(best & 0x3fffff) : -1;
+            if (c != choice[i]) { choice[i] = c; s_changed = 1; }
+        }
+        __syncthreads();
+        const int ch = s_changed;
+        __syncthreads();
+        if (!ch) break;
+    }
+    // commit the claims, build the rotation histogram
+    int mine = 0;
+    for (int i = tid; i < n1; i += nt) {
+        const int c = choice[i];
+        if (c < 0) continue;
+        match_cur[c] = i;
+        mine++;
+        if (check_ori) {
+            const int b = rot_bin(A.last.kps[i].angle, A.cur.kps[c].angle);
+            bin_of[c] = (int8_t)b;
+            atomicAdd(&hist[b], 1);
         }
     }
-    __syncwarp();
+    atomicAdd(&s_cnt, mine);
+    __syncthreads();
     if (check_ori) {
         int i1, i2, i3;
         three_maxima(hist, i1, i2, i3);
         int removed = 0;
-        for (int k = lane; k < A.cur.n; k += 32) {
+        for (int k = tid; k < n2; k += nt) {
             const int b = bin_of[k];
             if (b >= 0 && b != i1 && b != i2 && b != i3) { match_cur[k] = -1; removed++; }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
-        nmatches -= removed;
+        atomicSub(&s_cnt, removed);
+        __syncthreads();
     }
-    if (lane == 0) { result[0] = nmatches; result[1] = err; }
+    if (tid == 0) { result[0] = s_cnt; result[1] = s_err; }
 }
 
 // ------------------------------------------------------------------ K9: SearchByBoW scoring
@@ -618,9 +644,11 @@ int orb_launch_search_by_projection(orb_ctx* c, const orb_frame_view* cur, const
     for (int i = 1; i < ORB_MAX_LEVELS; i++) A.sf[i] = i < cur->nlevels ? A.sf[i - 1] * cur->scale_factor : A.sf[i - 1];
     A.th = th;
     if (cur->n >= (1 << 22)) return ORB_ERR_CAPACITY;
-    // scratch: cnt[last.n] | bin_of[cur.n] | list[last.n * cap]
+    // scratch: cnt[last.n] | choice[last.n] | owner[cur.n] | bin_of[cur.n] | list[last.n * cap]
     size_t off = 0;
     A.cnt = (int*)(scratch + off); off += ((size_t)last->n * 4 + 255) & ~(size_t)255;
+    int* choice = (int*)(scratch + off); off += ((size_t)last->n * 4 + 255) & ~(size_t)255;
+    int* owner = (int*)(scratch + off); off += ((size_t)cur->n * 4 + 255) & ~(size_t)255;
     int8_t* bin_of = (int8_t*)(scratch + off); off += ((size_t)cur->n + 255) & ~(size_t)255;
     const size_t avail = scratch_bytes > off ? (scratch_bytes - off) / 4 : 0;
     A.cap = (int)std::min<size_t>((size_t)cur->n, last->n ? avail / (size_t)last->n : 0);
@@ -628,7 +656,7 @@ int orb_launch_search_by_projection(orb_ctx* c, const orb_frame_view* cur, const
     A.list = (uint32_t*)(scratch + off);
     if (A.cap < 1) return ORB_ERR_CAPACITY;
     k_sbp_candidates<<<(last->n * 32 + 255) / 256, 256, 0, s>>>(A);
-    k_sbp_resolve<<<1, 32, 0, s>>>(A, check_ori, match_cur, bin_of, d_result);
+    k_sbp_resolve<<<1, 1024, 0, s>>>(A, check_ori, match_cur, bin_of, owner, choice, d_result);
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;
 }
@@ -636,7 +664,8 @@ int orb_launch_search_by_projection(orb_ctx* c, const orb_frame_view* cur, const
 size_t orb_sbp_scratch_bytes(int n_cur, int n_last)
 {
     const size_t cap = (size_t)std::min(n_cur, 1024);
-    return (((size_t)n_last * 4 + 255) & ~(size_t)255) + (((size_t)n_cur + 255) & ~(size_t)255) + (size_t)n_last * cap * 4 + 256;
+    return 2 * (((size_t)n_last * 4 + 255) & ~(size_t)255) + (((size_t)n_cur * 4 + 255) & ~(size_t)255) +
+           (((size_t)n_cur + 255) & ~(size_t)255) + (size_t)n_last * cap * 4 + 256;
 }
 
 int orb_launch_search_by_bow(orb_ctx* c, const orb_featvec_view* kf_fv, const uint8_t* kf_desc, const orb_keypoint* kf_kps,
