@@ -224,6 +224,38 @@ def run_matching(args, L, ex, dev, world, rank, stream, barrier, max_over_ranks,
                 "db_sharded": {"db_rows": shard * world, "queries": NQ, "pairs_per_s": pairs5, "ms_per_query_batch": ms5 / reps5,
                                "popc_frac": pairs5 / world * 8 / (popc.value * 1e9), "merge": "nccl all_gather + k_knn2_merge" if world > 1 else "none (1 shard)"}}
 
+    # config 3: KITTI-shaped 1241x376 pair, 2000 kp: extract both frames on the GPU, then frame-to-frame SearchByProjection
+    if rank == 0:
+        import orbslam_jpminipc_b200 as pkg
+        from orbslam_jpminipc_b200.synth import synth_frame, shifted_frame
+        h3, w3 = 376, 1241
+        ex3 = pkg.ORBextractor(2000, SCALE, NLEVELS, 1, FAST_TH, device=torch.cuda.current_device(), max_width=w3, max_height=h3, max_batch=2)
+        fa = synth_frame(h3, w3, 9000, quadrants=False)
+        fb = shifted_frame(fa, 3, 2, 9001)
+        (ka, da), (kb, db_) = ex3.extract_batch(np.stack([fa, fb]))
+        m3 = pkg.ORBmatcher(0.9, True, extractor=ex3)
+        fx = fy = 500.0
+        rng = np.random.default_rng(9000)
+        z = rng.uniform(2, 10, len(ka)).astype(np.float32)
+        xyz = np.stack([(ka["x"] - w3 / 2) / fx * z, (ka["y"] - h3 / 2) / fy * z, z], 1).astype(np.float32)
+        Tcw = np.eye(4, dtype=np.float32)
+        Tcw[:3, 3] = [0.03, 0.02, 0.01]
+        has, outl = np.ones(len(ka), np.uint8), np.zeros(len(ka), np.uint8)
+        cur = pkg.Frame(m3, kb, db_, w3, h3, fx, fy, w3 / 2, h3 / 2)
+        last = pkg.Frame(m3, ka, da, w3, h3, fx, fy, w3 / 2, h3 / 2)
+        nm, _ = m3.SearchByProjection(cur, last, 15.0, has, outl, xyz, Tcw)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            m3.SearchByProjection(cur, last, 15.0, has, outl, xyz, Tcw)
+        sbp_ms = (time.perf_counter() - t0) / 50 * 1e3
+        t0 = time.perf_counter()
+        for _ in range(20):
+            ex3.extract_batch(np.stack([fa, fb]))
+        ext_ms = (time.perf_counter() - t0) / 20 * 1e3
+        matching["search_by_projection_1241x376"] = {"keypoints": [int(len(ka)), int(len(kb))], "matches": int(nm), "th": 15,
+                                                     "ms_per_pair_host_api": sbp_ms, "extract_two_frames_host_api_ms": ext_ms,
+                                                     "note": "single frame pair, latency through the host-buffer C ABI (grid build excluded)"}
+        matching["_sbp_inputs"] = (cur, last, has, outl, xyz, Tcw)
     return matching
 
 
@@ -385,6 +417,7 @@ def run_gpu(args):
                     "d2h_bytes_per_step": int(B * cap * 60 + B * 4), "ms_per_step": e2e_ms / args.steps,
                     "gpu_launches_per_step": e2e_launches, "chunk": args.e2e_chunk, "api": "orb_extract_batch (pinned host buffers in and out, internally chunked + double-buffered)"},
             "roofline": roofline, "matching": matching}
+    sbp_inputs = matching.pop("_sbp_inputs", None) if matching else None
     if args.cpu_baseline:
         cores = os.cpu_count() or 1
         nfr = 64 * cores                                   # ~12 core-seconds of CPU work at ~80 frames/s/core
@@ -395,6 +428,19 @@ def run_gpu(args):
                                 "sample": "%d frames of the same workload, frame-parallel over %d host threads (%.1f s wall); "
                                           "single-thread figure on 48 frames (%.1f s); oracle port of src/ORBextractor.cc "
                                           "(the reference needs ROS + the OpenCV C++ SDK and cannot be built here)" % (nfr, cores, dtN, dt1)}
+        if sbp_inputs is not None:
+            from oracle import pyoracle as po
+            cur, last, has, outl, xyz, Tcw = sbp_inputs
+            oc = po.OracleFrame(cur.kps, cur.desc, cur.width, cur.height, cur.fx, cur.fy, cur.cx, cur.cy)
+            ol = po.OracleFrame(last.kps, last.desc, last.width, last.height, last.fx, last.fy, last.cx, last.cy)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                po.search_by_projection(oc, ol, has, outl, xyz, Tcw, 15.0, True)
+            line["cpu_baseline"]["search_by_projection_1241x376_ms_per_pair"] = (time.perf_counter() - t0) / 20 * 1e3
+            db4, q4 = synth_descriptors(2000, 2000)
+            t0 = time.perf_counter()
+            po.knn2(q4, db4)
+            line["cpu_baseline"]["knn2_2000x2000_pairs_per_s_1thread"] = 4e6 / (time.perf_counter() - t0)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
