@@ -389,17 +389,16 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
                 const uint32_t vlo = lo16x2(cw), vhi = hi16x2(cw);
                 uint32_t ring[16], Mn, Mx;
                 RING_ALL(0, ring)
-                // quick reject (exact): every 9-arc contains two ring-adjacent compass points (0,4,8,12), so a
-                // corner needs such a pair both brighter than v+th or both darker than v-th.
+                // quick reject (exact, never rejects a corner): every 9-arc contains a compass point (0,4,8,12), so a
+                // corner needs one of them brighter than v+th or darker than v-th.  Flat areas leave here.
                 const uint32_t h0 = RPAIR(w1[6], w2[6], 0, 1), h4 = RPAIR(w1[3], w2[3], 3, 1);
                 const uint32_t h8 = RPAIR(w1[0], w2[0], 0, 1), h12 = RPAIR(w0[3], w1[3], 1, 1);
                 bool any;
                 {
-                    const uint32_t n0 = ring[0], n4 = ring[4], n8 = ring[8], n12 = ring[12];
-                    const uint32_t bl = __vmaxu2(__vmaxu2(__vminu2(n0, n4), __vminu2(n4, n8)), __vmaxu2(__vminu2(n8, n12), __vminu2(n12, n0)));
-                    const uint32_t dl = __vminu2(__vminu2(__vmaxu2(n0, n4), __vmaxu2(n4, n8)), __vminu2(__vmaxu2(n8, n12), __vmaxu2(n12, n0)));
-                    const uint32_t bh = __vmaxu2(__vmaxu2(__vminu2(h0, h4), __vminu2(h4, h8)), __vmaxu2(__vminu2(h8, h12), __vminu2(h12, h0)));
-                    const uint32_t dh = __vminu2(__vminu2(__vmaxu2(h0, h4), __vmaxu2(h4, h8)), __vminu2(__vmaxu2(h8, h12), __vmaxu2(h12, h0)));
+                    const uint32_t bl = __vimax3_u16x2(ring[0], ring[4], __vmaxu2(ring[8], ring[12]));
+                    const uint32_t dl = __vimin3_u16x2(ring[0], ring[4], __vminu2(ring[8], ring[12]));
+                    const uint32_t bh = __vimax3_u16x2(h0, h4, __vmaxu2(h8, h12));
+                    const uint32_t dh = __vimin3_u16x2(h0, h4, __vminu2(h8, h12));
                     any = (score2(vlo, __byte_perm(bl, 0, 0x4240), __byte_perm(dl, 0, 0x4240), neg_th2, th_m1) |
                            score2(vhi, __byte_perm(bh, 0, 0x4240), __byte_perm(dh, 0, 0x4240), neg_th2, th_m1)) != 0;
                 }
