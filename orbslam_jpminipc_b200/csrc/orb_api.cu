@@ -41,7 +41,7 @@ int orb_build_tmaps(orb_ctx* c, WorkSet& W, int nframes)
         cuuint64_t dims[3] = { (cuuint64_t)L.stride, (cuuint64_t)L.prows, (cuuint64_t)nframes };
         cuuint64_t strides[2] = { (cuuint64_t)L.stride, (cuuint64_t)P.frame_bytes };
         cuuint32_t estr[3] = { 1, 1, 1 };
-        cuuint32_t box_fast[3] = { 96, ORB_TILE_H + 8, 1 };
+        cuuint32_t box_fast[3] = { ORB_TILE_W + 32, ORB_TILE_H + 8, 1 };
         cuuint32_t box_blur[3] = { 96, ORB_BLUR_TILE_H + 6, 1 };
         void* base = W.d_planes + L.plane_off;
         CUresult r1 = enc(&W.tm_fast.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box_fast, estr,

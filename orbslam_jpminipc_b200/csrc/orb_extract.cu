@@ -243,8 +243,8 @@ k_border(uint8_t* __restrict__ planes, uint8_t* __restrict__ blurred, size_t fby
 //   bright strength = max_k( min of ring[k..k+8] ) - v,   dark strength = v - min_k( max of ring[k..k+8] )
 // corner at threshold t  <=>  max(bright, dark) > t ;  OpenCV's response = that maximum - 1.
 constexpr int FT_W = ORB_TILE_W, FT_H = ORB_TILE_H;
-constexpr int FIW = 24, FI_H = FT_H + 8;   // image tile: 24 words (cols x0-16..x0+79) x rows y0-4..y0+35; TMA needs a 16-byte aligned x origin
-constexpr int FSW = 18, FS_H = FT_H + 2;   // score tile: 18 words (cols x0-4..x0+67) x rows y0-1..y0+32
+constexpr int FIW = FT_W / 4 + 8, FI_H = FT_H + 8;   // image tile: cols x0-16..x0+FT_W+15, rows y0-4..y0+FT_H+3; TMA needs a 16-byte aligned x origin
+constexpr int FSW = FT_W / 4 + 2, FS_H = FT_H + 2;   // score tile: cols x0-4..x0+FT_W+3, rows y0-1..y0+FT_H
 #ifndef ORB_FAST_THREADS
 #define ORB_FAST_THREADS 128      // measured on B200: 320x3 1.75 ms, 256x4 1.56, 128x8 1.46, 64x16 1.43 per 256 frames
 #define ORB_FAST_CTAS 8
@@ -422,7 +422,7 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
         uint8_t* out = nms + (size_t)f * fbytes + L.plane_off;
         uint8_t* bm = bitmap + (size_t)f * plan->bm_total + L.bm_off;
         for (int task = tid; task < FT_H * (FT_W / 16); task += FAST_THREADS) {
-            const int ro = task >> 2, q4 = task & 3;
+            const int ro = task / (FT_W / 16), q4 = task - ro * (FT_W / 16);
             const int r = ro + 1;
             const int rc = rowcell[r];
             const bool up = rowcell[r - 1] == rc, dn = rowcell[r + 1] == rc;

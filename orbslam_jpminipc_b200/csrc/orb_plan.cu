@@ -163,7 +163,7 @@ int orb_build_plan(orb_ctx* c, int w, int h)
                 c->cells.push_back(g);
             }
         }
-        L.bm_pitch = ((std::max(L.xend - ORB_EDGE, 0) + 63) / 64) * 8;          // whole 64-px tiles, 8 bytes each
+        L.bm_pitch = ((std::max(L.xend - ORB_EDGE, 0) + ORB_TILE_W - 1) / ORB_TILE_W) * (ORB_TILE_W / 8);   // whole FAST tiles
         L.bm_off = bm;
         bm += ((L.bm_pitch * std::max(((L.yend - ORB_EDGE + ORB_TILE_H - 1) / ORB_TILE_H) * ORB_TILE_H, 0) + 255) & ~255);
         L.lvl_base = lvl;
