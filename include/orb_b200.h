@@ -150,6 +150,35 @@ int orb_search_by_projection(orb_ctx*, const orb_frame_view* cur, const orb_fram
                              const uint8_t* last_has_mp, const uint8_t* last_outlier, const float* last_xyz,
                              const float* Tcw16, float th, int check_ori, int32_t* match_cur, int* nmatches);
 
+/* ------------------------------------------------------------------------------------------------
+ * Generic windowed greedy search: the loop shared by the other projection / window searches of ORBmatcher
+ * (SURVEY.md §8f.1).  Queries are processed in index order like the reference; each takes the best keypoint of
+ * `target` inside its window that no earlier query (and no pre-existing match) has claimed.
+ *   ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*>&, th)  src/ORBmatcher.cc:49-125
+ *       u,v = mTrackProjX/Y; radius = RadiusByViewingCos(viewCos)[*th]*scale[level]; levels [level-1, level];
+ *       accept = ORB_ACCEPT_LEVEL_RATIO, th_dist = TH_HIGH, no histogram
+ *   ORBmatcher::WindowSearch(F1, F2, windowSize, ...)                        src/ORBmatcher.cc:409-516
+ *       u,v = F1 keypoint; radius_const = windowSize; levels [l, l]; accept = ORB_ACCEPT_RATIO, TH_HIGH, histogram
+ *   ORBmatcher::SearchByProjection(F1, F2, windowSize, ...)                  src/ORBmatcher.cc:519-594
+ *       xyz + Tcw16 (projected with the target's intrinsics, no bounds test); radius_const = windowSize;
+ *       levels [l, l]; accept = ORB_ACCEPT_RATIO, TH_HIGH, no histogram; match_target pre-filled with F2's map points
+ * All pointers inside the structures are HOST pointers or all DEVICE pointers. */
+typedef struct orb_window_query_set {
+    int32_t n;
+    const uint8_t* active;          /* n: 0 = query skipped (no map point / bad / out of view / level filtered) */
+    const uint8_t* desc;            /* n x 32 query descriptors */
+    const float* u; const float* v; /* explicit window centres, or NULL ... */
+    const float* xyz; const float* Tcw16;   /* ... then 3-D points (n x 3) projected with Tcw16 (4x4 row major, host memory) */
+    int32_t check_bounds;           /* reject centres outside [min_x,max_x] x [min_y,max_y] (src/ORBmatcher.cc:1539-1542) */
+    const float* radius; float radius_const;   /* per-query radius, or NULL and one value */
+    const int32_t* min_level; const int32_t* max_level;   /* octave range per query (-1,-1: any) */
+    const float* angle;             /* query keypoint angles (rotation histogram), may be NULL */
+} orb_window_query_set;
+enum { ORB_ACCEPT_BEST = 0, ORB_ACCEPT_RATIO = 1, ORB_ACCEPT_LEVEL_RATIO = 2 };
+/* match_target[target->n] in/out: index of the query matched to each target keypoint, or -1 */
+int orb_search_window(orb_ctx*, const orb_frame_view* target, const orb_window_query_set* queries, int accept_mode,
+                      float nnratio, int th_dist, int check_ori, int32_t* match_target, int* nmatches);
+
 /* DBoW2::FeatureVector as CSR (Thirdparty/DBoW2/DBoW2/FeatureVector.cpp:31-45): node ids ascending,
  * per node the feature indices in insertion order. */
 typedef struct orb_featvec_view {

@@ -862,4 +862,125 @@ int orc_search_by_bow(const orc_featvec* kfv, const uint8_t* kf_desc, const orc_
     return nmatches;
 }
 
+
+/* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th), src/ORBmatcher.cc:49-125 */
+int orc_search_by_projection_mappoints(const orc_frame* f, int nmp, const uint8_t* in_view, const float* proj_x, const float* proj_y,
+                                       const int32_t* level, const float* view_cos, const uint8_t* mp_desc, float th, float nnratio,
+                                       int32_t* match_f)
+{
+    const int TH_HIGH = 100;
+    int nmatches = 0;
+    const bool bFactor = th != 1.0;
+    std::vector<float> sf(f->nlevels);
+    sf[0] = 1.0f;
+    for (int i = 1; i < f->nlevels; i++) sf[i] = sf[i - 1] * f->scale_factor;
+    std::vector<int32_t> cand(f->n > 0 ? f->n : 1);
+    for (int iMP = 0; iMP < nmp; iMP++) {
+        if (!in_view[iMP]) continue;
+        const int nPredictedLevel = level[iMP];
+        float r = view_cos[iMP] > 0.998 ? 2.5f : 4.0f;                 /* RadiusByViewingCos :127-133 */
+        if (bFactor) r *= th;
+        int nc = orc_features_in_area(f, proj_x[iMP], proj_y[iMP], r * sf[nPredictedLevel], nPredictedLevel - 1, nPredictedLevel,
+                                      cand.data(), f->n);
+        if (nc == 0) continue;
+        const uint8_t* d = mp_desc + (size_t)iMP * 32;
+        int bestDist = INT_MAX, bestLevel = -1, bestDist2 = INT_MAX, bestLevel2 = -1, bestIdx = -1;
+        for (int k = 0; k < nc; k++) {
+            const int idx = cand[k];
+            if (match_f[idx] >= 0) continue;
+            const int dist = orc_descriptor_distance(d, f->desc + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = f->kps[idx].octave; bestIdx = idx; }
+            else if (dist < bestDist2) { bestLevel2 = f->kps[idx].octave; bestDist2 = dist; }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+            match_f[bestIdx] = iMP;
+            nmatches++;
+        }
+    }
+    return nmatches;
+}
+
+/* ORBmatcher::WindowSearch, src/ORBmatcher.cc:409-516 */
+int orc_window_search(const orc_frame* f1, const orc_frame* f2, const uint8_t* f1_has_mp, int windowSize, int minScaleLevel, int maxScaleLevel,
+                      float nnratio, int check_ori, int32_t* match2)
+{
+    const int HISTO_LENGTH = 30, TH_HIGH = 100;
+    int nmatches = 0;
+    for (int i = 0; i < f2->n; i++) match2[i] = -1;
+    std::vector<int> rotHist[30];
+    const bool bMinLevel = minScaleLevel > 0, bMaxLevel = maxScaleLevel < INT_MAX;
+    std::vector<int32_t> cand(f2->n > 0 ? f2->n : 1);
+    for (int i1 = 0; i1 < f1->n; i1++) {
+        if (!f1_has_mp[i1]) continue;
+        const orc_keypoint& kp1 = f1->kps[i1];
+        const int level1 = kp1.octave;
+        if (bMinLevel && level1 < minScaleLevel) continue;
+        if (bMaxLevel && level1 > maxScaleLevel) continue;
+        int nc = orc_features_in_area(f2, kp1.x, kp1.y, (float)windowSize, level1, level1, cand.data(), f2->n);
+        if (nc == 0) continue;
+        const uint8_t* d1 = f1->desc + (size_t)i1 * 32;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int k = 0; k < nc; k++) {
+            const int i2 = cand[k];
+            if (match2[i2] >= 0) continue;
+            const int dist = orc_descriptor_distance(d1, f2->desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= bestDist2 * nnratio && bestDist <= TH_HIGH) {
+            match2[bestIdx2] = i1;
+            nmatches++;
+            rotHist[rot_bin(f1->kps[i1].angle, f2->kps[bestIdx2].angle)].push_back(bestIdx2);
+        }
+    }
+    if (check_ori) {
+        int hs[30], i1, i2, i3;
+        for (int i = 0; i < HISTO_LENGTH; i++) hs[i] = (int)rotHist[i].size();
+        orc_three_maxima(hs, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != i1 && i != i2 && i != i3)
+                for (int id : rotHist[i]) { match2[id] = -1; nmatches--; }
+    }
+    return nmatches;
+}
+
+/* ORBmatcher::SearchByProjection(Frame &F1, Frame &F2, int windowSize, ...), src/ORBmatcher.cc:519-594 */
+int orc_search_by_projection_window(const orc_frame* f1, const orc_frame* f2, const uint8_t* f1_active, const float* f1_xyz,
+                                    const float* T, int windowSize, float nnratio, int32_t* match2)
+{
+    const int TH_HIGH = 100;
+    int nmatches = 0;
+    std::vector<int32_t> cand(f2->n > 0 ? f2->n : 1);
+    for (int i1 = 0; i1 < f1->n; i1++) {
+        if (!f1_active[i1]) continue;
+        const int level1 = f1->kps[i1].octave;
+        const float X = f1_xyz[3 * i1], Y = f1_xyz[3 * i1 + 1], Z = f1_xyz[3 * i1 + 2];
+        float c[3];
+        for (int r = 0; r < 3; r++) {
+            float t0 = T[4 * r + 0] * X + T[4 * r + 1] * Y + T[4 * r + 2] * Z;
+            c[r] = (float)((double)t0 * 1.0 + (double)T[4 * r + 3] * 1.0);
+        }
+        const float invzc2 = (float)(1.0 / c[2]);
+        float u2 = f2->fx * c[0] * invzc2 + f2->cx;
+        float v2 = f2->fy * c[1] * invzc2 + f2->cy;
+        int nc = orc_features_in_area(f2, u2, v2, (float)windowSize, level1, level1, cand.data(), f2->n);
+        if (nc == 0) continue;
+        const uint8_t* d1 = f1->desc + (size_t)i1 * 32;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int k = 0; k < nc; k++) {
+            const int i2 = cand[k];
+            if (match2[i2] >= 0) continue;
+            const int dist = orc_descriptor_distance(d1, f2->desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if ((float)bestDist <= (float)bestDist2 * nnratio && bestDist <= TH_HIGH) {
+            match2[bestIdx2] = i1;
+            nmatches++;
+        }
+    }
+    return nmatches;
+}
+
 } // extern "C"

@@ -113,6 +113,23 @@ int   orc_search_by_bow(const orc_featvec* kf_fv, const uint8_t* kf_desc, const 
                         float nnratio, int check_ori, int32_t* match_f);
 void  orc_three_maxima(const int* hist_sizes, int L, int* ind1, int* ind2, int* ind3);
 
+/* ---- further ORBmatcher searches ---- */
+/* ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*>&, th), src/ORBmatcher.cc:49-125.
+ * Per map point: track_in_view (&& !isBad), mTrackProjX/Y, mnTrackScaleLevel, mTrackViewCos, descriptor.
+ * match_f[idx] in/out = index of the map point assigned to F.mvpMapPoints[idx], or -1. */
+int   orc_search_by_projection_mappoints(const orc_frame* f, int nmp, const uint8_t* in_view, const float* proj_x, const float* proj_y,
+                                         const int32_t* level, const float* view_cos, const uint8_t* mp_desc, float th, float nnratio,
+                                         int32_t* match_f);
+/* ORBmatcher::WindowSearch(F1, F2, windowSize, vpMapPointMatches2, minLevel, maxLevel), src/ORBmatcher.cc:409-516.
+ * f1_has_mp[i1] != 0 <=> F1.mvpMapPoints[i1] is a live map point.  match2[i2] out = i1 or -1. */
+int   orc_window_search(const orc_frame* f1, const orc_frame* f2, const uint8_t* f1_has_mp, int window, int min_level, int max_level,
+                        float nnratio, int check_ori, int32_t* match2);
+/* ORBmatcher::SearchByProjection(F1, F2, windowSize, vpMapPointMatches2), src/ORBmatcher.cc:519-594.
+ * f1_active[i1] != 0 <=> F1 map point is live and not already found in F2; f1_xyz its world position;
+ * match2[i2] in/out: >= 0 (or the caller's marker) means F2.mvpMapPoints[i2] is already set. */
+int   orc_search_by_projection_window(const orc_frame* f1, const orc_frame* f2, const uint8_t* f1_active, const float* f1_xyz,
+                                      const float* Tc2w16, int window, float nnratio, int32_t* match2);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,6 +84,10 @@ def lib():
         L.orc_search_by_bow.argtypes = [C.POINTER(_FeatVec), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                         C.POINTER(_FeatVec), C.c_void_p, C.c_void_p, C.c_int,
                                         C.c_float, C.c_int, C.c_void_p]
+        L.orc_search_by_projection_mappoints.argtypes = [C.POINTER(_Frame), C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_float, C.c_void_p]
+        L.orc_window_search.argtypes = [C.POINTER(_Frame), C.POINTER(_Frame), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]
+        L.orc_search_by_projection_window.argtypes = [C.POINTER(_Frame), C.POINTER(_Frame), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                      C.c_float, C.c_void_p]
         L.orc_three_maxima.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 3
         _lib = L
     return _lib
@@ -325,3 +329,27 @@ def merge_best2(parts):
             if p2[i] < D2[i]:
                 D2[i] = p2[i]
     return I, D1, D2
+
+
+def search_by_projection_mappoints(f, in_view, proj_x, proj_y, level, view_cos, mp_desc, th, nnratio, match_f=None):
+    if match_f is None:
+        match_f = np.full(f.n, -1, np.int32)
+    a = [np.ascontiguousarray(in_view, np.uint8), np.ascontiguousarray(proj_x, np.float32), np.ascontiguousarray(proj_y, np.float32),
+         np.ascontiguousarray(level, np.int32), np.ascontiguousarray(view_cos, np.float32), np.ascontiguousarray(mp_desc, np.uint8)]
+    n = lib().orc_search_by_projection_mappoints(C.byref(f.c), len(a[0]), *[_p(x) for x in a], th, nnratio, _p(match_f))
+    return n, match_f
+
+
+def window_search(f1, f2, f1_has_mp, window, nnratio, check_ori=True, min_level=-1, max_level=2**31 - 1):
+    has = np.ascontiguousarray(f1_has_mp, np.uint8)
+    m = np.full(f2.n, -1, np.int32)
+    n = lib().orc_window_search(C.byref(f1.c), C.byref(f2.c), _p(has), window, min_level, max_level, nnratio, int(check_ori), _p(m))
+    return n, m
+
+
+def search_by_projection_window(f1, f2, f1_active, f1_xyz, Tc2w, window, nnratio, match2):
+    act = np.ascontiguousarray(f1_active, np.uint8)
+    xyz = np.ascontiguousarray(f1_xyz, np.float32)
+    T = np.ascontiguousarray(Tc2w, np.float32).reshape(16)
+    n = lib().orc_search_by_projection_window(C.byref(f1.c), C.byref(f2.c), _p(act), _p(xyz), _p(T), window, nnratio, _p(match2))
+    return n, match2

@@ -24,7 +24,7 @@ EXPORTS = [
     "orb_scale_factor", "orb_keypoint_capacity", "orb_extract", "orb_extract_batch", "orb_extract_batch_device",
     "orb_last_launch_count", "orb_profile_enable", "orb_profile_read", "orb_profile_stage_name", "orb_debug_level_info", "orb_debug_level_plane", "orb_descriptor_distance",
     "orb_hamming_knn2", "orb_hamming_knn2_device", "orb_knn2_merge_device", "orb_match_ratio",
-    "orb_frame_grid_build", "orb_search_by_projection", "orb_search_by_bow", "orb_host_alloc", "orb_host_free",
+    "orb_frame_grid_build", "orb_search_by_projection", "orb_search_window", "orb_search_by_bow", "orb_host_alloc", "orb_host_free",
     "orb_measure_popc_peak",
 ]
 
@@ -35,6 +35,12 @@ class FrameView(C.Structure):
                 ("min_x", C.c_int32), ("max_x", C.c_int32), ("min_y", C.c_int32), ("max_y", C.c_int32),
                 ("nlevels", C.c_int32), ("scale_factor", C.c_float),
                 ("cell_start", C.c_void_p), ("cell_items", C.c_void_p)]
+
+
+class WindowQuerySet(C.Structure):
+    _fields_ = [("n", C.c_int32), ("active", C.c_void_p), ("desc", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p),
+                ("xyz", C.c_void_p), ("Tcw16", C.c_void_p), ("check_bounds", C.c_int32), ("radius", C.c_void_p),
+                ("radius_const", C.c_float), ("min_level", C.c_void_p), ("max_level", C.c_void_p), ("angle", C.c_void_p)]
 
 
 class FeatVecView(C.Structure):
@@ -91,6 +97,7 @@ def lib():
     L.orb_frame_grid_build.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]
     L.orb_search_by_projection.argtypes = [vp, C.POINTER(FrameView), C.POINTER(FrameView), vp, vp, vp, vp,
                                            f32, i32, vp, C.POINTER(C.c_int)]
+    L.orb_search_window.argtypes = [vp, C.POINTER(FrameView), C.POINTER(WindowQuerySet), i32, f32, i32, i32, vp, C.POINTER(C.c_int)]
     L.orb_search_by_bow.argtypes = [vp, C.POINTER(FeatVecView), vp, vp, vp, i32,
                                     C.POINTER(FeatVecView), vp, vp, i32, f32, i32, vp, C.POINTER(C.c_int)]
     L.orb_host_alloc.restype = vp

@@ -631,6 +631,51 @@ int orb_search_by_projection(orb_ctx* c, const orb_frame_view* cur, const orb_fr
     return res[1] ? ORB_ERR_CAPACITY : ORB_OK;
 }
 
+int orb_search_window(orb_ctx* c, const orb_frame_view* target, const orb_window_query_set* q, int accept_mode,
+                      float nnratio, int th_dist, int check_ori, int32_t* match_target, int* nmatches)
+{
+    if (!c || !target || !q || !nmatches || target->n < 0 || q->n < 0 || accept_mode < 0 || accept_mode > 2) return ORB_ERR_INVALID;
+    *nmatches = 0;
+    if (target->n == 0 || q->n == 0) return ORB_OK;
+    const bool project = q->xyz != nullptr && q->u == nullptr;
+    if (!match_target || !target->kps || !target->desc || !target->cell_start || !target->cell_items || !q->active || !q->desc ||
+        !q->min_level || !q->max_level || (!project && (!q->u || !q->v)) || (project && !q->Tcw16) ||
+        target->max_x <= target->min_x || target->max_y <= target->min_y) return ORB_ERR_INVALID;
+    ORB_CUDA(cudaSetDevice(c->device));
+    const bool dev = is_device_ptr(target->kps);
+    if (is_device_ptr(match_target) != dev || is_device_ptr(q->desc) != dev) return ORB_ERR_INVALID;
+    cudaStream_t s = c->streams[0];
+    const size_t work = orb_sbp_scratch_bytes(target->n, q->n);
+    const size_t nq = (size_t)q->n;
+    const size_t in_bytes = dev ? 0 : frame_view_bytes(target) + al256(nq) + al256(nq * 32) + 7 * al256(nq * 4) + al256(nq * 12) + al256((size_t)target->n * 4);
+    int rc = match_scratch(c, 256 + in_bytes + work, 256 + in_bytes + 4096);
+    if (rc) return rc;
+    Bump b(c->d_match_scratch, c->h_match_arena, c->match_scratch_bytes);
+    int* d_result = (int*)b.take(8);
+    orb_frame_view dt = *target;
+    orb_window_query_set dq = *q;
+    if ((rc = stage_frame(b, dev, dt, true, s))) return rc;
+    if ((rc = stage_in(b, dev, dq.active, nq, s)) || (rc = stage_in(b, dev, dq.desc, nq * 32, s)) ||
+        (rc = stage_in(b, dev, dq.u, nq, s)) || (rc = stage_in(b, dev, dq.v, nq, s)) || (rc = stage_in(b, dev, dq.xyz, nq * 3, s)) ||
+        (rc = stage_in(b, dev, dq.radius, nq, s)) || (rc = stage_in(b, dev, dq.min_level, nq, s)) ||
+        (rc = stage_in(b, dev, dq.max_level, nq, s)) || (rc = stage_in(b, dev, dq.angle, nq, s))) return rc;
+    float T[16] = { 0 };
+    if (project) { if (is_device_ptr(q->Tcw16)) ORB_CUDA(cudaMemcpy(T, q->Tcw16, sizeof T, cudaMemcpyDeviceToHost)); else memcpy(T, q->Tcw16, sizeof T); }
+    dq.Tcw16 = T;
+    int32_t* d_match = match_target;
+    if (!dev) { const int32_t* m = match_target; if ((rc = stage_in(b, false, m, (size_t)target->n, s))) return rc; d_match = (int32_t*)m; }
+    uint8_t* wk = (uint8_t*)b.take(work);
+    if ((rc = b.flush(s))) return rc;
+    rc = orb_launch_search_window(c, &dt, &dq, accept_mode, nnratio, th_dist, check_ori, d_match, d_result, wk, work, s);
+    if (rc) return rc;
+    int res[2] = { 0, 0 };
+    if (!dev) ORB_CUDA(cudaMemcpyAsync(match_target, d_match, (size_t)target->n * 4, cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaMemcpyAsync(res, d_result, sizeof res, cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaStreamSynchronize(s));
+    *nmatches = res[0];
+    return res[1] ? ORB_ERR_CAPACITY : ORB_OK;
+}
+
 int orb_search_by_bow(orb_ctx* c, const orb_featvec_view* kf_fv, const uint8_t* kf_desc, const orb_keypoint* kf_kps,
                       const uint8_t* kf_mp_valid, int n_kf,
                       const orb_featvec_view* f_fv, const uint8_t* f_desc, const orb_keypoint* f_kps, int n_f,

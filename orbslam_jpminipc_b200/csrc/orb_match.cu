@@ -437,6 +437,179 @@ k_sbp_resolve(SbpArgs A, int check_ori, int32_t* __restrict__ match_cur, int8_t*
     if (tid == 0) { result[0] = s_cnt; result[1] = s_err; }
 }
 
+// ------------------------------------------------------------------ generic windowed greedy search
+// The remaining projection / window searches of ORBmatcher (src/ORBmatcher.cc:49-125, :409-516, :519-594) are the
+// same loop with different window sources and acceptance rules: queries in index order, candidates from
+// Frame::GetFeaturesInArea, already-claimed keypoints skipped, best (and second best) Hamming distance, accept, claim.
+enum { WIN_ACCEPT_BEST = 0,          // bestDist <= th_dist                                              (:1576, :1701)
+       WIN_ACCEPT_RATIO = 1,         // (float)best <= (float)second*nnratio && best <= th_dist          (:476, :585)
+       WIN_ACCEPT_LEVEL_RATIO = 2 }; // best <= th_dist && !(bestLevel==secondLevel && best > nnratio*second)  (:114-117)
+
+struct WinArgs {
+    orb_frame_view tgt;                         // frame that is searched (device pointers)
+    int nq;
+    const uint8_t* active; const uint8_t* qdesc;
+    const float* u; const float* v;             // explicit window centres (project == 0)
+    const float* xyz; float T[16]; int project; // or world points projected with T and the target intrinsics
+    int check_bounds;
+    const float* radius; float radius_const;    // per query (radius != NULL) or one value
+    const int32_t* minl; const int32_t* maxl;
+    const float* qangle;                        // query keypoint angles for the rotation histogram (may be NULL)
+    int accept; float nnratio; int th_dist; int histogram;
+    int cap; uint32_t* list; int* cnt;
+};
+
+__global__ void __launch_bounds__(256)
+k_win_candidates(WinArgs A)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= A.nq) return;
+    int total = -1;
+    if (A.active[i]) {
+        float u, v;
+        if (A.project) {
+            const float X = A.xyz[3 * i], Y = A.xyz[3 * i + 1], Z = A.xyz[3 * i + 2];
+            float c[3];
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const float t0 = __fadd_rn(__fadd_rn(__fmul_rn(A.T[4 * r], X), __fmul_rn(A.T[4 * r + 1], Y)), __fmul_rn(A.T[4 * r + 2], Z));
+                c[r] = __double2float_rn((double)t0 + (double)A.T[4 * r + 3]);
+            }
+            const float invzc = __double2float_rn(1.0 / (double)c[2]);
+            u = __fadd_rn(__fmul_rn(__fmul_rn(A.tgt.fx, c[0]), invzc), A.tgt.cx);
+            v = __fadd_rn(__fmul_rn(__fmul_rn(A.tgt.fy, c[1]), invzc), A.tgt.cy);
+        } else { u = A.u[i]; v = A.v[i]; }
+        bool inb = true;
+        if (A.check_bounds)
+            inb = !(u < (float)A.tgt.min_x || u > (float)A.tgt.max_x) && !(v < (float)A.tgt.min_y || v > (float)A.tgt.max_y);
+        if (inb) {
+            total = 0;
+            const float r = A.radius ? A.radius[i] : A.radius_const;
+            const int minLevel = A.minl[i], maxLevel = A.maxl[i];
+            const float invW = __fdiv_rn((float)ORB_GRID_COLS, (float)(A.tgt.max_x - A.tgt.min_x));
+            const float invH = __fdiv_rn((float)ORB_GRID_ROWS, (float)(A.tgt.max_y - A.tgt.min_y));
+            const float ux = __fsub_rn(u, (float)A.tgt.min_x), vy = __fsub_rn(v, (float)A.tgt.min_y);
+            int x0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(ux, r), invW)));
+            int x1 = min(ORB_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(ux, r), invW)));
+            int y0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(vy, r), invH)));
+            int y1 = min(ORB_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(vy, r), invH)));
+            if (x0 >= ORB_GRID_COLS || x1 < 0 || y0 >= ORB_GRID_ROWS || y1 < 0) { x1 = -1; x0 = 0; }
+            uint32_t q[8];
+            {
+                const uint4* qp = reinterpret_cast<const uint4*>(A.qdesc + (size_t)i * 32);
+                const uint4 a = __ldg(qp), b = __ldg(qp + 1);
+                q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
+            }
+            const bool checkLevels = !(minLevel == -1 && maxLevel == -1);          // src/Frame.cc:225-231
+            const bool sameLevel = checkLevels && minLevel == maxLevel;
+            uint32_t* out = A.list + (size_t)i * A.cap;
+            const uint32_t lt = (1u << lane) - 1;
+            for (int ix = x0; ix <= x1; ix++)
+                for (int iy = y0; iy <= y1; iy++) {
+                    const int cidx = ix * ORB_GRID_ROWS + iy;
+                    const int b = A.tgt.cell_start[cidx], e = A.tgt.cell_start[cidx + 1];
+                    for (int j0 = b; j0 < e; j0 += 32) {
+                        const int j = j0 + lane;
+                        bool ok = false; int id = 0;
+                        if (j < e) {
+                            id = A.tgt.cell_items[j];
+                            const orb_keypoint kp = A.tgt.kps[id];
+                            ok = true;
+                            if (checkLevels && !sameLevel) { if (kp.octave < minLevel || kp.octave > maxLevel) ok = false; }
+                            else if (sameLevel) { if (kp.octave != minLevel) ok = false; }
+                            if (fabsf(__fsub_rn(kp.x, u)) > r || fabsf(__fsub_rn(kp.y, v)) > r) ok = false;
+                        }
+                        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+                        if (ok) {
+                            const int pos = total + __popc(m & lt);
+                            if (pos < A.cap) out[pos] = ((uint32_t)hamming256(q, A.tgt.desc + (size_t)id * 32) << 22) | (uint32_t)id;
+                        }
+                        total += __popc(m);
+                    }
+                }
+        }
+    }
+    if (lane == 0) A.cnt[i] = total;
+}
+
+// Same parallel fixed-point resolution as k_sbp_resolve, with the acceptance rules above.
+__global__ void __launch_bounds__(1024)
+k_win_resolve(WinArgs A, int32_t* __restrict__ match, int8_t* __restrict__ bin_of, int* __restrict__ owner,
+              int* __restrict__ choice, int* __restrict__ result)
+{
+    __shared__ int hist[HISTO_LENGTH];
+    __shared__ int s_changed, s_err, s_cnt;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int n1 = A.nq, n2 = A.tgt.n;
+    if (tid < HISTO_LENGTH) hist[tid] = 0;
+    if (tid == 0) { s_err = 0; s_cnt = 0; }
+    for (int i = tid; i < n1; i += nt) choice[i] = -1;
+    for (int k = tid; k < n2; k += nt) bin_of[k] = -1;
+    __syncthreads();
+    for (int round = 0; round <= n1; round++) {
+        for (int k = tid; k < n2; k += nt) owner[k] = INT_MAX;
+        if (tid == 0) s_changed = 0;
+        __syncthreads();
+        for (int i = tid; i < n1; i += nt) { const int c = choice[i]; if (c >= 0) atomicMin(&owner[c], i); }
+        __syncthreads();
+        for (int i = tid; i < n1; i += nt) {
+            const int n = A.cnt[i];
+            if (n <= 0) continue;
+            if (n > A.cap) { s_err = 1; continue; }
+            const uint32_t* L = A.list + (size_t)i * A.cap;
+            int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx = -1, bestLevel = -1, bestLevel2 = -1;
+            for (int p = 0; p < n; p++) {
+                const uint32_t e = L[p];
+                const int id = (int)(e & 0x3fffff), dist = (int)(e >> 22);
+                if (match[id] >= 0) continue;                     // keypoint already carries a map point
+                if (owner[id] < i) continue;                      // claimed by an earlier query
+                if (dist < bestDist) {
+                    bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestIdx = id;
+                    if (A.accept == WIN_ACCEPT_LEVEL_RATIO) bestLevel = A.tgt.kps[id].octave;
+                } else if (dist < bestDist2) {
+                    bestDist2 = dist;
+                    if (A.accept == WIN_ACCEPT_LEVEL_RATIO) bestLevel2 = A.tgt.kps[id].octave;
+                }
+            }
+            bool ok = bestIdx >= 0 && bestDist <= A.th_dist;
+            if (ok && A.accept == WIN_ACCEPT_RATIO) ok = (float)bestDist <= __fmul_rn((float)bestDist2, A.nnratio);
+            if (ok && A.accept == WIN_ACCEPT_LEVEL_RATIO) ok = !(bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(A.nnratio, (float)bestDist2));
+            const int c = ok ? bestIdx : -1;
+            if (c != choice[i]) { choice[i] = c; s_changed = 1; }
+        }
+        __syncthreads();
+        const int ch = s_changed;
+        __syncthreads();
+        if (!ch) break;
+    }
+    int mine = 0;
+    for (int i = tid; i < n1; i += nt) {
+        const int c = choice[i];
+        if (c < 0) continue;
+        match[c] = i;
+        mine++;
+        if (A.histogram) {
+            const int b = rot_bin(A.qangle[i], A.tgt.kps[c].angle);
+            bin_of[c] = (int8_t)b;
+            atomicAdd(&hist[b], 1);
+        }
+    }
+    atomicAdd(&s_cnt, mine);
+    __syncthreads();
+    if (A.histogram) {
+        int i1, i2, i3;
+        three_maxima(hist, i1, i2, i3);
+        int removed = 0;
+        for (int k = tid; k < n2; k += nt) {
+            const int b = bin_of[k];
+            if (b >= 0 && b != i1 && b != i2 && b != i3) { match[k] = -1; removed++; }
+        }
+        atomicSub(&s_cnt, removed);
+        __syncthreads();
+    }
+    if (tid == 0) { result[0] = s_cnt; result[1] = s_err; }
+}
+
 // ------------------------------------------------------------------ K9: SearchByBoW scoring
 struct BowArgs {
     orb_featvec_view kf, f;
@@ -695,4 +868,32 @@ int orb_launch_search_by_bow(orb_ctx* c, const orb_featvec_view* kf_fv, const ui
 size_t orb_bow_scratch_bytes(int n_f)
 {
     return 256 + (((size_t)n_f * 4 + 255) & ~(size_t)255) + (((size_t)n_f + 255) & ~(size_t)255) + 256;
+}
+
+int orb_launch_search_window(orb_ctx* c, const orb_frame_view* tgt, const orb_window_query_set* q, int accept, float nnratio, int th_dist,
+                             int histogram, int32_t* match, int* d_result, uint8_t* scratch, size_t scratch_bytes, cudaStream_t s)
+{
+    (void)c;
+    WinArgs A;
+    A.tgt = *tgt; A.nq = q->n; A.active = q->active; A.qdesc = q->desc; A.u = q->u; A.v = q->v; A.xyz = q->xyz;
+    A.project = q->xyz != nullptr && q->u == nullptr;
+    for (int i = 0; i < 16; i++) A.T[i] = (A.project && q->Tcw16) ? q->Tcw16[i] : 0.f;
+    A.check_bounds = q->check_bounds; A.radius = q->radius; A.radius_const = q->radius_const;
+    A.minl = q->min_level; A.maxl = q->max_level; A.qangle = q->angle;
+    A.accept = accept; A.nnratio = nnratio; A.th_dist = th_dist; A.histogram = histogram && q->angle;
+    if (tgt->n >= (1 << 22)) return ORB_ERR_CAPACITY;
+    size_t off = 0;
+    A.cnt = (int*)(scratch + off); off += ((size_t)q->n * 4 + 255) & ~(size_t)255;
+    int* choice = (int*)(scratch + off); off += ((size_t)q->n * 4 + 255) & ~(size_t)255;
+    int* owner = (int*)(scratch + off); off += ((size_t)tgt->n * 4 + 255) & ~(size_t)255;
+    int8_t* bin_of = (int8_t*)(scratch + off); off += ((size_t)tgt->n + 255) & ~(size_t)255;
+    const size_t avail = scratch_bytes > off ? (scratch_bytes - off) / 4 : 0;
+    A.cap = (int)std::min<size_t>((size_t)tgt->n, q->n ? avail / (size_t)q->n : 0);
+    A.cap = std::min(A.cap, 1 << 20);
+    A.list = (uint32_t*)(scratch + off);
+    if (A.cap < 1) return ORB_ERR_CAPACITY;
+    k_win_candidates<<<(q->n * 32 + 255) / 256, 256, 0, s>>>(A);
+    k_win_resolve<<<1, 1024, 0, s>>>(A, match, bin_of, owner, choice, d_result);
+    ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
 }

@@ -6,7 +6,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import (GRID_COLS, GRID_ROWS, KP_DTYPE, FeatVecView, FrameView, check, lib, ptr)
+from ._lib import (GRID_COLS, GRID_ROWS, KP_DTYPE, FeatVecView, FrameView, WindowQuerySet, check, lib, ptr)
 from .extractor import ORBextractor
 
 
@@ -83,6 +83,65 @@ class ORBmatcher:
                                              th, int(self.mbCheckOrientation), ptr(match_cur), C.byref(n)),
               "orb_search_by_projection")
         return n.value, match_cur
+
+    # ---- the other windowed searches, all through orb_search_window ----
+    ACCEPT_BEST, ACCEPT_RATIO, ACCEPT_LEVEL_RATIO = 0, 1, 2
+
+    def _search_window(self, target, n, active, desc, u, v, xyz, Tcw, check_bounds, radius, radius_const, min_level, max_level,
+                       angle, accept, th_dist, check_ori, match):
+        keep = []
+
+        def arr(a, dt):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dt)
+            keep.append(a)
+            return a.ctypes.data
+        q = WindowQuerySet(n, arr(active, np.uint8), arr(desc, np.uint8), arr(u, np.float32), arr(v, np.float32),
+                           arr(xyz, np.float32), arr(None if Tcw is None else np.asarray(Tcw, np.float32).reshape(16), np.float32),
+                           int(check_bounds), arr(radius, np.float32), float(radius_const), arr(min_level, np.int32),
+                           arr(max_level, np.int32), arr(angle, np.float32))
+        tv = target.view()
+        nm = C.c_int(0)
+        check(lib().orb_search_window(self._h, C.byref(tv), C.byref(q), accept, self.mfNNratio, th_dist, int(check_ori),
+                                      ptr(match), C.byref(nm)), "orb_search_window")
+        return nm.value, match
+
+    def SearchByProjectionMapPoints(self, F, in_view, proj_x, proj_y, level, view_cos, mp_desc, th=3.0, match_f=None):
+        """ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:49-125).
+        Per map point: mbTrackInView && !isBad, mTrackProjX/Y, mnTrackScaleLevel, mTrackViewCos, GetDescriptor()."""
+        n = len(in_view)
+        if match_f is None:
+            match_f = np.full(F.N, -1, np.int32)
+        sf = np.ones(F.nlevels, np.float32)
+        for i in range(1, F.nlevels):
+            sf[i] = np.float32(sf[i - 1] * np.float32(F.scale_factor))
+        level = np.asarray(level, np.int32)
+        r = np.where(np.asarray(view_cos, np.float32).astype(np.float64) > 0.998, np.float32(2.5), np.float32(4.0)).astype(np.float32)
+        if th != 1.0:                                      # bFactor, :53,:69-70
+            r = (r * np.float32(th)).astype(np.float32)
+        radius = (r * sf[np.clip(level, 0, F.nlevels - 1)]).astype(np.float32)
+        return self._search_window(F, n, in_view, mp_desc, proj_x, proj_y, None, None, 0, radius, 0.0, level - 1, level, None,
+                                   self.ACCEPT_LEVEL_RATIO, self.TH_HIGH, False, match_f)
+
+    def WindowSearch(self, F1, F2, windowSize, f1_has_mp, minScaleLevel=-1, maxScaleLevel=2**31 - 1):
+        """ORBmatcher::WindowSearch (src/ORBmatcher.cc:409-516).  Returns (nmatches, vnMatches21)."""
+        lv = F1.kps["octave"].astype(np.int32)
+        active = np.asarray(f1_has_mp, np.uint8).copy()
+        if minScaleLevel > 0:
+            active[lv < minScaleLevel] = 0
+        if maxScaleLevel < 2**31 - 1:
+            active[lv > maxScaleLevel] = 0
+        match2 = np.full(F2.N, -1, np.int32)
+        return self._search_window(F2, F1.N, active, F1.desc, F1.kps["x"], F1.kps["y"], None, None, 0, None, float(windowSize),
+                                   lv, lv, F1.kps["angle"], self.ACCEPT_RATIO, self.TH_HIGH, self.mbCheckOrientation, match2)
+
+    def SearchByProjectionWindow(self, F1, F2, windowSize, f1_active, f1_xyz, Tc2w, match2):
+        """ORBmatcher::SearchByProjection(Frame &F1, Frame &F2, int windowSize, ...) (src/ORBmatcher.cc:519-594).
+        f1_active: F1 map point is live and not already among F2's; match2 (in/out) starts as F2.mvpMapPoints (>=0 = set)."""
+        lv = F1.kps["octave"].astype(np.int32)
+        return self._search_window(F2, F1.N, f1_active, F1.desc, None, None, f1_xyz, Tc2w, 0, None, float(windowSize), lv, lv, None,
+                                   self.ACCEPT_RATIO, self.TH_HIGH, False, match2)
 
     def SearchByBoW(self, kf_featvec, kf_desc, kf_kps, kf_mp_valid, f_featvec, f_desc, f_kps):
         """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) scoring (src/ORBmatcher.cc:155-284).

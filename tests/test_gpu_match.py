@@ -271,3 +271,49 @@ def test_cpp_shim_program(pkg, po, tmp_path):
     i1, d1, d2 = po.knn2(rd, rd)
     rm, rn = po.match_ratio(i1, d1, d2, np.float32(0.9), 50)
     assert nmatch == rn and np.array_equal(match, rm)
+
+
+# ---------------------------------------------------------------- further windowed searches
+@pytest.mark.parametrize("shape,nf,th", [((240, 320), 500, 3.0), ((480, 752), 1000, 1.0), ((376, 1241), 2000, 5.0)])
+def test_search_by_projection_mappoints_vs_oracle(pkg, po, shape, nf, th):
+    """ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>, th), src/ORBmatcher.cc:49-125 (same-level ratio rule)."""
+    m = pkg.ORBmatcher(0.8, True)
+    gcur, glast, ocur, olast, has, outl, xyz, T = _scene(po, pkg, m, shape[0], shape[1], nf, 8000 + nf, 15.0)
+    rng = np.random.default_rng(nf)
+    n = glast.N                                           # "map points" = last-frame features seen slightly displaced
+    proj_x = (glast.kps["x"] + 3 + rng.normal(0, 1.0, n)).astype(np.float32)
+    proj_y = (glast.kps["y"] + 2 + rng.normal(0, 1.0, n)).astype(np.float32)
+    level = np.clip(glast.kps["octave"] + rng.integers(0, 2, n), 0, 7).astype(np.int32)
+    view_cos = rng.uniform(0.99, 1.0, n).astype(np.float32)
+    in_view = (rng.random(n) < 0.85).astype(np.uint8)
+    pre = np.full(gcur.N, -1, np.int32)
+    pre[::11] = 7                                         # keypoints that already carry a map point
+    nm, match = m.SearchByProjectionMapPoints(gcur, in_view, proj_x, proj_y, level, view_cos, glast.desc, th, match_f=pre.copy())
+    rn, rmatch = po.search_by_projection_mappoints(ocur, in_view, proj_x, proj_y, level, view_cos, glast.desc, th, 0.8, match_f=pre.copy())
+    assert rn > 20
+    assert nm == rn and np.array_equal(match, rmatch)
+
+
+@pytest.mark.parametrize("shape,nf,win,ori,minl", [((240, 320), 500, 20, True, -1), ((480, 752), 1000, 50, True, -1),
+                                                    ((376, 1241), 2000, 100, False, 2)])
+def test_window_search_vs_oracle(pkg, po, shape, nf, win, ori, minl):
+    """ORBmatcher::WindowSearch, src/ORBmatcher.cc:409-516."""
+    m = pkg.ORBmatcher(0.9, ori)
+    gcur, glast, ocur, olast, has, outl, xyz, T = _scene(po, pkg, m, shape[0], shape[1], nf, 8100 + nf, 15.0)
+    nm, match = m.WindowSearch(glast, gcur, win, has, minScaleLevel=minl)
+    rn, rmatch = po.window_search(olast, ocur, has, win, 0.9, ori, min_level=minl)
+    assert rn > 20
+    assert nm == rn and np.array_equal(match, rmatch)
+
+
+@pytest.mark.parametrize("shape,nf,win", [((240, 320), 500, 15), ((480, 752), 1000, 15), ((376, 1241), 2000, 30)])
+def test_search_by_projection_window_vs_oracle(pkg, po, shape, nf, win):
+    """ORBmatcher::SearchByProjection(F1, F2, windowSize, ...), src/ORBmatcher.cc:519-594 (no bounds test, pre-filled matches)."""
+    m = pkg.ORBmatcher(0.9, True)
+    gcur, glast, ocur, olast, has, outl, xyz, T = _scene(po, pkg, m, shape[0], shape[1], nf, 8200 + nf, 15.0)
+    pre = np.full(gcur.N, -1, np.int32)
+    pre[::5] = 100000                                     # F2.mvpMapPoints already set
+    nm, match = m.SearchByProjectionWindow(glast, gcur, win, has, xyz, T, pre.copy())
+    rn, rmatch = po.search_by_projection_window(olast, ocur, has, xyz, T, win, 0.9, pre.copy())
+    assert rn > 10
+    assert nm == rn and np.array_equal(match, rmatch)
