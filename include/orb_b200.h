@@ -193,6 +193,16 @@ int orb_search_by_bow(orb_ctx*, const orb_featvec_view* kf_fv, const uint8_t* kf
                       const orb_featvec_view* f_fv, const uint8_t* f_desc, const orb_keypoint* f_kps, int n_f,
                       float nnratio, int check_ori, int32_t* match_f, int* nmatches);
 
+/* ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12), src/ORBmatcher.cc:715-850
+ * (loop closing).  valid1/valid2[i] != 0 <=> the feature has a live map point; match12[n1] out = feature index in
+ * the second keyframe whose map point is assigned to vpMatches12[idx1], or -1.  Acceptance: bestDist1 < TH_LOW and
+ * (float)bestDist1 < nnratio*(float)bestDist2 (:791-793). */
+int orb_search_by_bow_kf(orb_ctx*, const orb_featvec_view* fv1, const uint8_t* desc1, const orb_keypoint* kps1,
+                         const uint8_t* valid1, int n1,
+                         const orb_featvec_view* fv2, const uint8_t* desc2, const orb_keypoint* kps2,
+                         const uint8_t* valid2, int n2,
+                         float nnratio, int check_ori, int32_t* match12, int* nmatches);
+
 /* pinned host memory helpers (page-locked buffers make the host<->device copies asynchronous) */
 void* orb_host_alloc(size_t bytes);
 void  orb_host_free(void* p);

@@ -983,4 +983,54 @@ int orc_search_by_projection_window(const orc_frame* f1, const orc_frame* f2, co
     return nmatches;
 }
 
+/* ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...), src/ORBmatcher.cc:715-850 */
+int orc_search_by_bow_kf(const orc_featvec* fv1, const uint8_t* desc1, const orc_keypoint* kps1, const uint8_t* valid1, int n1,
+                         const orc_featvec* fv2, const uint8_t* desc2, const orc_keypoint* kps2, const uint8_t* valid2, int n2,
+                         float nnratio, int check_ori, int32_t* match12)
+{
+    const int HISTO_LENGTH = 30, TH_LOW = 50;
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    std::vector<char> vbMatched2(n2 > 0 ? n2 : 1, 0);
+    std::vector<int> rotHist[30];
+    int nmatches = 0, a = 0, b = 0;
+    while (a < fv1->nnodes && b < fv2->nnodes) {
+        if (fv1->node_id[a] == fv2->node_id[b]) {
+            for (int i1 = fv1->start[a]; i1 < fv1->start[a + 1]; i1++) {
+                const int idx1 = fv1->items[i1];
+                if (!valid1[idx1]) continue;
+                const uint8_t* d1 = desc1 + (size_t)idx1 * 32;
+                int bestDist1 = INT_MAX, bestIdx2 = -1, bestDist2 = INT_MAX;
+                for (int i2 = fv2->start[b]; i2 < fv2->start[b + 1]; i2++) {
+                    const int idx2 = fv2->items[i2];
+                    if (vbMatched2[idx2] || !valid2[idx2]) continue;
+                    const int dist = orc_descriptor_distance(d1, desc2 + (size_t)idx2 * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 < TH_LOW && (float)bestDist1 < nnratio * (float)bestDist2) {
+                    match12[idx1] = bestIdx2;
+                    vbMatched2[bestIdx2] = 1;
+                    if (check_ori) rotHist[rot_bin(kps1[idx1].angle, kps2[bestIdx2].angle)].push_back(idx1);
+                    nmatches++;
+                }
+            }
+            a++; b++;
+        } else if (fv1->node_id[a] < fv2->node_id[b]) {
+            while (a < fv1->nnodes && fv1->node_id[a] < fv2->node_id[b]) a++;
+        } else {
+            while (b < fv2->nnodes && fv2->node_id[b] < fv1->node_id[a]) b++;
+        }
+    }
+    if (check_ori) {
+        int hs[30], i1, i2, i3;
+        for (int i = 0; i < HISTO_LENGTH; i++) hs[i] = (int)rotHist[i].size();
+        orc_three_maxima(hs, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == i1 || i == i2 || i == i3) continue;
+            for (int id : rotHist[i]) { match12[id] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
 } // extern "C"

@@ -130,6 +130,12 @@ int   orc_window_search(const orc_frame* f1, const orc_frame* f2, const uint8_t*
 int   orc_search_by_projection_window(const orc_frame* f1, const orc_frame* f2, const uint8_t* f1_active, const float* f1_xyz,
                                       const float* Tc2w16, int window, float nnratio, int32_t* match2);
 
+/* ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*>&), src/ORBmatcher.cc:715-850.
+ * valid1/valid2: feature has a live map point.  match12[idx1] out = idx2 or -1. */
+int   orc_search_by_bow_kf(const orc_featvec* fv1, const uint8_t* desc1, const orc_keypoint* kps1, const uint8_t* valid1, int n1,
+                           const orc_featvec* fv2, const uint8_t* desc2, const orc_keypoint* kps2, const uint8_t* valid2, int n2,
+                           float nnratio, int check_ori, int32_t* match12);
+
 #ifdef __cplusplus
 }
 #endif

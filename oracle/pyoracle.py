@@ -88,6 +88,9 @@ def lib():
         L.orc_window_search.argtypes = [C.POINTER(_Frame), C.POINTER(_Frame), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]
         L.orc_search_by_projection_window.argtypes = [C.POINTER(_Frame), C.POINTER(_Frame), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                                       C.c_float, C.c_void_p]
+        L.orc_search_by_bow_kf.argtypes = [C.POINTER(_FeatVec), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                           C.POINTER(_FeatVec), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                           C.c_float, C.c_int, C.c_void_p]
         L.orc_three_maxima.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 3
         _lib = L
     return _lib
@@ -353,3 +356,15 @@ def search_by_projection_window(f1, f2, f1_active, f1_xyz, Tc2w, window, nnratio
     T = np.ascontiguousarray(Tc2w, np.float32).reshape(16)
     n = lib().orc_search_by_projection_window(C.byref(f1.c), C.byref(f2.c), _p(act), _p(xyz), _p(T), window, nnratio, _p(match2))
     return n, match2
+
+
+def search_by_bow_kf(fv1, desc1, kps1, valid1, fv2, desc2, kps2, valid2, nnratio, check_ori=True):
+    a, keep_a = _fv(*fv1)
+    b, keep_b = _fv(*fv2)
+    desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
+    kps1 = np.ascontiguousarray(kps1, KP_DTYPE); kps2 = np.ascontiguousarray(kps2, KP_DTYPE)
+    v1 = np.ascontiguousarray(valid1, np.uint8); v2 = np.ascontiguousarray(valid2, np.uint8)
+    m = np.full(len(kps1), -1, np.int32)
+    n = lib().orc_search_by_bow_kf(C.byref(a), _p(desc1), _p(kps1), _p(v1), len(kps1), C.byref(b), _p(desc2), _p(kps2), _p(v2),
+                                   len(kps2), nnratio, int(check_ori), _p(m))
+    return n, m

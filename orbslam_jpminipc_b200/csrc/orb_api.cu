@@ -676,18 +676,22 @@ int orb_search_window(orb_ctx* c, const orb_frame_view* target, const orb_window
     return res[1] ? ORB_ERR_CAPACITY : ORB_OK;
 }
 
-int orb_search_by_bow(orb_ctx* c, const orb_featvec_view* kf_fv, const uint8_t* kf_desc, const orb_keypoint* kf_kps,
-                      const uint8_t* kf_mp_valid, int n_kf,
-                      const orb_featvec_view* f_fv, const uint8_t* f_desc, const orb_keypoint* f_kps, int n_f,
-                      float nnratio, int check_ori, int32_t* match_f, int* nmatches)
+} // extern "C"
+
+// shared body of SearchByBoW(KF, Frame) and SearchByBoW(KF, KF): the latter adds the validity of the second side's map
+// points, the strict TH_LOW test and an output indexed by the first keyframe's features (match12)
+static int search_by_bow_impl(orb_ctx* c, const orb_featvec_view* kf_fv, const uint8_t* kf_desc, const orb_keypoint* kf_kps,
+                              const uint8_t* kf_mp_valid, int n_kf,
+                              const orb_featvec_view* f_fv, const uint8_t* f_desc, const orb_keypoint* f_kps, int n_f,
+                              float nnratio, int check_ori, int32_t* match_f, int* nmatches, const uint8_t* f_valid, int32_t* match12)
 {
     if (!c || !kf_fv || !f_fv || !nmatches || n_kf < 0 || n_f < 0 || kf_fv->nnodes < 0 || f_fv->nnodes < 0) return ORB_ERR_INVALID;
     *nmatches = 0;
-    if (n_f == 0) return ORB_OK;
-    if (!match_f || !f_desc || !f_kps || (n_kf > 0 && (!kf_desc || !kf_kps || !kf_mp_valid))) return ORB_ERR_INVALID;
+    if (n_f == 0) { if (match12 && !is_device_ptr(match12)) for (int i = 0; i < n_kf; i++) match12[i] = -1; return ORB_OK; }
+    if ((!match_f && !match12) || !f_desc || !f_kps || (n_kf > 0 && (!kf_desc || !kf_kps || !kf_mp_valid))) return ORB_ERR_INVALID;
     ORB_CUDA(cudaSetDevice(c->device));
     const bool dev = is_device_ptr(f_desc);
-    if (is_device_ptr(match_f) != dev) return ORB_ERR_INVALID;
+    if (is_device_ptr(match12 ? (const void*)match12 : (const void*)match_f) != dev) return ORB_ERR_INVALID;
     cudaStream_t s = c->streams[0];
     // item totals live at start[nnodes]
     int kf_total = 0, f_total = 0;
@@ -696,7 +700,7 @@ int orb_search_by_bow(orb_ctx* c, const orb_featvec_view* kf_fv, const uint8_t* 
     const size_t work = orb_bow_scratch_bytes(n_f);
     size_t in_bytes = 0;
     if (!dev) in_bytes = al256((size_t)n_kf * 32) + al256((size_t)n_kf * 28) + al256(n_kf) + al256((size_t)n_f * 32) + al256((size_t)n_f * 28) +
-                         al256((size_t)n_f * 4) + 2 * al256((size_t)(kf_fv->nnodes + 1) * 4) + al256((size_t)kf_total * 4 + 4) +
+                         al256((size_t)n_f * 4) + al256(n_f) + al256((size_t)std::max(n_kf, 1) * 4) + 2 * al256((size_t)(kf_fv->nnodes + 1) * 4) + al256((size_t)kf_total * 4 + 4) +
                          2 * al256((size_t)(f_fv->nnodes + 1) * 4) + al256((size_t)f_total * 4 + 4) + 4096;
     int rc = match_scratch(c, in_bytes + work + 256, in_bytes + 4096);
     if (rc) return rc;
@@ -710,18 +714,42 @@ int orb_search_by_bow(orb_ctx* c, const orb_featvec_view* kf_fv, const uint8_t* 
         (rc = stage_in(b, dev, f.start, (size_t)f.nnodes + 1, s)) || (rc = stage_in(b, dev, f.items, (size_t)f_total, s)) ||
         (rc = stage_in(b, dev, kf_desc, (size_t)n_kf * 32, s)) || (rc = stage_in(b, dev, kf_kps, (size_t)n_kf, s)) ||
         (rc = stage_in(b, dev, kf_mp_valid, (size_t)n_kf, s)) || (rc = stage_in(b, dev, f_desc, (size_t)n_f * 32, s)) ||
-        (rc = stage_in(b, dev, f_kps, (size_t)n_f, s))) return rc;
-    int32_t* d_match = dev ? match_f : (int32_t*)b.take((size_t)n_f * 4);
+        (rc = stage_in(b, dev, f_kps, (size_t)n_f, s)) || (rc = stage_in(b, dev, f_valid, (size_t)n_f, s))) return rc;
+    int32_t* d_match = (dev && match_f) ? match_f : (int32_t*)b.take((size_t)n_f * 4);
+    int32_t* d_match12 = !match12 ? nullptr : (dev ? match12 : (int32_t*)b.take((size_t)std::max(n_kf, 1) * 4));
     uint8_t* wk = (uint8_t*)b.take(work);
     if ((rc = b.flush(s))) return rc;
-    rc = orb_launch_search_by_bow(c, &a, kf_desc, kf_kps, kf_mp_valid, &f, f_desc, f_kps, n_f, f_total, nnratio, check_ori, d_match, wk, s);
+    rc = orb_launch_search_by_bow(c, &a, kf_desc, kf_kps, kf_mp_valid, &f, f_desc, f_kps, n_f, f_total, nnratio, check_ori, d_match, wk, s,
+                                  f_valid, d_match12, n_kf);
     if (rc) return rc;
     int res = 0;
-    if (!dev) ORB_CUDA(cudaMemcpyAsync(match_f, d_match, (size_t)n_f * 4, cudaMemcpyDeviceToHost, s));
+    if (!dev && match_f) ORB_CUDA(cudaMemcpyAsync(match_f, d_match, (size_t)n_f * 4, cudaMemcpyDeviceToHost, s));
+    if (!dev && match12 && n_kf) ORB_CUDA(cudaMemcpyAsync(match12, d_match12, (size_t)n_kf * 4, cudaMemcpyDeviceToHost, s));
     ORB_CUDA(cudaMemcpyAsync(&res, wk, sizeof res, cudaMemcpyDeviceToHost, s));
     ORB_CUDA(cudaStreamSynchronize(s));
     *nmatches = res;
     return ORB_OK;
+}
+
+
+extern "C" {
+
+int orb_search_by_bow(orb_ctx* c, const orb_featvec_view* kf_fv, const uint8_t* kf_desc, const orb_keypoint* kf_kps,
+                      const uint8_t* kf_mp_valid, int n_kf,
+                      const orb_featvec_view* f_fv, const uint8_t* f_desc, const orb_keypoint* f_kps, int n_f,
+                      float nnratio, int check_ori, int32_t* match_f, int* nmatches)
+{
+    if (!match_f) return ORB_ERR_INVALID;
+    return search_by_bow_impl(c, kf_fv, kf_desc, kf_kps, kf_mp_valid, n_kf, f_fv, f_desc, f_kps, n_f, nnratio, check_ori, match_f, nmatches,
+                              nullptr, nullptr);
+}
+
+int orb_search_by_bow_kf(orb_ctx* c, const orb_featvec_view* fv1, const uint8_t* desc1, const orb_keypoint* kps1, const uint8_t* valid1, int n1,
+                         const orb_featvec_view* fv2, const uint8_t* desc2, const orb_keypoint* kps2, const uint8_t* valid2, int n2,
+                         float nnratio, int check_ori, int32_t* match12, int* nmatches)
+{
+    if (!match12 || (n2 > 0 && !valid2)) return ORB_ERR_INVALID;
+    return search_by_bow_impl(c, fv1, desc1, kps1, valid1, n1, fv2, desc2, kps2, n2, nnratio, check_ori, nullptr, nmatches, valid2, match12);
 }
 
 int orb_measure_popc_peak(orb_ctx* c, double* gpopc_per_s)

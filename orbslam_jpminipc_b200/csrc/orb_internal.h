@@ -169,7 +169,7 @@ size_t orb_sbp_scratch_bytes(int n_cur, int n_last);
 int orb_launch_search_by_bow(orb_ctx* c, const orb_featvec_view* kf_fv, const uint8_t* kf_desc, const orb_keypoint* kf_kps,
                              const uint8_t* kf_mp_valid, const orb_featvec_view* f_fv, const uint8_t* f_desc,
                              const orb_keypoint* f_kps, int n_f, int f_items_total, float nnratio, int check_ori, int32_t* match_f,
-                             uint8_t* scratch, cudaStream_t s);
+                             uint8_t* scratch, cudaStream_t s, const uint8_t* f_valid = nullptr, int32_t* match12 = nullptr, int n_kf = 0);
 size_t orb_bow_scratch_bytes(int n_f);
 int orb_launch_search_window(orb_ctx* c, const orb_frame_view* tgt, const orb_window_query_set* q, int accept, float nnratio, int th_dist,
                              int histogram, int32_t* match, int* d_result, uint8_t* scratch, size_t scratch_bytes, cudaStream_t s);

@@ -618,6 +618,9 @@ struct BowArgs {
     float nnratio; int check_ori;
     int32_t* match_f; int8_t* bin_of; int* hist; int* result;   // hist[30], result[0]=nmatches, result[1]=overlap flag
     int* seen;                                                   // n_f counters for the disjointness check
+    const uint8_t* f_valid;                                      // KF-KF form (:769): second frame's feature needs a live map point (NULL: all)
+    int strict_low;                                              // KF-KF form (:791): bestDist1 < TH_LOW instead of <=
+    int32_t* match12; int n_kf;                                  // KF-KF form: output indexed by the first keyframe's features
 };
 
 // A frame feature that appears under two vocabulary nodes would couple the nodes through the claim
@@ -657,7 +660,8 @@ k_bow_match(BowArgs A)
             int d1 = INT_MAX, d2 = INT_MAX;
             for (int jf = fb + lane; jf < fe; jf += 32) {
                 const int realIdxF = A.f.items[jf];
-                if (((volatile int32_t*)A.match_f)[realIdxF] >= 0) continue;      // :205
+                if (((volatile int32_t*)A.match_f)[realIdxF] >= 0) continue;      // :205 / vbMatched2 :769
+                if (A.f_valid && !A.f_valid[realIdxF]) continue;
                 const int dist = hamming256(q, A.f_desc + (size_t)realIdxF * 32);
                 const unsigned long long key = ((unsigned long long)dist << 44) | ((unsigned long long)(jf - fb) << 22) | (unsigned long long)realIdxF;
                 best = key < best ? key : best;
@@ -673,7 +677,7 @@ k_bow_match(BowArgs A)
             }
             if (best == ~0ull) continue;
             const int bestIdxF = (int)(best & 0x3fffff);
-            if (d1 <= TH_LOW && (float)d1 < __fmul_rn(A.nnratio, (float)d2)) {    // :224-226
+            if ((A.strict_low ? d1 < TH_LOW : d1 <= TH_LOW) && (float)d1 < __fmul_rn(A.nnratio, (float)d2)) {    // :224-226 / :791-793
                 if (lane == 0) {
                     A.match_f[bestIdxF] = realIdxKF;
                     if (A.check_ori) {
@@ -707,6 +711,11 @@ k_bow_orientation(BowArgs A)
     if (removed) atomicAdd(&s_removed, removed);
     __syncthreads();
     if (threadIdx.x == 0) A.result[0] -= s_removed;
+    if (A.match12) {          // KF-KF form: vpMatches12[idx1] = feature of the second keyframe
+        for (int k = threadIdx.x; k < A.n_kf; k += blockDim.x) A.match12[k] = -1;
+        __syncthreads();
+        for (int k = threadIdx.x; k < A.n_f; k += blockDim.x) { const int first = A.match_f[k]; if (first >= 0) A.match12[first] = k; }
+    }
 }
 
 } // namespace
@@ -844,13 +853,14 @@ size_t orb_sbp_scratch_bytes(int n_cur, int n_last)
 int orb_launch_search_by_bow(orb_ctx* c, const orb_featvec_view* kf_fv, const uint8_t* kf_desc, const orb_keypoint* kf_kps,
                              const uint8_t* kf_mp_valid, const orb_featvec_view* f_fv, const uint8_t* f_desc,
                              const orb_keypoint* f_kps, int n_f, int f_items_total, float nnratio, int check_ori, int32_t* match_f,
-                             uint8_t* scratch, cudaStream_t s)
+                             uint8_t* scratch, cudaStream_t s, const uint8_t* f_valid, int32_t* match12, int n_kf)
 {
     (void)c;
     if (n_f >= (1 << 22)) return ORB_ERR_CAPACITY;
     BowArgs A;
     A.kf = *kf_fv; A.f = *f_fv; A.kf_desc = kf_desc; A.kf_kps = kf_kps; A.kf_valid = kf_mp_valid;
     A.f_desc = f_desc; A.f_kps = f_kps; A.n_f = n_f; A.nnratio = nnratio; A.check_ori = check_ori; A.match_f = match_f;
+    A.f_valid = f_valid; A.strict_low = match12 != nullptr; A.match12 = match12; A.n_kf = n_kf;
     // scratch: result[2] + hist[30] (256 B) | seen[n_f] | bin_of[n_f]
     A.result = (int*)scratch; A.hist = (int*)scratch + 2;
     A.seen = (int*)(scratch + 256);
@@ -860,7 +870,7 @@ int orb_launch_search_by_bow(orb_ctx* c, const orb_featvec_view* kf_fv, const ui
     ORB_CUDA(cudaMemsetAsync(match_f, 0xff, (size_t)std::max(n_f, 1) * 4, s));     // :159
     if (f_items_total > 0) k_bow_check<<<(f_items_total + 255) / 256, 256, 0, s>>>(A);
     if (kf_fv->nnodes > 0) k_bow_match<<<std::max(1, std::min(148, (kf_fv->nnodes + 7) / 8)), 256, 0, s>>>(A);
-    if (check_ori) k_bow_orientation<<<1, 256, 0, s>>>(A);
+    if (check_ori || match12) k_bow_orientation<<<1, 256, 0, s>>>(A);
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;
 }

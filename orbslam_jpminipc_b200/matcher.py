@@ -164,3 +164,22 @@ class ORBmatcher:
                                       C.byref(b), ptr(f_desc), ptr(f_kps), len(f_kps), self.mfNNratio,
                                       int(self.mbCheckOrientation), ptr(m), C.byref(n)), "orb_search_by_bow")
         return n.value, m
+
+    def SearchByBoWKeyFrames(self, fv1, desc1, kps1, valid1, fv2, desc2, kps2, valid2):
+        """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...) (src/ORBmatcher.cc:715-850).  Returns (nmatches, match12)."""
+        keep = []
+
+        def fv(t):
+            arrs = [np.ascontiguousarray(a, np.int32) for a in t]
+            keep.append(arrs)
+            return FeatVecView(len(arrs[0]), arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data)
+        a, b = fv(fv1), fv(fv2)
+        desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
+        kps1 = np.ascontiguousarray(kps1, KP_DTYPE); kps2 = np.ascontiguousarray(kps2, KP_DTYPE)
+        v1 = np.ascontiguousarray(valid1, np.uint8); v2 = np.ascontiguousarray(valid2, np.uint8)
+        m = np.full(len(kps1), -1, np.int32)
+        n = C.c_int(0)
+        check(lib().orb_search_by_bow_kf(self._h, C.byref(a), ptr(desc1), ptr(kps1), ptr(v1), len(kps1),
+                                         C.byref(b), ptr(desc2), ptr(kps2), ptr(v2), len(kps2), self.mfNNratio,
+                                         int(self.mbCheckOrientation), ptr(m), C.byref(n)), "orb_search_by_bow_kf")
+        return n.value, m

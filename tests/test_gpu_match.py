@@ -317,3 +317,15 @@ def test_search_by_projection_window_vs_oracle(pkg, po, shape, nf, win):
     rn, rmatch = po.search_by_projection_window(olast, ocur, has, xyz, T, win, 0.9, pre.copy())
     assert rn > 10
     assert nm == rn and np.array_equal(match, rmatch)
+
+
+@pytest.mark.parametrize("n1,n2,nnodes,ori", [(2000, 2000, 100, True), (600, 500, 12, True), (300, 300, 3, False)])
+def test_search_by_bow_keyframes_vs_oracle(pkg, po, n1, n2, nnodes, ori):
+    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...), src/ORBmatcher.cc:715-850."""
+    m = pkg.ORBmatcher(0.75, ori)
+    fv1, d1, k1, v1, fv2, d2, k2 = _bow_case(po, pkg, n1, n2, nnodes, seed=n1 + 7 * nnodes)
+    v2 = (np.random.default_rng(n2).random(n2) < 0.85).astype(np.uint8)
+    n, match = m.SearchByBoWKeyFrames(fv1, d1, k1, v1, fv2, d2, k2, v2)
+    rn, rmatch = po.search_by_bow_kf(fv1, d1, k1, v1, fv2, d2, k2, v2, 0.75, ori)
+    assert rn > 5
+    assert n == rn and np.array_equal(match, rmatch)
