@@ -3,7 +3,9 @@
  * include/ORBmatcher.h:37-107) for the matcher methods on the accelerated path:
  *   DescriptorDistance (src/ORBmatcher.cc:1794-1810)
  *   SearchByProjection(Frame&, const Frame&, th) (:1507-1620)
- *   SearchByBoW(KeyFrame*, Frame&, ...) candidate scoring (:155-284)
+ *   SearchByBoW(KeyFrame*, Frame&, ...) candidate scoring (:155-284), SearchByBoW(KeyFrame*, KeyFrame*, ...) (:715-850)
+ *   SearchByProjection(Frame&, vector<MapPoint*>, th) (:49-125), WindowSearch (:409-516),
+ *   SearchByProjection(F1, F2, windowSize, ...) (:519-594), SearchByProjection(Frame&, KeyFrame*, ...) (:1622-1746)
  * plus the brute-force best/second-best + ratio test used for relocalisation-sized searches.
  * Frame / KeyFrame / MapPoint are the reference's own graph classes and stay on the host: the shim
  * takes the plain arrays those methods read (see INTEGRATION.md for the adapter code).
@@ -85,6 +87,91 @@ public:
         return n;
     }
 
+    // ---- the other windowed searches (all map to orb_search_window, see orb_b200.h) ----
+    // Search matches between Frame keypoints and projected MapPoints (src/ORBmatcher.cc:49-125).  Per map point:
+    // mbTrackInView && !isBad, mTrackProjX/Y, mnTrackScaleLevel, mTrackViewCos, GetDescriptor().
+    int SearchByProjection(const FrameArrays& F, const std::vector<unsigned char>& inView, const std::vector<float>& projX,
+                           const std::vector<float>& projY, const std::vector<int32_t>& level, const std::vector<float>& viewCos,
+                           const std::vector<unsigned char>& mpDesc, float th, std::vector<int32_t>& matchF)
+    {
+        const size_t n = inView.size();
+        if (matchF.size() != F.mvKeysUn.size()) matchF.assign(F.mvKeysUn.size(), -1);
+        std::vector<float> sf(F.mnScaleLevels, 1.0f), radius(n);
+        for (int i = 1; i < F.mnScaleLevels; i++) sf[i] = sf[i - 1] * F.mfScaleFactor;
+        std::vector<int32_t> lmin(n), lmax(n);
+        const bool bFactor = th != 1.0;
+        for (size_t i = 0; i < n; i++) {
+            float r = viewCos[i] > 0.998 ? 2.5f : 4.0f;               // RadiusByViewingCos, :127-133
+            if (bFactor) r *= th;
+            radius[i] = r * sf[level[i]];
+            lmin[i] = level[i] - 1; lmax[i] = level[i];
+        }
+        orb_window_query_set q = { (int32_t)n, inView.data(), mpDesc.data(), projX.data(), projY.data(), nullptr, nullptr, 0,
+                                   radius.data(), 0.f, lmin.data(), lmax.data(), nullptr };
+        return window(F, q, ORB_ACCEPT_LEVEL_RATIO, TH_HIGH, false, matchF);
+    }
+
+    // WindowSearch (src/ORBmatcher.cc:409-516): matches21[i2] = i1 or -1
+    int WindowSearch(const FrameArrays& F1, const FrameArrays& F2, int windowSize, const std::vector<unsigned char>& f1HasMapPoint,
+                     std::vector<int32_t>& matches21, int minScaleLevel = -1, int maxScaleLevel = 2147483647)
+    {
+        const size_t n = F1.mvKeysUn.size();
+        std::vector<unsigned char> active(f1HasMapPoint);
+        std::vector<float> u(n), v(n), ang(n);
+        std::vector<int32_t> lv(n);
+        for (size_t i = 0; i < n; i++) {
+            const orb_keypoint& k = F1.mvKeysUn[i];
+            u[i] = k.x; v[i] = k.y; ang[i] = k.angle; lv[i] = k.octave;
+            if (minScaleLevel > 0 && k.octave < minScaleLevel) active[i] = 0;
+            if (maxScaleLevel < 2147483647 && k.octave > maxScaleLevel) active[i] = 0;
+        }
+        matches21.assign(F2.mvKeysUn.size(), -1);
+        orb_window_query_set q = { (int32_t)n, active.data(), F1.mDescriptors.data(), u.data(), v.data(), nullptr, nullptr, 0,
+                                   nullptr, (float)windowSize, lv.data(), lv.data(), ang.data() };
+        return window(F2, q, ORB_ACCEPT_RATIO, TH_HIGH, mbCheckOrientation, matches21);
+    }
+
+    // Refined matching with a pose guess for F2 (src/ORBmatcher.cc:519-594): matches2 starts as F2's own map points
+    int SearchByProjection(const FrameArrays& F1, const FrameArrays& F2, int windowSize, const std::vector<unsigned char>& f1Active,
+                           const std::vector<float>& f1WorldPos, const float* Tc2w, std::vector<int32_t>& matches2)
+    {
+        const size_t n = F1.mvKeysUn.size();
+        std::vector<int32_t> lv(n);
+        for (size_t i = 0; i < n; i++) lv[i] = F1.mvKeysUn[i].octave;
+        orb_window_query_set q = { (int32_t)n, f1Active.data(), F1.mDescriptors.data(), nullptr, nullptr, f1WorldPos.data(), Tc2w, 0,
+                                   nullptr, (float)windowSize, lv.data(), lv.data(), nullptr };
+        return window(F2, q, ORB_ACCEPT_RATIO, TH_HIGH, false, matches2);
+    }
+
+    // Project MapPoints seen in a KeyFrame into the Frame (relocalisation, src/ORBmatcher.cc:1622-1746).  predLevel is the
+    // level the reference derives from dist3D / minDistance (:1663-1669); kfAngle = pKF->GetKeyPointUn(i).angle.
+    int SearchByProjection(const FrameArrays& CurrentFrame, const std::vector<unsigned char>& active, const std::vector<float>& worldPos,
+                           const float* Tcw, const std::vector<int32_t>& predLevel, const std::vector<unsigned char>& mpDesc,
+                           const std::vector<float>& kfAngle, float th, int ORBdist, std::vector<int32_t>& matchCur)
+    {
+        const size_t n = active.size();
+        if (matchCur.size() != CurrentFrame.mvKeysUn.size()) matchCur.assign(CurrentFrame.mvKeysUn.size(), -1);
+        std::vector<float> sf(CurrentFrame.mnScaleLevels, 1.0f), radius(n);
+        for (int i = 1; i < CurrentFrame.mnScaleLevels; i++) sf[i] = sf[i - 1] * CurrentFrame.mfScaleFactor;
+        std::vector<int32_t> lmin(n), lmax(n);
+        for (size_t i = 0; i < n; i++) { radius[i] = th * sf[predLevel[i]]; lmin[i] = predLevel[i] - 1; lmax[i] = predLevel[i] + 1; }
+        orb_window_query_set q = { (int32_t)n, active.data(), mpDesc.data(), nullptr, nullptr, worldPos.data(), Tcw, 1,
+                                   radius.data(), 0.f, lmin.data(), lmax.data(), kfAngle.data() };
+        return window(CurrentFrame, q, ORB_ACCEPT_BEST, ORBdist, mbCheckOrientation, matchCur);
+    }
+
+    // SearchByBoW between two keyframes (loop closing, src/ORBmatcher.cc:715-850): matches12[idx1] = idx2 or -1
+    int SearchByBoW(const orb_featvec_view& fv1, const unsigned char* desc1, const orb_keypoint* kps1, const unsigned char* valid1, int n1,
+                    const orb_featvec_view& fv2, const unsigned char* desc2, const orb_keypoint* kps2, const unsigned char* valid2, int n2,
+                    std::vector<int32_t>& matches12)
+    {
+        matches12.assign(n1, -1);
+        int n = 0;
+        check(orb_search_by_bow_kf(ctx, &fv1, desc1, kps1, valid1, n1, &fv2, desc2, kps2, valid2, n2, mfNNratio,
+                                   mbCheckOrientation ? 1 : 0, matches12.data(), &n));
+        return n;
+    }
+
     // best / second-best over all DB rows + the acceptance test of :224-226; returns the number of matches
     int MatchBruteForce(const unsigned char* q, int nq, const unsigned char* db, long long ndb, int th, std::vector<int32_t>& match)
     {
@@ -101,6 +188,13 @@ public:
     static const int HISTO_LENGTH = 30;
 
 protected:
+    int window(const FrameArrays& target, const orb_window_query_set& q, int accept, int thDist, bool hist, std::vector<int32_t>& match)
+    {
+        orb_frame_view tv = target.view();
+        int n = 0;
+        check(orb_search_window(ctx, &tv, &q, accept, mfNNratio, thDist, hist ? 1 : 0, match.data(), &n));
+        return n;
+    }
     void check(int status)
     {
         if (status != ORB_OK)

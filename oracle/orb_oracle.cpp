@@ -983,6 +983,60 @@ int orc_search_by_projection_window(const orc_frame* f1, const orc_frame* f2, co
     return nmatches;
 }
 
+/* ORBmatcher::SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist), src/ORBmatcher.cc:1622-1746 */
+int orc_search_by_projection_kf(const orc_frame* cur, int nmp, const uint8_t* active, const float* xyz, const float* T,
+                                const int32_t* pred_level, const uint8_t* mp_desc, const float* kf_angle, float th, int orb_dist,
+                                int check_ori, int32_t* match_cur)
+{
+    const int HISTO_LENGTH = 30;
+    int nmatches = 0;
+    std::vector<int> rotHist[30];
+    std::vector<float> sf(cur->nlevels);
+    sf[0] = 1.0f;
+    for (int i = 1; i < cur->nlevels; i++) sf[i] = sf[i - 1] * cur->scale_factor;
+    std::vector<int32_t> cand(cur->n > 0 ? cur->n : 1);
+    for (int i = 0; i < nmp; i++) {
+        if (!active[i]) continue;
+        const float X = xyz[3 * i], Y = xyz[3 * i + 1], Z = xyz[3 * i + 2];
+        float c[3];
+        for (int r = 0; r < 3; r++) {
+            float t0 = T[4 * r + 0] * X + T[4 * r + 1] * Y + T[4 * r + 2] * Z;
+            c[r] = (float)((double)t0 * 1.0 + (double)T[4 * r + 3] * 1.0);
+        }
+        const float invzc = (float)(1.0 / c[2]);
+        float u = cur->fx * c[0] * invzc + cur->cx;
+        float v = cur->fy * c[1] * invzc + cur->cy;
+        if (u < cur->min_x || u > cur->max_x) continue;
+        if (v < cur->min_y || v > cur->max_y) continue;
+        const int nPredictedLevel = pred_level[i];
+        float radius = th * sf[nPredictedLevel];
+        int nc = orc_features_in_area(cur, u, v, radius, nPredictedLevel - 1, nPredictedLevel + 1, cand.data(), cur->n);
+        if (nc == 0) continue;
+        const uint8_t* dMP = mp_desc + (size_t)i * 32;
+        int bestDist = INT_MAX, bestIdx2 = -1;
+        for (int k = 0; k < nc; k++) {
+            int i2 = cand[k];
+            if (match_cur[i2] >= 0) continue;
+            int dist = orc_descriptor_distance(dMP, cur->desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= orb_dist) {
+            match_cur[bestIdx2] = i;
+            nmatches++;
+            if (check_ori) rotHist[rot_bin(kf_angle[i], cur->kps[bestIdx2].angle)].push_back(bestIdx2);
+        }
+    }
+    if (check_ori) {
+        int hs[30], i1, i2, i3;
+        for (int i = 0; i < HISTO_LENGTH; i++) hs[i] = (int)rotHist[i].size();
+        orc_three_maxima(hs, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != i1 && i != i2 && i != i3)
+                for (int id : rotHist[i]) { match_cur[id] = -1; nmatches--; }
+    }
+    return nmatches;
+}
+
 /* ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...), src/ORBmatcher.cc:715-850 */
 int orc_search_by_bow_kf(const orc_featvec* fv1, const uint8_t* desc1, const orc_keypoint* kps1, const uint8_t* valid1, int n1,
                          const orc_featvec* fv2, const uint8_t* desc2, const orc_keypoint* kps2, const uint8_t* valid2, int n2,

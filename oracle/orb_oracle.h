@@ -130,6 +130,13 @@ int   orc_window_search(const orc_frame* f1, const orc_frame* f2, const uint8_t*
 int   orc_search_by_projection_window(const orc_frame* f1, const orc_frame* f2, const uint8_t* f1_active, const float* f1_xyz,
                                       const float* Tc2w16, int window, float nnratio, int32_t* match2);
 
+/* ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*>&, float th, int ORBdist),
+ * src/ORBmatcher.cc:1622-1746.  active[i]: KF map point i is live and not already found; pred_level[i]: the level the
+ * reference derives from dist3D/minDistance (:1663-1669, computed by the caller); kf_angle[i] = pKF->GetKeyPointUn(i).angle. */
+int   orc_search_by_projection_kf(const orc_frame* cur, int nmp, const uint8_t* active, const float* xyz, const float* Tcw16,
+                                  const int32_t* pred_level, const uint8_t* mp_desc, const float* kf_angle, float th, int orb_dist,
+                                  int check_ori, int32_t* match_cur);
+
 /* ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*>&), src/ORBmatcher.cc:715-850.
  * valid1/valid2: feature has a live map point.  match12[idx1] out = idx2 or -1. */
 int   orc_search_by_bow_kf(const orc_featvec* fv1, const uint8_t* desc1, const orc_keypoint* kps1, const uint8_t* valid1, int n1,

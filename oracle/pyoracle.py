@@ -91,6 +91,7 @@ def lib():
         L.orc_search_by_bow_kf.argtypes = [C.POINTER(_FeatVec), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                            C.POINTER(_FeatVec), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                            C.c_float, C.c_int, C.c_void_p]
+        L.orc_search_by_projection_kf.argtypes = [C.POINTER(_Frame), C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_int, C.c_int, C.c_void_p]
         L.orc_three_maxima.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 3
         _lib = L
     return _lib
@@ -368,3 +369,12 @@ def search_by_bow_kf(fv1, desc1, kps1, valid1, fv2, desc2, kps2, valid2, nnratio
     n = lib().orc_search_by_bow_kf(C.byref(a), _p(desc1), _p(kps1), _p(v1), len(kps1), C.byref(b), _p(desc2), _p(kps2), _p(v2),
                                    len(kps2), nnratio, int(check_ori), _p(m))
     return n, m
+
+
+def search_by_projection_kf(cur, active, xyz, Tcw, pred_level, mp_desc, kf_angle, th, orb_dist, check_ori=True, match_cur=None):
+    if match_cur is None:
+        match_cur = np.full(cur.n, -1, np.int32)
+    a = [np.ascontiguousarray(active, np.uint8), np.ascontiguousarray(xyz, np.float32), np.ascontiguousarray(Tcw, np.float32).reshape(16),
+         np.ascontiguousarray(pred_level, np.int32), np.ascontiguousarray(mp_desc, np.uint8), np.ascontiguousarray(kf_angle, np.float32)]
+    n = lib().orc_search_by_projection_kf(C.byref(cur.c), len(a[0]), *[_p(x) for x in a], th, orb_dist, int(check_ori), _p(match_cur))
+    return n, match_cur

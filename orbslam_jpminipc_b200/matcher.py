@@ -143,6 +143,21 @@ class ORBmatcher:
         return self._search_window(F2, F1.N, f1_active, F1.desc, None, None, f1_xyz, Tc2w, 0, None, float(windowSize), lv, lv, None,
                                    self.ACCEPT_RATIO, self.TH_HIGH, False, match2)
 
+    def SearchByProjectionKeyFrame(self, CurrentFrame, active, xyz, Tcw, pred_level, mp_desc, kf_angle, th, ORBdist, match_cur=None):
+        """ORBmatcher::SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1622-1746).
+        active: KF map point live and not in sAlreadyFound; pred_level: the level predicted from dist3D/minDistance
+        (:1663-1669, host side); kf_angle: pKF->GetKeyPointUn(i).angle."""
+        n = len(active)
+        if match_cur is None:
+            match_cur = np.full(CurrentFrame.N, -1, np.int32)
+        sf = np.ones(CurrentFrame.nlevels, np.float32)
+        for i in range(1, CurrentFrame.nlevels):
+            sf[i] = np.float32(sf[i - 1] * np.float32(CurrentFrame.scale_factor))
+        lv = np.asarray(pred_level, np.int32)
+        radius = (np.float32(th) * sf[np.clip(lv, 0, CurrentFrame.nlevels - 1)]).astype(np.float32)
+        return self._search_window(CurrentFrame, n, active, mp_desc, None, None, xyz, Tcw, 1, radius, 0.0, lv - 1, lv + 1, kf_angle,
+                                   self.ACCEPT_BEST, int(ORBdist), self.mbCheckOrientation, match_cur)
+
     def SearchByBoW(self, kf_featvec, kf_desc, kf_kps, kf_mp_valid, f_featvec, f_desc, f_kps):
         """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) scoring (src/ORBmatcher.cc:155-284).
         featvec = (node_id, start, items) CSR arrays.  Returns (nmatches, match_f)."""

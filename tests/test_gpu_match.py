@@ -329,3 +329,19 @@ def test_search_by_bow_keyframes_vs_oracle(pkg, po, n1, n2, nnodes, ori):
     rn, rmatch = po.search_by_bow_kf(fv1, d1, k1, v1, fv2, d2, k2, v2, 0.75, ori)
     assert rn > 5
     assert n == rn and np.array_equal(match, rmatch)
+
+
+@pytest.mark.parametrize("shape,nf,th,dist,ori", [((240, 320), 500, 10.0, 100, True), ((480, 752), 1000, 3.0, 64, True),
+                                                   ((376, 1241), 2000, 10.0, 100, False)])
+def test_search_by_projection_keyframe_vs_oracle(pkg, po, shape, nf, th, dist, ori):
+    """ORBmatcher::SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist), src/ORBmatcher.cc:1622-1746."""
+    m = pkg.ORBmatcher(0.9, ori)
+    gcur, glast, ocur, olast, has, outl, xyz, T = _scene(po, pkg, m, shape[0], shape[1], nf, 8300 + nf, 15.0)
+    rng = np.random.default_rng(nf + 1)
+    pred = np.clip(glast.kps["octave"] + rng.integers(-1, 2, glast.N), 0, 7).astype(np.int32)
+    pre = np.full(gcur.N, -1, np.int32)
+    pre[::9] = 4242
+    nm, match = m.SearchByProjectionKeyFrame(gcur, has, xyz, T, pred, glast.desc, glast.kps["angle"], th, dist, match_cur=pre.copy())
+    rn, rmatch = po.search_by_projection_kf(ocur, has, xyz, T, pred, glast.desc, glast.kps["angle"], th, dist, ori, match_cur=pre.copy())
+    assert rn > 10
+    assert nm == rn and np.array_equal(match, rmatch)
