@@ -80,17 +80,20 @@ k_level0(const uint8_t* __restrict__ src, int w, int h, int sstride, size_t spit
 // the current one is computed.  A thread owns 4 adjacent output columns (source offsets and weights
 // in registers) and walks down 8 output rows; the horizontal pass of a source row is kept in
 // registers and reused when the next output row needs the same source row (4 rows in 5 at 1.2).
-constexpr int RT_W = 128, RT_H = 64, RS_ROWS = 8;
+// tile = tile_w columns x (1024 / tile_w) * rs_rows rows: 128 x 64 normally, 64 x 64 with 4 rows per thread when the
+// scale factor is so large that the 128-wide source footprint would exceed the 256-element TMA box limit
 
 __global__ void __launch_bounds__(256)
 k_resize(const __grid_constant__ CUtensorMap tm, uint8_t* __restrict__ planes, size_t fbytes, LevelGeom D,
          const int2* __restrict__ xtab, const int2* __restrict__ ytab, int box_w, int box_h, int buf_bytes,
-         int nimg, int* __restrict__ work_counter)
+         int nimg, int* __restrict__ work_counter, int RT_W, int RS_ROWS)
 {
     extern __shared__ __align__(128) uint8_t rs_sm[];       // two source tiles of buf_bytes each
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ int s_next[2];
     const int tid = threadIdx.x;
+    const int ncg = RT_W >> 2;                              // column groups (4 columns each) per tile
+    const int RT_H = (256 / ncg) * RS_ROWS;
     const int tiles_x = (D.w + RT_W - 1) / RT_W, tiles_y = (D.h + RT_H - 1) / RT_H;
     const int ntiles = tiles_x * tiles_y, total = ntiles * nimg;
     const int2* xt = xtab + D.xtab_off;
@@ -116,7 +119,7 @@ k_resize(const __grid_constant__ CUtensorMap tm, uint8_t* __restrict__ planes, s
     __syncthreads();
     int item = blockIdx.x;
     if (tid == 0 && item < total) issue(item, 0);
-    const int cgx = (tid & 31) * 4, rg = tid >> 5;           // 32 column groups x 8 row groups
+    const int rg = tid / ncg, cgx = (tid - rg * ncg) * 4;
     for (int it = 0; item < total; it++) {
         const int buf = it & 1;
         int x0, y0, f, sxo, syo;
@@ -936,12 +939,13 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
     mark();
     for (int l = 1; l < P.nlevels; l++) {
         const LevelGeom& D = P.L[l];
-        const int tiles = ((D.w + RT_W - 1) / RT_W) * ((D.h + RT_H - 1) / RT_H) * nimg;
+        const int tw = c->rs_tile_w[l], rr = c->rs_rows[l], th = (1024 / tw) * rr;
+        const int tiles = ((D.w + tw - 1) / tw) * ((D.h + th - 1) / th) * nimg;
         const int bufb = (c->rs_box_w[l] * c->rs_box_h[l] + 127) & ~127;
         const int grid = std::min(tiles, c->num_sms * 4);
         cudaMemsetAsync(W.d_counters + 4 + l, 0, sizeof(int), s);
         k_resize<<<grid, 256, 2 * bufb, s>>>(W.tm_resize.m[l], W.d_planes, fb, D, c->d_xtab, c->d_ytab, c->rs_box_w[l], c->rs_box_h[l],
-                                               bufb, nimg, W.d_counters + 4 + l);
+                                               bufb, nimg, W.d_counters + 4 + l, tw, rr);
         launches++;
     }
     k_border<<<dim3((P.L[0].border_items + 255) / 256, nimg * P.nlevels), 256, 0, s>>>(W.d_planes, W.d_blur, fb, c->d_plan);

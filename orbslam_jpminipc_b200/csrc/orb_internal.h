@@ -102,7 +102,8 @@ struct orb_ctx {
     std::vector<CellGeom> cells;
     std::vector<Tile> tiles_fast, tiles_blur;
     std::vector<int2> xtab, ytab;
-    int rs_box_w[ORB_MAX_LEVELS] = { 0 }, rs_box_h[ORB_MAX_LEVELS] = { 0 };   // k_resize TMA box (source footprint of a 128x64 tile)
+    int rs_box_w[ORB_MAX_LEVELS] = { 0 }, rs_box_h[ORB_MAX_LEVELS] = { 0 };   // k_resize TMA box (source footprint of one output tile)
+    int rs_tile_w[ORB_MAX_LEVELS] = { 0 }, rs_rows[ORB_MAX_LEVELS] = { 0 };   // k_resize tile width / rows per thread
 
     // device tables (shared by both work sets)
     Plan* d_plan = nullptr;

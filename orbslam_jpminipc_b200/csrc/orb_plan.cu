@@ -103,19 +103,25 @@ int orb_build_plan(orb_ctx* c, int w, int h)
         if (l > 0) {
             axis_table(P.L[l - 1].w, L.w, true, c->xtab);
             axis_table(P.L[l - 1].h, L.h, false, c->ytab);
-            // largest source footprint of a 128x64 output tile, from a 16-byte aligned origin (k_resize TMA box)
-            int mw = 16, mr = 1;
-            for (int x0 = 0; x0 < L.w; x0 += 128) {
-                const int x1 = std::min(x0 + 128, L.w) - 1;
-                const int lo = (c->xtab[L.xtab_off + x0].x & 0xffff) & ~15, hi = c->xtab[L.xtab_off + x1].x >> 16;
-                mw = std::max(mw, hi - lo + 1);
+            // largest source footprint of one output tile, from a 16-byte aligned origin (k_resize TMA box, <= 256 per side);
+            // 128x64 tiles normally, 64x64 (4 rows per thread) for scale factors whose 128-wide footprint is too large
+            bool fits = false;
+            for (int attempt = 0; attempt < 2 && !fits; attempt++) {
+                const int tw = attempt ? 64 : 128, rr = attempt ? 4 : 8, th = (1024 / tw) * rr;
+                int mw = 16, mr = 1;
+                for (int x0 = 0; x0 < L.w; x0 += tw) {
+                    const int x1 = std::min(x0 + tw, L.w) - 1;
+                    const int lo = (c->xtab[L.xtab_off + x0].x & 0xffff) & ~15, hi = c->xtab[L.xtab_off + x1].x >> 16;
+                    mw = std::max(mw, hi - lo + 1);
+                }
+                for (int y0 = 0; y0 < L.h; y0 += th) {
+                    const int y1 = std::min(y0 + th, L.h) - 1;
+                    mr = std::max(mr, (c->ytab[L.ytab_off + y1].x >> 16) - (c->ytab[L.ytab_off + y0].x & 0xffff) + 1);
+                }
+                c->rs_box_w[l] = (mw + 15) & ~15; c->rs_box_h[l] = mr; c->rs_tile_w[l] = tw; c->rs_rows[l] = rr;
+                fits = c->rs_box_w[l] <= 256 && mr <= 256;
             }
-            for (int y0 = 0; y0 < L.h; y0 += 64) {
-                const int y1 = std::min(y0 + 64, L.h) - 1;
-                mr = std::max(mr, (c->ytab[L.ytab_off + y1].x >> 16) - (c->ytab[L.ytab_off + y0].x & 0xffff) + 1);
-            }
-            c->rs_box_w[l] = (mw + 15) & ~15; c->rs_box_h[l] = mr;
-            if (c->rs_box_w[l] > 256 || mr > 256) return ORB_ERR_CAPACITY;      // TMA box limit (scale factors above ~1.9)
+            if (!fits) return ORB_ERR_CAPACITY;      // scale factors above ~3.7
         }
         L.border_base = border;
         L.border_items = 2 * ORB_EDGE * (L.stride / 4) + L.h * (4 + L.stride / 4 - (ORB_EDGE + L.w) / 4);

@@ -106,7 +106,8 @@ def test_batch_equals_single_and_chunks(pkg, po):
 def test_other_parameters(pkg, po):
     from orbslam_jpminipc_b200.synth import synth_frame
     img = synth_frame(360, 480, 5000)
-    for nf, sf, nl, th in [(800, 1.2, 8, 12), (600, 1.5, 5, 20), (500, 1.1, 6, 5), (1200, 1.2, 4, 30)]:
+    for nf, sf, nl, th in [(800, 1.2, 8, 12), (600, 1.5, 5, 20), (500, 1.1, 6, 5), (1200, 1.2, 4, 30), (300, 1.2, 1, 20),
+                           (400, 2.0, 3, 20), (400, 1.2, 2, 9), (500, 2.5, 2, 20)]:
         ex = pkg.ORBextractor(nf, sf, nl, 1, th, max_width=480, max_height=360, max_batch=1)
         kps, desc = ex(img)
         rk, rd = po.OracleExtractor(nf, sf, nl, 1, th)(img)
