@@ -5,7 +5,8 @@
  *   SearchByProjection(Frame&, const Frame&, th) (:1507-1620)
  *   SearchByBoW(KeyFrame*, Frame&, ...) candidate scoring (:155-284), SearchByBoW(KeyFrame*, KeyFrame*, ...) (:715-850)
  *   SearchByProjection(Frame&, vector<MapPoint*>, th) (:49-125), WindowSearch (:409-516),
- *   SearchByProjection(F1, F2, windowSize, ...) (:519-594), SearchByProjection(Frame&, KeyFrame*, ...) (:1622-1746)
+ *   SearchByProjection(F1, F2, windowSize, ...) (:519-594), SearchByProjection(Frame&, KeyFrame*, ...) (:1622-1746),
+ *   SearchForInitialization (:598-713)
  * plus the brute-force best/second-best + ratio test used for relocalisation-sized searches.
  * Frame / KeyFrame / MapPoint are the reference's own graph classes and stay on the host: the shim
  * takes the plain arrays those methods read (see INTEGRATION.md for the adapter code).
@@ -129,6 +130,19 @@ public:
         orb_window_query_set q = { (int32_t)n, active.data(), F1.mDescriptors.data(), u.data(), v.data(), nullptr, nullptr, 0,
                                    nullptr, (float)windowSize, lv.data(), lv.data(), ang.data() };
         return window(F2, q, ORB_ACCEPT_RATIO, TH_HIGH, mbCheckOrientation, matches21);
+    }
+
+    // SearchForInitialization (src/ORBmatcher.cc:598-713): vbPrevMatched holds x,y per F1 keypoint (in/out)
+    int SearchForInitialization(const FrameArrays& F1, const FrameArrays& F2, std::vector<float>& vbPrevMatched,
+                                std::vector<int32_t>& vnMatches12, int windowSize = 10)
+    {
+        if (vbPrevMatched.size() != 2 * F1.mvKeysUn.size()) throw std::invalid_argument("vbPrevMatched: one point per F1 keypoint");
+        vnMatches12.assign(F1.mvKeysUn.size(), -1);
+        orb_frame_view v1 = F1.view(), v2 = F2.view();
+        int n = 0;
+        check(orb_search_for_initialization(ctx, &v1, &v2, vbPrevMatched.data(), windowSize, mfNNratio, mbCheckOrientation ? 1 : 0,
+                                            vnMatches12.data(), &n));
+        return n;
     }
 
     // Refined matching with a pose guess for F2 (src/ORBmatcher.cc:519-594): matches2 starts as F2's own map points

@@ -179,6 +179,13 @@ enum { ORB_ACCEPT_BEST = 0, ORB_ACCEPT_RATIO = 1, ORB_ACCEPT_LEVEL_RATIO = 2 };
 int orb_search_window(orb_ctx*, const orb_frame_view* target, const orb_window_query_set* queries, int accept_mode,
                       float nnratio, int th_dist, int check_ori, int32_t* match_target, int* nmatches);
 
+/* ORBmatcher::SearchForInitialization(Frame &F1, Frame &F2, vector<cv::Point2f> &vbPrevMatched, vector<int> &vnMatches12,
+ * int windowSize), src/ORBmatcher.cc:598-713 (monocular initialisation, src/Tracking.cc:393-401).  Octave-0 features of F1
+ * search a window around prev_matched[i] in F2; a closer later feature steals an earlier one's match (:637,:656-660).
+ * prev_matched: n1 x 2 floats in/out; matches12[n1] out = F2 index or -1.  f1 needs kps/desc only, f2 also its grid. */
+int orb_search_for_initialization(orb_ctx*, const orb_frame_view* f1, const orb_frame_view* f2, float* prev_matched, int window_size,
+                                  float nnratio, int check_ori, int32_t* matches12, int* nmatches);
+
 /* DBoW2::FeatureVector as CSR (Thirdparty/DBoW2/DBoW2/FeatureVector.cpp:31-45): node ids ascending,
  * per node the feature indices in insertion order. */
 typedef struct orb_featvec_view {

@@ -1037,6 +1037,56 @@ int orc_search_by_projection_kf(const orc_frame* cur, int nmp, const uint8_t* ac
     return nmatches;
 }
 
+/* ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:598-713 */
+int orc_search_for_initialization(const orc_frame* f1, const orc_frame* f2, float* prev, int windowSize, float nnratio,
+                                  int check_ori, int32_t* vnMatches12)
+{
+    const int HISTO_LENGTH = 30, TH_LOW = 50;
+    int nmatches = 0;
+    for (int i = 0; i < f1->n; i++) vnMatches12[i] = -1;
+    std::vector<int> rotHist[30];
+    std::vector<int> vMatchedDistance(f2->n > 0 ? f2->n : 1, INT_MAX), vnMatches21(f2->n > 0 ? f2->n : 1, -1);
+    std::vector<int32_t> cand(f2->n > 0 ? f2->n : 1);
+    for (int i1 = 0; i1 < f1->n; i1++) {
+        const int level1 = f1->kps[i1].octave;
+        if (level1 > 0) continue;
+        int nc = orc_features_in_area(f2, prev[2 * i1], prev[2 * i1 + 1], (float)windowSize, level1, level1, cand.data(), f2->n);
+        if (nc == 0) continue;
+        const uint8_t* d1 = f1->desc + (size_t)i1 * 32;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int k = 0; k < nc; k++) {
+            const int i2 = cand[k];
+            const int dist = orc_descriptor_distance(d1, f2->desc + (size_t)i2 * 32);
+            if (vMatchedDistance[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW) {
+            if (bestDist < (float)bestDist2 * nnratio) {
+                if (vnMatches21[bestIdx2] >= 0) { vnMatches12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+                vnMatches12[i1] = bestIdx2;
+                vnMatches21[bestIdx2] = i1;
+                vMatchedDistance[bestIdx2] = bestDist;
+                nmatches++;
+                if (check_ori) rotHist[rot_bin(f1->kps[i1].angle, f2->kps[bestIdx2].angle)].push_back(i1);
+            }
+        }
+    }
+    if (check_ori) {
+        int hs[30], a, b, c;
+        for (int i = 0; i < HISTO_LENGTH; i++) hs[i] = (int)rotHist[i].size();
+        orc_three_maxima(hs, HISTO_LENGTH, &a, &b, &c);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == a || i == b || i == c) continue;
+            for (int idx1 : rotHist[i])
+                if (vnMatches12[idx1] >= 0) { vnMatches12[idx1] = -1; nmatches--; }
+        }
+    }
+    for (int i1 = 0; i1 < f1->n; i1++)
+        if (vnMatches12[i1] >= 0) { prev[2 * i1] = f2->kps[vnMatches12[i1]].x; prev[2 * i1 + 1] = f2->kps[vnMatches12[i1]].y; }
+    return nmatches;
+}
+
 /* ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...), src/ORBmatcher.cc:715-850 */
 int orc_search_by_bow_kf(const orc_featvec* fv1, const uint8_t* desc1, const orc_keypoint* kps1, const uint8_t* valid1, int n1,
                          const orc_featvec* fv2, const uint8_t* desc2, const orc_keypoint* kps2, const uint8_t* valid2, int n2,

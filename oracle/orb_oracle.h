@@ -137,6 +137,11 @@ int   orc_search_by_projection_kf(const orc_frame* cur, int nmp, const uint8_t* 
                                   const int32_t* pred_level, const uint8_t* mp_desc, const float* kf_angle, float th, int orb_dist,
                                   int check_ori, int32_t* match_cur);
 
+/* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize), src/ORBmatcher.cc:598-713.
+ * prev_matched: n1 x 2 floats in/out (vbPrevMatched); matches12[n1] out. */
+int   orc_search_for_initialization(const orc_frame* f1, const orc_frame* f2, float* prev_matched, int window, float nnratio,
+                                    int check_ori, int32_t* matches12);
+
 /* ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*>&), src/ORBmatcher.cc:715-850.
  * valid1/valid2: feature has a live map point.  match12[idx1] out = idx2 or -1. */
 int   orc_search_by_bow_kf(const orc_featvec* fv1, const uint8_t* desc1, const orc_keypoint* kps1, const uint8_t* valid1, int n1,

@@ -92,6 +92,7 @@ def lib():
                                            C.POINTER(_FeatVec), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                            C.c_float, C.c_int, C.c_void_p]
         L.orc_search_by_projection_kf.argtypes = [C.POINTER(_Frame), C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_int, C.c_int, C.c_void_p]
+        L.orc_search_for_initialization.argtypes = [C.POINTER(_Frame), C.POINTER(_Frame), C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
         L.orc_three_maxima.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 3
         _lib = L
     return _lib
@@ -378,3 +379,10 @@ def search_by_projection_kf(cur, active, xyz, Tcw, pred_level, mp_desc, kf_angle
          np.ascontiguousarray(pred_level, np.int32), np.ascontiguousarray(mp_desc, np.uint8), np.ascontiguousarray(kf_angle, np.float32)]
     n = lib().orc_search_by_projection_kf(C.byref(cur.c), len(a[0]), *[_p(x) for x in a], th, orb_dist, int(check_ori), _p(match_cur))
     return n, match_cur
+
+
+def search_for_initialization(f1, f2, prev_matched, window, nnratio, check_ori=True):
+    prev = np.ascontiguousarray(prev_matched, np.float32).copy()
+    m = np.full(f1.n, -1, np.int32)
+    n = lib().orc_search_for_initialization(C.byref(f1.c), C.byref(f2.c), _p(prev), window, nnratio, int(check_ori), _p(m))
+    return n, m, prev

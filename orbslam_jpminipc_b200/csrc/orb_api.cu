@@ -676,6 +676,57 @@ int orb_search_window(orb_ctx* c, const orb_frame_view* target, const orb_window
     return res[1] ? ORB_ERR_CAPACITY : ORB_OK;
 }
 
+int orb_search_for_initialization(orb_ctx* c, const orb_frame_view* f1, const orb_frame_view* f2, float* prev_matched, int window_size,
+                                  float nnratio, int check_ori, int32_t* matches12, int* nmatches)
+{
+    if (!c || !f1 || !f2 || !nmatches || f1->n < 0 || f2->n < 0) return ORB_ERR_INVALID;
+    *nmatches = 0;
+    if (f1->n == 0) return ORB_OK;
+    if (!matches12 || !prev_matched || !f1->kps || !f1->desc) return ORB_ERR_INVALID;
+    ORB_CUDA(cudaSetDevice(c->device));
+    const bool dev = is_device_ptr(f1->kps);
+    if (is_device_ptr(matches12) != dev || is_device_ptr(prev_matched) != dev) return ORB_ERR_INVALID;
+    cudaStream_t s = c->streams[0];
+    if (f2->n == 0) {                                       // no candidates anywhere: vnMatches12 = -1 (:601), prev untouched
+        if (dev) ORB_CUDA(cudaMemsetAsync(matches12, 0xff, (size_t)f1->n * 4, s)); else for (int i = 0; i < f1->n; i++) matches12[i] = -1;
+        if (dev) ORB_CUDA(cudaStreamSynchronize(s));
+        return ORB_OK;
+    }
+    if (!f2->kps || !f2->desc || !f2->cell_start || !f2->cell_items || is_device_ptr(f2->kps) != dev ||
+        f2->max_x <= f2->min_x || f2->max_y <= f2->min_y) return ORB_ERR_INVALID;
+    const size_t n1 = (size_t)f1->n;
+    const size_t work = orb_init_scratch_bytes(f1->n, f2->n);
+    const size_t in_bytes = dev ? 0 : frame_view_bytes(f2) + al256(n1 * 28) + al256(n1 * 32) + al256(n1 * 8) + al256(n1 * 4);
+    int rc = match_scratch(c, 256 + in_bytes + work, 256 + in_bytes + 4096);
+    if (rc) return rc;
+    Bump b(c->d_match_scratch, c->h_match_arena, c->match_scratch_bytes);
+    int* d_result = (int*)b.take(8);
+    orb_frame_view d1 = *f1, d2 = *f2;
+    if ((rc = stage_frame(b, dev, d2, true, s))) return rc;
+    if ((rc = stage_in(b, dev, d1.kps, n1, s)) || (rc = stage_in(b, dev, d1.desc, n1 * 32, s))) return rc;
+    float* d_prev = prev_matched;
+    int32_t* d_m12 = matches12;
+    if (!dev) {
+        const float* p = prev_matched;
+        if ((rc = stage_in(b, false, p, n1 * 2, s))) return rc;
+        d_prev = (float*)p;
+        d_m12 = (int32_t*)b.take(n1 * 4);
+    }
+    uint8_t* wk = (uint8_t*)b.take(work);
+    if ((rc = b.flush(s))) return rc;
+    rc = orb_launch_search_for_initialization(c, &d1, &d2, d_prev, window_size, nnratio, check_ori, d_m12, d_result, wk, work, s);
+    if (rc) return rc;
+    int res[2] = { 0, 0 };
+    if (!dev) {
+        ORB_CUDA(cudaMemcpyAsync(matches12, d_m12, n1 * 4, cudaMemcpyDeviceToHost, s));
+        ORB_CUDA(cudaMemcpyAsync(prev_matched, d_prev, n1 * 8, cudaMemcpyDeviceToHost, s));
+    }
+    ORB_CUDA(cudaMemcpyAsync(res, d_result, sizeof res, cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaStreamSynchronize(s));
+    *nmatches = res[0];
+    return res[1] ? ORB_ERR_CAPACITY : ORB_OK;
+}
+
 } // extern "C"
 
 // shared body of SearchByBoW(KF, Frame) and SearchByBoW(KF, KF): the latter adds the validity of the second side's map

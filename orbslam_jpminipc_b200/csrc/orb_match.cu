@@ -610,6 +610,122 @@ k_win_resolve(WinArgs A, int32_t* __restrict__ match, int8_t* __restrict__ bin_o
     if (tid == 0) { result[0] = s_cnt; result[1] = s_err; }
 }
 
+// ------------------------------------------------------------------ SearchForInitialization (:598-713)
+// Here a later query may STEAL a keypoint: candidate c is skipped by query i only if an earlier query took it with a
+// distance <= dist(i,c) (vMatchedDistance, :637), so
+//     blocked(i,c)  <=>  exists j < i with choice[j] == c and dist(j,c) <= dist(i,c)
+// still only looks at lower indices and the same fixed-point iteration applies.  Accepted distances are <= TH_LOW, so per
+// keypoint a 51-entry table "lowest query index that chose me with distance <= d" answers the test in one load; it is
+// rebuilt every round for the keypoints that have choosers.  The last taker (highest index) keeps the match; the rotation
+// histogram counts every acceptance, stolen ones included, exactly like the reference's rotHist (:666-676,:688-703).
+constexpr int INIT_TAB = TH_LOW + 2;       // 52 ints per F2 keypoint (entries 0..50 used)
+
+__global__ void __launch_bounds__(1024)
+k_init_resolve(WinArgs A, int32_t* __restrict__ matches12, float* __restrict__ prev_matched, int* __restrict__ tab /* n2 x INIT_TAB */,
+               int* __restrict__ has /* n2 */, int* __restrict__ choice, int* __restrict__ cdist, int* __restrict__ result)
+{
+    __shared__ int hist[HISTO_LENGTH];
+    __shared__ int s_changed, s_err, s_cnt;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int n1 = A.nq, n2 = A.tgt.n;
+    if (tid < HISTO_LENGTH) hist[tid] = 0;
+    if (tid == 0) { s_err = 0; s_cnt = 0; }
+    for (int i = tid; i < n1; i += nt) { choice[i] = -1; cdist[i] = INT_MAX; }
+    for (int k = tid; k < n2; k += nt) has[k] = 0;
+    for (size_t k = tid; k < (size_t)n2 * INIT_TAB; k += nt) tab[k] = INT_MAX;
+    __syncthreads();
+    for (int round = 0; round <= n1; round++) {
+        if (tid == 0) s_changed = 0;
+        // (1) wipe the tables of last round's chosen keypoints (a warp per keypoint)
+        for (int k = warp; k < n2; k += nwarps) {
+            if (!has[k]) continue;
+            for (int d = lane; d < INIT_TAB; d += 32) tab[(size_t)k * INIT_TAB + d] = INT_MAX;
+            if (lane == 0) has[k] = 0;
+        }
+        __syncthreads();
+        // (2) lowest chooser index per (keypoint, exact distance)
+        for (int i = tid; i < n1; i += nt) {
+            const int c = choice[i];
+            if (c < 0) continue;
+            atomicMin(&tab[(size_t)c * INIT_TAB + cdist[i]], i);
+            has[c] = 1;
+        }
+        __syncthreads();
+        // (3) running minimum over the distance axis: tab[c][d] = lowest index that chose c with distance <= d
+        for (int k = warp; k < n2; k += nwarps) {
+            if (!has[k]) continue;
+            int* T = tab + (size_t)k * INIT_TAB;
+            int v0 = T[lane], v1 = lane + 32 < INIT_TAB ? T[lane + 32] : INT_MAX;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t0 = __shfl_up_sync(0xffffffffu, v0, o), t1 = __shfl_up_sync(0xffffffffu, v1, o);
+                if (lane >= o) { v0 = min(v0, t0); v1 = min(v1, t1); }
+            }
+            v1 = min(v1, __shfl_sync(0xffffffffu, v0, 31));
+            T[lane] = v0;
+            if (lane + 32 < INIT_TAB) T[lane + 32] = v1;
+        }
+        __syncthreads();
+        // (4) every query rescans its candidate list against the tables
+        for (int i = tid; i < n1; i += nt) {
+            const int n = A.cnt[i];
+            if (n <= 0) continue;
+            if (n > A.cap) { s_err = 1; continue; }
+            const uint32_t* L = A.list + (size_t)i * A.cap;
+            int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx = -1;
+            for (int p = 0; p < n; p++) {
+                const uint32_t e = L[p];
+                const int id = (int)(e & 0x3fffff), dist = (int)(e >> 22);
+                if (has[id] && tab[(size_t)id * INIT_TAB + min(dist, TH_LOW)] < i) continue;      // vMatchedDistance[i2] <= dist (:637)
+                if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx = id; }
+                else if (dist < bestDist2) bestDist2 = dist;
+            }
+            const bool ok = bestIdx >= 0 && bestDist <= TH_LOW && (float)bestDist < __fmul_rn((float)bestDist2, A.nnratio);   // :652-654
+            const int c = ok ? bestIdx : -1;
+            if (c != choice[i]) { choice[i] = c; s_changed = 1; }
+            cdist[i] = ok ? bestDist : INT_MAX;
+        }
+        __syncthreads();
+        const int ch = s_changed;
+        __syncthreads();
+        if (!ch) break;
+    }
+    // converged: the highest index among a keypoint's takers keeps it (:656-662); has[] is reused as vnMatches21
+    for (int k = tid; k < n2; k += nt) has[k] = -1;
+    for (int i = tid; i < n1; i += nt) matches12[i] = -1;
+    __syncthreads();
+    for (int i = tid; i < n1; i += nt) {
+        const int c = choice[i];
+        if (c < 0) continue;
+        atomicMax(&has[c], i);
+        if (A.histogram) atomicAdd(&hist[rot_bin(A.qangle[i], A.tgt.kps[c].angle)], 1);
+    }
+    __syncthreads();
+    int mine = 0;
+    for (int k = tid; k < n2; k += nt)
+        if (has[k] >= 0) { matches12[has[k]] = k; mine++; }
+    atomicAdd(&s_cnt, mine);
+    __syncthreads();
+    if (A.histogram) {
+        int i1, i2, i3;
+        three_maxima(hist, i1, i2, i3);
+        int removed = 0;
+        for (int i = tid; i < n1; i += nt) {
+            const int c = choice[i];
+            if (c < 0) continue;
+            const int b = rot_bin(A.qangle[i], A.tgt.kps[c].angle);
+            if (b != i1 && b != i2 && b != i3 && matches12[i] >= 0) { matches12[i] = -1; removed++; }
+        }
+        atomicSub(&s_cnt, removed);
+        __syncthreads();
+    }
+    for (int i = tid; i < n1; i += nt) {                       // update prev matched (:707-710)
+        const int c = matches12[i];
+        if (c >= 0) { prev_matched[2 * i] = A.tgt.kps[c].x; prev_matched[2 * i + 1] = A.tgt.kps[c].y; }
+    }
+    if (tid == 0) { result[0] = s_cnt; result[1] = s_err; }
+}
+
 // ------------------------------------------------------------------ K9: SearchByBoW scoring
 struct BowArgs {
     orb_featvec_view kf, f;
@@ -904,6 +1020,56 @@ int orb_launch_search_window(orb_ctx* c, const orb_frame_view* tgt, const orb_wi
     if (A.cap < 1) return ORB_ERR_CAPACITY;
     k_win_candidates<<<(q->n * 32 + 255) / 256, 256, 0, s>>>(A);
     k_win_resolve<<<1, 1024, 0, s>>>(A, match, bin_of, owner, choice, d_result);
+    ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
+}
+
+size_t orb_init_scratch_bytes(int n1, int n2)
+{
+    const size_t cap = (size_t)std::min(n2, 1024);
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    return al((size_t)n1 * 4) * 7 + al((size_t)n1) + al((size_t)n2 * 4) + al((size_t)n2 * INIT_TAB * 4) + (size_t)n1 * cap * 4 + 1024;
+}
+
+// window centres = vbPrevMatched, level range [0,0], only octave-0 features of F1 search (:613-618)
+__global__ void k_init_prepare(const orb_keypoint* __restrict__ kps1, const float* __restrict__ prev, int n1, float* __restrict__ u,
+                               float* __restrict__ v, int32_t* __restrict__ lv, uint8_t* __restrict__ active, float* __restrict__ angle)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1) return;
+    const orb_keypoint kp = kps1[i];
+    u[i] = prev[2 * i]; v[i] = prev[2 * i + 1]; lv[i] = 0; active[i] = kp.octave <= 0; angle[i] = kp.angle;
+}
+
+int orb_launch_search_for_initialization(orb_ctx* c, const orb_frame_view* f1, const orb_frame_view* f2, float* d_prev, int window,
+                                         float nnratio, int check_ori, int32_t* d_matches12, int* d_result, uint8_t* scratch,
+                                         size_t scratch_bytes, cudaStream_t s)
+{
+    (void)c;
+    if (f2->n >= (1 << 22)) return ORB_ERR_CAPACITY;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t n1 = (size_t)f1->n, n2 = (size_t)f2->n;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { uint8_t* p = scratch + off; off += al(bytes); return p; };
+    float* d_u = (float*)take(n1 * 4); float* d_v = (float*)take(n1 * 4); float* d_angle = (float*)take(n1 * 4);
+    int32_t* d_lv = (int32_t*)take(n1 * 4); uint8_t* d_active = take(n1);
+    WinArgs A;
+    A.tgt = *f2; A.nq = f1->n; A.active = d_active; A.qdesc = f1->desc; A.u = d_u; A.v = d_v; A.xyz = nullptr; A.project = 0;
+    for (int i = 0; i < 16; i++) A.T[i] = 0.f;
+    A.check_bounds = 0; A.radius = nullptr; A.radius_const = (float)window; A.minl = d_lv; A.maxl = d_lv; A.qangle = d_angle;
+    A.accept = 0; A.nnratio = nnratio; A.th_dist = TH_LOW; A.histogram = check_ori;
+    A.cnt = (int*)take(n1 * 4);
+    int* choice = (int*)take(n1 * 4);
+    int* cdist = (int*)take(n1 * 4);
+    int* has = (int*)take(n2 * 4);
+    int* tab = (int*)take(n2 * INIT_TAB * 4);
+    const size_t avail = scratch_bytes > off ? (scratch_bytes - off) / 4 : 0;
+    A.cap = (int)std::min<size_t>(n2, n1 ? avail / n1 : 0);
+    A.list = (uint32_t*)(scratch + off);
+    if (A.cap < 1) return ORB_ERR_CAPACITY;
+    k_init_prepare<<<(f1->n + 255) / 256, 256, 0, s>>>(f1->kps, d_prev, f1->n, d_u, d_v, d_lv, d_active, d_angle);
+    k_win_candidates<<<(f1->n * 32 + 255) / 256, 256, 0, s>>>(A);
+    k_init_resolve<<<1, 1024, 0, s>>>(A, d_matches12, d_prev, tab, has, choice, cdist, d_result);
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;
 }

@@ -143,6 +143,19 @@ class ORBmatcher:
         return self._search_window(F2, F1.N, f1_active, F1.desc, None, None, f1_xyz, Tc2w, 0, None, float(windowSize), lv, lv, None,
                                    self.ACCEPT_RATIO, self.TH_HIGH, False, match2)
 
+    def SearchForInitialization(self, F1, F2, vbPrevMatched, windowSize=10):
+        """ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:598-713).  vbPrevMatched: n1 x 2 float32 window centres.
+        Returns (nmatches, vnMatches12, updated vbPrevMatched)."""
+        prev = np.ascontiguousarray(vbPrevMatched, np.float32).reshape(-1, 2).copy()
+        if len(prev) != F1.N:
+            raise ValueError("vbPrevMatched must hold one point per F1 keypoint")
+        m12 = np.full(F1.N, -1, np.int32)
+        n = C.c_int(0)
+        v1, v2 = F1.view(), F2.view()
+        check(lib().orb_search_for_initialization(self._h, C.byref(v1), C.byref(v2), ptr(prev), int(windowSize), self.mfNNratio,
+                                                  int(self.mbCheckOrientation), ptr(m12), C.byref(n)), "orb_search_for_initialization")
+        return n.value, m12, prev
+
     def SearchByProjectionKeyFrame(self, CurrentFrame, active, xyz, Tcw, pred_level, mp_desc, kf_angle, th, ORBdist, match_cur=None):
         """ORBmatcher::SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1622-1746).
         active: KF map point live and not in sAlreadyFound; pred_level: the level predicted from dist3D/minDistance

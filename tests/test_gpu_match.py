@@ -345,3 +345,63 @@ def test_search_by_projection_keyframe_vs_oracle(pkg, po, shape, nf, th, dist, o
     rn, rmatch = po.search_by_projection_kf(ocur, has, xyz, T, pred, glast.desc, glast.kps["angle"], th, dist, ori, match_cur=pre.copy())
     assert rn > 10
     assert nm == rn and np.array_equal(match, rmatch)
+
+
+@pytest.mark.parametrize("shape,nf,win,ori", [((240, 320), 500, 30, True), ((480, 752), 1000, 100, True), ((376, 1241), 2000, 100, False)])
+def test_search_for_initialization_vs_oracle(pkg, po, shape, nf, win, ori):
+    """ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:598-713 (call site src/Tracking.cc:393-401: vbPrevMatched
+    starts as the first frame's own keypoint positions)."""
+    m = pkg.ORBmatcher(0.9, ori)
+    gcur, glast, ocur, olast, has, outl, xyz, T = _scene(po, pkg, m, shape[0], shape[1], nf, 8400 + nf, 15.0)
+    prev = np.stack([glast.kps["x"], glast.kps["y"]], 1).astype(np.float32)
+    nm, m12, pnew = m.SearchForInitialization(glast, gcur, prev, win)
+    rn, rm12, rprev = po.search_for_initialization(olast, ocur, prev, win, 0.9, ori)
+    assert rn > 10
+    assert nm == rn and np.array_equal(m12, rm12) and np.array_equal(pnew, rprev)
+    # second call with the updated centres, as the initializer does frame after frame
+    nm2, m12b, pnew2 = m.SearchForInitialization(glast, gcur, pnew, win)
+    rn2, rm12b, rprev2 = po.search_for_initialization(olast, ocur, rprev, win, 0.9, ori)
+    assert nm2 == rn2 and np.array_equal(m12b, rm12b) and np.array_equal(pnew2, rprev2)
+
+
+@pytest.mark.parametrize("n1,n2,seed", [(600, 40, 1), (2000, 150, 2), (64, 64, 3)])
+def test_search_for_initialization_steal_chains(pkg, po, n1, n2, seed):
+    """Many F1 features compete for few F2 keypoints with ever closer descriptors, so matches are stolen repeatedly
+    (src/ORBmatcher.cc:637,:656-660)."""
+    rng = np.random.default_rng(seed)
+    m = pkg.ORBmatcher(0.9, True)
+    k2 = np.zeros(n2, pkg.KP_DTYPE)
+    k2["x"] = rng.uniform(100, 200, n2).astype(np.float32); k2["y"] = rng.uniform(100, 200, n2).astype(np.float32)
+    k2["angle"] = rng.uniform(0, 360, n2).astype(np.float32); k2["size"] = 31; k2["octave"] = rng.integers(0, 2, n2)
+    d2 = rng.integers(0, 256, (n2, 32), dtype=np.uint8)
+    src = rng.integers(0, n2, n1)
+    d1 = d2[src].copy()
+    bits = np.unpackbits(d1, axis=1)
+    for i in range(n1):                                    # later queries tend to be closer: long steal chains
+        nflip = int(rng.integers(0, 60))
+        bits[i, rng.choice(256, nflip, replace=False)] ^= 1
+    d1 = np.packbits(bits, axis=1)
+    k1 = np.zeros(n1, pkg.KP_DTYPE)
+    k1["x"] = rng.uniform(100, 200, n1).astype(np.float32); k1["y"] = rng.uniform(100, 200, n1).astype(np.float32)
+    k1["angle"] = (k2["angle"][src] + rng.choice([0.0] * 6 + [45.0, 90.0, 135.0, 180.0, 270.0], n1)).astype(np.float32) % np.float32(360)
+    k1["size"] = 31; k1["octave"] = (rng.random(n1) < 0.1).astype(np.int32)
+    F1 = pkg.Frame(m, k1, d1, 320, 240, 300.0, 300.0, 160.0, 120.0); F2 = pkg.Frame(m, k2, d2, 320, 240, 300.0, 300.0, 160.0, 120.0)
+    O1 = po.OracleFrame(k1, d1, 320, 240, 300.0, 300.0, 160.0, 120.0); O2 = po.OracleFrame(k2, d2, 320, 240, 300.0, 300.0, 160.0, 120.0)
+    prev = np.stack([k1["x"], k1["y"]], 1)
+    nm, m12, pnew = m.SearchForInitialization(F1, F2, prev, 120)
+    rn, rm12, rprev = po.search_for_initialization(O1, O2, prev, 120, 0.9, True)
+    assert rn > 5
+    assert nm == rn and np.array_equal(m12, rm12) and np.array_equal(pnew, rprev)
+
+
+def test_search_for_initialization_empty(pkg):
+    m = pkg.ORBmatcher(0.9, True)
+    k = np.zeros(0, pkg.KP_DTYPE); d = np.zeros((0, 32), np.uint8)
+    E = pkg.Frame(m, k, d, 320, 240, 300.0, 300.0, 160.0, 120.0)
+    rng = np.random.default_rng(0)
+    k1 = np.zeros(10, pkg.KP_DTYPE); k1["x"] = 50; k1["y"] = 60
+    F = pkg.Frame(m, k1, rng.integers(0, 256, (10, 32), dtype=np.uint8), 320, 240, 300.0, 300.0, 160.0, 120.0)
+    n, m12, _ = m.SearchForInitialization(F, E, np.zeros((10, 2), np.float32), 50)
+    assert n == 0 and (m12 == -1).all()
+    n, m12, _ = m.SearchForInitialization(E, F, np.zeros((0, 2), np.float32), 50)
+    assert n == 0 and len(m12) == 0
