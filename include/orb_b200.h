@@ -210,6 +210,38 @@ int orb_search_by_bow_kf(orb_ctx*, const orb_featvec_view* fv1, const uint8_t* d
                          const uint8_t* valid2, int n2,
                          float nnratio, int check_ori, int32_t* match12, int* nmatches);
 
+/* ---- DBoW2 vocabulary tree (ORB descriptors): Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h ----
+ * Nodes are given in the order of the reference's text format (loadFromTextFile, :1338-1425): node 0 is the root, node i >= 1
+ * has parent[i] < i, a 32-byte descriptor and a weight; children keep file order, nodes without children are the words and get
+ * word ids in node order (:328, :1408-1414).  scoring / weighting are DBoW2's ScoringType / WeightingType (BowVector.h:36-53);
+ * Data/ORBvoc.txt of the reference is k=10, L=6, L1_NORM, TF_IDF. */
+typedef struct orb_vocab orb_vocab;
+enum { ORB_L1_NORM = 0, ORB_L2_NORM, ORB_CHI_SQUARE, ORB_KL, ORB_BHATTACHARYYA, ORB_DOT_PRODUCT };
+enum { ORB_TF_IDF = 0, ORB_TF, ORB_IDF, ORB_BINARY };
+int  orb_vocab_create(orb_ctx*, int k, int L, int scoring, int weighting, int nnodes, const int32_t* parent, const uint8_t* desc,
+                      const double* weight, orb_vocab** out);
+/* ORBVocabulary::loadFromTextFile(strVocFile), src/main.cc:85-97 */
+int  orb_vocab_load_text(orb_ctx*, const char* path, orb_vocab** out);
+void orb_vocab_destroy(orb_vocab*);
+int  orb_vocab_info(const orb_vocab*, int* k, int* L, int* nnodes, int* nwords);
+/* transform(feature, word_id, weight, nid, levelsup) for n features, :1218-1260.  All pointers host or all device. */
+int  orb_vocab_transform_features(orb_ctx*, orb_vocab*, const uint8_t* desc, int n, int levelsup, int32_t* word, double* weight,
+                                  int32_t* node);
+/* transform(features, BowVector&, FeatureVector&, levelsup), :1127-1193, as called by Frame::ComputeBoW (src/Frame.cc:279-287) and
+ * KeyFrame::ComputeBoW (src/KeyFrame.cc:56-65), for nframes frames in one launch.  Frame f has counts[f] descriptors starting at row
+ * f*slot_rows of desc (the layout orb_extract_batch writes).  Outputs use fixed slots of cap entries per frame (cap >= slot_rows,
+ * <= 8192): BowVector = bow_word (ascending) / bow_val with nbow[f] entries; FeatureVector = CSR fv_node (ascending) / fv_start
+ * (cap+1 per frame) / fv_items with nfv[f] nodes.  All pointers host or all device. */
+int  orb_vocab_transform_batch(orb_ctx*, orb_vocab*, const uint8_t* desc, int slot_rows, const int32_t* counts, int nframes, int levelsup,
+                               int cap, int32_t* bow_word, double* bow_val, int32_t* nbow, int32_t* fv_node, int32_t* fv_start,
+                               int32_t* fv_items, int32_t* nfv);
+/* Shared-word count and L1 score (ScoringObject.cpp:22-64) of a query BowVector against nkf keyframe BowVectors stored as CSR: the
+ * loops of KeyFrameDatabase::DetectRelocalisationCandidates (src/KeyFrameDatabase.cc:198-252) / DetectLoopCandidates (:75-135)
+ * without the list and covisibility bookkeeping.  common[k] = shared words; score[k] = (float)score for keyframes with more than
+ * (int)(max_common*0.8f) shared words (all keyframes sharing a word if score_all), else 0. */
+int  orb_bow_score_db(orb_ctx*, orb_vocab*, const int32_t* qword, const double* qval, int nq, int nkf, const int32_t* kf_start,
+                      const int32_t* kf_word, const double* kf_val, int score_all, int32_t* common, float* score, int* max_common);
+
 /* pinned host memory helpers (page-locked buffers make the host<->device copies asynchronous) */
 void* orb_host_alloc(size_t bytes);
 void  orb_host_free(void* p);

@@ -1137,4 +1137,180 @@ int orc_search_by_bow_kf(const orc_featvec* fv1, const uint8_t* desc1, const orc
     return nmatches;
 }
 
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * DBoW2 vocabulary: Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h, BowVector.cpp, FeatureVector.cpp, ScoringObject.cpp.
+ * The vocabulary file of the reference (Data/ORBvoc.txt, k=10 L=6 L1_NORM TF_IDF) is not in the repository; tests use
+ * synthetic trees in the same text format.
+ * ------------------------------------------------------------------------------------------------------------------ */
+} // extern "C"
+#include <map>
+#include <cstdio>
+#include <cstdlib>
+struct orc_vocab {
+    int k, L, scoring, weighting;
+    std::vector<std::vector<int>> children;      /* m_nodes[i].children */
+    std::vector<uint8_t> desc;                   /* nnodes x 32 */
+    std::vector<double> weight;
+    std::vector<int> word_id;                    /* -1 for inner nodes */
+    int nwords;
+};
+static void vocab_finish(orc_vocab* v)
+{
+    const int n = (int)v->children.size();
+    v->word_id.assign(n, -1);
+    v->nwords = 0;
+    for (int i = 1; i < n; i++)                  /* :1408-1414: leaves get word ids in node order */
+        if (v->children[i].empty()) v->word_id[i] = v->nwords++;
+}
+extern "C" {
+
+orc_vocab* orc_vocab_create(int k, int L, int scoring, int weighting, int nnodes, const int32_t* parent, const uint8_t* desc,
+                            const double* weight)
+{
+    if (nnodes < 1) return nullptr;
+    for (int i = 1; i < nnodes; i++) if (parent[i] < 0 || parent[i] >= i) return nullptr;   /* a parent precedes its children in the file */
+    orc_vocab* v = new orc_vocab;
+    v->k = k; v->L = L; v->scoring = scoring; v->weighting = weighting;
+    v->children.resize(nnodes);
+    v->desc.assign(desc, desc + (size_t)nnodes * 32);
+    v->weight.assign(weight, weight + nnodes);
+    for (int i = 1; i < nnodes; i++) v->children[parent[i]].push_back(i);
+    vocab_finish(v);
+    return v;
+}
+
+orc_vocab* orc_vocab_load_text(const char* path)
+{
+    FILE* f = fopen(path, "r");              /* C stdio: this library may carry a static libstdc++, keep iostreams out of it */
+    if (!f) return nullptr;
+    std::vector<char> line(1 << 16);
+    if (!fgets(line.data(), (int)line.size(), f)) { fclose(f); return nullptr; }
+    int k = 0, L = 0, n1 = -1, n2 = -1;
+    sscanf(line.data(), "%d %d %d %d", &k, &L, &n1, &n2);
+    if (k < 0 || k > 20 || L < 1 || L > 10 || n1 < 0 || n1 > 5 || n2 < 0 || n2 > 3) { fclose(f); return nullptr; }      /* :1358-1362 */
+    std::vector<int32_t> parent(1, 0);
+    std::vector<uint8_t> desc(32, 0);
+    std::vector<double> weight(1, 0.0);
+    while (fgets(line.data(), (int)line.size(), f)) {
+        const char* p = line.data();
+        char* end = nullptr;
+        const long pid = strtol(p, &end, 10);
+        if (end == p) continue;              /* blank trailing line (the reference would read garbage here) */
+        p = end;
+        strtol(p, &end, 10);                 /* nIsLeaf */
+        p = end;
+        parent.push_back((int32_t)pid);
+        for (int i = 0; i < 32; i++) { const long b = strtol(p, &end, 10); desc.push_back((uint8_t)b); p = end; }
+        weight.push_back(strtod(p, &end));
+    }
+    fclose(f);
+    return orc_vocab_create(k, L, n1, n2, (int)parent.size(), parent.data(), desc.data(), weight.data());
+}
+
+void orc_vocab_destroy(orc_vocab* v) { delete v; }
+int orc_vocab_nnodes(const orc_vocab* v) { return (int)v->children.size(); }
+int orc_vocab_nwords(const orc_vocab* v) { return v->nwords; }
+
+/* :1218-1260.  Where the reference leaves *nid unset (a leaf above level L-levelsup) the leaf itself is reported. */
+void orc_vocab_transform_feature(const orc_vocab* v, const uint8_t* d, int levelsup, int32_t* word, double* weight, int32_t* node)
+{
+    const int nid_level = v->L - levelsup;
+    int nid = -1;
+    if (nid_level <= 0) nid = 0;
+    int final_id = 0, current_level = 0;
+    if (v->children[0].empty()) { *word = -1; *weight = 0; *node = 0; return; }
+    do {
+        ++current_level;
+        const std::vector<int>& nodes = v->children[final_id];
+        final_id = nodes[0];
+        double best_d = orc_descriptor_distance(d, &v->desc[(size_t)final_id * 32]);
+        for (size_t c = 1; c < nodes.size(); c++) {
+            const double dist = orc_descriptor_distance(d, &v->desc[(size_t)nodes[c] * 32]);
+            if (dist < best_d) { best_d = dist; final_id = nodes[c]; }
+        }
+        if (current_level == nid_level) nid = final_id;
+    } while (!v->children[final_id].empty());
+    *word = v->word_id[final_id];
+    *weight = v->weight[final_id];
+    *node = nid >= 0 ? nid : final_id;
+}
+
+/* :1127-1193 with BowVector::addWeight / addIfNotExist / normalize (BowVector.cpp:33-95), FeatureVector::addFeature (:31-45) */
+void orc_vocab_transform(const orc_vocab* v, const uint8_t* desc, int n, int levelsup, int32_t* bow_word, double* bow_val, int* nbow,
+                         int32_t* fv_node, int32_t* fv_start, int32_t* fv_items, int* nfv)
+{
+    std::map<unsigned, double> bow;
+    std::map<unsigned, std::vector<unsigned>> fv;
+    *nbow = 0; *nfv = 0; fv_start[0] = 0;
+    if (v->children[0].empty()) return;
+    const bool l2 = v->scoring == ORC_L2_NORM, must = v->scoring != ORC_DOT_PRODUCT;
+    const bool tf = v->weighting == ORC_TF || v->weighting == ORC_TF_IDF;
+    for (int i = 0; i < n; i++) {
+        int32_t id, nid; double w;
+        orc_vocab_transform_feature(v, desc + (size_t)i * 32, levelsup, &id, &w, &nid);
+        if (w > 0) {
+            auto it = bow.find((unsigned)id);
+            if (it == bow.end()) bow[(unsigned)id] = w;
+            else if (tf) it->second += w;
+            fv[(unsigned)nid].push_back((unsigned)i);
+        }
+    }
+    if (tf && !bow.empty() && !must) {
+        const double nd = (double)bow.size();
+        for (auto& e : bow) e.second /= nd;
+    }
+    if (must) {
+        double norm = 0.0;
+        if (!l2) { for (auto& e : bow) norm += fabs(e.second); }
+        else { for (auto& e : bow) norm += e.second * e.second; norm = sqrt(norm); }
+        if (norm > 0.0) for (auto& e : bow) e.second /= norm;
+    }
+    int c = 0;
+    for (auto& e : bow) { bow_word[c] = (int32_t)e.first; bow_val[c] = e.second; c++; }
+    *nbow = c;
+    int nn = 0, pos = 0;
+    for (auto& e : fv) {
+        fv_node[nn] = (int32_t)e.first;
+        for (unsigned idx : e.second) fv_items[pos++] = (int32_t)idx;
+        fv_start[++nn] = pos;
+    }
+    *nfv = nn;
+}
+
+/* ScoringObject.cpp:22-64 */
+double orc_bow_score_l1(const int32_t* w1, const double* v1, int n1, const int32_t* w2, const double* v2, int n2)
+{
+    int a = 0, b = 0;
+    double score = 0;
+    while (a < n1 && b < n2) {
+        if (w1[a] == w2[b]) { score += fabs(v1[a] - v2[b]) - fabs(v1[a]) - fabs(v2[b]); a++; b++; }
+        else if (w1[a] < w2[b]) a = (int)(std::lower_bound(w1 + a, w1 + n1, w2[b]) - w1);
+        else b = (int)(std::lower_bound(w2 + b, w2 + n2, w1[a]) - w2);
+    }
+    return -score / 2.0;
+}
+
+/* src/KeyFrameDatabase.cc:198-252 without the list / covisibility bookkeeping */
+void orc_bow_score_db(const int32_t* qw, const double* qv, int nq, int nkf, const int32_t* kf_start, const int32_t* kf_word,
+                      const double* kf_val, int32_t* common, float* score, int* max_common)
+{
+    int mx = 0;
+    for (int k = 0; k < nkf; k++) {
+        const int32_t* w = kf_word + kf_start[k];
+        const int n = kf_start[k + 1] - kf_start[k];
+        int c = 0, a = 0, b = 0;
+        while (a < nq && b < n) { if (qw[a] == w[b]) { c++; a++; b++; } else if (qw[a] < w[b]) a++; else b++; }
+        common[k] = c;
+        mx = std::max(mx, c);
+    }
+    const int min_common = (int)((float)mx * 0.8f);
+    for (int k = 0; k < nkf; k++) {
+        score[k] = 0.f;
+        if (common[k] > 0 && common[k] > min_common)
+            score[k] = (float)orc_bow_score_l1(qw, qv, nq, kf_word + kf_start[k], kf_val + kf_start[k], kf_start[k + 1] - kf_start[k]);
+    }
+    *max_common = mx;
+}
+
 } // extern "C"

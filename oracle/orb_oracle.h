@@ -148,6 +148,31 @@ int   orc_search_by_bow_kf(const orc_featvec* fv1, const uint8_t* desc1, const o
                            const orc_featvec* fv2, const uint8_t* desc2, const orc_keypoint* kps2, const uint8_t* valid2, int n2,
                            float nnratio, int check_ori, int32_t* match12);
 
+/* ---- DBoW2 vocabulary, Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h ---- */
+typedef struct orc_vocab orc_vocab;
+enum { ORC_L1_NORM = 0, ORC_L2_NORM, ORC_CHI_SQUARE, ORC_KL, ORC_BHATTACHARYYA, ORC_DOT_PRODUCT };   /* BowVector.h:45-53 */
+enum { ORC_TF_IDF = 0, ORC_TF, ORC_IDF, ORC_BINARY };                                                /* BowVector.h:36-42 */
+/* Nodes in text-file order (loadFromTextFile, TemplatedVocabulary.h:1338-1425): node 0 is the root, rows i>=1 give parent,
+ * 32-byte descriptor and weight; children keep file order; leaves (nodes without children, :328) get word ids in node order. */
+orc_vocab* orc_vocab_create(int k, int L, int scoring, int weighting, int nnodes, const int32_t* parent, const uint8_t* desc,
+                            const double* weight);
+orc_vocab* orc_vocab_load_text(const char* path);
+void  orc_vocab_destroy(orc_vocab*);
+int   orc_vocab_nnodes(const orc_vocab*);
+int   orc_vocab_nwords(const orc_vocab*);
+/* transform(feature, word_id, weight, nid, levelsup), TemplatedVocabulary.h:1218-1260 */
+void  orc_vocab_transform_feature(const orc_vocab*, const uint8_t* desc32, int levelsup, int32_t* word, double* weight, int32_t* node);
+/* transform(features, BowVector&, FeatureVector&, levelsup), :1127-1193.  BowVector as (word ascending, value); FeatureVector as
+ * CSR (fv_start has nfv+1 entries).  Capacities: n entries each (fv_start n+1). */
+void  orc_vocab_transform(const orc_vocab*, const uint8_t* desc, int n, int levelsup, int32_t* bow_word, double* bow_val, int* nbow,
+                          int32_t* fv_node, int32_t* fv_start, int32_t* fv_items, int* nfv);
+/* L1Scoring::score, ScoringObject.cpp:22-64 */
+double orc_bow_score_l1(const int32_t* w1, const double* v1, int n1, const int32_t* w2, const double* v2, int n2);
+/* the data-parallel part of KeyFrameDatabase::DetectRelocalisationCandidates, src/KeyFrameDatabase.cc:198-252: words shared with
+ * every keyframe (mnRelocWords), max, and the score of those with more than (int)(max*0.8f) shared words (others 0). */
+void  orc_bow_score_db(const int32_t* qw, const double* qv, int nq, int nkf, const int32_t* kf_start, const int32_t* kf_word,
+                       const double* kf_val, int32_t* common, float* score, int* max_common);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,18 @@ def lib():
                                            C.c_float, C.c_int, C.c_void_p]
         L.orc_search_by_projection_kf.argtypes = [C.POINTER(_Frame), C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_int, C.c_int, C.c_void_p]
         L.orc_search_for_initialization.argtypes = [C.POINTER(_Frame), C.POINTER(_Frame), C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
+        L.orc_vocab_create.restype = C.c_void_p
+        L.orc_vocab_create.argtypes = [C.c_int] * 5 + [C.c_void_p] * 3
+        L.orc_vocab_load_text.restype = C.c_void_p
+        L.orc_vocab_load_text.argtypes = [C.c_char_p]
+        L.orc_vocab_destroy.argtypes = [C.c_void_p]
+        L.orc_vocab_nnodes.argtypes = [C.c_void_p]
+        L.orc_vocab_nwords.argtypes = [C.c_void_p]
+        L.orc_vocab_transform_feature.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_vocab_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7
+        L.orc_bow_score_l1.restype = C.c_double
+        L.orc_bow_score_l1.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_bow_score_db.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
         L.orc_three_maxima.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 3
         _lib = L
     return _lib
@@ -386,3 +398,69 @@ def search_for_initialization(f1, f2, prev_matched, window, nnratio, check_ori=T
     m = np.full(f1.n, -1, np.int32)
     n = lib().orc_search_for_initialization(C.byref(f1.c), C.byref(f2.c), _p(prev), window, nnratio, int(check_ori), _p(m))
     return n, m, prev
+
+
+class OracleVocabulary:
+    """DBoW2 TemplatedVocabulary<FORB> restated (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h)."""
+
+    def __init__(self, k=None, L=None, parent=None, desc=None, weight=None, scoring=0, weighting=0, path=None):
+        if path is not None:
+            self._h = lib().orc_vocab_load_text(str(path).encode())
+        else:
+            parent = np.ascontiguousarray(parent, np.int32)
+            desc = np.ascontiguousarray(desc, np.uint8)
+            weight = np.ascontiguousarray(weight, np.float64)
+            self._h = lib().orc_vocab_create(k, L, scoring, weighting, len(parent), _p(parent), _p(desc), _p(weight))
+        if not self._h:
+            raise ValueError("invalid vocabulary")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_vocab_destroy(self._h)
+            self._h = None
+
+    @property
+    def nnodes(self):
+        return lib().orc_vocab_nnodes(self._h)
+
+    @property
+    def nwords(self):
+        return lib().orc_vocab_nwords(self._h)
+
+    def transform_features(self, desc, levelsup=0):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        word = np.zeros(n, np.int32); weight = np.zeros(n, np.float64); node = np.zeros(n, np.int32)
+        w = C.c_int32(0); wt = C.c_double(0); nd = C.c_int32(0)
+        for i in range(n):
+            lib().orc_vocab_transform_feature(self._h, desc[i].ctypes.data, levelsup, C.addressof(w), C.addressof(wt), C.addressof(nd))
+            word[i], weight[i], node[i] = w.value, wt.value, nd.value
+        return word, weight, node
+
+    def transform(self, desc, levelsup=4):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        bw = np.zeros(max(n, 1), np.int32); bv = np.zeros(max(n, 1), np.float64)
+        fn = np.zeros(max(n, 1), np.int32); fs = np.zeros(n + 1, np.int32); fi = np.zeros(max(n, 1), np.int32)
+        nb = C.c_int(0); nf = C.c_int(0)
+        lib().orc_vocab_transform(self._h, _p(desc), n, levelsup, _p(bw), _p(bv), C.addressof(nb), _p(fn), _p(fs), _p(fi), C.addressof(nf))
+        return (bw[:nb.value].copy(), bv[:nb.value].copy()), (fn[:nf.value].copy(), fs[:nf.value + 1].copy(), fi[:fs[nf.value]].copy())
+
+
+def bow_score_l1(v1, v2):
+    w1 = np.ascontiguousarray(v1[0], np.int32); x1 = np.ascontiguousarray(v1[1], np.float64)
+    w2 = np.ascontiguousarray(v2[0], np.int32); x2 = np.ascontiguousarray(v2[1], np.float64)
+    return lib().orc_bow_score_l1(_p(w1), _p(x1), len(w1), _p(w2), _p(x2), len(w2))
+
+
+def bow_score_db(query, kf_bows):
+    qw = np.ascontiguousarray(query[0], np.int32); qv = np.ascontiguousarray(query[1], np.float64)
+    start = np.zeros(len(kf_bows) + 1, np.int32)
+    for i, b in enumerate(kf_bows):
+        start[i + 1] = start[i] + len(b[0])
+    words = np.ascontiguousarray(np.concatenate([np.asarray(b[0], np.int32) for b in kf_bows]), np.int32)
+    vals = np.ascontiguousarray(np.concatenate([np.asarray(b[1], np.float64) for b in kf_bows]), np.float64)
+    common = np.zeros(len(kf_bows), np.int32); score = np.zeros(len(kf_bows), np.float32)
+    mx = C.c_int(0)
+    lib().orc_bow_score_db(_p(qw), _p(qv), len(qw), len(kf_bows), _p(start), _p(words), _p(vals), _p(common), _p(score), C.addressof(mx))
+    return common, score, mx.value

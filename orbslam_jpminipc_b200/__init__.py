@@ -9,3 +9,4 @@ CUDA device and raises otherwise.
 from ._lib import KP_DTYPE, OrbError, SO_PATH, lib  # noqa: F401
 from .extractor import ORBextractor  # noqa: F401
 from .matcher import Frame, ORBmatcher  # noqa: F401
+from .vocabulary import ORBVocabulary  # noqa: F401

@@ -26,6 +26,8 @@ EXPORTS = [
     "orb_hamming_knn2", "orb_hamming_knn2_device", "orb_knn2_merge_device", "orb_match_ratio",
     "orb_frame_grid_build", "orb_search_by_projection", "orb_search_window", "orb_search_for_initialization", "orb_search_by_bow", "orb_search_by_bow_kf", "orb_host_alloc", "orb_host_free",
     "orb_measure_popc_peak",
+    "orb_vocab_create", "orb_vocab_load_text", "orb_vocab_destroy", "orb_vocab_info", "orb_vocab_transform_features",
+    "orb_vocab_transform_batch", "orb_bow_score_db",
 ]
 
 
@@ -107,6 +109,14 @@ def lib():
     L.orb_host_alloc.argtypes = [sz]
     L.orb_host_free.argtypes = [vp]
     L.orb_measure_popc_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.orb_vocab_create.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, C.POINTER(vp)]
+    L.orb_vocab_load_text.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    L.orb_vocab_destroy.restype = None
+    L.orb_vocab_destroy.argtypes = [vp]
+    L.orb_vocab_info.argtypes = [vp] + [C.POINTER(C.c_int)] * 4
+    L.orb_vocab_transform_features.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
+    L.orb_vocab_transform_batch.argtypes = [vp, vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.orb_bow_score_db.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, i32, vp, vp, C.POINTER(C.c_int)]
     _lib = L
     return L
 

@@ -86,3 +86,90 @@ def synth_descriptors(n_db, n_q, seed_db=42, seed_q=43, flip_p=0.08, dup_frac=0.
         flips = np.packbits((rq.random(((n_q + 1) // 2, 256)) < flip_p).astype(np.uint8), axis=1)
         q[0::2] = db[perm] ^ flips
     return db, q
+
+
+def synth_vocabulary(k=10, L=6, seed=5, flip_bits=24, stop_frac=0.02, prune_frac=0.0, order="bfs"):
+    """Synthetic vocabulary tree in the node order of DBoW2's text format (the reference's Data/ORBvoc.txt is not in the
+    repository).  Children are their parent's descriptor with `flip_bits` random bits flipped, so the Hamming descent is
+    meaningful; weights are idf-like positive doubles with a fraction `stop_frac` of zero-weight (stopped) words;
+    `prune_frac` removes random subtrees (ragged tree: fewer than k children, leaves above level L);
+    order="dfs" numbers nodes depth first (children of a node not consecutive).
+    Returns (parent int32[n], desc uint8[n,32], weight float64[n]) with node 0 the root."""
+    rng = np.random.default_rng(seed)
+    parent = [0]
+    bits = [np.zeros(256, np.uint8)]
+    level = [0]
+    root_children = rng.integers(0, 2, (k, 256), dtype=np.uint8)
+    if order == "bfs":
+        frontier = [0]
+        for lv in range(1, L + 1):
+            nxt = []
+            for p in frontier:
+                for c in range(k):
+                    if lv > 1 and prune_frac > 0 and rng.random() < prune_frac:
+                        continue
+                    b = root_children[c].copy() if p == 0 else bits[p].copy()
+                    if p != 0:
+                        b[rng.choice(256, flip_bits, replace=False)] ^= 1
+                    parent.append(p); bits.append(b); level.append(lv)
+                    nxt.append(len(parent) - 1)
+            frontier = nxt
+    else:
+        def grow(p, lv):
+            if lv > L:
+                return
+            for c in range(k):
+                if lv > 1 and prune_frac > 0 and rng.random() < prune_frac:
+                    continue
+                b = root_children[c].copy() if p == 0 else bits[p].copy()
+                if p != 0:
+                    b[rng.choice(256, flip_bits, replace=False)] ^= 1
+                parent.append(p); bits.append(b); level.append(lv)
+                grow(len(parent) - 1, lv + 1)
+        grow(0, 1)
+    n = len(parent)
+    desc = np.packbits(np.stack(bits), axis=1, bitorder="little")
+    weight = rng.uniform(0.5, 12.0, n)
+    weight[rng.random(n) < stop_frac] = 0.0
+    weight[0] = 0.0
+    return np.asarray(parent, np.int32), desc, weight
+
+
+def synth_vocabulary_fast(k=10, L=6, seed=5, flip_bits=24, stop_frac=0.02):
+    """Full, balanced tree generated level by level with numpy (for k=10, L=6: 1 111 111 nodes), breadth-first order."""
+    rng = np.random.default_rng(seed)
+    parents = [np.zeros(1, np.int32)]
+    descs = [np.zeros((1, 32), np.uint8)]
+    prev_ids = np.zeros(1, np.int64)
+    prev_desc = None
+    next_id = 1
+    for lv in range(1, L + 1):
+        m = len(prev_ids) * k
+        par = np.repeat(prev_ids, k)
+        if lv == 1:
+            d = rng.integers(0, 256, (m, 32), dtype=np.uint8)
+        else:
+            d = np.repeat(prev_desc, k, axis=0)
+            # flip bits: xor with a sparse random mask (about flip_bits of 256 set)
+            mask = np.packbits(rng.random((m, 256)) < flip_bits / 256.0, axis=1)
+            d = d ^ mask
+        parents.append(par.astype(np.int32)); descs.append(d)
+        prev_ids = np.arange(next_id, next_id + m, dtype=np.int64)
+        prev_desc = d
+        next_id += m
+    parent = np.concatenate(parents); desc = np.concatenate(descs)
+    weight = rng.uniform(0.5, 12.0, len(parent))
+    weight[rng.random(len(parent)) < stop_frac] = 0.0
+    weight[0] = 0.0
+    return parent, desc, weight
+
+
+def write_vocabulary_text(path, k, L, parent, desc, weight, scoring=0, weighting=0):
+    """DBoW2 text format (TemplatedVocabulary::saveToTextFile / loadFromTextFile, TemplatedVocabulary.h:1338-1460)."""
+    n = len(parent)
+    has_child = np.zeros(n, bool)
+    has_child[parent[1:]] = True
+    with open(path, "w") as f:
+        f.write("%d %d %d %d\n" % (k, L, scoring, weighting))
+        for i in range(1, n):
+            f.write("%d %d %s %s\n" % (parent[i], 0 if has_child[i] else 1, " ".join(str(int(b)) for b in desc[i]), repr(float(weight[i]))))
