@@ -256,6 +256,36 @@ def run_matching(args, L, ex, dev, world, rank, stream, barrier, max_over_ranks,
                                                      "ms_per_pair_host_api": sbp_ms, "extract_two_frames_host_api_ms": ext_ms,
                                                      "note": "single frame pair, latency through the host-buffer C ABI (grid build excluded)"}
         matching["_sbp_inputs"] = (cur, last, has, outl, xyz, Tcw)
+        # vocabulary transform (Frame::ComputeBoW, src/Frame.cc:279-287) on the reference's tree shape: k=10, L=6, levelsup=4
+        from orbslam_jpminipc_b200.synth import synth_vocabulary_fast
+        parent, vdesc, vweight = synth_vocabulary_fast(10, 6, seed=7)
+        voc = pkg.ORBVocabulary(ex).create(10, 6, parent, vdesc, vweight)
+        VB, VN = 256, 1000
+        rng = np.random.default_rng(5)
+        leaves = rng.integers(111111, 1111111, VB * VN)
+        feats = vdesc[leaves] ^ (rng.integers(0, 256, (VB * VN, 32), dtype=np.uint8) & rng.integers(0, 256, (VB * VN, 32), dtype=np.uint8)
+                                 & rng.integers(0, 256, (VB * VN, 32), dtype=np.uint8) & rng.integers(0, 256, (VB * VN, 32), dtype=np.uint8))
+        d_feats = torch.from_numpy(feats).to(dev)
+        d_cnt = torch.full((VB,), VN, dtype=torch.int32, device=dev)
+        vo = {k_: torch.zeros(VB * (VN + 1), dtype=torch.int32, device=dev) for k_ in ("bw", "fn", "fs", "fi", "nb", "nf")}
+        d_bv = torch.zeros(VB * VN, dtype=torch.float64, device=dev)
+
+        def vocab_step():
+            check(L.orb_vocab_transform_batch(ex._h, voc._v, ptr(d_feats), VN, ptr(d_cnt), VB, 4, VN, ptr(vo["bw"]), ptr(d_bv), ptr(vo["nb"]),
+                                              ptr(vo["fn"]), ptr(vo["fs"]), ptr(vo["fi"]), ptr(vo["nf"])), "orb_vocab_transform_batch")
+        for _ in range(3):
+            vocab_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            vocab_step()
+        torch.cuda.synchronize()
+        vms = (time.perf_counter() - t0) / 10 * 1e3
+        matching["vocabulary_transform_k10_L6"] = {"frames": VB, "features_per_frame": VN, "levelsup": 4, "ms_per_batch": vms,
+                                                   "features_per_s": VB * VN / (vms * 1e-3), "frames_per_s": VB / (vms * 1e-3),
+                                                   "mean_words_per_frame": float(vo["nb"][:VB].float().mean().item()),
+                                                   "note": "device-resident descriptors, synthetic tree (ORBvoc.txt is not in the reference repository)"}
+        matching["_vocab_inputs"] = (parent, vdesc, vweight, feats[:VN].copy())
     return matching
 
 
@@ -418,6 +448,7 @@ def run_gpu(args):
                     "gpu_launches_per_step": e2e_launches, "chunk": args.e2e_chunk, "api": "orb_extract_batch (pinned host buffers in and out, internally chunked + double-buffered)"},
             "roofline": roofline, "matching": matching}
     sbp_inputs = matching.pop("_sbp_inputs", None) if matching else None
+    vocab_inputs = matching.pop("_vocab_inputs", None) if matching else None
     if args.cpu_baseline:
         cores = os.cpu_count() or 1
         nfr = 64 * cores                                   # ~12 core-seconds of CPU work at ~80 frames/s/core
@@ -441,6 +472,15 @@ def run_gpu(args):
             t0 = time.perf_counter()
             po.knn2(q4, db4)
             line["cpu_baseline"]["knn2_2000x2000_pairs_per_s_1thread"] = 4e6 / (time.perf_counter() - t0)
+        if vocab_inputs is not None:
+            from oracle import pyoracle as po
+            parent, vdesc, vweight, f1 = vocab_inputs
+            ov = po.OracleVocabulary(10, 6, parent, vdesc, vweight)
+            ov.transform(f1, 4)
+            t0 = time.perf_counter()
+            for _ in range(10):
+                ov.transform(f1, 4)
+            line["cpu_baseline"]["vocabulary_transform_k10_L6_ms_per_frame_1thread"] = (time.perf_counter() - t0) / 10 * 1e3
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

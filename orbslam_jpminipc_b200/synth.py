@@ -150,8 +150,11 @@ def synth_vocabulary_fast(k=10, L=6, seed=5, flip_bits=24, stop_frac=0.02):
             d = rng.integers(0, 256, (m, 32), dtype=np.uint8)
         else:
             d = np.repeat(prev_desc, k, axis=0)
-            # flip bits: xor with a sparse random mask (about flip_bits of 256 set)
-            mask = np.packbits(rng.random((m, 256)) < flip_bits / 256.0, axis=1)
+            # flip bits: xor with a sparse random mask (AND of j random bytes sets a bit with probability 2^-j)
+            ands = max(1, int(round(np.log2(256.0 / flip_bits))))
+            mask = rng.integers(0, 256, (m, 32), dtype=np.uint8)
+            for _ in range(ands - 1):
+                mask &= rng.integers(0, 256, (m, 32), dtype=np.uint8)
             d = d ^ mask
         parents.append(par.astype(np.int32)); descs.append(d)
         prev_ids = np.arange(next_id, next_id + m, dtype=np.int64)

@@ -260,12 +260,31 @@ def test_cpp_shim_program(pkg, po, tmp_path):
     img = synth_frame(240, 320, 8100)
     raw, out = str(tmp_path / "f.raw"), str(tmp_path / "o.bin")
     img.tofile(raw)
-    subprocess.check_call([exe, raw, "320", "240", "300", out])
+    from orbslam_jpminipc_b200 import synth
+    parent, vdesc, weight = synth.synth_vocabulary(6, 3, seed=4, stop_frac=0.03)
+    voc_path = str(tmp_path / "voc.txt")
+    synth.write_vocabulary_text(voc_path, 6, 3, parent, vdesc, weight)
+    subprocess.check_call([exe, raw, "320", "240", "300", out, voc_path])
     buf = open(out, "rb").read()
     n, nmatch = np.frombuffer(buf[:8], np.int32)
     kps = np.frombuffer(buf[8:8 + 28 * n], pkg.KP_DTYPE)
     desc = np.frombuffer(buf[8 + 28 * n:8 + 60 * n], np.uint8).reshape(n, 32)
-    match = np.frombuffer(buf[8 + 60 * n:], np.int32)
+    match = np.frombuffer(buf[8 + 60 * n:8 + 64 * n], np.int32)
+    # vocabulary part: BowVector / FeatureVector as the std::map based shim returned them
+    off = 8 + 64 * n
+    nb, nfv = np.frombuffer(buf[off:off + 8], np.int32)
+    self_score = np.frombuffer(buf[off + 8:off + 12], np.float32)[0]
+    off += 12
+    bow = np.frombuffer(buf[off:off + 12 * nb], np.dtype([("w", "<u4"), ("v", "<f8")]))
+    off += 12 * nb
+    (rbw, rbv), (rfn, rfs, rfi) = po.OracleVocabulary(path=voc_path).transform(desc, 1)
+    assert nb == len(rbw) and np.array_equal(bow["w"], rbw) and np.array_equal(bow["v"], rbv) and self_score == 1.0
+    assert nfv == len(rfn)
+    for j in range(nfv):
+        node, m = np.frombuffer(buf[off:off + 8], np.int32)
+        items = np.frombuffer(buf[off + 8:off + 8 + 4 * m], np.int32)
+        off += 8 + 4 * m
+        assert node == rfn[j] and np.array_equal(items, rfi[rfs[j]:rfs[j + 1]])
     rk, rd = po.OracleExtractor(300)(img)
     assert n == len(rk) and np.array_equal(kps.view(np.uint8), rk.view(np.uint8)) and np.array_equal(desc, rd)
     i1, d1, d2 = po.knn2(rd, rd)
