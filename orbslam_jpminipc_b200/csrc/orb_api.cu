@@ -109,7 +109,7 @@ static int prepare(orb_ctx* c, int w, int h)
         if ((size_t)maxcap * 8 > 170 * 1024) return ORB_ERR_CAPACITY;
         rc = orb_select_smem_setup(maxcap * 8 + 6144 * 4 + 1024); if (rc) return rc;
         size_t rsm = 1024;
-        for (int l = 1; l < c->plan.nlevels; l++) rsm = std::max(rsm, (size_t)2 * (((size_t)c->rs_box_w[l] * c->rs_box_h[l] + 127) & ~(size_t)127));
+        for (int l = 1; l < c->plan.nlevels; l++) rsm = std::max(rsm, (size_t)2 * (((size_t)c->rs_box_w[l] * c->rs_box_h[l] + 127) & ~(size_t)127) + 16);
         rc = orb_resize_smem_setup((int)rsm); if (rc) return rc;
         c->plan_valid = true;
     }

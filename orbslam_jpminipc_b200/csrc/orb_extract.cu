@@ -91,6 +91,7 @@ k_resize(const __grid_constant__ CUtensorMap tm, uint8_t* __restrict__ planes, s
     extern __shared__ __align__(128) uint8_t rs_sm[];       // two source tiles of buf_bytes each
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ int s_next[2];
+    __shared__ int s_org[2][5];                             // x0, y0, frame, source origin x / y of the item in each buffer
     const int tid = threadIdx.x;
     const int ncg = RT_W >> 2;                              // column groups (4 columns each) per tile
     const int RT_H = (256 / ncg) * RS_ROWS;
@@ -98,17 +99,14 @@ k_resize(const __grid_constant__ CUtensorMap tm, uint8_t* __restrict__ planes, s
     const int ntiles = tiles_x * tiles_y, total = ntiles * nimg;
     const int2* xt = xtab + D.xtab_off;
     const int2* yt = ytab + D.ytab_off;
-    auto origin = [&](int item, int& x0, int& y0, int& fr, int& sx_org, int& sy_org) {
-        const int ti = item % ntiles;
-        fr = item / ntiles;
-        const int by = ti / tiles_x, bx = ti - by * tiles_x;
-        x0 = bx * RT_W; y0 = by * RT_H;
-        sx_org = (__ldg(&xt[x0]).x & 0xffff) & ~15;          // 16-byte aligned TMA origin (ROI starts at padded x = 16)
-        sy_org = __ldg(&yt[y0]).x & 0xffff;
-    };
+    // thread 0 only: decode an item, remember its origin for everybody and start its copy
     auto issue = [&](int item, int buf) {
-        int x0, y0, fr, sxo, syo;
-        origin(item, x0, y0, fr, sxo, syo);
+        const int ti = item % ntiles, fr = item / ntiles;
+        const int by = ti / tiles_x, bx = ti - by * tiles_x;
+        const int x0 = bx * RT_W, y0 = by * RT_H;
+        const int sxo = (__ldg(&xt[x0]).x & 0xffff) & ~15;   // 16-byte aligned TMA origin (ROI starts at padded x = 16)
+        const int syo = __ldg(&yt[y0]).x & 0xffff;
+        s_org[buf][0] = x0; s_org[buf][1] = y0; s_org[buf][2] = fr; s_org[buf][3] = sxo; s_org[buf][4] = syo;
         mbar_expect_tx(&bar[buf], (uint32_t)(box_w * box_h));
         tma_load_3d(rs_sm + (size_t)buf * buf_bytes, &tm, sxo + ORB_EDGE, syo + ORB_EDGE, fr, &bar[buf]);
     };
@@ -119,11 +117,11 @@ k_resize(const __grid_constant__ CUtensorMap tm, uint8_t* __restrict__ planes, s
     __syncthreads();
     int item = blockIdx.x;
     if (tid == 0 && item < total) issue(item, 0);
+    __syncthreads();
     const int rg = tid / ncg, cgx = (tid - rg * ncg) * 4;
     for (int it = 0; item < total; it++) {
         const int buf = it & 1;
-        int x0, y0, f, sxo, syo;
-        origin(item, x0, y0, f, sxo, syo);
+        const int x0 = s_org[buf][0], y0 = s_org[buf][1], f = s_org[buf][2], sxo = s_org[buf][3], syo = s_org[buf][4];
         if (tid == 0) {
             const int nxt = atomicAdd(work_counter, 1) + (int)gridDim.x;
             s_next[buf] = nxt;
@@ -131,55 +129,72 @@ k_resize(const __grid_constant__ CUtensorMap tm, uint8_t* __restrict__ planes, s
         }
         const int gx = x0 + cgx, ys = y0 + rg * RS_ROWS;
         const bool active = gx < D.w && ys < D.h;
-        int c0[4], c1[4], a0[4], a1[4];
+        // Horizontal taps of the thread's four columns.  Their source bytes lie within 8 bytes of the first one for every scale
+        // factor <= 2, so a source row costs three aligned words, two funnel shifts and per column one PRMT (both taps into
+        // bytes 0,1) + one IDP.2A with the packed 16-bit weights; otherwise bytes are fetched one by one.
+        int c0[4], c1[4];
+        uint32_t aw[4], sel[4];
+        bool fastp = true;
+        int wofs = 0, sh = 0;
         if (active) {
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int2 e = __ldg(&xt[min(gx + k, D.w - 1)]);
                 c0[k] = (e.x & 0xffff) - sxo; c1[k] = (e.x >> 16) - sxo;
-                a0[k] = (short)(e.y & 0xffff); a1[k] = (short)(e.y >> 16);
+                aw[k] = (uint32_t)e.y;                                  // a0 | a1 << 16, both in [0, 2048]
             }
+            const int cb = c0[0];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int d0 = c0[k] - cb, d1 = c1[k] - cb;
+                fastp = fastp && d0 >= 0 && d1 >= 0 && d0 <= 7 && d1 <= 7;
+                sel[k] = (uint32_t)(d0 & 7) | ((uint32_t)(d1 & 7) << 4);
+            }
+            wofs = cb & ~3; sh = (cb & 3) * 8;
         }
         mbar_wait(&bar[buf], (uint32_t)((it >> 1) & 1));
         if (active) {
             const uint8_t* src = rs_sm + (size_t)buf * buf_bytes;
-            int id0 = -1, id1 = -1, H0[4], H1[4];
+            int id0 = -1, id1 = -1, G0[4], G1[4];                       // G = horizontal sum >> 4 of source rows id0 / id1
+            auto hrow = [&](int srow, int (&G)[4]) {
+                const uint8_t* r = src + srow * box_w;
+                if (fastp) {
+                    const uint32_t* rw = reinterpret_cast<const uint32_t*>(r + wofs);
+                    const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
+                    const uint32_t W0 = __funnelshift_r(w0, w1, sh), W1 = __funnelshift_r(w1, w2, sh);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) G[k] = (int)(__dp2a_lo(aw[k], __byte_perm(W0, W1, sel[k]), 0u) >> 4);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) G[k] = (int)((r[c0[k]] * (aw[k] & 0xffffu) + r[c1[k]] * (aw[k] >> 16)) >> 4);
+                }
+            };
             uint8_t* drow = planes + (size_t)f * fbytes + D.plane_off + (size_t)(ys + ORB_EDGE) * D.stride + ORB_EDGE + gx;
             const int yend = min(ys + RS_ROWS, D.h);
             for (int y = ys; y < yend; y++, drow += D.stride) {
                 const int2 e = __ldg(&yt[y]);
                 const int s0 = (e.x & 0xffff) - syo, s1 = (e.x >> 16) - syo;
-                const int b0 = (short)(e.y & 0xffff), b1 = (short)(e.y >> 16);
+                const int b0 = e.y & 0xffff, b1 = (int)((uint32_t)e.y >> 16);
                 if (s0 != id0) {
                     if (s0 == id1) {
 #pragma unroll
-                        for (int k = 0; k < 4; k++) H0[k] = H1[k];
-                    } else {
-                        const uint8_t* r = src + s0 * box_w;
-#pragma unroll
-                        for (int k = 0; k < 4; k++) H0[k] = r[c0[k]] * a0[k] + r[c1[k]] * a1[k];
-                    }
+                        for (int k = 0; k < 4; k++) G0[k] = G1[k];
+                    } else hrow(s0, G0);
                     id0 = s0;
                 }
                 if (s1 != id1) {
                     if (s1 == id0) {
 #pragma unroll
-                        for (int k = 0; k < 4; k++) H1[k] = H0[k];
-                    } else {
-                        const uint8_t* r = src + s1 * box_w;
-#pragma unroll
-                        for (int k = 0; k < 4; k++) H1[k] = r[c0[k]] * a0[k] + r[c1[k]] * a1[k];
-                    }
+                        for (int k = 0; k < 4; k++) G1[k] = G0[k];
+                    } else hrow(s1, G1);
                     id1 = s1;
                 }
-                uint32_t v = 0;
+                // (((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2 ; weights sum to <= 2048, so the result is already in 0..255
+                uint32_t o[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {          // (((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2
-                    const int o = (((b0 * (H0[k] >> 4)) >> 16) + ((b1 * (H1[k] >> 4)) >> 16) + 2) >> 2;
-                    v |= (uint32_t)min(max(o, 0), 255) << (8 * k);
-                }
+                for (int k = 0; k < 4; k++) o[k] = (uint32_t)((((b0 * G0[k]) >> 16) + ((b1 * G1[k]) >> 16) + 2) >> 2);
                 // bytes past the right ROI edge fall into the border and are rewritten by k_border
-                *reinterpret_cast<uint32_t*>(drow) = v;
+                *reinterpret_cast<uint32_t*>(drow) = (o[0] | (o[1] << 8)) | ((o[2] << 16) | (o[3] << 24));
             }
         }
         __syncthreads();          // the other buffer is refilled by the next iteration's prefetch
@@ -944,7 +959,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         const int bufb = (c->rs_box_w[l] * c->rs_box_h[l] + 127) & ~127;
         const int grid = std::min(tiles, c->num_sms * 4);
         cudaMemsetAsync(W.d_counters + 4 + l, 0, sizeof(int), s);
-        k_resize<<<grid, 256, 2 * bufb, s>>>(W.tm_resize.m[l], W.d_planes, fb, D, c->d_xtab, c->d_ytab, c->rs_box_w[l], c->rs_box_h[l],
+        k_resize<<<grid, 256, 2 * bufb + 16, s>>>(W.tm_resize.m[l], W.d_planes, fb, D, c->d_xtab, c->d_ytab, c->rs_box_w[l], c->rs_box_h[l],
                                                bufb, nimg, W.d_counters + 4 + l, tw, rr);
         launches++;
     }
