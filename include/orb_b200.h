@@ -77,6 +77,14 @@ int orb_extract(orb_ctx*, const uint8_t* img, int w, int h, int stride,
  * copies and kernels overlapped on two streams when the buffers are host memory. */
 int orb_extract_batch(orb_ctx*, const uint8_t* imgs, int nimg, int w, int h, int stride, size_t frame_pitch,
                       orb_keypoint* kps, uint8_t* desc, int cap, int32_t* counts);
+/* Asynchronous form of orb_extract_batch for streaming ingest: enqueues the batch and returns a ticket; consecutive calls keep
+ * alternating the two internal work sets, so the host->device copy of one call overlaps the kernels of the previous one.  All
+ * buffers of a call must stay valid (host buffers pinned for real overlap) until orb_wait(ticket) returns; at most 7 calls may
+ * be in flight (an 8th waits for the oldest).  orb_wait returns what the synchronous call would have returned. */
+int orb_extract_batch_async(orb_ctx*, const uint8_t* images, int nimg, int width, int height, int stride, size_t frame_pitch,
+                            orb_keypoint* kps, uint8_t* desc, int cap, int32_t* counts, long long* ticket);
+int orb_wait(orb_ctx*, long long ticket);
+
 /* device pointers only, nimg <= max_batch, asynchronous on `stream` (a cudaStream_t). */
 int orb_extract_batch_device(orb_ctx*, const uint8_t* d_imgs, int nimg, int w, int h, int stride, size_t frame_pitch,
                              orb_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts, void* stream);

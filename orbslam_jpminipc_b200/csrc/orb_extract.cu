@@ -376,7 +376,7 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
             m_l[i] = (i > 0 && c >= 0 && colcell[i - 1] == c) ? 0xff : 0;
             m_r[i] = (i < FSW * 4 - 1 && c >= 0 && colcell[i + 1] == c) ? 0xff : 0;
         }
-        mbar_wait(&bar[buf], (uint32_t)((it >> 1) & 1));      // image tile has landed
+        if (tid < 32) mbar_wait(&bar[buf], (uint32_t)((it >> 1) & 1));      // image tile has landed; one warp polls, the rest sleep in the barrier
         __syncthreads();
         const uint32_t* img = img2[buf];
 
@@ -723,7 +723,8 @@ k_blur(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ blurred, size_t
             s_next[buf] = nxt;
             if (nxt < total) issue(nxt, buf ^ 1);
         }
-        mbar_wait(&bar[buf], (uint32_t)((it >> 1) & 1));
+        if (tid < 32) mbar_wait(&bar[buf], (uint32_t)((it >> 1) & 1));      // one warp polls, the rest sleep in the barrier
+        __syncthreads();
         const uint32_t* img = reinterpret_cast<const uint32_t*>(img2[buf]);
         // row pass: one task = 8 adjacent outputs of one row; ROI column x0+c sits at tile byte 16+c
         for (int task = tid; task < BI_H * (BT_W / 8); task += 256) {
@@ -760,7 +761,7 @@ k_blur(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ blurred, size_t
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const int y = t.y0 + rg * 4 + q;
-                uint32_t w = 0;
+                uint32_t iv[4];
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
 #define RV(i) (e == 0 ? R[i].x : e == 1 ? R[i].y : e == 2 ? R[i].z : R[i].w)
@@ -769,10 +770,11 @@ k_blur(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ blurred, size_t
                     s = fmaf(__fadd_rn(RV(q + 5), RV(q + 1)), k1, s);
                     s = fmaf(__fadd_rn(RV(q + 6), RV(q)), k0, s);
 #undef RV
-                    // rint via the 1.5*2^23 magic constant (0 <= s < 2^22), then saturate to 255
-                    const uint32_t iv = min(__float_as_uint(__fadd_rn(s, 12582912.0f)) & 0x3ffu, 255u);
-                    w |= iv << (8 * e);
+                    // rint via the 1.5*2^23 magic constant: the low mantissa byte is the result.  No saturation needed: the taps
+                    // sum to 1 within 1e-7, so s < 255.5 for 8-bit inputs.
+                    iv[e] = __float_as_uint(__fadd_rn(s, 12582912.0f));
                 }
+                const uint32_t w = __byte_perm(__byte_perm(iv[0], iv[1], 0x0040), __byte_perm(iv[2], iv[3], 0x0040), 0x5410);
                 if (y < L.h && x < L.w) {    // exactly the ROI bytes: the frame of the blurred buffer holds the un-blurred reflection
                     uint8_t* o = out + (size_t)(y + ORB_EDGE) * L.stride + x + ORB_EDGE;
                     if (x + 3 < L.w) *reinterpret_cast<uint32_t*>(o) = w;

@@ -117,6 +117,15 @@ struct orb_ctx {
     WorkSet ws[2];
     cudaEvent_t ev_user = nullptr, ev_half[2] = { nullptr, nullptr };
     int last_n0 = 0, last_n1 = 0;     // frames handled by ws[0] / ws[1] in the last launch (debug getters)
+    // asynchronous host-buffer calls (orb_extract_batch_async / orb_wait): a ring of completion records
+    static constexpr int NTICKETS = 8;
+    struct Ticket { cudaEvent_t done = nullptr, a = nullptr, b = nullptr; int* h_status = nullptr; int32_t* counts = nullptr;
+                    int nimg = 0, cap = 0; long long seq = -1; bool host_out = false; };
+    Ticket tickets[NTICKETS];
+    cudaStream_t done_stream = nullptr;
+    long long next_seq = 0, waited_seq = -1;   // tickets issued / highest ticket known complete
+    int chunk_parity = 0;             // work set / stream the next chunk goes to
+    bool chain_chunks = true, kernels_pending = false;
     // staging for host-pointer calls (two slots for copy/compute overlap)
     uint8_t* d_src[2] = { nullptr, nullptr };  size_t src_bytes[2] = { 0, 0 };
     size_t kps_bytes[2] = { 0, 0 }, desc_bytes[2] = { 0, 0 }, counts_bytes[2] = { 0, 0 };

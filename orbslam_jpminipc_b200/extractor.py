@@ -37,6 +37,21 @@ class ORBextractor:
     def GetScaleFactor(self):
         return lib().orb_scale_factor(self._h)
 
+    def extract_batch_async(self, images, kps, desc, counts):
+        """Enqueue a batch (uint8 array N x H x W, ideally pinned) into caller-owned output arrays (N x capacity keypoints,
+        N x capacity x 32 descriptors, N counts) and return a ticket for wait(); see orb_extract_batch_async."""
+        import ctypes as C
+        from ._lib import check, ptr
+        n, h, w = images.shape
+        t = C.c_longlong(-1)
+        check(lib().orb_extract_batch_async(self._h, ptr(images), n, w, h, images.strides[1], images.strides[0], ptr(kps), ptr(desc),
+                                            self.capacity, ptr(counts), C.byref(t)), "orb_extract_batch_async")
+        return t.value
+
+    def wait(self, ticket):
+        from ._lib import check
+        check(lib().orb_wait(self._h, ticket), "orb_wait")
+
     # ORBextractor::operator()(image, mask, keypoints, descriptors)
     def __call__(self, image, mask=None):
         image = np.asarray(image)

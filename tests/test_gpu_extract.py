@@ -134,3 +134,39 @@ def test_strided_input_and_edge_cases(pkg, po):
     with pytest.raises(pkg.OrbError):                # grid with zero columns: the reference divides by zero
         tiny(np.zeros((100, 100), np.uint8))
     tiny.close()
+
+
+def test_async_tickets_match_sync_call(pkg):
+    """orb_extract_batch_async / orb_wait: several calls in flight (more than the ticket ring holds) give the results of the
+    blocking call, chunked over both work sets."""
+    import ctypes as C
+    from orbslam_jpminipc_b200._lib import check, lib, ptr
+    from orbslam_jpminipc_b200.synth import synth_frames
+    L = lib()
+    h, w, nb = 240, 320, 6
+    ex = pkg.ORBextractor(300, 1.2, 8, 1, 20, max_width=w, max_height=h, max_batch=4)
+    cap = ex.capacity
+    batches = [np.stack(synth_frames(nb, h, w, seed0=4000 + 10 * b)) for b in range(11)]
+    ref = []
+    for fr in batches:
+        k = np.zeros((nb, cap), pkg.KP_DTYPE); d = np.zeros((nb, cap, 32), np.uint8); c = np.zeros(nb, np.int32)
+        check(L.orb_extract_batch(ex._h, ptr(fr), nb, w, h, w, w * h, ptr(k), ptr(d), cap, ptr(c)), "sync")
+        ref.append((k, d, c))
+    outs, tickets = [], []
+    for fr in batches:
+        k = np.zeros((nb, cap), pkg.KP_DTYPE); d = np.zeros((nb, cap, 32), np.uint8); c = np.zeros(nb, np.int32)
+        t = C.c_longlong(-1)
+        check(L.orb_extract_batch_async(ex._h, ptr(fr), nb, w, h, w, w * h, ptr(k), ptr(d), cap, ptr(c), C.byref(t)), "async")
+        outs.append((k, d, c)); tickets.append(t.value)
+    assert tickets == list(range(tickets[0], tickets[0] + len(batches)))
+    for t in reversed(tickets):                    # any order, also tickets whose record was recycled
+        check(L.orb_wait(ex._h, t), "wait")
+    for (k, d, c), (rk, rd, rc) in zip(outs, ref):
+        assert np.array_equal(c, rc)
+        for i in range(nb):
+            assert np.array_equal(k[i, :c[i]].view(np.uint8), rk[i, :c[i]].view(np.uint8)) and np.array_equal(d[i, :c[i]], rd[i, :c[i]])
+    assert L.orb_wait(ex._h, tickets[-1] + 5) != 0          # unknown ticket
+    # the blocking call still works with nothing in flight
+    k = np.zeros((nb, cap), pkg.KP_DTYPE); d = np.zeros((nb, cap, 32), np.uint8); c = np.zeros(nb, np.int32)
+    check(L.orb_extract_batch(ex._h, ptr(batches[0]), nb, w, h, w, w * h, ptr(k), ptr(d), cap, ptr(c)), "sync again")
+    assert np.array_equal(c, ref[0][2])
