@@ -170,3 +170,29 @@ def test_async_tickets_match_sync_call(pkg):
     k = np.zeros((nb, cap), pkg.KP_DTYPE); d = np.zeros((nb, cap, 32), np.uint8); c = np.zeros(nb, np.int32)
     check(L.orb_extract_batch(ex._h, ptr(batches[0]), nb, w, h, w, w * h, ptr(k), ptr(d), cap, ptr(c)), "sync again")
     assert np.array_equal(c, ref[0][2])
+
+
+def test_threshold_fallback_cells(pkg, po):
+    """Cells with <= 3 corners at fastTh are re-detected at threshold 7 (src/ORBextractor.cc:609-614): low-contrast frames where
+    most cells fall back, huge cells (tiny nfeatures -> one CTA walks a cell wider than its bitmap), and fastTh on both sides of 7."""
+    from orbslam_jpminipc_b200.synth import synth_frame
+    rng = np.random.default_rng(77)
+    base = synth_frame(480, 640, 7100).astype(np.float32)
+    low = np.clip((base - 128.0) * 0.18 + 120.0, 0, 255).astype(np.uint8)            # contrast too low for th=20 almost everywhere
+    mixed = low.copy(); mixed[100:300, 200:500] = base[100:300, 200:500].astype(np.uint8)
+    sparse = np.full((480, 640), 100, np.uint8)
+    for _ in range(40):                                                               # a few isolated bright blobs on a flat frame
+        y, x = int(rng.integers(30, 450)), int(rng.integers(30, 610))
+        sparse[y:y + 3, x:x + 3] = int(rng.integers(110, 140))
+    for img, tag in ((low, "low"), (mixed, "mixed"), (sparse, "sparse")):
+        for nf, th in ((1000, 20), (60, 20), (20, 40), (1000, 7), (1000, 5), (500, 8)):
+            ex = pkg.ORBextractor(nf, 1.2, 8, 1, th, max_width=640, max_height=480, max_batch=1)
+            orc = po.OracleExtractor(nf, 1.2, 8, 1, th)
+            try:
+                rk, rd = orc(img)
+            except Exception:
+                ex.close()
+                continue                              # geometry the reference cannot process either (covered elsewhere)
+            kps, desc = ex(img)
+            _same(kps, desc, rk, rd, (tag, nf, th))
+            ex.close()
