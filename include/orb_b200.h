@@ -218,6 +218,24 @@ int orb_search_by_bow_kf(orb_ctx*, const orb_featvec_view* fv1, const uint8_t* d
                          const uint8_t* valid2, int n2,
                          float nnratio, int check_ori, int32_t* match12, int* nmatches);
 
+/* ---- frame plumbing on either side of the extractor (reference src/Tracking.cc:200-212, src/Frame.cc:289-349) ---- */
+enum { ORB_RGB = 0, ORB_BGR = 1 };
+/* cvtColor(image, im, CV_RGB2GRAY / CV_BGR2GRAY) of Tracking::GrabImage (src/Tracking.cc:202-208) for nimg interleaved 8-bit
+ * 3-channel frames: gray = (R*9798 + G*19235 + B*3735 + 2^14) >> 15 (OpenCV 4.x).  stride / pitch in bytes; host or device. */
+int orb_cvt_gray(orb_ctx*, const uint8_t* src, int nimg, int width, int height, size_t stride, size_t frame_pitch, int order,
+                 uint8_t* dst, size_t dst_stride, size_t dst_pitch);
+/* the colour conversion followed by orb_extract_batch */
+int orb_extract_batch_color(orb_ctx*, const uint8_t* images, int nimg, int width, int height, size_t stride, size_t frame_pitch,
+                            int order, orb_keypoint* kps, uint8_t* desc, int cap, int32_t* counts);
+/* Frame::UndistortKeyPoints (src/Frame.cc:289-320): cv::undistortPoints(pts, pts, mK, mDistCoef, Mat(), mK) on the keypoint
+ * positions, everything else of the keypoint copied; dist = (k1,k2,p1,p2[,k3[,k4,k5,k6[,s1..s4]]]) as CV_32F like mDistCoef;
+ * dist[0] == 0 means no distortion (the copy of :291-295).  In place allowed.  Host or device pointers. */
+int orb_undistort_keypoints(orb_ctx*, const orb_keypoint* kps, int n, float fx, float fy, float cx, float cy, const float* dist,
+                            int ndist, orb_keypoint* kps_un);
+/* Frame::ComputeImageBounds (src/Frame.cc:322-349): bounds = { mnMinX, mnMaxX, mnMinY, mnMaxY } */
+int orb_image_bounds(orb_ctx*, int width, int height, float fx, float fy, float cx, float cy, const float* dist, int ndist,
+                     int32_t bounds[4]);
+
 /* ---- DBoW2 vocabulary tree (ORB descriptors): Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h ----
  * Nodes are given in the order of the reference's text format (loadFromTextFile, :1338-1425): node 0 is the root, node i >= 1
  * has parent[i] < i, a 32-byte descriptor and a weight; children keep file order, nodes without children are the words and get

@@ -1313,4 +1313,67 @@ void orc_bow_score_db(const int32_t* qw, const double* qv, int nq, int nkf, cons
     *max_common = mx;
 }
 
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Frame plumbing: src/Tracking.cc:202-208 (cvtColor), src/Frame.cc:289-349 (undistortPoints).  OpenCV 4.13 arithmetic,
+ * checked against cv2 in tests/test_oracle_frame.py.
+ * ------------------------------------------------------------------------------------------------------------------ */
+void orc_cvt_gray(const uint8_t* src, int w, int h, int stride, int order, uint8_t* dst, int dstride)
+{
+    const int c0 = order ? 3735 : 9798, c2 = order ? 9798 : 3735;
+    for (int y = 0; y < h; y++) {
+        const uint8_t* s = src + (size_t)y * stride;
+        uint8_t* d = dst + (size_t)y * dstride;
+        for (int x = 0; x < w; x++) d[x] = (uint8_t)((s[3 * x] * c0 + s[3 * x + 1] * 19235 + s[3 * x + 2] * c2 + (1 << 14)) >> 15);
+    }
+}
+
+void orc_undistort_points(float* xy, int n, float ffx, float ffy, float fcx, float fcy, const float* dist, int ndist)
+{
+    const double fx = ffx, fy = ffy, cx = fcx, cy = fcy;
+    double k[14] = { 0 };
+    for (int i = 0; i < ndist && i < 14; i++) k[i] = dist[i];
+    const double ifx = 1. / fx, ify = 1. / fy;
+    for (int i = 0; i < n; i++) {
+        double x = xy[2 * i], y = xy[2 * i + 1];
+        const double u = x, v = y;
+        x = (x - cx) * ifx; y = (y - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; j++) {                       /* TermCriteria(MAX_ITER, 5, 0.01): count only */
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+            if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+            const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+            const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        const double xx = fx * x + 0.0 * y + cx, yy = 0.0 * x + fy * y + cy, ww = 1. / (0.0 * x + 0.0 * y + 1.0);
+        xy[2 * i] = (float)(xx * ww); xy[2 * i + 1] = (float)(yy * ww);
+    }
+}
+
+void orc_undistort_keypoints(const orc_keypoint* in, int n, float fx, float fy, float cx, float cy, const float* dist, int ndist,
+                             orc_keypoint* out)
+{
+    for (int i = 0; i < n; i++) out[i] = in[i];
+    if (ndist == 0 || dist[0] == 0.f) return;               /* src/Frame.cc:291-295 */
+    for (int i = 0; i < n; i++) {
+        float p[2] = { in[i].x, in[i].y };
+        orc_undistort_points(p, 1, fx, fy, cx, cy, dist, ndist);
+        out[i].x = p[0]; out[i].y = p[1];
+    }
+}
+
+void orc_image_bounds(int w, int h, float fx, float fy, float cx, float cy, const float* dist, int ndist, int32_t b[4])
+{
+    if (ndist == 0 || dist[0] == 0.f) { b[0] = 0; b[1] = w; b[2] = 0; b[3] = h; return; }
+    float m[8] = { 0.f, 0.f, (float)w, 0.f, 0.f, (float)h, (float)w, (float)h };
+    orc_undistort_points(m, 4, fx, fy, cx, cy, dist, ndist);
+    b[0] = (int32_t)std::min(floorf(m[0]), floorf(m[4]));
+    b[1] = (int32_t)std::max(ceilf(m[2]), ceilf(m[6]));
+    b[2] = (int32_t)std::min(floorf(m[1]), floorf(m[3]));
+    b[3] = (int32_t)std::max(ceilf(m[5]), ceilf(m[7]));
+}
+
 } // extern "C"

@@ -173,6 +173,16 @@ double orc_bow_score_l1(const int32_t* w1, const double* v1, int n1, const int32
 void  orc_bow_score_db(const int32_t* qw, const double* qv, int nq, int nkf, const int32_t* kf_start, const int32_t* kf_word,
                        const double* kf_val, int32_t* common, float* score, int* max_common);
 
+/* ---- frame plumbing ---- */
+/* cvtColor(CV_RGB2GRAY / CV_BGR2GRAY), src/Tracking.cc:202-208; order 0 = RGB, 1 = BGR; OpenCV 4.x 15-bit coefficients */
+void  orc_cvt_gray(const uint8_t* src, int w, int h, int stride, int order, uint8_t* dst, int dstride);
+/* cv::undistortPoints(pts, pts, K, D, Mat(), K) as used by Frame::UndistortKeyPoints / ComputeImageBounds (src/Frame.cc:289-349);
+ * xy: n x 2 floats in/out; dist: ndist CV_32F coefficients */
+void  orc_undistort_points(float* xy, int n, float fx, float fy, float cx, float cy, const float* dist, int ndist);
+void  orc_undistort_keypoints(const orc_keypoint* in, int n, float fx, float fy, float cx, float cy, const float* dist, int ndist,
+                              orc_keypoint* out);
+void  orc_image_bounds(int w, int h, float fx, float fy, float cx, float cy, const float* dist, int ndist, int32_t bounds[4]);
+
 #ifdef __cplusplus
 }
 #endif

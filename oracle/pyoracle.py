@@ -105,6 +105,10 @@ def lib():
         L.orc_bow_score_l1.restype = C.c_double
         L.orc_bow_score_l1.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_bow_score_db.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
+        L.orc_cvt_gray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orc_undistort_points.argtypes = [C.c_void_p, C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_int]
+        L.orc_undistort_keypoints.argtypes = [C.c_void_p, C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_image_bounds.argtypes = [C.c_int, C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_three_maxima.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 3
         _lib = L
     return _lib
@@ -271,14 +275,15 @@ def match_ratio(idx1, d1, d2, nnratio, th):
 class OracleFrame:
     """The slice of ORB_SLAM::Frame the matcher reads (reference src/Frame.cc:56-128)."""
 
-    def __init__(self, kps, desc, w, h, fx, fy, cx, cy, nlevels=8, scale_factor=1.2):
+    def __init__(self, kps, desc, w, h, fx, fy, cx, cy, nlevels=8, scale_factor=1.2, bounds=None):
         self.kps = np.ascontiguousarray(kps, KP_DTYPE)
         self.desc = np.ascontiguousarray(desc, np.uint8)
         self.n = len(self.kps)
         self.cell_start = np.zeros(64 * 48 + 1, np.int32)
         self.cell_items = np.zeros(max(self.n, 1), np.int32)
-        lib().orc_frame_grid(_p(self.kps), self.n, 0, w, 0, h, _p(self.cell_start), _p(self.cell_items))
-        self.c = _Frame(self.n, self.kps.ctypes.data, self.desc.ctypes.data, fx, fy, cx, cy, 0, w, 0, h,
+        b = (0, w, 0, h) if bounds is None else tuple(int(v) for v in bounds)
+        lib().orc_frame_grid(_p(self.kps), self.n, b[0], b[1], b[2], b[3], _p(self.cell_start), _p(self.cell_items))
+        self.c = _Frame(self.n, self.kps.ctypes.data, self.desc.ctypes.data, fx, fy, cx, cy, b[0], b[1], b[2], b[3],
                         nlevels, scale_factor, self.cell_start.ctypes.data, self.cell_items.ctypes.data)
 
     def features_in_area(self, x, y, r, min_level=-1, max_level=-1):
@@ -464,3 +469,33 @@ def bow_score_db(query, kf_bows):
     mx = C.c_int(0)
     lib().orc_bow_score_db(_p(qw), _p(qv), len(qw), len(kf_bows), _p(start), _p(words), _p(vals), _p(common), _p(score), C.addressof(mx))
     return common, score, mx.value
+
+
+def cvt_gray(img, order=0):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape[:2]
+    out = np.zeros((h, w), np.uint8)
+    lib().orc_cvt_gray(_p(img), w, h, img.strides[0], order, _p(out), w)
+    return out
+
+
+def undistort_points(xy, K, dist):
+    xy = np.ascontiguousarray(xy, np.float32).copy()
+    d = np.ascontiguousarray(dist, np.float32)
+    lib().orc_undistort_points(_p(xy), len(xy), K[0], K[1], K[2], K[3], _p(d), len(d))
+    return xy
+
+
+def undistort_keypoints(kps, K, dist):
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    out = np.zeros_like(kps)
+    d = np.ascontiguousarray(dist, np.float32)
+    lib().orc_undistort_keypoints(_p(kps), len(kps), K[0], K[1], K[2], K[3], _p(d), len(d), _p(out))
+    return out
+
+
+def image_bounds(w, h, K, dist):
+    d = np.ascontiguousarray(dist, np.float32)
+    b = np.zeros(4, np.int32)
+    lib().orc_image_bounds(w, h, K[0], K[1], K[2], K[3], _p(d), len(d), _p(b))
+    return b

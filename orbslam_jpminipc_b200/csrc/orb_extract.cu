@@ -977,16 +977,20 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         cudaMemsetAsync(W.d_counters + 2, 0, sizeof(int), bs);
         k_blur<<<grid, 256, 0, bs>>>(W.tm_blur, W.d_blur, fb, c->d_plan, c->d_tiles_blur, P.ntiles_blur, total, W.d_counters + 2);
     };
-    if (fork && c->fork_early) {          // blur next to FAST: FAST saturates the ALU pipe and leaves the FMA pipe idle
+    if (fork && c->fork_early == 1) {          // blur next to FAST: FAST saturates the ALU pipe and leaves the FMA pipe idle
         ORB_CUDA(cudaEventRecord(W.ev_fork, s));
         ORB_CUDA(cudaStreamWaitEvent(W.aux_stream, W.ev_fork, 0));
     }
     mark();
     {
         const int total = P.ntiles_fast * nimg;
-        const int grid = std::min(total, c->num_sms * (fork && c->fork_early ? c->fast_ctas : FAST_CTAS));
+        const int grid = std::min(total, c->num_sms * (fork && c->fork_early == 1 ? c->fast_ctas : FAST_CTAS));
         cudaMemsetAsync(W.d_counters + 1, 0, sizeof(int), s);
         k_fast_nms<<<grid, FAST_THREADS, 0, s>>>(W.tm_fast, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total, W.d_counters + 1);
+    }
+    if (fork && c->fork_early == 2) {     // blur starts behind FAST, next to compaction + selection
+        ORB_CUDA(cudaEventRecord(W.ev_fork, s));
+        ORB_CUDA(cudaStreamWaitEvent(W.aux_stream, W.ev_fork, 0));
     }
     if (fork && c->fork_early) { launch_blur(W.aux_stream); ORB_CUDA(cudaEventRecord(W.ev_join, W.aux_stream)); }
     mark();

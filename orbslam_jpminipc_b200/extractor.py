@@ -37,6 +37,48 @@ class ORBextractor:
     def GetScaleFactor(self):
         return lib().orb_scale_factor(self._h)
 
+    # ---- frame plumbing around the extractor (reference src/Tracking.cc:200-212, src/Frame.cc:289-349)
+    def cvt_gray(self, images, order="RGB"):
+        """cvtColor(RGB2GRAY / BGR2GRAY) of Tracking::GrabImage for an (N,)H x W x 3 uint8 array."""
+        from ._lib import check, ptr
+        a = np.ascontiguousarray(images, np.uint8)
+        single = a.ndim == 3
+        if single:
+            a = a[None]
+        n, h, w, _ = a.shape
+        out = np.zeros((n, h, w), np.uint8)
+        check(lib().orb_cvt_gray(self._h, ptr(a), n, w, h, a.strides[1], a.strides[0], 0 if order == "RGB" else 1, ptr(out), w, w * h),
+              "orb_cvt_gray")
+        return out[0] if single else out
+
+    def extract_color(self, image, order="RGB"):
+        """Colour frame -> (keypoints, descriptors), like GrabImage + Frame::Frame."""
+        from ._lib import check, ptr
+        a = np.ascontiguousarray(image, np.uint8)
+        h, w, _ = a.shape
+        kps = np.zeros(self.capacity, KP_DTYPE); desc = np.zeros((self.capacity, 32), np.uint8); cnt = np.zeros(1, np.int32)
+        check(lib().orb_extract_batch_color(self._h, ptr(a), 1, w, h, a.strides[0], a.strides[0] * h, 0 if order == "RGB" else 1,
+                                            ptr(kps), ptr(desc), self.capacity, ptr(cnt)), "orb_extract_batch_color")
+        return kps[:cnt[0]].copy(), desc[:cnt[0]].copy()
+
+    def undistort_keypoints(self, kps, K, dist):
+        """Frame::UndistortKeyPoints: K = (fx, fy, cx, cy), dist = (k1, k2, p1, p2[, k3 ...]) float32."""
+        from ._lib import check, ptr
+        kps = np.ascontiguousarray(kps, KP_DTYPE)
+        d = np.ascontiguousarray(dist, np.float32)
+        out = np.zeros_like(kps)
+        check(lib().orb_undistort_keypoints(self._h, ptr(kps), len(kps), K[0], K[1], K[2], K[3], ptr(d), len(d), ptr(out)),
+              "orb_undistort_keypoints")
+        return out
+
+    def image_bounds(self, w, h, K, dist):
+        """Frame::ComputeImageBounds -> (mnMinX, mnMaxX, mnMinY, mnMaxY)."""
+        from ._lib import check, ptr
+        d = np.ascontiguousarray(dist, np.float32)
+        b = np.zeros(4, np.int32)
+        check(lib().orb_image_bounds(self._h, w, h, K[0], K[1], K[2], K[3], ptr(d), len(d), ptr(b)), "orb_image_bounds")
+        return b
+
     def extract_batch_async(self, images, kps, desc, counts):
         """Enqueue a batch (uint8 array N x H x W, ideally pinned) into caller-owned output arrays (N x capacity keypoints,
         N x capacity x 32 descriptors, N counts) and return a ticket for wait(); see orb_extract_batch_async."""

@@ -14,7 +14,7 @@ class Frame:
     """Keypoints + descriptors + the 64x48 lookup grid (src/Frame.cc:109-123), zero distortion
     (mvKeysUn == mvKeys, image bounds = image rectangle, src/Frame.cc:291-295,:342-348)."""
 
-    def __init__(self, ctx, kps, desc, width, height, fx, fy, cx, cy, nlevels=8, scale_factor=1.2):
+    def __init__(self, ctx, kps, desc, width, height, fx, fy, cx, cy, nlevels=8, scale_factor=1.2, bounds=None):
         self.kps = np.ascontiguousarray(kps, KP_DTYPE)
         self.desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
         self.N = len(self.kps)
@@ -23,13 +23,15 @@ class Frame:
         self.nlevels, self.scale_factor = nlevels, scale_factor
         self.cell_start = np.zeros(GRID_COLS * GRID_ROWS + 1, np.int32)
         self.cell_items = np.zeros(max(self.N, 1), np.int32)
+        # mnMinX, mnMaxX, mnMinY, mnMaxY: the image rectangle, or Frame::ComputeImageBounds for a distorted camera
+        self.bounds = (0, width, 0, height) if bounds is None else tuple(int(v) for v in bounds)
         h = ctx._h if hasattr(ctx, "_h") else ctx
-        check(lib().orb_frame_grid_build(h, ptr(self.kps), self.N, 0, width, 0, height,
+        check(lib().orb_frame_grid_build(h, ptr(self.kps), self.N, self.bounds[0], self.bounds[1], self.bounds[2], self.bounds[3],
                                          ptr(self.cell_start), ptr(self.cell_items)), "orb_frame_grid_build")
 
     def view(self):
         return FrameView(self.N, self.kps.ctypes.data, self.desc.ctypes.data, self.fx, self.fy, self.cx, self.cy,
-                         0, self.width, 0, self.height, self.nlevels, self.scale_factor,
+                         self.bounds[0], self.bounds[1], self.bounds[2], self.bounds[3], self.nlevels, self.scale_factor,
                          self.cell_start.ctypes.data, self.cell_items.ctypes.data)
 
 
