@@ -218,6 +218,13 @@ int orb_search_by_bow_kf(orb_ctx*, const orb_featvec_view* fv1, const uint8_t* d
                          const uint8_t* valid2, int n2,
                          float nnratio, int check_ori, int32_t* match12, int* nmatches);
 
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:185-250) for npoints map points at once: point p owns the observation
+ * descriptors desc[start[p] .. start[p+1]) (32 bytes each, in the order of its observation map); best_idx[p] = index within the
+ * group of the descriptor with the least median distance to the others (first on ties, -1 for an empty group), best_median[p] =
+ * that median.  Host or device pointers. */
+int orb_distinctive_descriptors(orb_ctx*, const uint8_t* desc, const int32_t* start, int npoints, int32_t* best_idx,
+                                int32_t* best_median);
+
 /* ---- frame plumbing on either side of the extractor (reference src/Tracking.cc:200-212, src/Frame.cc:289-349) ---- */
 enum { ORB_RGB = 0, ORB_BGR = 1 };
 /* cvtColor(image, im, CV_RGB2GRAY / CV_BGR2GRAY) of Tracking::GrabImage (src/Tracking.cc:202-208) for nimg interleaved 8-bit

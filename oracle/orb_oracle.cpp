@@ -1376,4 +1376,32 @@ void orc_image_bounds(int w, int h, float fx, float fy, float cx, float cy, cons
     b[3] = (int32_t)std::max(ceilf(m[5]), ceilf(m[7]));
 }
 
+
+/* src/MapPoint.cc:214-242 */
+void orc_distinctive_descriptors(const uint8_t* desc, const int32_t* start, int npoints, int32_t* best_idx, int32_t* best_median)
+{
+    for (int p = 0; p < npoints; p++) {
+        const int N = start[p + 1] - start[p];
+        best_idx[p] = -1; best_median[p] = INT_MAX;
+        if (N <= 0) continue;
+        const uint8_t* d = desc + (size_t)start[p] * 32;
+        std::vector<float> D((size_t)N * N);
+        for (int i = 0; i < N; i++) {
+            D[(size_t)i * N + i] = 0;
+            for (int j = i + 1; j < N; j++) {
+                const int dij = orc_descriptor_distance(d + (size_t)i * 32, d + (size_t)j * 32);
+                D[(size_t)i * N + j] = (float)dij; D[(size_t)j * N + i] = (float)dij;
+            }
+        }
+        int BestMedian = INT_MAX, BestIdx = 0;
+        for (int i = 0; i < N; i++) {
+            std::vector<int> v(D.begin() + (size_t)i * N, D.begin() + (size_t)(i + 1) * N);
+            std::sort(v.begin(), v.end());
+            const int median = v[(size_t)(0.5 * (N - 1))];
+            if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+        }
+        best_idx[p] = BestIdx; best_median[p] = BestMedian;
+    }
+}
+
 } // extern "C"

@@ -183,6 +183,10 @@ void  orc_undistort_keypoints(const orc_keypoint* in, int n, float fx, float fy,
                               orc_keypoint* out);
 void  orc_image_bounds(int w, int h, float fx, float fy, float cx, float cy, const float* dist, int ndist, int32_t bounds[4]);
 
+/* MapPoint::ComputeDistinctiveDescriptors, src/MapPoint.cc:185-250, for npoints map points at once: point p owns the observation
+ * descriptors desc[start[p] .. start[p+1]); best_idx[p] = BestIdx within its group (-1 for an empty group), best_median[p] = BestMedian */
+void  orc_distinctive_descriptors(const uint8_t* desc, const int32_t* start, int npoints, int32_t* best_idx, int32_t* best_median);
+
 #ifdef __cplusplus
 }
 #endif

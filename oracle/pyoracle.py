@@ -109,6 +109,7 @@ def lib():
         L.orc_undistort_points.argtypes = [C.c_void_p, C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_int]
         L.orc_undistort_keypoints.argtypes = [C.c_void_p, C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_image_bounds.argtypes = [C.c_int, C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_distinctive_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_three_maxima.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 3
         _lib = L
     return _lib
@@ -499,3 +500,12 @@ def image_bounds(w, h, K, dist):
     b = np.zeros(4, np.int32)
     lib().orc_image_bounds(w, h, K[0], K[1], K[2], K[3], _p(d), len(d), _p(b))
     return b
+
+
+def distinctive_descriptors(desc, start):
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    start = np.ascontiguousarray(start, np.int32)
+    n = len(start) - 1
+    bi = np.zeros(n, np.int32); bm = np.zeros(n, np.int32)
+    lib().orc_distinctive_descriptors(_p(desc), _p(start), n, _p(bi), _p(bm))
+    return bi, bm

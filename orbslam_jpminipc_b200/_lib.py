@@ -26,7 +26,7 @@ EXPORTS = [
     "orb_hamming_knn2", "orb_hamming_knn2_device", "orb_knn2_merge_device", "orb_match_ratio",
     "orb_frame_grid_build", "orb_search_by_projection", "orb_search_window", "orb_search_for_initialization", "orb_search_by_bow", "orb_search_by_bow_kf", "orb_host_alloc", "orb_host_free",
     "orb_measure_popc_peak",
-    "orb_cvt_gray", "orb_extract_batch_color", "orb_undistort_keypoints", "orb_image_bounds",
+    "orb_distinctive_descriptors", "orb_cvt_gray", "orb_extract_batch_color", "orb_undistort_keypoints", "orb_image_bounds",
     "orb_vocab_create", "orb_vocab_load_text", "orb_vocab_destroy", "orb_vocab_info", "orb_vocab_transform_features",
     "orb_vocab_transform_batch", "orb_bow_score_db",
 ]
@@ -112,6 +112,7 @@ def lib():
     L.orb_host_alloc.argtypes = [sz]
     L.orb_host_free.argtypes = [vp]
     L.orb_measure_popc_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.orb_distinctive_descriptors.argtypes = [vp, vp, vp, i32, vp, vp]
     L.orb_cvt_gray.argtypes = [vp, vp, i32, i32, i32, sz, sz, i32, vp, sz, sz]
     L.orb_extract_batch_color.argtypes = [vp, vp, i32, i32, i32, sz, sz, i32, vp, vp, i32, vp]
     L.orb_undistort_keypoints.argtypes = [vp, vp, i32, f32, f32, f32, f32, vp, i32, vp]

@@ -799,6 +799,41 @@ int orb_search_for_initialization(orb_ctx* c, const orb_frame_view* f1, const or
     return res[1] ? ORB_ERR_CAPACITY : ORB_OK;
 }
 
+int orb_distinctive_descriptors(orb_ctx* c, const uint8_t* desc, const int32_t* start, int npoints, int32_t* best_idx, int32_t* best_median)
+{
+    if (!c || npoints < 0) return ORB_ERR_INVALID;
+    if (npoints == 0) return ORB_OK;
+    if (!start || !best_idx || !best_median) return ORB_ERR_INVALID;
+    ORB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->streams[0];
+    const bool dev = is_device_ptr(start);
+    if (is_device_ptr(best_idx) != dev || is_device_ptr(best_median) != dev) return ORB_ERR_INVALID;
+    int total = 0;
+    if (dev) ORB_CUDA(cudaMemcpy(&total, start + npoints, 4, cudaMemcpyDeviceToHost)); else total = start[npoints];
+    if (total < 0 || (total > 0 && (!desc || is_device_ptr(desc) != dev))) return ORB_ERR_INVALID;
+    if (dev) {
+        const int rc = orb_launch_distinctive(desc, start, npoints, best_idx, best_median, s);
+        if (rc) return rc;
+        ORB_CUDA(cudaStreamSynchronize(s));
+        return ORB_OK;
+    }
+    for (int p = 0; p < npoints; p++) if (start[p + 1] < start[p]) return ORB_ERR_INVALID;
+    const size_t P = (size_t)npoints, in_bytes = al256((size_t)total * 32 + 32) + al256((P + 1) * 4);
+    int rc = match_scratch(c, 256 + in_bytes + 2 * al256(P * 4), 256 + in_bytes);
+    if (rc) return rc;
+    Bump b(c->d_match_scratch, c->h_match_arena, c->match_scratch_bytes);
+    const uint8_t* d_desc = desc; const int32_t* d_start = start;
+    if ((rc = stage_in(b, false, d_desc, (size_t)total * 32, s)) || (rc = stage_in(b, false, d_start, P + 1, s))) return rc;
+    int32_t* d_bi = (int32_t*)b.take(P * 4);
+    int32_t* d_bm = (int32_t*)b.take(P * 4);
+    if ((rc = b.flush(s))) return rc;
+    if ((rc = orb_launch_distinctive(total ? d_desc : nullptr, d_start, npoints, d_bi, d_bm, s))) return rc;
+    ORB_CUDA(cudaMemcpyAsync(best_idx, d_bi, P * 4, cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaMemcpyAsync(best_median, d_bm, P * 4, cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaStreamSynchronize(s));
+    return ORB_OK;
+}
+
 } // extern "C"
 
 // shared body of SearchByBoW(KF, Frame) and SearchByBoW(KF, KF): the latter adds the validity of the second side's map

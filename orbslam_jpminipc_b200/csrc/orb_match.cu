@@ -1024,6 +1024,58 @@ int orb_launch_search_window(orb_ctx* c, const orb_frame_view* tgt, const orb_wi
     return ORB_OK;
 }
 
+// ------------------------------------------------------------------ MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:185-250)
+// One CTA of 64 threads per map point.  Row i's median is the k-th smallest (k = (int)(0.5*(N-1)), :236) of its N distances, found
+// by bisection on the value (distances are 0..256): 9 counting passes that recompute the distances from the descriptors in shared
+// memory, so N is unbounded and nothing but the descriptors is stored.  BestIdx = first row with the smallest median (:238).
+constexpr int DD_THREADS = 64, DD_SMEM_DESC = 512;          // descriptors staged in shared memory; larger groups read global memory
+__global__ void __launch_bounds__(DD_THREADS)
+k_distinctive(const uint8_t* __restrict__ desc, const int32_t* __restrict__ start, int32_t* __restrict__ best_idx,
+              int32_t* __restrict__ best_median)
+{
+    __shared__ uint4 sd[DD_SMEM_DESC * 2];
+    __shared__ unsigned long long s_best;
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const int s0 = start[p], N = start[p + 1] - s0;
+    if (N <= 0) { if (tid == 0) { best_idx[p] = -1; best_median[p] = INT_MAX; } return; }
+    const uint4* gd = reinterpret_cast<const uint4*>(desc + (size_t)s0 * 32);
+    const bool in_smem = N <= DD_SMEM_DESC;
+    if (in_smem) for (int i = tid; i < 2 * N; i += DD_THREADS) sd[i] = __ldg(gd + i);
+    if (tid == 0) s_best = ~0ull;
+    __syncthreads();
+    const uint4* D = in_smem ? sd : gd;
+    const int k = (int)(0.5 * (double)(N - 1));
+    unsigned long long mine = ~0ull;
+    for (int i = tid; i < N; i += DD_THREADS) {
+        const uint4 a = D[2 * i], b = D[2 * i + 1];
+        int lo = 0, hi = 256;                                   // smallest v with #(d <= v) > k
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            int cnt = 0;
+            for (int j = 0; j < N; j++) {
+                const uint4 c = D[2 * j], e = D[2 * j + 1];
+                const int dist = __popc(a.x ^ c.x) + __popc(a.y ^ c.y) + __popc(a.z ^ c.z) + __popc(a.w ^ c.w) +
+                                 __popc(b.x ^ e.x) + __popc(b.y ^ e.y) + __popc(b.z ^ e.z) + __popc(b.w ^ e.w);
+                cnt += dist <= mid;
+            }
+            if (cnt > k) hi = mid; else lo = mid + 1;
+        }
+        mine = min(mine, ((unsigned long long)lo << 32) | (unsigned)i);       // rows ascend per thread: the first minimum survives
+    }
+    atomicMin(&s_best, mine);
+    __syncthreads();
+    if (tid == 0) { best_idx[p] = (int32_t)(s_best & 0xffffffffu); best_median[p] = (int32_t)(s_best >> 32); }
+}
+
+int orb_launch_distinctive(const uint8_t* d_desc, const int32_t* d_start, int npoints, int32_t* d_best_idx, int32_t* d_best_median,
+                           cudaStream_t s)
+{
+    if (npoints <= 0) return ORB_OK;
+    k_distinctive<<<npoints, DD_THREADS, 0, s>>>(d_desc, d_start, d_best_idx, d_best_median);
+    ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
+}
+
 size_t orb_init_scratch_bytes(int n1, int n2)
 {
     const size_t cap = (size_t)std::min(n2, 1024);

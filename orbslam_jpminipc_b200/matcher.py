@@ -173,6 +173,16 @@ class ORBmatcher:
         return self._search_window(CurrentFrame, n, active, mp_desc, None, None, xyz, Tcw, 1, radius, 0.0, lv - 1, lv + 1, kf_angle,
                                    self.ACCEPT_BEST, int(ORBdist), self.mbCheckOrientation, match_cur)
 
+    def ComputeDistinctiveDescriptors(self, desc, start):
+        """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:185-250) for many map points: desc = all observation descriptors,
+        start = CSR offsets per point.  Returns (BestIdx within each group or -1, BestMedian)."""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        start = np.ascontiguousarray(start, np.int32)
+        n = len(start) - 1
+        bi = np.zeros(n, np.int32); bm = np.zeros(n, np.int32)
+        check(lib().orb_distinctive_descriptors(self._h, ptr(desc), ptr(start), n, ptr(bi), ptr(bm)), "orb_distinctive_descriptors")
+        return bi, bm
+
     def SearchByBoW(self, kf_featvec, kf_desc, kf_kps, kf_mp_valid, f_featvec, f_desc, f_kps):
         """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) scoring (src/ORBmatcher.cc:155-284).
         featvec = (node_id, start, items) CSR arrays.  Returns (nmatches, match_f)."""

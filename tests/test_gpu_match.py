@@ -424,3 +424,30 @@ def test_search_for_initialization_empty(pkg):
     assert n == 0 and (m12 == -1).all()
     n, m12, _ = m.SearchForInitialization(E, F, np.zeros((0, 2), np.float32), 50)
     assert n == 0 and len(m12) == 0
+
+
+@pytest.mark.parametrize("npoints,maxobs,seed", [(2000, 12, 1), (300, 70, 2), (5, 700, 3), (50, 1, 4)])
+def test_distinctive_descriptors_vs_oracle(pkg, po, npoints, maxobs, seed):
+    """MapPoint::ComputeDistinctiveDescriptors, src/MapPoint.cc:185-250 (batched over map points; groups of 0, 1, 2 and many
+    observations, duplicates for ties, one group larger than the shared-memory staging)."""
+    rng = np.random.default_rng(seed)
+    m = pkg.ORBmatcher(0.6, True)
+    sizes = rng.integers(0, maxobs + 1, npoints)
+    sizes[:3] = [0, 1, 2][:min(3, npoints)]
+    start = np.zeros(npoints + 1, np.int32); start[1:] = np.cumsum(sizes)
+    base = rng.integers(0, 256, (npoints, 32), dtype=np.uint8)
+    desc = np.zeros((start[-1], 32), np.uint8)
+    for p in range(npoints):
+        n = sizes[p]
+        if n == 0:
+            continue
+        bits = np.unpackbits(np.repeat(base[p][None], n, 0), axis=1)
+        bits ^= rng.random(bits.shape) < rng.uniform(0.0, 0.2)
+        d = np.packbits(bits, axis=1)
+        if n > 3:
+            d[n // 2] = d[0]                                # exact duplicates -> tied medians
+        desc[start[p]:start[p + 1]] = d
+    bi, bm = m.ComputeDistinctiveDescriptors(desc, start)
+    rbi, rbm = po.distinctive_descriptors(desc, start)
+    assert np.array_equal(bi, rbi) and np.array_equal(bm, rbm)
+    assert bi[0] == -1 and (bi[1:3] == 0).all()
