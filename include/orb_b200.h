@@ -243,6 +243,17 @@ int orb_undistort_keypoints(orb_ctx*, const orb_keypoint* kps, int n, float fx, 
 int orb_image_bounds(orb_ctx*, int width, int height, float fx, float fy, float cx, float cy, const float* dist, int ndist,
                      int32_t bounds[4]);
 
+/* ---- the fork's binary dumps (include/SaveLoadWorld.h:1408-1459) as database files; host-side file I/O, no GPU involved ----
+ * Descriptor file: per keyframe { 0xEB 0x90, int32 n, n x 32 bytes }; keypoint file: { 0xEB 0x90, size_t n, n x 28-byte KeyPoint }.
+ * Readers concatenate the rows of all records; rec_start (may be NULL) receives the nrecords+1 row offsets of the keyframes.
+ * Call with rows == NULL to size the buffers (returns the totals); ORB_ERR_CAPACITY if a buffer is too small (totals still set). */
+int orb_db_read_descriptors(const char* path, uint8_t* desc, int64_t cap_rows, int32_t* rec_start, int cap_records, int64_t* nrows,
+                            int32_t* nrecords);
+int orb_db_write_descriptors(const char* path, const uint8_t* desc, const int32_t* rec_start, int nrecords);
+int orb_db_read_keypoints(const char* path, orb_keypoint* kps, int64_t cap_rows, int32_t* rec_start, int cap_records, int64_t* nrows,
+                          int32_t* nrecords);
+int orb_db_write_keypoints(const char* path, const orb_keypoint* kps, const int32_t* rec_start, int nrecords);
+
 /* ---- DBoW2 vocabulary tree (ORB descriptors): Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h ----
  * Nodes are given in the order of the reference's text format (loadFromTextFile, :1338-1425): node 0 is the root, node i >= 1
  * has parent[i] < i, a 32-byte descriptor and a weight; children keep file order, nodes without children are the words and get

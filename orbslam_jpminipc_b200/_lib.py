@@ -27,6 +27,7 @@ EXPORTS = [
     "orb_frame_grid_build", "orb_search_by_projection", "orb_search_window", "orb_search_for_initialization", "orb_search_by_bow", "orb_search_by_bow_kf", "orb_host_alloc", "orb_host_free",
     "orb_measure_popc_peak",
     "orb_distinctive_descriptors", "orb_cvt_gray", "orb_extract_batch_color", "orb_undistort_keypoints", "orb_image_bounds",
+    "orb_db_read_descriptors", "orb_db_write_descriptors", "orb_db_read_keypoints", "orb_db_write_keypoints",
     "orb_vocab_create", "orb_vocab_load_text", "orb_vocab_destroy", "orb_vocab_info", "orb_vocab_transform_features",
     "orb_vocab_transform_batch", "orb_bow_score_db",
 ]
@@ -117,6 +118,10 @@ def lib():
     L.orb_extract_batch_color.argtypes = [vp, vp, i32, i32, i32, sz, sz, i32, vp, vp, i32, vp]
     L.orb_undistort_keypoints.argtypes = [vp, vp, i32, f32, f32, f32, f32, vp, i32, vp]
     L.orb_image_bounds.argtypes = [vp, i32, i32, f32, f32, f32, f32, vp, i32, vp]
+    L.orb_db_read_descriptors.argtypes = [C.c_char_p, vp, i64, vp, i32, C.POINTER(i64), C.POINTER(C.c_int32)]
+    L.orb_db_read_keypoints.argtypes = [C.c_char_p, vp, i64, vp, i32, C.POINTER(i64), C.POINTER(C.c_int32)]
+    L.orb_db_write_descriptors.argtypes = [C.c_char_p, vp, vp, i32]
+    L.orb_db_write_keypoints.argtypes = [C.c_char_p, vp, vp, i32]
     L.orb_vocab_create.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, C.POINTER(vp)]
     L.orb_vocab_load_text.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.orb_vocab_destroy.restype = None
