@@ -41,7 +41,7 @@ enum {
     ORB_ERR_GEOMETRY = -2,     /* cell grid the reference itself cannot process (it throws / divides by 0) */
     ORB_ERR_CAPACITY = -3,     /* caller buffer or context limit (max_w/max_h/max_batch/cap) too small */
     ORB_ERR_CUDA = -4,         /* CUDA runtime error or no device; details via orb_last_cuda_error */
-    ORB_ERR_UNSUPPORTED = -5   /* e.g. HARRIS_SCORE (src/ORBextractor.cc:616-620, off the accelerated path) */
+    ORB_ERR_UNSUPPORTED = -5   /* an option outside the accelerated path (e.g. a tilted-sensor distortion model, a non-L1 vocabulary score) */
 };
 enum { ORB_HARRIS_SCORE = 0, ORB_FAST_SCORE = 1 };   /* include/ORBextractor.h:37 */
 

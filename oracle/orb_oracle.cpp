@@ -387,6 +387,27 @@ orc_extractor* orc_extractor_create(int nfeatures, float scale_factor, int nleve
 
 void orc_extractor_destroy(orc_extractor* e) { delete e; }
 
+/* HarrisResponses(img, pts, 7, HARRIS_K), src/ORBextractor.cc:79-120, for one keypoint at (x, y) of the image whose origin is img */
+static float harris_response(const uint8_t* img, int step, int x, int y)
+{
+    const int blockSize = 7, r = blockSize / 2;
+    const float harris_k = 0.04f;                                   /* HARRIS_K, :73 */
+    float scale = (1 << 2) * blockSize * 255.0f;
+    scale = 1.0f / scale;
+    const float scale_sq_sq = scale * scale * scale * scale;
+    const uint8_t* ptr0 = img + (ptrdiff_t)(y - r) * step + (x - r);
+    int a = 0, b = 0, c = 0;
+    for (int i = 0; i < blockSize; i++)
+        for (int j = 0; j < blockSize; j++) {
+            const uint8_t* ptr = ptr0 + (ptrdiff_t)i * step + j;
+            const int Ix = (ptr[1] - ptr[-1]) * 2 + (ptr[-step + 1] - ptr[-step - 1]) + (ptr[step + 1] - ptr[step - 1]);
+            const int Iy = (ptr[step] - ptr[-step]) * 2 + (ptr[step - 1] - ptr[-step - 1]) + (ptr[step + 1] - ptr[-step + 1]);
+            a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
+        }
+    return ((float)a * b - (float)c * c - harris_k * ((float)a + b) * ((float)a + b)) * scale_sq_sq;
+}
+float orc_harris_response(const uint8_t* img, int stride, int x, int y) { return harris_response(img, stride, x, y); }
+
 int orc_extract(orc_extractor* e, const uint8_t* img, int w, int h, int stride,
                 orc_keypoint* kps, uint8_t* desc, int cap, int* n)
 {
@@ -465,7 +486,8 @@ int orc_extract(orc_extractor* e, const uint8_t* img, int w, int h, int stride,
                 std::vector<KP>& kc = cellKeyPoints[i][j];
                 fast9_nms(cellImage, x1 - x0, y1 - y0, L.stride, e->fastTh, kc);      /* :607 */
                 if (kc.size() <= 3) { kc.clear(); fast9_nms(cellImage, x1 - x0, y1 - y0, L.stride, 7, kc); } /* :609-614 */
-                /* HARRIS_SCORE (:616-620) is not on the accelerated path */
+                if (e->scoreType == 0)                                                   /* HARRIS_SCORE, :616-620 */
+                    for (KP& k : kc) k.response = harris_response(cellImage, L.stride, (int)k.x, (int)k.y);
                 for (size_t k = 0; k < kc.size(); k++) {
                     L.candCell.push_back(i * levelCols + j); L.candX.push_back((int)kc[k].x);
                     L.candY.push_back((int)kc[k].y); L.candScore.push_back((int)kc[k].response);

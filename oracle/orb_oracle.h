@@ -69,6 +69,8 @@ void  orc_gaussian_blur7(const uint8_t* src_padded_roi, int w, int h, int stride
 void  orc_nth_element_desc(float* resp, int32_t* idx, int n, int nth);
 /* KeyPointsFilter::retainBest + the reference's resize(n): returns new count */
 int   orc_retain_best(float* resp, int32_t* idx, int n, int npoints);
+/* HarrisResponses(img, pts, 7, 0.04f) for one point, src/ORBextractor.cc:79-120 */
+float orc_harris_response(const uint8_t* img, int stride, int x, int y);
 float orc_ic_angle(const uint8_t* center, int stride);
 void  orc_rbrief(const uint8_t* center, int stride, float angle_deg, uint8_t* desc32);
 

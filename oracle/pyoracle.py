@@ -110,6 +110,8 @@ def lib():
         L.orc_undistort_keypoints.argtypes = [C.c_void_p, C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_image_bounds.argtypes = [C.c_int, C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_distinctive_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_harris_response.restype = C.c_float
+        L.orc_harris_response.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.orc_three_maxima.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 3
         _lib = L
     return _lib
@@ -509,3 +511,8 @@ def distinctive_descriptors(desc, start):
     bi = np.zeros(n, np.int32); bm = np.zeros(n, np.int32)
     lib().orc_distinctive_descriptors(_p(desc), _p(start), n, _p(bi), _p(bm))
     return bi, bm
+
+
+def harris_response(img, x, y):
+    img = np.ascontiguousarray(img, np.uint8)
+    return lib().orc_harris_response(_p(img), img.strides[0], int(x), int(y))

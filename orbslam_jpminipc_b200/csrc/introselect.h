@@ -27,6 +27,17 @@ struct KeyGreater {
     ORB_HD bool operator()(T a, T b) const { return (a >> SHIFT) > (b >> SHIFT); }
 };
 
+// HARRIS_SCORE: the key in the high 32 bits is an IEEE float (Harris responses may be negative)
+struct FloatKeyGreater64 {
+    ORB_HD static float key(unsigned long long a)
+    {
+        union { uint32_t u; float f; } c;
+        c.u = (uint32_t)(a >> 32);
+        return c.f;
+    }
+    ORB_HD bool operator()(unsigned long long a, unsigned long long b) const { return key(a) > key(b); }
+};
+
 template <typename T>
 ORB_HD void swp(T* v, int a, int b) { T t = v[a]; v[a] = v[b]; v[b] = t; }
 

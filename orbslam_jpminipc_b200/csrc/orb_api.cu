@@ -128,6 +128,7 @@ static int prepare_ws(orb_ctx* c, WorkSet& W, int nimg)
     rc = ensure(W.d_blur, W.blur_bytes, B * P.frame_bytes); if (rc) return rc;
     rc = ensure(W.d_bitmap, W.bitmap_bytes, B * (size_t)std::max(P.bm_total, 256)); if (rc) return rc;
     rc = ensure(W.d_cand, W.cand_bytes, B * (size_t)P.cand_total * 4); if (rc) return rc;
+    if (P.harris) { rc = ensure(W.d_cand64, W.cand64_bytes, B * (size_t)P.cand_total * 8); if (rc) return rc; }
     rc = ensure(W.d_ntotal, W.ntotal_bytes, B * (size_t)P.ncells * 4); if (rc) return rc;
     rc = ensure(W.d_lvl, W.lvl_bytes, B * (size_t)P.lvl_total * 8); if (rc) return rc;
     rc = ensure(W.d_nkept, W.nkept_bytes, B * ORB_MAX_LEVELS * sizeof(int)); if (rc) return rc;
@@ -167,8 +168,8 @@ orb_ctx* orb_create(int device, int nfeatures, float scale_factor, int nlevels, 
         cudaGetLastError();
         return nullptr;
     }
-    if (score_type != ORB_FAST_SCORE || max_w < 1 || max_h < 1 || max_batch < 1 || fast_th < 1 || fast_th > 254) {
-        g_last_cuda_error = "orb_create: invalid or unsupported argument (HARRIS_SCORE is not accelerated)";
+    if ((score_type != ORB_FAST_SCORE && score_type != ORB_HARRIS_SCORE) || max_w < 1 || max_h < 1 || max_batch < 1 || fast_th < 1 || fast_th > 254) {
+        g_last_cuda_error = "orb_create: invalid argument";
         return nullptr;
     }
     if (cudaSetDevice(device) != cudaSuccess) { orb_cuda_fail(cudaGetLastError(), "cudaSetDevice"); return nullptr; }
@@ -201,7 +202,7 @@ void orb_destroy(orb_ctx* c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (WorkSet& W : c->ws) {
-        void* wp[] = { W.d_planes, W.d_work, W.d_blur, W.d_bitmap, W.d_cand, W.d_ntotal, W.d_lvl, W.d_nkept, W.d_counters };
+        void* wp[] = { W.d_planes, W.d_work, W.d_blur, W.d_bitmap, W.d_cand, W.d_cand64, W.d_ntotal, W.d_lvl, W.d_nkept, W.d_counters };
         for (void* p : wp) if (p) cudaFree(p);
         if (W.aux_stream) cudaStreamDestroy(W.aux_stream);
         if (W.ev_fork) cudaEventDestroy(W.ev_fork);

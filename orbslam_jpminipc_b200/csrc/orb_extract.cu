@@ -584,10 +584,55 @@ k_cell_compact(const uint8_t* __restrict__ nms, const uint8_t* __restrict__ bitm
 // level record = score<<32 | y<<16 | x  (level ROI coordinates)
 constexpr int SEL_STAGE = 6144;     // candidate records staged in shared memory per (frame, level)
 
+// HARRIS_SCORE (src/ORBextractor.cc:616-620 -> HarrisResponses :79-120, blockSize 7, k = 0.04): one thread per candidate of the
+// per-cell lists replaces the FAST response by the Harris measure; integer moments a, b, c over the 7x7 block of Sobel-like
+// gradients, then the float expression of :117-118 with every operation rounded on its own.
+__global__ void __launch_bounds__(256)
+k_harris(const uint8_t* __restrict__ planes, size_t fbytes, const Plan* __restrict__ plan, const CellGeom* __restrict__ cells,
+         const uint32_t* __restrict__ cand, const int* __restrict__ ntotal, unsigned long long* __restrict__ cand64)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= plan->ncells) return;
+    const int f = blockIdx.y;
+    const CellGeom g = cells[warp];
+    const LevelGeom& L = plan->L[g.level];
+    const int n = ntotal[(size_t)f * plan->ncells + warp];
+    const uint8_t* roi = planes + (size_t)f * fbytes + L.plane_off + (size_t)ORB_EDGE * L.stride + ORB_EDGE;
+    const uint32_t* in = cand + (size_t)f * plan->cand_total + g.cand_off;
+    unsigned long long* out = cand64 + (size_t)f * plan->cand_total + g.cand_off;
+    const int step = L.stride;
+    float scale = __fmul_rn((float)((1 << 2) * 7), 255.0f);
+    scale = __fdiv_rn(1.0f, scale);
+    const float scale_sq_sq = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
+    for (int i = lane; i < n; i += 32) {
+        const uint32_t r = in[i];
+        const int x = (int)(r & 0xfff) + g.inix, y = (int)((r >> 12) & 0xfff) + g.iniy;      // level (ROI) coordinates
+        const uint8_t* p0 = roi + (size_t)(y - 3) * step + (x - 3);
+        int a = 0, b = 0, c = 0;
+        for (int yy = 0; yy < 7; yy++) {
+            const uint8_t* pu = p0 + (ptrdiff_t)(yy - 1) * step, *pc = pu + step, *pd = pc + step;
+            int u0 = pu[-1], u1 = pu[0], c0 = pc[-1], c1 = pc[0], d0 = pd[-1], d1 = pd[0];
+#pragma unroll
+            for (int xx = 0; xx < 7; xx++) {
+                const int u2 = pu[xx + 1], c2 = pc[xx + 1], d2 = pd[xx + 1];
+                const int Ix = (c2 - c0) * 2 + (u2 - u0) + (d2 - d0);
+                const int Iy = (d1 - u1) * 2 + (d0 - u0) + (d2 - u2);
+                a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
+                u0 = u1; u1 = u2; c0 = c1; c1 = c2; d0 = d1; d1 = d2;
+            }
+        }
+        const float fa = (float)a, fb = (float)b, fc = (float)c;
+        const float sum = __fadd_rn(fa, fb);
+        const float resp = __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, sum), sum)), scale_sq_sq);
+        out[i] = ((unsigned long long)__float_as_uint(resp) << 32) | (r & 0xffffffu);
+    }
+}
+
+template <bool HARRIS>
 __global__ void __launch_bounds__(128)
 k_select(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells, uint32_t* __restrict__ cand,
-         const int* __restrict__ ntotal, unsigned long long* __restrict__ lvl, int* __restrict__ nkept,
-         int* __restrict__ status)
+         unsigned long long* __restrict__ cand64, const int* __restrict__ ntotal, unsigned long long* __restrict__ lvl,
+         int* __restrict__ nkept, int* __restrict__ status)
 {
     extern __shared__ unsigned long long s_list[];            // lvl_cap records, then SEL_STAGE u32 records
     __shared__ int s_total[ORB_MAX_CELLS_LEVEL], s_retain[ORB_MAX_CELLS_LEVEL], s_off[ORB_MAX_CELLS_LEVEL + 1];
@@ -632,8 +677,9 @@ k_select(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells, uint
     __syncthreads();
     int total = s_off[nCells];
     if (total < 0) { if (tid == 0) nkept[f * plan->nlevels + level] = 0; return; }
-    const bool staged = s_coff[nCells] <= SEL_STAGE;
+    const bool staged = !HARRIS && s_coff[nCells] <= SEL_STAGE;
     uint32_t* gbase = cand + (size_t)f * plan->cand_total;
+    unsigned long long* gbase64 = HARRIS ? cand64 + (size_t)f * plan->cand_total : nullptr;
     if (staged) {          // coalesced copy of the lists that need a selection into shared memory
         const int warp = tid >> 5, lane = tid & 31;
         for (int c = warp; c < nCells; c += 4) {
@@ -645,21 +691,34 @@ k_select(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells, uint
     }
     for (int c = tid; c < nCells; c += blockDim.x) {
         const int n = s_total[c], keep = s_retain[c];
-        uint32_t* v = gbase + cg[c].cand_off;
-        if (n > keep && keep > 0) {
-            if (staged) v = s_cand + s_coff[c];
-            orbsel::nth_element(v, n, keep - 1, orbsel::KeyGreater<uint32_t, 24>());
-        }
         const int ix = cg[c].inix, iy = cg[c].iniy;
-        for (int k = 0; k < keep; k++) {
-            const uint32_t r = v[k];
-            const unsigned long long x = (r & 0xfff) + ix, y = ((r >> 12) & 0xfff) + iy;
-            s_list[s_off[c] + k] = ((unsigned long long)(r >> 24) << 32) | (y << 16) | x;
+        if (HARRIS) {             // 64-bit records (float response | position) straight in global memory
+            unsigned long long* v = gbase64 + cg[c].cand_off;
+            if (n > keep && keep > 0) orbsel::nth_element(v, n, keep - 1, orbsel::FloatKeyGreater64());
+            for (int k = 0; k < keep; k++) {
+                const unsigned long long r = v[k];
+                const unsigned long long x = (r & 0xfff) + ix, y = ((r >> 12) & 0xfff) + iy;
+                s_list[s_off[c] + k] = (r & 0xffffffff00000000ull) | (y << 16) | x;
+            }
+        } else {
+            uint32_t* v = gbase + cg[c].cand_off;
+            if (n > keep && keep > 0) {
+                if (staged) v = s_cand + s_coff[c];
+                orbsel::nth_element(v, n, keep - 1, orbsel::KeyGreater<uint32_t, 24>());
+            }
+            for (int k = 0; k < keep; k++) {
+                const uint32_t r = v[k];
+                const unsigned long long x = (r & 0xfff) + ix, y = ((r >> 12) & 0xfff) + iy;
+                s_list[s_off[c] + k] = ((unsigned long long)(r >> 24) << 32) | (y << 16) | x;
+            }
         }
     }
     __syncthreads();
     if (total > L.nDesired) {
-        if (tid == 0) orbsel::nth_element(s_list, total, L.nDesired - 1, orbsel::KeyGreater<unsigned long long, 32>());
+        if (tid == 0) {
+            if (HARRIS) orbsel::nth_element(s_list, total, L.nDesired - 1, orbsel::FloatKeyGreater64());
+            else orbsel::nth_element(s_list, total, L.nDesired - 1, orbsel::KeyGreater<unsigned long long, 32>());
+        }
         total = L.nDesired;
         __syncthreads();
     }
@@ -902,7 +961,7 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
         float fx = (float)x, fy = (float)y;
         if (level != 0) { fx = __fmul_rn(fx, L.scale); fy = __fmul_rn(fy, L.scale); }   // :769-775
         kp.x = fx; kp.y = fy; kp.size = (float)L.patch_size; kp.angle = angle;
-        kp.response = (float)score; kp.octave = level; kp.class_id = -1;
+        kp.response = plan->harris ? __int_as_float(score) : (float)score; kp.octave = level; kp.class_id = -1;
         kps[(size_t)f * cap + slot] = kp;
     }
 }
@@ -1002,7 +1061,12 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         ORB_CUDA(cudaEventRecord(W.ev_join, W.aux_stream));
     }
     mark();
-    k_select<<<dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s>>>(c->d_plan, c->d_cells, W.d_cand, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status);
+    if (P.harris) {
+        k_harris<<<dim3((P.ncells + 7) / 8, nimg), 256, 0, s>>>(W.d_planes, fb, c->d_plan, c->d_cells, W.d_cand, W.d_ntotal, W.d_cand64);
+        k_select<true><<<dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s>>>(c->d_plan, c->d_cells, W.d_cand, W.d_cand64, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status);
+        launches++;
+    } else
+        k_select<false><<<dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s>>>(c->d_plan, c->d_cells, W.d_cand, nullptr, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status);
     mark();
     if (fork) ORB_CUDA(cudaStreamWaitEvent(s, W.ev_join, 0));
     else launch_blur(s);
@@ -1025,6 +1089,7 @@ int orb_resize_smem_setup(int max_bytes)
 
 int orb_select_smem_setup(int max_bytes)
 {
-    ORB_CUDA(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
+    ORB_CUDA(cudaFuncSetAttribute(k_select<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
+    ORB_CUDA(cudaFuncSetAttribute(k_select<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
     return ORB_OK;
 }

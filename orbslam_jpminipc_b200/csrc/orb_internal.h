@@ -48,6 +48,7 @@ struct Plan {
     int lvl_total;         // level-list slots per frame (u64 records)
     int kp_cap;            // sum of nDesired
     int fast_th, th_lo;
+    int harris;                  // HARRIS_SCORE: candidate responses are replaced by HarrisResponses before the selection (:616-620)
     int ntiles_fast, ntiles_blur;
     int bm_total;          // bitmap bytes per frame
     int sel_list_cap;      // max lvl_cap over levels (k_select shared-memory list)
@@ -77,6 +78,7 @@ struct WorkSet {
     uint8_t* d_blur = nullptr;    size_t blur_bytes = 0;       // blurred ROIs + un-blurred frame
     uint8_t* d_bitmap = nullptr;  size_t bitmap_bytes = 0;     // 1 bit per detection pixel: NMS survivor
     uint32_t* d_cand = nullptr;   size_t cand_bytes = 0;
+    unsigned long long* d_cand64 = nullptr; size_t cand64_bytes = 0;   // HARRIS_SCORE only: (float response bits << 32) | y << 12 | x
     int* d_ntotal = nullptr;      size_t ntotal_bytes = 0;
     unsigned long long* d_lvl = nullptr; size_t lvl_bytes = 0;
     int* d_nkept = nullptr;       size_t nkept_bytes = 0;

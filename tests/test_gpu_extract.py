@@ -196,3 +196,23 @@ def test_threshold_fallback_cells(pkg, po):
             kps, desc = ex(img)
             _same(kps, desc, rk, rd, (tag, nf, th))
             ex.close()
+
+
+@pytest.mark.parametrize("shape,nf,th", [((240, 320), 300, 20), ((480, 640), 1000, 20), ((480, 752), 1000, 12), ((376, 1241), 2000, 20)])
+def test_harris_score_vs_oracle(pkg, po, shape, nf, th):
+    """scoreType = HARRIS_SCORE (src/ORBextractor.cc:616-620, HarrisResponses :79-120): float responses drive both retainBest
+    passes; keypoints (incl. response bit patterns), order and descriptors must equal the oracle's."""
+    from orbslam_jpminipc_b200.synth import synth_frame
+    h, w = shape
+    ex = pkg.ORBextractor(nf, 1.2, 8, pkg.ORBextractor.HARRIS_SCORE, th, max_width=w, max_height=h, max_batch=2)
+    orc = po.OracleExtractor(nf, 1.2, 8, 0, th)
+    for seed in (3000, 3001):
+        img = synth_frame(h, w, seed, quadrants=(seed == 3000))
+        kps, desc = ex(img)
+        rk, rd = orc(img)
+        _same(kps, desc, rk, rd, ("harris", shape, nf, seed))
+        assert len(kps) > 50 and (kps["response"] != np.round(kps["response"])).any()      # Harris values, not FAST scores
+    # the FAST_SCORE result on the same frame differs (different selection)
+    fk, _ = pkg.ORBextractor(nf, 1.2, 8, 1, th, max_width=w, max_height=h, max_batch=1)(img)
+    assert len(fk) != len(kps) or not np.array_equal(fk["x"], kps["x"])
+    ex.close()
