@@ -215,6 +215,7 @@ void orb_destroy(orb_ctx* c)
         if (t.h_status) cudaFreeHost(t.h_status);
     }
     if (c->done_stream) cudaStreamDestroy(c->done_stream);
+    if (c->ev_dev_done) cudaEventDestroy(c->ev_dev_done);
     if (c->ev_user) cudaEventDestroy(c->ev_user);
     for (cudaEvent_t e : c->ev_half) if (e) cudaEventDestroy(e);
     void* ptrs[] = { c->d_plan, c->d_cells, c->d_tiles_fast, c->d_tiles_blur, c->d_xtab, c->d_ytab, c->d_status, c->d_src[0], c->d_src[1], c->d_kps[0],
@@ -253,8 +254,12 @@ int orb_extract_batch_device(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w,
     }
     if (nimg > c->max_batch) return ORB_ERR_CAPACITY;
     if (stride < w) return ORB_ERR_INVALID;
+    // the work sets are shared with the host-buffer calls: anything those still have in flight finishes first
+    while (c->waited_seq + 1 < c->next_seq) { const int rw = orb_wait(c, c->waited_seq + 1); if (rw != ORB_OK) return rw; }
     int rc = prepare(c, w, h);
     if (rc != ORB_OK) return rc;
+    if (!c->ev_dev_done) ORB_CUDA(cudaEventCreateWithFlags(&c->ev_dev_done, cudaEventDisableTiming));
+    struct Done { orb_ctx* c; cudaStream_t s; ~Done() { if (cudaEventRecord(c->ev_dev_done, s) == cudaSuccess) c->dev_call_pending = true; } } done{ c, us };
     // Optional (ORB_SPLIT_DEVICE=1): two halves on the two internal streams, forked from / joined to the caller's
     // stream.  Measured on B200 at 256 frames: 3.19 ms split vs 3.03 ms unsplit, so it is off by default; the
     // host-buffer path always alternates the two work sets so that copies and kernels of neighbouring chunks overlap.
@@ -332,6 +337,11 @@ int orb_extract_batch_async(orb_ctx* c, const uint8_t* imgs, int nimg, int w, in
         else for (int i = 0; i < nimg; i++) counts[i] = 0;
     } else {
         const bool idle = c->waited_seq + 1 == c->next_seq;          // nothing in flight
+        if (c->dev_call_pending) {                                   // a device-pointer call on a caller stream used the same work sets
+            ORB_CUDA(cudaStreamWaitEvent(c->streams[0], c->ev_dev_done, 0));
+            ORB_CUDA(cudaStreamWaitEvent(c->streams[1], c->ev_dev_done, 0));
+            c->dev_call_pending = false;
+        }
         if (idle) c->chunk_parity = 0;                               // blocking callers always start on work set 0 (debug getters rely on it)
         int rc = prepare(c, w, h);
         if (rc != ORB_OK) return rc;

@@ -128,6 +128,7 @@ struct orb_ctx {
     long long next_seq = 0, waited_seq = -1;   // tickets issued / highest ticket known complete
     int chunk_parity = 0;             // work set / stream the next chunk goes to
     bool chain_chunks = true, kernels_pending = false;
+    cudaEvent_t ev_dev_done = nullptr; bool dev_call_pending = false;   // last orb_extract_batch_device call on a caller stream
     // staging for host-pointer calls (two slots for copy/compute overlap)
     uint8_t* d_src[2] = { nullptr, nullptr };  size_t src_bytes[2] = { 0, 0 };
     size_t kps_bytes[2] = { 0, 0 }, desc_bytes[2] = { 0, 0 }, counts_bytes[2] = { 0, 0 };

@@ -899,8 +899,7 @@ int orb_launch_grid_build(const orb_keypoint* kps, int n, int min_x, int max_x, 
 {
     const size_t sm = (size_t)std::max(n, 1) * sizeof(unsigned short);
     if (sm > 160 * 1024) return ORB_ERR_CAPACITY;
-    static bool attr_set = false;
-    if (!attr_set) { ORB_CUDA(cudaFuncSetAttribute(k_grid_build, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set = true; }
+    if (sm > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_grid_build, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));   // per device, no caching
     k_grid_build<<<1, 1024, sm, s>>>(kps, n, min_x, max_x, min_y, max_y, cell_start, cell_items);
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;

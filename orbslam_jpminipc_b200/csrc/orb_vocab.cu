@@ -496,8 +496,8 @@ int orb_vocab_transform_batch(orb_ctx* c, orb_vocab* v, const uint8_t* desc, int
     int P = 32;
     while (P < std::max(slot_rows, 1)) P <<= 1;
     const size_t smem = (size_t)P * 8;
-    static bool attr_set = false;
-    if (!attr_set) { ORB_CUDA(cudaFuncSetAttribute(k_bow_build, cudaFuncAttributeMaxDynamicSharedMemorySize, BOW_MAX_FEATURES * 8)); attr_set = true; }
+    // per device and cheap: no caching, a process may drive several GPUs
+    ORB_CUDA(cudaFuncSetAttribute(k_bow_build, cudaFuncAttributeMaxDynamicSharedMemorySize, BOW_MAX_FEATURES * 8));
     k_bow_build<<<nframes, BOW_THREADS, smem, s>>>(d_word, d_weight, d_node, d_counts, 0, slot_rows, cap, v->scoring, v->weighting,
                                                    o_bw, o_bv, o_nb, o_fn, o_fs, o_fi, o_nf);
     ORB_CUDA(cudaGetLastError());
