@@ -83,7 +83,7 @@ k_level0(const uint8_t* __restrict__ src, int w, int h, int sstride, size_t spit
 // tile = tile_w columns x (1024 / tile_w) * rs_rows rows: 128 x 64 normally, 64 x 64 with 4 rows per thread when the
 // scale factor is so large that the 128-wide source footprint would exceed the 256-element TMA box limit
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(ORB_RESIZE_THREADS)
 k_resize(const __grid_constant__ CUtensorMap tm, uint8_t* __restrict__ planes, size_t fbytes, LevelGeom D,
          const int2* __restrict__ xtab, const int2* __restrict__ ytab, int box_w, int box_h, int buf_bytes,
          int nimg, int* __restrict__ work_counter, int RT_W, int RS_ROWS)
@@ -94,7 +94,7 @@ k_resize(const __grid_constant__ CUtensorMap tm, uint8_t* __restrict__ planes, s
     __shared__ int s_org[2][5];                             // x0, y0, frame, source origin x / y of the item in each buffer
     const int tid = threadIdx.x;
     const int ncg = RT_W >> 2;                              // column groups (4 columns each) per tile
-    const int RT_H = (256 / ncg) * RS_ROWS;
+    const int RT_H = (ORB_RESIZE_THREADS / ncg) * RS_ROWS;
     const int tiles_x = (D.w + RT_W - 1) / RT_W, tiles_y = (D.h + RT_H - 1) / RT_H;
     const int ntiles = tiles_x * tiles_y, total = ntiles * nimg;
     const int2* xt = xtab + D.xtab_off;
@@ -748,7 +748,11 @@ __device__ __forceinline__ float u8f(uint32_t w, int j)     // byte j of w as fl
 
 // Persistent kernel, same pipeline shape as k_fast_nms: TMA fetches the input tile of the next work
 // item while the current one runs its row and column passes.
-__global__ void __launch_bounds__(256)
+#ifndef ORB_BLUR_THREADS
+#define ORB_BLUR_THREADS 128     // measured on B200 (ms per 256 frames, CTAs/SM): 256x4 0.475, 192x5 0.497, 128x7 0.408, 128x8 0.388, 64x8 0.446
+#endif
+constexpr int BLUR_THREADS = ORB_BLUR_THREADS;
+__global__ void __launch_bounds__(BLUR_THREADS)
 k_blur(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ blurred, size_t fbytes,
        const Plan* __restrict__ plan, const Tile* __restrict__ tiles, int ntiles, int total, int* __restrict__ work_counter)
 {
@@ -786,7 +790,7 @@ k_blur(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ blurred, size_t
         __syncthreads();
         const uint32_t* img = reinterpret_cast<const uint32_t*>(img2[buf]);
         // row pass: one task = 8 adjacent outputs of one row; ROI column x0+c sits at tile byte 16+c
-        for (int task = tid; task < BI_H * (BT_W / 8); task += 256) {
+        for (int task = tid; task < BI_H * (BT_W / 8); task += BLUR_THREADS) {
             const int r = task >> 3, seg = task & 7;
             const uint32_t* ip = img + r * BIW + 3 + 2 * seg;          // bytes 12+8seg .. 27+8seg
             const uint32_t ax = ip[0], ay = ip[1], bx = ip[2], by = ip[3];
@@ -810,7 +814,7 @@ k_blur(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ blurred, size_t
         __syncthreads();
         // column pass: one task = 4 columns x 4 rows of outputs (10 row-pass rows, float4 loads)
         uint8_t* out = blurred + (size_t)f * fbytes + L.plane_off;
-        for (int task = tid; task < (BT_W / 4) * (BT_H / 4); task += 256) {
+        for (int task = tid; task < (BT_W / 4) * (BT_H / 4); task += BLUR_THREADS) {
             const int cg = task & 15, rg = task >> 4;
             const float4* rp = reinterpret_cast<const float4*>(rowp + (rg * 4) * BT_W + cg * 4);
             float4 R[10];
@@ -1015,12 +1019,12 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
     mark();
     for (int l = 1; l < P.nlevels; l++) {
         const LevelGeom& D = P.L[l];
-        const int tw = c->rs_tile_w[l], rr = c->rs_rows[l], th = (1024 / tw) * rr;
+        const int tw = c->rs_tile_w[l], rr = c->rs_rows[l], th = (4 * ORB_RESIZE_THREADS / tw) * rr;
         const int tiles = ((D.w + tw - 1) / tw) * ((D.h + th - 1) / th) * nimg;
         const int bufb = (c->rs_box_w[l] * c->rs_box_h[l] + 127) & ~127;
-        const int grid = std::min(tiles, c->num_sms * 4);
+        const int grid = std::min(tiles, c->num_sms * ORB_RESIZE_CTAS);
         cudaMemsetAsync(W.d_counters + 4 + l, 0, sizeof(int), s);
-        k_resize<<<grid, 256, 2 * bufb + 16, s>>>(W.tm_resize.m[l], W.d_planes, fb, D, c->d_xtab, c->d_ytab, c->rs_box_w[l], c->rs_box_h[l],
+        k_resize<<<grid, ORB_RESIZE_THREADS, 2 * bufb + 16, s>>>(W.tm_resize.m[l], W.d_planes, fb, D, c->d_xtab, c->d_ytab, c->rs_box_w[l], c->rs_box_h[l],
                                                bufb, nimg, W.d_counters + 4 + l, tw, rr);
         launches++;
     }
@@ -1034,7 +1038,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         const int total = P.ntiles_blur * nimg;
         const int grid = std::min(total, c->num_sms * c->blur_ctas);
         cudaMemsetAsync(W.d_counters + 2, 0, sizeof(int), bs);
-        k_blur<<<grid, 256, 0, bs>>>(W.tm_blur, W.d_blur, fb, c->d_plan, c->d_tiles_blur, P.ntiles_blur, total, W.d_counters + 2);
+        k_blur<<<grid, BLUR_THREADS, 0, bs>>>(W.tm_blur, W.d_blur, fb, c->d_plan, c->d_tiles_blur, P.ntiles_blur, total, W.d_counters + 2);
     };
     if (fork && c->fork_early == 1) {          // blur next to FAST: FAST saturates the ALU pipe and leaves the FMA pipe idle
         ORB_CUDA(cudaEventRecord(W.ev_fork, s));

@@ -14,6 +14,10 @@
 #ifndef ORB_TILE_W
 #define ORB_TILE_W 64            // FAST tile width (multiple of 64); measured 64x32 1.38 ms, 64x64 1.28, 128x64 1.25, 64x128 1.24 per 256 frames
 #endif
+#ifndef ORB_RESIZE_THREADS
+#define ORB_RESIZE_THREADS 256     // k_resize CTA size; a thread owns 4 output columns, so a tile is (4*threads/tile_w)*rows high
+#define ORB_RESIZE_CTAS 4
+#endif
 #ifndef ORB_TILE_H
 #define ORB_TILE_H 128
 #endif
@@ -140,7 +144,7 @@ struct orb_ctx {
     int last_launches = 0;
     int num_sms = 148;
     int split_device = 0;
-    int fork_early = 0, fast_ctas = 6, blur_ctas = 4;      // stream-overlap tuning (ORB_FORK_EARLY / ORB_FAST_CTAS_FORK / ORB_BLUR_CTAS env)
+    int fork_early = 0, fast_ctas = 6, blur_ctas = 8;      // stream-overlap tuning (ORB_FORK_EARLY / ORB_FAST_CTAS_FORK / ORB_BLUR_CTAS env)
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;   // (ORB_NSTAGES+1) per profiled launch
     std::vector<cudaEvent_t> prof_pool;
