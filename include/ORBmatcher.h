@@ -6,7 +6,8 @@
  *   SearchByBoW(KeyFrame*, Frame&, ...) candidate scoring (:155-284), SearchByBoW(KeyFrame*, KeyFrame*, ...) (:715-850)
  *   SearchByProjection(Frame&, vector<MapPoint*>, th) (:49-125), WindowSearch (:409-516),
  *   SearchByProjection(F1, F2, windowSize, ...) (:519-594), SearchByProjection(Frame&, KeyFrame*, ...) (:1622-1746),
- *   SearchForInitialization (:598-713)
+ *   SearchForInitialization (:598-713), SearchByProjection(KeyFrame*, Scw, ...) (:286-407), the scoring loops of Fuse
+ *   (:1016-1265) and SearchBySim3 (:1267-1505)
  * plus the brute-force best/second-best + ratio test used for relocalisation-sized searches.
  * Frame / KeyFrame / MapPoint are the reference's own graph classes and stay on the host: the shim
  * takes the plain arrays those methods read (see INTEGRATION.md for the adapter code).
@@ -186,6 +187,52 @@ public:
         return n;
     }
 
+    // ---- back-end searches on map points the caller has already projected (Sim3 / pose projection and level prediction,
+    //      src/ORBmatcher.cc:300-349, :1033-1078, :1301-1354, stay in the adapter)
+    // SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (:286-407): matchedKF[idx] >= 0 where vpMatched[idx] is set
+    int SearchByProjection(const FrameArrays& KF, const std::vector<unsigned char>& active, const std::vector<float>& u,
+                           const std::vector<float>& v, const std::vector<int32_t>& predLevel, const std::vector<unsigned char>& mpDesc,
+                           int th, std::vector<int32_t>& matchedKF)
+    {
+        const size_t n = active.size();
+        std::vector<float> radius(n);
+        std::vector<int32_t> lmin(n);
+        const std::vector<float> sf = scaleFactors(KF);
+        for (size_t i = 0; i < n; i++) { radius[i] = (float)th * sf[clampLevel(KF, predLevel[i])]; lmin[i] = predLevel[i] - 1; }
+        orb_window_query_set q = { (int32_t)n, active.data(), mpDesc.data(), u.data(), v.data(), nullptr, nullptr, 0,
+                                   radius.data(), 0.f, lmin.data(), predLevel.data(), nullptr };
+        return window(KF, q, ORB_ACCEPT_BEST, TH_LOW, false, matchedKF);
+    }
+
+    // scoring loop of Fuse (:1016-1134, :1136-1265): fuseIdx[i] = KF keypoint map point i fuses with (bestDist <= TH_LOW) or -1
+    void FuseCandidates(const FrameArrays& KF, const std::vector<unsigned char>& active, const std::vector<float>& u,
+                        const std::vector<float>& v, const std::vector<int32_t>& predLevel, const std::vector<unsigned char>& mpDesc,
+                        float th, std::vector<int32_t>& fuseIdx)
+    {
+        std::vector<int32_t> dist;
+        best(KF, active, u, v, predLevel, mpDesc, th, fuseIdx, dist);
+        for (size_t i = 0; i < fuseIdx.size(); i++) if (dist[i] > TH_LOW) fuseIdx[i] = -1;
+    }
+
+    // SearchBySim3 (:1267-1505): points of KF1 projected into KF2 (u12, v12, level12) and the other way round; matches12[i1] = idx2 or -1
+    int SearchBySim3(const FrameArrays& KF1, const FrameArrays& KF2,
+                     const std::vector<unsigned char>& active1, const std::vector<float>& u12, const std::vector<float>& v12,
+                     const std::vector<int32_t>& level12, const std::vector<unsigned char>& desc1,
+                     const std::vector<unsigned char>& active2, const std::vector<float>& u21, const std::vector<float>& v21,
+                     const std::vector<int32_t>& level21, const std::vector<unsigned char>& desc2, float th, std::vector<int32_t>& matches12)
+    {
+        std::vector<int32_t> m1, d1, m2, d2;
+        best(KF2, active1, u12, v12, level12, desc1, th, m1, d1);
+        best(KF1, active2, u21, v21, level21, desc2, th, m2, d2);
+        matches12.assign(m1.size(), -1);
+        int nFound = 0;
+        for (size_t i1 = 0; i1 < m1.size(); i1++) {                    // agreement, :1478-1493
+            const int idx2 = d1[i1] <= TH_HIGH ? m1[i1] : -1;
+            if (idx2 >= 0 && d2[idx2] <= TH_HIGH && m2[idx2] == (int32_t)i1) { matches12[i1] = idx2; nFound++; }
+        }
+        return nFound;
+    }
+
     // best / second-best over all DB rows + the acceptance test of :224-226; returns the number of matches
     int MatchBruteForce(const unsigned char* q, int nq, const unsigned char* db, long long ndb, int th, std::vector<int32_t>& match)
     {
@@ -208,6 +255,28 @@ protected:
         int n = 0;
         check(orb_search_window(ctx, &tv, &q, accept, mfNNratio, thDist, hist ? 1 : 0, match.data(), &n));
         return n;
+    }
+    static std::vector<float> scaleFactors(const FrameArrays& F)
+    {
+        std::vector<float> sf(F.mnScaleLevels > 0 ? F.mnScaleLevels : 1, 1.0f);
+        for (size_t i = 1; i < sf.size(); i++) sf[i] = sf[i - 1] * F.mfScaleFactor;
+        return sf;
+    }
+    static int clampLevel(const FrameArrays& F, int l) { return l < 0 ? 0 : (l >= F.mnScaleLevels ? F.mnScaleLevels - 1 : l); }
+    void best(const FrameArrays& F, const std::vector<unsigned char>& active, const std::vector<float>& u, const std::vector<float>& v,
+              const std::vector<int32_t>& predLevel, const std::vector<unsigned char>& desc, float th, std::vector<int32_t>& idx,
+              std::vector<int32_t>& dist)
+    {
+        const size_t n = active.size();
+        std::vector<float> radius(n);
+        std::vector<int32_t> lmin(n);
+        const std::vector<float> sf = scaleFactors(F);
+        for (size_t i = 0; i < n; i++) { radius[i] = th * sf[clampLevel(F, predLevel[i])]; lmin[i] = predLevel[i] - 1; }
+        orb_window_query_set q = { (int32_t)n, active.data(), desc.data(), u.data(), v.data(), nullptr, nullptr, 0,
+                                   radius.data(), 0.f, lmin.data(), predLevel.data(), nullptr };
+        idx.assign(n, -1); dist.assign(n, 0);
+        orb_frame_view tv = F.view();
+        check(orb_search_window_best(ctx, &tv, &q, idx.data(), dist.data()));
     }
     void check(int status)
     {

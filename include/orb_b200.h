@@ -194,6 +194,15 @@ int orb_search_window(orb_ctx*, const orb_frame_view* target, const orb_window_q
 int orb_search_for_initialization(orb_ctx*, const orb_frame_view* f1, const orb_frame_view* f2, float* prev_matched, int window_size,
                                   float nnratio, int check_ori, int32_t* matches12, int* nmatches);
 
+/* Best candidate per query without claims ("match to the most similar keypoint in the radius"): the scoring loops of
+ * ORBmatcher::Fuse (src/ORBmatcher.cc:1016-1134 and :1136-1265, candidates of KeyFrame::GetFeaturesInArea with octave in
+ * [nPredictedLevel-1, nPredictedLevel]) and of both directions of ORBmatcher::SearchBySim3 (:1267-1505).  best_idx[i] = target
+ * keypoint or -1, best_dist[i] = its distance or INT_MAX; the caller applies TH_LOW / TH_HIGH and the graph updates.
+ * ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (:286-407) is orb_search_window with ORB_ACCEPT_BEST,
+ * th_dist = 50, octave range [nPredictedLevel-1, nPredictedLevel] and match_target pre-filled from vpMatched. */
+int orb_search_window_best(orb_ctx*, const orb_frame_view* target, const orb_window_query_set* queries, int32_t* best_idx,
+                           int32_t* best_dist);
+
 /* DBoW2::FeatureVector as CSR (Thirdparty/DBoW2/DBoW2/FeatureVector.cpp:31-45): node ids ascending,
  * per node the feature indices in insertion order. */
 typedef struct orb_featvec_view {

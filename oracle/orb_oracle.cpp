@@ -1109,6 +1109,52 @@ int orc_search_for_initialization(const orc_frame* f1, const orc_frame* f2, floa
     return nmatches;
 }
 
+/* src/ORBmatcher.cc:350-404 */
+int orc_search_by_projection_sim3(const orc_frame* kf, int nmp, const uint8_t* active, const float* u, const float* v,
+                                  const int32_t* pred_level, const uint8_t* mp_desc, int th, int32_t* matched)
+{
+    const int TH_LOW = 50;
+    std::vector<float> sf(kf->nlevels > 0 ? kf->nlevels : 1, 1.0f);
+    for (int i = 1; i < kf->nlevels; i++) sf[i] = sf[i - 1] * kf->scale_factor;
+    std::vector<int32_t> cand(kf->n > 0 ? kf->n : 1);
+    int nmatches = 0;
+    for (int i = 0; i < nmp; i++) {
+        if (!active[i]) continue;
+        const int nPredictedLevel = pred_level[i];
+        const float radius = th * sf[nPredictedLevel];
+        const int nc = orc_features_in_area(kf, u[i], v[i], radius, -1, -1, cand.data(), kf->n);
+        if (nc == 0) continue;
+        int bestDist = INT_MAX, bestIdx = -1;
+        for (int k = 0; k < nc; k++) {
+            const int idx = cand[k];
+            if (matched[idx] >= 0) continue;
+            const int kpLevel = kf->kps[idx].octave;
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            const int dist = orc_descriptor_distance(mp_desc + (size_t)i * 32, kf->desc + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        if (bestDist <= TH_LOW) { matched[bestIdx] = i; nmatches++; }
+    }
+    return nmatches;
+}
+
+void orc_window_best(const orc_frame* f, int nq, const uint8_t* active, const float* u, const float* v, const float* radius,
+                     const int32_t* pred_level, const uint8_t* desc, int32_t* best_idx, int32_t* best_dist)
+{
+    std::vector<int32_t> cand(f->n > 0 ? f->n : 1);
+    for (int i = 0; i < nq; i++) {
+        best_idx[i] = -1; best_dist[i] = INT_MAX;
+        if (!active[i]) continue;
+        const int nc = orc_features_in_area(f, u[i], v[i], radius[i], -1, -1, cand.data(), f->n);
+        for (int k = 0; k < nc; k++) {
+            const int idx = cand[k], lv = f->kps[idx].octave;
+            if (lv < pred_level[i] - 1 || lv > pred_level[i]) continue;
+            const int dist = orc_descriptor_distance(desc + (size_t)i * 32, f->desc + (size_t)idx * 32);
+            if (dist < best_dist[i]) { best_dist[i] = dist; best_idx[i] = idx; }
+        }
+    }
+}
+
 /* ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...), src/ORBmatcher.cc:715-850 */
 int orc_search_by_bow_kf(const orc_featvec* fv1, const uint8_t* desc1, const orc_keypoint* kps1, const uint8_t* valid1, int n1,
                          const orc_featvec* fv2, const uint8_t* desc2, const orc_keypoint* kps2, const uint8_t* valid2, int n2,

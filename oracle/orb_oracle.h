@@ -150,6 +150,17 @@ int   orc_search_by_bow_kf(const orc_featvec* fv1, const uint8_t* desc1, const o
                            const orc_featvec* fv2, const uint8_t* desc2, const orc_keypoint* kps2, const uint8_t* valid2, int n2,
                            float nnratio, int check_ori, int32_t* match12);
 
+/* ---- back-end searches of ORBmatcher on pre-projected map points ---- */
+/* ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th), src/ORBmatcher.cc:286-407, from :350 on: u, v and the
+ * predicted level come from the caller (Sim3 projection :300-349); radius = th * scaleFactor[level] (:352).  matched[idx] in/out:
+ * >= 0 = vpMatched[idx] already set (skipped, :376), on return the index of the map point assigned to it. */
+int   orc_search_by_projection_sim3(const orc_frame* kf, int nmp, const uint8_t* active, const float* u, const float* v,
+                                    const int32_t* pred_level, const uint8_t* mp_desc, int th, int32_t* matched);
+/* "Match to the most similar keypoint in the radius" without claims: the loops of ORBmatcher::Fuse (:1083-1115, :1211-1243) and
+ * SearchBySim3 (:1356-1385, :1436-1465); best_idx -1 / best_dist INT_MAX when no candidate */
+void  orc_window_best(const orc_frame* f, int nq, const uint8_t* active, const float* u, const float* v, const float* radius,
+                      const int32_t* pred_level, const uint8_t* desc, int32_t* best_idx, int32_t* best_dist);
+
 /* ---- DBoW2 vocabulary, Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h ---- */
 typedef struct orc_vocab orc_vocab;
 enum { ORC_L1_NORM = 0, ORC_L2_NORM, ORC_CHI_SQUARE, ORC_KL, ORC_BHATTACHARYYA, ORC_DOT_PRODUCT };   /* BowVector.h:45-53 */

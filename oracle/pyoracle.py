@@ -112,6 +112,8 @@ def lib():
         L.orc_distinctive_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_harris_response.restype = C.c_float
         L.orc_harris_response.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_search_by_projection_sim3.argtypes = [C.POINTER(_Frame), C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
+        L.orc_window_best.argtypes = [C.POINTER(_Frame), C.c_int] + [C.c_void_p] * 8
         L.orc_three_maxima.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 3
         _lib = L
     return _lib
@@ -516,3 +518,18 @@ def distinctive_descriptors(desc, start):
 def harris_response(img, x, y):
     img = np.ascontiguousarray(img, np.uint8)
     return lib().orc_harris_response(_p(img), img.strides[0], int(x), int(y))
+
+
+def search_by_projection_sim3(kf, active, u, v, pred_level, mp_desc, th, matched):
+    a = np.ascontiguousarray(active, np.uint8); uu = np.ascontiguousarray(u, np.float32); vv = np.ascontiguousarray(v, np.float32)
+    lv = np.ascontiguousarray(pred_level, np.int32); d = np.ascontiguousarray(mp_desc, np.uint8)
+    n = lib().orc_search_by_projection_sim3(C.byref(kf.c), len(a), _p(a), _p(uu), _p(vv), _p(lv), _p(d), int(th), _p(matched))
+    return n, matched
+
+
+def window_best(f, active, u, v, radius, pred_level, desc):
+    a = np.ascontiguousarray(active, np.uint8); uu = np.ascontiguousarray(u, np.float32); vv = np.ascontiguousarray(v, np.float32)
+    r = np.ascontiguousarray(radius, np.float32); lv = np.ascontiguousarray(pred_level, np.int32); d = np.ascontiguousarray(desc, np.uint8)
+    bi = np.zeros(len(a), np.int32); bd = np.zeros(len(a), np.int32)
+    lib().orc_window_best(C.byref(f.c), len(a), _p(a), _p(uu), _p(vv), _p(r), _p(lv), _p(d), _p(bi), _p(bd))
+    return bi, bd

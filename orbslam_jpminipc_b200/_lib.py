@@ -24,7 +24,7 @@ EXPORTS = [
     "orb_scale_factor", "orb_keypoint_capacity", "orb_extract", "orb_extract_batch", "orb_extract_batch_device", "orb_extract_batch_async", "orb_wait",
     "orb_last_launch_count", "orb_profile_enable", "orb_profile_read", "orb_profile_stage_name", "orb_debug_level_info", "orb_debug_level_plane", "orb_descriptor_distance",
     "orb_hamming_knn2", "orb_hamming_knn2_device", "orb_knn2_merge_device", "orb_match_ratio",
-    "orb_frame_grid_build", "orb_search_by_projection", "orb_search_window", "orb_search_for_initialization", "orb_search_by_bow", "orb_search_by_bow_kf", "orb_host_alloc", "orb_host_free",
+    "orb_frame_grid_build", "orb_search_by_projection", "orb_search_window", "orb_search_window_best", "orb_search_for_initialization", "orb_search_by_bow", "orb_search_by_bow_kf", "orb_host_alloc", "orb_host_free",
     "orb_measure_popc_peak",
     "orb_distinctive_descriptors", "orb_cvt_gray", "orb_extract_batch_color", "orb_undistort_keypoints", "orb_image_bounds",
     "orb_db_read_descriptors", "orb_db_write_descriptors", "orb_db_read_keypoints", "orb_db_write_keypoints",
@@ -104,6 +104,7 @@ def lib():
     L.orb_search_by_projection.argtypes = [vp, C.POINTER(FrameView), C.POINTER(FrameView), vp, vp, vp, vp,
                                            f32, i32, vp, C.POINTER(C.c_int)]
     L.orb_search_window.argtypes = [vp, C.POINTER(FrameView), C.POINTER(WindowQuerySet), i32, f32, i32, i32, vp, C.POINTER(C.c_int)]
+    L.orb_search_window_best.argtypes = [vp, C.POINTER(FrameView), C.POINTER(WindowQuerySet), vp, vp]
     L.orb_search_for_initialization.argtypes = [vp, C.POINTER(FrameView), C.POINTER(FrameView), vp, i32, f32, i32, vp, C.POINTER(C.c_int)]
     L.orb_search_by_bow.argtypes = [vp, C.POINTER(FeatVecView), vp, vp, vp, i32,
                                     C.POINTER(FeatVecView), vp, vp, i32, f32, i32, vp, C.POINTER(C.c_int)]

@@ -1,5 +1,6 @@
 // orb_api.cu — C ABI (include/orb_b200.h): context, device buffers, extraction entry points.
 #include "orb_internal.h"
+#include <climits>
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -807,6 +808,58 @@ int orb_search_for_initialization(orb_ctx* c, const orb_frame_view* f1, const or
     ORB_CUDA(cudaMemcpyAsync(res, d_result, sizeof res, cudaMemcpyDeviceToHost, s));
     ORB_CUDA(cudaStreamSynchronize(s));
     *nmatches = res[0];
+    return res[1] ? ORB_ERR_CAPACITY : ORB_OK;
+}
+
+int orb_search_window_best(orb_ctx* c, const orb_frame_view* target, const orb_window_query_set* q, int32_t* best_idx, int32_t* best_dist)
+{
+    if (!c || !target || !q || target->n < 0 || q->n < 0) return ORB_ERR_INVALID;
+    if (q->n == 0) return ORB_OK;
+    if (!best_idx || !best_dist) return ORB_ERR_INVALID;
+    ORB_CUDA(cudaSetDevice(c->device));
+    const bool dev = is_device_ptr(best_idx);
+    if (is_device_ptr(best_dist) != dev) return ORB_ERR_INVALID;
+    cudaStream_t s = c->streams[0];
+    if (target->n == 0) {                                   // no keypoints: nothing is ever in the radius
+        if (dev) { ORB_CUDA(cudaMemsetAsync(best_idx, 0xff, (size_t)q->n * 4, s)); ORB_CUDA(cudaMemsetAsync(best_dist, 0x7f, (size_t)q->n * 4, s)); ORB_CUDA(cudaStreamSynchronize(s)); }
+        else for (int i = 0; i < q->n; i++) { best_idx[i] = -1; best_dist[i] = INT_MAX; }
+        return ORB_OK;
+    }
+    const bool project = q->xyz != nullptr && q->u == nullptr;
+    if (!target->kps || !target->desc || !target->cell_start || !target->cell_items || !q->active || !q->desc ||
+        !q->min_level || !q->max_level || (!project && (!q->u || !q->v)) || (project && !q->Tcw16) ||
+        target->max_x <= target->min_x || target->max_y <= target->min_y) return ORB_ERR_INVALID;
+    if (is_device_ptr(target->kps) != dev || is_device_ptr(q->desc) != dev) return ORB_ERR_INVALID;
+    const size_t work = orb_sbp_scratch_bytes(target->n, q->n);
+    const size_t nq = (size_t)q->n;
+    const size_t in_bytes = dev ? 0 : frame_view_bytes(target) + al256(nq) + al256(nq * 32) + 7 * al256(nq * 4) + al256(nq * 12) + 2 * al256(nq * 4);
+    int rc = match_scratch(c, 256 + in_bytes + work, 256 + in_bytes + 4096);
+    if (rc) return rc;
+    Bump b(c->d_match_scratch, c->h_match_arena, c->match_scratch_bytes);
+    int* d_result = (int*)b.take(8);
+    orb_frame_view dt = *target;
+    orb_window_query_set dq = *q;
+    if ((rc = stage_frame(b, dev, dt, true, s))) return rc;
+    if ((rc = stage_in(b, dev, dq.active, nq, s)) || (rc = stage_in(b, dev, dq.desc, nq * 32, s)) ||
+        (rc = stage_in(b, dev, dq.u, nq, s)) || (rc = stage_in(b, dev, dq.v, nq, s)) || (rc = stage_in(b, dev, dq.xyz, nq * 3, s)) ||
+        (rc = stage_in(b, dev, dq.radius, nq, s)) || (rc = stage_in(b, dev, dq.min_level, nq, s)) ||
+        (rc = stage_in(b, dev, dq.max_level, nq, s))) return rc;
+    dq.angle = nullptr;
+    float T[16] = { 0 };
+    if (project) { if (is_device_ptr(q->Tcw16)) ORB_CUDA(cudaMemcpy(T, q->Tcw16, sizeof T, cudaMemcpyDeviceToHost)); else memcpy(T, q->Tcw16, sizeof T); }
+    dq.Tcw16 = T;
+    int32_t *d_bi = best_idx, *d_bd = best_dist;
+    if (!dev) { d_bi = (int32_t*)b.take(nq * 4); d_bd = (int32_t*)b.take(nq * 4); }
+    uint8_t* wk = (uint8_t*)b.take(work);
+    if ((rc = b.flush(s))) return rc;
+    if ((rc = orb_launch_search_window_best(c, &dt, &dq, d_bi, d_bd, d_result, wk, work, s))) return rc;
+    int res[2] = { 0, 0 };
+    if (!dev) {
+        ORB_CUDA(cudaMemcpyAsync(best_idx, d_bi, nq * 4, cudaMemcpyDeviceToHost, s));
+        ORB_CUDA(cudaMemcpyAsync(best_dist, d_bd, nq * 4, cudaMemcpyDeviceToHost, s));
+    }
+    ORB_CUDA(cudaMemcpyAsync(res, d_result, sizeof res, cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaStreamSynchronize(s));
     return res[1] ? ORB_ERR_CAPACITY : ORB_OK;
 }
 

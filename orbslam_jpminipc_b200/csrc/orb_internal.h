@@ -190,6 +190,8 @@ int orb_launch_search_by_bow(orb_ctx* c, const orb_featvec_view* kf_fv, const ui
 size_t orb_bow_scratch_bytes(int n_f);
 int orb_launch_search_window(orb_ctx* c, const orb_frame_view* tgt, const orb_window_query_set* q, int accept, float nnratio, int th_dist,
                              int histogram, int32_t* match, int* d_result, uint8_t* scratch, size_t scratch_bytes, cudaStream_t s);
+int orb_launch_search_window_best(orb_ctx* c, const orb_frame_view* tgt, const orb_window_query_set* q, int32_t* best_idx, int32_t* best_dist,
+                                  int* d_result, uint8_t* scratch, size_t scratch_bytes, cudaStream_t s);
 int orb_launch_distinctive(const uint8_t* d_desc, const int32_t* d_start, int npoints, int32_t* d_best_idx, int32_t* d_best_median,
                            cudaStream_t s);
 size_t orb_init_scratch_bytes(int n1, int n2);

@@ -1023,6 +1023,54 @@ int orb_launch_search_window(orb_ctx* c, const orb_frame_view* tgt, const orb_wi
     return ORB_OK;
 }
 
+// Best candidate per query WITHOUT claims: the scoring loops of ORBmatcher::Fuse (src/ORBmatcher.cc:1016-1134, :1136-1265) and of
+// both directions of SearchBySim3 (:1267-1505) only pick "the most similar keypoint in the radius"; what is done with it afterwards
+// (replace / add observations, agreement test) does not feed back into the search.  Strict '<' in scan order like the reference.
+__global__ void __launch_bounds__(256)
+k_win_best(WinArgs A, int32_t* __restrict__ best_idx, int32_t* __restrict__ best_dist, int* __restrict__ result)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.nq) return;
+    const int n = A.cnt[i];
+    int bd = INT_MAX, bi = -1;
+    if (n > A.cap) atomicExch(result + 1, 1);
+    else {
+        const uint32_t* L = A.list + (size_t)i * A.cap;
+        for (int p = 0; p < n; p++) {
+            const uint32_t e = L[p];
+            const int dist = (int)(e >> 22);
+            if (dist < bd) { bd = dist; bi = (int)(e & 0x3fffff); }
+        }
+    }
+    best_idx[i] = bi; best_dist[i] = bd;
+}
+
+int orb_launch_search_window_best(orb_ctx* c, const orb_frame_view* tgt, const orb_window_query_set* q, int32_t* best_idx, int32_t* best_dist,
+                                  int* d_result, uint8_t* scratch, size_t scratch_bytes, cudaStream_t s)
+{
+    (void)c;
+    WinArgs A;
+    A.tgt = *tgt; A.nq = q->n; A.active = q->active; A.qdesc = q->desc; A.u = q->u; A.v = q->v; A.xyz = q->xyz;
+    A.project = q->xyz != nullptr && q->u == nullptr;
+    for (int i = 0; i < 16; i++) A.T[i] = (A.project && q->Tcw16) ? q->Tcw16[i] : 0.f;
+    A.check_bounds = q->check_bounds; A.radius = q->radius; A.radius_const = q->radius_const;
+    A.minl = q->min_level; A.maxl = q->max_level; A.qangle = nullptr;
+    A.accept = 0; A.nnratio = 0.f; A.th_dist = 256; A.histogram = 0;
+    if (tgt->n >= (1 << 22)) return ORB_ERR_CAPACITY;
+    size_t off = 0;
+    A.cnt = (int*)(scratch + off); off += ((size_t)q->n * 4 + 255) & ~(size_t)255;
+    const size_t avail = scratch_bytes > off ? (scratch_bytes - off) / 4 : 0;
+    A.cap = (int)std::min<size_t>((size_t)tgt->n, q->n ? avail / (size_t)q->n : 0);
+    A.cap = std::min(A.cap, 1 << 20);
+    A.list = (uint32_t*)(scratch + off);
+    if (A.cap < 1) return ORB_ERR_CAPACITY;
+    ORB_CUDA(cudaMemsetAsync(d_result, 0, 8, s));
+    k_win_candidates<<<(q->n * 32 + 255) / 256, 256, 0, s>>>(A);
+    k_win_best<<<(q->n + 255) / 256, 256, 0, s>>>(A, best_idx, best_dist, d_result);
+    ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
+}
+
 // ------------------------------------------------------------------ MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:185-250)
 // One CTA of 64 threads per map point.  Row i's median is the k-th smallest (k = (int)(0.5*(N-1)), :236) of its N distances, found
 // by bisection on the value (distances are 0..256): 9 counting passes that recompute the distances from the descriptors in shared

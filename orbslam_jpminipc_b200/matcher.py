@@ -173,6 +173,66 @@ class ORBmatcher:
         return self._search_window(CurrentFrame, n, active, mp_desc, None, None, xyz, Tcw, 1, radius, 0.0, lv - 1, lv + 1, kf_angle,
                                    self.ACCEPT_BEST, int(ORBdist), self.mbCheckOrientation, match_cur)
 
+    # ---- back-end searches on pre-projected map points (the Sim3 / pose projection and the level prediction of the reference stay
+    #      in the adapter, like for SearchByProjectionKeyFrame)
+    @staticmethod
+    def _scale_factors(F):
+        sf = np.ones(F.nlevels, np.float32)
+        for i in range(1, F.nlevels):
+            sf[i] = np.float32(sf[i - 1] * np.float32(F.scale_factor))
+        return sf
+
+    def SearchByProjectionSim3(self, KF, active, u, v, pred_level, mp_desc, th, matched):
+        """ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (src/ORBmatcher.cc:286-407) from the radius search
+        on.  matched (in/out, one per KF keypoint): >= 0 where vpMatched is already set; returns (nmatches, matched)."""
+        lv = np.asarray(pred_level, np.int32)
+        radius = (np.float32(int(th)) * self._scale_factors(KF)[np.clip(lv, 0, KF.nlevels - 1)]).astype(np.float32)
+        return self._search_window(KF, len(lv), active, mp_desc, u, v, None, None, 0, radius, 0.0, lv - 1, lv, None,
+                                   self.ACCEPT_BEST, self.TH_LOW, False, matched)
+
+    def BestInWindow(self, F, active, u, v, radius, min_level, max_level, desc):
+        """orb_search_window_best: most similar keypoint in each query's radius, no claims -> (best_idx, best_dist)."""
+        keep = []
+
+        def arr(a, dt):
+            a = np.ascontiguousarray(a, dt)
+            keep.append(a)
+            return a.ctypes.data
+        n = len(active)
+        q = WindowQuerySet(n, arr(active, np.uint8), arr(desc, np.uint8), arr(u, np.float32), arr(v, np.float32), None, None, 0,
+                           arr(radius, np.float32), 0.0, arr(min_level, np.int32), arr(max_level, np.int32), None)
+        tv = F.view()
+        bi = np.full(n, -1, np.int32); bd = np.zeros(n, np.int32)
+        check(lib().orb_search_window_best(self._h, C.byref(tv), C.byref(q), ptr(bi), ptr(bd)), "orb_search_window_best")
+        return bi, bd
+
+    def FuseCandidates(self, KF, active, u, v, pred_level, mp_desc, th=2.5):
+        """Scoring loop of ORBmatcher::Fuse (src/ORBmatcher.cc:1016-1134; the Scw form :1136-1265 is the same after projection):
+        for every projected map point the KF keypoint it fuses with (bestDist <= TH_LOW), or -1.  Replace / AddObservation on the
+        result is graph bookkeeping and stays with the caller."""
+        lv = np.asarray(pred_level, np.int32)
+        radius = (np.float32(th) * self._scale_factors(KF)[np.clip(lv, 0, KF.nlevels - 1)]).astype(np.float32)
+        bi, bd = self.BestInWindow(KF, active, u, v, radius, lv - 1, lv, mp_desc)
+        return np.where(bd <= self.TH_LOW, bi, -1).astype(np.int32)
+
+    def SearchBySim3(self, KF1, KF2, act1, u12, v12, lvl12, desc1, act2, u21, v21, lvl21, desc2, th=7.5):
+        """ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:1267-1505).  act1/u12/v12/lvl12/desc1: map points of KF1 (one per KF1 keypoint)
+        projected into KF2 with their predicted level there; act2/... the other way round.  Returns (nFound, matches12) where
+        matches12[i1] = KF2 keypoint whose map point matches, or -1 (agreement test :1478-1493)."""
+        l12 = np.asarray(lvl12, np.int32); l21 = np.asarray(lvl21, np.int32)
+        r12 = (np.float32(th) * self._scale_factors(KF2)[np.clip(l12, 0, KF2.nlevels - 1)]).astype(np.float32)
+        r21 = (np.float32(th) * self._scale_factors(KF1)[np.clip(l21, 0, KF1.nlevels - 1)]).astype(np.float32)
+        b1, d1 = self.BestInWindow(KF2, act1, u12, v12, r12, l12 - 1, l12, desc1)
+        b2, d2 = self.BestInWindow(KF1, act2, u21, v21, r21, l21 - 1, l21, desc2)
+        m1 = np.where(d1 <= self.TH_HIGH, b1, -1)
+        m2 = np.where(d2 <= self.TH_HIGH, b2, -1)
+        out = np.full(len(m1), -1, np.int32)
+        ok = m1 >= 0
+        idx = np.flatnonzero(ok)
+        agree = m2[m1[idx]] == idx
+        out[idx[agree]] = m1[idx[agree]]
+        return int(agree.sum()), out
+
     def ComputeDistinctiveDescriptors(self, desc, start):
         """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:185-250) for many map points: desc = all observation descriptors,
         start = CSR offsets per point.  Returns (BestIdx within each group or -1, BestMedian)."""

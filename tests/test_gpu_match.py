@@ -451,3 +451,70 @@ def test_distinctive_descriptors_vs_oracle(pkg, po, npoints, maxobs, seed):
     rbi, rbm = po.distinctive_descriptors(desc, start)
     assert np.array_equal(bi, rbi) and np.array_equal(bm, rbm)
     assert bi[0] == -1 and (bi[1:3] == 0).all()
+
+
+def _projected_points(rng, src, dst_w, dst_h, jitter=3.0):
+    """Map points observed at src keypoints, 'projected' into another keyframe near the same place, with a predicted level."""
+    n = len(src)
+    u = (src["x"] + rng.normal(0, jitter, n)).astype(np.float32)
+    v = (src["y"] + rng.normal(0, jitter, n)).astype(np.float32)
+    lvl = np.clip(src["octave"] + rng.integers(0, 2, n), 0, 7).astype(np.int32)
+    active = ((rng.random(n) < 0.85) & (u >= 0) & (u < dst_w) & (v >= 0) & (v < dst_h)).astype(np.uint8)
+    return active, u, v, lvl
+
+
+@pytest.mark.parametrize("shape,nf,th", [((240, 320), 500, 10), ((480, 752), 1000, 10), ((376, 1241), 2000, 4)])
+def test_search_by_projection_sim3_vs_oracle(pkg, po, shape, nf, th):
+    """ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th), src/ORBmatcher.cc:286-407 (loop closing, :389)."""
+    m = pkg.ORBmatcher(0.75, True)
+    gcur, glast, ocur, olast, has, outl, xyz, T = _scene(po, pkg, m, shape[0], shape[1], nf, 8500 + nf, 15.0)
+    rng = np.random.default_rng(nf)
+    active, u, v, lvl = _projected_points(rng, glast.kps, shape[1], shape[0])
+    pre = np.full(gcur.N, -1, np.int32)
+    pre[::7] = 1 << 20                                     # vpMatched already holds a point there
+    n, match = m.SearchByProjectionSim3(gcur, active, u, v, lvl, glast.desc, th, pre.copy())
+    rn, rmatch = po.search_by_projection_sim3(ocur, active, u, v, lvl, glast.desc, th, pre.copy())
+    assert rn > 10 and n == rn and np.array_equal(match, rmatch)
+
+
+@pytest.mark.parametrize("shape,nf,th", [((240, 320), 500, 2.5), ((480, 752), 1000, 2.5), ((376, 1241), 2000, 7.5)])
+def test_fuse_and_sim3_candidates_vs_oracle(pkg, po, shape, nf, th):
+    """Scoring loops of ORBmatcher::Fuse (src/ORBmatcher.cc:1016-1265) and SearchBySim3 (:1267-1505): independent best per point."""
+    m = pkg.ORBmatcher(0.75, True)
+    gcur, glast, ocur, olast, has, outl, xyz, T = _scene(po, pkg, m, shape[0], shape[1], nf, 8600 + nf, 15.0)
+    rng = np.random.default_rng(nf + 1)
+    a1, u1, v1, l1 = _projected_points(rng, glast.kps, shape[1], shape[0])
+    a2, u2, v2, l2 = _projected_points(rng, gcur.kps, shape[1], shape[0])
+    sf = np.ones(8, np.float32)
+    for i in range(1, 8):
+        sf[i] = np.float32(sf[i - 1] * np.float32(1.2))
+    # Fuse: map points seen in `last` fused into `cur`
+    fused = m.FuseCandidates(gcur, a1, u1, v1, l1, glast.desc, th)
+    rbi, rbd = po.window_best(ocur, a1, u1, v1, np.float32(th) * sf[l1], l1, glast.desc)
+    assert np.array_equal(fused, np.where(rbd <= 50, rbi, -1)) and (fused >= 0).sum() > 10
+    bi, bd = m.BestInWindow(gcur, a1, u1, v1, np.float32(th) * sf[l1], l1 - 1, l1, glast.desc)
+    assert np.array_equal(bi, rbi) and np.array_equal(bd, rbd)
+    # SearchBySim3: both directions + agreement
+    nfound, m12 = m.SearchBySim3(glast, gcur, a1, u1, v1, l1, glast.desc, a2, u2, v2, l2, gcur.desc, th)
+    b1, d1 = po.window_best(ocur, a1, u1, v1, np.float32(th) * sf[l1], l1, glast.desc)
+    b2, d2 = po.window_best(olast, a2, u2, v2, np.float32(th) * sf[l2], l2, gcur.desc)
+    exp = np.full(glast.N, -1, np.int32)
+    for i1 in range(glast.N):                              # src/ORBmatcher.cc:1478-1493
+        idx2 = b1[i1] if d1[i1] <= 100 else -1
+        if idx2 >= 0 and (b2[idx2] if d2[idx2] <= 100 else -1) == i1:
+            exp[i1] = idx2
+    assert nfound == (exp >= 0).sum() > 5 and np.array_equal(m12, exp)
+
+
+def test_window_best_empty_cases(pkg):
+    m = pkg.ORBmatcher(0.75, True)
+    k = np.zeros(0, pkg.KP_DTYPE); d = np.zeros((0, 32), np.uint8)
+    E = pkg.Frame(m, k, d, 320, 240, 300.0, 300.0, 160.0, 120.0)
+    q = np.zeros((4, 32), np.uint8)
+    bi, bd = m.BestInWindow(E, np.ones(4, np.uint8), np.full(4, 50.0), np.full(4, 50.0), np.full(4, 10.0), np.zeros(4), np.zeros(4), q)
+    assert (bi == -1).all() and (bd == np.iinfo(np.int32).max).all()
+    k1 = np.zeros(3, pkg.KP_DTYPE); k1["x"] = [10, 50, 52]; k1["y"] = [10, 50, 50]
+    F = pkg.Frame(m, k1, np.zeros((3, 32), np.uint8), 320, 240, 300.0, 300.0, 160.0, 120.0)
+    bi, bd = m.BestInWindow(F, np.array([1, 0, 1, 1], np.uint8), np.array([50, 50, 300, 51], np.float32), np.array([50, 50, 200, 50], np.float32),
+                            np.full(4, 5.0, np.float32), np.full(4, -1), np.full(4, 0), q)
+    assert list(bi) == [1, -1, -1, 1] and list(bd[[0, 3]]) == [0, 0]      # ties keep the first in scan order
