@@ -7,7 +7,7 @@
  *   SearchByProjection(Frame&, vector<MapPoint*>, th) (:49-125), WindowSearch (:409-516),
  *   SearchByProjection(F1, F2, windowSize, ...) (:519-594), SearchByProjection(Frame&, KeyFrame*, ...) (:1622-1746),
  *   SearchForInitialization (:598-713), SearchByProjection(KeyFrame*, Scw, ...) (:286-407), the scoring loops of Fuse
- *   (:1016-1265) and SearchBySim3 (:1267-1505)
+ *   (:1016-1265) and SearchBySim3 (:1267-1505), SearchForTriangulation (:852-1014)
  * plus the brute-force best/second-best + ratio test used for relocalisation-sized searches.
  * Frame / KeyFrame / MapPoint are the reference's own graph classes and stay on the host: the shim
  * takes the plain arrays those methods read (see INTEGRATION.md for the adapter code).
@@ -17,6 +17,7 @@
 
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 #include "orb_b200.h"
 
@@ -184,6 +185,23 @@ public:
         int n = 0;
         check(orb_search_by_bow_kf(ctx, &fv1, desc1, kps1, valid1, n1, &fv2, desc2, kps2, valid2, n2, mfNNratio,
                                    mbCheckOrientation ? 1 : 0, matches12.data(), &n));
+        return n;
+    }
+
+    // SearchForTriangulation (src/ORBmatcher.cc:852-1014): vMatchedPairs = (index in KF1, index in KF2); F12 = 3x3 CV_32F row major,
+    // levelSigma2 = pKF2's mvLevelSigma2
+    int SearchForTriangulation(const orb_featvec_view& fv1, const FrameArrays& KF1, const std::vector<unsigned char>& hasMapPoint1,
+                               const orb_featvec_view& fv2, const FrameArrays& KF2, const std::vector<unsigned char>& hasMapPoint2,
+                               const float* F12, const std::vector<float>& levelSigma2,
+                               std::vector<std::pair<size_t, size_t> >& vMatchedPairs)
+    {
+        std::vector<int32_t> m12(KF1.mvKeysUn.size(), -1);
+        int n = 0;
+        check(orb_search_for_triangulation(ctx, &fv1, KF1.mDescriptors.data(), KF1.mvKeysUn.data(), hasMapPoint1.data(), (int)KF1.mvKeysUn.size(),
+                                           &fv2, KF2.mDescriptors.data(), KF2.mvKeysUn.data(), hasMapPoint2.data(), (int)KF2.mvKeysUn.size(),
+                                           F12, levelSigma2.data(), (int)levelSigma2.size(), mbCheckOrientation ? 1 : 0, m12.data(), &n));
+        vMatchedPairs.clear();
+        for (size_t i = 0; i < m12.size(); i++) if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)m12[i]));
         return n;
     }
 

@@ -234,6 +234,17 @@ int orb_search_by_bow_kf(orb_ctx*, const orb_featvec_view* fv1, const uint8_t* d
 int orb_distinctive_descriptors(orb_ctx*, const uint8_t* desc, const int32_t* start, int npoints, int32_t* best_idx,
                                 int32_t* best_median);
 
+/* ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedKeys1, vMatchedKeys2, vMatchedPairs), src/ORBmatcher.cc:852-1014
+ * (LocalMapping::CreateNewMapPoints, src/LocalMapping.cc:274): features of two keyframes without a map point, joined through the
+ * shared vocabulary nodes, distance <= TH_LOW and within 2*BestDist, epipolar test CheckDistEpipolarLine (:136-153) with the
+ * 3x3 CV_32F fundamental matrix F12 (row major) and pKF2's level_sigma2[nlevels] (mvLevelSigma2), rotation histogram.
+ * has_mp1/2[i] != 0: the feature already has a map point.  match12[n1] out = index in KF2 or -1; vMatchedPairs are the pairs
+ * (i, match12[i]) in ascending i. */
+int orb_search_for_triangulation(orb_ctx*, const orb_featvec_view* fv1, const uint8_t* desc1, const orb_keypoint* kps1,
+                                 const uint8_t* has_mp1, int n1, const orb_featvec_view* fv2, const uint8_t* desc2,
+                                 const orb_keypoint* kps2, const uint8_t* has_mp2, int n2, const float* F12, const float* level_sigma2,
+                                 int nlevels, int check_ori, int32_t* match12, int* nmatches);
+
 /* ---- frame plumbing on either side of the extractor (reference src/Tracking.cc:200-212, src/Frame.cc:289-349) ---- */
 enum { ORB_RGB = 0, ORB_BGR = 1 };
 /* cvtColor(image, im, CV_RGB2GRAY / CV_BGR2GRAY) of Tracking::GrabImage (src/Tracking.cc:202-208) for nimg interleaved 8-bit

@@ -1155,6 +1155,78 @@ void orc_window_best(const orc_frame* f, int nq, const uint8_t* active, const fl
     }
 }
 
+/* ORBmatcher::CheckDistEpipolarLine, src/ORBmatcher.cc:136-153 */
+static bool check_dist_epipolar_line(const orc_keypoint& kp1, const orc_keypoint& kp2, const float* F12, const float* sigma2)
+{
+    const float a = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+    const float b = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+    const float c = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+    const float num = a * kp2.x + b * kp2.y + c;
+    const float den = a * a + b * b;
+    if (den == 0) return false;
+    const float dsqr = num * num / den;
+    return dsqr < 3.84 * sigma2[kp2.octave];
+}
+
+/* src/ORBmatcher.cc:852-1014 */
+int orc_search_for_triangulation(const orc_featvec* fv1, const uint8_t* desc1, const orc_keypoint* kps1, const uint8_t* has_mp1, int n1,
+                                 const orc_featvec* fv2, const uint8_t* desc2, const orc_keypoint* kps2, const uint8_t* has_mp2, int n2,
+                                 const float* F12, const float* level_sigma2, int check_ori, int32_t* vMatches12)
+{
+    const int HISTO_LENGTH = 30, TH_LOW = 50;
+    int nmatches = 0;
+    std::vector<char> vbMatched2(n2 > 0 ? n2 : 1, 0);
+    for (int i = 0; i < n1; i++) vMatches12[i] = -1;
+    std::vector<int> rotHist[30];
+    int a = 0, b = 0;
+    while (a < fv1->nnodes && b < fv2->nnodes) {
+        if (fv1->node_id[a] == fv2->node_id[b]) {
+            for (int i1 = fv1->start[a]; i1 < fv1->start[a + 1]; i1++) {
+                const int idx1 = fv1->items[i1];
+                if (has_mp1[idx1]) continue;
+                std::vector<std::pair<int, size_t> > vDistIndex;
+                for (int i2 = fv2->start[b]; i2 < fv2->start[b + 1]; i2++) {
+                    const int idx2 = fv2->items[i2];
+                    if (vbMatched2[idx2] || has_mp2[idx2]) continue;
+                    const int dist = orc_descriptor_distance(desc1 + (size_t)idx1 * 32, desc2 + (size_t)idx2 * 32);
+                    if (dist > TH_LOW) continue;
+                    vDistIndex.push_back(std::make_pair(dist, (size_t)idx2));
+                }
+                if (vDistIndex.empty()) continue;
+                std::sort(vDistIndex.begin(), vDistIndex.end());
+                const int BestDist = vDistIndex.front().first;
+                const int DistTh = (int)round(2 * BestDist);
+                for (size_t id = 0; id < vDistIndex.size(); id++) {
+                    if (vDistIndex[id].first > DistTh) break;
+                    const int currentIdx2 = (int)vDistIndex[id].second;
+                    if (check_dist_epipolar_line(kps1[idx1], kps2[currentIdx2], F12, level_sigma2)) {
+                        vbMatched2[currentIdx2] = 1;
+                        vMatches12[idx1] = currentIdx2;
+                        nmatches++;
+                        if (check_ori) rotHist[rot_bin(kps1[idx1].angle, kps2[currentIdx2].angle)].push_back(idx1);
+                        break;
+                    }
+                }
+            }
+            a++; b++;
+        } else if (fv1->node_id[a] < fv2->node_id[b]) {
+            while (a < fv1->nnodes && fv1->node_id[a] < fv2->node_id[b]) a++;
+        } else {
+            while (b < fv2->nnodes && fv2->node_id[b] < fv1->node_id[a]) b++;
+        }
+    }
+    if (check_ori) {
+        int hs[30], i1, i2, i3;
+        for (int i = 0; i < HISTO_LENGTH; i++) hs[i] = (int)rotHist[i].size();
+        orc_three_maxima(hs, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == i1 || i == i2 || i == i3) continue;
+            for (int id : rotHist[i]) { vMatches12[id] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
 /* ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...), src/ORBmatcher.cc:715-850 */
 int orc_search_by_bow_kf(const orc_featvec* fv1, const uint8_t* desc1, const orc_keypoint* kps1, const uint8_t* valid1, int n1,
                          const orc_featvec* fv2, const uint8_t* desc2, const orc_keypoint* kps2, const uint8_t* valid2, int n2,

@@ -161,6 +161,13 @@ int   orc_search_by_projection_sim3(const orc_frame* kf, int nmp, const uint8_t*
 void  orc_window_best(const orc_frame* f, int nq, const uint8_t* active, const float* u, const float* v, const float* radius,
                       const int32_t* pred_level, const uint8_t* desc, int32_t* best_idx, int32_t* best_dist);
 
+/* ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, ...), src/ORBmatcher.cc:852-1014 with CheckDistEpipolarLine (:136-153).
+ * has_mp1/2: the feature already has a map point (skipped); F12: 3x3 CV_32F row major; level_sigma2 = pKF2's mvLevelSigma2.
+ * match12[n1] out = idx2 or -1 (vMatchedPairs = the pairs (i, match12[i]) in ascending i). */
+int   orc_search_for_triangulation(const orc_featvec* fv1, const uint8_t* desc1, const orc_keypoint* kps1, const uint8_t* has_mp1, int n1,
+                                   const orc_featvec* fv2, const uint8_t* desc2, const orc_keypoint* kps2, const uint8_t* has_mp2, int n2,
+                                   const float* F12, const float* level_sigma2, int check_ori, int32_t* match12);
+
 /* ---- DBoW2 vocabulary, Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h ---- */
 typedef struct orc_vocab orc_vocab;
 enum { ORC_L1_NORM = 0, ORC_L2_NORM, ORC_CHI_SQUARE, ORC_KL, ORC_BHATTACHARYYA, ORC_DOT_PRODUCT };   /* BowVector.h:45-53 */

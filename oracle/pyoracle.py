@@ -114,6 +114,7 @@ def lib():
         L.orc_harris_response.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.orc_search_by_projection_sim3.argtypes = [C.POINTER(_Frame), C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
         L.orc_window_best.argtypes = [C.POINTER(_Frame), C.c_int] + [C.c_void_p] * 8
+        L.orc_search_for_triangulation.argtypes = [C.POINTER(_FeatVec), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(_FeatVec), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.orc_three_maxima.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 3
         _lib = L
     return _lib
@@ -533,3 +534,16 @@ def window_best(f, active, u, v, radius, pred_level, desc):
     bi = np.zeros(len(a), np.int32); bd = np.zeros(len(a), np.int32)
     lib().orc_window_best(C.byref(f.c), len(a), _p(a), _p(uu), _p(vv), _p(r), _p(lv), _p(d), _p(bi), _p(bd))
     return bi, bd
+
+
+def search_for_triangulation(fv1, desc1, kps1, has_mp1, fv2, desc2, kps2, has_mp2, F12, level_sigma2, check_ori=True):
+    a, keep_a = _fv(*fv1)
+    b, keep_b = _fv(*fv2)
+    desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
+    kps1 = np.ascontiguousarray(kps1, KP_DTYPE); kps2 = np.ascontiguousarray(kps2, KP_DTYPE)
+    h1 = np.ascontiguousarray(has_mp1, np.uint8); h2 = np.ascontiguousarray(has_mp2, np.uint8)
+    F = np.ascontiguousarray(F12, np.float32).reshape(9); sg = np.ascontiguousarray(level_sigma2, np.float32)
+    m = np.full(len(kps1), -1, np.int32)
+    n = lib().orc_search_for_triangulation(C.byref(a), _p(desc1), _p(kps1), _p(h1), len(kps1), C.byref(b), _p(desc2), _p(kps2), _p(h2),
+                                           len(kps2), _p(F), _p(sg), int(check_ori), _p(m))
+    return n, m

@@ -974,6 +974,56 @@ int orb_search_by_bow_kf(orb_ctx* c, const orb_featvec_view* fv1, const uint8_t*
     return search_by_bow_impl(c, fv1, desc1, kps1, valid1, n1, fv2, desc2, kps2, n2, nnratio, check_ori, nullptr, nmatches, valid2, match12);
 }
 
+int orb_search_for_triangulation(orb_ctx* c, const orb_featvec_view* fv1, const uint8_t* desc1, const orb_keypoint* kps1,
+                                 const uint8_t* has_mp1, int n1, const orb_featvec_view* fv2, const uint8_t* desc2,
+                                 const orb_keypoint* kps2, const uint8_t* has_mp2, int n2, const float* F12, const float* level_sigma2,
+                                 int nlevels, int check_ori, int32_t* match12, int* nmatches)
+{
+    if (!c || !fv1 || !fv2 || !nmatches || n1 < 0 || n2 < 0 || fv1->nnodes < 0 || fv2->nnodes < 0 || !F12 || !level_sigma2 ||
+        nlevels < 1 || nlevels > ORB_MAX_LEVELS) return ORB_ERR_INVALID;
+    *nmatches = 0;
+    if (n1 == 0) return ORB_OK;
+    if (!match12 || !desc1 || !kps1 || !has_mp1 || (n2 > 0 && (!desc2 || !kps2 || !has_mp2))) return ORB_ERR_INVALID;
+    ORB_CUDA(cudaSetDevice(c->device));
+    const bool dev = is_device_ptr(desc1);
+    if (is_device_ptr(match12) != dev) return ORB_ERR_INVALID;
+    cudaStream_t s = c->streams[0];
+    int t1 = 0, t2 = 0;
+    if (fv1->nnodes) { if (dev) ORB_CUDA(cudaMemcpy(&t1, fv1->start + fv1->nnodes, 4, cudaMemcpyDeviceToHost)); else t1 = fv1->start[fv1->nnodes]; }
+    if (fv2->nnodes) { if (dev) ORB_CUDA(cudaMemcpy(&t2, fv2->start + fv2->nnodes, 4, cudaMemcpyDeviceToHost)); else t2 = fv2->start[fv2->nnodes]; }
+    const size_t work = orb_tri_scratch_bytes(n1, n2);
+    size_t in_bytes = 0;
+    if (!dev) in_bytes = al256((size_t)n1 * 32) + al256((size_t)n1 * 28) + al256(n1) + al256((size_t)n2 * 32 + 32) + al256((size_t)n2 * 28 + 28) + al256(n2 + 1) +
+                         2 * al256((size_t)(fv1->nnodes + 1) * 4) + al256((size_t)t1 * 4 + 4) + 2 * al256((size_t)(fv2->nnodes + 1) * 4) + al256((size_t)t2 * 4 + 4) +
+                         al256((size_t)n1 * 4) + 4096;
+    int rc = match_scratch(c, in_bytes + work + 256, in_bytes + 4096);
+    if (rc) return rc;
+    Bump b(c->d_match_scratch, c->h_match_arena, c->match_scratch_bytes);
+    orb_featvec_view a = *fv1, f = *fv2;
+    static const int32_t zero_start[1] = { 0 };
+    if (!dev) { if (!a.start) a.start = zero_start; if (!f.start) f.start = zero_start; }
+    if ((rc = stage_in(b, dev, a.node_id, (size_t)a.nnodes, s)) || (rc = stage_in(b, dev, a.start, (size_t)a.nnodes + 1, s)) ||
+        (rc = stage_in(b, dev, a.items, (size_t)t1, s)) || (rc = stage_in(b, dev, f.node_id, (size_t)f.nnodes, s)) ||
+        (rc = stage_in(b, dev, f.start, (size_t)f.nnodes + 1, s)) || (rc = stage_in(b, dev, f.items, (size_t)t2, s)) ||
+        (rc = stage_in(b, dev, desc1, (size_t)n1 * 32, s)) || (rc = stage_in(b, dev, kps1, (size_t)n1, s)) ||
+        (rc = stage_in(b, dev, has_mp1, (size_t)n1, s)) || (rc = stage_in(b, dev, desc2, (size_t)n2 * 32, s)) ||
+        (rc = stage_in(b, dev, kps2, (size_t)n2, s)) || (rc = stage_in(b, dev, has_mp2, (size_t)n2, s))) return rc;
+    int32_t* d_m12 = dev ? match12 : (int32_t*)b.take((size_t)n1 * 4);
+    uint8_t* wk = (uint8_t*)b.take(work);
+    if ((rc = b.flush(s))) return rc;
+    float F[9], sg[ORB_MAX_LEVELS];
+    if (is_device_ptr(F12)) ORB_CUDA(cudaMemcpy(F, F12, sizeof F, cudaMemcpyDeviceToHost)); else memcpy(F, F12, sizeof F);
+    if (is_device_ptr(level_sigma2)) ORB_CUDA(cudaMemcpy(sg, level_sigma2, (size_t)nlevels * 4, cudaMemcpyDeviceToHost)); else memcpy(sg, level_sigma2, (size_t)nlevels * 4);
+    rc = orb_launch_search_for_triangulation(&a, desc1, kps1, has_mp1, n1, &f, desc2, kps2, has_mp2, n2, t2, F, sg, nlevels, check_ori, d_m12, wk, s);
+    if (rc) return rc;
+    int res = 0;
+    if (!dev) ORB_CUDA(cudaMemcpyAsync(match12, d_m12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaMemcpyAsync(&res, wk, sizeof res, cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaStreamSynchronize(s));
+    *nmatches = res;
+    return ORB_OK;
+}
+
 int orb_measure_popc_peak(orb_ctx* c, double* gpopc_per_s)
 {
     if (!c || !gpopc_per_s) return ORB_ERR_INVALID;

@@ -192,6 +192,11 @@ int orb_launch_search_window(orb_ctx* c, const orb_frame_view* tgt, const orb_wi
                              int histogram, int32_t* match, int* d_result, uint8_t* scratch, size_t scratch_bytes, cudaStream_t s);
 int orb_launch_search_window_best(orb_ctx* c, const orb_frame_view* tgt, const orb_window_query_set* q, int32_t* best_idx, int32_t* best_dist,
                                   int* d_result, uint8_t* scratch, size_t scratch_bytes, cudaStream_t s);
+size_t orb_tri_scratch_bytes(int n1, int n2);
+int orb_launch_search_for_triangulation(const orb_featvec_view* fv1, const uint8_t* desc1, const orb_keypoint* kps1, const uint8_t* has_mp1,
+                                        int n1, const orb_featvec_view* fv2, const uint8_t* desc2, const orb_keypoint* kps2,
+                                        const uint8_t* has_mp2, int n2, int items2_total, const float* F12, const float* sigma2, int nlevels,
+                                        int check_ori, int32_t* match12, uint8_t* scratch, cudaStream_t s);
 int orb_launch_distinctive(const uint8_t* d_desc, const int32_t* d_start, int npoints, int32_t* d_best_idx, int32_t* d_best_median,
                            cudaStream_t s);
 size_t orb_init_scratch_bytes(int n1, int n2);

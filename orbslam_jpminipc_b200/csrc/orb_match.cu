@@ -990,6 +990,157 @@ int orb_launch_search_by_bow(orb_ctx* c, const orb_featvec_view* kf_fv, const ui
     return ORB_OK;
 }
 
+// ------------------------------------------------------------------ ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:852-1014)
+// Same vocabulary-node join as SearchByBoW, between the features of two keyframes that have no map point yet.  Per feature of
+// KF1 the reference sorts the unclaimed candidates with dist <= TH_LOW by (dist, index), and takes the first one within
+// 2 * BestDist that passes the epipolar test (:136-153); that is the minimum of (dist, index) over the passing candidates, so a warp
+// needs two sweeps (smallest distance, then smallest passing key) and no sort.  Claims couple only features of one node.
+struct TriArgs {
+    orb_featvec_view fv1, fv2;
+    const uint8_t* desc1; const orb_keypoint* kps1; const uint8_t* has_mp1; int n1;
+    const uint8_t* desc2; const orb_keypoint* kps2; const uint8_t* has_mp2; int n2;
+    float F[9]; float sigma2[ORB_MAX_LEVELS];
+    int check_ori;
+    int32_t* match12; int32_t* matched2; int8_t* bin_of; int* hist; int* result; int* seen;
+};
+
+__device__ __forceinline__ bool epipolar_ok(const TriArgs& A, const orb_keypoint& k1, const orb_keypoint& k2)
+{
+    const float a = __fadd_rn(__fadd_rn(__fmul_rn(k1.x, A.F[0]), __fmul_rn(k1.y, A.F[3])), A.F[6]);
+    const float b = __fadd_rn(__fadd_rn(__fmul_rn(k1.x, A.F[1]), __fmul_rn(k1.y, A.F[4])), A.F[7]);
+    const float c = __fadd_rn(__fadd_rn(__fmul_rn(k1.x, A.F[2]), __fmul_rn(k1.y, A.F[5])), A.F[8]);
+    const float num = __fadd_rn(__fadd_rn(__fmul_rn(a, k2.x), __fmul_rn(b, k2.y)), c);
+    const float den = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
+    if (den == 0.f) return false;
+    const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+    const int oct = min(max(k2.octave, 0), ORB_MAX_LEVELS - 1);
+    return (double)dsqr < __dmul_rn(3.84, (double)A.sigma2[oct]);
+}
+
+__global__ void k_tri_check(TriArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = A.fv2.start[A.fv2.nnodes];
+    if (j < total) { if (atomicAdd(&A.seen[A.fv2.items[j]], 1) > 0) A.result[1] = 1; }
+}
+
+__global__ void __launch_bounds__(256)
+k_tri_match(TriArgs A)
+{
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const bool serial = A.result[1] != 0;
+    if (serial && gw != 0) return;
+    int local_matches = 0;
+    for (int a = serial ? 0 : gw; a < A.fv1.nnodes; a += serial ? 1 : nw) {
+        const int node = A.fv1.node_id[a];
+        int lo = 0, hi = A.fv2.nnodes;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (A.fv2.node_id[mid] < node) lo = mid + 1; else hi = mid; }
+        if (lo >= A.fv2.nnodes || A.fv2.node_id[lo] != node) continue;
+        const int fb = A.fv2.start[lo], fe = A.fv2.start[lo + 1];
+        for (int ik = A.fv1.start[a]; ik < A.fv1.start[a + 1]; ik++) {
+            const int idx1 = A.fv1.items[ik];
+            if (A.has_mp1[idx1]) continue;                                        // :891-893
+            uint32_t q[8];
+            {
+                const uint4* qp = reinterpret_cast<const uint4*>(A.desc1 + (size_t)idx1 * 32);
+                const uint4 x = __ldg(qp), y = __ldg(qp + 1);
+                q[0] = x.x; q[1] = x.y; q[2] = x.z; q[3] = x.w; q[4] = y.x; q[5] = y.y; q[6] = y.z; q[7] = y.w;
+            }
+            int best = INT_MAX;                                                   // BestDist over the admissible candidates (:901-925)
+            for (int jf = fb + lane; jf < fe; jf += 32) {
+                const int idx2 = A.fv2.items[jf];
+                if (((volatile int32_t*)A.matched2)[idx2] >= 0 || A.has_mp2[idx2]) continue;
+                best = min(best, hamming256(q, A.desc2 + (size_t)idx2 * 32));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+            if (best > TH_LOW) continue;
+            const int dist_th = 2 * best;                                         // round(2*BestDist), :927
+            const orb_keypoint k1 = A.kps1[idx1];
+            uint32_t key = 0xffffffffu;                                           // (dist, idx2): first passing entry of the sorted list
+            for (int jf = fb + lane; jf < fe; jf += 32) {
+                const int idx2 = A.fv2.items[jf];
+                if (((volatile int32_t*)A.matched2)[idx2] >= 0 || A.has_mp2[idx2]) continue;
+                const int dist = hamming256(q, A.desc2 + (size_t)idx2 * 32);
+                if (dist > TH_LOW || dist > dist_th) continue;
+                if (!epipolar_ok(A, k1, A.kps2[idx2])) continue;
+                key = min(key, ((uint32_t)dist << 22) | (uint32_t)idx2);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+            if (key == 0xffffffffu) continue;
+            const int idx2 = (int)(key & 0x3fffff);
+            if (lane == 0) {
+                A.matched2[idx2] = idx1;
+                A.match12[idx1] = idx2;
+                if (A.check_ori) {
+                    const int b = rot_bin(k1.angle, A.kps2[idx2].angle);
+                    A.bin_of[idx1] = (int8_t)b;
+                    atomicAdd(&A.hist[b], 1);
+                }
+            }
+            local_matches++;
+            __threadfence_block();
+            __syncwarp();
+        }
+    }
+    if (lane == 0 && local_matches) atomicAdd(&A.result[0], local_matches);
+}
+
+__global__ void __launch_bounds__(256)
+k_tri_orientation(TriArgs A)
+{
+    __shared__ int s_removed;
+    if (threadIdx.x == 0) s_removed = 0;
+    __syncthreads();
+    int i1, i2, i3;
+    three_maxima(A.hist, i1, i2, i3);
+    int removed = 0;
+    for (int k = threadIdx.x; k < A.n1; k += blockDim.x) {
+        const int b = A.bin_of[k];
+        if (b >= 0 && b != i1 && b != i2 && b != i3) { A.match12[k] = -1; removed++; }
+    }
+    if (removed) atomicAdd(&s_removed, removed);
+    __syncthreads();
+    if (threadIdx.x == 0) A.result[0] -= s_removed;
+}
+
+size_t orb_tri_scratch_bytes(int n1, int n2)
+{
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    return 256 + al((size_t)std::max(n2, 1) * 4) * 2 + al((size_t)std::max(n1, 1)) + 256;
+}
+
+// scratch: result[2] + hist[30] (256 B) | seen[n2] | matched2[n2] | bin_of[n1]
+int orb_launch_search_for_triangulation(const orb_featvec_view* fv1, const uint8_t* desc1, const orb_keypoint* kps1, const uint8_t* has_mp1,
+                                        int n1, const orb_featvec_view* fv2, const uint8_t* desc2, const orb_keypoint* kps2,
+                                        const uint8_t* has_mp2, int n2, int items2_total, const float* F12, const float* sigma2, int nlevels,
+                                        int check_ori, int32_t* match12, uint8_t* scratch, cudaStream_t s)
+{
+    if (n2 >= (1 << 22)) return ORB_ERR_CAPACITY;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    TriArgs A;
+    A.fv1 = *fv1; A.fv2 = *fv2; A.desc1 = desc1; A.kps1 = kps1; A.has_mp1 = has_mp1; A.n1 = n1;
+    A.desc2 = desc2; A.kps2 = kps2; A.has_mp2 = has_mp2; A.n2 = n2; A.check_ori = check_ori; A.match12 = match12;
+    for (int i = 0; i < 9; i++) A.F[i] = F12[i];
+    for (int i = 0; i < ORB_MAX_LEVELS; i++) A.sigma2[i] = nlevels > 0 ? sigma2[std::min(i, nlevels - 1)] : 1.f;
+    const size_t b2 = al((size_t)std::max(n2, 1) * 4);
+    A.result = (int*)scratch; A.hist = (int*)scratch + 2;
+    A.seen = (int*)(scratch + 256);
+    A.matched2 = (int32_t*)(scratch + 256 + b2);
+    A.bin_of = (int8_t*)(scratch + 256 + 2 * b2);
+    ORB_CUDA(cudaMemsetAsync(scratch, 0, 256 + b2, s));
+    ORB_CUDA(cudaMemsetAsync(A.matched2, 0xff, b2, s));
+    ORB_CUDA(cudaMemsetAsync(A.bin_of, 0xff, (size_t)std::max(n1, 1), s));
+    ORB_CUDA(cudaMemsetAsync(match12, 0xff, (size_t)std::max(n1, 1) * 4, s));
+    if (items2_total > 0) k_tri_check<<<(items2_total + 255) / 256, 256, 0, s>>>(A);
+    if (fv1->nnodes > 0 && n2 > 0) k_tri_match<<<std::max(1, std::min(148, (fv1->nnodes + 7) / 8)), 256, 0, s>>>(A);
+    if (check_ori) k_tri_orientation<<<1, 256, 0, s>>>(A);
+    ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
+}
+
 size_t orb_bow_scratch_bytes(int n_f)
 {
     return 256 + (((size_t)n_f * 4 + 255) & ~(size_t)255) + (((size_t)n_f + 255) & ~(size_t)255) + 256;

@@ -233,6 +233,28 @@ class ORBmatcher:
         out[idx[agree]] = m1[idx[agree]]
         return int(agree.sum()), out
 
+    def SearchForTriangulation(self, fv1, desc1, kps1, has_mp1, fv2, desc2, kps2, has_mp2, F12, level_sigma2):
+        """ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:852-1014).  fv = (node_id, start, items) CSR; has_mp: the feature
+        already has a map point; F12 3x3 float32; level_sigma2 = pKF2's mvLevelSigma2.  Returns (nmatches, vMatchedPairs as N x 2)."""
+        keep = []
+
+        def fv(t):
+            arrs = [np.ascontiguousarray(a, np.int32) for a in t]
+            keep.append(arrs)
+            return FeatVecView(len(arrs[0]), arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data)
+        a, b = fv(fv1), fv(fv2)
+        desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
+        kps1 = np.ascontiguousarray(kps1, KP_DTYPE); kps2 = np.ascontiguousarray(kps2, KP_DTYPE)
+        h1 = np.ascontiguousarray(has_mp1, np.uint8); h2 = np.ascontiguousarray(has_mp2, np.uint8)
+        F = np.ascontiguousarray(F12, np.float32).reshape(9); sg = np.ascontiguousarray(level_sigma2, np.float32)
+        m12 = np.full(len(kps1), -1, np.int32)
+        n = C.c_int(0)
+        check(lib().orb_search_for_triangulation(self._h, C.byref(a), ptr(desc1), ptr(kps1), ptr(h1), len(kps1), C.byref(b), ptr(desc2),
+                                                 ptr(kps2), ptr(h2), len(kps2), ptr(F), ptr(sg), len(sg), int(self.mbCheckOrientation),
+                                                 ptr(m12), C.byref(n)), "orb_search_for_triangulation")
+        i1 = np.flatnonzero(m12 >= 0)
+        return n.value, np.stack([i1, m12[i1]], 1).astype(np.int32), m12
+
     def ComputeDistinctiveDescriptors(self, desc, start):
         """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:185-250) for many map points: desc = all observation descriptors,
         start = CSR offsets per point.  Returns (BestIdx within each group or -1, BestMedian)."""

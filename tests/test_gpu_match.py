@@ -518,3 +518,44 @@ def test_window_best_empty_cases(pkg):
     bi, bd = m.BestInWindow(F, np.array([1, 0, 1, 1], np.uint8), np.array([50, 50, 300, 51], np.float32), np.array([50, 50, 200, 50], np.float32),
                             np.full(4, 5.0, np.float32), np.full(4, -1), np.full(4, 0), q)
     assert list(bi) == [1, -1, -1, 1] and list(bd[[0, 3]]) == [0, 0]      # ties keep the first in scan order
+
+
+@pytest.mark.parametrize("n1,n2,nnodes,ori,seed", [(2000, 2000, 100, True, 1), (700, 500, 12, True, 2), (300, 300, 2, False, 3), (40, 60, 30, True, 4)])
+def test_search_for_triangulation_vs_oracle(pkg, po, n1, n2, nnodes, ori, seed):
+    """ORBmatcher::SearchForTriangulation, src/ORBmatcher.cc:852-1014 with CheckDistEpipolarLine (:136-153)."""
+    m = pkg.ORBmatcher(0.6, ori)
+    fv1, d1, k1, v1, fv2, d2, k2 = _bow_case(po, pkg, n1, n2, nnodes, seed=seed + 40, flip=0.05)
+    rng = np.random.default_rng(seed)
+    # geometry: KF2 sees the scene shifted by about (6, 4) px; F12 of a pure sideways translation in pixel units (K = identity)
+    k1["x"] = rng.uniform(20, 600, n1).astype(np.float32); k1["y"] = rng.uniform(20, 440, n1).astype(np.float32)
+    k1["octave"] = rng.integers(0, 8, n1)
+    twin = rng.integers(0, n1, n2)
+    lam = rng.uniform(0.5, 3.0, n2)
+    k2["x"] = (k1["x"][twin] + 6 * lam + rng.normal(0, 1.0, n2)).astype(np.float32)
+    k2["y"] = (k1["y"][twin] + 4 * lam + rng.normal(0, 1.0, n2)).astype(np.float32)
+    k2["octave"] = rng.integers(0, 8, n2)
+    # descriptors of the twins so that nodes hold real matches
+    d2 = d1[twin] ^ np.packbits((rng.random((n2, 256)) < 0.04).astype(np.uint8), axis=1)
+    t = np.array([6.0, 4.0, 0.0])
+    F12 = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]], np.float32)      # x1' F12 x2 = 0 for x2 = x1 + lambda t
+    sg = np.ones(8, np.float32)
+    for i in range(1, 8):
+        sg[i] = np.float32(np.float32(1.2) ** i) ** 2
+    has1 = (rng.random(n1) < 0.3).astype(np.uint8); has2 = (rng.random(n2) < 0.3).astype(np.uint8)
+    # node membership of KF2 follows its twin most of the time
+    node1 = np.zeros(n1, np.int64)
+    ids, start, items = fv1
+    for j, nid in enumerate(ids):
+        node1[items[start[j]:start[j + 1]]] = nid
+    node2 = np.where(rng.random(n2) < 0.9, node1[twin], rng.choice(ids, n2))
+    ids2 = np.unique(node2)
+    st2, it2 = [0], []
+    for nid in ids2:
+        w = np.nonzero(node2 == nid)[0]
+        it2 += list(w); st2.append(len(it2))
+    fv2 = (ids2.astype(np.int32), np.array(st2, np.int32), np.array(it2, np.int32))
+    n, pairs, m12 = m.SearchForTriangulation(fv1, d1, k1, has1, fv2, d2, k2, has2, F12, sg)
+    rn, rm12 = po.search_for_triangulation(fv1, d1, k1, has1, fv2, d2, k2, has2, F12, sg, ori)
+    assert rn > 3 and n == rn and np.array_equal(m12, rm12)
+    assert len(pairs) == n and not has1[pairs[:, 0]].any() and not has2[pairs[:, 1]].any()
+    assert len(np.unique(pairs[:, 1])) == len(pairs)       # a KF2 feature is matched once
