@@ -1,0 +1,505 @@
+/*
+ * ref_glue.cpp — C entry points around the REFERENCE's own classes, compiled together with the reference's sources from
+ * /root/reference (never copied) against oracle/refshim/ into oracle/_ref/libref_orbslam.so.  TEST INFRASTRUCTURE: it
+ * validates the oracle restatement (tests/test_ref_build.py) and serves bench.py's `--impl reference` arm; the product
+ * never loads it.  See oracle/refshim/minicv.hpp for what is real reference code and what is shim.
+ */
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "ORBextractor.h"            /* /root/reference/include */
+
+extern "C" {
+
+/* ORB_SLAM::ORBextractor, include/ORBextractor.h:32-77 */
+void* ref_extractor_create(int nfeatures, float scale_factor, int nlevels, int score_type, int fast_th)
+{
+    return new ORB_SLAM::ORBextractor(nfeatures, scale_factor, nlevels, score_type, fast_th);
+}
+void ref_extractor_destroy(void* e) { delete (ORB_SLAM::ORBextractor*)e; }
+
+/* ORBextractor::operator()(image, mask = Mat(), keypoints, descriptors) as Frame::Frame calls it (src/Frame.cc:60).
+ * kps: 28-byte cv::KeyPoint records.  Returns 0, -3 when cap is too small (n still reports the count), -1 on an exception. */
+int ref_extract(void* e, const uint8_t* img, int w, int h, int stride, void* kps, uint8_t* desc, int cap, int* n)
+{
+    try {
+        cv::Mat image(h, w, CV_8UC1);
+        for (int y = 0; y < h; y++) std::memcpy(image.ptr(y), img + (size_t)y * stride, (size_t)w);
+        std::vector<cv::KeyPoint> keys;
+        cv::Mat descriptors;
+        (*(ORB_SLAM::ORBextractor*)e)(image, cv::Mat(), keys, descriptors);
+        *n = (int)keys.size();
+        if (*n > cap) return -3;
+        static_assert(sizeof(cv::KeyPoint) == 28, "cv::KeyPoint layout");
+        if (*n) {
+            std::memcpy(kps, keys.data(), keys.size() * sizeof(cv::KeyPoint));
+            for (int i = 0; i < *n; i++) std::memcpy(desc + (size_t)i * 32, descriptors.ptr(i), 32);
+        }
+        return 0;
+    } catch (const std::exception& ex) {
+        std::fprintf(stderr, "ref_extract: %s\n", ex.what());
+        return -1;
+    }
+}
+
+} // extern "C"
+
+/* =====================================================================================================================
+ * Map classes and ORBmatcher: the reference's Frame / KeyFrame / MapPoint / Map / KeyFrameDatabase / ORBmatcher objects
+ * built from flat arrays.  Every search below runs the reference's own member function (src/ORBmatcher.cc); the glue only
+ * builds its inputs and turns MapPoint pointers in its outputs back into feature indices.
+ * ===================================================================================================================== */
+#include <map>
+#include <set>
+
+#include "Frame.h"
+#include "KeyFrame.h"
+#include "KeyFrameDatabase.h"
+#include "Map.h"
+#include "MapPoint.h"
+#include "ORBVocabulary.h"
+#include "ORBmatcher.h"
+#include "Converter.h"               /* oracle/refshim/Converter.h */
+
+namespace ORB_SLAM {
+/* src/Converter.cc:28-36 needs Eigen + g2o for its other members; this is the one the front end calls */
+std::vector<cv::Mat> Converter::toDescriptorVector(const cv::Mat& Descriptors)
+{
+    std::vector<cv::Mat> v;
+    v.reserve(Descriptors.rows);
+    for (int j = 0; j < Descriptors.rows; j++) v.push_back(Descriptors.row(j));
+    return v;
+}
+}
+
+using namespace ORB_SLAM;
+
+namespace {
+struct RefFrame {
+    Frame f;
+    KeyFrame* kf = nullptr;
+    Map* map = nullptr;
+    std::vector<MapPoint*> owned;                  /* every MapPoint created for this frame */
+    int min_x, max_x, min_y, max_y;
+    float fx, fy, cx, cy;
+    void statics()                                 /* the camera lives in static members of Frame (include/Frame.h:62-65,128-131) */
+    {
+        Frame::mnMinX = min_x; Frame::mnMaxX = max_x; Frame::mnMinY = min_y; Frame::mnMaxY = max_y;
+        Frame::fx = fx; Frame::fy = fy; Frame::cx = cx; Frame::cy = cy;
+        Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(max_x - min_x);
+        Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(max_y - min_y);
+        Frame::mbInitialComputations = false;
+    }
+    KeyFrame* keyframe()
+    {
+        if (!kf) {
+            statics();
+            map = new Map();
+            kf = new KeyFrame(f, map, nullptr);
+        }
+        return kf;
+    }
+    MapPoint* new_point(const float* xyz, const uint8_t* desc32)
+    {
+        cv::Mat pos(3, 1, CV_32F);
+        for (int k = 0; k < 3; k++) pos.at<float>(k) = xyz ? xyz[k] : 0.f;
+        MapPoint* p = new MapPoint(pos, keyframe(), map);
+        if (desc32) { cv::Mat d(1, 32, CV_8U, (void*)desc32); p->SetDescriptor(d.clone()); }
+        owned.push_back(p);
+        return p;
+    }
+};
+template <typename F> int guarded(const char* what, F fn)
+{
+    try { return fn(); }
+    catch (const std::exception& ex) { std::fprintf(stderr, "%s: %s\n", what, ex.what()); return -1000; }
+    catch (const std::string& s) { std::fprintf(stderr, "%s: %s\n", what, s.c_str()); return -1000; }
+}
+void index_of(const std::vector<MapPoint*>& pts, std::map<MapPoint*, int>& m)
+{
+    for (size_t i = 0; i < pts.size(); i++) if (pts[i]) m[pts[i]] = (int)i;
+}
+}
+
+extern "C" {
+
+/* A Frame from undistorted keypoints + descriptors (what Frame::Frame leaves behind after extraction and
+ * UndistortKeyPoints, src/Frame.cc:56-128): scale tables as :92-107, the grid filled by the loop of :109-123 calling the
+ * reference's own PosInGrid (:267-277). */
+void* ref_frame_create(const void* kps_un, const uint8_t* desc, int n, int min_x, int max_x, int min_y, int max_y,
+                       float fx, float fy, float cx, float cy, int nlevels, float scale_factor)
+{
+    RefFrame* r = new RefFrame();
+    r->min_x = min_x; r->max_x = max_x; r->min_y = min_y; r->max_y = max_y;
+    r->fx = fx; r->fy = fy; r->cx = cx; r->cy = cy;
+    r->statics();
+    Frame& F = r->f;
+    F.mpORBvocabulary = nullptr; F.mpORBextractor = nullptr; F.mTimeStamp = 0; F.mpReferenceKF = nullptr;
+    F.N = n;
+    F.mvKeysUn.resize(n);
+    if (n) std::memcpy((void*)F.mvKeysUn.data(), kps_un, (size_t)n * sizeof(cv::KeyPoint));
+    F.mvKeys = F.mvKeysUn;
+    F.mDescriptors.create(std::max(n, 1), 32, CV_8U);
+    if (n) std::memcpy(F.mDescriptors.data, desc, (size_t)n * 32);
+    if (n == 0) F.mDescriptors = F.mDescriptors.rowRange(0, 0);
+    F.mvpMapPoints = std::vector<MapPoint*>(n, static_cast<MapPoint*>(nullptr));
+    F.mvbOutlier = std::vector<bool>(n, false);
+    F.mK = cv::Mat::eye(3, 3, CV_32F);
+    F.mK.at<float>(0, 0) = fx; F.mK.at<float>(1, 1) = fy; F.mK.at<float>(0, 2) = cx; F.mK.at<float>(1, 2) = cy;
+    F.mDistCoef = cv::Mat::zeros(4, 1, CV_32F);
+    F.mTcw = cv::Mat::eye(4, 4, CV_32F);
+    F.UpdatePoseMatrices();
+    F.mnId = Frame::nNextId++;
+    F.mnScaleLevels = nlevels;
+    F.mfScaleFactor = scale_factor;
+    F.mvScaleFactors.resize(nlevels);
+    F.mvLevelSigma2.resize(nlevels);
+    F.mvScaleFactors[0] = 1.0f;
+    F.mvLevelSigma2[0] = 1.0f;
+    for (int i = 1; i < nlevels; i++) {
+        F.mvScaleFactors[i] = F.mvScaleFactors[i - 1] * F.mfScaleFactor;
+        F.mvLevelSigma2[i] = F.mvScaleFactors[i] * F.mvScaleFactors[i];
+    }
+    F.mvInvLevelSigma2.resize(nlevels);
+    for (int i = 0; i < nlevels; i++) F.mvInvLevelSigma2[i] = 1 / F.mvLevelSigma2[i];
+    for (size_t i = 0; i < F.mvKeysUn.size(); i++) {
+        int gx, gy;
+        if (F.PosInGrid(F.mvKeysUn[i], gx, gy)) F.mGrid[gx][gy].push_back(i);
+    }
+    return r;
+}
+
+/* Frame::Frame(im, timeStamp, extractor, voc, K, distCoef), src/Frame.cc:56-128, run as is: extraction, UndistortKeyPoints,
+ * ComputeImageBounds, grid.  dist4 = k1 k2 p1 p2.  voc may be NULL. */
+void* ref_frame_from_image(void* extractor, void* voc, const uint8_t* img, int w, int h, int stride, float fx, float fy, float cx, float cy,
+                           const float* dist4)
+{
+    RefFrame* r = nullptr;
+    int rc = guarded("ref_frame_from_image", [&] {
+        cv::Mat image(h, w, CV_8UC1);
+        for (int y = 0; y < h; y++) std::memcpy(image.ptr(y), img + (size_t)y * stride, (size_t)w);
+        cv::Mat K = cv::Mat::eye(3, 3, CV_32F);
+        K.at<float>(0, 0) = fx; K.at<float>(1, 1) = fy; K.at<float>(0, 2) = cx; K.at<float>(1, 2) = cy;
+        cv::Mat D(4, 1, CV_32F);
+        for (int i = 0; i < 4; i++) D.at<float>(i) = dist4[i];
+        Frame::mbInitialComputations = true;               /* a new camera: recompute the image bounds */
+        Frame F(image, 0.0, (ORBextractor*)extractor, (ORBVocabulary*)voc, K, D);
+        r = new RefFrame();
+        r->f = F;
+        r->min_x = Frame::mnMinX; r->max_x = Frame::mnMaxX; r->min_y = Frame::mnMinY; r->max_y = Frame::mnMaxY;
+        r->fx = fx; r->fy = fy; r->cx = cx; r->cy = cy;
+        r->f.mTcw = cv::Mat::eye(4, 4, CV_32F);
+        r->f.UpdatePoseMatrices();
+        return 0;
+    });
+    return rc == 0 ? r : nullptr;
+}
+void ref_frame_destroy(void* h)
+{
+    RefFrame* r = (RefFrame*)h;
+    for (MapPoint* p : r->owned) delete p;
+    delete r->kf;
+    delete r->map;
+    delete r;
+}
+int ref_frame_n(void* h) { return ((RefFrame*)h)->f.N; }
+/* keys (as extracted), undistorted keys, descriptors, bounds[4] = minX maxX minY maxY; any pointer may be NULL */
+void ref_frame_get(void* h, void* keys, void* keys_un, uint8_t* desc, int32_t* bounds)
+{
+    RefFrame* r = (RefFrame*)h;
+    const int n = r->f.N;
+    if (keys && n) std::memcpy(keys, r->f.mvKeys.data(), (size_t)n * sizeof(cv::KeyPoint));
+    if (keys_un && n) std::memcpy(keys_un, r->f.mvKeysUn.data(), (size_t)n * sizeof(cv::KeyPoint));
+    if (desc) for (int i = 0; i < n; i++) std::memcpy(desc + (size_t)i * 32, r->f.mDescriptors.ptr(i), 32);
+    if (bounds) { bounds[0] = r->min_x; bounds[1] = r->max_x; bounds[2] = r->min_y; bounds[3] = r->max_y; }
+}
+/* the grid as CSR, cell id = ix*48+iy, items in insertion order (src/Frame.cc:109-123) */
+void ref_frame_grid(void* h, int32_t* cell_start, int32_t* cell_items)
+{
+    RefFrame* r = (RefFrame*)h;
+    int k = 0;
+    for (int ix = 0; ix < FRAME_GRID_COLS; ix++)
+        for (int iy = 0; iy < FRAME_GRID_ROWS; iy++) {
+            cell_start[ix * FRAME_GRID_ROWS + iy] = k;
+            for (size_t v : r->f.mGrid[ix][iy]) cell_items[k++] = (int32_t)v;
+        }
+    cell_start[FRAME_GRID_COLS * FRAME_GRID_ROWS] = k;
+}
+/* Frame::GetFeaturesInArea, src/Frame.cc:200-265 */
+int ref_features_in_area(void* h, float x, float y, float rad, int min_level, int max_level, int32_t* out, int cap)
+{
+    RefFrame* r = (RefFrame*)h;
+    r->statics();
+    std::vector<size_t> v = r->f.GetFeaturesInArea(x, y, rad, min_level, max_level);
+    for (size_t i = 0; i < v.size() && (int)i < cap; i++) out[i] = (int32_t)v[i];
+    return (int)v.size();
+}
+void ref_frame_set_pose(void* h, const float* Tcw16)
+{
+    RefFrame* r = (RefFrame*)h;
+    cv::Mat T(4, 4, CV_32F);
+    std::memcpy(T.data, Tcw16, 64);
+    r->f.mTcw = T;
+    r->f.UpdatePoseMatrices();
+    if (r->kf) r->kf->SetPose(T);
+}
+/* FeatureVector from CSR (node ids ascending, feature indices in insertion order); must precede anything that makes the KeyFrame */
+void ref_frame_set_featvec(void* h, int nnodes, const int32_t* node_id, const int32_t* start, const int32_t* items)
+{
+    RefFrame* r = (RefFrame*)h;
+    r->f.mFeatVec.clear();
+    for (int k = 0; k < nnodes; k++)
+        for (int j = start[k]; j < start[k + 1]; j++) r->f.mFeatVec.addFeature((DBoW2::NodeId)node_id[k], (unsigned)items[j]);
+}
+/* map points on the frame's features: has[i] != 0 -> a MapPoint at xyz[3i..] (NULL: origin) observed by this frame's KeyFrame at
+ * feature i; its descriptor comes from MapPoint::ComputeDistinctiveDescriptors over that one observation.  outlier may be NULL. */
+void ref_frame_set_mappoints(void* h, const uint8_t* has, const float* xyz, const uint8_t* outlier)
+{
+    RefFrame* r = (RefFrame*)h;
+    KeyFrame* kf = r->keyframe();
+    for (int i = 0; i < r->f.N; i++) {
+        r->f.mvbOutlier[i] = outlier && outlier[i];
+        if (!has[i]) { r->f.mvpMapPoints[i] = nullptr; continue; }
+        MapPoint* p = r->new_point(xyz ? xyz + 3 * i : nullptr, nullptr);
+        p->AddObservation(kf, i);
+        p->ComputeDistinctiveDescriptors();
+        kf->AddMapPoint(p, i);
+        r->f.mvpMapPoints[i] = p;
+    }
+}
+
+/* ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:1794-1810 */
+int ref_descriptor_distance(const uint8_t* a, const uint8_t* b)
+{
+    cv::Mat ma(1, 32, CV_8U, (void*)a), mb(1, 32, CV_8U, (void*)b);
+    return ORBmatcher::DescriptorDistance(ma, mb);
+}
+
+/* ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, float th), :1507-1620.
+ * match_cur[i2] in: >= 0 -> CurrentFrame.mvpMapPoints[i2] already holds LastFrame's point of that feature; out: the same map. */
+int ref_search_by_projection_ff(void* cur_, void* last_, float th, float nnratio, int check_ori, int32_t* match_cur)
+{
+    RefFrame *cur = (RefFrame*)cur_, *last = (RefFrame*)last_;
+    return guarded("SearchByProjection(F,F)", [&] {
+        cur->statics();
+        std::map<MapPoint*, int> idx;
+        index_of(last->f.mvpMapPoints, idx);
+        for (int i = 0; i < cur->f.N; i++) cur->f.mvpMapPoints[i] = match_cur[i] >= 0 ? last->f.mvpMapPoints[match_cur[i]] : nullptr;
+        ORBmatcher m(nnratio, check_ori != 0);
+        const int n = m.SearchByProjection(cur->f, last->f, th);
+        for (int i = 0; i < cur->f.N; i++) match_cur[i] = cur->f.mvpMapPoints[i] ? idx.at(cur->f.mvpMapPoints[i]) : -1;
+        return n;
+    });
+}
+
+/* ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*>&, th), :49-125, on nmp free-standing map points whose tracking
+ * members (set by Frame::isInFrustum in the reference) are given.  match_f[idx] in/out = index of the point on feature idx or -1. */
+int ref_search_by_projection_mappoints(void* f_, int nmp, const uint8_t* in_view, const float* proj_x, const float* proj_y, const int32_t* level,
+                                       const float* view_cos, const uint8_t* mp_desc, float th, float nnratio, int32_t* match_f)
+{
+    RefFrame* f = (RefFrame*)f_;
+    return guarded("SearchByProjection(F,MapPoints)", [&] {
+        f->statics();
+        std::vector<MapPoint*> pts(nmp);
+        for (int i = 0; i < nmp; i++) {
+            MapPoint* p = f->new_point(nullptr, mp_desc + (size_t)i * 32);
+            p->mbTrackInView = in_view[i] != 0;
+            p->mTrackProjX = proj_x[i]; p->mTrackProjY = proj_y[i];
+            p->mnTrackScaleLevel = level[i]; p->mTrackViewCos = view_cos[i];
+            pts[i] = p;
+        }
+        std::map<MapPoint*, int> idx;
+        index_of(pts, idx);
+        for (int i = 0; i < f->f.N; i++) f->f.mvpMapPoints[i] = match_f[i] >= 0 ? pts[match_f[i]] : nullptr;
+        ORBmatcher m(nnratio, true);
+        const int n = m.SearchByProjection(f->f, pts, th);
+        for (int i = 0; i < f->f.N; i++) match_f[i] = f->f.mvpMapPoints[i] ? idx.at(f->f.mvpMapPoints[i]) : -1;
+        return n;
+    });
+}
+
+/* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), :155-284.  match_f[idxF] out = KeyFrame feature whose point matched. */
+int ref_search_by_bow(void* kf_, void* f_, float nnratio, int check_ori, int32_t* match_f)
+{
+    RefFrame *k = (RefFrame*)kf_, *f = (RefFrame*)f_;
+    return guarded("SearchByBoW(KF,F)", [&] {
+        f->statics();
+        std::map<MapPoint*, int> idx;
+        index_of(k->keyframe()->GetMapPointMatches(), idx);
+        std::vector<MapPoint*> out;
+        ORBmatcher m(nnratio, check_ori != 0);
+        const int n = m.SearchByBoW(k->keyframe(), f->f, out);
+        for (int i = 0; i < f->f.N; i++) match_f[i] = out[i] ? idx.at(out[i]) : -1;
+        return n;
+    });
+}
+
+/* ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&), :715-850.  match12[idx1] out = idx2 or -1. */
+int ref_search_by_bow_kf(void* k1_, void* k2_, float nnratio, int check_ori, int32_t* match12)
+{
+    RefFrame *k1 = (RefFrame*)k1_, *k2 = (RefFrame*)k2_;
+    return guarded("SearchByBoW(KF,KF)", [&] {
+        k1->statics();
+        std::map<MapPoint*, int> idx;
+        index_of(k2->keyframe()->GetMapPointMatches(), idx);
+        std::vector<MapPoint*> out;
+        ORBmatcher m(nnratio, check_ori != 0);
+        const int n = m.SearchByBoW(k1->keyframe(), k2->keyframe(), out);
+        for (int i = 0; i < k1->f.N; i++) match12[i] = out[i] ? idx.at(out[i]) : -1;
+        return n;
+    });
+}
+
+/* ORBmatcher::WindowSearch(F1, F2, windowSize, vpMapPointMatches2, minLevel, maxLevel), :409-516.  match2[i2] out = i1 or -1. */
+int ref_window_search(void* f1_, void* f2_, int window, int min_level, int max_level, float nnratio, int check_ori, int32_t* match2)
+{
+    RefFrame *f1 = (RefFrame*)f1_, *f2 = (RefFrame*)f2_;
+    return guarded("WindowSearch", [&] {
+        f1->statics();
+        std::map<MapPoint*, int> idx;
+        index_of(f1->f.mvpMapPoints, idx);
+        std::vector<MapPoint*> out;
+        ORBmatcher m(nnratio, check_ori != 0);
+        const int n = m.WindowSearch(f1->f, f2->f, window, out, min_level, max_level);
+        for (int i = 0; i < f2->f.N; i++) match2[i] = out[i] ? idx.at(out[i]) : -1;
+        return n;
+    });
+}
+
+/* ORBmatcher::SearchByProjection(F1, F2, windowSize, vpMapPointMatches2), :519-594.  F2's pose must be set.  match2[i2] in: >= 0 ->
+ * F2.mvpMapPoints[i2] is already set (to a point that F1 does not hold); out: i1 for new matches, the input value otherwise. */
+int ref_search_by_projection_window(void* f1_, void* f2_, int window, float nnratio, int32_t* match2)
+{
+    RefFrame *f1 = (RefFrame*)f1_, *f2 = (RefFrame*)f2_;
+    return guarded("SearchByProjection(F1,F2,window)", [&] {
+        f1->statics();
+        std::map<MapPoint*, int> idx;
+        index_of(f1->f.mvpMapPoints, idx);
+        for (int i = 0; i < f2->f.N; i++) f2->f.mvpMapPoints[i] = match2[i] >= 0 ? f2->new_point(nullptr, f2->f.mDescriptors.ptr(i)) : nullptr;
+        std::vector<MapPoint*> out;
+        ORBmatcher m(nnratio, true);
+        const int n = m.SearchByProjection(f1->f, f2->f, window, out);
+        for (int i = 0; i < f2->f.N; i++)
+            if (out[i] && idx.count(out[i])) match2[i] = idx[out[i]];
+            else if (!out[i]) match2[i] = -1;
+        return n;
+    });
+}
+
+/* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize), :598-713 */
+int ref_search_for_initialization(void* f1_, void* f2_, float* prev_matched, int window, float nnratio, int check_ori, int32_t* matches12)
+{
+    RefFrame *f1 = (RefFrame*)f1_, *f2 = (RefFrame*)f2_;
+    return guarded("SearchForInitialization", [&] {
+        f1->statics();
+        std::vector<cv::Point2f> prev(f1->f.N);
+        for (int i = 0; i < f1->f.N; i++) prev[i] = cv::Point2f(prev_matched[2 * i], prev_matched[2 * i + 1]);
+        std::vector<int> m12;
+        ORBmatcher m(nnratio, check_ori != 0);
+        const int n = m.SearchForInitialization(f1->f, f2->f, prev, m12, window);
+        for (int i = 0; i < f1->f.N; i++) { matches12[i] = m12[i]; prev_matched[2 * i] = prev[i].x; prev_matched[2 * i + 1] = prev[i].y; }
+        return n;
+    });
+}
+
+/* ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, ...), :852-1014.  match12[n1] out = idx2 of the pair (idx1, idx2) or -1;
+ * returns the reference's return value, npairs the length of vMatchedPairs. */
+int ref_search_for_triangulation(void* k1_, void* k2_, const float* F12, float nnratio, int check_ori, int32_t* match12, int* npairs)
+{
+    RefFrame *k1 = (RefFrame*)k1_, *k2 = (RefFrame*)k2_;
+    return guarded("SearchForTriangulation", [&] {
+        k1->statics();
+        cv::Mat F(3, 3, CV_32F);
+        std::memcpy(F.data, F12, 36);
+        std::vector<cv::KeyPoint> a, b;
+        std::vector<std::pair<size_t, size_t> > pairs;
+        ORBmatcher m(nnratio, check_ori != 0);
+        const int n = m.SearchForTriangulation(k1->keyframe(), k2->keyframe(), F, a, b, pairs);
+        for (int i = 0; i < k1->f.N; i++) match12[i] = -1;
+        for (auto& p : pairs) match12[p.first] = (int32_t)p.second;
+        *npairs = (int)pairs.size();
+        return n;
+    });
+}
+
+/* MapPoint::ComputeDistinctiveDescriptors, src/MapPoint.cc:185-250, for a point observed at features obs[0..nobs) of this frame's
+ * KeyFrame... one KeyFrame can hold a point once, so each observation gets its own single-feature KeyFrame built from desc rows. */
+int ref_distinctive_descriptor(const uint8_t* desc, int nobs, uint8_t* out32)
+{
+    return guarded("ComputeDistinctiveDescriptors", [&] {
+        std::vector<RefFrame*> frames;
+        cv::KeyPoint kp(10.f, 10.f, 31.f, 0.f, 1.f, 0, -1);
+        MapPoint* p = nullptr;
+        for (int i = 0; i < nobs; i++) {
+            RefFrame* r = (RefFrame*)ref_frame_create(&kp, desc + (size_t)i * 32, 1, 0, 640, 0, 480, 500, 500, 320, 240, 8, 1.2f);
+            frames.push_back(r);
+            if (!p) p = r->new_point(nullptr, nullptr);
+            p->AddObservation(r->keyframe(), 0);
+        }
+        int rc = -1;
+        if (p) {
+            p->ComputeDistinctiveDescriptors();
+            cv::Mat d = p->GetDescriptor();
+            if (!d.empty()) { std::memcpy(out32, d.data, 32); rc = 0; }
+        }
+        for (RefFrame* r : frames) ref_frame_destroy(r);
+        return rc;
+    });
+}
+
+/* ---- DBoW2 (Thirdparty/DBoW2): ORBVocabulary = TemplatedVocabulary<FORB::TDescriptor, FORB> ---- */
+void* ref_vocab_load_text(const char* path)
+{
+    ORBVocabulary* v = new ORBVocabulary();
+    bool ok = false;
+    guarded("loadFromTextFile", [&] { ok = v->loadFromTextFile(path); return 0; });
+    if (!ok) { delete v; return nullptr; }
+    return v;
+}
+void ref_vocab_destroy(void* v) { delete (ORBVocabulary*)v; }
+int ref_vocab_nwords(void* v) { return (int)((ORBVocabulary*)v)->size(); }
+/* transform(features, BowVector&, FeatureVector&, levelsup), TemplatedVocabulary.h:1127-1193 */
+int ref_vocab_transform(void* v_, const uint8_t* desc, int n, int levelsup, int32_t* bow_word, double* bow_val, int* nbow,
+                        int32_t* fv_node, int32_t* fv_start, int32_t* fv_items, int* nfv)
+{
+    return guarded("transform", [&] {
+        ORBVocabulary* v = (ORBVocabulary*)v_;
+        cv::Mat D(std::max(n, 1), 32, CV_8U);
+        if (n) std::memcpy(D.data, desc, (size_t)n * 32);
+        std::vector<cv::Mat> feats = Converter::toDescriptorVector(n ? D : D.rowRange(0, 0));
+        DBoW2::BowVector bv;
+        DBoW2::FeatureVector fv;
+        v->transform(feats, bv, fv, levelsup);
+        int k = 0;
+        for (auto& e : bv) { bow_word[k] = (int32_t)e.first; bow_val[k] = e.second; k++; }
+        *nbow = k;
+        int nn = 0, ni = 0;
+        for (auto& e : fv) {
+            fv_node[nn] = (int32_t)e.first; fv_start[nn] = ni; nn++;
+            for (unsigned f : e.second) fv_items[ni++] = (int32_t)f;
+        }
+        fv_start[nn] = ni;
+        *nfv = nn;
+        return 0;
+    });
+}
+/* transform(feature, word_id, weight, nid, levelsup), :1218-1260, through the public single-feature transform (:1197-1205) */
+int ref_vocab_transform_feature(void* v_, const uint8_t* desc32, int32_t* word)
+{
+    ORBVocabulary* v = (ORBVocabulary*)v_;
+    cv::Mat d(1, 32, CV_8U, (void*)desc32);
+    *word = (int32_t)v->transform(d);
+    return 0;
+}
+/* ORBVocabulary::score -> L1Scoring::score, ScoringObject.cpp:22-64 */
+double ref_vocab_score(void* v_, const int32_t* w1, const double* v1, int n1, const int32_t* w2, const double* v2, int n2)
+{
+    ORBVocabulary* v = (ORBVocabulary*)v_;
+    DBoW2::BowVector a, b;
+    for (int i = 0; i < n1; i++) a.insert(a.end(), std::make_pair((DBoW2::WordId)w1[i], v1[i]));
+    for (int i = 0; i < n2; i++) b.insert(b.end(), std::make_pair((DBoW2::WordId)w2[i], v2[i]));
+    return v->score(a, b);
+}
+
+} // extern "C"

@@ -1,0 +1,2 @@
+/* reference-build shim: see ../../minicv.hpp */
+#include "../../minicv.hpp"

@@ -167,12 +167,16 @@ def synth_vocabulary_fast(k=10, L=6, seed=5, flip_bits=24, stop_frac=0.02):
     return parent, desc, weight
 
 
-def write_vocabulary_text(path, k, L, parent, desc, weight, scoring=0, weighting=0):
-    """DBoW2 text format (TemplatedVocabulary::saveToTextFile / loadFromTextFile, TemplatedVocabulary.h:1338-1460)."""
+def write_vocabulary_text(path, k, L, parent, desc, weight, scoring=0, weighting=0, trailing_newline=True):
+    """DBoW2 text format (TemplatedVocabulary::saveToTextFile / loadFromTextFile, TemplatedVocabulary.h:1338-1460).
+    saveToTextFile ends the file with a newline; the reference's loader (`while(!f.eof())`, :1377) then reads one more, empty,
+    line and hangs a phantom child with an uninitialised descriptor under the root.  trailing_newline=False writes the file the
+    reference loads without that phantom (used when the reference's own DBoW2 is the checker, tests/test_ref_build.py)."""
     n = len(parent)
     has_child = np.zeros(n, bool)
     has_child[parent[1:]] = True
     with open(path, "w") as f:
         f.write("%d %d %d %d\n" % (k, L, scoring, weighting))
         for i in range(1, n):
-            f.write("%d %d %s %s\n" % (parent[i], 0 if has_child[i] else 1, " ".join(str(int(b)) for b in desc[i]), repr(float(weight[i]))))
+            f.write("%d %d %s %s%s" % (parent[i], 0 if has_child[i] else 1, " ".join(str(int(b)) for b in desc[i]), repr(float(weight[i])),
+                                       "\n" if (trailing_newline or i + 1 < n) else ""))
