@@ -15,8 +15,8 @@ A "step" is one pass of the hot path (ORBextractor::operator()) over one batch o
             10M-row DB sharded over the ranks, NCCL all-gather + exact merge) in descriptor pairs/s
             against the measured POPC-pipe peak.
 Frames are sharded over ranks with no data-path collective (weak scaling: fixed frames per GPU).
-The reference cannot be compiled here (needs ROS + the OpenCV C++ SDK); its CPU arm is the oracle
-port of the same algorithm (oracle/), timed on the host cores.
+The reference's CPU arm is oracle/_ref (its own src/ORBextractor.cc compiled against oracle/refshim/, built in the
+build container and shipped as a built file), or the oracle port when that library is absent; timed on the host cores.
 """
 import argparse
 import ctypes as C
@@ -103,13 +103,28 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------- CPU arm
+def cpu_kind():
+    """"reference": oracle/_ref/libref_orbslam.so = the reference's own src/ORBextractor.cc compiled against oracle/refshim/ (its
+    OpenCV primitives are the oracle's restatements); "port": the oracle restatement, when that library was not built."""
+    from oracle import pyref
+    return "reference" if pyref.available() else "port"
+
+
+CPU_WHAT = {"reference": "the reference's own src/ORBextractor.cc compiled against oracle/refshim (OpenCV primitives = the oracle's restatements)",
+            "port": "oracle port of src/ORBextractor.cc (oracle/_ref is not built on this box)"}
+
+
 def cpu_extract_rate(frames, nthreads, seconds_hint=None):
-    """frames/s of the oracle port (reference algorithm) with `nthreads` host threads, one extractor
-    instance per thread (the reference extractor is stateful, include/ORBextractor.h:74-75)."""
+    """frames/s of the reference extractor on the host with `nthreads` threads, one extractor instance per thread (the
+    reference extractor is stateful, include/ORBextractor.h:74-75; ctypes releases the GIL during the call)."""
     from oracle import pyoracle as po
+    from oracle import pyref
     po.lib()
     n = len(frames)
-    exs = [po.OracleExtractor(NFEAT, SCALE, NLEVELS, 1, FAST_TH) for _ in range(nthreads)]
+    if pyref.available():
+        exs = [pyref.RefExtractor(NFEAT, SCALE, NLEVELS, 1, FAST_TH) for _ in range(nthreads)]
+    else:
+        exs = [po.OracleExtractor(NFEAT, SCALE, NLEVELS, 1, FAST_TH) for _ in range(nthreads)]
     exs[0](frames[0])                                     # warm
     nxt, lock, done = [0], threading.Lock(), [0]
 
@@ -151,9 +166,9 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step": per_step, "width": W, "height": H, "nfeatures": NFEAT},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": "%d frames per step x %d steps, frame-parallel over %d host threads, oracle port of "
-                                       "src/ORBextractor.cc (the reference needs ROS+OpenCV C++ and cannot be built here)" % (per_step, args.steps, cores)},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": cpu_kind(),
+                             "sample": "%d frames per step x %d steps, frame-parallel over %d host threads; %s"
+                                       % (per_step, args.steps, cores, CPU_WHAT[cpu_kind()])},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -433,6 +448,33 @@ def run_gpu(args):
     same = all(torch.equal(a_, b_) for a_, b_ in zip(outs[0][2:], outs[1][2:]))    # both buffer sets hold the same counts
     assert same, "streaming call: the two output buffer sets disagree"
 
+    # ---- the metric's other named shape: 640x480 / 1000 kp (BASELINE.json configs[0], the reference's own CPU-runnable case) ----
+    W0, H0 = 640, 480
+    ex0 = pkg.ORBextractor(NFEAT, SCALE, NLEVELS, 1, FAST_TH, device=local, max_width=W0, max_height=H0, max_batch=B)
+    base0 = synth_frames(min(B, 32), H0, W0, 1000 + 100 * rank)
+    d_img0 = torch.from_numpy(np.concatenate([base0] * ((B + len(base0) - 1) // len(base0)))[:B].copy()).to(dev)
+
+    def step0():
+        check(L.orb_extract_batch_device(ex0._h, ptr(d_img0), B, W0, H0, W0, W0 * H0, ptr(d_kps), ptr(d_desc), cap, ptr(d_cnt),
+                                         C.c_void_p(stream)), "orb_extract_batch_device 640x480")
+    assert ex0.capacity <= cap
+    for _ in range(3):
+        step0()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step0()
+    e1.record()
+    barrier()
+    ms0 = max_over_ranks(e0.elapsed_time(e1))
+    nkp0 = float(d_cnt.float().mean().item())
+    hbm0, _ = measured_peaks()
+    config0 = {"workload": "batched ORB extraction, 640x480 synthetic frames, 1000 kp", "value": frames_total / (ms0 * 1e-3), "unit": "frames/s",
+               "ms_per_step": ms0 / args.steps, "mean_keypoints": nkp0,
+               "pipeline_frac": (frames_total / world / (ms0 * 1e-3)) * algorithmic_bytes_per_frame(W0, H0, nkp0) / (hbm0 * 1e9)}
+    step_device()                                          # leave the 752x480 results in the output buffers
+    torch.cuda.synchronize()
+
     # ---- roofline of the dominant kernel ----
     hbm, hbm_src = measured_peaks()
     dom = max(stage, key=stage.get)
@@ -478,7 +520,7 @@ def run_gpu(args):
                     "synchronous_call": {"value": frames_total / (e2e_sync_ms * 1e-3), "ms_per_step": e2e_sync_ms / args.steps,
                                          "gpu_launches_per_step": e2e_launches, "chunk": args.e2e_chunk,
                                          "api": "orb_extract_batch (one blocking call per step, internally chunked + double-buffered)"}},
-            "roofline": roofline, "matching": matching}
+            "roofline": roofline, "config0_640x480": config0, "matching": matching}
     sbp_inputs = matching.pop("_sbp_inputs", None) if matching else None
     vocab_inputs = matching.pop("_vocab_inputs", None) if matching else None
     if args.cpu_baseline:
@@ -487,10 +529,9 @@ def run_gpu(args):
         fr = [base[i % len(base)] for i in range(nfr)]
         fps1, dt1 = cpu_extract_rate(fr[:48], 1)
         fpsN, dtN = cpu_extract_rate(fr, cores)
-        line["cpu_baseline"] = {"value": fpsN, "unit": "frames/s", "cores": cores, "kind": "port", "single_thread_value": fps1,
+        line["cpu_baseline"] = {"value": fpsN, "unit": "frames/s", "cores": cores, "kind": cpu_kind(), "single_thread_value": fps1,
                                 "sample": "%d frames of the same workload, frame-parallel over %d host threads (%.1f s wall); "
-                                          "single-thread figure on 48 frames (%.1f s); oracle port of src/ORBextractor.cc "
-                                          "(the reference needs ROS + the OpenCV C++ SDK and cannot be built here)" % (nfr, cores, dtN, dt1)}
+                                          "single-thread figure on 48 frames (%.1f s); %s" % (nfr, cores, dtN, dt1, CPU_WHAT[cpu_kind()])}
         if sbp_inputs is not None:
             from oracle import pyoracle as po
             cur, last, has, outl, xyz, Tcw = sbp_inputs
