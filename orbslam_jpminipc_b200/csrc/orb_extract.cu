@@ -13,6 +13,7 @@
 // Integer stages are bit-exact by construction; the two floating-point stages (blur, angle /
 // rotation) spell out every rounding with __f*_rn / fmaf so the compiler cannot contract them.
 #include "orb_internal.h"
+#include <mutex>
 #include "introselect.h"
 
 namespace {
@@ -273,6 +274,37 @@ __device__ __forceinline__ uint32_t lo16x2(uint32_t w) { return __byte_perm(w, 0
 __device__ __forceinline__ uint32_t hi16x2(uint32_t w) { return __byte_perm(w, 0, 0x4342); }   // bytes 2,3 -> u16 lanes
 
 // ring[k] packed for two pixels -> (max over arcs of arc-min, min over arcs of arc-max), packed
+#ifndef ORB_FAST_ARC_V1
+// 34 three-input operations per polarity instead of 40.  The four arcs starting at k..k+3 share the six samples C = r[k+3..k+8];
+// with max(min(S,a), min(S,b)) = min(S, max(a,b)):
+//   max(arc k,   arc k+1) = min(C, r[k+1], r[k+2],  max(r[k],   r[k+9]))
+//   max(arc k+2, arc k+3) = min(C, r[k+9], r[k+10], max(r[k+2], r[k+11]))
+// so one group of four arcs costs 8 operations (k = 0, 4, 8, 12) and two more combine the groups.
+__device__ __forceinline__ void arc_minmax(const uint32_t (&r)[16], uint32_t& Mn, uint32_t& Mx)
+{
+    uint32_t g[4], h[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int k = 4 * q;
+#define R_(i) r[(k + (i)) & 15]
+        {
+            const uint32_t eA = __vimin3_u16x2(R_(1), R_(2), __vmaxu2(R_(0), R_(9)));
+            const uint32_t eB = __vimin3_u16x2(R_(9), R_(10), __vmaxu2(R_(2), R_(11)));
+            const uint32_t c1 = __vimin3_u16x2(R_(3), R_(4), R_(5)), c2 = __vimin3_u16x2(R_(6), R_(7), R_(8));
+            g[q] = __vimin3_u16x2(c1, c2, __vmaxu2(eA, eB));
+        }
+        {
+            const uint32_t eA = __vimax3_u16x2(R_(1), R_(2), __vminu2(R_(0), R_(9)));
+            const uint32_t eB = __vimax3_u16x2(R_(9), R_(10), __vminu2(R_(2), R_(11)));
+            const uint32_t c1 = __vimax3_u16x2(R_(3), R_(4), R_(5)), c2 = __vimax3_u16x2(R_(6), R_(7), R_(8));
+            h[q] = __vimax3_u16x2(c1, c2, __vminu2(eA, eB));
+        }
+#undef R_
+    }
+    Mn = __vmaxu2(__vimax3_u16x2(g[0], g[1], g[2]), g[3]);
+    Mx = __vminu2(__vimin3_u16x2(h[0], h[1], h[2]), h[3]);
+}
+#else
 __device__ __forceinline__ void arc_minmax(const uint32_t (&r)[16], uint32_t& Mn, uint32_t& Mx)
 {
     uint32_t a[16], b[16];
@@ -291,6 +323,7 @@ __device__ __forceinline__ void arc_minmax(const uint32_t (&r)[16], uint32_t& Mn
     Mx = __vimin3_u16x2(Mx, __vimin3_u16x2(b[9], b[10], b[11]), __vimin3_u16x2(b[12], b[13], b[14]));
     Mx = __vminu2(Mx, b[15]);
 }
+#endif
 
 // packed epilogue for two pixels: strength = max(Mn - v, v - Mx) per s16 lane, response = strength-1 where
 // strength > th, else 0.  v2/Mn/Mx are u16x2 (values 0..255); returns the two responses in the low bytes of each lane.
@@ -1085,15 +1118,25 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
     return ORB_OK;
 }
 
-int orb_resize_smem_setup(int max_bytes)
+// cudaFuncAttributeMaxDynamicSharedMemorySize is one value per kernel and device, shared by every context of the process: contexts
+// of different shapes (ORB-SLAM keeps a 1000- and a 2000-feature extractor alive, src/Tracking.cc:111,126) must only ever RAISE it.
+static int raise_dyn_smem(const void* fn, int slot, int bytes)
 {
-    ORB_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
+    static std::mutex mu;
+    static int cur[3][64] = {};
+    int dev = 0;
+    ORB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && bytes <= cur[slot][dev]) return ORB_OK;
+    ORB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (dev >= 0 && dev < 64) cur[slot][dev] = bytes;
     return ORB_OK;
 }
 
+int orb_resize_smem_setup(int max_bytes) { return raise_dyn_smem((const void*)k_resize, 0, max_bytes); }
+
 int orb_select_smem_setup(int max_bytes)
 {
-    ORB_CUDA(cudaFuncSetAttribute(k_select<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
-    ORB_CUDA(cudaFuncSetAttribute(k_select<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
-    return ORB_OK;
+    const int rc = raise_dyn_smem((const void*)k_select<false>, 1, max_bytes);
+    return rc ? rc : raise_dyn_smem((const void*)k_select<true>, 2, max_bytes);
 }

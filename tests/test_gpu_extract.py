@@ -216,3 +216,21 @@ def test_harris_score_vs_oracle(pkg, po, shape, nf, th):
     fk, _ = pkg.ORBextractor(nf, 1.2, 8, 1, th, max_width=w, max_height=h, max_batch=1)(img)
     assert len(fk) != len(kps) or not np.array_equal(fk["x"], kps["x"])
     ex.close()
+
+
+def test_two_extractors_of_different_shapes_coexist(pkg, po):
+    """ORB-SLAM keeps two long-lived extractors (src/Tracking.cc:111,126: nFeatures and 2*nFeatures); a later, smaller context must
+    not shrink per-kernel attributes the earlier one relies on."""
+    from orbslam_jpminipc_b200.synth import synth_frame
+    big = pkg.ORBextractor(2000, 1.2, 8, 1, 20, device=0, max_width=752, max_height=480, max_batch=2)
+    a = synth_frame(480, 752, 4100)
+    k1, d1 = big(a)
+    small = pkg.ORBextractor(300, 1.2, 8, 1, 20, device=0, max_width=320, max_height=240, max_batch=1)
+    b = synth_frame(240, 320, 4101)
+    ks, ds = small(b)
+    k2, d2 = big(a)                                          # the first context still works and gives the same answer
+    assert np.array_equal(k1, k2) and np.array_equal(d1, d2)
+    rk, rd = po.OracleExtractor(2000, 1.2, 8, 1, 20)(a)
+    assert len(k2) == len(rk) and np.array_equal(d2, rd)
+    rks, rds = po.OracleExtractor(300, 1.2, 8, 1, 20)(b)
+    assert len(ks) == len(rks) and np.array_equal(ds, rds)
