@@ -45,6 +45,10 @@ def lib():
         L.ref_frame_set_pose.argtypes = [vp, vp]
         L.ref_frame_set_featvec.argtypes = [vp, i, vp, vp, vp]
         L.ref_frame_set_mappoints.argtypes = [vp, vp, vp, vp]
+        L.ref_frame_set_bowvec.argtypes = [vp, i, vp, vp]
+        L.ref_detect_relocalisation_candidates.argtypes = [vp, vp, vp, i, vp, vp, vp]
+        L.ref_frame_update_points.argtypes = [vp]
+        L.ref_search_by_projection_kf.argtypes = [vp, vp, vp, f, i, f, i, vp, vp]
         L.ref_descriptor_distance.argtypes = [vp, vp]
         L.ref_search_by_projection_ff.argtypes = [vp, vp, f, f, i, vp]
         L.ref_search_by_projection_mappoints.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, f, f, vp]
@@ -149,6 +153,15 @@ class RefFrame:
         lib().ref_frame_set_featvec(self._h, len(a), _p(a), _p(b), _p(c))
         return self
 
+    def update_points(self):
+        lib().ref_frame_update_points(self._h)
+        return self
+
+    def set_bowvec(self, word, val):
+        w, v = np.ascontiguousarray(word, np.int32), np.ascontiguousarray(val, np.float64)
+        lib().ref_frame_set_bowvec(self._h, len(w), _p(w), _p(v))
+        return self
+
     def set_mappoints(self, has, xyz=None, outlier=None):
         has = np.ascontiguousarray(has, np.uint8)
         xyz = None if xyz is None else np.ascontiguousarray(xyz, np.float32)
@@ -175,6 +188,14 @@ def search_by_projection_mappoints(f, in_view, proj_x, proj_y, level, view_cos, 
     n = _ok(lib().ref_search_by_projection_mappoints(f._h, len(iv), _p(iv), _p(px), _p(py), _p(lv), _p(vc), _p(dd), th, nnratio, _p(m)),
             "SearchByProjection(F,MapPoints)")
     return n, m
+
+
+def search_by_projection_kf(cur, kf, already_found, th, orb_dist, nnratio=0.9, check_ori=True, match_cur=None):
+    m = np.full(cur.n, -1, np.int32) if match_cur is None else np.ascontiguousarray(match_cur, np.int32)
+    af = np.ascontiguousarray(already_found, np.uint8)
+    pred = np.full(kf.n, -1, np.int32)
+    n = _ok(lib().ref_search_by_projection_kf(cur._h, kf._h, _p(af), th, orb_dist, nnratio, int(check_ori), _p(m), _p(pred)), "SearchByProjection(F,KF)")
+    return n, m, pred
 
 
 def search_by_bow(kf, f, nnratio, check_ori=True):
@@ -217,6 +238,15 @@ def distinctive_descriptor(desc):
     out = np.zeros(32, np.uint8)
     rc = _ok(lib().ref_distinctive_descriptor(_p(d), len(d), _p(out)), "ComputeDistinctiveDescriptors")
     return out if rc == 0 else None
+
+
+def detect_relocalisation_candidates(vocab, query, keyframes):
+    """KeyFrameDatabase::DetectRelocalisationCandidates over a database holding `keyframes` -> (common words, score, returned?)"""
+    n = len(keyframes)
+    hs = (C.c_void_p * n)(*[k._h for k in keyframes])
+    common, score, cand = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.int32)
+    _ok(lib().ref_detect_relocalisation_candidates(vocab._h, query._h, hs, n, _p(common), _p(score), _p(cand)), "DetectRelocalisationCandidates")
+    return common, score, cand.astype(bool)
 
 
 class RefVocabulary:

@@ -502,4 +502,95 @@ double ref_vocab_score(void* v_, const int32_t* w1, const double* v1, int n1, co
     return v->score(a, b);
 }
 
+/* BowVector of a frame from (word ascending, value) arrays; must precede anything that makes the KeyFrame (it copies F.mBowVec) */
+void ref_frame_set_bowvec(void* h, int n, const int32_t* word, const double* val)
+{
+    RefFrame* r = (RefFrame*)h;
+    r->f.mBowVec.clear();
+    for (int i = 0; i < n; i++) r->f.mBowVec.insert(r->f.mBowVec.end(), std::make_pair((DBoW2::WordId)word[i], val[i]));
+}
+
+/* KeyFrameDatabase::add for every keyframe, then KeyFrameDatabase::DetectRelocalisationCandidates(F), src/KeyFrameDatabase.cc:198-308.
+ * common[k] = pKF->mnRelocWords, score[k] = pKF->mRelocScore (0 where the reference does not compute it), candidate[k] = returned. */
+int ref_detect_relocalisation_candidates(void* voc_, void* query_, void** kfs, int nkf, int32_t* common, float* score, int32_t* candidate)
+{
+    return guarded("DetectRelocalisationCandidates", [&] {
+        ORBVocabulary* voc = (ORBVocabulary*)voc_;
+        RefFrame* q = (RefFrame*)query_;
+        if (q->f.mnId == 0) q->f.mnId = Frame::nNextId++;     /* the reference compares mnRelocQuery (initially 0) with F->mnId */
+        KeyFrameDatabase db(*voc);
+        std::map<KeyFrame*, int> idx;
+        for (int k = 0; k < nkf; k++) {
+            KeyFrame* kf = ((RefFrame*)kfs[k])->keyframe();
+            kf->mnRelocWords = 0; kf->mRelocScore = 0.f; kf->mnRelocQuery = 0;
+            db.add(kf);
+            idx[kf] = k;
+        }
+        std::vector<KeyFrame*> cand = db.DetectRelocalisationCandidates(&q->f);
+        for (int k = 0; k < nkf; k++) {
+            KeyFrame* kf = ((RefFrame*)kfs[k])->keyframe();
+            common[k] = kf->mnRelocQuery == q->f.mnId ? kf->mnRelocWords : 0;
+            score[k] = kf->mRelocScore;
+            candidate[k] = 0;
+        }
+        for (KeyFrame* kf : cand) candidate[idx.at(kf)] = 1;
+        return (int)cand.size();
+    });
+}
+
+/* MapPoint::UpdateNormalAndDepth (src/MapPoint.cc:271-313) on every point of this frame's KeyFrame: fills the normal and the scale
+ * invariance distances the back-end searches read.  Call after the pose is set. */
+void ref_frame_update_points(void* h)
+{
+    RefFrame* r = (RefFrame*)h;
+    for (MapPoint* p : r->f.mvpMapPoints) if (p) p->UpdateNormalAndDepth();
+}
+
+/* ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, th, ORBdist), :1622-1746.
+ * already_found[i] != 0 puts the KeyFrame's point i into sAlreadyFound.  match_cur[i2] in: >= 0 -> the keypoint already carries some
+ * other map point; out: KeyFrame feature index of the point assigned, the input value where it was occupied, else -1.
+ * pred_level[i] out: the level the reference derives for point i (:1662-1669, recomputed here with the same member calls) or -1 when
+ * the point is absent; the C ABI of the CUDA path takes that level from its caller. */
+int ref_search_by_projection_kf(void* cur_, void* kf_, const uint8_t* already_found, float th, int orb_dist, float nnratio, int check_ori,
+                                int32_t* match_cur, int32_t* pred_level)
+{
+    RefFrame *cur = (RefFrame*)cur_, *k = (RefFrame*)kf_;
+    return guarded("SearchByProjection(F,KF)", [&] {
+        cur->statics();
+        KeyFrame* kf = k->keyframe();
+        std::vector<MapPoint*> pts = kf->GetMapPointMatches();
+        std::map<MapPoint*, int> idx;
+        index_of(pts, idx);
+        std::set<MapPoint*> found;
+        const cv::Mat Rcw = cur->f.mTcw.rowRange(0, 3).colRange(0, 3);
+        const cv::Mat tcw = cur->f.mTcw.rowRange(0, 3).col(3);
+        const cv::Mat Ow = -Rcw.t() * tcw;
+        for (size_t i = 0; i < pts.size(); i++) {
+            pred_level[i] = -1;
+            if (!pts[i]) continue;
+            if (already_found[i]) found.insert(pts[i]);
+            cv::Mat x3Dw = pts[i]->GetWorldPos();
+            float minDistance = pts[i]->GetMinDistanceInvariance();
+            cv::Mat PO = x3Dw - Ow;
+            float dist3D = cv::norm(PO);
+            float ratio = dist3D / minDistance;
+            std::vector<float>::iterator it = std::lower_bound(cur->f.mvScaleFactors.begin(), cur->f.mvScaleFactors.end(), ratio);
+            pred_level[i] = std::min(static_cast<int>(it - cur->f.mvScaleFactors.begin()), cur->f.mnScaleLevels - 1);
+        }
+        std::vector<MapPoint*> other(cur->f.N, nullptr);
+        for (int i = 0; i < cur->f.N; i++) {
+            other[i] = match_cur[i] >= 0 ? cur->new_point(nullptr, cur->f.mDescriptors.ptr(i)) : nullptr;
+            cur->f.mvpMapPoints[i] = other[i];
+        }
+        ORBmatcher m(nnratio, check_ori != 0);
+        const int n = m.SearchByProjection(cur->f, kf, found, th, orb_dist);
+        for (int i = 0; i < cur->f.N; i++) {
+            MapPoint* p = cur->f.mvpMapPoints[i];
+            if (!p) match_cur[i] = -1;
+            else if (p != other[i]) match_cur[i] = idx.at(p);
+        }
+        return n;
+    });
+}
+
 } // extern "C"

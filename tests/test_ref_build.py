@@ -364,3 +364,60 @@ def test_vocabulary_transform_and_score(po, tmp_path, k, L, levelsup, prune, ord
         for b in bows[1:]:
             s_ref, s_orc = rv.score(a, b), po.bow_score_l1(a, b)
             assert np.float64(s_ref).view(np.uint64) == np.float64(s_orc).view(np.uint64)
+
+
+def test_relocalisation_candidate_scoring(po, tmp_path):
+    """KeyFrameDatabase::add + DetectRelocalisationCandidates (src/KeyFrameDatabase.cc:198-308) on BowVectors made by DBoW2's own
+    transform: shared-word counts, the 0.8*max gate and the L1 scores against the oracle's orc_bow_score_db."""
+    from orbslam_jpminipc_b200 import synth
+    k, L = 6, 4
+    parent, desc, weight = synth.synth_vocabulary(k, L, seed=11)
+    path = str(tmp_path / "voc.txt")
+    synth.write_vocabulary_text(path, k, L, parent, desc, weight, trailing_newline=False)
+    rv = pyref.RefVocabulary(path)
+    rng = np.random.default_rng(4)
+    leaves = np.nonzero(~np.isin(np.arange(len(parent)), parent))[0]
+    scene = rng.choice(leaves, 400)                                    # the query sees these words
+
+    def bow_of(words):
+        feats = desc[words] ^ np.packbits((rng.random((len(words), 256)) < 0.03).astype(np.uint8), axis=1)
+        return rv.transform(feats, 4)[0]
+    qbow = bow_of(scene)
+    kf_bows = []
+    for i in range(40):                                                 # keyframes sharing 0 .. 100 % of the scene
+        share = int(len(scene) * (i % 10) / 9.0)
+        words = np.concatenate([rng.choice(scene, share), rng.choice(leaves, 300 - min(share, 299))]) if share else rng.choice(leaves, 300)
+        kf_bows.append(bow_of(words))
+    kp = np.zeros(1, pyref.KP_DTYPE); kp["x"] = 10; kp["y"] = 10
+    d1 = np.zeros((1, 32), np.uint8)
+    cam = (640, 480, 500.0, 500.0, 320.0, 240.0)
+    kfs = [pyref.RefFrame(kp, d1, *cam).set_bowvec(*b) for b in kf_bows]
+    q = pyref.RefFrame(kp, d1, *cam).set_bowvec(*qbow)
+    common, score, cand = pyref.detect_relocalisation_candidates(rv, q, kfs)
+    ocommon, oscore, omax = po.bow_score_db(qbow, kf_bows)
+    assert omax > 50 and common.max() == omax
+    assert np.array_equal(common, ocommon)
+    assert np.array_equal(score.view(np.uint32), oscore.view(np.uint32))
+    assert cand.any() and (score[cand] > 0).all()
+    # no covisibility edges here, so the returned set is { score > 0.75 * best score } (:262-306)
+    assert np.array_equal(cand, score > np.float32(0.75) * score.max())
+
+
+@pytest.mark.parametrize("shape,nf,th,dist,ori", [((240, 320), 500, 10.0, 100, True), ((480, 752), 1000, 3.0, 64, True), ((376, 1241), 2000, 10.0, 100, False)])
+def test_search_by_projection_keyframe(po, shape, nf, th, dist, ori):
+    """src/ORBmatcher.cc:1622-1746 (relocalisation).  The level prediction (:1662-1669) is the caller's job at the C ABI, so the
+    reference's own levels (from MapPoint::UpdateNormalAndDepth + GetMinDistanceInvariance) are handed to the oracle."""
+    (ka, da), (kb, db), cam, has, outl, xyz, T = _scene(po, shape[0], shape[1], nf, 8300 + nf)
+    rng = np.random.default_rng(nf + 1)
+    found = ((rng.random(len(ka)) < 0.1) & (has > 0)).astype(np.uint8)
+    pre = np.full(len(kb), -1, np.int32)
+    pre[::9] = 4242
+    rkf = pyref.RefFrame(ka, da, *cam).set_mappoints(has, xyz).update_points()        # keyframe at the world origin
+    rcur = pyref.RefFrame(kb, db, *cam).set_pose(T)
+    nm, match, pred = pyref.search_by_projection_kf(rcur, rkf, found, th, dist, 0.9, ori, pre.copy())
+    assert (pred[has > 0] >= 0).all() and len(np.unique(pred[has > 0])) > 2
+    active = ((has > 0) & (found == 0)).astype(np.uint8)
+    rn, rmatch = po.search_by_projection_kf(po.OracleFrame(kb, db, *cam), active, xyz, T, np.maximum(pred, 0), da, ka["angle"], th, dist, ori,
+                                            match_cur=pre.copy())
+    assert nm > 10
+    assert nm == rn and np.array_equal(match, rmatch)
