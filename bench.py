@@ -475,6 +475,27 @@ def run_gpu(args):
     step_device()                                          # leave the 752x480 results in the output buffers
     torch.cuda.synchronize()
 
+    # ---- single-frame latency through orb_extract (how the tracking thread calls the extractor: one frame, host buffers in and
+    #      out, blocking); with and without the CUDA-graph replay of the pass ----
+    def frame_latency(graph):
+        old = os.environ.get("ORB_GRAPH")
+        os.environ["ORB_GRAPH"] = "1" if graph else "0"
+        ex1 = pkg.ORBextractor(NFEAT, SCALE, NLEVELS, 1, FAST_TH, device=local, max_width=W, max_height=H, max_batch=1)
+        if old is None:
+            del os.environ["ORB_GRAPH"]
+        else:
+            os.environ["ORB_GRAPH"] = old
+        for i in range(10):
+            ex1(base[i % len(base)])
+        ts = []
+        for i in range(200):
+            t0 = time.perf_counter()
+            ex1(base[i % len(base)])
+            ts.append(time.perf_counter() - t0)
+        return {"median_ms": float(np.median(ts) * 1e3), "p90_ms": float(np.percentile(ts, 90) * 1e3)}
+    latency = {"api": "orb_extract (one 752x480 frame per blocking call, pageable host buffers, python ctypes caller)",
+               "graph_replay": frame_latency(True), "plain_launches": frame_latency(False)} if rank == 0 else None
+
     # ---- roofline of the dominant kernel ----
     hbm, hbm_src = measured_peaks()
     dom = max(stage, key=stage.get)
@@ -520,7 +541,7 @@ def run_gpu(args):
                     "synchronous_call": {"value": frames_total / (e2e_sync_ms * 1e-3), "ms_per_step": e2e_sync_ms / args.steps,
                                          "gpu_launches_per_step": e2e_launches, "chunk": args.e2e_chunk,
                                          "api": "orb_extract_batch (one blocking call per step, internally chunked + double-buffered)"}},
-            "roofline": roofline, "config0_640x480": config0, "matching": matching}
+            "roofline": roofline, "config0_640x480": config0, "single_frame_latency": latency, "matching": matching}
     sbp_inputs = matching.pop("_sbp_inputs", None) if matching else None
     vocab_inputs = matching.pop("_vocab_inputs", None) if matching else None
     if args.cpu_baseline:

@@ -1,5 +1,6 @@
 // orb_api.cu — C ABI (include/orb_b200.h): context, device buffers, extraction entry points.
 #include "orb_internal.h"
+#include <atomic>
 #include <climits>
 #include <algorithm>
 #include <cstdio>
@@ -66,10 +67,12 @@ int orb_build_tmaps(orb_ctx* c, WorkSet& W, int nframes)
     return ORB_OK;
 }
 
+static std::atomic<long long> g_alloc_gen{0};        // bumped by every (re)allocation: captured graphs hold raw pointers and are keyed on it
 template <typename T>
 static int ensure(T*& p, size_t& cap, size_t bytes)
 {
     if (bytes <= cap && p) return ORB_OK;
+    g_alloc_gen++;
     if (p) { cudaFree(p); p = nullptr; cap = 0; }
     ORB_CUDA(cudaMalloc((void**)&p, std::max<size_t>(bytes, 256)));
     cap = std::max<size_t>(bytes, 256);
@@ -113,6 +116,7 @@ static int prepare(orb_ctx* c, int w, int h)
         for (int l = 1; l < c->plan.nlevels; l++) rsm = std::max(rsm, (size_t)2 * (((size_t)c->rs_box_w[l] * c->rs_box_h[l] + 127) & ~(size_t)127) + 16);
         rc = orb_resize_smem_setup((int)rsm); if (rc) return rc;
         c->plan_valid = true;
+        c->plan_gen++;
     }
     for (WorkSet& W : c->ws) W.tm_w = rebuild ? 0 : W.tm_w;      // a new plan invalidates the descriptors
     return ORB_OK;
@@ -141,6 +145,51 @@ static int prepare_ws(orb_ctx* c, WorkSet& W, int nimg)
     }
     // descriptors span the whole allocation (capacity in frames), so they survive smaller batches
     return orb_build_tmaps(c, W, (int)(W.planes_bytes / P.frame_bytes));
+}
+
+// One extraction pass = 1 memset + 14 kernels on two streams.  For small batches (the tracking thread's one frame per call) the host
+// cost of those launches is most of the latency, so a pass whose shape AND buffers repeat is captured into a CUDA graph the second
+// time it comes by and replayed afterwards.  Not used on the legacy default stream (capture is not allowed there), in profiling mode,
+// or for large batches, where launch cost is noise.
+static int launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_in, int n, int w, int h, int stride, size_t pitch,
+                          orb_keypoint* o_k, uint8_t* o_d, int cap, int32_t* o_c, cudaStream_t s)
+{
+    const bool eligible = c->use_graph && !c->profile && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread &&
+                          (double)n * w * h <= 12e6;
+    if (!eligible) return orb_launch_extract(c, W, d_in, n, w, h, stride, pitch, o_k, o_d, cap, o_c, s);
+    WorkSet::GraphKey key;
+    key.in = d_in; key.kps = o_k; key.desc = o_d; key.counts = o_c; key.planes = W.d_planes;
+    key.n = n; key.w = w; key.h = h; key.stride = stride; key.cap = cap; key.pitch = pitch; key.plan_gen = c->plan_gen * 1000003LL + g_alloc_gen;
+    if (W.graph_exec && W.graph_key == key) {
+        ORB_CUDA(cudaGraphLaunch(W.graph_exec, s));
+        c->last_launches = W.graph_launches;
+        return ORB_OK;
+    }
+    const bool repeat = W.last_key == key;
+    W.last_key = key;
+    if (!repeat) return orb_launch_extract(c, W, d_in, n, w, h, stride, pitch, o_k, o_d, cap, o_c, s);
+    if (W.graph_exec) { cudaGraphExecDestroy(W.graph_exec); W.graph_exec = nullptr; }
+    ORB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int rc = orb_launch_extract(c, W, d_in, n, w, h, stride, pitch, o_k, o_d, cap, o_c, s);
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(s, &g);
+    if (rc != ORB_OK || ce != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        if (rc != ORB_OK) return rc;
+        c->use_graph = 0;                                   // capture is not possible here: fall back to plain launches for good
+        return orb_launch_extract(c, W, d_in, n, w, h, stride, pitch, o_k, o_d, cap, o_c, s);
+    }
+    const cudaError_t ci = cudaGraphInstantiate(&W.graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (ci != cudaSuccess) {
+        W.graph_exec = nullptr; cudaGetLastError(); c->use_graph = 0;
+        return orb_launch_extract(c, W, d_in, n, w, h, stride, pitch, o_k, o_d, cap, o_c, s);
+    }
+    W.graph_key = key;
+    W.graph_launches = c->last_launches;
+    ORB_CUDA(cudaGraphLaunch(W.graph_exec, s));
+    return ORB_OK;
 }
 
 extern "C" {
@@ -178,6 +227,7 @@ orb_ctx* orb_create(int device, int nfeatures, float scale_factor, int nlevels, 
     c->device = device; c->nfeatures = nfeatures; c->scale_factor_f = scale_factor; c->nlevels = nlevels;
     c->score_type = score_type; c->fast_th = fast_th; c->max_w = max_w; c->max_h = max_h; c->max_batch = max_batch;
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
+    if (const char* e = getenv("ORB_GRAPH")) c->use_graph = atoi(e);
     if (const char* e = getenv("ORB_FORK_EARLY")) c->fork_early = atoi(e);
     if (const char* e = getenv("ORB_FAST_CTAS_FORK")) c->fast_ctas = atoi(e);
     if (const char* e = getenv("ORB_BLUR_CTAS")) c->blur_ctas = atoi(e);
@@ -205,6 +255,7 @@ void orb_destroy(orb_ctx* c)
     for (WorkSet& W : c->ws) {
         void* wp[] = { W.d_planes, W.d_work, W.d_blur, W.d_bitmap, W.d_cand, W.d_cand64, W.d_ntotal, W.d_lvl, W.d_nkept, W.d_counters };
         for (void* p : wp) if (p) cudaFree(p);
+        if (W.graph_exec) cudaGraphExecDestroy(W.graph_exec);
         if (W.aux_stream) cudaStreamDestroy(W.aux_stream);
         if (W.ev_fork) cudaEventDestroy(W.ev_fork);
         if (W.ev_join) cudaEventDestroy(W.ev_join);
@@ -269,7 +320,7 @@ int orb_extract_batch_device(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w,
     if ((rc = prepare_ws(c, c->ws[0], n0))) return rc;
     if (n1 && (rc = prepare_ws(c, c->ws[1], n1))) return rc;
     c->last_n0 = n0; c->last_n1 = n1;
-    if (!split) return orb_launch_extract(c, c->ws[0], d_imgs, nimg, w, h, stride, frame_pitch, d_kps, d_desc, cap, d_counts, us);
+    if (!split) return launch_extract(c, c->ws[0], d_imgs, nimg, w, h, stride, frame_pitch, d_kps, d_desc, cap, d_counts, us);
     ORB_CUDA(cudaEventRecord(c->ev_user, us));
     int launches = 0;
     for (int k = 0; k < 2; k++) {
@@ -381,7 +432,7 @@ int orb_extract_batch_async(orb_ctx* c, const uint8_t* imgs, int nimg, int w, in
             // B200, 256 frames 752x480 per step, streaming: chunk 256 chained 86.9 K frames/s, free 81.6 K; chunk 64 chained 67.4 K,
             // free 78.9 K (small grids do not fill the GPU and gain from overlapping), hence the size test.
             if (c->chain_chunks && c->kernels_pending && (double)n * w * h >= 40e6) ORB_CUDA(cudaStreamWaitEvent(s, c->ev_free[slot ^ 1], 0));
-            rc = orb_launch_extract(c, c->ws[slot], d_in, n, w, h, stride, frame_pitch, o_k, o_d, cap, o_c, s);
+            rc = launch_extract(c, c->ws[slot], d_in, n, w, h, stride, frame_pitch, o_k, o_d, cap, o_c, s);
             if (rc != ORB_OK) return rc;
             launches += c->last_launches;
             ORB_CUDA(cudaEventRecord(c->ev_free[slot], s));

@@ -1041,6 +1041,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         cudaEventRecord(e, s);
         c->prof_events.push_back(e);
     };
+    ORB_CUDA(cudaMemsetAsync(W.d_counters, 0, 32 * sizeof(int), s));      // every tile queue of this pass (FAST 1, blur 2, resize 4+l) in one node
     mark();
     {
         const LevelGeom& L = P.L[0];
@@ -1056,7 +1057,6 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         const int tiles = ((D.w + tw - 1) / tw) * ((D.h + th - 1) / th) * nimg;
         const int bufb = (c->rs_box_w[l] * c->rs_box_h[l] + 127) & ~127;
         const int grid = std::min(tiles, c->num_sms * ORB_RESIZE_CTAS);
-        cudaMemsetAsync(W.d_counters + 4 + l, 0, sizeof(int), s);
         k_resize<<<grid, ORB_RESIZE_THREADS, 2 * bufb + 16, s>>>(W.tm_resize.m[l], W.d_planes, fb, D, c->d_xtab, c->d_ytab, c->rs_box_w[l], c->rs_box_h[l],
                                                bufb, nimg, W.d_counters + 4 + l, tw, rr);
         launches++;
@@ -1070,7 +1070,6 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
     auto launch_blur = [&](cudaStream_t bs) {
         const int total = P.ntiles_blur * nimg;
         const int grid = std::min(total, c->num_sms * c->blur_ctas);
-        cudaMemsetAsync(W.d_counters + 2, 0, sizeof(int), bs);
         k_blur<<<grid, BLUR_THREADS, 0, bs>>>(W.tm_blur, W.d_blur, fb, c->d_plan, c->d_tiles_blur, P.ntiles_blur, total, W.d_counters + 2);
     };
     if (fork && c->fork_early == 1) {          // blur next to FAST: FAST saturates the ALU pipe and leaves the FMA pipe idle
@@ -1081,7 +1080,6 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
     {
         const int total = P.ntiles_fast * nimg;
         const int grid = std::min(total, c->num_sms * (fork && c->fork_early == 1 ? c->fast_ctas : FAST_CTAS));
-        cudaMemsetAsync(W.d_counters + 1, 0, sizeof(int), s);
         k_fast_nms<<<grid, FAST_THREADS, 0, s>>>(W.tm_fast, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total, W.d_counters + 1);
     }
     if (fork && c->fork_early == 2) {     // blur starts behind FAST, next to compaction + selection

@@ -90,6 +90,20 @@ struct WorkSet {
     TmapSet tm_fast{}, tm_blur{}, tm_resize{};                 // boxes: FAST tile / blur tile / resize source footprint (map l reads level l-1)
     const uint8_t* tm_base = nullptr; int tm_frames = 0, tm_w = 0, tm_h = 0;
     cudaStream_t aux_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // CUDA-graph replay of one extraction pass (orb_api.cu, launch_extract): captured the second time the same call shape and
+    // buffers come by, replayed while they stay the same
+    struct GraphKey {
+        const void *in = nullptr, *kps = nullptr, *desc = nullptr, *counts = nullptr, *planes = nullptr;
+        int n = 0, w = 0, h = 0, stride = 0, cap = 0; size_t pitch = 0; long long plan_gen = -1;
+        bool operator==(const GraphKey& o) const
+        {
+            return in == o.in && kps == o.kps && desc == o.desc && counts == o.counts && planes == o.planes && n == o.n && w == o.w && h == o.h &&
+                   stride == o.stride && cap == o.cap && pitch == o.pitch && plan_gen == o.plan_gen;
+        }
+    };
+    GraphKey graph_key{}, last_key{};
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_launches = 0;
 };
 
 struct orb_ctx {
@@ -144,6 +158,8 @@ struct orb_ctx {
     int last_launches = 0;
     int num_sms = 148;
     int split_device = 0;
+    int use_graph = 1;                                     // ORB_GRAPH=0 switches the CUDA-graph replay off
+    long long plan_gen = 0;                                // bumped whenever the plan (image shape) is rebuilt
     int fork_early = 0, fast_ctas = 6, blur_ctas = 8;      // stream-overlap tuning (ORB_FORK_EARLY / ORB_FAST_CTAS_FORK / ORB_BLUR_CTAS env)
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;   // (ORB_NSTAGES+1) per profiled launch

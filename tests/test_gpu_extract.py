@@ -234,3 +234,24 @@ def test_two_extractors_of_different_shapes_coexist(pkg, po):
     assert len(k2) == len(rk) and np.array_equal(d2, rd)
     rks, rds = po.OracleExtractor(300, 1.2, 8, 1, 20)(b)
     assert len(ks) == len(rks) and np.array_equal(ds, rds)
+
+
+def test_repeated_single_frame_calls_replay_a_graph(pkg, po):
+    """The tracking thread calls the extractor once per frame with the same buffers: from the third call on the pass is replayed from a
+    CUDA graph (orb_api.cu launch_extract).  Results must not depend on that, also when the image content and then the shape change."""
+    from orbslam_jpminipc_b200.synth import synth_frame
+    ex = pkg.ORBextractor(500, 1.2, 8, 1, 20, device=0, max_width=640, max_height=480, max_batch=1)
+    orc = po.OracleExtractor(500, 1.2, 8, 1, 20)
+    imgs = [synth_frame(240, 320, 5000 + i) for i in range(3)]
+    want = [orc(im) for im in imgs]
+    for rep in range(4):
+        for im, (rk, rd) in zip(imgs, want):
+            k, d = ex(im)
+            assert len(k) == len(rk) and np.array_equal(k["response"], rk["response"]) and np.array_equal(d, rd)
+    big = synth_frame(480, 640, 5100)                      # new plan: the captured graph must not be replayed
+    rk, rd = orc(big)
+    for rep in range(3):
+        k, d = ex(big)
+        assert len(k) == len(rk) and np.array_equal(d, rd)
+    k, d = ex(imgs[0])
+    assert np.array_equal(d, want[0][1])
