@@ -76,6 +76,8 @@ public:
     int inline GetLevels() { return nlevels; }
     float inline GetScaleFactor() { return (float)scaleFactor; }
     orb_ctx* context() { return ctx; }
+    /* not in the reference: pick which reference BUILD the descriptors reproduce (orb_set_descriptor_fma, orb_b200.h) */
+    void SetDescriptorFMA(bool on) { check(orb_set_descriptor_fma(ctx, on ? 1 : 0)); }
 
 protected:
     void check(int status)

@@ -62,6 +62,11 @@ void     orb_destroy(orb_ctx*);
 int      orb_nlevels(const orb_ctx*);          /* ORBextractor::GetLevels()      include/ORBextractor.h:47 */
 float    orb_scale_factor(const orb_ctx*);     /* ORBextractor::GetScaleFactor() include/ORBextractor.h:50 */
 int      orb_keypoint_capacity(const orb_ctx*);/* rows to allocate per image: sum of per-level quotas */
+/* Which reference BUILD the descriptors reproduce.  The rotation of the sampling pattern, `x*b + y*a` / `x*a - y*b`
+ * (src/ORBextractor.cc:166-167), is written with two roundings per expression; the reference's own flags (-O3 -march=native,
+ * CMakeLists.txt:12-13) let GCC contract it to fma(x, b, y*a) / fma(x, a, -(y*b)) on an FMA-capable host, which changes about 2
+ * descriptor bits per 40 000 keypoints.  on = 0 (default): as written; on = 1: the contracted form.  Keypoints are unaffected. */
+int      orb_set_descriptor_fma(orb_ctx*, int on);
 
 /* ORBextractor::operator()(image, mask, keypoints, descriptors), src/ORBextractor.cc:718-779.
  * The mask is a no-op in the reference (built at :791-810 but never handed to FAST, :601-607),

@@ -249,7 +249,7 @@ float ic_angle(const uint8_t* center, int step, const int* umax)
 /* computeOrbDescriptor, src/ORBextractor.cc:155-194.  cos/sin: the reference's
  * cosf/sinf (libm-variant dependent in the last bit) are pinned to correctly
  * rounded single precision computed through double. */
-void rbrief(const uint8_t* center, int step, float angle_deg, uint8_t* desc)
+void rbrief(const uint8_t* center, int step, float angle_deg, uint8_t* desc, bool fma_form = false)
 {
     const float factorPI = (float)(M_PI / 180.f);        /* :154 */
     float angle = angle_deg * factorPI;                   /* :159 */
@@ -259,8 +259,14 @@ void rbrief(const uint8_t* center, int step, float angle_deg, uint8_t* desc)
         int val = 0;
         for (int k = 0; k < 8; k++) {
             float x0 = pat[4 * k], y0 = pat[4 * k + 1], x1 = pat[4 * k + 2], y1 = pat[4 * k + 3];
-            int t0 = center[cv_roundf(x0 * b + y0 * a) * step + cv_roundf(x0 * a - y0 * b)];
-            int t1 = center[cv_roundf(x1 * b + y1 * a) * step + cv_roundf(x1 * a - y1 * b)];
+            int t0, t1;
+            if (!fma_form) {
+                t0 = center[cv_roundf(x0 * b + y0 * a) * step + cv_roundf(x0 * a - y0 * b)];
+                t1 = center[cv_roundf(x1 * b + y1 * a) * step + cv_roundf(x1 * a - y1 * b)];
+            } else {     /* GCC's contraction under the reference's own -O3 -march=native: vfmadd231ss / vfmsub132ss */
+                t0 = center[cv_roundf(fmaf(x0, b, y0 * a)) * step + cv_roundf(fmaf(x0, a, -(y0 * b)))];
+                t1 = center[cv_roundf(fmaf(x1, b, y1 * a)) * step + cv_roundf(fmaf(x1, a, -(y1 * b)))];
+            }
             val |= (t0 < t1) << k;
         }
         desc[i] = (uint8_t)val;
@@ -333,7 +339,7 @@ void gaussian_blur7(const uint8_t* src, int w, int h, int stride, uint8_t* dst, 
 
 /* ================================================================ extractor */
 struct orc_extractor {
-    int nfeatures; double scaleFactor; int nlevels, scoreType, fastTh, blurVariant;
+    int nfeatures; double scaleFactor; int nlevels, scoreType, fastTh, blurVariant; bool descFma = false;
     std::vector<float> mvScaleFactor, mvInvScaleFactor;
     std::vector<int> mnFeaturesPerLevel, umax;
     struct Level {
@@ -386,6 +392,7 @@ orc_extractor* orc_extractor_create(int nfeatures, float scale_factor, int nleve
 }
 
 void orc_extractor_destroy(orc_extractor* e) { delete e; }
+void orc_extractor_set_descriptor_fma(orc_extractor* e, int on) { e->descFma = on != 0; }
 
 /* HarrisResponses(img, pts, 7, HARRIS_K), src/ORBextractor.cc:79-120, for one keypoint at (x, y) of the image whose origin is img */
 static float harris_response(const uint8_t* img, int step, int x, int y)
@@ -557,7 +564,7 @@ int orc_extract(orc_extractor* e, const uint8_t* img, int w, int h, int stride,
         for (size_t i = 0; i < keypoints.size(); i++) {
             const KP& k = keypoints[i];
             rbrief(roi + (size_t)cv_roundf(k.y) * L.stride + cv_roundf(k.x), L.stride, k.angle,
-                   desc + (size_t)(offset + i) * 32);
+                   desc + (size_t)(offset + i) * 32, e->descFma);
         }
         if (level != 0) {
             float scale = e->mvScaleFactor[level];

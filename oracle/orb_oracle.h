@@ -35,6 +35,9 @@ typedef struct orc_extractor orc_extractor;
 orc_extractor* orc_extractor_create(int nfeatures, float scale_factor, int nlevels,
                                     int score_type, int fast_th, int blur_variant);
 void orc_extractor_destroy(orc_extractor*);
+/* descriptor rotation x*b + y*a (src/ORBextractor.cc:166-167) as GCC contracts it under the reference's own -O3 -march=native on an
+ * FMA host: fma(x, b, y*a) / fma(x, a, -(y*b)).  Default 0 = as written (two roundings). */
+void orc_extractor_set_descriptor_fma(orc_extractor*, int on);
 
 /* ORBextractor::operator(), src/ORBextractor.cc:718-779.  Returns 0, or <0 on error
  * (-2: geometry the reference itself would throw on, -3: capacity). */

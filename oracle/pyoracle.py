@@ -48,6 +48,7 @@ def lib():
         L.orc_extractor_create.restype = C.c_void_p
         L.orc_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_extractor_destroy.argtypes = [C.c_void_p]
+        L.orc_extractor_set_descriptor_fma.argtypes = [C.c_void_p, C.c_int]
         L.orc_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_int, C.POINTER(C.c_int)]
         L.orc_scale_factor.restype = C.c_float
@@ -128,9 +129,11 @@ class OracleExtractor:
     """ORB_SLAM::ORBextractor restated on the CPU (reference include/ORBextractor.h:32-77)."""
     HARRIS_SCORE, FAST_SCORE = 0, 1
 
-    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, scoreType=1, fastTh=20, blur=BLUR_F32):
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, scoreType=1, fastTh=20, blur=BLUR_F32, desc_fma=False):
         self.nfeatures, self.nlevels = nfeatures, nlevels
         self._h = lib().orc_extractor_create(nfeatures, scaleFactor, nlevels, scoreType, fastTh, blur)
+        if desc_fma:
+            lib().orc_extractor_set_descriptor_fma(self._h, 1)
 
     def __del__(self):
         if getattr(self, "_h", None):

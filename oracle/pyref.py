@@ -77,16 +77,39 @@ def _ok(rc, what):
     return rc
 
 
-class RefExtractor:
-    """ORB_SLAM::ORBextractor (reference include/ORBextractor.h:32-77, src/ORBextractor.cc), the real thing."""
+_SO_FMA = os.path.join(_HERE, "_ref", "libref_extractor_fma.so")
+_lib_fma = None
 
-    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, scoreType=1, fastTh=20):
-        self._h = lib().ref_extractor_create(nfeatures, scaleFactor, nlevels, scoreType, fastTh)
+
+def fma_available():
+    return os.path.exists(_SO_FMA)
+
+
+def lib_fma():
+    """the reference extractor built with floating-point contraction on (its own -O3 -march=native on an FMA host)"""
+    global _lib_fma
+    if _lib_fma is None:
+        L = C.CDLL(_SO_FMA)
+        L.ref_extractor_create.restype = C.c_void_p
+        L.ref_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.ref_extractor_destroy.argtypes = [C.c_void_p]
+        L.ref_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        _lib_fma = L
+    return _lib_fma
+
+
+class RefExtractor:
+    """ORB_SLAM::ORBextractor (reference include/ORBextractor.h:32-77, src/ORBextractor.cc), the real thing.
+    fma=True: the build with floating-point contraction on."""
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, scoreType=1, fastTh=20, fma=False):
+        self._L = lib_fma() if fma else lib()
+        self._h = self._L.ref_extractor_create(nfeatures, scaleFactor, nlevels, scoreType, fastTh)
         self.cap = max(4 * nfeatures, 64)
 
     def __del__(self):
-        if getattr(self, "_h", None) and _lib is not None:
-            _lib.ref_extractor_destroy(self._h)
+        if getattr(self, "_h", None) and getattr(self, "_L", None) is not None:
+            self._L.ref_extractor_destroy(self._h)
             self._h = None
 
     def __call__(self, image):
@@ -94,7 +117,7 @@ class RefExtractor:
         k = np.zeros(self.cap, KP_DTYPE)
         d = np.zeros((self.cap, 32), np.uint8)
         n = C.c_int(0)
-        rc = lib().ref_extract(self._h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(k), _p(d), self.cap, C.byref(n))
+        rc = self._L.ref_extract(self._h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(k), _p(d), self.cap, C.byref(n))
         if rc != 0:
             raise RuntimeError("ref_extract failed: %d" % rc)
         return k[:n.value].copy(), d[:n.value].copy()

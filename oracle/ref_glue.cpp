@@ -45,6 +45,7 @@ int ref_extract(void* e, const uint8_t* img, int w, int h, int stride, void* kps
 
 } // extern "C"
 
+#ifndef REF_GLUE_EXTRACTOR_ONLY
 /* =====================================================================================================================
  * Map classes and ORBmatcher: the reference's Frame / KeyFrame / MapPoint / Map / KeyFrameDatabase / ORBmatcher objects
  * built from flat arrays.  Every search below runs the reference's own member function (src/ORBmatcher.cc); the glue only
@@ -594,3 +595,4 @@ int ref_search_by_projection_kf(void* cur_, void* kf_, const uint8_t* already_fo
 }
 
 } // extern "C"
+#endif /* REF_GLUE_EXTRACTOR_ONLY */

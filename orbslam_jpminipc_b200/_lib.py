@@ -21,7 +21,7 @@ GRID_COLS, GRID_ROWS = 64, 48
 # every symbol include/orb_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "orb_error_string", "orb_last_cuda_error", "orb_abi_version", "orb_create", "orb_destroy", "orb_nlevels",
-    "orb_scale_factor", "orb_keypoint_capacity", "orb_extract", "orb_extract_batch", "orb_extract_batch_device", "orb_extract_batch_async", "orb_wait",
+    "orb_scale_factor", "orb_keypoint_capacity", "orb_set_descriptor_fma", "orb_extract", "orb_extract_batch", "orb_extract_batch_device", "orb_extract_batch_async", "orb_wait",
     "orb_last_launch_count", "orb_profile_enable", "orb_profile_read", "orb_profile_stage_name", "orb_debug_level_info", "orb_debug_level_plane", "orb_descriptor_distance",
     "orb_hamming_knn2", "orb_hamming_knn2_device", "orb_knn2_merge_device", "orb_match_ratio",
     "orb_frame_grid_build", "orb_search_by_projection", "orb_search_window", "orb_search_window_best", "orb_search_for_initialization", "orb_search_by_bow", "orb_search_by_bow_kf", "orb_search_for_triangulation", "orb_host_alloc", "orb_host_free",
@@ -83,6 +83,7 @@ def lib():
     L.orb_scale_factor.restype = f32
     L.orb_scale_factor.argtypes = [vp]
     L.orb_keypoint_capacity.argtypes = [vp]
+    L.orb_set_descriptor_fma.argtypes = [vp, C.c_int]
     L.orb_extract.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, C.POINTER(C.c_int)]
     L.orb_extract_batch.argtypes = [vp, vp, i32, i32, i32, i32, sz, vp, vp, i32, vp]
     L.orb_extract_batch_async.argtypes = [vp, vp, i32, i32, i32, i32, sz, vp, vp, i32, vp, C.POINTER(C.c_longlong)]

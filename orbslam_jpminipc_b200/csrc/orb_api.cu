@@ -284,6 +284,13 @@ void orb_destroy(orb_ctx* c)
 }
 
 int orb_nlevels(const orb_ctx* c) { return c ? c->nlevels : 0; }
+
+int orb_set_descriptor_fma(orb_ctx* c, int on)
+{
+    if (!c) return ORB_ERR_INVALID;
+    if ((on != 0) != (c->desc_fma != 0)) { c->desc_fma = on != 0; c->plan_valid = false; }     // the plan carries the flag to the device
+    return ORB_OK;
+}
 float orb_scale_factor(const orb_ctx* c) { return c ? (float)c->scaleFactor : 0.f; }
 int orb_keypoint_capacity(const orb_ctx* c)
 {

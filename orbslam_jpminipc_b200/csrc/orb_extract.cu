@@ -977,6 +977,7 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
     if (lane == 0) { double sd, cd; sincos((double)arad, &sd, &cd); a = (float)cd; b = (float)sd; }
     a = __shfl_sync(0xffffffffu, a, 0); b = __shfl_sync(0xffffffffu, b, 0);
     const float2* pat = g_pattern_t + lane;
+    const bool fma_form = plan->desc_fma != 0;
     // offset = cvRound(y')*stride + cvRound(x'); the 1.5*2^23 magic add leaves the rounded integer in the mantissa
     const uint32_t magic_fix = 0u - 0x4B400000u * (uint32_t)(stride + 1);      // modulo-2^32 arithmetic, exact for the in-range result
     int val = 0;
@@ -986,8 +987,12 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
 #pragma unroll
         for (int e = 0; e < 2; e++) {
             const float2 p = __ldg(pat + (2 * k + e) * 32);
-            const uint32_t yb = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(p.x, b), __fmul_rn(p.y, a)), 12582912.0f));
-            const uint32_t xb = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(p.x, a), __fmul_rn(p.y, b)), 12582912.0f));
+            // x*b + y*a and x*a - y*b (:166-167): two roundings each as written, or, when the reference is built with its own
+            // -O3 -march=native on an FMA host, GCC's contraction fma(x, b, y*a) / fma(x, a, -(y*b)) (orb_set_descriptor_fma)
+            const float ry = fma_form ? __fmaf_rn(p.x, b, __fmul_rn(p.y, a)) : __fadd_rn(__fmul_rn(p.x, b), __fmul_rn(p.y, a));
+            const float rx = fma_form ? __fmaf_rn(p.x, a, -__fmul_rn(p.y, b)) : __fsub_rn(__fmul_rn(p.x, a), __fmul_rn(p.y, b));
+            const uint32_t yb = __float_as_uint(__fadd_rn(ry, 12582912.0f));
+            const uint32_t xb = __float_as_uint(__fadd_rn(rx, 12582912.0f));
             t[e] = bcenter[(int)(yb * (uint32_t)stride + xb + magic_fix)];
         }
         val |= (t[0] < t[1]) << k;
@@ -1086,14 +1091,13 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         ORB_CUDA(cudaEventRecord(W.ev_fork, s));
         ORB_CUDA(cudaStreamWaitEvent(W.aux_stream, W.ev_fork, 0));
     }
-    if (fork && c->fork_early) { launch_blur(W.aux_stream); ORB_CUDA(cudaEventRecord(W.ev_join, W.aux_stream)); }
+    if (fork && (c->fork_early == 1 || c->fork_early == 2)) { launch_blur(W.aux_stream); ORB_CUDA(cudaEventRecord(W.ev_join, W.aux_stream)); }
     mark();
     k_cell_compact<<<dim3((P.ncells + 7) / 8, nimg), 256, 0, s>>>(W.d_work, W.d_bitmap, fb, c->d_plan, c->d_cells, W.d_cand, W.d_ntotal);
-    if (fork && !c->fork_early) {          // blur starts when compaction is done, i.e. next to the selection kernel
+    if (fork && (c->fork_early == 0 || c->fork_early == 3)) {          // blur starts when compaction is done, i.e. next to the selection kernel
         ORB_CUDA(cudaEventRecord(W.ev_fork, s));
         ORB_CUDA(cudaStreamWaitEvent(W.aux_stream, W.ev_fork, 0));
-        launch_blur(W.aux_stream);
-        ORB_CUDA(cudaEventRecord(W.ev_join, W.aux_stream));
+        if (c->fork_early == 0) { launch_blur(W.aux_stream); ORB_CUDA(cudaEventRecord(W.ev_join, W.aux_stream)); }
     }
     mark();
     if (P.harris) {
@@ -1102,6 +1106,10 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         launches++;
     } else
         k_select<false><<<dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s>>>(c->d_plan, c->d_cells, W.d_cand, nullptr, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status);
+    if (fork && c->fork_early == 3) {      // selection first: the latency-bound kernel takes the residency it needs, blur fills the rest
+        launch_blur(W.aux_stream);
+        ORB_CUDA(cudaEventRecord(W.ev_join, W.aux_stream));
+    }
     mark();
     if (fork) ORB_CUDA(cudaStreamWaitEvent(s, W.ev_join, 0));
     else launch_blur(s);

@@ -57,6 +57,7 @@ struct Plan {
     int bm_total;          // bitmap bytes per frame
     int sel_list_cap;      // max lvl_cap over levels (k_select shared-memory list)
     int border_total;      // k_border work items (32-bit words of all frame regions) per image
+    int desc_fma;          // descriptor rotation with the reference compiler's FMA contraction (orb_set_descriptor_fma)
     LevelGeom L[ORB_MAX_LEVELS];
 };
 
@@ -158,6 +159,7 @@ struct orb_ctx {
     int last_launches = 0;
     int num_sms = 148;
     int split_device = 0;
+    int desc_fma = 0;                                      // orb_set_descriptor_fma
     int use_graph = 1;                                     // ORB_GRAPH=0 switches the CUDA-graph replay off
     long long plan_gen = 0;                                // bumped whenever the plan (image shape) is rebuilt
     int fork_early = 0, fast_ctas = 6, blur_ctas = 8;      // stream-overlap tuning (ORB_FORK_EARLY / ORB_FAST_CTAS_FORK / ORB_BLUR_CTAS env)

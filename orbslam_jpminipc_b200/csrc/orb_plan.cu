@@ -83,7 +83,7 @@ int orb_build_plan(orb_ctx* c, int w, int h)
     Plan& P = c->plan;
     memset(&P, 0, sizeof(P));
     P.nlevels = c->nlevels; P.w = w; P.h = h;
-    P.fast_th = c->fast_th; P.th_lo = std::min(c->fast_th, 7); P.harris = c->score_type == ORB_HARRIS_SCORE;
+    P.fast_th = c->fast_th; P.th_lo = std::min(c->fast_th, 7); P.harris = c->score_type == ORB_HARRIS_SCORE; P.desc_fma = c->desc_fma;
     c->cells.clear(); c->tiles_fast.clear(); c->tiles_blur.clear(); c->xtab.clear(); c->ytab.clear();
 
     int off = 0, cand = 0, lvl = 0, kp = 0, border = 0, bm = 0;

@@ -15,7 +15,7 @@ class ORBextractor:
     HARRIS_SCORE, FAST_SCORE = 0, 1
 
     def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, scoreType=1, fastTh=20,
-                 device=0, max_width=1920, max_height=1200, max_batch=64):
+                 device=0, max_width=1920, max_height=1200, max_batch=64, desc_fma=False):
         self.nfeatures, self.nlevels, self.device = nfeatures, nlevels, device
         self.max_batch = max_batch
         self._h = lib().orb_create(device, nfeatures, scaleFactor, nlevels, scoreType, fastTh,
@@ -23,6 +23,8 @@ class ORBextractor:
         if not self._h:
             raise RuntimeError("orb_create failed: " + lib().orb_last_cuda_error().decode())
         self.capacity = lib().orb_keypoint_capacity(self._h)
+        if desc_fma:                                         # reproduce a reference built with FMA contraction (orb_b200.h)
+            check(lib().orb_set_descriptor_fma(self._h, 1), "orb_set_descriptor_fma")
 
     def close(self):
         if getattr(self, "_h", None):

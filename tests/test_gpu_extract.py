@@ -255,3 +255,25 @@ def test_repeated_single_frame_calls_replay_a_graph(pkg, po):
         assert len(k) == len(rk) and np.array_equal(d, rd)
     k, d = ex(imgs[0])
     assert np.array_equal(d, want[0][1])
+
+
+def test_descriptor_fma_variant(pkg, po):
+    """orb_set_descriptor_fma: the descriptor rotation as GCC contracts it under the reference's own flags; against the oracle's variant
+    (which tests/test_ref_build.py pins to the reference built that way) and, where it travelled, that reference build itself."""
+    from oracle import pyref
+    from orbslam_jpminipc_b200.synth import synth_frames
+    frames = synth_frames(8, 480, 752, 6000)
+    ex = pkg.ORBextractor(1000, 1.2, 8, 1, 20, device=0, max_width=752, max_height=480, max_batch=8, desc_fma=True)
+    orc = po.OracleExtractor(1000, 1.2, 8, 1, 20, desc_fma=True)
+    ref = pyref.RefExtractor(1000, 1.2, 8, 1, 20, fma=True) if pyref.fma_available() else None
+    for img, (k, d) in zip(frames, ex.extract_batch(frames)):
+        rk, rd = orc(img)
+        assert len(k) == len(rk) and np.array_equal(k["angle"].view(np.uint32), rk["angle"].view(np.uint32)) and np.array_equal(d, rd)
+        if ref is not None:
+            assert np.array_equal(d, ref(img)[1])
+    # switching the flag back restores the default form
+    from orbslam_jpminipc_b200._lib import lib, check
+    check(lib().orb_set_descriptor_fma(ex._h, 0), "orb_set_descriptor_fma")
+    plain = po.OracleExtractor(1000, 1.2, 8, 1, 20)
+    for img, (k, d) in zip(frames, ex.extract_batch(frames)):
+        assert np.array_equal(d, plain(img)[1])

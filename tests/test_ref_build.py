@@ -421,3 +421,27 @@ def test_search_by_projection_keyframe(po, shape, nf, th, dist, ori):
                                             match_cur=pre.copy())
     assert nm > 10
     assert nm == rn and np.array_equal(match, rmatch)
+
+
+@pytest.mark.skipif(not pyref.fma_available(), reason="oracle/_ref/libref_extractor_fma.so not built")
+def test_extractor_fma_contracted_build(po):
+    """The reference's flags (-O3 -march=native, CMakeLists.txt:12-13) let GCC contract the descriptor rotation x*b + y*a on an FMA host.
+    oracle/_ref/libref_extractor_fma.so is src/ORBextractor.cc built that way; the oracle's desc_fma variant must equal it bit for bit,
+    and the two variants differ in (only) a handful of descriptor bits."""
+    from orbslam_jpminipc_b200.synth import synth_frame
+    nrows = nbits = total = 0
+    for (h, w, nf) in [(480, 640, 1000), (480, 752, 1000), (376, 1241, 2000)]:
+        ref_fma = pyref.RefExtractor(nf, 1.2, 8, 1, 20, fma=True)
+        orc_fma = po.OracleExtractor(nf, 1.2, 8, 1, 20, desc_fma=True)
+        orc = po.OracleExtractor(nf, 1.2, 8, 1, 20)
+        for seed in range(1000, 1008):
+            img = synth_frame(h, w, seed)
+            rk, rd = ref_fma(img)
+            fk, fd = orc_fma(img)
+            _same_keypoints(rk, fk)
+            assert np.array_equal(rd, fd)
+            pk, pd = orc(img)
+            _same_keypoints(pk, fk)                          # keypoints and angles do not depend on the variant
+            nrows += int((pd != fd).any(1).sum()); nbits += int(np.unpackbits(pd ^ fd).sum()); total += len(pk)
+    assert total > 30000
+    assert 0 < nbits <= 20 and nrows <= nbits, (nrows, nbits, total)
