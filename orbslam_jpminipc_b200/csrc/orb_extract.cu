@@ -325,16 +325,14 @@ __device__ __forceinline__ void arc_minmax(const uint32_t (&r)[16], uint32_t& Mn
 }
 #endif
 
-// packed epilogue for two pixels: strength = max(Mn - v, v - Mx) per s16 lane, response = strength-1 where
-// strength > th, else 0.  v2/Mn/Mx are u16x2 (values 0..255); returns the two responses in the low bytes of each lane.
-__device__ __forceinline__ uint32_t score2(uint32_t v2, uint32_t Mn, uint32_t Mx, uint32_t neg_th2, int th_m1)
+// packed epilogue for two pixels.  strength T = max(Mn - v, v - Mx); a corner has T > th and OpenCV's response is T - 1.  The score
+// tile holds the EXCESS q = max(T - th, 0) instead (same order among corners, 0 for the rest, so the strict NMS decides identically);
+// the survivors get th - 1 added back when they are written.  With nvp = -(v + th) and vm1 = v - th + 1 per lane (once per pixel
+// pair) one evaluation is a NOT and two VIADDMNMX.RELU:  q = max(Mn + nvp, ~Mx + vm1, 0)   (~Mx = -Mx - 1 in a 16-bit lane).
+__device__ __forceinline__ uint32_t excess2(uint32_t Mn, uint32_t Mx, uint32_t nvp, uint32_t vm1)
 {
-    const uint32_t negv = __vneg2(v2), negMx = __vneg2(Mx);
-    const uint32_t dark = __vadd2(v2, negMx);                         // v - Mx  (may be negative)
-    const uint32_t T = __viaddmax_s16x2(Mn, negv, dark);              // max(Mn - v, v - Mx)
-    const uint32_t q = __viaddmax_s16x2_relu(T, neg_th2, 0u);         // max(T - th, 0)
-    const uint32_t m = __vmins2(q, 0x00010001u);                 // 1 where corner
-    return m * (uint32_t)th_m1 + q;                                   // T - 1 where corner (lanes cannot carry)
+    const uint32_t qb = __viaddmax_s16x2_relu(Mn, nvp, 0u);
+    return __viaddmax_s16x2_relu(~Mx, vm1, qb);
 }
 
 // Persistent kernel: each CTA walks (tile, frame) work items; the image tile of item i+1 is fetched by
@@ -350,9 +348,11 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
     __shared__ __align__(4) uint8_t m_in[FSW * 4], m_l[FSW * 4], m_r[FSW * 4];
     __shared__ __align__(8) uint64_t bar[2];
     const int tid = threadIdx.x;
-    const int th = plan->th_lo;
-    const uint32_t neg_th2 = __vneg2((uint32_t)th * 0x00010001u);
-    const int th_m1 = th - 1;
+    // th = 0 (fastTh 0): a corner of strength 1 has response 0, never survives the strict NMS and never suppresses anything, exactly
+    // like a non-corner, so the kernel may treat it as one
+    const int th = max(plan->th_lo, 1);
+    const uint32_t c1 = (uint32_t)((1 - th) & 0xffff) * 0x00010001u;       // (1 - th) in both lanes
+    const uint32_t th_m1 = (uint32_t)(th - 1);
     constexpr uint32_t TILE_BYTES = FI_H * FIW * 4;
 
     auto issue = [&](int item, int buf) {      // one thread: arm the barrier, start the copy
@@ -444,21 +444,23 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
                 // corner needs one of them brighter than v+th or darker than v-th.  Flat areas leave here.
                 const uint32_t h0 = RPAIR(w1[6], w2[6], 0, 1), h4 = RPAIR(w1[3], w2[3], 3, 1);
                 const uint32_t h8 = RPAIR(w1[0], w2[0], 0, 1), h12 = RPAIR(w0[3], w1[3], 1, 1);
+                const uint32_t nvp_lo = __vadd2(~vlo, c1), vm1_lo = __vadd2(vlo, c1);      // -(v + th), v - th + 1
+                const uint32_t nvp_hi = __vadd2(~vhi, c1), vm1_hi = __vadd2(vhi, c1);
                 bool any;
                 {
                     const uint32_t bl = __vimax3_u16x2(ring[0], ring[4], __vmaxu2(ring[8], ring[12]));
                     const uint32_t dl = __vimin3_u16x2(ring[0], ring[4], __vminu2(ring[8], ring[12]));
                     const uint32_t bh = __vimax3_u16x2(h0, h4, __vmaxu2(h8, h12));
                     const uint32_t dh = __vimin3_u16x2(h0, h4, __vminu2(h8, h12));
-                    any = (score2(vlo, __byte_perm(bl, 0, 0x4240), __byte_perm(dl, 0, 0x4240), neg_th2, th_m1) |
-                           score2(vhi, __byte_perm(bh, 0, 0x4240), __byte_perm(dh, 0, 0x4240), neg_th2, th_m1)) != 0;
+                    any = (excess2(__byte_perm(bl, 0, 0x4240), __byte_perm(dl, 0, 0x4240), nvp_lo, vm1_lo) |
+                           excess2(__byte_perm(bh, 0, 0x4240), __byte_perm(dh, 0, 0x4240), nvp_hi, vm1_hi)) != 0;
                 }
                 if (any) {
                     arc_minmax(ring, Mn, Mx);
-                    const uint32_t slo = score2(vlo, __byte_perm(Mn, 0, 0x4240), __byte_perm(Mx, 0, 0x4240), neg_th2, th_m1);
+                    const uint32_t slo = excess2(__byte_perm(Mn, 0, 0x4240), __byte_perm(Mx, 0, 0x4240), nvp_lo, vm1_lo);
                     RING_ALL(1, ring)
                     arc_minmax(ring, Mn, Mx);
-                    const uint32_t shi = score2(vhi, __byte_perm(Mn, 0, 0x4240), __byte_perm(Mx, 0, 0x4240), neg_th2, th_m1);
+                    const uint32_t shi = excess2(__byte_perm(Mn, 0, 0x4240), __byte_perm(Mx, 0, 0x4240), nvp_hi, vm1_hi);
                     outw = __byte_perm(slo, shi, 0x6420) & cm;              // low byte of each of the four lanes
                 }
 #undef RING_ALL
@@ -506,10 +508,11 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
                                                         __vmaxu2(hi16x2(nb[6]), hi16x2(nb[7])));
                     const uint32_t s0 = c & 0xff, s1 = (c >> 8) & 0xff, s2 = (c >> 16) & 0xff, s3 = c >> 24;
                     // strictly greater than all 8 neighbours; s == 0 never passes
-                    if (s0 > (mlo & 0xffff)) { v |= s0; bits |= 1u << (4 * j); }
-                    if (s1 > (mlo >> 16)) { v |= s1 << 8; bits |= 2u << (4 * j); }
-                    if (s2 > (mhi & 0xffff)) { v |= s2 << 16; bits |= 4u << (4 * j); }
-                    if (s3 > (mhi >> 16)) { v |= s3 << 24; bits |= 8u << (4 * j); }
+                    // survivors: excess -> OpenCV's response (T - 1 = excess + th - 1, at most 254)
+                    if (s0 > (mlo & 0xffff)) { v |= s0 + th_m1; bits |= 1u << (4 * j); }
+                    if (s1 > (mlo >> 16)) { v |= (s1 + th_m1) << 8; bits |= 2u << (4 * j); }
+                    if (s2 > (mhi & 0xffff)) { v |= (s2 + th_m1) << 16; bits |= 4u << (4 * j); }
+                    if (s3 > (mhi >> 16)) { v |= (s3 + th_m1) << 24; bits |= 8u << (4 * j); }
                 }
                 vv[j] = v;
             }
