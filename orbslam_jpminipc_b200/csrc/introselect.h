@@ -111,15 +111,18 @@ ORB_HD void insertion_sort_(T* v, int first, int last, C lt)
     }
 }
 
-// nth_element(v, v+nth, v+n) under the strict weak order lt
-template <typename T, typename C>
-ORB_HD void nth_element(T* v, int n, int nth, C lt)
+// floor(log2 n) * 2: the depth budget of std::__introselect
+ORB_HD int depth_limit(int n)
 {
-    if (n <= 0 || nth >= n) return;
-    int first = 0, last = n;
     int depth = 0;
-    for (int t = n; t > 1; t >>= 1) depth++;   // floor(log2 n)
-    depth *= 2;
+    for (int t = n; t > 1; t >>= 1) depth++;
+    return depth * 2;
+}
+
+// the loop of std::__introselect from a given state (range [first, last), remaining depth budget)
+template <typename T, typename C>
+ORB_HD void nth_element_from(T* v, int first, int last, int nth, int depth, C lt)
+{
     while (last - first > 3) {
         if (depth == 0) {
 #ifdef ORBSEL_TRACE_HEAP
@@ -152,6 +155,64 @@ ORB_HD void nth_element(T* v, int n, int nth, C lt)
             ++lo;
         }
         if (lo <= nth) first = lo; else last = lo;
+    }
+    insertion_sort_(v, first, last, lt);
+}
+
+// nth_element(v, v+nth, v+n) under the strict weak order lt
+template <typename T, typename C>
+ORB_HD void nth_element(T* v, int n, int nth, C lt)
+{
+    if (n <= 0 || nth >= n) return;
+    nth_element_from(v, 0, n, nth, depth_limit(n), lt);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Data-parallel form of the unguarded partition, with the same result as the sequential scan.  Call A the elements of
+// [first+1, last) that stop the left scan (!lt(v[i], pivot)) and B those that stop the right scan (!lt(pivot, v[i])); a_k is the
+// k-th A from the left, b_k the k-th B from the right, both in the ORIGINAL array.  The sequential loop swaps exactly the pairs
+// (a_k, b_k), k = 1..m, where m is the largest k with a_k < b_k (until they cross, the left scan only meets untouched elements and
+// elements it has put there itself, likewise the right scan), and returns min(a_{m+1}, b_m) (a_1 if m = 0): after the last swap
+// the left scan runs into the next original stopper or into the element it just moved to b_m, whichever comes first.
+// The model below executes that description with plain loops; k_select's warp version (orb_extract.cu, warp_partition) executes
+// it with ballots.  tests/cpp/test_introselect.cpp checks the model against std::nth_element.
+template <typename T, typename C>
+inline int partition_model(T* v, int first, int last, C lt, int* scratch /* >= last - first entries */)
+{
+    const T pivot = v[first];
+    int nB = 0;
+    for (int i = last - 1; i > first; --i) if (!lt(pivot, v[i])) scratch[nB++] = i;          // b_1, b_2, ... (from the right)
+    int k = 0, cut = -1, m = 0;
+    for (int i = first + 1; i < last; ++i) {
+        if (lt(v[i], pivot)) continue;                                                       // not a left stopper
+        const int partner = k < nB ? scratch[k] : -1;
+        if (partner > i) { swp(v, i, partner); m = ++k; }                                    // a_k < b_k: swap, as the scan would
+        else { cut = i; break; }                                                             // a_{m+1} (or a moved element at b_j >= b_m)
+    }
+    const int bm = m > 0 ? scratch[m - 1] : last;                                            // last: larger than any index (m = 0 -> a_1)
+    if (cut < 0 || bm < cut) cut = bm;
+    return cut;
+}
+
+template <typename T, typename C>
+inline void nth_element_model(T* v, int n, int nth, C lt, int* scratch, int serial_below = 8)
+{
+    if (n <= 0 || nth >= n) return;
+    int first = 0, last = n, depth = depth_limit(n);
+    while (last - first > 3) {
+        if (depth == 0 || last - first < serial_below) { nth_element_from(v, first, last, nth, depth, lt); return; }
+        --depth;
+        const int mid = first + (last - first) / 2;
+        const int a = first + 1, b = mid, c = last - 1;
+        if (lt(v[a], v[b])) {
+            if (lt(v[b], v[c])) swp(v, first, b);
+            else if (lt(v[a], v[c])) swp(v, first, c);
+            else swp(v, first, a);
+        } else if (lt(v[a], v[c])) swp(v, first, a);
+        else if (lt(v[b], v[c])) swp(v, first, c);
+        else swp(v, first, b);
+        const int cut = partition_model(v, first, last, lt, scratch);
+        if (cut <= nth) first = cut; else last = cut;
     }
     insertion_sort_(v, first, last, lt);
 }

@@ -111,7 +111,7 @@ static int prepare(orb_ctx* c, int w, int h)
         int maxcap = 0;
         for (int l = 0; l < c->plan.nlevels; l++) maxcap = std::max(maxcap, c->plan.L[l].lvl_cap);
         if ((size_t)maxcap * 8 > 170 * 1024) return ORB_ERR_CAPACITY;
-        rc = orb_select_smem_setup(maxcap * 8 + 6144 * 4 + 1024); if (rc) return rc;
+        rc = orb_select_smem_setup(maxcap); if (rc) return rc;
         size_t rsm = 1024;
         for (int l = 1; l < c->plan.nlevels; l++) rsm = std::max(rsm, (size_t)2 * (((size_t)c->rs_box_w[l] * c->rs_box_h[l] + 127) & ~(size_t)127) + 16);
         rc = orb_resize_smem_setup((int)rsm); if (rc) return rc;
@@ -228,6 +228,8 @@ orb_ctx* orb_create(int device, int nfeatures, float scale_factor, int nlevels, 
     c->score_type = score_type; c->fast_th = fast_th; c->max_w = max_w; c->max_h = max_h; c->max_batch = max_batch;
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (const char* e = getenv("ORB_GRAPH")) c->use_graph = atoi(e);
+    if (const char* e = getenv("ORB_DEBUG_SKIP")) c->debug_skip = atoi(e);
+    if (const char* e = getenv("ORB_SELECT_SERIAL")) c->select_serial = atoi(e);
     if (const char* e = getenv("ORB_FORK_EARLY")) c->fork_early = atoi(e);
     if (const char* e = getenv("ORB_FAST_CTAS_FORK")) c->fast_ctas = atoi(e);
     if (const char* e = getenv("ORB_BLUR_CTAS")) c->blur_ctas = atoi(e);

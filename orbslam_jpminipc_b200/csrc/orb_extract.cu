@@ -14,6 +14,7 @@
 // rotation) spell out every rounding with __f*_rn / fmaf so the compiler cannot contract them.
 #include "orb_internal.h"
 #include <mutex>
+#include <climits>
 #include "introselect.h"
 
 namespace {
@@ -664,6 +665,160 @@ k_harris(const uint8_t* __restrict__ planes, size_t fbytes, const Plan* __restri
     }
 }
 
+// ---- warp-cooperative, exact replay of std::nth_element (introselect.h explains why the partition may be evaluated in parallel) ----
+constexpr int SEL_WCAP = 1024;      // candidates one warp stages in shared memory (larger cell lists are selected serially in place)
+#ifndef ORB_SEL_WARPS
+#define ORB_SEL_WARPS 8
+#define ORB_SEL_SERIAL_BELOW 8
+#endif
+constexpr int SEL_WARPS = ORB_SEL_WARPS, SEL_SERIAL_BELOW = ORB_SEL_SERIAL_BELOW;   // below that range length lane 0 finishes alone
+
+template <typename T, typename C>
+__device__ __forceinline__ int warp_partition(T* v, int first, int last, C lt, unsigned short* scratch, int lane)
+{
+    const T pivot = v[first];
+    const unsigned below = (1u << lane) - 1u;
+    int nB = 0;                                                     // b_1, b_2, ...: right-scan stoppers, from the right
+    for (int base = last - 1; base > first; base -= 128) {          // four chunks per trip: the loads are independent
+        bool isB[4];
+        unsigned bal[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int i = base - 32 * u - lane; isB[u] = i > first && !lt(pivot, v[i]); }
+#pragma unroll
+        for (int u = 0; u < 4; u++) bal[u] = __ballot_sync(0xffffffffu, isB[u]);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (isB[u]) scratch[nB + __popc(bal[u] & below)] = (unsigned short)(base - 32 * u - lane);
+            nB += __popc(bal[u]);
+        }
+    }
+    __syncwarp();
+    int m = 0, cut = INT_MAX;
+    for (int base = first + 1; base < last; base += 32) {
+        const int i = base + lane;
+        const bool isA = i < last && !lt(v[i], pivot);                // left-scan stopper
+        const unsigned bal = __ballot_sync(0xffffffffu, isA);
+        const int rank = m + __popc(bal & below);
+        const int partner = (isA && rank < nB) ? (int)scratch[rank] : -1;
+        const bool ok = isA && partner > i;                          // a_k < b_k: the scan would swap this pair
+        const unsigned okm = __ballot_sync(0xffffffffu, ok), fail = bal & ~okm;
+        if (ok) { const T t = v[i]; v[i] = v[partner]; v[partner] = t; }
+        m += __popc(okm);
+        if (fail) { cut = base + __ffs(fail) - 1; break; }
+    }
+    __syncwarp();
+    const int bm = m > 0 ? (int)scratch[m - 1] : INT_MAX;
+    cut = min(cut, bm);
+    return cut == INT_MAX ? last : cut;
+}
+
+template <typename T, typename C>
+__device__ __forceinline__ void warp_nth_element(T* v, int n, int nth, C lt, unsigned short* scratch, int lane)
+{
+    if (n <= 0 || nth >= n) return;
+    int first = 0, last = n, depth = orbsel::depth_limit(n);
+    while (last - first >= SEL_SERIAL_BELOW && depth > 0) {
+        --depth;
+        const int a = first + 1, b = first + (last - first) / 2, c = last - 1;      // median of three -> first
+        const T va = v[a], vb = v[b], vc = v[c];
+        int pick;
+        if (lt(va, vb)) pick = lt(vb, vc) ? b : (lt(va, vc) ? c : a);
+        else pick = lt(va, vc) ? a : (lt(vb, vc) ? c : b);
+        __syncwarp();
+        if (lane == 0) orbsel::swp(v, first, pick);
+        __syncwarp();
+        const int cut = warp_partition(v, first, last, lt, scratch, lane);
+        if (cut <= nth) first = cut; else last = cut;
+    }
+    if (lane == 0) orbsel::nth_element_from(v, first, last, nth, depth, lt);       // short ranges, the heap-select fallback, the final insertion sort
+    __syncwarp();
+}
+
+// FAST_SCORE selection: CTA per (frame, level), warp per cell.
+__global__ void __launch_bounds__(SEL_WARPS * 32)
+k_select_fast(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells, uint32_t* __restrict__ cand, const int* __restrict__ ntotal,
+              unsigned long long* __restrict__ lvl, int* __restrict__ nkept, int* __restrict__ status)
+{
+    extern __shared__ unsigned long long s_list[];            // sel_list_cap u64 | SEL_WARPS x SEL_WCAP u32 | SEL_WARPS x SEL_WCAP u16
+    __shared__ int s_total[ORB_MAX_CELLS_LEVEL], s_retain[ORB_MAX_CELLS_LEVEL], s_off[ORB_MAX_CELLS_LEVEL + 1];
+    const int level = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const LevelGeom& L = plan->L[level];
+    const int nCells = L.ncells;
+    const CellGeom* cg = cells + L.cell_base;
+    const int* nt = ntotal + (size_t)f * plan->ncells + L.cell_base;
+    uint32_t* s_wbuf = reinterpret_cast<uint32_t*>(s_list + plan->sel_list_cap);
+    unsigned short* s_scr = reinterpret_cast<unsigned short*>(s_wbuf + SEL_WARPS * SEL_WCAP);
+    for (int c = tid; c < nCells; c += blockDim.x) s_total[c] = nt[c];
+    __syncthreads();
+    if (tid == 0) {                                            // quota redistribution, src/ORBextractor.cc:622-670
+        const int nfc = L.nfCell;
+        int nNoMore = 0, nToDistribute = 0;
+        unsigned char noMore[ORB_MAX_CELLS_LEVEL];
+        for (int c = 0; c < nCells; c++) {
+            noMore[c] = 0; s_retain[c] = 0;
+            if (cg[c].skipped) continue;                       // stays open with nTotal = 0
+            const int nKeys = s_total[c];
+            if (nKeys > nfc) { s_retain[c] = nfc; }
+            else { s_retain[c] = nKeys; nToDistribute += nfc - nKeys; noMore[c] = 1; nNoMore++; }
+        }
+        while (nToDistribute > 0 && nNoMore < nCells) {
+            const int nNew = nfc + (int)ceilf(__fdiv_rn((float)nToDistribute, (float)(nCells - nNoMore)));
+            nToDistribute = 0;
+            for (int c = 0; c < nCells; c++) {
+                if (noMore[c]) continue;
+                if (s_total[c] > nNew) s_retain[c] = nNew;
+                else { s_retain[c] = s_total[c]; nToDistribute += nNew - s_total[c]; noMore[c] = 1; nNoMore++; }
+            }
+        }
+        int o = 0;
+        for (int c = 0; c < nCells; c++) { s_off[c] = o; o += s_retain[c]; }
+        s_off[nCells] = o;
+        if (o > L.lvl_cap) { atomicExch(status, ORB_ERR_CAPACITY); s_off[nCells] = -1; }
+    }
+    __syncthreads();
+    int total = s_off[nCells];
+    if (total < 0) { if (tid == 0) nkept[f * plan->nlevels + level] = 0; return; }
+    uint32_t* gbase = cand + (size_t)f * plan->cand_total;
+    const orbsel::KeyGreater<uint32_t, 24> lt32;
+    for (int c = warp; c < nCells; c += SEL_WARPS) {           // retainBest per cell (:683-685)
+        const int n = s_total[c], keep = s_retain[c];
+        if (keep <= 0) continue;
+        uint32_t* v = gbase + cg[c].cand_off;
+        if (n > keep) {
+            if (n <= SEL_WCAP) {
+                uint32_t* w = s_wbuf + warp * SEL_WCAP;
+                for (int k = lane; k < n; k += 32) w[k] = v[k];
+                __syncwarp();
+                warp_nth_element(w, n, keep - 1, lt32, s_scr + warp * SEL_WCAP, lane);
+                v = w;
+            } else {                                           // a list longer than the staging buffer: in place, one thread
+                if (lane == 0) orbsel::nth_element(v, n, keep - 1, lt32);
+                __syncwarp();
+            }
+        }
+        const int ix = cg[c].inix, iy = cg[c].iniy;
+        for (int k = lane; k < keep; k += 32) {
+            const uint32_t r = v[k];
+            const unsigned long long x = (r & 0xfff) + ix, y = ((r >> 12) & 0xfff) + iy;
+            s_list[s_off[c] + k] = ((unsigned long long)(r >> 24) << 32) | (y << 16) | x;
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (total > L.nDesired) {                                  // retainBest per level (:697-701)
+        const orbsel::KeyGreater<unsigned long long, 32> lt64;
+        if (warp == 0) {
+            if (total <= SEL_WARPS * SEL_WCAP) warp_nth_element(s_list, total, L.nDesired - 1, lt64, s_scr, lane);
+            else if (lane == 0) orbsel::nth_element(s_list, total, L.nDesired - 1, lt64);
+        }
+        total = L.nDesired;
+        __syncthreads();
+    }
+    unsigned long long* dst = lvl + (size_t)f * plan->lvl_total + L.lvl_base;
+    for (int k = tid; k < total; k += blockDim.x) dst[k] = s_list[k];
+    if (tid == 0) nkept[f * plan->nlevels + level] = total;
+}
+
 template <bool HARRIS>
 __global__ void __launch_bounds__(128)
 k_select(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells, uint32_t* __restrict__ cand,
@@ -1076,6 +1231,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
     // leaves most of the machine idle); k_describe joins both.
     const bool fork = !c->profile;
     auto launch_blur = [&](cudaStream_t bs) {
+        if (c->debug_skip & 1) return;
         const int total = P.ntiles_blur * nimg;
         const int grid = std::min(total, c->num_sms * c->blur_ctas);
         k_blur<<<grid, BLUR_THREADS, 0, bs>>>(W.tm_blur, W.d_blur, fb, c->d_plan, c->d_tiles_blur, P.ntiles_blur, total, W.d_counters + 2);
@@ -1107,8 +1263,12 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         k_harris<<<dim3((P.ncells + 7) / 8, nimg), 256, 0, s>>>(W.d_planes, fb, c->d_plan, c->d_cells, W.d_cand, W.d_ntotal, W.d_cand64);
         k_select<true><<<dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s>>>(c->d_plan, c->d_cells, W.d_cand, W.d_cand64, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status);
         launches++;
-    } else
-        k_select<false><<<dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s>>>(c->d_plan, c->d_cells, W.d_cand, nullptr, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status);
+    } else if (!(c->debug_skip & 2)) {
+        if (c->select_serial)
+            k_select<false><<<dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s>>>(c->d_plan, c->d_cells, W.d_cand, nullptr, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status);
+        else
+            k_select_fast<<<dim3(P.nlevels, nimg), SEL_WARPS * 32, (size_t)P.sel_list_cap * 8 + (size_t)SEL_WARPS * SEL_WCAP * 6, s>>>(c->d_plan, c->d_cells, W.d_cand, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status);
+    }
     if (fork && c->fork_early == 3) {      // selection first: the latency-bound kernel takes the residency it needs, blur fills the rest
         launch_blur(W.aux_stream);
         ORB_CUDA(cudaEventRecord(W.ev_join, W.aux_stream));
@@ -1118,7 +1278,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
     else launch_blur(s);
     mark();
     const int slots = std::min(cap, P.kp_cap);
-    k_describe<<<dim3((std::max(slots, 1) + 7) / 8, nimg), 256, 0, s>>>(W.d_planes, W.d_blur, fb, c->d_plan, W.d_lvl, W.d_nkept,
+    if (!(c->debug_skip & 4)) k_describe<<<dim3((std::max(slots, 1) + 7) / 8, nimg), 256, 0, s>>>(W.d_planes, W.d_blur, fb, c->d_plan, W.d_lvl, W.d_nkept,
                                                                     d_kps, d_desc, cap, d_counts);
     mark();
     launches += 5;
@@ -1132,7 +1292,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
 static int raise_dyn_smem(const void* fn, int slot, int bytes)
 {
     static std::mutex mu;
-    static int cur[3][64] = {};
+    static int cur[4][64] = {};
     int dev = 0;
     ORB_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(mu);
@@ -1144,8 +1304,10 @@ static int raise_dyn_smem(const void* fn, int slot, int bytes)
 
 int orb_resize_smem_setup(int max_bytes) { return raise_dyn_smem((const void*)k_resize, 0, max_bytes); }
 
-int orb_select_smem_setup(int max_bytes)
+int orb_select_smem_setup(int list_cap)     // list_cap: the largest per-level keypoint list (u64 records) of the plan
 {
-    const int rc = raise_dyn_smem((const void*)k_select<false>, 1, max_bytes);
-    return rc ? rc : raise_dyn_smem((const void*)k_select<true>, 2, max_bytes);
+    const int serial = list_cap * 8 + SEL_STAGE * 4 + 1024, fast = list_cap * 8 + SEL_WARPS * SEL_WCAP * 6 + 1024;
+    int rc = raise_dyn_smem((const void*)k_select<false>, 1, serial);
+    if (!rc) rc = raise_dyn_smem((const void*)k_select<true>, 2, serial);
+    return rc ? rc : raise_dyn_smem((const void*)k_select_fast, 3, fast);
 }

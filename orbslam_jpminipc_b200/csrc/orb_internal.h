@@ -160,6 +160,8 @@ struct orb_ctx {
     int num_sms = 148;
     int split_device = 0;
     int desc_fma = 0;                                      // orb_set_descriptor_fma
+    int debug_skip = 0;                                    // ORB_DEBUG_SKIP (timing experiments only, results are wrong): 1 no blur, 2 no selection, 4 no describe
+    int select_serial = 0;                                 // ORB_SELECT_SERIAL=1: the thread-per-cell selection kernel (A/B timing)
     int use_graph = 1;                                     // ORB_GRAPH=0 switches the CUDA-graph replay off
     long long plan_gen = 0;                                // bumped whenever the plan (image shape) is rebuilt
     int fork_early = 0, fast_ctas = 6, blur_ctas = 8;      // stream-overlap tuning (ORB_FORK_EARLY / ORB_FAST_CTAS_FORK / ORB_BLUR_CTAS env)

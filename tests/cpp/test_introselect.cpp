@@ -27,6 +27,14 @@ static int run_case(const std::vector<int>& keys, int nth, const char* what)
     bool small = true;                       // the 32-bit record has an 8-bit key
     for (int v : keys) small = small && v >= 0 && v <= 255;
     orbsel::nth_element(mine32.data(), n, nth, orbsel::KeyGreater<uint32_t, 24>());
+    // the data-parallel description of the partition (what k_select's warps execute) must give the same permutation
+    for (int serial_below : {4, 48}) {
+        std::vector<uint64_t> par(n);
+        std::vector<int> scratch(n + 1);
+        for (int i = 0; i < n; i++) par[i] = ((uint64_t)keys[i] << 32) | (uint32_t)i;
+        orbsel::nth_element_model(par.data(), n, nth, orbsel::KeyGreater<uint64_t, 32>(), scratch.data(), serial_below);
+        if (par != mine64) { std::printf("MODEL MISMATCH %s n=%d nth=%d serial_below=%d\n", what, n, nth, serial_below); return 1; }
+    }
     for (int i = 0; i < n; i++)
         if ((int)(mine64[i] & 0xffffffffu) != ref[i].id || (small && (int)(mine32[i] & 0xffffff) != ref[i].id)) {
             std::printf("MISMATCH %s n=%d nth=%d at %d\n", what, n, nth, i);
