@@ -49,6 +49,8 @@ def lib():
         L.ref_detect_relocalisation_candidates.argtypes = [vp, vp, vp, i, vp, vp, vp]
         L.ref_frame_update_points.argtypes = [vp]
         L.ref_search_by_projection_kf.argtypes = [vp, vp, vp, f, i, f, i, vp, vp]
+        L.ref_search_by_projection_sim3.argtypes = [vp, vp, vp, i, vp, vp, vp, vp, vp]
+        L.ref_fuse.argtypes = [vp, vp, f, vp, vp, vp, vp, vp]
         L.ref_descriptor_distance.argtypes = [vp, vp]
         L.ref_search_by_projection_ff.argtypes = [vp, vp, f, f, i, vp]
         L.ref_search_by_projection_mappoints.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, f, f, vp]
@@ -219,6 +221,23 @@ def search_by_projection_kf(cur, kf, already_found, th, orb_dist, nnratio=0.9, c
     pred = np.full(kf.n, -1, np.int32)
     n = _ok(lib().ref_search_by_projection_kf(cur._h, kf._h, _p(af), th, orb_dist, nnratio, int(check_ori), _p(m), _p(pred)), "SearchByProjection(F,KF)")
     return n, m, pred
+
+
+def search_by_projection_sim3(kf, src, Scw, th, matched=None):
+    """-> (nmatches, matched, (active, u, v, level)) : the reference's result and the projections it worked from"""
+    S = np.ascontiguousarray(Scw, np.float32).reshape(16)
+    m = np.full(kf.n, -1, np.int32) if matched is None else np.ascontiguousarray(matched, np.int32)
+    a, u, v, lv = np.zeros(src.n, np.uint8), np.zeros(src.n, np.float32), np.zeros(src.n, np.float32), np.zeros(src.n, np.int32)
+    n = _ok(lib().ref_search_by_projection_sim3(kf._h, src._h, _p(S), int(th), _p(m), _p(a), _p(u), _p(v), _p(lv)), "SearchByProjection(KF,Scw)")
+    return n, m, (a, u, v, lv)
+
+
+def fuse(kf, src, th=2.5):
+    """ORBmatcher::Fuse(pKF, points of src, th) -> (nFused, fused keypoint per source point, (active, u, v, level))"""
+    fz = np.full(src.n, -1, np.int32)
+    a, u, v, lv = np.zeros(src.n, np.uint8), np.zeros(src.n, np.float32), np.zeros(src.n, np.float32), np.zeros(src.n, np.int32)
+    n = _ok(lib().ref_fuse(kf._h, src._h, th, _p(fz), _p(a), _p(u), _p(v), _p(lv)), "Fuse")
+    return n, fz, (a, u, v, lv)
 
 
 def search_by_bow(kf, f, nnratio, check_ori=True):

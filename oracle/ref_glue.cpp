@@ -595,4 +595,123 @@ int ref_search_by_projection_kf(void* cur_, void* kf_, const uint8_t* already_fo
 }
 
 } // extern "C"
+namespace {
+/* What the back-end searches compute for every candidate point before their radius search, restated from
+ * ORBmatcher::SearchByProjection(KeyFrame*, Scw, ...) :316-362 and ORBmatcher::Fuse :1036-1070 with the same member calls: the C ABI
+ * of the CUDA path takes (active, u, v, predicted level) from its caller, so the tests hand these to the oracle and compare what
+ * follows (window, level filter, best descriptor, threshold) with what the reference's own function did. */
+void project_candidates(KeyFrame* kf, const cv::Mat& Rcw, const cv::Mat& tcw, const cv::Mat& Ow, const std::vector<MapPoint*>& pts,
+                        const std::set<MapPoint*>& skip, bool skip_in_kf, uint8_t* active, float* pu, float* pv, int32_t* level)
+{
+    const float fx = kf->fx, fy = kf->fy, cx = kf->cx, cy = kf->cy;
+    const int nMaxLevel = kf->GetScaleLevels() - 1;
+    std::vector<float> vfScaleFactors = kf->GetScaleFactors();
+    for (size_t i = 0; i < pts.size(); i++) {
+        active[i] = 0; pu[i] = pv[i] = 0.f; level[i] = 0;
+        MapPoint* pMP = pts[i];
+        if (!pMP) continue;
+        if (pMP->isBad() || skip.count(pMP) || (skip_in_kf && pMP->IsInKeyFrame(kf))) continue;
+        cv::Mat p3Dw = pMP->GetWorldPos();
+        cv::Mat p3Dc = Rcw * p3Dw + tcw;
+        if (p3Dc.at<float>(2) < 0.0f) continue;
+        const float invz = 1 / p3Dc.at<float>(2);
+        const float x = p3Dc.at<float>(0) * invz;
+        const float y = p3Dc.at<float>(1) * invz;
+        const float u = fx * x + cx;
+        const float v = fy * y + cy;
+        if (!kf->IsInImage(u, v)) continue;
+        const float maxDistance = pMP->GetMaxDistanceInvariance();
+        const float minDistance = pMP->GetMinDistanceInvariance();
+        cv::Mat PO = p3Dw - Ow;
+        const float dist = cv::norm(PO);
+        if (dist < minDistance || dist > maxDistance) continue;
+        cv::Mat Pn = pMP->GetNormal();
+        if (PO.dot(Pn) < 0.5 * dist) continue;
+        const float ratio = dist / minDistance;
+        std::vector<float>::iterator it = std::lower_bound(vfScaleFactors.begin(), vfScaleFactors.end(), ratio);
+        active[i] = 1; pu[i] = u; pv[i] = v;
+        level[i] = std::min(static_cast<int>(it - vfScaleFactors.begin()), nMaxLevel);
+    }
+}
+}
+
+extern "C" {
+
+/* ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, vpPoints, vpMatched, th), :286-407.  The candidates are the map points
+ * of `src` (its feature i <-> point i).  matched[idx] in: >= 0 -> vpMatched[idx] already holds some other point; out: source index of
+ * the point assigned, the input where it was occupied, else -1.  active/u/v/level: see project_candidates. */
+int ref_search_by_projection_sim3(void* kf_, void* src_, const float* Scw16, int th, int32_t* matched, uint8_t* active, float* u, float* v,
+                                  int32_t* level)
+{
+    RefFrame *k = (RefFrame*)kf_, *src = (RefFrame*)src_;
+    return guarded("SearchByProjection(KF,Scw)", [&] {
+        k->statics();
+        KeyFrame* kf = k->keyframe();
+        cv::Mat Scw(4, 4, CV_32F);
+        std::memcpy(Scw.data, Scw16, 64);
+        std::vector<MapPoint*> pts = src->f.mvpMapPoints;
+        std::map<MapPoint*, int> idx;
+        index_of(pts, idx);
+        std::vector<MapPoint*> cand;                       /* vpPoints holds no NULLs in the reference (:313 dereferences) */
+        std::vector<int> cand_src;
+        for (size_t i = 0; i < pts.size(); i++) if (pts[i]) { cand.push_back(pts[i]); cand_src.push_back((int)i); }
+        std::vector<MapPoint*> vpMatched(k->f.N, nullptr), other(k->f.N, nullptr);
+        for (int i = 0; i < k->f.N; i++) if (matched[i] >= 0) vpMatched[i] = other[i] = k->new_point(nullptr, k->f.mDescriptors.ptr(i));
+        {
+            cv::Mat sRcw = Scw.rowRange(0, 3).colRange(0, 3);
+            const float scw = sqrt(sRcw.row(0).dot(sRcw.row(0)));
+            cv::Mat Rcw = sRcw / scw;
+            cv::Mat tcw = Scw.rowRange(0, 3).col(3) / scw;
+            cv::Mat Ow = -Rcw.t() * tcw;
+            std::set<MapPoint*> found(vpMatched.begin(), vpMatched.end());
+            found.erase(nullptr);
+            std::vector<uint8_t> a(cand.size()); std::vector<float> uu(cand.size()), vv(cand.size()); std::vector<int32_t> ll(cand.size());
+            project_candidates(kf, Rcw, tcw, Ow, cand, found, false, a.data(), uu.data(), vv.data(), ll.data());
+            for (size_t i = 0; i < pts.size(); i++) { active[i] = 0; u[i] = v[i] = 0.f; level[i] = 0; }
+            for (size_t c = 0; c < cand.size(); c++) { const int i = cand_src[c]; active[i] = a[c]; u[i] = uu[c]; v[i] = vv[c]; level[i] = ll[c]; }
+        }
+        ORBmatcher m(0.6f, true);
+        const int n = m.SearchByProjection(kf, Scw, cand, vpMatched, th);
+        for (int i = 0; i < k->f.N; i++) {
+            if (!vpMatched[i]) matched[i] = -1;
+            else if (vpMatched[i] != other[i]) matched[i] = idx.at(vpMatched[i]);
+        }
+        return n;
+    });
+}
+
+/* ORBmatcher::Fuse(KeyFrame* pKF, vector<MapPoint*>&, th), :1016-1134, called with one candidate at a time (the choice of keypoint
+ * does not depend on the bookkeeping of earlier candidates: Fuse keeps no claims), so that the keypoint each point fused with can be
+ * read back: fused[i] = keypoint of pKF that source point i was merged into (Replace) or attached to (AddObservation), else -1. */
+int ref_fuse(void* kf_, void* src_, float th, int32_t* fused, uint8_t* active, float* u, float* v, int32_t* level)
+{
+    RefFrame *k = (RefFrame*)kf_, *src = (RefFrame*)src_;
+    return guarded("Fuse", [&] {
+        k->statics();
+        KeyFrame* kf = k->keyframe();
+        KeyFrame* skf = src->keyframe();
+        std::vector<MapPoint*> pts = src->f.mvpMapPoints;
+        project_candidates(kf, kf->GetRotation(), kf->GetTranslation(), kf->GetCameraCenter(), pts, std::set<MapPoint*>(), true,
+                           active, u, v, level);
+        ORBmatcher m(0.6f, true);
+        int total = 0;
+        for (size_t i = 0; i < pts.size(); i++) {
+            fused[i] = -1;
+            if (!pts[i]) continue;
+            std::vector<MapPoint*> one(1, pts[i]);
+            const int n = m.Fuse(kf, one, th);
+            if (n != 1) continue;
+            total++;
+            if (!pts[i]->isBad()) fused[i] = pts[i]->GetIndexInKeyFrame(kf);          /* AddObservation(pKF, bestIdx) */
+            else {                                                                    /* Replace(pMPinKF): it took over the observation (skf, i) */
+                std::vector<MapPoint*> in_kf = kf->GetMapPointMatches();
+                for (size_t j = 0; j < in_kf.size(); j++)
+                    if (in_kf[j] && in_kf[j] != pts[i] && in_kf[j]->IsInKeyFrame(skf) && in_kf[j]->GetIndexInKeyFrame(skf) == (int)i) { fused[i] = (int)j; break; }
+            }
+        }
+        return total;
+    });
+}
+
+} // extern "C"
 #endif /* REF_GLUE_EXTRACTOR_ONLY */

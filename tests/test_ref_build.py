@@ -445,3 +445,59 @@ def test_extractor_fma_contracted_build(po):
             nrows += int((pd != fd).any(1).sum()); nbits += int(np.unpackbits(pd ^ fd).sum()); total += len(pk)
     assert total > 30000
     assert 0 < nbits <= 20 and nrows <= nbits, (nrows, nbits, total)
+
+
+def _backend_scene(po, shape, nf, seed, scale=1.0):
+    """A source keyframe at the world origin whose features carry map points, and a target keyframe that sees them from a slightly
+    different pose (optionally through a similarity of scale `scale`)."""
+    (ka, da), (kb, db), cam, has, outl, xyz, T = _scene(po, shape[0], shape[1], nf, seed)
+    src = pyref.RefFrame(ka, da, *cam).set_mappoints(has, xyz).update_points()
+    S = T.copy()
+    S[:3, :] *= np.float32(scale)
+    return (ka, da), (kb, db), cam, has, src, T, S
+
+
+@pytest.mark.parametrize("shape,nf,th,scale", [((240, 320), 500, 10, 1.0), ((480, 752), 1000, 10, 1.3), ((376, 1241), 2000, 4, 0.8)])
+def test_search_by_projection_sim3(po, shape, nf, th, scale):
+    """src/ORBmatcher.cc:286-407 (loop closing).  The Sim3 decomposition, projection, depth / viewing-angle gates and level prediction are
+    the caller's at the C ABI: the reference's own values (restated in the glue with the same member calls) feed the oracle, and the radius
+    search, level filter, best-descriptor choice, TH_LOW test and vpMatched bookkeeping must agree with the reference's function."""
+    (ka, da), (kb, db), cam, has, src, T, S = _backend_scene(po, shape, nf, 8600 + nf, scale)
+    kf = pyref.RefFrame(kb, db, *cam).set_pose(T)
+    pre = np.full(len(kb), -1, np.int32)
+    pre[::7] = 555555
+    n, matched, (active, u, v, level) = pyref.search_by_projection_sim3(kf, src, S, th, pre.copy())
+    assert active.sum() > 50 and len(np.unique(level[active > 0])) > 2
+    rn, rmatched = po.search_by_projection_sim3(po.OracleFrame(kb, db, *cam), active, u, v, level, da, th, pre.copy())
+    assert n > 10
+    assert n == rn and np.array_equal(matched, rmatched)
+
+
+@pytest.mark.parametrize("shape,nf,th", [((240, 320), 500, 2.5), ((480, 752), 1000, 2.5), ((376, 1241), 2000, 7.5)])
+def test_fuse(po, shape, nf, th):
+    """src/ORBmatcher.cc:1016-1134 (local mapping), one candidate per call so that the keypoint every point was fused with can be read
+    back from the reference's Replace / AddObservation bookkeeping; half of the target's keypoints already carry a map point."""
+    (ka, da), (kb, db), cam, has, src, T, S = _backend_scene(po, shape, nf, 8700 + nf)
+    rng = np.random.default_rng(nf)
+    occupied = (rng.random(len(kb)) < 0.5).astype(np.uint8)
+    kf = pyref.RefFrame(kb, db, *cam).set_pose(T).set_mappoints(occupied).update_points()
+    n, fused, (active, u, v, level) = pyref.fuse(kf, src, th)
+    of = po.OracleFrame(kb, db, *cam)
+    sf = np.ones(8, np.float32)
+    for i in range(1, 8):
+        sf[i] = np.float32(sf[i - 1] * np.float32(1.2))
+    radius = (np.float32(th) * sf[level]).astype(np.float32)
+    bi, bd = po.window_best(of, active, u, v, radius, level, da)
+    want = np.where((active > 0) & (bi >= 0) & (bd <= 50), bi, -1)
+    assert n > 10 and n == int((want >= 0).sum())
+    # the keypoint can be read back from the reference's bookkeeping unless an earlier candidate already went to the same keypoint
+    # (MapPoint::Replace then only erases, src/MapPoint.cc:118-150); those few are covered by the count above
+    first = np.ones(len(want), bool)
+    seen = set()
+    for i, w in enumerate(want):
+        if w >= 0:
+            first[i] = w not in seen
+            seen.add(w)
+    assert first.sum() > 0.95 * len(want)
+    assert np.array_equal(fused[first], want[first])
+    assert occupied[fused[fused >= 0]].any() and not occupied[fused[fused >= 0]].all()       # both the Replace and the AddObservation branch ran
