@@ -51,6 +51,8 @@ def lib():
         L.ref_search_by_projection_kf.argtypes = [vp, vp, vp, f, i, f, i, vp, vp]
         L.ref_search_by_projection_sim3.argtypes = [vp, vp, vp, i, vp, vp, vp, vp, vp]
         L.ref_fuse.argtypes = [vp, vp, f, vp, vp, vp, vp, vp]
+        L.ref_search_by_sim3.argtypes = [vp, vp, f, vp, vp, f, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.ref_fuse_sim3.argtypes = [vp, vp, vp, f, vp, vp, vp, vp, vp]
         L.ref_descriptor_distance.argtypes = [vp, vp]
         L.ref_search_by_projection_ff.argtypes = [vp, vp, f, f, i, vp]
         L.ref_search_by_projection_mappoints.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, f, f, vp]
@@ -232,11 +234,30 @@ def search_by_projection_sim3(kf, src, Scw, th, matched=None):
     return n, m, (a, u, v, lv)
 
 
+def search_by_sim3(k1, k2, s12, R12, t12, th=7.5, matches12=None):
+    """ORBmatcher::SearchBySim3 -> (nFound, matches12, (act, u, v, level) of KF1's points in KF2, the same of KF2's points in KF1)"""
+    R = np.ascontiguousarray(R12, np.float32).reshape(9); t = np.ascontiguousarray(t12, np.float32).reshape(3)
+    m = np.full(k1.n, -1, np.int32) if matches12 is None else np.ascontiguousarray(matches12, np.int32)
+    p12 = (np.zeros(k1.n, np.uint8), np.zeros(k1.n, np.float32), np.zeros(k1.n, np.float32), np.zeros(k1.n, np.int32))
+    p21 = (np.zeros(k2.n, np.uint8), np.zeros(k2.n, np.float32), np.zeros(k2.n, np.float32), np.zeros(k2.n, np.int32))
+    n = _ok(lib().ref_search_by_sim3(k1._h, k2._h, s12, _p(R), _p(t), th, _p(m), *[_p(x) for x in p12], *[_p(x) for x in p21]), "SearchBySim3")
+    return n, m, p12, p21
+
+
 def fuse(kf, src, th=2.5):
     """ORBmatcher::Fuse(pKF, points of src, th) -> (nFused, fused keypoint per source point, (active, u, v, level))"""
     fz = np.full(src.n, -1, np.int32)
     a, u, v, lv = np.zeros(src.n, np.uint8), np.zeros(src.n, np.float32), np.zeros(src.n, np.float32), np.zeros(src.n, np.int32)
     n = _ok(lib().ref_fuse(kf._h, src._h, th, _p(fz), _p(a), _p(u), _p(v), _p(lv)), "Fuse")
+    return n, fz, (a, u, v, lv)
+
+
+def fuse_sim3(kf, src, Scw, th=2.5):
+    """ORBmatcher::Fuse(pKF, Scw, points of src, th) -> (nFused, fused keypoint per source point, (active, u, v, level))"""
+    S = np.ascontiguousarray(Scw, np.float32).reshape(16)
+    fz = np.full(src.n, -1, np.int32)
+    a, u, v, lv = np.zeros(src.n, np.uint8), np.zeros(src.n, np.float32), np.zeros(src.n, np.float32), np.zeros(src.n, np.int32)
+    n = _ok(lib().ref_fuse_sim3(kf._h, src._h, _p(S), th, _p(fz), _p(a), _p(u), _p(v), _p(lv)), "Fuse(Scw)")
     return n, fz, (a, u, v, lv)
 
 

@@ -714,4 +714,112 @@ int ref_fuse(void* kf_, void* src_, float th, int32_t* fused, uint8_t* active, f
 }
 
 } // extern "C"
+extern "C" {
+
+/* ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th), :1267-1505.  matches12[i1] in: >= 0 -> vpMatches12[i1] already
+ * holds pKF2's point of that feature; out: feature of pKF2 whose point was matched, else -1.  act/u/v/level 12: the points of pKF1
+ * projected into pKF2 (:1316-1353), 21: the other way round (:1398-1433), restated with the same expressions. */
+int ref_search_by_sim3(void* k1_, void* k2_, float s12, const float* R12_9, const float* t12_3, float th, int32_t* matches12,
+                       uint8_t* act12, float* u12, float* v12, int32_t* l12, uint8_t* act21, float* u21, float* v21, int32_t* l21)
+{
+    RefFrame *a = (RefFrame*)k1_, *b = (RefFrame*)k2_;
+    return guarded("SearchBySim3", [&] {
+        a->statics();
+        KeyFrame *pKF1 = a->keyframe(), *pKF2 = b->keyframe();
+        cv::Mat R12(3, 3, CV_32F), t12(3, 1, CV_32F);
+        std::memcpy(R12.data, R12_9, 36);
+        std::memcpy(t12.data, t12_3, 12);
+        std::vector<MapPoint*> vp1 = pKF1->GetMapPointMatches(), vp2 = pKF2->GetMapPointMatches();
+        const int N1 = (int)vp1.size(), N2 = (int)vp2.size();
+        std::map<MapPoint*, int> idx2;
+        index_of(vp2, idx2);
+        std::vector<MapPoint*> vpMatches12(N1, nullptr);
+        std::vector<bool> done1(N1, false), done2(N2, false);
+        for (int i = 0; i < N1; i++)
+            if (matches12[i] >= 0 && vp2[matches12[i]]) { vpMatches12[i] = vp2[matches12[i]]; done1[i] = true; done2[matches12[i]] = true; }
+        {
+            const float fx = pKF1->fx, fy = pKF1->fy, cx = pKF1->cx, cy = pKF1->cy;
+            cv::Mat R1w = pKF1->GetRotation(), t1w = pKF1->GetTranslation(), R2w = pKF2->GetRotation(), t2w = pKF2->GetTranslation();
+            cv::Mat sR12 = s12 * R12;
+            cv::Mat sR21 = (1.0 / s12) * R12.t();
+            cv::Mat t21 = -sR21 * t12;
+            for (int dir = 0; dir < 2; dir++) {
+                const std::vector<MapPoint*>& src = dir == 0 ? vp1 : vp2;
+                KeyFrame* dst = dir == 0 ? pKF2 : pKF1;
+                const std::vector<bool>& done = dir == 0 ? done1 : done2;
+                uint8_t* act = dir == 0 ? act12 : act21; float* pu = dir == 0 ? u12 : u21; float* pv = dir == 0 ? v12 : v21; int32_t* pl = dir == 0 ? l12 : l21;
+                const int nMaxLevel = dst->GetScaleLevels() - 1;
+                std::vector<float> vfScaleFactors = dst->GetScaleFactors();
+                for (size_t i = 0; i < src.size(); i++) {
+                    act[i] = 0; pu[i] = pv[i] = 0.f; pl[i] = 0;
+                    MapPoint* pMP = src[i];
+                    if (!pMP || done[i]) continue;
+                    if (pMP->isBad()) continue;
+                    cv::Mat p3Dw = pMP->GetWorldPos();
+                    cv::Mat p3Dc;
+                    if (dir == 0) { cv::Mat p3Dc1 = R1w * p3Dw + t1w; p3Dc = sR21 * p3Dc1 + t21; }
+                    else { cv::Mat p3Dc2 = R2w * p3Dw + t2w; p3Dc = sR12 * p3Dc2 + t12; }
+                    if (p3Dc.at<float>(2) < 0.0) continue;
+                    float invz = 1.0 / p3Dc.at<float>(2);
+                    float x = p3Dc.at<float>(0) * invz;
+                    float y = p3Dc.at<float>(1) * invz;
+                    float u = fx * x + cx;
+                    float v = fy * y + cy;
+                    if (!dst->IsInImage(u, v)) continue;
+                    float maxDistance = pMP->GetMaxDistanceInvariance();
+                    float minDistance = pMP->GetMinDistanceInvariance();
+                    float dist3D = cv::norm(p3Dc);
+                    if (dist3D < minDistance || dist3D > maxDistance) continue;
+                    float ratio = dist3D / minDistance;
+                    std::vector<float>::iterator it = std::lower_bound(vfScaleFactors.begin(), vfScaleFactors.end(), ratio);
+                    act[i] = 1; pu[i] = u; pv[i] = v;
+                    pl[i] = std::min(static_cast<int>(it - vfScaleFactors.begin()), nMaxLevel);
+                }
+            }
+        }
+        ORBmatcher m(0.6f, true);
+        const int n = m.SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th);
+        for (int i = 0; i < N1; i++) matches12[i] = vpMatches12[i] ? idx2.at(vpMatches12[i]) : -1;
+        return n;
+    });
+}
+
+} // extern "C"
+extern "C" {
+
+/* ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>&, th), :1136-1265 (loop correction), one candidate per call
+ * like ref_fuse; here the keyframe's point is replaced BY the candidate (:1249), so the candidate always ends up observing pKF at the
+ * keypoint it fused with. */
+int ref_fuse_sim3(void* kf_, void* src_, const float* Scw16, float th, int32_t* fused, uint8_t* active, float* u, float* v, int32_t* level)
+{
+    RefFrame *k = (RefFrame*)kf_, *src = (RefFrame*)src_;
+    return guarded("Fuse(Scw)", [&] {
+        k->statics();
+        KeyFrame* kf = k->keyframe();
+        cv::Mat Scw(4, 4, CV_32F);
+        std::memcpy(Scw.data, Scw16, 64);
+        std::vector<MapPoint*> pts = src->f.mvpMapPoints;
+        {
+            cv::Mat sRcw = Scw.rowRange(0, 3).colRange(0, 3);
+            const float scw = sqrt(sRcw.row(0).dot(sRcw.row(0)));
+            cv::Mat Rcw = sRcw / scw;
+            cv::Mat tcw = Scw.rowRange(0, 3).col(3) / scw;
+            cv::Mat Ow = -Rcw.t() * tcw;
+            project_candidates(kf, Rcw, tcw, Ow, pts, kf->GetMapPoints(), false, active, u, v, level);
+        }
+        ORBmatcher m(0.6f, true);
+        int total = 0;
+        for (size_t i = 0; i < pts.size(); i++) {
+            fused[i] = -1;
+            if (!pts[i]) continue;
+            std::vector<MapPoint*> one(1, pts[i]);
+            if (m.Fuse(kf, Scw, one, th) != 1) continue;
+            total++;
+            fused[i] = pts[i]->GetIndexInKeyFrame(kf);
+        }
+        return total;
+    });
+}
+
+} // extern "C"
 #endif /* REF_GLUE_EXTRACTOR_ONLY */

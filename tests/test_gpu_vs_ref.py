@@ -97,3 +97,47 @@ def test_vocabulary_transform_equals_reference(pkg, tmp_path):
         bow, fv = gv.transform(feats, 2)
         assert np.array_equal(bow[0], rw) and np.array_equal(np.asarray(bow[1]).view(np.uint64), rvv.view(np.uint64))
         assert np.array_equal(fv[0], rn_) and np.array_equal(fv[1], rs) and np.array_equal(fv[2], ri)
+
+
+def test_backend_searches_equal_reference(pkg):
+    """SearchByProjection(KeyFrame,Scw), Fuse and SearchBySim3 (reference src/ORBmatcher.cc:286-407, :1016-1134, :1267-1505) through the
+    CUDA window searches, fed the reference's own projections and predicted levels (the adapter's part at the C ABI)."""
+    from oracle import pyoracle as po
+    import test_ref_build as T
+    (ka, da), (kb, db), cam, has, src, Tcw, S = T._backend_scene(po, (480, 752), 1000, 9900, 1.2)
+    w, h, fx, fy, cx, cy = cam
+    m = pkg.ORBmatcher(0.6, True)
+    gkf = pkg.Frame(m, kb, db, w, h, fx, fy, cx, cy)
+    # SearchByProjection(KF, Scw)
+    kf = pyref.RefFrame(kb, db, *cam).set_pose(Tcw)
+    pre = np.full(len(kb), -1, np.int32); pre[::7] = 555555
+    rn, rmatched, (act, u, v, lv) = pyref.search_by_projection_sim3(kf, src, S, 10, pre.copy())
+    n, matched = m.SearchByProjectionSim3(gkf, act, u, v, lv, da, 10, pre.copy())
+    assert rn > 20 and n == rn and np.array_equal(matched, rmatched)
+    # Fuse
+    rng = np.random.default_rng(1)
+    occupied = (rng.random(len(kb)) < 0.5).astype(np.uint8)
+    kf2 = pyref.RefFrame(kb, db, *cam).set_pose(Tcw).set_mappoints(occupied).update_points()
+    rn, rfused, (act, u, v, lv) = pyref.fuse_sim3(kf2, src, S, 4.0)
+    fused = m.FuseCandidates(gkf, act, u, v, lv, da, th=4.0)
+    assert rn > 20 and np.array_equal(fused, rfused)
+
+
+def test_search_by_sim3_equals_reference(pkg):
+    from oracle import pyoracle as po
+    import test_ref_build as T
+    (ka, da), (kb, db), cam, has, outl, xyz, Tcw = T._scene(po, 480, 752, 1000, 9901)
+    w, h, fx, fy, cx, cy = cam
+    rng = np.random.default_rng(4)
+    k1 = pyref.RefFrame(ka, da, *cam).set_mappoints(has, xyz).update_points()
+    z2 = rng.uniform(2, 10, len(kb)).astype(np.float32)
+    pc2 = np.stack([(kb["x"] - cx) / fx * z2, (kb["y"] - cy) / fy * z2, z2], 1).astype(np.float64)
+    R, t = Tcw[:3, :3].astype(np.float64), Tcw[:3, 3].astype(np.float64)
+    has2 = (rng.random(len(kb)) < 0.9).astype(np.uint8)
+    k2 = pyref.RefFrame(kb, db, *cam).set_pose(Tcw).set_mappoints(has2, ((pc2 - t) @ R).astype(np.float32)).update_points()
+    s12 = 1.1
+    rn, rm12, (a12, u12, v12, l12), (a21, u21, v21, l21) = pyref.search_by_sim3(k1, k2, s12, R.T.astype(np.float32), (-s12 * (R.T @ t)).astype(np.float32), 7.5)
+    m = pkg.ORBmatcher(0.6, True)
+    g1, g2 = pkg.Frame(m, ka, da, w, h, fx, fy, cx, cy), pkg.Frame(m, kb, db, w, h, fx, fy, cx, cy)
+    n, m12 = m.SearchBySim3(g1, g2, a12, u12, v12, l12, da, a21, u21, v21, l21, db, th=7.5)
+    assert rn > 20 and n == rn and np.array_equal(m12, rm12)

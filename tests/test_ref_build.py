@@ -501,3 +501,57 @@ def test_fuse(po, shape, nf, th):
     assert first.sum() > 0.95 * len(want)
     assert np.array_equal(fused[first], want[first])
     assert occupied[fused[fused >= 0]].any() and not occupied[fused[fused >= 0]].all()       # both the Replace and the AddObservation branch ran
+
+
+@pytest.mark.parametrize("shape,nf,th,s12", [((240, 320), 500, 7.5, 1.0), ((480, 752), 1000, 7.5, 1.1), ((376, 1241), 2000, 5.0, 0.9)])
+def test_search_by_sim3(po, shape, nf, th, s12):
+    """src/ORBmatcher.cc:1267-1505 (loop closing): both projection directions, TH_HIGH, and the mutual-agreement test, against
+    window_best of the oracle on the reference's own projections."""
+    (ka, da), (kb, db), cam, has, outl, xyz, T = _scene(po, shape[0], shape[1], nf, 8800 + nf)
+    rng = np.random.default_rng(nf + 3)
+    # KF1 at the world origin with its points; KF2 at pose T holding points for ITS features: the same 3-D structure seen from T
+    k1 = pyref.RefFrame(ka, da, *cam).set_mappoints(has, xyz).update_points()
+    fx, fy, cx, cy = cam[2:]
+    z2 = rng.uniform(2, 10, len(kb)).astype(np.float32)
+    pc2 = np.stack([(kb["x"] - cx) / fx * z2, (kb["y"] - cy) / fy * z2, z2], 1).astype(np.float64)
+    R, t = T[:3, :3].astype(np.float64), T[:3, 3].astype(np.float64)
+    xyz2 = ((pc2 - t) @ R).astype(np.float32)                         # world = R^T (pc - t)
+    has2 = (rng.random(len(kb)) < 0.9).astype(np.uint8)
+    k2 = pyref.RefFrame(kb, db, *cam).set_pose(T).set_mappoints(has2, xyz2).update_points()
+    # Sim3 camera1 <- camera2: x1 = s12 R12 x2 + t12 with R12 = R^T, t12 = -s12 R^T t (poses: camera1 = world, camera2 = T)
+    R12 = R.T.astype(np.float32)
+    t12 = (-s12 * (R.T @ t)).astype(np.float32)
+    pre = np.full(len(ka), -1, np.int32)
+    n, m12, (a12, u12, v12, l12), (a21, u21, v21, l21) = pyref.search_by_sim3(k1, k2, s12, R12, t12, th, pre.copy())
+    assert a12.sum() > 50 and a21.sum() > 50
+    o1, o2 = po.OracleFrame(ka, da, *cam), po.OracleFrame(kb, db, *cam)
+    sf = np.ones(8, np.float32)
+    for i in range(1, 8):
+        sf[i] = np.float32(sf[i - 1] * np.float32(1.2))
+    b1, d1 = po.window_best(o2, a12, u12, v12, (np.float32(th) * sf[l12]).astype(np.float32), l12, da)
+    b2, d2 = po.window_best(o1, a21, u21, v21, (np.float32(th) * sf[l21]).astype(np.float32), l21, db)
+    m1 = np.where((a12 > 0) & (b1 >= 0) & (d1 <= 100), b1, -1)
+    m2 = np.where((a21 > 0) & (b2 >= 0) & (d2 <= 100), b2, -1)
+    want = np.full(len(ka), -1, np.int32)
+    for i1 in np.flatnonzero(m1 >= 0):
+        if m2[m1[i1]] == i1:
+            want[i1] = m1[i1]
+    assert n > 10
+    assert n == int((want >= 0).sum()) and np.array_equal(m12, want)
+
+
+@pytest.mark.parametrize("shape,nf,th,scale", [((240, 320), 500, 2.5, 1.0), ((480, 752), 1000, 4.0, 1.25)])
+def test_fuse_sim3(po, shape, nf, th, scale):
+    """src/ORBmatcher.cc:1136-1265 (loop correction): Fuse through a similarity; here every candidate's keypoint can be read back."""
+    (ka, da), (kb, db), cam, has, src, T, S = _backend_scene(po, shape, nf, 8900 + nf, scale)
+    rng = np.random.default_rng(nf)
+    occupied = (rng.random(len(kb)) < 0.5).astype(np.uint8)
+    kf = pyref.RefFrame(kb, db, *cam).set_pose(T).set_mappoints(occupied).update_points()
+    n, fused, (active, u, v, level) = pyref.fuse_sim3(kf, src, S, th)
+    sf = np.ones(8, np.float32)
+    for i in range(1, 8):
+        sf[i] = np.float32(sf[i - 1] * np.float32(1.2))
+    bi, bd = po.window_best(po.OracleFrame(kb, db, *cam), active, u, v, (np.float32(th) * sf[level]).astype(np.float32), level, da)
+    want = np.where((active > 0) & (bi >= 0) & (bd <= 50), bi, -1)
+    assert n > 10 and n == int((want >= 0).sum())
+    assert np.array_equal(fused, want)
