@@ -705,6 +705,7 @@ __device__ __forceinline__ int warp_partition(T* v, int first, int last, C lt, u
         if (ok) { const T t = v[i]; v[i] = v[partner]; v[partner] = t; }
         m += __popc(okm);
         if (fail) { cut = base + __ffs(fail) - 1; break; }
+        __syncwarp();      // a partner may lie in the next chunk: order this trip's stores before the next trip's loads
     }
     __syncwarp();
     const int bm = m > 0 ? (int)scratch[m - 1] : INT_MAX;
