@@ -277,3 +277,27 @@ def test_descriptor_fma_variant(pkg, po):
     plain = po.OracleExtractor(1000, 1.2, 8, 1, 20)
     for img, (k, d) in zip(frames, ex.extract_batch(frames)):
         assert np.array_equal(d, plain(img)[1])
+
+
+@pytest.mark.parametrize("kind,h,w,nf", [("two_level", 240, 320, 300), ("two_level", 480, 752, 1000), ("big_cells", 720, 1280, 200),
+                                          ("big_cells", 1080, 1920, 1000), ("blocks", 376, 1241, 2000)])
+def test_selection_ties_and_long_lists(pkg, po, kind, h, w, nf):
+    """The selection kernel replays std::nth_element with a warp per cell (k_select_fast): tie-heavy scores (images with two or a
+    few gray levels), cell lists longer than the 1024-entry staging buffer (few features on a large image: the serial in-place path)
+    and level lists far above the quota must all keep the reference's order."""
+    rng = np.random.default_rng(h * 7 + nf)
+    if kind == "two_level":                               # two gray levels: a handful of distinct FAST scores
+        small = rng.random((h // 3 + 1, w // 3 + 1)) < 0.5
+        img = np.where(np.kron(small, np.ones((3, 3), bool))[:h, :w], 200, 60).astype(np.uint8)
+    elif kind == "blocks":
+        lv = rng.integers(0, 4, (h // 5 + 1, w // 5 + 1)) * 60 + 20
+        img = np.kron(lv, np.ones((5, 5), np.int64))[:h, :w].astype(np.uint8)
+    else:                                                  # dense noise: thousands of candidates per (large) cell
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    ex = pkg.ORBextractor(nf, 1.2, 8, 1, 20, device=0, max_width=w, max_height=h, max_batch=1)
+    k, d = ex(img)
+    rk, rd = po.OracleExtractor(nf, 1.2, 8, 1, 20)(img)
+    assert len(k) == len(rk) and len(k) > nf // 4
+    for f in ("x", "y", "response", "octave"):
+        assert np.array_equal(k[f], rk[f]), f
+    assert np.array_equal(d, rd)
