@@ -738,7 +738,7 @@ __device__ __forceinline__ void warp_nth_element(T* v, int n, int nth, C lt, uns
 // FAST_SCORE selection: CTA per (frame, level), warp per cell.
 __global__ void __launch_bounds__(SEL_WARPS * 32)
 k_select_fast(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells, uint32_t* __restrict__ cand, const int* __restrict__ ntotal,
-              unsigned long long* __restrict__ lvl, int* __restrict__ nkept, int* __restrict__ status)
+              unsigned long long* __restrict__ lvl, int* __restrict__ nkept, int* __restrict__ status, uint8_t* __restrict__ spare, size_t fbytes)
 {
     extern __shared__ unsigned long long s_list[];            // sel_list_cap u64 | SEL_WARPS x SEL_WCAP u32 | SEL_WARPS x SEL_WCAP u16
     __shared__ int s_total[ORB_MAX_CELLS_LEVEL], s_retain[ORB_MAX_CELLS_LEVEL], s_off[ORB_MAX_CELLS_LEVEL + 1];
@@ -792,7 +792,12 @@ k_select_fast(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells,
                 __syncwarp();
                 warp_nth_element(w, n, keep - 1, lt32, s_scr + warp * SEL_WCAP, lane);
                 v = w;
-            } else {                                           // a list longer than the staging buffer: in place, one thread
+            } else if (n <= 65535 && spare) {
+                // longer than the staging buffer (few features on a large image): the same warp algorithm in place in global memory;
+                // its index scratch is the frame's NMS score map, which nothing reads after k_cell_compact (2 bytes per candidate slot)
+                unsigned short* gs = reinterpret_cast<unsigned short*>(spare + (size_t)f * fbytes) + cg[c].cand_off;
+                warp_nth_element(v, n, keep - 1, lt32, gs, lane);
+            } else {
                 if (lane == 0) orbsel::nth_element(v, n, keep - 1, lt32);
                 __syncwarp();
             }
@@ -1268,7 +1273,8 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         if (c->select_serial)
             k_select<false><<<dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s>>>(c->d_plan, c->d_cells, W.d_cand, nullptr, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status);
         else
-            k_select_fast<<<dim3(P.nlevels, nimg), SEL_WARPS * 32, (size_t)P.sel_list_cap * 8 + (size_t)SEL_WARPS * SEL_WCAP * 6, s>>>(c->d_plan, c->d_cells, W.d_cand, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status);
+            k_select_fast<<<dim3(P.nlevels, nimg), SEL_WARPS * 32, (size_t)P.sel_list_cap * 8 + (size_t)SEL_WARPS * SEL_WCAP * 6, s>>>(c->d_plan, c->d_cells, W.d_cand, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status,
+                                                                                                                                         (size_t)P.cand_total * 2 <= fb ? W.d_work : nullptr, fb);
     }
     if (fork && c->fork_early == 3) {      // selection first: the latency-bound kernel takes the residency it needs, blur fills the rest
         launch_blur(W.aux_stream);
