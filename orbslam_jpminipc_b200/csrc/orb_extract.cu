@@ -735,9 +735,11 @@ __device__ __forceinline__ void warp_nth_element(T* v, int n, int nth, C lt, uns
     __syncwarp();
 }
 
-// FAST_SCORE selection: CTA per (frame, level), warp per cell.
+// Selection: CTA per (frame, level), warp per cell.  HARRIS: 64-bit records (float response | position) in global memory.
+template <bool HARRIS>
 __global__ void __launch_bounds__(SEL_WARPS * 32)
-k_select_fast(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells, uint32_t* __restrict__ cand, const int* __restrict__ ntotal,
+k_select_fast(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells, uint32_t* __restrict__ cand,
+              unsigned long long* __restrict__ cand64, const int* __restrict__ ntotal,
               unsigned long long* __restrict__ lvl, int* __restrict__ nkept, int* __restrict__ status, uint8_t* __restrict__ spare, size_t fbytes)
 {
     extern __shared__ unsigned long long s_list[];            // sel_list_cap u64 | SEL_WARPS x SEL_WCAP u32 | SEL_WARPS x SEL_WCAP u16
@@ -780,33 +782,48 @@ k_select_fast(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells,
     int total = s_off[nCells];
     if (total < 0) { if (tid == 0) nkept[f * plan->nlevels + level] = 0; return; }
     uint32_t* gbase = cand + (size_t)f * plan->cand_total;
+    unsigned long long* gbase64 = HARRIS ? cand64 + (size_t)f * plan->cand_total : nullptr;
     const orbsel::KeyGreater<uint32_t, 24> lt32;
+    const orbsel::FloatKeyGreater64 ltf;
     for (int c = warp; c < nCells; c += SEL_WARPS) {           // retainBest per cell (:683-685)
         const int n = s_total[c], keep = s_retain[c];
         if (keep <= 0) continue;
-        uint32_t* v = gbase + cg[c].cand_off;
-        if (n > keep) {
-            if (n <= SEL_WCAP) {
-                uint32_t* w = s_wbuf + warp * SEL_WCAP;
-                for (int k = lane; k < n; k += 32) w[k] = v[k];
-                __syncwarp();
-                warp_nth_element(w, n, keep - 1, lt32, s_scr + warp * SEL_WCAP, lane);
-                v = w;
-            } else if (n <= 65535 && spare) {
-                // longer than the staging buffer (few features on a large image): the same warp algorithm in place in global memory;
-                // its index scratch is the frame's NMS score map, which nothing reads after k_cell_compact (2 bytes per candidate slot)
-                unsigned short* gs = reinterpret_cast<unsigned short*>(spare + (size_t)f * fbytes) + cg[c].cand_off;
-                warp_nth_element(v, n, keep - 1, lt32, gs, lane);
-            } else {
-                if (lane == 0) orbsel::nth_element(v, n, keep - 1, lt32);
-                __syncwarp();
-            }
-        }
         const int ix = cg[c].inix, iy = cg[c].iniy;
-        for (int k = lane; k < keep; k += 32) {
-            const uint32_t r = v[k];
-            const unsigned long long x = (r & 0xfff) + ix, y = ((r >> 12) & 0xfff) + iy;
-            s_list[s_off[c] + k] = ((unsigned long long)(r >> 24) << 32) | (y << 16) | x;
+        // index scratch for lists that are selected in place in global memory: the frame's NMS score map, which nothing reads after
+        // k_cell_compact (2 bytes per candidate slot)
+        unsigned short* gs = spare ? reinterpret_cast<unsigned short*>(spare + (size_t)f * fbytes) + cg[c].cand_off : nullptr;
+        if (HARRIS) {
+            unsigned long long* v = gbase64 + cg[c].cand_off;
+            if (n > keep) {
+                if (n <= 65535 && gs) warp_nth_element(v, n, keep - 1, ltf, gs, lane);
+                else { if (lane == 0) orbsel::nth_element(v, n, keep - 1, ltf); __syncwarp(); }
+            }
+            for (int k = lane; k < keep; k += 32) {
+                const unsigned long long r = v[k];
+                const unsigned long long x = (r & 0xfff) + ix, y = ((r >> 12) & 0xfff) + iy;
+                s_list[s_off[c] + k] = (r & 0xffffffff00000000ull) | (y << 16) | x;
+            }
+        } else {
+            uint32_t* v = gbase + cg[c].cand_off;
+            if (n > keep) {
+                if (n <= SEL_WCAP) {
+                    uint32_t* w = s_wbuf + warp * SEL_WCAP;
+                    for (int k = lane; k < n; k += 32) w[k] = v[k];
+                    __syncwarp();
+                    warp_nth_element(w, n, keep - 1, lt32, s_scr + warp * SEL_WCAP, lane);
+                    v = w;
+                } else if (n <= 65535 && gs) {                     // longer than the staging buffer (few features on a large image)
+                    warp_nth_element(v, n, keep - 1, lt32, gs, lane);
+                } else {
+                    if (lane == 0) orbsel::nth_element(v, n, keep - 1, lt32);
+                    __syncwarp();
+                }
+            }
+            for (int k = lane; k < keep; k += 32) {
+                const uint32_t r = v[k];
+                const unsigned long long x = (r & 0xfff) + ix, y = ((r >> 12) & 0xfff) + iy;
+                s_list[s_off[c] + k] = ((unsigned long long)(r >> 24) << 32) | (y << 16) | x;
+            }
         }
         __syncwarp();
     }
@@ -814,8 +831,13 @@ k_select_fast(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells,
     if (total > L.nDesired) {                                  // retainBest per level (:697-701)
         const orbsel::KeyGreater<unsigned long long, 32> lt64;
         if (warp == 0) {
-            if (total <= SEL_WARPS * SEL_WCAP) warp_nth_element(s_list, total, L.nDesired - 1, lt64, s_scr, lane);
-            else if (lane == 0) orbsel::nth_element(s_list, total, L.nDesired - 1, lt64);
+            if (total <= SEL_WARPS * SEL_WCAP) {
+                if (HARRIS) warp_nth_element(s_list, total, L.nDesired - 1, ltf, s_scr, lane);
+                else warp_nth_element(s_list, total, L.nDesired - 1, lt64, s_scr, lane);
+            } else if (lane == 0) {
+                if (HARRIS) orbsel::nth_element(s_list, total, L.nDesired - 1, ltf);
+                else orbsel::nth_element(s_list, total, L.nDesired - 1, lt64);
+            }
         }
         total = L.nDesired;
         __syncthreads();
@@ -1265,16 +1287,20 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         if (c->fork_early == 0) { launch_blur(W.aux_stream); ORB_CUDA(cudaEventRecord(W.ev_join, W.aux_stream)); }
     }
     mark();
+    const size_t sel_smem = (size_t)P.sel_list_cap * 8 + (size_t)SEL_WARPS * SEL_WCAP * 6;
+    uint8_t* sel_spare = (size_t)P.cand_total * 2 <= fb ? W.d_work : nullptr;
     if (P.harris) {
         k_harris<<<dim3((P.ncells + 7) / 8, nimg), 256, 0, s>>>(W.d_planes, fb, c->d_plan, c->d_cells, W.d_cand, W.d_ntotal, W.d_cand64);
-        k_select<true><<<dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s>>>(c->d_plan, c->d_cells, W.d_cand, W.d_cand64, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status);
+        if (c->select_serial)
+            k_select<true><<<dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s>>>(c->d_plan, c->d_cells, W.d_cand, W.d_cand64, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status);
+        else
+            k_select_fast<true><<<dim3(P.nlevels, nimg), SEL_WARPS * 32, sel_smem, s>>>(c->d_plan, c->d_cells, W.d_cand, W.d_cand64, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status, sel_spare, fb);
         launches++;
     } else if (!(c->debug_skip & 2)) {
         if (c->select_serial)
             k_select<false><<<dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s>>>(c->d_plan, c->d_cells, W.d_cand, nullptr, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status);
         else
-            k_select_fast<<<dim3(P.nlevels, nimg), SEL_WARPS * 32, (size_t)P.sel_list_cap * 8 + (size_t)SEL_WARPS * SEL_WCAP * 6, s>>>(c->d_plan, c->d_cells, W.d_cand, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status,
-                                                                                                                                         (size_t)P.cand_total * 2 <= fb ? W.d_work : nullptr, fb);
+            k_select_fast<false><<<dim3(P.nlevels, nimg), SEL_WARPS * 32, sel_smem, s>>>(c->d_plan, c->d_cells, W.d_cand, nullptr, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status, sel_spare, fb);
     }
     if (fork && c->fork_early == 3) {      // selection first: the latency-bound kernel takes the residency it needs, blur fills the rest
         launch_blur(W.aux_stream);
@@ -1299,7 +1325,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
 static int raise_dyn_smem(const void* fn, int slot, int bytes)
 {
     static std::mutex mu;
-    static int cur[4][64] = {};
+    static int cur[5][64] = {};
     int dev = 0;
     ORB_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(mu);
@@ -1316,5 +1342,6 @@ int orb_select_smem_setup(int list_cap)     // list_cap: the largest per-level k
     const int serial = list_cap * 8 + SEL_STAGE * 4 + 1024, fast = list_cap * 8 + SEL_WARPS * SEL_WCAP * 6 + 1024;
     int rc = raise_dyn_smem((const void*)k_select<false>, 1, serial);
     if (!rc) rc = raise_dyn_smem((const void*)k_select<true>, 2, serial);
-    return rc ? rc : raise_dyn_smem((const void*)k_select_fast, 3, fast);
+    if (!rc) rc = raise_dyn_smem((const void*)k_select_fast<true>, 4, fast);
+    return rc ? rc : raise_dyn_smem((const void*)k_select_fast<false>, 3, fast);
 }
