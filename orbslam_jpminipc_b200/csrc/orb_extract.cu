@@ -241,13 +241,23 @@ k_border(uint8_t* __restrict__ planes, uint8_t* __restrict__ blurred, size_t fby
     if ((unsigned)sy >= (unsigned)h) sy = reflect101(sy, h);            // only for ROIs lower than the frame
     const uint8_t* srow = planes + poff + (size_t)(sy + ORB_EDGE) * L.stride + ORB_EDGE;
     uint32_t v = 0;
+    const int xw = wx * 4 - ORB_EDGE;                   // ROI column of the word's first byte; ROI rows start 16-byte aligned
+    if (xw >= 0 && xw + 3 < w) {
+        v = *reinterpret_cast<const uint32_t*>(srow + xw);              // band word above / below the ROI: an aligned copy
+    } else if (xw < 0 && w > ORB_EDGE + 3) {
+        // left frame: bytes x = xw..xw+3 mirror columns -xw, -xw-1, -xw-2, -xw-3 = byte 0 of the aligned word at -xw and
+        // bytes 3, 2, 1 of the word before it
+        const uint32_t hi = *reinterpret_cast<const uint32_t*>(srow - xw), lo = *reinterpret_cast<const uint32_t*>(srow - xw - 4);
+        v = __byte_perm(lo, hi, 0x1234);
+    } else {
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        int x = wx * 4 + k - ORB_EDGE;                  // ROI column of this byte
-        if (x < w + ORB_EDGE) {
-            if (x < 0) x = -x; else if (x >= w) x = 2 * w - 2 - x;
-            if ((unsigned)x >= (unsigned)w) x = reflect101(x, w);       // only for ROIs narrower than the frame
-            v |= (uint32_t)srow[x] << (8 * k);
+        for (int k = 0; k < 4; k++) {
+            int x = xw + k;                                 // ROI column of this byte
+            if (x < w + ORB_EDGE) {
+                if (x < 0) x = -x; else if (x >= w) x = 2 * w - 2 - x;
+                if ((unsigned)x >= (unsigned)w) x = reflect101(x, w);       // only for ROIs narrower than the frame
+                v |= (uint32_t)srow[x] << (8 * k);
+            }
         }
     }
     const size_t o = poff + (size_t)py * L.stride + wx * 4;
