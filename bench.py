@@ -173,6 +173,25 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run (and first-touch the pinned staging buffers) on the CPUs NVML reports as local to that GPU, so that
+    eight ranks do not pull their frames through one socket's memory controllers.  Returns the CPU count bound to, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------- GPU arm
 def run_matching(args, L, ex, dev, world, rank, stream, barrier, max_over_ranks, e0, e1):
     import torch
@@ -317,6 +336,7 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -532,7 +552,8 @@ def run_gpu(args):
                        "nlevels": NLEVELS, "scale": SCALE, "fast_th": FAST_TH, "mean_keypoints": nkp,
                        "l2_policy": "no flush needed: per-step working set (frames + pyramids + score maps, %.0f MB) exceeds the 126 MB L2"
                                     % (B * (W * H + 2 * 1.45e6) / 1e6),
-                       "parallelism": "frames sharded over %d GPU(s), no collective on the extraction path" % world},
+                       "parallelism": "frames sharded over %d GPU(s), no collective on the extraction path" % world,
+                       "cpu_affinity": ("rank bound to the %d CPUs local to its GPU (NVML)" % numa) if numa else "unbound"},
             "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(B * W * H),
                     "d2h_bytes_per_step": int(B * cap * 60 + B * 4), "ms_per_step": e2e_ms / args.steps,
