@@ -21,7 +21,8 @@ BLUR_F32, BLUR_FIXED_256, BLUR_FIXED_257 = 0, 1, 2
 def build(force=False):
     src = os.path.join(_HERE, "orb_oracle.cpp")
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-s", "clean", "all"])
+        # only this library: oracle/_ref/ can be rebuilt only where the reference tree exists and must survive on the GPU box
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B" if force else "-s", "liborb_oracle.so"])
     return _SO
 
 
