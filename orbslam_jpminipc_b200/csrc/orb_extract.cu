@@ -552,7 +552,7 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
 // threshold 7 (src/ORBextractor.cc:609-614) — both sets are sub-sequences of the th_lo list
 // ("one-pass fallback").
 // record = score<<24 | y_local<<12 | x_local   (cell-image coordinates, as cv::FAST reports)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)      // 32 registers (20 bytes spilled): latency bound, 0.128 -> 0.108 ms per 256 frames against 47 registers
 k_cell_compact(const uint8_t* __restrict__ nms, const uint8_t* __restrict__ bitmap, size_t fbytes, const Plan* __restrict__ plan,
                const CellGeom* __restrict__ cells, uint32_t* __restrict__ cand, int* __restrict__ ntotal)
 {
