@@ -212,16 +212,19 @@ k_resize(const __grid_constant__ CUtensorMap tm, uint8_t* __restrict__ planes, s
 __global__ void __launch_bounds__(256)
 k_border(uint8_t* __restrict__ planes, uint8_t* __restrict__ blurred, size_t fbytes, const Plan* __restrict__ plan)
 {
-    // blockIdx.y = frame * nlevels + level; blockIdx.x walks the level's frame words (levels with fewer words exit)
+    // blockIdx.y = frame * nlevels + level; blockIdx.x walks the level's frame words (levels with fewer words exit).  Two words per
+    // thread, both fetched before either is stored: the kernel is bound by load latency, not by instructions.
     const int l = blockIdx.y % plan->nlevels, f = blockIdx.y / plan->nlevels;
     const LevelGeom& L = plan->L[l];
-    int item = blockIdx.x * blockDim.x + threadIdx.x;
-    if (item >= L.border_items) return;
+    const int first = blockIdx.x * (2 * blockDim.x) + threadIdx.x;
+    if (first >= L.border_items) return;
     const int w = L.w, h = L.h;
     const int wpr = L.stride >> 2;                      // words per padded row
     const int band = ORB_EDGE * wpr;                    // words in the top (or bottom) band
     const int rw0 = (ORB_EDGE + w) >> 2;                // first word that contains right-frame pixels
     const int side = 4 + (wpr - rw0);                   // frame words per middle row
+    const size_t poff = (size_t)f * fbytes + L.plane_off;
+    auto fetch = [&](int item, size_t& o) -> uint32_t {
     int py, wx;
     if (item < 2 * band) {                              // float reciprocal division is exact here (item < 2^23)
         const int bi = item >= band;
@@ -236,7 +239,6 @@ k_border(uint8_t* __restrict__ planes, uint8_t* __restrict__ blurred, size_t fby
         py += ORB_EDGE;
         if (wx >= 4) wx = rw0 + (wx - 4);
     }
-    const size_t poff = (size_t)f * fbytes + L.plane_off;
     int sy = py - ORB_EDGE;
     if (sy < 0) sy = -sy; else if (sy >= h) sy = 2 * h - 2 - sy;
     if ((unsigned)sy >= (unsigned)h) sy = reflect101(sy, h);            // only for ROIs lower than the frame
@@ -261,11 +263,22 @@ k_border(uint8_t* __restrict__ planes, uint8_t* __restrict__ blurred, size_t fby
             }
         }
     }
-    const size_t o = poff + (size_t)py * L.stride + wx * 4;
-    *reinterpret_cast<uint32_t*>(planes + o) = v;
+    o = poff + (size_t)py * L.stride + wx * 4;
+    return v;
+    };
+    size_t o0 = 0, o1 = 0;
+    const int second = first + blockDim.x;
+    const bool two = second < L.border_items;
+    const uint32_t v0 = fetch(first, o0);
+    const uint32_t v1 = two ? fetch(second, o1) : 0u;
     // the in-place blur of the reference leaves the frame un-blurred (:760): give the blurred buffer the same frame so
     // that the descriptor sampler reads one buffer only (k_blur later rewrites exactly the ROI bytes)
-    *reinterpret_cast<uint32_t*>(blurred + o) = v;
+    *reinterpret_cast<uint32_t*>(planes + o0) = v0;
+    *reinterpret_cast<uint32_t*>(blurred + o0) = v0;
+    if (two) {
+        *reinterpret_cast<uint32_t*>(planes + o1) = v1;
+        *reinterpret_cast<uint32_t*>(blurred + o1) = v1;
+    }
 }
 
 // ------------------------------------------------------------------ K2
@@ -1269,7 +1282,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
                                                bufb, nimg, W.d_counters + 4 + l, tw, rr);
         launches++;
     }
-    k_border<<<dim3((P.L[0].border_items + 255) / 256, nimg * P.nlevels), 256, 0, s>>>(W.d_planes, W.d_blur, fb, c->d_plan);
+    k_border<<<dim3((P.L[0].border_items + 511) / 512, nimg * P.nlevels), 256, 0, s>>>(W.d_planes, W.d_blur, fb, c->d_plan);
     launches++;
     // k_blur only needs the finished pyramid: outside profiling mode it runs on a second stream,
     // concurrently with FAST -> compaction -> selection (the selection kernel is latency bound and
