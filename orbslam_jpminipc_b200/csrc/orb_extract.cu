@@ -704,7 +704,7 @@ k_harris(const uint8_t* __restrict__ planes, size_t fbytes, const Plan* __restri
 }
 
 // ---- warp-cooperative, exact replay of std::nth_element (introselect.h explains why the partition may be evaluated in parallel) ----
-constexpr int SEL_WCAP = 1024;      // candidates one warp stages in shared memory (larger cell lists are selected serially in place)
+constexpr int SEL_WCAP = 512;       // candidates one warp stages in shared memory (longer cell lists are selected in place in global memory); 1024: 0.140 ms, 512: 0.104, 256: 0.110 per 256 frames
 #ifndef ORB_SEL_WARPS
 #define ORB_SEL_WARPS 8
 #define ORB_SEL_SERIAL_BELOW 8
