@@ -1016,13 +1016,14 @@ k_blur(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ blurred, size_t
     __shared__ __align__(128) uint8_t img2[2][BI_BUF];
     __shared__ __align__(16) float rowp[BI_H * BT_W];
     __shared__ __align__(8) uint64_t bar[2];
-    __shared__ int s_next[2];
+    __shared__ int s_next[2], s_ti[2], s_fr[2];             // next work item; tile index and frame of the item in each buffer
     const float k0 = __uint_as_float(0x3d8fafb1u), k1 = __uint_as_float(0x3e06387eu),
                 k2 = __uint_as_float(0x3e434a39u), k3 = __uint_as_float(0x3e5d4ae0u);
     const int tid = threadIdx.x;
     auto issue = [&](int item, int buf) {
         const int ti = item % ntiles, fr = item / ntiles;
         const Tile t = tiles[ti];
+        s_ti[buf] = ti; s_fr[buf] = fr;                     // decoded once here instead of by every thread (two integer divisions)
         mbar_expect_tx(&bar[buf], BI_BYTES);
         tma_load_3d(&img2[buf][0], &tm.m[t.level], t.x0, t.y0 - 3 + ORB_EDGE, fr, &bar[buf]);   // padded x0 = ROI x0 - 16
     };
@@ -1035,9 +1036,6 @@ k_blur(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ blurred, size_t
     if (tid == 0 && item < total) issue(item, 0);
     for (int it = 0; item < total; it++) {
         const int buf = it & 1;
-        const int ti = item % ntiles, f = item / ntiles;
-        const Tile t = tiles[ti];
-        const LevelGeom& L = plan->L[t.level];
         if (tid == 0) {
             const int nxt = atomicAdd(work_counter, 1) + (int)gridDim.x;
             s_next[buf] = nxt;
@@ -1045,6 +1043,10 @@ k_blur(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ blurred, size_t
         }
         if (tid < 32) mbar_wait(&bar[buf], (uint32_t)((it >> 1) & 1));      // one warp polls, the rest sleep in the barrier
         __syncthreads();
+        const int f = s_fr[buf];
+        const Tile t = tiles[s_ti[buf]];
+        const LevelGeom& L = plan->L[t.level];
+        const int Lw = L.w, Lh = L.h, Lstride = L.stride;
         const uint32_t* img = reinterpret_cast<const uint32_t*>(img2[buf]);
         // row pass: one task = 8 adjacent outputs of one row; ROI column x0+c sits at tile byte 16+c
         for (int task = tid; task < BI_H * (BT_W / 8); task += BLUR_THREADS) {
@@ -1095,10 +1097,10 @@ k_blur(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ blurred, size_t
                     iv[e] = __float_as_uint(__fadd_rn(s, 12582912.0f));
                 }
                 const uint32_t w = __byte_perm(__byte_perm(iv[0], iv[1], 0x0040), __byte_perm(iv[2], iv[3], 0x0040), 0x5410);
-                if (y < L.h && x < L.w) {    // exactly the ROI bytes: the frame of the blurred buffer holds the un-blurred reflection
-                    uint8_t* o = out + (size_t)(y + ORB_EDGE) * L.stride + x + ORB_EDGE;
-                    if (x + 3 < L.w) *reinterpret_cast<uint32_t*>(o) = w;
-                    else for (int e = 0; x + e < L.w; e++) o[e] = (uint8_t)(w >> (8 * e));
+                if (y < Lh && x < Lw) {    // exactly the ROI bytes: the frame of the blurred buffer holds the un-blurred reflection
+                    uint8_t* o = out + (size_t)(y + ORB_EDGE) * Lstride + x + ORB_EDGE;
+                    if (x + 3 < Lw) *reinterpret_cast<uint32_t*>(o) = w;
+                    else for (int e = 0; x + e < Lw; e++) o[e] = (uint8_t)(w >> (8 * e));
                 }
             }
         }
