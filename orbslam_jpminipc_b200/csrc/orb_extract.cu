@@ -381,7 +381,7 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
            const Plan* __restrict__ plan, const Tile* __restrict__ tiles, int ntiles, int total, int* __restrict__ work_counter)
 {
     __shared__ __align__(128) uint32_t img2[2][FI_H * FIW];
-    __shared__ int s_next[2];
+    __shared__ int s_next[2], s_ti[2], s_fr[2];             // next work item; tile index and frame of the item in each buffer
     __shared__ __align__(16) uint32_t sc[FS_H * FSW];
     __shared__ short colcell[FSW * 4], rowcell[FS_H];
     __shared__ __align__(4) uint8_t m_in[FSW * 4], m_l[FSW * 4], m_r[FSW * 4];
@@ -397,6 +397,7 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
     auto issue = [&](int item, int buf) {      // one thread: arm the barrier, start the copy
         const int ti = item % ntiles, fr = item / ntiles;
         const Tile t = tiles[ti];
+        s_ti[buf] = ti; s_fr[buf] = fr;                     // decoded once here instead of by every thread
         mbar_expect_tx(&bar[buf], TILE_BYTES);
         tma_load_3d(&img2[buf][0], &tm.m[t.level], t.x0 - 16 + ORB_EDGE, t.y0 - 4 + ORB_EDGE, fr, &bar[buf]);
     };
@@ -408,11 +409,12 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
     // dynamic work distribution: items differ a lot in cost (flat areas are rejected early)
     int item = blockIdx.x;
     if (tid == 0 && item < total) issue(item, 0);
+    __syncthreads();
 
     for (int it = 0; item < total; it++) {
         const int buf = it & 1;
-        const int ti = item % ntiles, f = item / ntiles;
-        const Tile t = tiles[ti];
+        const int f = s_fr[buf];
+        const Tile t = tiles[s_ti[buf]];
         const LevelGeom& L = plan->L[t.level];
         // claim + prefetch the next item; its buffer was last read before the post-scoring barrier of the previous iteration
         if (tid == 0) {
