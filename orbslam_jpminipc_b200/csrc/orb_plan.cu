@@ -107,7 +107,7 @@ int orb_build_plan(orb_ctx* c, int w, int h)
             // 128x64 tiles normally, 64x64 (4 rows per thread) for scale factors whose 128-wide footprint is too large
             bool fits = false;
             for (int attempt = 0; attempt < 2 && !fits; attempt++) {
-                const int tw = attempt ? 64 : 128, rr = attempt ? 4 : 8, th = (4 * ORB_RESIZE_THREADS / tw) * rr;
+                const int tw = attempt ? 64 : 128, rr = attempt ? 4 : c->rs_rows_pref, th = (4 * ORB_RESIZE_THREADS / tw) * rr;
                 int mw = 16, mr = 1;
                 for (int x0 = 0; x0 < L.w; x0 += tw) {
                     const int x1 = std::min(x0 + tw, L.w) - 1;
