@@ -30,9 +30,26 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# rank 0 prints exactly one JSON line on stdout: keep NCCL's version banner out of it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# rank 0 prints exactly one JSON line on stdout.  Native libraries write there too (NCCL's "NCCL version ..." banner appears at
+# every debug level from VERSION up, WARN included), so file descriptor 1 is pointed at stderr for the whole run and the result
+# line goes to the saved descriptor.
+_RESULT_FD = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
+def capture_stdout():
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
 
 W, H, NFEAT, NLEVELS, SCALE, FAST_TH = 752, 480, 1000, 8, 1.2, 20
 METRIC = "ORB frames/sec (752x480 EuRoC-shaped synthetic frames, 1000 kp, 8 levels, scale 1.2)"
@@ -170,7 +187,7 @@ def run_reference(args):
                              "sample": "%d frames per step x %d steps, frame-parallel over %d host threads; %s"
                                        % (per_step, args.steps, cores, CPU_WHAT[cpu_kind()])},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def bind_to_gpu_numa_node(index):
@@ -596,7 +613,7 @@ def run_gpu(args):
             for _ in range(10):
                 ov.transform(f1, 4)
             line["cpu_baseline"]["vocabulary_transform_k10_L6_ms_per_frame_1thread"] = (time.perf_counter() - t0) / 10 * 1e3
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -614,6 +631,7 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=64)
     ap.add_argument("--chunk", type=int, default=0, help="frames per kernel launch (context max_batch); 0 = batch")
     args = ap.parse_args()
+    capture_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
