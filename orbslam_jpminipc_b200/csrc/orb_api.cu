@@ -229,6 +229,7 @@ orb_ctx* orb_create(int device, int nfeatures, float scale_factor, int nlevels, 
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (const char* e = getenv("ORB_GRAPH")) c->use_graph = atoi(e);
     if (const char* e = getenv("ORB_DEBUG_SKIP")) c->debug_skip = atoi(e);
+    if (const char* e = getenv("ORB_RESIZE_FLEX")) c->rs_flex_width = atoi(e) != 0;
     if (const char* e = getenv("ORB_RESIZE_ROWS")) c->rs_rows_pref = std::max(1, std::min(atoi(e), 32));
     if (const char* e = getenv("ORB_SELECT_SERIAL")) c->select_serial = atoi(e);
     if (const char* e = getenv("ORB_FORK_EARLY")) c->fork_early = atoi(e);

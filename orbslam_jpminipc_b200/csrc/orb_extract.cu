@@ -145,7 +145,7 @@ k_resize(const __grid_constant__ CUtensorMap tm, uint8_t* __restrict__ planes, s
             if (nxt < total) issue(nxt, buf ^ 1);
         }
         const int gx = x0 + cgx, ys = y0 + rg * RS_ROWS;
-        const bool active = gx < D.w && ys < D.h;
+        const bool active = gx < D.w && ys < D.h && rg < ORB_RESIZE_THREADS / ncg;     // tile widths that do not divide 1024 leave a few threads over
         // Horizontal taps of the thread's four columns.  Their source bytes lie within 8 bytes of the first one for every scale
         // factor <= 2, so a source row costs three aligned words, two funnel shifts and per column one PRMT (both taps into
         // bytes 0,1) + one IDP.2A with the packed 16-bit weights; otherwise bytes are fetched one by one.
@@ -453,10 +453,17 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
         if (tid < 32) mbar_wait(&bar[buf], (uint32_t)((it >> 1) & 1));      // image tile has landed; one warp polls, the rest sleep in the barrier
         __syncthreads();
         const uint32_t* img = img2[buf];
+        // Tiles on the right / bottom edge of the detection region are only partly filled (8 % of the tile area at 752x480):
+        // tasks are numbered over the filled part only, so that a narrow tile takes fewer rounds instead of idle lanes.
+        // vw x vh = detection pixels of the tile; the NMS walks nq 16-pixel groups per row and reads one score word more on
+        // either side, one row more above and below.  Score words outside [nr) x [nw) keep stale values and are never read.
+        const int vw = min(FT_W, L.w - ORB_EDGE - t.x0), vh = min(FT_H, L.h - ORB_EDGE - t.y0);
+        const int nq = (vw + 15) >> 4, nw = min(FSW, 4 * nq + 2), nr = min(FS_H, vh + 2);
+        const uint32_t inv_nw = ((1u << 20) + nw - 1) / nw, inv_nq = ((1u << 20) + nq - 1) / nq;   // floor(task / n) = task * inv >> 20, exact for task < 4000, n <= 66
 
         // ---- corner strength: one task = 4 horizontally adjacent pixels ----
-        for (int task = tid; task < FS_H * FSW; task += FAST_THREADS) {
-            const int r = task / FSW, g = task - r * FSW;
+        for (int task = tid; task < nr * nw; task += FAST_THREADS) {
+            const int r = (int)(((uint32_t)task * inv_nw) >> 20), g = task - r * nw;
             const uint32_t cm = reinterpret_cast<const uint32_t*>(m_in)[g];
             uint32_t outw = 0;
             if (cm != 0 && rowcell[r] >= 0) {
@@ -507,7 +514,7 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
 #undef RING_ALL
 #undef RPAIR
             }
-            sc[task] = outw;
+            sc[r * FSW + g] = outw;
         }
         __syncthreads();
 
@@ -515,8 +522,8 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
         //      of responses to the score map and one 16-bit store to the survivor bitmap ----
         uint8_t* out = nms + (size_t)f * fbytes + L.plane_off;
         uint8_t* bm = bitmap + (size_t)f * plan->bm_total + L.bm_off;
-        for (int task = tid; task < FT_H * (FT_W / 16); task += FAST_THREADS) {
-            const int ro = task / (FT_W / 16), q4 = task - ro * (FT_W / 16);
+        for (int task = tid; task < vh * nq; task += FAST_THREADS) {
+            const int ro = (int)(((uint32_t)task * inv_nq) >> 20), q4 = task - ro * nq;
             const int r = ro + 1;
             const int rc = rowcell[r];
             const bool up = rowcell[r - 1] == rc, dn = rowcell[r + 1] == rc;
@@ -1050,61 +1057,84 @@ k_blur(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ blurred, size_t
         const LevelGeom& L = plan->L[t.level];
         const int Lw = L.w, Lh = L.h, Lstride = L.stride;
         const uint32_t* img = reinterpret_cast<const uint32_t*>(img2[buf]);
-        // row pass: one task = 8 adjacent outputs of one row; ROI column x0+c sits at tile byte 16+c
-        for (int task = tid; task < BI_H * (BT_W / 8); task += BLUR_THREADS) {
-            const int r = task >> 3, seg = task & 7;
-            const uint32_t* ip = img + r * BIW + 3 + 2 * seg;          // bytes 12+8seg .. 27+8seg
-            const uint32_t ax = ip[0], ay = ip[1], bx = ip[2], by = ip[3];
-            float v[14];
-            v[0] = u8f(ax, 1); v[1] = u8f(ax, 2); v[2] = u8f(ax, 3);
-            v[3] = u8f(ay, 0); v[4] = u8f(ay, 1); v[5] = u8f(ay, 2); v[6] = u8f(ay, 3);
-            v[7] = u8f(bx, 0); v[8] = u8f(bx, 1); v[9] = u8f(bx, 2); v[10] = u8f(bx, 3);
-            v[11] = u8f(by, 0); v[12] = u8f(by, 1); v[13] = u8f(by, 2);
-            float o[8];
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                float s = __fmul_rn(v[q], k0);
-                s = fmaf(v[q + 1], k1, s); s = fmaf(v[q + 2], k2, s); s = fmaf(v[q + 3], k3, s);
-                s = fmaf(v[q + 4], k2, s); s = fmaf(v[q + 5], k1, s); s = fmaf(v[q + 6], k0, s);
-                o[q] = s;
-            }
-            float4* op = reinterpret_cast<float4*>(rowp + r * BT_W + 8 * seg);
-            op[0] = make_float4(o[0], o[1], o[2], o[3]);
-            op[1] = make_float4(o[4], o[5], o[6], o[7]);
-        }
-        __syncthreads();
-        // column pass: one task = 4 columns x 4 rows of outputs (10 row-pass rows, float4 loads)
+        // Tiles on the right / bottom edge of the ROI are only partly filled (11 % of the tile area at 752x480): there, tasks are
+        // numbered over the filled part only (rowp entries outside it keep stale values and feed only outputs that are not stored).
+        // Full tiles keep compile-time task counts: with run-time bounds the compiler no longer overlaps the loads of consecutive
+        // tasks and the kernel as a whole gets slower (0.349 -> 0.365 ms per 256 frames), so both forms are instantiated.
+        const int ncg = (min(BT_W, Lw - t.x0) + 3) >> 2, nrg = (min(BT_H, Lh - t.y0) + 3) >> 2;     // 4x4 output blocks
+        const int nseg = (ncg + 1) >> 1, nrow = min(BI_H, 4 * nrg + 6);
+        const uint32_t inv_nseg = (65536u + nseg - 1) / nseg, inv_ncg = (65536u + ncg - 1) / ncg;   // floor(task / n) = task * inv >> 16, exact here
         uint8_t* out = blurred + (size_t)f * fbytes + L.plane_off;
-        for (int task = tid; task < (BT_W / 4) * (BT_H / 4); task += BLUR_THREADS) {
-            const int cg = task & 15, rg = task >> 4;
-            const float4* rp = reinterpret_cast<const float4*>(rowp + (rg * 4) * BT_W + cg * 4);
-            float4 R[10];
+        // row pass: one task = 8 adjacent outputs of one row; ROI column x0+c sits at tile byte 16+c
+        auto row_pass = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            const int ntask = FULL ? BI_H * (BT_W / 8) : nrow * nseg;
+            for (int task = tid; task < ntask; task += BLUR_THREADS) {
+                const int r = FULL ? task >> 3 : (int)(((uint32_t)task * inv_nseg) >> 16), seg = FULL ? task & 7 : task - r * nseg;
+                const uint32_t* ip = img + r * BIW + 3 + 2 * seg;          // bytes 12+8seg .. 27+8seg
+                const uint32_t ax = ip[0], ay = ip[1], bx = ip[2], by = ip[3];
+                float v[14];
+                v[0] = u8f(ax, 1); v[1] = u8f(ax, 2); v[2] = u8f(ax, 3);
+                v[3] = u8f(ay, 0); v[4] = u8f(ay, 1); v[5] = u8f(ay, 2); v[6] = u8f(ay, 3);
+                v[7] = u8f(bx, 0); v[8] = u8f(bx, 1); v[9] = u8f(bx, 2); v[10] = u8f(bx, 3);
+                v[11] = u8f(by, 0); v[12] = u8f(by, 1); v[13] = u8f(by, 2);
+                float o[8];
 #pragma unroll
-            for (int q = 0; q < 10; q++) R[q] = rp[q * (BT_W / 4)];
-            const int x = t.x0 + cg * 4;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int y = t.y0 + rg * 4 + q;
-                uint32_t iv[4];
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-#define RV(i) (e == 0 ? R[i].x : e == 1 ? R[i].y : e == 2 ? R[i].z : R[i].w)
-                    float s = __fmul_rn(k3, RV(q + 3));
-                    s = fmaf(__fadd_rn(RV(q + 4), RV(q + 2)), k2, s);
-                    s = fmaf(__fadd_rn(RV(q + 5), RV(q + 1)), k1, s);
-                    s = fmaf(__fadd_rn(RV(q + 6), RV(q)), k0, s);
-#undef RV
-                    // rint via the 1.5*2^23 magic constant: the low mantissa byte is the result.  No saturation needed: the taps
-                    // sum to 1 within 1e-7, so s < 255.5 for 8-bit inputs.
-                    iv[e] = __float_as_uint(__fadd_rn(s, 12582912.0f));
+                for (int q = 0; q < 8; q++) {
+                    float s = __fmul_rn(v[q], k0);
+                    s = fmaf(v[q + 1], k1, s); s = fmaf(v[q + 2], k2, s); s = fmaf(v[q + 3], k3, s);
+                    s = fmaf(v[q + 4], k2, s); s = fmaf(v[q + 5], k1, s); s = fmaf(v[q + 6], k0, s);
+                    o[q] = s;
                 }
-                const uint32_t w = __byte_perm(__byte_perm(iv[0], iv[1], 0x0040), __byte_perm(iv[2], iv[3], 0x0040), 0x5410);
-                if (y < Lh && x < Lw) {    // exactly the ROI bytes: the frame of the blurred buffer holds the un-blurred reflection
-                    uint8_t* o = out + (size_t)(y + ORB_EDGE) * Lstride + x + ORB_EDGE;
-                    if (x + 3 < Lw) *reinterpret_cast<uint32_t*>(o) = w;
-                    else for (int e = 0; x + e < Lw; e++) o[e] = (uint8_t)(w >> (8 * e));
+                float4* op = reinterpret_cast<float4*>(rowp + r * BT_W + 8 * seg);
+                op[0] = make_float4(o[0], o[1], o[2], o[3]);
+                op[1] = make_float4(o[4], o[5], o[6], o[7]);
+            }
+        };
+        // column pass: one task = 4 columns x 4 rows of outputs (10 row-pass rows, float4 loads)
+        auto col_pass = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            const int ntask = FULL ? (BT_W / 4) * (BT_H / 4) : ncg * nrg;
+            for (int task = tid; task < ntask; task += BLUR_THREADS) {
+                const int rg = FULL ? task >> 4 : (int)(((uint32_t)task * inv_ncg) >> 16), cg = FULL ? task & 15 : task - rg * ncg;
+                const float4* rp = reinterpret_cast<const float4*>(rowp + (rg * 4) * BT_W + cg * 4);
+                float4 R[10];
+#pragma unroll
+                for (int q = 0; q < 10; q++) R[q] = rp[q * (BT_W / 4)];
+                const int x = t.x0 + cg * 4;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int y = t.y0 + rg * 4 + q;
+                    uint32_t iv[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+#define RV(i) (e == 0 ? R[i].x : e == 1 ? R[i].y : e == 2 ? R[i].z : R[i].w)
+                        float s = __fmul_rn(k3, RV(q + 3));
+                        s = fmaf(__fadd_rn(RV(q + 4), RV(q + 2)), k2, s);
+                        s = fmaf(__fadd_rn(RV(q + 5), RV(q + 1)), k1, s);
+                        s = fmaf(__fadd_rn(RV(q + 6), RV(q)), k0, s);
+#undef RV
+                        // rint via the 1.5*2^23 magic constant: the low mantissa byte is the result.  No saturation needed: the taps
+                        // sum to 1 within 1e-7, so s < 255.5 for 8-bit inputs.
+                        iv[e] = __float_as_uint(__fadd_rn(s, 12582912.0f));
+                    }
+                    const uint32_t w = __byte_perm(__byte_perm(iv[0], iv[1], 0x0040), __byte_perm(iv[2], iv[3], 0x0040), 0x5410);
+                    if (y < Lh && x < Lw) {    // exactly the ROI bytes: the frame of the blurred buffer holds the un-blurred reflection
+                        uint8_t* o = out + (size_t)(y + ORB_EDGE) * Lstride + x + ORB_EDGE;
+                        if (x + 3 < Lw) *reinterpret_cast<uint32_t*>(o) = w;
+                        else for (int e = 0; x + e < Lw; e++) o[e] = (uint8_t)(w >> (8 * e));
+                    }
                 }
             }
+        };
+        if (ncg == BT_W / 4 && nrg == BT_H / 4) {
+            row_pass(std::true_type{});
+            __syncthreads();
+            col_pass(std::true_type{});
+        } else {
+            row_pass(std::false_type{});
+            __syncthreads();
+            col_pass(std::false_type{});
         }
         __syncthreads();          // rowp and the other image buffer are reused by the next item
         item = s_next[buf];

@@ -161,6 +161,7 @@ struct orb_ctx {
     int split_device = 0;
     int desc_fma = 0;                                      // orb_set_descriptor_fma
     int debug_skip = 0;                                    // ORB_DEBUG_SKIP (timing experiments only, results are wrong): 1 no blur, 2 no selection, 4 no describe
+    int rs_flex_width = 1;                                 // ORB_RESIZE_FLEX=0: fixed 128-column k_resize tiles (A/B timing)
     int rs_rows_pref = 8;                                  // ORB_RESIZE_ROWS: output rows per k_resize thread (tile height = 8 * rows at 128 columns)
     int select_serial = 0;                                 // ORB_SELECT_SERIAL=1: the thread-per-cell selection kernel (A/B timing)
     int use_graph = 1;                                     // ORB_GRAPH=0 switches the CUDA-graph replay off

@@ -103,11 +103,12 @@ int orb_build_plan(orb_ctx* c, int w, int h)
         if (l > 0) {
             axis_table(P.L[l - 1].w, L.w, true, c->xtab);
             axis_table(P.L[l - 1].h, L.h, false, c->ytab);
-            // largest source footprint of one output tile, from a 16-byte aligned origin (k_resize TMA box, <= 256 per side);
-            // 128x64 tiles normally, 64x64 (4 rows per thread) for scale factors whose 128-wide footprint is too large
-            bool fits = false;
-            for (int attempt = 0; attempt < 2 && !fits; attempt++) {
-                const int tw = attempt ? 64 : 128, rr = attempt ? 4 : c->rs_rows_pref, th = (4 * ORB_RESIZE_THREADS / tw) * rr;
+            // largest source footprint of one output tile, from a 16-byte aligned origin (k_resize TMA box, <= 256 per side).
+            // A thread owns 4 columns x rr rows, a CTA tw columns x (1024 / tw) * rr rows.  Among the tile widths 64..128 the one
+            // that leaves the fewest idle threads on this level's size wins (a fixed 128 wastes 18 % of the lanes on a 522-wide
+            // level); 64x64 tiles with 4 rows per thread remain the fallback for scale factors whose footprint is too large.
+            auto try_tile = [&](int tw, int rr) {
+                const int th = (4 * ORB_RESIZE_THREADS / tw) * rr;
                 int mw = 16, mr = 1;
                 for (int x0 = 0; x0 < L.w; x0 += tw) {
                     const int x1 = std::min(x0 + tw, L.w) - 1;
@@ -119,8 +120,21 @@ int orb_build_plan(orb_ctx* c, int w, int h)
                     mr = std::max(mr, (c->ytab[L.ytab_off + y1].x >> 16) - (c->ytab[L.ytab_off + y0].x & 0xffff) + 1);
                 }
                 c->rs_box_w[l] = (mw + 15) & ~15; c->rs_box_h[l] = mr; c->rs_tile_w[l] = tw; c->rs_rows[l] = rr;
-                fits = c->rs_box_w[l] <= 256 && mr <= 256;
+                return c->rs_box_w[l] <= 256 && mr <= 256;
+            };
+            int best_tw = 128;
+            if (c->rs_flex_width) {
+                double best = -1;
+                for (int tw = 64; tw <= 128; tw += 4) {
+                    const int th = (4 * ORB_RESIZE_THREADS / tw) * c->rs_rows_pref;
+                    const double ctas = (double)((L.w + tw - 1) / tw) * ((L.h + th - 1) / th);
+                    const double eff = (double)L.w * L.h / (ctas * ORB_RESIZE_THREADS * 4 * c->rs_rows_pref);
+                    if (eff >= best) { best = eff; best_tw = tw; }
+                }
             }
+            bool fits = try_tile(best_tw, c->rs_rows_pref);
+            if (!fits && best_tw != 128) fits = try_tile(128, c->rs_rows_pref);
+            if (!fits) fits = try_tile(64, 4);
             if (!fits) return ORB_ERR_CAPACITY;      // scale factors above ~3.7
         }
         L.border_base = border;
