@@ -458,12 +458,13 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
         // vw x vh = detection pixels of the tile; the NMS walks nq 16-pixel groups per row and reads one score word more on
         // either side, one row more above and below.  Score words outside [nr) x [nw) keep stale values and are never read.
         const int vw = min(FT_W, L.w - ORB_EDGE - t.x0), vh = min(FT_H, L.h - ORB_EDGE - t.y0);
-        const int nq = (vw + 15) >> 4, nw = min(FSW, 4 * nq + 2), nr = min(FS_H, vh + 2);
-        const uint32_t inv_nw = ((1u << 20) + nw - 1) / nw, inv_nq = ((1u << 20) + nq - 1) / nq;   // floor(task / n) = task * inv >> 20, exact for task < 4000, n <= 66
+        const int nq = (vw + 15) >> 4, nwi = 4 * nq, nr = min(FS_H, vh + 2);
+        const uint32_t inv_nq = ((1u << 20) + nq - 1) / nq;   // floor(task / nq) = task * inv >> 20, exact for task < 4000, nq <= 66
 
         // ---- corner strength: one task = 4 horizontally adjacent pixels ----
-        for (int task = tid; task < nr * nw; task += FAST_THREADS) {
-            const int r = (int)(((uint32_t)task * inv_nw) >> 20), g = task - r * nw;
+        // (score words 1 .. 4 nq; the two halo words of a row are one pixel each and have their own pass below)
+        for (int task = tid; task < nr * nwi; task += FAST_THREADS) {
+            const int r = (int)(((uint32_t)(task >> 2) * inv_nq) >> 20), g = task - r * nwi + 1;
             const uint32_t cm = reinterpret_cast<const uint32_t*>(m_in)[g];
             uint32_t outw = 0;
             if (cm != 0 && rowcell[r] >= 0) {
@@ -515,6 +516,40 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
 #undef RPAIR
             }
             sc[r * FSW + g] = outw;
+        }
+        // ---- halo columns: the NMS of the tile's first / last pixel column needs the strength of ONE pixel to the left (x0 - 1,
+        //      byte 3 of score word 0) and to the right (x0 + 16 nq, byte 0 of score word 4 nq + 1).  Scoring those two words like
+        //      the others would spend 2 of 18 tasks per row on 2 useful pixels of 8; here one task scores the pair (left, right)
+        //      of a row in the two 16-bit lanes: 1 task per row instead of 2, and with 2 pixels instead of 4. ----
+        for (int r = tid; r < nr; r += FAST_THREADS) {
+            const int gr = nwi + 1;
+            const uint32_t mL = m_in[3], mR = m_in[4 * gr];
+            uint32_t sL = 0, sR = 0;
+            if (rowcell[r] >= 0 && (mL | mR) != 0) {
+                const uint32_t* ip = img + r * FIW + 3;              // image words 3,4 hold columns x0-4 .. x0+3; words gr+2, gr+3 hold x0+16nq-4 .. +3
+                uint32_t a[7], b[7], c[7], d[7];
+#pragma unroll
+                for (int q = 0; q < 7; q++) { a[q] = ip[q * FIW]; b[q] = ip[q * FIW + 1]; c[q] = ip[q * FIW + nwi]; d[q] = ip[q * FIW + nwi + 1]; }
+                // sample (dx, row q) of both pixels, each duplicated into its 16-bit lane: left pixel = byte 3 of a[], right = byte 0 of d[]
+#define HP(q, dx) __byte_perm((dx) <= 0 ? a[q] : b[q], (dx) < 0 ? c[q] : d[q],                                               \
+                              (((dx) <= 0 ? 3 + (dx) : (dx) - 1) * 0x11) | ((4 + ((dx) < 0 ? 4 + (dx) : (dx))) * 0x1100))
+                uint32_t ring[16], Mn, Mx;
+                ring[0]  = HP(6, 0);  ring[1]  = HP(6, 1);  ring[2]  = HP(5, 2);  ring[3]  = HP(4, 3);
+                ring[4]  = HP(3, 3);  ring[5]  = HP(2, 3);  ring[6]  = HP(1, 2);  ring[7]  = HP(0, 1);
+                ring[8]  = HP(0, 0);  ring[9]  = HP(0, -1); ring[10] = HP(1, -2); ring[11] = HP(2, -3);
+                ring[12] = HP(3, -3); ring[13] = HP(4, -3); ring[14] = HP(5, -2); ring[15] = HP(6, -1);
+                const uint32_t v = HP(3, 0) & 0x00ff00ffu;
+#undef HP
+                const uint32_t nvp = __vadd2(~v, c1), vm1 = __vadd2(v, c1);
+                const uint32_t bl = __vimax3_u16x2(ring[0], ring[4], __vmaxu2(ring[8], ring[12]));
+                const uint32_t dl = __vimin3_u16x2(ring[0], ring[4], __vminu2(ring[8], ring[12]));
+                if (excess2(__byte_perm(bl, 0, 0x4240), __byte_perm(dl, 0, 0x4240), nvp, vm1) != 0) {
+                    arc_minmax(ring, Mn, Mx);
+                    const uint32_t sp2 = excess2(__byte_perm(Mn, 0, 0x4240), __byte_perm(Mx, 0, 0x4240), nvp, vm1);
+                    sL = (sp2 & 0xffu) & mL; sR = (sp2 >> 16) & mR;
+                }
+            }
+            sc[r * FSW] = sL << 24; sc[r * FSW + gr] = sR;
         }
         __syncthreads();
 
