@@ -101,6 +101,8 @@ static int prepare(orb_ctx* c, int w, int h)
         rc = ensure(c->d_tiles_blur, c->cap_tiles_blur, c->tiles_blur.size() * sizeof(Tile)); if (rc) return rc;
         rc = ensure(c->d_xtab, c->cap_xtab, c->xtab.size() * sizeof(int2)); if (rc) return rc;
         rc = ensure(c->d_ytab, c->cap_ytab, c->ytab.size() * sizeof(int2)); if (rc) return rc;
+        rc = ensure(c->d_fast_coltab, c->cap_fast_coltab, c->fast_coltab.size()); if (rc) return rc;
+        rc = ensure(c->d_fast_rowtab, c->cap_fast_rowtab, c->fast_rowtab.size() * sizeof(int16_t)); if (rc) return rc;
         ORB_CUDA(cudaDeviceSynchronize());       // nothing in flight may still read the old tables
         ORB_CUDA(cudaMemcpy(c->d_plan, &c->plan, sizeof(Plan), cudaMemcpyHostToDevice));
         ORB_CUDA(cudaMemcpy(c->d_cells, c->cells.data(), c->cells.size() * sizeof(CellGeom), cudaMemcpyHostToDevice));
@@ -108,6 +110,8 @@ static int prepare(orb_ctx* c, int w, int h)
         ORB_CUDA(cudaMemcpy(c->d_tiles_blur, c->tiles_blur.data(), c->tiles_blur.size() * sizeof(Tile), cudaMemcpyHostToDevice));
         if (!c->xtab.empty()) ORB_CUDA(cudaMemcpy(c->d_xtab, c->xtab.data(), c->xtab.size() * sizeof(int2), cudaMemcpyHostToDevice));
         if (!c->ytab.empty()) ORB_CUDA(cudaMemcpy(c->d_ytab, c->ytab.data(), c->ytab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        ORB_CUDA(cudaMemcpy(c->d_fast_coltab, c->fast_coltab.data(), c->fast_coltab.size(), cudaMemcpyHostToDevice));
+        ORB_CUDA(cudaMemcpy(c->d_fast_rowtab, c->fast_rowtab.data(), c->fast_rowtab.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
         int maxcap = 0;
         for (int l = 0; l < c->plan.nlevels; l++) maxcap = std::max(maxcap, c->plan.L[l].lvl_cap);
         if ((size_t)maxcap * 8 > 170 * 1024) return ORB_ERR_CAPACITY;
@@ -274,7 +278,7 @@ void orb_destroy(orb_ctx* c)
     if (c->ev_dev_done) cudaEventDestroy(c->ev_dev_done);
     if (c->ev_user) cudaEventDestroy(c->ev_user);
     for (cudaEvent_t e : c->ev_half) if (e) cudaEventDestroy(e);
-    void* ptrs[] = { c->d_plan, c->d_cells, c->d_tiles_fast, c->d_tiles_blur, c->d_xtab, c->d_ytab, c->d_status, c->d_src[0], c->d_src[1], c->d_kps[0],
+    void* ptrs[] = { c->d_plan, c->d_cells, c->d_tiles_fast, c->d_tiles_blur, c->d_xtab, c->d_ytab, c->d_fast_coltab, c->d_fast_rowtab, c->d_status, c->d_src[0], c->d_src[1], c->d_kps[0],
                      c->d_kps[1], c->d_desc[0], c->d_desc[1], c->d_counts[0], c->d_counts[1], c->d_knn_part, c->d_match_scratch };
     if (c->h_match_arena) cudaFreeHost(c->h_match_arena);
     for (void* p : ptrs) if (p) cudaFree(p);

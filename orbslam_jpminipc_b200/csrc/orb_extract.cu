@@ -378,13 +378,17 @@ __device__ __forceinline__ uint32_t excess2(uint32_t Mn, uint32_t Mx, uint32_t n
 // TMA into the other shared-memory buffer while item i is being scored.
 __global__ void __launch_bounds__(FAST_THREADS, FAST_CTAS)
 k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_t* __restrict__ bitmap, size_t fbytes,
-           const Plan* __restrict__ plan, const Tile* __restrict__ tiles, int ntiles, int total, int* __restrict__ work_counter)
+           const Plan* __restrict__ plan, const Tile* __restrict__ tiles, int ntiles, int total, int* __restrict__ work_counter,
+           const uint8_t* __restrict__ coltab, const int16_t* __restrict__ rowtab)
 {
     __shared__ __align__(128) uint32_t img2[2][FI_H * FIW];
     __shared__ int s_next[2], s_ti[2], s_fr[2];             // next work item; tile index and frame of the item in each buffer
     __shared__ __align__(16) uint32_t sc[FS_H * FSW];
-    __shared__ short colcell[FSW * 4], rowcell[FS_H];
-    __shared__ __align__(4) uint8_t m_in[FSW * 4], m_l[FSW * 4], m_r[FSW * 4];
+    __shared__ short rowcell[FS_H];
+    __shared__ __align__(16) uint32_t mask3[3 * FSW];       // byte masks per score-tile column: in region / left, right neighbour in the same cell
+    const uint8_t* m_in = reinterpret_cast<const uint8_t*>(mask3);
+    const uint8_t* m_l = m_in + FSW * 4;
+    const uint8_t* m_r = m_in + FSW * 8;
     __shared__ __align__(8) uint64_t bar[2];
     const int tid = threadIdx.x;
     // th = 0 (fastTh 0): a corner of strength 1 has response 0, never survives the strict NMS and never suppresses anything, exactly
@@ -423,32 +427,18 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
             if (nxt < total) issue(nxt, buf ^ 1);
         }
 
-        // detection-cell id of every score-tile column / row (-1: outside every detection rectangle)
-        for (int i = tid; i < FSW * 4 + FS_H; i += FAST_THREADS) {
-            if (i < FSW * 4) {
-                const int x = t.x0 - 4 + i;
-                int c = -1;
-                if (x >= ORB_EDGE) {
-                    c = (x - ORB_EDGE) / L.cellW;
-                    if (c >= L.cols - 1) { c = L.cols - 1; if (x >= L.w - ORB_EDGE) c = -1; }
-                }
-                colcell[i] = (short)c;
-            } else {
-                const int r = i - FSW * 4, y = t.y0 - 1 + r;
-                int c = -1;
-                if (y >= ORB_EDGE) {
-                    c = (y - ORB_EDGE) / L.cellH;
-                    if (c >= L.rows - 1) { c = L.rows - 1; if (y >= L.h - ORB_EDGE) c = -1; }
-                }
-                rowcell[r] = (short)c;
+        // detection cells of the score tile's columns (as byte masks) and rows: copied from the per-level tables the host built
+        // (orb_plan.cu); computing them here cost two integer divisions per entry and one more barrier per tile
+        {
+            const uint32_t* ct = reinterpret_cast<const uint32_t*>(coltab + L.ct_off) + (t.x0 >> 2);     // column x0 - 4 is entry x0
+            const int16_t* rt = rowtab + L.rt_off + t.y0;                                                // row y0 - 1 is entry y0
+            const int ctw = L.ct_len >> 2;
+            for (int i = tid; i < 3 * FSW + FS_H; i += FAST_THREADS) {
+                if (i < 3 * FSW) {
+                    const int a = i / FSW;
+                    mask3[i] = __ldg(ct + a * ctw + (i - a * FSW));
+                } else rowcell[i - 3 * FSW] = __ldg(rt + (i - 3 * FSW));
             }
-        }
-        __syncthreads();
-        for (int i = tid; i < FSW * 4; i += FAST_THREADS) {   // byte masks: in region / left, right neighbour in same cell
-            const int c = colcell[i];
-            m_in[i] = c >= 0 ? 0xff : 0;
-            m_l[i] = (i > 0 && c >= 0 && colcell[i - 1] == c) ? 0xff : 0;
-            m_r[i] = (i < FSW * 4 - 1 && c >= 0 && colcell[i + 1] == c) ? 0xff : 0;
         }
         if (tid < 32) mbar_wait(&bar[buf], (uint32_t)((it >> 1) & 1));      // image tile has landed; one warp polls, the rest sleep in the barrier
         __syncthreads();
@@ -1390,7 +1380,8 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
     {
         const int total = P.ntiles_fast * nimg;
         const int grid = std::min(total, c->num_sms * (fork && c->fork_early == 1 ? c->fast_ctas : FAST_CTAS));
-        k_fast_nms<<<grid, FAST_THREADS, 0, s>>>(W.tm_fast, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total, W.d_counters + 1);
+        k_fast_nms<<<grid, FAST_THREADS, 0, s>>>(W.tm_fast, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total, W.d_counters + 1,
+                                                     c->d_fast_coltab, c->d_fast_rowtab);
     }
     if (fork && c->fork_early == 2) {     // blur starts behind FAST, next to compaction + selection
         ORB_CUDA(cudaEventRecord(W.ev_fork, s));

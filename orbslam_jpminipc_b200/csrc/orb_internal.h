@@ -41,6 +41,9 @@ struct LevelGeom {
     int kp_base;           // prefix of nDesired over levels (unused slots stay empty)
     int border_base;       // first k_border work item of this level
     int border_items;      // 32-bit words of this level's 16-px frame
+    int ct_off, ct_len;    // k_fast_nms column masks: byte offset of this level's three arrays (in-region, left / right neighbour in the
+                           // same cell; entry x + 4 for ROI column x) in the mask table, bytes per array (multiple of 4)
+    int rt_off;            // k_fast_nms detection-cell row of ROI row y at rt_off + y + 1 of the row table (int16, -1 = outside)
     int bm_off, bm_pitch;  // NMS-survivor bitmap of this level: byte offset in the frame's bitmap block, row pitch in bytes (bit i = ROI x 16+i)
 };
 
@@ -123,6 +126,8 @@ struct orb_ctx {
     std::vector<CellGeom> cells;
     std::vector<Tile> tiles_fast, tiles_blur;
     std::vector<int2> xtab, ytab;
+    std::vector<uint8_t> fast_coltab;      // per level: in-region / left / right byte masks of every column (k_fast_nms)
+    std::vector<int16_t> fast_rowtab;      // per level: detection-cell row of every row
     int rs_box_w[ORB_MAX_LEVELS] = { 0 }, rs_box_h[ORB_MAX_LEVELS] = { 0 };   // k_resize TMA box (source footprint of one output tile)
     int rs_tile_w[ORB_MAX_LEVELS] = { 0 }, rs_rows[ORB_MAX_LEVELS] = { 0 };   // k_resize tile width / rows per thread
 
@@ -131,6 +136,8 @@ struct orb_ctx {
     CellGeom* d_cells = nullptr;
     Tile* d_tiles_fast = nullptr; Tile* d_tiles_blur = nullptr;
     int2* d_xtab = nullptr; int2* d_ytab = nullptr;
+    uint8_t* d_fast_coltab = nullptr; int16_t* d_fast_rowtab = nullptr;
+    size_t cap_fast_coltab = 0, cap_fast_rowtab = 0;
     size_t cap_cells = 0, cap_tiles_fast = 0, cap_tiles_blur = 0, cap_xtab = 0, cap_ytab = 0;
     int* d_status = nullptr;          // error flag raised by kernels
     // two independent sets of work buffers: two chunks (or the two halves of one device batch) run on two streams

@@ -84,7 +84,7 @@ int orb_build_plan(orb_ctx* c, int w, int h)
     memset(&P, 0, sizeof(P));
     P.nlevels = c->nlevels; P.w = w; P.h = h;
     P.fast_th = c->fast_th; P.th_lo = std::min(c->fast_th, 7); P.harris = c->score_type == ORB_HARRIS_SCORE; P.desc_fma = c->desc_fma;
-    c->cells.clear(); c->tiles_fast.clear(); c->tiles_blur.clear(); c->xtab.clear(); c->ytab.clear();
+    c->cells.clear(); c->tiles_fast.clear(); c->tiles_blur.clear(); c->xtab.clear(); c->ytab.clear(); c->fast_coltab.clear(); c->fast_rowtab.clear();
 
     int off = 0, cand = 0, lvl = 0, kp = 0, border = 0, bm = 0;
     const float imageRatio = (float)w / h;                                   // :527
@@ -191,6 +191,29 @@ int orb_build_plan(orb_ctx* c, int w, int h)
         lvl += L.lvl_cap;
         L.kp_base = kp;
         kp += L.nDesired;
+        {
+            // k_fast_nms tables: which detection cell a column / row belongs to (-1: outside [16, w-16) resp. [16, h-16); the last cell
+            // takes the remainder, :560-572,:591-596), as byte masks per column (in region, left / right neighbour in the same cell) and
+            // as a cell row per row.  A tile reads 72 columns from x0 - 4 and 130 rows from y0 - 1, hence the margins.
+            auto cell_of = [](int v, int size, int cell, int n) {
+                if (v < ORB_EDGE || cell <= 0) return -1;                                 // cell <= 0: level no larger than its 16-px margins, no tiles
+                int cc = (v - ORB_EDGE) / cell;
+                if (cc >= n - 1) { cc = n - 1; if (v >= size - ORB_EDGE) cc = -1; }     // degenerate grids: an inner cell may reach past size - 16
+                return cc;
+            };
+            const int nx = (L.w + ORB_TILE_W + 16 + 3) & ~3, ny = L.h + ORB_TILE_H + 8;
+            L.ct_off = (int)c->fast_coltab.size(); L.ct_len = nx;
+            c->fast_coltab.resize(c->fast_coltab.size() + 3 * (size_t)nx, 0);
+            uint8_t* ct = c->fast_coltab.data() + L.ct_off;
+            for (int i = 0; i < nx; i++) {
+                const int x = i - 4, cc = cell_of(x, L.w, L.cellW, L.cols);
+                ct[i] = cc >= 0 ? 0xff : 0;
+                ct[nx + i] = (cc >= 0 && cell_of(x - 1, L.w, L.cellW, L.cols) == cc) ? 0xff : 0;
+                ct[2 * nx + i] = (cc >= 0 && cell_of(x + 1, L.w, L.cellW, L.cols) == cc) ? 0xff : 0;
+            }
+            L.rt_off = (int)c->fast_rowtab.size();
+            for (int i = 0; i < ny; i++) c->fast_rowtab.push_back((int16_t)cell_of(i - 1, L.h, L.cellH, L.rows));
+        }
         for (int y = minB; y < L.yend; y += ORB_TILE_H)
             for (int x = minB; x < L.xend; x += ORB_TILE_W) c->tiles_fast.push_back(Tile{ l, x, y, 0 });
         for (int y = 0; y < L.h; y += ORB_BLUR_TILE_H)
