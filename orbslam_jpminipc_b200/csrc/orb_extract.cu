@@ -453,8 +453,12 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
 
         // ---- corner strength: one task = 4 horizontally adjacent pixels ----
         // (score words 1 .. 4 nq; the two halo words of a row are one pixel each and have their own pass below)
-        for (int task = tid; task < nr * nwi; task += FAST_THREADS) {
-            const int r = (int)(((uint32_t)(task >> 2) * inv_nq) >> 20), g = task - r * nwi + 1;
+        // Full tiles (the common case) keep compile-time task counts, partly filled ones take the run-time form (both instantiated).
+        auto score_pass = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        const int ntask = FULL ? FS_H * (FT_W / 4) : nr * nwi;
+        for (int task = tid; task < ntask; task += FAST_THREADS) {
+            const int r = FULL ? task / (FT_W / 4) : (int)(((uint32_t)(task >> 2) * inv_nq) >> 20), g = task - r * (FULL ? FT_W / 4 : nwi) + 1;
             const uint32_t cm = reinterpret_cast<const uint32_t*>(m_in)[g];
             uint32_t outw = 0;
             if (cm != 0 && rowcell[r] >= 0) {
@@ -511,15 +515,15 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
         //      byte 3 of score word 0) and to the right (x0 + 16 nq, byte 0 of score word 4 nq + 1).  Scoring those two words like
         //      the others would spend 2 of 18 tasks per row on 2 useful pixels of 8; here one task scores the pair (left, right)
         //      of a row in the two 16-bit lanes: 1 task per row instead of 2, and with 2 pixels instead of 4. ----
-        for (int r = tid; r < nr; r += FAST_THREADS) {
-            const int gr = nwi + 1;
+        const int nrh = FULL ? FS_H : nr, gr = (FULL ? FT_W / 4 : nwi) + 1;
+        for (int r = tid; r < nrh; r += FAST_THREADS) {
             const uint32_t mL = m_in[3], mR = m_in[4 * gr];
             uint32_t sL = 0, sR = 0;
             if (rowcell[r] >= 0 && (mL | mR) != 0) {
                 const uint32_t* ip = img + r * FIW + 3;              // image words 3,4 hold columns x0-4 .. x0+3; words gr+2, gr+3 hold x0+16nq-4 .. +3
                 uint32_t a[7], b[7], c[7], d[7];
 #pragma unroll
-                for (int q = 0; q < 7; q++) { a[q] = ip[q * FIW]; b[q] = ip[q * FIW + 1]; c[q] = ip[q * FIW + nwi]; d[q] = ip[q * FIW + nwi + 1]; }
+                for (int q = 0; q < 7; q++) { a[q] = ip[q * FIW]; b[q] = ip[q * FIW + 1]; c[q] = ip[q * FIW + gr - 1]; d[q] = ip[q * FIW + gr]; }
                 // sample (dx, row q) of both pixels, each duplicated into its 16-bit lane: left pixel = byte 3 of a[], right = byte 0 of d[]
 #define HP(q, dx) __byte_perm((dx) <= 0 ? a[q] : b[q], (dx) < 0 ? c[q] : d[q],                                               \
                               (((dx) <= 0 ? 3 + (dx) : (dx) - 1) * 0x11) | ((4 + ((dx) < 0 ? 4 + (dx) : (dx))) * 0x1100))
@@ -541,14 +545,20 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
             }
             sc[r * FSW] = sL << 24; sc[r * FSW + gr] = sR;
         }
+        };
+        const bool full = vw == FT_W && nr == FS_H;
+        if (full) score_pass(std::true_type{}); else score_pass(std::false_type{});
         __syncthreads();
 
         // ---- NMS restricted to the pixel's own cell: one task = 16 output pixels (four words): one 128-bit store
         //      of responses to the score map and one 16-bit store to the survivor bitmap ----
         uint8_t* out = nms + (size_t)f * fbytes + L.plane_off;
         uint8_t* bm = bitmap + (size_t)f * plan->bm_total + L.bm_off;
-        for (int task = tid; task < vh * nq; task += FAST_THREADS) {
-            const int ro = (int)(((uint32_t)task * inv_nq) >> 20), q4 = task - ro * nq;
+        auto nms_pass = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        const int ntask = FULL ? FT_H * (FT_W / 16) : vh * nq;
+        for (int task = tid; task < ntask; task += FAST_THREADS) {
+            const int ro = FULL ? task / (FT_W / 16) : (int)(((uint32_t)task * inv_nq) >> 20), q4 = task - ro * (FULL ? FT_W / 16 : nq);
             const int r = ro + 1;
             const int rc = rowcell[r];
             const bool up = rowcell[r - 1] == rc, dn = rowcell[r + 1] == rc;
@@ -600,6 +610,8 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
             // bitmap: bit i of row y (ROI) = ROI column 16+i ; tiles start at ROI x0 = 16 + 64k
             *reinterpret_cast<uint16_t*>(bm + (size_t)(t.y0 + ro - ORB_EDGE) * L.bm_pitch + ((t.x0 - ORB_EDGE) >> 3) + q4 * 2) = (uint16_t)bits;
         }
+        };
+        if (full && vh == FT_H) nms_pass(std::true_type{}); else nms_pass(std::false_type{});
         __syncthreads();       // masks / score tile are rewritten by the next item
         item = s_next[buf];
     }
