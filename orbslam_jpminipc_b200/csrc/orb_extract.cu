@@ -589,13 +589,16 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
                     const uint32_t mhi = __vimax3_u16x2(__vimax3_u16x2(hi16x2(nb[0]), hi16x2(nb[1]), hi16x2(nb[2])),
                                                         __vimax3_u16x2(hi16x2(nb[3]), hi16x2(nb[4]), hi16x2(nb[5])),
                                                         __vmaxu2(hi16x2(nb[6]), hi16x2(nb[7])));
-                    const uint32_t s0 = c & 0xff, s1 = (c >> 8) & 0xff, s2 = (c >> 16) & 0xff, s3 = c >> 24;
-                    // strictly greater than all 8 neighbours; s == 0 never passes
-                    // survivors: excess -> OpenCV's response (T - 1 = excess + th - 1, at most 254)
-                    if (s0 > (mlo & 0xffff)) { v |= s0 + th_m1; bits |= 1u << (4 * j); }
-                    if (s1 > (mlo >> 16)) { v |= (s1 + th_m1) << 8; bits |= 2u << (4 * j); }
-                    if (s2 > (mhi & 0xffff)) { v |= (s2 + th_m1) << 16; bits |= 4u << (4 * j); }
-                    if (s3 > (mhi >> 16)) { v |= (s3 + th_m1) << 24; bits |= 8u << (4 * j); }
+                    // strictly greater than all 8 neighbours (a score of 0 never passes), for the four pixels at once: in 16-bit lanes
+                    // score - min(score, neighbour max) is positive exactly for a survivor; adding 0x7fff moves that into the lane's
+                    // sign bit and one PRMT in sign-replication mode turns the four sign bits into byte masks.
+                    // survivors: excess -> OpenCV's response (T - 1 = excess + th - 1, at most 254, so the byte-wise add cannot carry)
+                    const uint32_t clo = lo16x2(c), chi = hi16x2(c);
+                    const uint32_t ylo = clo - __vminu2(clo, mlo) + 0x7fff7fffu, yhi = chi - __vminu2(chi, mhi) + 0x7fff7fffu;
+                    uint32_t m4;
+                    asm("prmt.b32 %0, %1, %2, 0xfdb9;" : "=r"(m4) : "r"(ylo), "r"(yhi));       // byte i = 0xff iff pixel i survives
+                    v = (c + th_m1 * 0x01010101u) & m4;
+                    bits |= (((m4 & 0x01010101u) * 0x01020408u) >> 24) << (4 * j);             // mask bits 0, 8, 16, 24 -> bits 0..3
                 }
                 vv[j] = v;
             }
