@@ -544,12 +544,12 @@ def run_gpu(args):
     achieved = bytes_per_launch / (stage[dom] / nlaunch * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum per frame from the committed `ncu --set full` capture
     # (profiles/r1l_ncu_full_summary.md, 64-frame launches), scaled to this run's launch size
-    ncu_mb_per_frame = {"k_fast_nms": (81.4 + 32.5) / 64, "k_blur": (85.7 + 36.7) / 64, "k_describe": (117.3 + 4.9) / 64,
-                        "k_cell_compact": (64.7 + 3.8) / 64, "k_select": 6.6 / 64, "k_level0": 23.2 / 64}
+    ncu_mb_per_frame = {"k_fast_nms": (81.4 + 33.0) / 64, "k_blur": (85.6 + 37.3) / 64, "k_describe": (117.3 + 5.2) / 64,
+                        "k_cell_compact": (64.7 + 4.3) / 64, "k_select": 6.6 / 64, "k_level0": 23.2 / 64}
     traffic = ncu_mb_per_frame[dom] * 1e6 * B / nlaunch if dom in ncu_mb_per_frame and W == 752 else None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                "traffic": traffic, "alu_pipe_pct_ncu": 88.2 if dom == "k_fast_nms" else None,
-                "note": "k_fast_nms is integer-ALU bound (ncu, profiles/r1l_ncu_full_summary.md: ALU pipe 88.2 % of peak, DRAM 5.0 %); the HBM fraction is the required yardstick, not its limiter", "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                "traffic": traffic, "alu_pipe_pct_ncu": 87.7 if dom == "k_fast_nms" else None,
+                "note": "k_fast_nms is integer-ALU bound (ncu, profiles/r1l_ncu_full_summary.md: ALU pipe 87.7 % of peak, DRAM 5.3 %); the HBM fraction is the required yardstick, not its limiter", "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                 "kernel_ms_per_launch": stage[dom] / nlaunch, "stage_ms_per_step": stage, "profiled_ms_per_step": ms_profiled / args.steps,
                 "pipeline_bytes_per_frame": algorithmic_bytes_per_frame(W, H, nkp),
                 "pipeline_frac": (value / world) * algorithmic_bytes_per_frame(W, H, nkp) / (hbm * 1e9)}
