@@ -74,6 +74,32 @@ def test_vs_oracle_shapes(pkg, po, shape, nf):
     ex.close()
 
 
+@pytest.mark.parametrize("h,w", [(161, 225), (162, 239), (287, 240), (289, 241), (300, 257), (193, 272), (416, 287), (290, 352)])
+def test_partly_filled_edge_tiles(pkg, po, h, w):
+    """k_fast_nms / k_blur / k_resize walk only the filled part of a tile on the right / bottom edge of a level: widths with
+    (w - 32) mod 64 in {1, 15, 16, 17, 33, 48, 63, 0} and heights with (h - 32) mod 128 in {1, 2, 127, 129, ...} at level 0 (the
+    other levels add their own residues), dense and sparse frames through one context so that stale tile contents would show."""
+    from orbslam_jpminipc_b200.synth import synth_frame
+    rng = np.random.default_rng(h * 1000 + w)
+    frames = [synth_frame(h, w, 500 + h), rng.integers(0, 256, (h, w), dtype=np.uint8), synth_frame(h, w, 501 + w, quadrants=False)]
+    ex = pkg.ORBextractor(400, 1.2, 8, 1, 20, max_width=w, max_height=h, max_batch=3)
+    orc = po.OracleExtractor(400, 1.2, 8, 1, 20)
+    try:
+        ref = [orc(f) for f in frames]
+    except RuntimeError:
+        with pytest.raises(pkg.OrbError):
+            ex(frames[0])
+        ex.close()
+        return
+    for f, (rk, rd) in zip(frames, ref):
+        kps, desc = ex(f)
+        _same(kps, desc, rk, rd, (h, w))
+    out = ex.extract_batch(np.stack(frames))
+    for (kps, desc), (rk, rd) in zip(out, ref):
+        _same(kps, desc, rk, rd, (h, w, "batch"))
+    ex.close()
+
+
 @pytest.mark.parametrize("h,w,nf", [(97, 203, 150), (120, 160, 100), (90, 300, 200), (64, 64, 60), (200, 200, 50), (150, 170, 130)])
 def test_degenerate_geometry_agrees_with_oracle(pkg, po, h, w, nf):
     """Shapes on which the reference itself throws / divides by zero: product and oracle must agree on the verdict."""
