@@ -459,7 +459,7 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
         const int ntask = FULL ? FS_H * (FT_W / 4) : nr * nwi;
         for (int task = tid; task < ntask; task += FAST_THREADS) {
             const int r = FULL ? task / (FT_W / 4) : (int)(((uint32_t)(task >> 2) * inv_nq) >> 20), g = task - r * (FULL ? FT_W / 4 : nwi) + 1;
-            const uint32_t cm = reinterpret_cast<const uint32_t*>(m_in)[g];
+            const uint32_t cm = FULL ? 0xffffffffu : reinterpret_cast<const uint32_t*>(m_in)[g];   // every column of a full tile is a detection column
             uint32_t outw = 0;
             if (cm != 0 && rowcell[r] >= 0) {
                 const uint32_t* ip = img + r * FIW + g + 2;          // rows r..r+6 (y-3..y+3), words of cols x-4..x+7
