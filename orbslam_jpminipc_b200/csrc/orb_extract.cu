@@ -1142,8 +1142,9 @@ k_blur(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ blurred, size_t
 #pragma unroll
                 for (int q = 0; q < 10; q++) R[q] = rp[q * (BT_W / 4)];
                 const int x = t.x0 + cg * 4;
+                uint8_t* o = out + (size_t)(t.y0 + rg * 4 + ORB_EDGE) * Lstride + x + ORB_EDGE;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
+                for (int q = 0; q < 4; q++, o += Lstride) {
                     const int y = t.y0 + rg * 4 + q;
                     uint32_t iv[4];
 #pragma unroll
@@ -1159,15 +1160,15 @@ k_blur(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ blurred, size_t
                         iv[e] = __float_as_uint(__fadd_rn(s, 12582912.0f));
                     }
                     const uint32_t w = __byte_perm(__byte_perm(iv[0], iv[1], 0x0040), __byte_perm(iv[2], iv[3], 0x0040), 0x5410);
-                    if (y < Lh && x < Lw) {    // exactly the ROI bytes: the frame of the blurred buffer holds the un-blurred reflection
-                        uint8_t* o = out + (size_t)(y + ORB_EDGE) * Lstride + x + ORB_EDGE;
+                    if (FULL) *reinterpret_cast<uint32_t*>(o) = w;       // a full tile lies inside the ROI
+                    else if (y < Lh && x < Lw) {    // exactly the ROI bytes: the frame of the blurred buffer holds the un-blurred reflection
                         if (x + 3 < Lw) *reinterpret_cast<uint32_t*>(o) = w;
                         else for (int e = 0; x + e < Lw; e++) o[e] = (uint8_t)(w >> (8 * e));
                     }
                 }
             }
         };
-        if (ncg == BT_W / 4 && nrg == BT_H / 4) {
+        if (Lw - t.x0 >= BT_W && Lh - t.y0 >= BT_H) {
             row_pass(std::true_type{});
             __syncthreads();
             col_pass(std::true_type{});
