@@ -572,6 +572,30 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
                 uint32_t v = 0;
                 if (c) {
                     const uint32_t ml = reinterpret_cast<const uint32_t*>(m_l)[g], mr = reinterpret_cast<const uint32_t*>(m_r)[g];
+#ifdef ORB_NMS_HIBYTE
+                    // EXPERIMENTAL, off by default and not yet timed on a GPU (host model: tests/test_kernel_arith_models.py,
+                    // test_nms_high_byte_lanes_model).  A 16-bit unsigned max looks at a lane's low byte only on ties of the high
+                    // byte, so a lane may carry its pixel in the HIGH byte and anything below it.  The score word itself is then the
+                    // lane pair of pixels (1, 3), `word << 8` that of pixels (0, 2), and every neighbour is a shift or funnel shift of
+                    // the nine words: no PRMT unpacking (16 per word in the form below).  For the strict comparison the lanes are
+                    // halved first (score << 7 against max << 7 | 0x7f) so that adding 0x7fff cannot carry into the next lane.
+                    const uint32_t pc = sp[-1], nc = sp[1];
+                    uint32_t ul = sp[-FSW - 1], uc = sp[-FSW], ur = sp[-FSW + 1], dl = sp[FSW - 1], dc = sp[FSW], dr = sp[FSW + 1];
+                    if (!up) { ul = 0u; uc = 0u; ur = 0u; }
+                    if (!dn) { dl = 0u; dc = 0u; dr = 0u; }
+                    const uint32_t c8 = c << 8, u8 = uc << 8, d8 = dc << 8;
+                    const uint32_t Lo = __vimax3_u16x2(c8, u8, d8) & ml;                                      // pixels 1, 3: left neighbours
+                    const uint32_t Ro = __vimax3_u16x2(__funnelshift_r(c, nc, 8), __funnelshift_r(uc, ur, 8), __funnelshift_r(dc, dr, 8)) & mr;
+                    const uint32_t Mo = __vimax3_u16x2(Lo, Ro, __vmaxu2(uc, dc));
+                    const uint32_t Le = __vimax3_u16x2(__funnelshift_r(pc, c, 16), __funnelshift_r(ul, uc, 16), __funnelshift_r(dl, dc, 16)) & (ml << 8);
+                    const uint32_t Re = __vimax3_u16x2(c, uc, dc) & (mr << 8);                                // pixels 0, 2: right neighbours
+                    const uint32_t Me = __vimax3_u16x2(Le, Re, __vmaxu2(u8, d8));
+                    const uint32_t ao = (c >> 1) & 0x7f807f80u, bo = ((Mo >> 1) | 0x007f007fu) & 0x7fff7fffu;
+                    const uint32_t ae = (c8 >> 1) & 0x7f807f80u, be = ((Me >> 1) | 0x007f007fu) & 0x7fff7fffu;
+                    const uint32_t yo = ao - __vminu2(ao, bo) + 0x7fff7fffu, ye = ae - __vminu2(ae, be) + 0x7fff7fffu;
+                    uint32_t m4;
+                    asm("prmt.b32 %0, %1, %2, 0xfbd9;" : "=r"(m4) : "r"(ye), "r"(yo));         // byte i = 0xff iff pixel i survives
+#else
                     uint32_t nb[8];
                     nb[0] = __funnelshift_r(sp[-1], c, 24) & ml;
                     nb[1] = __funnelshift_r(c, sp[1], 8) & mr;
@@ -597,6 +621,7 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
                     const uint32_t ylo = clo - __vminu2(clo, mlo) + 0x7fff7fffu, yhi = chi - __vminu2(chi, mhi) + 0x7fff7fffu;
                     uint32_t m4;
                     asm("prmt.b32 %0, %1, %2, 0xfdb9;" : "=r"(m4) : "r"(ylo), "r"(yhi));       // byte i = 0xff iff pixel i survives
+#endif
                     v = (c + th_m1 * 0x01010101u) & m4;
                     bits |= (((m4 & 0x01010101u) * 0x01020408u) >> 24) << (4 * j);             // mask bits 0, 8, 16, 24 -> bits 0..3
                 }

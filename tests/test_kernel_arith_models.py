@@ -80,3 +80,71 @@ def test_excess_epilogue_equals_strength_minus_threshold():
         qb = np.maximum(mn + nvp, 0)                            # VIADDMNMX.RELU
         got = np.maximum((-mx - 1) + vm1, qb)                   # ~Mx = -Mx - 1 in a 16-bit lane
         assert np.array_equal(got, want)
+
+
+# ---- high-byte-lane NMS (the ORB_NMS_HIBYTE variant of k_fast_nms, compiled out by default) ---------------------------------
+# numpy restatement of the exact lane operations of that variant, compared with the plain definition of the masked strict
+# 8-neighbour test on tie-heavy random score words.
+U=np.uint32
+def lanes(x): return (x & U(0xffff)), (x >> U(16))
+def pack(lo,hi): return (lo | (hi << U(16))).astype(U)
+def vmax(a,b):
+    al,ah=lanes(a); bl,bh=lanes(b); return pack(np.maximum(al,bl), np.maximum(ah,bh))
+def vmin(a,b):
+    al,ah=lanes(a); bl,bh=lanes(b); return pack(np.minimum(al,bl), np.minimum(ah,bh))
+def vmax3(a,b,c): return vmax(vmax(a,b),c)
+def funnel_r(lo,hi,sh):   # __funnelshift_r(lo, hi, sh): (hi:lo) >> sh, low 32 bits
+    v=(hi.astype(np.uint64)<<np.uint64(32))|lo.astype(np.uint64)
+    return ((v>>np.uint64(sh)) & np.uint64(0xffffffff)).astype(U)
+def prmt_sign(a,b,sel):
+    src=[(a>>U(8*i))&U(0xff) for i in range(4)]+[(b>>U(8*i))&U(0xff) for i in range(4)]
+    out=np.zeros_like(a)
+    for i in range(4):
+        n=(sel>>(4*i))&0xf
+        byte=src[n&7]
+        if n&8: byte=np.where(byte&U(0x80),U(0xff),U(0)).astype(U)
+        out|=byte<<U(8*i)
+    return out
+def hibyte_nms(pc,c,nc,ul,uc,ur,dl,dc,dr,ml,mr,up,dn):
+    z=U(0)
+    ul=np.where(up,ul,z); uc=np.where(up,uc,z); ur=np.where(up,ur,z)
+    dl=np.where(dn,dl,z); dc=np.where(dn,dc,z); dr=np.where(dn,dr,z)
+    c8=(c<<U(8)); u8=(uc<<U(8)); d8=(dc<<U(8)); ml8=ml<<U(8); mr8=mr<<U(8)
+    Lo=vmax3(c8,u8,d8)&ml
+    Ro=vmax3(funnel_r(c,nc,8),funnel_r(uc,ur,8),funnel_r(dc,dr,8))&mr
+    Mo=vmax3(Lo,Ro,vmax(uc,dc))
+    Le=vmax3(funnel_r(pc,c,16),funnel_r(ul,uc,16),funnel_r(dl,dc,16))&ml8
+    Re=vmax3(c,uc,dc)&mr8
+    Me=vmax3(Le,Re,vmax(u8,d8))
+    ao=(c>>U(1))&U(0x7f807f80); bo=((Mo>>U(1))|U(0x007f007f))&U(0x7fff7fff)
+    ae=(c8>>U(1))&U(0x7f807f80); be=((Me>>U(1))|U(0x007f007f))&U(0x7fff7fff)
+    yo=(ao-vmin(ao,bo)+U(0x7fff7fff)).astype(U); ye=(ae-vmin(ae,be)+U(0x7fff7fff)).astype(U)
+    return prmt_sign(ye,yo,0xfbd9)
+def direct(pc,c,nc,ul,uc,ur,dl,dc,dr,ml,mr,up,dn):
+    def row(p,x,n):   # 12 bytes: p(4) x(4) n(4)
+        return np.stack([(w>>U(8*i))&U(0xff) for w in (p,x,n) for i in range(4)],-1).astype(np.int64)
+    R=row(pc,c,nc); Uu=row(ul,uc,ur)*up[...,None]; D=row(dl,dc,dr)*dn[...,None]
+    out=np.zeros_like(c)
+    for i in range(4):
+        k=4+i
+        l=((ml>>U(8*i))&U(1)).astype(np.int64); r=((mr>>U(8*i))&U(1)).astype(np.int64)
+        nb=np.stack([R[...,k-1]*l,R[...,k+1]*r,Uu[...,k],Uu[...,k-1]*l,Uu[...,k+1]*r,D[...,k],D[...,k-1]*l,D[...,k+1]*r],-1).max(-1)
+        out|=np.where(R[...,k]>nb,U(0xff),U(0)).astype(U)<<U(8*i)
+    return out
+
+
+def test_nms_high_byte_lanes_model():
+    rng = np.random.default_rng(0)
+    n = 100000
+    for trial in range(8):
+        def word(vals):
+            return (vals[:, 0] | (vals[:, 1] << U(8)) | (vals[:, 2] << U(16)) | (vals[:, 3] << U(24))).astype(U)
+        def score_word():      # tie-heavy small scores or the full byte range, 40 % zeros
+            b = rng.integers(0, 6 if trial % 2 else 256, (n, 4)).astype(U) * (rng.random((n, 4)) < 0.6)
+            return word(b.astype(U))
+        def mask_word():
+            return word(np.where(rng.random((n, 4)) < 0.85, 0xff, 0).astype(U))
+        W = [score_word() for _ in range(9)]
+        ml, mr = mask_word(), mask_word()
+        up, dn = rng.random(n) < 0.9, rng.random(n) < 0.9
+        assert np.array_equal(hibyte_nms(*W, ml, mr, up, dn), direct(*W, ml, mr, up, dn)), trial
