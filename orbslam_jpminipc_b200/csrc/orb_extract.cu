@@ -573,8 +573,8 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
                 if (c) {
                     const uint32_t ml = reinterpret_cast<const uint32_t*>(m_l)[g], mr = reinterpret_cast<const uint32_t*>(m_r)[g];
 #ifdef ORB_NMS_HIBYTE
-                    // EXPERIMENTAL, off by default and not yet timed on a GPU (host model: tests/test_kernel_arith_models.py,
-                    // test_nms_high_byte_lanes_model).  A 16-bit unsigned max looks at a lane's low byte only on ties of the high
+                    // EXPERIMENTAL, off by default: bit-exact on the GPU parity tests it was run on, not yet timed (host model:
+                    // tests/test_kernel_arith_models.py, test_nms_high_byte_lanes_model).  A 16-bit unsigned max looks at a lane's low byte only on ties of the high
                     // byte, so a lane may carry its pixel in the HIGH byte and anything below it.  The score word itself is then the
                     // lane pair of pixels (1, 3), `word << 8` that of pixels (0, 2), and every neighbour is a shift or funnel shift of
                     // the nine words: no PRMT unpacking (16 per word in the form below).  For the strict comparison the lanes are
