@@ -90,7 +90,12 @@ int orb_extract_batch_async(orb_ctx*, const uint8_t* images, int nimg, int width
                             orb_keypoint* kps, uint8_t* desc, int cap, int32_t* counts, long long* ticket);
 int orb_wait(orb_ctx*, long long ticket);
 
-/* device pointers only, nimg <= max_batch, asynchronous on `stream` (a cudaStream_t). */
+/* device pointers only, nimg <= max_batch, asynchronous on `stream` (a cudaStream_t).  Truncation contract of the device-output
+ * form (nothing is read back, so no status can report it): d_counts[i] is the number of keypoints the frame HAS; when it exceeds
+ * cap only the first cap rows of its slot were written, so a consumer reads min(d_counts[i], cap) rows.  (The host-output calls
+ * clamp every counts[i] to cap and return ORB_ERR_CAPACITY instead.)  cap >= orb_keypoint_capacity(ctx) never truncates.
+ * A context owns one set of work buffers: consecutive device calls on one context are ordered behind each other by an event even
+ * when they are given different streams. */
 int orb_extract_batch_device(orb_ctx*, const uint8_t* d_imgs, int nimg, int w, int h, int stride, size_t frame_pitch,
                              orb_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts, void* stream);
 /* kernels launched by the last orb_extract* call on this context (for bench accounting) */

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 thread_local std::string g_last_cuda_error;
 
@@ -232,7 +233,9 @@ orb_ctx* orb_create(int device, int nfeatures, float scale_factor, int nlevels, 
     c->score_type = score_type; c->fast_th = fast_th; c->max_w = max_w; c->max_h = max_h; c->max_batch = max_batch;
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (const char* e = getenv("ORB_GRAPH")) c->use_graph = atoi(e);
+#ifdef ORB_DEBUG                 // stage-skipping switch of tools/exposure.sh: only in a -DORB_DEBUG build, never in the shipped library
     if (const char* e = getenv("ORB_DEBUG_SKIP")) c->debug_skip = atoi(e);
+#endif
     if (const char* e = getenv("ORB_RESIZE_FLEX")) c->rs_flex_width = atoi(e) != 0;
     if (const char* e = getenv("ORB_RESIZE_ROWS")) c->rs_rows_pref = std::max(1, std::min(atoi(e), 32));
     if (const char* e = getenv("ORB_SELECT_SERIAL")) c->select_serial = atoi(e);
@@ -251,6 +254,14 @@ orb_ctx* orb_create(int device, int nfeatures, float scale_factor, int nlevels, 
     ok = ok && cudaEventCreateWithFlags(&c->ev_user, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&c->ev_half[0], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&c->ev_half[1], cudaEventDisableTiming) == cudaSuccess;
+    if (ok) {      // private stream-ordered pool that keeps its memory across synchronisations (k_knn2 partials of the *_device calls)
+        cudaMemPoolProps pp = {};
+        pp.allocType = cudaMemAllocationTypePinned; pp.handleTypes = cudaMemHandleTypeNone;
+        pp.location.type = cudaMemLocationTypeDevice; pp.location.id = device;
+        unsigned long long keep = ~0ull;
+        ok = cudaMemPoolCreate(&c->pool, &pp) == cudaSuccess &&
+             cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess;
+    }
     if (!ok) { orb_cuda_fail(cudaGetLastError(), "orb_create allocations"); orb_destroy(c); return nullptr; }
     return c;
 }
@@ -279,8 +290,14 @@ void orb_destroy(orb_ctx* c)
     if (c->ev_user) cudaEventDestroy(c->ev_user);
     for (cudaEvent_t e : c->ev_half) if (e) cudaEventDestroy(e);
     void* ptrs[] = { c->d_plan, c->d_cells, c->d_tiles_fast, c->d_tiles_blur, c->d_xtab, c->d_ytab, c->d_fast_coltab, c->d_fast_rowtab, c->d_status, c->d_src[0], c->d_src[1], c->d_kps[0],
-                     c->d_kps[1], c->d_desc[0], c->d_desc[1], c->d_counts[0], c->d_counts[1], c->d_knn_part, c->d_match_scratch };
-    if (c->h_match_arena) cudaFreeHost(c->h_match_arena);
+                     c->d_kps[1], c->d_desc[0], c->d_desc[1], c->d_counts[0], c->d_counts[1] };
+    for (int i = 0; i < c->nlanes; i++) {
+        MatchLane& L = c->lanes[i];
+        if (L.d_scratch) cudaFree(L.d_scratch);
+        if (L.h_arena) cudaFreeHost(L.h_arena);
+        if (L.stream) cudaStreamDestroy(L.stream);
+    }
+    if (c->pool) cudaMemPoolDestroy(c->pool);
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
@@ -296,6 +313,7 @@ int orb_nlevels(const orb_ctx* c) { return c ? c->nlevels : 0; }
 int orb_set_descriptor_fma(orb_ctx* c, int on)
 {
     if (!c) return ORB_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> ex_lock(c->ex_mu);
     if ((on != 0) != (c->desc_fma != 0)) { c->desc_fma = on != 0; c->plan_valid = false; }     // the plan carries the flag to the device
     return ORB_OK;
 }
@@ -314,6 +332,7 @@ int orb_extract_batch_device(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w,
 {
     if (!c || !d_kps || !d_desc || !d_counts || cap < 1 || nimg < 0) return ORB_ERR_INVALID;
     if (nimg == 0) return ORB_OK;
+    std::lock_guard<std::recursive_mutex> ex_lock(c->ex_mu);
     cudaStream_t us = (cudaStream_t)stream;
     if (!d_imgs || w <= 0 || h <= 0) {              // empty image: no keypoints (src/ORBextractor.cc:721-722)
         ORB_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * nimg, us));
@@ -326,6 +345,9 @@ int orb_extract_batch_device(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w,
     int rc = prepare(c, w, h);
     if (rc != ORB_OK) return rc;
     if (!c->ev_dev_done) ORB_CUDA(cudaEventCreateWithFlags(&c->ev_dev_done, cudaEventDisableTiming));
+    // a context owns ONE set of pyramid / candidate buffers: a second device call, possibly on another caller stream, is ordered
+    // behind the previous one instead of racing it on those buffers (same-stream callers pay one no-op wait)
+    if (c->dev_call_pending) ORB_CUDA(cudaStreamWaitEvent(us, c->ev_dev_done, 0));
     struct Done { orb_ctx* c; cudaStream_t s; ~Done() { if (cudaEventRecord(c->ev_dev_done, s) == cudaSuccess) c->dev_call_pending = true; } } done{ c, us };
     // Optional (ORB_SPLIT_DEVICE=1): two halves on the two internal streams, forked from / joined to the caller's
     // stream.  Measured on B200 at 256 frames: 3.19 ms split vs 3.03 ms unsplit, so it is off by default; the
@@ -356,7 +378,9 @@ int orb_extract_batch_device(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w,
 // Completion of ticket `seq`: wait for its event, surface kernel-side errors, clamp counts like the synchronous call.
 int orb_wait(orb_ctx* c, long long seq)
 {
-    if (!c || seq < 0 || seq >= c->next_seq) return ORB_ERR_INVALID;
+    if (!c) return ORB_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> ex_lock(c->ex_mu);
+    if (seq < 0 || seq >= c->next_seq) return ORB_ERR_INVALID;
     if (seq <= c->waited_seq && seq + orb_ctx::NTICKETS < c->next_seq) return ORB_OK;     // record recycled: long complete
     orb_ctx::Ticket& t = c->tickets[seq % orb_ctx::NTICKETS];
     if (t.seq != seq) return ORB_OK;                                                       // recycled by a later call
@@ -370,8 +394,9 @@ int orb_wait(orb_ctx* c, long long seq)
         ORB_CUDA(cudaMemset(c->d_status, 0, sizeof(int)));
         return st;
     }
-    if (t.host_out) for (int i = 0; i < t.nimg; i++) if (t.counts[i] > t.cap) { t.counts[i] = t.cap; return ORB_ERR_CAPACITY; }
-    return ORB_OK;
+    int rc = ORB_OK;                  // every entry is clamped before the error is reported: a caller that reads counts[i] rows stays inside its slots
+    if (t.host_out) for (int i = 0; i < t.nimg; i++) if (t.counts[i] > t.cap) { t.counts[i] = t.cap; rc = ORB_ERR_CAPACITY; }
+    return rc;
 }
 
 // Enqueue one host- or device-buffer batch without waiting for it.  Chunks alternate between the two work sets / streams and keep
@@ -382,6 +407,7 @@ int orb_extract_batch_async(orb_ctx* c, const uint8_t* imgs, int nimg, int w, in
 {
     if (!c || !kps || !desc || !counts || !ticket || cap < 1 || nimg < 0) return ORB_ERR_INVALID;
     *ticket = -1;
+    std::lock_guard<std::recursive_mutex> ex_lock(c->ex_mu);
     ORB_CUDA(cudaSetDevice(c->device));
     const bool dev_in = imgs && is_device_ptr(imgs), dev_out = is_device_ptr(kps);
     if (dev_out != is_device_ptr(desc) || dev_out != is_device_ptr(counts)) return ORB_ERR_INVALID;
@@ -512,6 +538,7 @@ const char* orb_profile_stage_name(int i)
 int orb_profile_read(orb_ctx* c, double* ms, int* ncalls)
 {
     if (!c || !ms || !ncalls) return ORB_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> ex_lock(c->ex_mu);
     ORB_CUDA(cudaSetDevice(c->device));
     ORB_CUDA(cudaDeviceSynchronize());
     for (int i = 0; i < ORB_NSTAGES; i++) ms[i] = 0;
@@ -531,7 +558,9 @@ int orb_profile_read(orb_ctx* c, double* ms, int* ncalls)
 
 int orb_debug_level_info(orb_ctx* c, int frame, int level, int32_t* info)
 {
-    if (!c || !c->plan_valid || level < 0 || level >= c->plan.nlevels || frame < 0 || frame >= c->last_n0 + c->last_n1) return ORB_ERR_INVALID;
+    if (!c) return ORB_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> ex_lock(c->ex_mu);
+    if (!c->plan_valid || level < 0 || level >= c->plan.nlevels || frame < 0 || frame >= c->last_n0 + c->last_n1) return ORB_ERR_INVALID;
     const LevelGeom& L = c->plan.L[level];
     const WorkSet& W = c->ws[frame < c->last_n0 ? 0 : 1];
     if (frame >= c->last_n0) frame -= c->last_n0;
@@ -546,7 +575,9 @@ int orb_debug_level_info(orb_ctx* c, int frame, int level, int32_t* info)
 
 int orb_debug_level_plane(orb_ctx* c, int frame, int level, int which, uint8_t* out, size_t out_bytes)
 {
-    if (!c || !c->plan_valid || level < 0 || level >= c->plan.nlevels || frame < 0 || frame >= c->last_n0 + c->last_n1) return ORB_ERR_INVALID;
+    if (!c) return ORB_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> ex_lock(c->ex_mu);
+    if (!c->plan_valid || level < 0 || level >= c->plan.nlevels || frame < 0 || frame >= c->last_n0 + c->last_n1) return ORB_ERR_INVALID;
     const LevelGeom& L = c->plan.L[level];
     const WorkSet& W = c->ws[frame < c->last_n0 ? 0 : 1];
     if (frame >= c->last_n0) frame -= c->last_n0;
@@ -572,26 +603,56 @@ int orb_descriptor_distance(const uint8_t* a, const uint8_t* b)
     return d;
 }
 
-// scratch for host-pointer matcher calls
-static int match_scratch(orb_ctx* c, size_t bytes, size_t arena_bytes = 0)
+} // extern "C"
+
+// ---- matcher lanes (orb_internal.h): per-call stream + scratch, so that Tracking / LocalMapping / LoopClosing threads may share a context ----
+LaneGuard::LaneGuard(orb_ctx* ctx) : c(ctx), lane(nullptr)
 {
-    if (arena_bytes > c->match_arena_bytes || !c->h_match_arena) {
-        ORB_CUDA(cudaDeviceSynchronize());
-        if (c->h_match_arena) cudaFreeHost(c->h_match_arena);
-        c->h_match_arena = nullptr; c->match_arena_bytes = 0;
-        const size_t want = std::max<size_t>(arena_bytes, 1 << 20);
-        ORB_CUDA(cudaMallocHost((void**)&c->h_match_arena, want));
-        c->match_arena_bytes = want;
+    std::unique_lock<std::mutex> lk(c->lane_mu);
+    for (;;) {
+        for (int i = 0; i < c->nlanes; i++) if (!c->lanes[i].busy) { lane = &c->lanes[i]; lane->busy = true; return; }
+        if (c->nlanes < orb_ctx::MAX_LANES) {
+            MatchLane& L = c->lanes[c->nlanes];
+            if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) {
+                orb_cuda_fail(cudaGetLastError(), "matcher lane stream");
+                return;
+            }
+            c->nlanes++;
+            L.busy = true; lane = &L;
+            return;
+        }
+        c->lane_cv.wait(lk);
     }
-    if (bytes <= c->match_scratch_bytes && c->d_match_scratch) return ORB_OK;
-    ORB_CUDA(cudaDeviceSynchronize());
-    if (c->d_match_scratch) cudaFree(c->d_match_scratch);
-    c->d_match_scratch = nullptr; c->match_scratch_bytes = 0;
-    ORB_CUDA(cudaMalloc(&c->d_match_scratch, bytes));
-    c->match_scratch_bytes = bytes;
+}
+LaneGuard::~LaneGuard()
+{
+    if (!lane) return;
+    { std::lock_guard<std::mutex> lk(c->lane_mu); lane->busy = false; }
+    c->lane_cv.notify_one();
+}
+
+int orb_lane_scratch(MatchLane* L, size_t bytes, size_t arena_bytes)
+{
+    if (arena_bytes > L->arena_bytes || !L->h_arena) {
+        ORB_CUDA(cudaStreamSynchronize(L->stream));          // the lane is ours: nothing else uses its buffers
+        if (L->h_arena) cudaFreeHost(L->h_arena);
+        L->h_arena = nullptr; L->arena_bytes = 0;
+        const size_t want = std::max<size_t>(arena_bytes, 1 << 20);
+        ORB_CUDA(cudaMallocHost((void**)&L->h_arena, want));
+        L->arena_bytes = want;
+    }
+    if (bytes <= L->scratch_bytes && L->d_scratch) return ORB_OK;
+    ORB_CUDA(cudaStreamSynchronize(L->stream));
+    if (L->d_scratch) cudaFree(L->d_scratch);
+    L->d_scratch = nullptr; L->scratch_bytes = 0;
+    const size_t want = std::max<size_t>(bytes + bytes / 4, 1 << 20);     // head room: the next slightly larger frame does not reallocate
+    ORB_CUDA(cudaMalloc(&L->d_scratch, want));
+    L->scratch_bytes = want;
     return ORB_OK;
 }
 static inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+extern "C" {
 
 int orb_hamming_knn2_device(orb_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_db, int64_t ndb, int npairs,
                             int32_t idx_base, int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, void* stream)
@@ -611,11 +672,13 @@ int orb_hamming_knn2(orb_ctx* c, const uint8_t* q, int nq, const uint8_t* db, in
     if (nq == 0) return ORB_OK;
     ORB_CUDA(cudaSetDevice(c->device));
     const bool dq = is_device_ptr(q), ddb = is_device_ptr(db), dout = is_device_ptr(idx1);
-    cudaStream_t s = c->streams[0];
+    LaneGuard lg(c);
+    if (!lg.lane) return ORB_ERR_CUDA;
+    cudaStream_t s = lg.lane->stream;
     const size_t qb = al256((size_t)nq * 32), dbb = al256((size_t)ndb * 32), ob = al256((size_t)nq * 4);
-    int rc = match_scratch(c, (dq ? 0 : qb) + (ddb ? 0 : dbb) + (dout ? 0 : 3 * ob) + 256);
+    int rc = orb_lane_scratch(lg.lane, (dq ? 0 : qb) + (ddb ? 0 : dbb) + (dout ? 0 : 3 * ob) + 256);
     if (rc) return rc;
-    uint8_t* p = (uint8_t*)c->d_match_scratch;
+    uint8_t* p = (uint8_t*)lg.lane->d_scratch;
     const uint8_t* d_q = q; const uint8_t* d_db = db;
     if (!dq) { ORB_CUDA(cudaMemcpyAsync(p, q, (size_t)nq * 32, cudaMemcpyHostToDevice, s)); d_q = p; p += qb; }
     if (!ddb) { if (ndb) ORB_CUDA(cudaMemcpyAsync(p, db, (size_t)ndb * 32, cudaMemcpyHostToDevice, s)); d_db = p; p += dbb; }
@@ -649,11 +712,13 @@ int orb_match_ratio(orb_ctx* c, const int32_t* idx1, const int32_t* d1, const in
     if (nq == 0) return ORB_OK;
     ORB_CUDA(cudaSetDevice(c->device));
     const bool din = is_device_ptr(idx1), dout = is_device_ptr(match);
-    cudaStream_t s = c->streams[0];
+    LaneGuard lg(c);
+    if (!lg.lane) return ORB_ERR_CUDA;
+    cudaStream_t s = lg.lane->stream;
     const size_t ob = al256((size_t)nq * 4);
-    int rc = match_scratch(c, 4 * ob + 256);
+    int rc = orb_lane_scratch(lg.lane, 4 * ob + 256);
     if (rc) return rc;
-    uint8_t* p = (uint8_t*)c->d_match_scratch;
+    uint8_t* p = (uint8_t*)lg.lane->d_scratch;
     int* d_cnt = (int*)p; p += 256;
     const int32_t *i0 = idx1, *i1 = d1, *i2 = d2;
     if (!din) {
@@ -677,7 +742,9 @@ int orb_frame_grid_build(orb_ctx* c, const orb_keypoint* kps, int n, int min_x, 
     if (!c || n < 0 || !cell_start || (n > 0 && (!kps || !cell_items)) || max_x <= min_x || max_y <= min_y) return ORB_ERR_INVALID;
     ORB_CUDA(cudaSetDevice(c->device));
     const int NC = ORB_GRID_COLS * ORB_GRID_ROWS + 1;
-    cudaStream_t s = c->streams[0];
+    LaneGuard lg(c);
+    if (!lg.lane) return ORB_ERR_CUDA;
+    cudaStream_t s = lg.lane->stream;
     if (is_device_ptr(cell_start)) {
         int rc = orb_launch_grid_build(kps, n, min_x, max_x, min_y, max_y, cell_start, cell_items, s);
         if (rc) return rc;
@@ -685,9 +752,9 @@ int orb_frame_grid_build(orb_ctx* c, const orb_keypoint* kps, int n, int min_x, 
         return ORB_OK;
     }
     const size_t kb = al256((size_t)std::max(n, 1) * sizeof(orb_keypoint)), sb = al256((size_t)NC * 4), ib = al256((size_t)std::max(n, 1) * 4);
-    int rc = match_scratch(c, kb + sb + ib);
+    int rc = orb_lane_scratch(lg.lane, kb + sb + ib);
     if (rc) return rc;
-    uint8_t* p = (uint8_t*)c->d_match_scratch;
+    uint8_t* p = (uint8_t*)lg.lane->d_scratch;
     if (n) ORB_CUDA(cudaMemcpyAsync(p, kps, (size_t)n * sizeof(orb_keypoint), cudaMemcpyHostToDevice, s));
     rc = orb_launch_grid_build((orb_keypoint*)p, n, min_x, max_x, min_y, max_y, (int32_t*)(p + kb), (int32_t*)(p + kb + sb), s);
     if (rc) return rc;
@@ -756,12 +823,14 @@ int orb_search_by_projection(orb_ctx* c, const orb_frame_view* cur, const orb_fr
     if (is_device_ptr(match_cur) != dev || is_device_ptr(last->kps) != dev) return ORB_ERR_INVALID;
     float T[16];
     if (is_device_ptr(Tcw16)) ORB_CUDA(cudaMemcpy(T, Tcw16, sizeof T, cudaMemcpyDeviceToHost)); else memcpy(T, Tcw16, sizeof T);
-    cudaStream_t s = c->streams[0];
+    LaneGuard lg(c);
+    if (!lg.lane) return ORB_ERR_CUDA;
+    cudaStream_t s = lg.lane->stream;
     const size_t work = orb_sbp_scratch_bytes(cur->n, last->n);
     const size_t in_bytes = dev ? 0 : frame_view_bytes(cur) + frame_view_bytes(last) + 2 * al256(last->n) + al256((size_t)last->n * 12) + al256((size_t)cur->n * 4);
-    int rc = match_scratch(c, 256 + in_bytes + work, 256 + in_bytes + 4096);
+    int rc = orb_lane_scratch(lg.lane, 256 + in_bytes + work, 256 + in_bytes + 4096);
     if (rc) return rc;
-    Bump b(c->d_match_scratch, c->h_match_arena, c->match_scratch_bytes);
+    Bump b(lg.lane->d_scratch, lg.lane->h_arena, lg.lane->scratch_bytes);
     int* d_result = (int*)b.take(8);
     orb_frame_view dc = *cur, dl = *last;
     if ((rc = stage_frame(b, dev, dc, true, s)) || (rc = stage_frame(b, dev, dl, false, s))) return rc;
@@ -794,13 +863,15 @@ int orb_search_window(orb_ctx* c, const orb_frame_view* target, const orb_window
     ORB_CUDA(cudaSetDevice(c->device));
     const bool dev = is_device_ptr(target->kps);
     if (is_device_ptr(match_target) != dev || is_device_ptr(q->desc) != dev) return ORB_ERR_INVALID;
-    cudaStream_t s = c->streams[0];
+    LaneGuard lg(c);
+    if (!lg.lane) return ORB_ERR_CUDA;
+    cudaStream_t s = lg.lane->stream;
     const size_t work = orb_sbp_scratch_bytes(target->n, q->n);
     const size_t nq = (size_t)q->n;
     const size_t in_bytes = dev ? 0 : frame_view_bytes(target) + al256(nq) + al256(nq * 32) + 7 * al256(nq * 4) + al256(nq * 12) + al256((size_t)target->n * 4);
-    int rc = match_scratch(c, 256 + in_bytes + work, 256 + in_bytes + 4096);
+    int rc = orb_lane_scratch(lg.lane, 256 + in_bytes + work, 256 + in_bytes + 4096);
     if (rc) return rc;
-    Bump b(c->d_match_scratch, c->h_match_arena, c->match_scratch_bytes);
+    Bump b(lg.lane->d_scratch, lg.lane->h_arena, lg.lane->scratch_bytes);
     int* d_result = (int*)b.take(8);
     orb_frame_view dt = *target;
     orb_window_query_set dq = *q;
@@ -836,7 +907,9 @@ int orb_search_for_initialization(orb_ctx* c, const orb_frame_view* f1, const or
     ORB_CUDA(cudaSetDevice(c->device));
     const bool dev = is_device_ptr(f1->kps);
     if (is_device_ptr(matches12) != dev || is_device_ptr(prev_matched) != dev) return ORB_ERR_INVALID;
-    cudaStream_t s = c->streams[0];
+    LaneGuard lg(c);
+    if (!lg.lane) return ORB_ERR_CUDA;
+    cudaStream_t s = lg.lane->stream;
     if (f2->n == 0) {                                       // no candidates anywhere: vnMatches12 = -1 (:601), prev untouched
         if (dev) ORB_CUDA(cudaMemsetAsync(matches12, 0xff, (size_t)f1->n * 4, s)); else for (int i = 0; i < f1->n; i++) matches12[i] = -1;
         if (dev) ORB_CUDA(cudaStreamSynchronize(s));
@@ -847,9 +920,9 @@ int orb_search_for_initialization(orb_ctx* c, const orb_frame_view* f1, const or
     const size_t n1 = (size_t)f1->n;
     const size_t work = orb_init_scratch_bytes(f1->n, f2->n);
     const size_t in_bytes = dev ? 0 : frame_view_bytes(f2) + al256(n1 * 28) + al256(n1 * 32) + al256(n1 * 8) + al256(n1 * 4);
-    int rc = match_scratch(c, 256 + in_bytes + work, 256 + in_bytes + 4096);
+    int rc = orb_lane_scratch(lg.lane, 256 + in_bytes + work, 256 + in_bytes + 4096);
     if (rc) return rc;
-    Bump b(c->d_match_scratch, c->h_match_arena, c->match_scratch_bytes);
+    Bump b(lg.lane->d_scratch, lg.lane->h_arena, lg.lane->scratch_bytes);
     int* d_result = (int*)b.take(8);
     orb_frame_view d1 = *f1, d2 = *f2;
     if ((rc = stage_frame(b, dev, d2, true, s))) return rc;
@@ -885,7 +958,9 @@ int orb_search_window_best(orb_ctx* c, const orb_frame_view* target, const orb_w
     ORB_CUDA(cudaSetDevice(c->device));
     const bool dev = is_device_ptr(best_idx);
     if (is_device_ptr(best_dist) != dev) return ORB_ERR_INVALID;
-    cudaStream_t s = c->streams[0];
+    LaneGuard lg(c);
+    if (!lg.lane) return ORB_ERR_CUDA;
+    cudaStream_t s = lg.lane->stream;
     if (target->n == 0) {                                   // no keypoints: nothing is ever in the radius
         if (dev) { ORB_CUDA(cudaMemsetAsync(best_idx, 0xff, (size_t)q->n * 4, s)); ORB_CUDA(cudaMemsetAsync(best_dist, 0x7f, (size_t)q->n * 4, s)); ORB_CUDA(cudaStreamSynchronize(s)); }
         else for (int i = 0; i < q->n; i++) { best_idx[i] = -1; best_dist[i] = INT_MAX; }
@@ -899,9 +974,9 @@ int orb_search_window_best(orb_ctx* c, const orb_frame_view* target, const orb_w
     const size_t work = orb_sbp_scratch_bytes(target->n, q->n);
     const size_t nq = (size_t)q->n;
     const size_t in_bytes = dev ? 0 : frame_view_bytes(target) + al256(nq) + al256(nq * 32) + 7 * al256(nq * 4) + al256(nq * 12) + 2 * al256(nq * 4);
-    int rc = match_scratch(c, 256 + in_bytes + work, 256 + in_bytes + 4096);
+    int rc = orb_lane_scratch(lg.lane, 256 + in_bytes + work, 256 + in_bytes + 4096);
     if (rc) return rc;
-    Bump b(c->d_match_scratch, c->h_match_arena, c->match_scratch_bytes);
+    Bump b(lg.lane->d_scratch, lg.lane->h_arena, lg.lane->scratch_bytes);
     int* d_result = (int*)b.take(8);
     orb_frame_view dt = *target;
     orb_window_query_set dq = *q;
@@ -935,7 +1010,9 @@ int orb_distinctive_descriptors(orb_ctx* c, const uint8_t* desc, const int32_t* 
     if (npoints == 0) return ORB_OK;
     if (!start || !best_idx || !best_median) return ORB_ERR_INVALID;
     ORB_CUDA(cudaSetDevice(c->device));
-    cudaStream_t s = c->streams[0];
+    LaneGuard lg(c);
+    if (!lg.lane) return ORB_ERR_CUDA;
+    cudaStream_t s = lg.lane->stream;
     const bool dev = is_device_ptr(start);
     if (is_device_ptr(best_idx) != dev || is_device_ptr(best_median) != dev) return ORB_ERR_INVALID;
     int total = 0;
@@ -949,9 +1026,9 @@ int orb_distinctive_descriptors(orb_ctx* c, const uint8_t* desc, const int32_t* 
     }
     for (int p = 0; p < npoints; p++) if (start[p + 1] < start[p]) return ORB_ERR_INVALID;
     const size_t P = (size_t)npoints, in_bytes = al256((size_t)total * 32 + 32) + al256((P + 1) * 4);
-    int rc = match_scratch(c, 256 + in_bytes + 2 * al256(P * 4), 256 + in_bytes);
+    int rc = orb_lane_scratch(lg.lane, 256 + in_bytes + 2 * al256(P * 4), 256 + in_bytes);
     if (rc) return rc;
-    Bump b(c->d_match_scratch, c->h_match_arena, c->match_scratch_bytes);
+    Bump b(lg.lane->d_scratch, lg.lane->h_arena, lg.lane->scratch_bytes);
     const uint8_t* d_desc = desc; const int32_t* d_start = start;
     if ((rc = stage_in(b, false, d_desc, (size_t)total * 32, s)) || (rc = stage_in(b, false, d_start, P + 1, s))) return rc;
     int32_t* d_bi = (int32_t*)b.take(P * 4);
@@ -980,7 +1057,9 @@ static int search_by_bow_impl(orb_ctx* c, const orb_featvec_view* kf_fv, const u
     ORB_CUDA(cudaSetDevice(c->device));
     const bool dev = is_device_ptr(f_desc);
     if (is_device_ptr(match12 ? (const void*)match12 : (const void*)match_f) != dev) return ORB_ERR_INVALID;
-    cudaStream_t s = c->streams[0];
+    LaneGuard lg(c);
+    if (!lg.lane) return ORB_ERR_CUDA;
+    cudaStream_t s = lg.lane->stream;
     // item totals live at start[nnodes]
     int kf_total = 0, f_total = 0;
     if (kf_fv->nnodes) { if (dev) ORB_CUDA(cudaMemcpy(&kf_total, kf_fv->start + kf_fv->nnodes, 4, cudaMemcpyDeviceToHost)); else kf_total = kf_fv->start[kf_fv->nnodes]; }
@@ -990,9 +1069,9 @@ static int search_by_bow_impl(orb_ctx* c, const orb_featvec_view* kf_fv, const u
     if (!dev) in_bytes = al256((size_t)n_kf * 32) + al256((size_t)n_kf * 28) + al256(n_kf) + al256((size_t)n_f * 32) + al256((size_t)n_f * 28) +
                          al256((size_t)n_f * 4) + al256(n_f) + al256((size_t)std::max(n_kf, 1) * 4) + 2 * al256((size_t)(kf_fv->nnodes + 1) * 4) + al256((size_t)kf_total * 4 + 4) +
                          2 * al256((size_t)(f_fv->nnodes + 1) * 4) + al256((size_t)f_total * 4 + 4) + 4096;
-    int rc = match_scratch(c, in_bytes + work + 256, in_bytes + 4096);
+    int rc = orb_lane_scratch(lg.lane, in_bytes + work + 256, in_bytes + 4096);
     if (rc) return rc;
-    Bump b(c->d_match_scratch, c->h_match_arena, c->match_scratch_bytes);
+    Bump b(lg.lane->d_scratch, lg.lane->h_arena, lg.lane->scratch_bytes);
     orb_featvec_view a = *kf_fv, f = *f_fv;
     static const int32_t zero_start[1] = { 0 };
     if (!a.start) a.start = zero_start;
@@ -1053,7 +1132,9 @@ int orb_search_for_triangulation(orb_ctx* c, const orb_featvec_view* fv1, const 
     ORB_CUDA(cudaSetDevice(c->device));
     const bool dev = is_device_ptr(desc1);
     if (is_device_ptr(match12) != dev) return ORB_ERR_INVALID;
-    cudaStream_t s = c->streams[0];
+    LaneGuard lg(c);
+    if (!lg.lane) return ORB_ERR_CUDA;
+    cudaStream_t s = lg.lane->stream;
     int t1 = 0, t2 = 0;
     if (fv1->nnodes) { if (dev) ORB_CUDA(cudaMemcpy(&t1, fv1->start + fv1->nnodes, 4, cudaMemcpyDeviceToHost)); else t1 = fv1->start[fv1->nnodes]; }
     if (fv2->nnodes) { if (dev) ORB_CUDA(cudaMemcpy(&t2, fv2->start + fv2->nnodes, 4, cudaMemcpyDeviceToHost)); else t2 = fv2->start[fv2->nnodes]; }
@@ -1062,9 +1143,9 @@ int orb_search_for_triangulation(orb_ctx* c, const orb_featvec_view* fv1, const 
     if (!dev) in_bytes = al256((size_t)n1 * 32) + al256((size_t)n1 * 28) + al256(n1) + al256((size_t)n2 * 32 + 32) + al256((size_t)n2 * 28 + 28) + al256(n2 + 1) +
                          2 * al256((size_t)(fv1->nnodes + 1) * 4) + al256((size_t)t1 * 4 + 4) + 2 * al256((size_t)(fv2->nnodes + 1) * 4) + al256((size_t)t2 * 4 + 4) +
                          al256((size_t)n1 * 4) + 4096;
-    int rc = match_scratch(c, in_bytes + work + 256, in_bytes + 4096);
+    int rc = orb_lane_scratch(lg.lane, in_bytes + work + 256, in_bytes + 4096);
     if (rc) return rc;
-    Bump b(c->d_match_scratch, c->h_match_arena, c->match_scratch_bytes);
+    Bump b(lg.lane->d_scratch, lg.lane->h_arena, lg.lane->scratch_bytes);
     orb_featvec_view a = *fv1, f = *fv2;
     static const int32_t zero_start[1] = { 0 };
     if (!dev) { if (!a.start) a.start = zero_start; if (!f.start) f.start = zero_start; }
@@ -1094,7 +1175,9 @@ int orb_measure_popc_peak(orb_ctx* c, double* gpopc_per_s)
 {
     if (!c || !gpopc_per_s) return ORB_ERR_INVALID;
     ORB_CUDA(cudaSetDevice(c->device));
-    return orb_launch_popc_bench(gpopc_per_s, c->streams[0]);
+    LaneGuard lg(c);
+    if (!lg.lane) return ORB_ERR_CUDA;
+    return orb_launch_popc_bench(gpopc_per_s, lg.lane->stream);
 }
 
 void* orb_host_alloc(size_t bytes)

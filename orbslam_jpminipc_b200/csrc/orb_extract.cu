@@ -1361,6 +1361,11 @@ int orb_upload_constants(const int* umax)
     return ORB_OK;
 }
 
+#ifdef ORB_DEBUG
+#define ORB_SKIP(bit) (c->debug_skip & (bit))
+#else
+#define ORB_SKIP(bit) 0
+#endif
 int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, int w, int h, int stride, size_t frame_pitch,
                        orb_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts, cudaStream_t s)
 {
@@ -1408,7 +1413,9 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
     // leaves most of the machine idle); k_describe joins both.
     const bool fork = !c->profile;
     auto launch_blur = [&](cudaStream_t bs) {
+#ifdef ORB_DEBUG
         if (c->debug_skip & 1) return;
+#endif
         const int total = P.ntiles_blur * nimg;
         const int grid = std::min(total, c->num_sms * c->blur_ctas);
         k_blur<<<grid, BLUR_THREADS, 0, bs>>>(W.tm_blur, W.d_blur, fb, c->d_plan, c->d_tiles_blur, P.ntiles_blur, total, W.d_counters + 2);
@@ -1446,7 +1453,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         else
             k_select_fast<true><<<dim3(P.nlevels, nimg), SEL_WARPS * 32, sel_smem, s>>>(c->d_plan, c->d_cells, W.d_cand, W.d_cand64, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status, sel_spare, fb);
         launches++;
-    } else if (!(c->debug_skip & 2)) {
+    } else if (!ORB_SKIP(2)) {
         if (c->select_serial)
             k_select<false><<<dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s>>>(c->d_plan, c->d_cells, W.d_cand, nullptr, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status);
         else
@@ -1461,7 +1468,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
     else launch_blur(s);
     mark();
     const int slots = std::min(cap, P.kp_cap);
-    if (!(c->debug_skip & 4)) k_describe<<<dim3((std::max(slots, 1) + 7) / 8, nimg), 256, 0, s>>>(W.d_planes, W.d_blur, fb, c->d_plan, W.d_lvl, W.d_nkept,
+    if (!ORB_SKIP(4)) k_describe<<<dim3((std::max(slots, 1) + 7) / 8, nimg), 256, 0, s>>>(W.d_planes, W.d_blur, fb, c->d_plan, W.d_lvl, W.d_nkept,
                                                                     d_kps, d_desc, cap, d_counts);
     mark();
     launches += 5;

@@ -114,7 +114,9 @@ int orb_cvt_gray(orb_ctx* c, const uint8_t* src, int nimg, int w, int h, size_t 
     if (nimg == 0 || w == 0 || h == 0) return ORB_OK;
     if (!src || !dst || stride < (size_t)w * 3 || dst_stride < (size_t)w) return ORB_ERR_INVALID;
     ORB_CUDA(cudaSetDevice(c->device));
-    cudaStream_t s = c->streams[0];
+    LaneGuard lg(c);
+    if (!lg.lane) return ORB_ERR_CUDA;
+    cudaStream_t s = lg.lane->stream;
     const bool dev_in = on_device(src), dev_out = on_device(dst);
     const size_t in_bytes = (size_t)(nimg - 1) * frame_pitch + (size_t)(h - 1) * stride + (size_t)w * 3;
     const size_t out_bytes = (size_t)(nimg - 1) * dst_pitch + (size_t)(h - 1) * dst_stride + (size_t)w;
@@ -160,7 +162,9 @@ int orb_undistort_keypoints(orb_ctx* c, const orb_keypoint* kps, int n, float fx
     int rc = make_camera(fx, fy, cx, cy, dist, ndist, C);
     if (rc) return rc;
     ORB_CUDA(cudaSetDevice(c->device));
-    cudaStream_t s = c->streams[0];
+    LaneGuard lg(c);
+    if (!lg.lane) return ORB_ERR_CUDA;
+    cudaStream_t s = lg.lane->stream;
     const bool dev = on_device(kps);
     if (on_device(kps_un) != dev) return ORB_ERR_INVALID;
     const size_t bytes = (size_t)n * sizeof(orb_keypoint);

@@ -3,6 +3,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/orb_b200.h"
@@ -110,8 +112,24 @@ struct WorkSet {
     int graph_launches = 0;
 };
 
+// One matcher "lane": stream + device scratch + pinned staging arena of ONE host-pointer matcher / vocabulary / frame-plumbing call.
+// The reference calls ORBmatcher from three threads (Tracking, LocalMapping, LoopClosing: src/main.cc:165,182,193), so a context
+// keeps a small pool of lanes; every such call borrows one for its duration (LaneGuard) and never touches the extraction buffers.
+struct MatchLane {
+    cudaStream_t stream = nullptr;
+    void* d_scratch = nullptr; size_t scratch_bytes = 0;
+    uint8_t* h_arena = nullptr; size_t arena_bytes = 0;     // pinned mirror of the input part of the scratch: one H2D per call
+    bool busy = false;
+};
+
 struct orb_ctx {
     int device = 0;
+    // extraction entry points are serialised per context (the reference object is not re-entrant either, include/ORBextractor.h:74-75)
+    std::recursive_mutex ex_mu;
+    static constexpr int MAX_LANES = 8;
+    std::mutex lane_mu; std::condition_variable lane_cv;
+    MatchLane lanes[MAX_LANES]; int nlanes = 0;
+    cudaMemPool_t pool = nullptr;                           // stream-ordered scratch of the *_device matcher calls (k_knn2 partials)
     int nfeatures = 0, nlevels = 0, score_type = 1, fast_th = 20;
     float scale_factor_f = 1.2f;
     double scaleFactor = 1.2;
@@ -167,7 +185,7 @@ struct orb_ctx {
     int num_sms = 148;
     int split_device = 0;
     int desc_fma = 0;                                      // orb_set_descriptor_fma
-    int debug_skip = 0;                                    // ORB_DEBUG_SKIP (timing experiments only, results are wrong): 1 no blur, 2 no selection, 4 no describe
+    int debug_skip = 0;                                    // ORB_DEBUG_SKIP, honoured only by a -DORB_DEBUG build (timing experiments, results are wrong): 1 no blur, 2 no selection, 4 no describe
     int rs_flex_width = 1;                                 // ORB_RESIZE_FLEX=0: fixed 128-column k_resize tiles (A/B timing)
     int rs_rows_pref = 8;                                  // ORB_RESIZE_ROWS: output rows per k_resize thread (tile height = 8 * rows at 128 columns)
     int select_serial = 0;                                 // ORB_SELECT_SERIAL=1: the thread-per-cell selection kernel (A/B timing)
@@ -178,11 +196,17 @@ struct orb_ctx {
     std::vector<cudaEvent_t> prof_events;   // (ORB_NSTAGES+1) per profiled launch
     std::vector<cudaEvent_t> prof_pool;
     int last_nimg = 0;
-    // matcher scratch
-    int32_t* d_knn_part = nullptr; size_t knn_part_bytes = 0;
-    void* d_match_scratch = nullptr; size_t match_scratch_bytes = 0;
-    uint8_t* h_match_arena = nullptr; size_t match_arena_bytes = 0;   // pinned mirror of the input part of the scratch: one H2D per call
 };
+
+// borrows a lane for the scope of one call (blocks while all MAX_LANES are in use); lane == nullptr after a CUDA failure
+struct LaneGuard {
+    orb_ctx* c; MatchLane* lane;
+    explicit LaneGuard(orb_ctx* ctx);
+    ~LaneGuard();
+    LaneGuard(const LaneGuard&) = delete; LaneGuard& operator=(const LaneGuard&) = delete;
+};
+// make sure the lane's device scratch / pinned arena hold `bytes` / `arena_bytes`
+int orb_lane_scratch(MatchLane* L, size_t bytes, size_t arena_bytes = 0);
 
 // status helpers
 extern thread_local std::string g_last_cuda_error;

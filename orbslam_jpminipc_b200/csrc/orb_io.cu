@@ -6,6 +6,8 @@
 #include "orb_internal.h"
 #include <cstdio>
 #include <cstring>
+#include <climits>
+#include <sys/types.h>
 
 namespace {
 
@@ -16,6 +18,10 @@ int read_records(const char* path, uint8_t* rows, int64_t cap_rows, int32_t* rec
     *nrows = 0; *nrecords = 0;
     FILE* f = fopen(path, "rb");
     if (!f) return ORB_ERR_INVALID;
+    // a record count is trusted only as far as the file can hold it
+    if (fseeko(f, 0, SEEK_END) != 0) { fclose(f); return ORB_ERR_INVALID; }
+    const int64_t fsize = (int64_t)ftello(f);
+    rewind(f);
     int64_t total = 0;
     int32_t recs = 0;
     int rc = ORB_OK;
@@ -24,10 +30,13 @@ int read_records(const char* path, uint8_t* rows, int64_t cap_rows, int32_t* rec
         if (fread(hdr, 1, 2, f) != 2) break;                           // clean end of file
         CountT n = 0;
         if (hdr[0] != 0xEB || hdr[1] != 0x90 || fread(&n, sizeof n, 1, f) != 1 || (int64_t)n < 0) { rc = ORB_ERR_INVALID; break; }
+        const int64_t here = (int64_t)ftello(f);
+        if (here < 0 || (uint64_t)n > (uint64_t)(fsize - here) / ROW) { rc = ORB_ERR_INVALID; break; }      // truncated / corrupt record
+        if (total + (int64_t)n > INT32_MAX || recs == INT32_MAX) { rc = ORB_ERR_CAPACITY; break; }            // row offsets are int32 (rec_start, match indices)
         if (rec_start && recs < cap_records) rec_start[recs] = (int32_t)total;
         if (rows && total + (int64_t)n <= cap_rows) {
             if (n && fread(rows + (size_t)total * ROW, ROW, (size_t)n, f) != (size_t)n) { rc = ORB_ERR_INVALID; break; }
-        } else if (fseek(f, (long)((size_t)n * ROW), SEEK_CUR) != 0) { rc = ORB_ERR_INVALID; break; }
+        } else if (fseeko(f, (off_t)((uint64_t)n * ROW), SEEK_CUR) != 0) { rc = ORB_ERR_INVALID; break; }
         total += (int64_t)n;
         recs++;
     }

@@ -853,26 +853,28 @@ int orb_launch_knn2(orb_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_db,
         ORB_CUDA(cudaGetLastError());
         return ORB_OK;
     }
+    if (nchunks > 65535 || npairs > 65535 || qtiles > 65535) return ORB_ERR_CAPACITY;     // grid limits, before anything is allocated
+    // global row indices are int32: a shard whose last row does not fit is refused instead of wrapping to negative indices
+    // (which the merge would then drop as "empty")
+    if (idx_base < 0) return ORB_ERR_INVALID;
+    if (ndb + (int64_t)idx_base > (int64_t)INT_MAX) return ORB_ERR_CAPACITY;
     Knn2Args A;
     A.q = d_q; A.db = d_db; A.nq = nq; A.ndb = ndb; A.rows_per_chunk = (int)rows; A.nchunks = nchunks;
     A.idx_base = idx_base; A.out = nullptr; A.o_idx1 = d_idx1; A.o_d1 = d_d1; A.o_d2 = d_d2;
+    int32_t* part = nullptr;
     if (nchunks > 1) {
+        // per-call partials from the context's stream-ordered pool: calls on different streams (or from different threads) never
+        // share scratch, and nothing synchronises
         const size_t need = (size_t)npairs * nchunks * 3 * nq * sizeof(int32_t);
-        if (need > c->knn_part_bytes) {
-            ORB_CUDA(cudaStreamSynchronize(s));
-            if (c->d_knn_part) cudaFree(c->d_knn_part);
-            c->d_knn_part = nullptr; c->knn_part_bytes = 0;
-            ORB_CUDA(cudaMalloc((void**)&c->d_knn_part, need));
-            c->knn_part_bytes = need;
-        }
-        A.out = c->d_knn_part;
+        ORB_CUDA(cudaMallocFromPoolAsync((void**)&part, need, c->pool, s));
+        A.out = part;
     }
-    if (nchunks > 65535 || npairs > 65535) return ORB_ERR_CAPACITY;
     k_knn2<<<dim3(nchunks, qtiles, npairs), KNN_THREADS, 0, s>>>(A);
     c->last_launches = 1;
     if (nchunks > 1) {
-        k_knn2_merge<<<dim3((nq + 127) / 128, npairs), 128, 0, s>>>(c->d_knn_part, nchunks, nq, npairs, d_idx1, d_d1, d_d2);
+        k_knn2_merge<<<dim3((nq + 127) / 128, npairs), 128, 0, s>>>(part, nchunks, nq, npairs, d_idx1, d_d1, d_d2);
         c->last_launches = 2;
+        ORB_CUDA(cudaFreeAsync(part, s));
     }
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;

@@ -28,8 +28,6 @@ struct orb_vocab {
     int32_t* d_orig = nullptr;
     int32_t* d_word = nullptr;
     double* d_weight = nullptr;
-    uint8_t* d_scratch = nullptr;
-    size_t scratch_bytes = 0;
 };
 
 namespace {
@@ -268,17 +266,6 @@ k_bow_score(const int32_t* __restrict__ qw, const double* __restrict__ qv, int n
     if (lane == 0) score[k] = __double2float_rn(__ddiv_rn(-acc, 2.0));
 }
 
-int vocab_scratch(orb_vocab* v, size_t bytes)
-{
-    if (bytes <= v->scratch_bytes && v->d_scratch) return ORB_OK;
-    ORB_CUDA(cudaDeviceSynchronize());
-    if (v->d_scratch) cudaFree(v->d_scratch);
-    v->d_scratch = nullptr; v->scratch_bytes = 0;
-    ORB_CUDA(cudaMalloc(&v->d_scratch, bytes));
-    v->scratch_bytes = bytes;
-    return ORB_OK;
-}
-
 inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 bool on_device(const void* p)
@@ -409,7 +396,7 @@ void orb_vocab_destroy(orb_vocab* v)
 {
     if (!v) return;
     cudaSetDevice(v->device);
-    cudaFree(v->d_kids); cudaFree(v->d_desc); cudaFree(v->d_orig); cudaFree(v->d_word); cudaFree(v->d_weight); cudaFree(v->d_scratch);
+    cudaFree(v->d_kids); cudaFree(v->d_desc); cudaFree(v->d_orig); cudaFree(v->d_word); cudaFree(v->d_weight);
     delete v;
 }
 
@@ -430,7 +417,9 @@ int orb_vocab_transform_features(orb_ctx* c, orb_vocab* v, const uint8_t* desc, 
     if (n == 0) return ORB_OK;
     if (!desc) return ORB_ERR_INVALID;
     ORB_CUDA(cudaSetDevice(c->device));
-    cudaStream_t s = c->streams[0];
+    LaneGuard lg(c);                              // scratch and stream of this call only: transforms of different threads run side by side
+    if (!lg.lane) return ORB_ERR_CUDA;
+    cudaStream_t s = lg.lane->stream;
     const bool dev = on_device(desc);
     if (on_device(word) != dev || on_device(weight) != dev || on_device(node) != dev) return ORB_ERR_INVALID;
     if (dev) {
@@ -440,9 +429,9 @@ int orb_vocab_transform_features(orb_ctx* c, orb_vocab* v, const uint8_t* desc, 
         return ORB_OK;
     }
     const size_t N = (size_t)n;
-    int rc = vocab_scratch(v, al256(N * 32) + al256(N * 4) * 2 + al256(N * 8));
+    int rc = orb_lane_scratch(lg.lane, al256(N * 32) + al256(N * 4) * 2 + al256(N * 8));
     if (rc) return rc;
-    uint8_t* p = v->d_scratch;
+    uint8_t* p = (uint8_t*)lg.lane->d_scratch;
     uint8_t* d_desc = p; p += al256(N * 32);
     int32_t* d_word = (int32_t*)p; p += al256(N * 4);
     int32_t* d_node = (int32_t*)p; p += al256(N * 4);
@@ -465,16 +454,18 @@ int orb_vocab_transform_batch(orb_ctx* c, orb_vocab* v, const uint8_t* desc, int
     if (cap > BOW_MAX_FEATURES || slot_rows > cap) return ORB_ERR_CAPACITY;
     if (cap > 0 && (!desc || !bow_word || !bow_val || !fv_node || !fv_start || !fv_items)) return ORB_ERR_INVALID;
     ORB_CUDA(cudaSetDevice(c->device));
-    cudaStream_t s = c->streams[0];
+    LaneGuard lg(c);                              // scratch and stream of this call only: transforms of different threads run side by side
+    if (!lg.lane) return ORB_ERR_CUDA;
+    cudaStream_t s = lg.lane->stream;
     const bool dev = on_device(counts);
     const void* ptrs[] = { desc, bow_word, bow_val, nbow, fv_node, fv_start, fv_items, nfv };
     for (const void* p : ptrs) if (p && on_device(p) != dev) return ORB_ERR_INVALID;
     const size_t F = (size_t)nframes, slots = F * (size_t)slot_rows, outs = F * (size_t)cap;
     size_t need = al256(slots * 4) * 2 + al256(slots * 8);
     if (!dev) need += al256(slots * 32) + al256(F * 4) * 3 + al256(outs * 4) * 3 + al256(outs * 8) + al256(F * (size_t)(cap + 1) * 4);
-    int rc = vocab_scratch(v, need + 4096);
+    int rc = orb_lane_scratch(lg.lane, need + 4096);
     if (rc) return rc;
-    uint8_t* p = v->d_scratch;
+    uint8_t* p = (uint8_t*)lg.lane->d_scratch;
     auto take = [&](size_t bytes) { uint8_t* r = p; p += al256(bytes); return r; };
     int32_t* d_word = (int32_t*)take(slots * 4);
     int32_t* d_node = (int32_t*)take(slots * 4);
@@ -525,7 +516,9 @@ int orb_bow_score_db(orb_ctx* c, orb_vocab* v, const int32_t* qw, const double* 
     if (!kf_start || !common || !score || (nq > 0 && (!qw || !qv))) return ORB_ERR_INVALID;
     if (v->scoring != 0) return ORB_ERR_UNSUPPORTED;                     // only L1_NORM (what the reference's vocabulary uses)
     ORB_CUDA(cudaSetDevice(c->device));
-    cudaStream_t s = c->streams[0];
+    LaneGuard lg(c);                              // scratch and stream of this call only: transforms of different threads run side by side
+    if (!lg.lane) return ORB_ERR_CUDA;
+    cudaStream_t s = lg.lane->stream;
     const bool dev = on_device(kf_start);
     if (on_device(common) != dev || on_device(score) != dev || (nq > 0 && on_device(qw) != dev)) return ORB_ERR_INVALID;
     int total = 0;
@@ -534,9 +527,9 @@ int orb_bow_score_db(orb_ctx* c, orb_vocab* v, const int32_t* qw, const double* 
     const size_t K = (size_t)nkf, T = (size_t)total, Q = (size_t)nq;
     size_t need = 256;
     if (!dev) need += al256(Q * 4) + al256(Q * 8) + al256((K + 1) * 4) + al256(T * 4) + al256(T * 8) + al256(K * 4) * 2;
-    int rc = vocab_scratch(v, need + 1024);
+    int rc = orb_lane_scratch(lg.lane, need + 1024);
     if (rc) return rc;
-    uint8_t* p = v->d_scratch;
+    uint8_t* p = (uint8_t*)lg.lane->d_scratch;
     auto take = [&](size_t bytes) { uint8_t* r = p; p += al256(std::max<size_t>(bytes, 1)); return r; };
     int* d_max = (int*)take(4);
     int32_t* d_common = common; float* d_score = score;

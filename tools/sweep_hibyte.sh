@@ -1,13 +1,12 @@
-# A/B of the ORB_NMS_HIBYTE variant of k_fast_nms ("Next candidates" (a)).
-# Here (build container):   make -C orbslam_jpminipc_b200/csrc -s OUT=../liborb_b200_hibyte.so EXTRA=-DORB_NMS_HIBYTE && make -C orbslam_jpminipc_b200/csrc -s
-# then:                     gpurun --timeout 600 -- 'bash tools/sweep_hibyte.sh > gpurun_out/sweep_hibyte.log 2>&1; cat gpurun_out/sweep_hibyte.log'
-cd $GRAFT_REPO_ROOT
-cp orbslam_jpminipc_b200/liborb_b200.so /tmp/orig.so
-run() { timeout 300 python bench.py --steps 40 --skip-matching --no-cpu-baseline > gpurun_out/sr.json 2>gpurun_out/sr.err; python -c "
-import json; d=json.load(open('gpurun_out/sr.json')); s=d['roofline']['stage_ms_per_step']; print('$1', round(d['value']), round(d['ms_per_step'],4), round(d['e2e']['value']), round(s['k_fast_nms'],4))"; }
+# A/B of a k_fast_nms build variant (e.g. -DORB_NMS_HIBYTE) WITHOUT touching the product library: the variant is a second .so selected
+# through ORB_B200_LIB (orbslam_jpminipc_b200/_lib.py).
+# Here (build container):   make -C orbslam_jpminipc_b200/csrc -s OUT=../liborb_b200_variant.so EXTRA=-DORB_NMS_HIBYTE
+# then:                     gpurun --timeout 600 -- 'bash tools/sweep_hibyte.sh > gpurun_out/sweep_variant.log 2>&1; cat gpurun_out/sweep_variant.log'
+cd "$GRAFT_REPO_ROOT"
+VAR=$PWD/orbslam_jpminipc_b200/liborb_b200_variant.so
+run() { timeout 300 python bench.py --steps 10 --skip-matching --no-cpu-baseline > gpurun_out/sr.json 2>gpurun_out/sr.err; python -c "
+import json; d=json.load(open('gpurun_out/sr.json')); s=d['roofline']['stage_ms_per_launch']; print('$1', round(d['value']), round(d['ms_per_step'],4), round(d['e2e']['value']), {k: round(v,4) for k,v in s.items()})" || tail -3 gpurun_out/sr.err; }
 run "default"
-cp orbslam_jpminipc_b200/liborb_b200_hibyte.so orbslam_jpminipc_b200/liborb_b200.so
-timeout 600 python -m pytest tests/test_gpu_extract.py tests/test_gpu_vs_ref.py tests/test_gpu_fullsize.py -x -q -m gpu 2>&1 | tail -2
-run "ORB_NMS_HIBYTE"
-cp /tmp/orig.so orbslam_jpminipc_b200/liborb_b200.so
+ORB_B200_LIB=$VAR timeout 900 python -m pytest tests/test_gpu_extract.py tests/test_gpu_vs_ref.py tests/test_gpu_fullsize.py -x -q -m gpu 2>&1 | tail -2
+ORB_B200_LIB=$VAR run "variant"
 run "default (again)"
