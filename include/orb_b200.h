@@ -316,6 +316,46 @@ int  orb_vocab_transform_batch(orb_ctx*, orb_vocab*, const uint8_t* desc, int sl
 int  orb_bow_score_db(orb_ctx*, orb_vocab*, const int32_t* qword, const double* qval, int nq, int nkf, const int32_t* kf_start,
                       const int32_t* kf_word, const double* kf_val, int score_all, int32_t* common, float* score, int* max_common);
 
+/* ------------------------------------------------------------------ multi-GPU ----------
+ * The path shards two ways: frames are independent (contiguous blocks of frames per GPU, no data-path collective), and the
+ * relocalisation-sized kNN splits the keyframe-descriptor DATABASE by contiguous row ranges with the queries replicated; each
+ * rank returns (idx1, d1, d2) with GLOBAL row indices, ONE exchange of 12 bytes per query and rank follows (ncclAllGather over
+ * NVLink / NVSwitch on the rank's own stream; or, single process without NCCL, rank 0's merge kernel loading the peers' partials
+ * in place), then the exact merge: best = lexicographic min of (d1, idx1), second = 2nd smallest of the multiset union.  The
+ * result is bit-identical to orb_hamming_knn2 over the whole database.  The reference is a single process (src/main.cc:165-212),
+ * hence orb_comm_init; one process per GPU (torchrun / MPI) uses orb_comm_unique_id + orb_comm_init_rank.
+ * libnccl.so.2 is opened at run time (no link dependency); ORB_COMM_TRANSPORT=p2p|nccl, ORB_NCCL_LIB=<path> override.
+ * A communicator is driven by one host thread at a time (calls are serialised by a mutex). */
+typedef struct orb_comm orb_comm;
+/* single process: ranks = devices 0..ngpus-1 (ngpus <= 0: every visible device), one matcher-only context + stream per device */
+orb_comm* orb_comm_init(int ngpus);
+/* one process per GPU: rank 0 calls orb_comm_unique_id (128 bytes) and the host application broadcasts it; ctx is the rank's
+ * context (not owned) */
+int       orb_comm_unique_id(void* id128);
+orb_comm* orb_comm_init_rank(orb_ctx* ctx, int nranks, int rank, const void* id128);
+void      orb_comm_destroy(orb_comm*);
+int       orb_comm_size(const orb_comm*);
+const char* orb_comm_transport(const orb_comm*);          /* "nccl", "p2p" or "none (1 rank)" */
+orb_ctx*  orb_comm_context(orb_comm*, int rank);          /* the context of a local rank (e.g. for orb_keypoint_capacity) */
+/* single process: size the per-device extractors (ORBextractor constructor arguments, as orb_create) */
+int orb_comm_set_extractor(orb_comm*, int nfeatures, float scale_factor, int nlevels, int score_type, int fast_th,
+                           int max_w, int max_h, int max_batch);
+/* single process: split ndb rows (host or device memory) into contiguous ranges, rank r gets rows [lo_r, hi_r), and upload them */
+int orb_comm_db_upload(orb_comm*, const uint8_t* db, int64_t ndb);
+/* a shard that already lives on the rank's device (e.g. generated there, or read from a dump by orb_db_read_descriptors and copied):
+ * rows are global rows [row_base, row_base + nrows); not owned */
+int orb_comm_db_attach(orb_comm*, int rank, const uint8_t* d_rows, int64_t nrows, int64_t row_base);
+/* single process: q[nq*32] and the outputs are host pointers, or device pointers on rank 0's device; blocking */
+int orb_knn2_sharded(orb_comm*, const uint8_t* q, int nq, int32_t* idx1, int32_t* d1, int32_t* d2);
+/* one process per GPU: this rank's shard and replicated queries as device pointers; kNN, exchange and merge are enqueued on
+ * `stream`, every rank receives the full result; asynchronous */
+int orb_knn2_sharded_device(orb_comm*, const uint8_t* d_q, int nq, const uint8_t* d_rows, int64_t nrows, int64_t row_base,
+                            int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, void* stream);
+/* single process: orb_extract_batch with the frames split into contiguous blocks over the devices (after orb_comm_set_extractor);
+ * host buffers (pinned for real overlap); every device runs its own copy / compute pipeline, one host thread drives all of them */
+int orb_extract_batch_multi(orb_comm*, const uint8_t* imgs, int nimg, int w, int h, int stride, size_t frame_pitch,
+                            orb_keypoint* kps, uint8_t* desc, int cap, int32_t* counts);
+
 /* pinned host memory helpers (page-locked buffers make the host<->device copies asynchronous) */
 void* orb_host_alloc(size_t bytes);
 void  orb_host_free(void* p);

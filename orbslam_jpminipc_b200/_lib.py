@@ -30,6 +30,9 @@ EXPORTS = [
     "orb_db_read_descriptors", "orb_db_write_descriptors", "orb_db_read_keypoints", "orb_db_write_keypoints",
     "orb_vocab_create", "orb_vocab_load_text", "orb_vocab_destroy", "orb_vocab_info", "orb_vocab_transform_features",
     "orb_vocab_transform_batch", "orb_bow_score_db",
+    "orb_comm_init", "orb_comm_unique_id", "orb_comm_init_rank", "orb_comm_destroy", "orb_comm_size", "orb_comm_transport",
+    "orb_comm_context", "orb_comm_set_extractor", "orb_comm_db_upload", "orb_comm_db_attach", "orb_knn2_sharded",
+    "orb_knn2_sharded_device", "orb_extract_batch_multi",
 ]
 
 
@@ -134,6 +137,24 @@ def lib():
     L.orb_vocab_transform_features.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
     L.orb_vocab_transform_batch.argtypes = [vp, vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.orb_bow_score_db.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, i32, vp, vp, C.POINTER(C.c_int)]
+    L.orb_comm_init.restype = vp
+    L.orb_comm_init.argtypes = [i32]
+    L.orb_comm_unique_id.argtypes = [vp]
+    L.orb_comm_init_rank.restype = vp
+    L.orb_comm_init_rank.argtypes = [vp, i32, i32, vp]
+    L.orb_comm_destroy.restype = None
+    L.orb_comm_destroy.argtypes = [vp]
+    L.orb_comm_size.argtypes = [vp]
+    L.orb_comm_transport.restype = C.c_char_p
+    L.orb_comm_transport.argtypes = [vp]
+    L.orb_comm_context.restype = vp
+    L.orb_comm_context.argtypes = [vp, i32]
+    L.orb_comm_set_extractor.argtypes = [vp, i32, f32, i32, i32, i32, i32, i32, i32]
+    L.orb_comm_db_upload.argtypes = [vp, vp, i64]
+    L.orb_comm_db_attach.argtypes = [vp, i32, vp, i64, i64]
+    L.orb_knn2_sharded.argtypes = [vp, vp, i32, vp, vp, vp]
+    L.orb_knn2_sharded_device.argtypes = [vp, vp, i32, vp, i64, i64, vp, vp, vp, vp]
+    L.orb_extract_batch_multi.argtypes = [vp, vp, i32, i32, i32, i32, sz, vp, vp, i32, vp]
     _lib = L
     return L
 

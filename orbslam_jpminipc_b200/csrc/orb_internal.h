@@ -227,6 +227,9 @@ int orb_resize_smem_setup(int max_bytes);
 int orb_launch_knn2(orb_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_db, int64_t ndb, int npairs, int32_t idx_base,
                     int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, cudaStream_t s);
 int orb_launch_knn2_merge(const int32_t* d_parts, int nparts, int nq, int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, cudaStream_t s);
+#define ORB_COMM_MAX_RANKS 16
+// the same merge with one pointer per part (parts may live on peer devices: orb_comm.cu, "p2p" transport)
+int orb_launch_knn2_merge_ptrs(const int32_t* const* d_parts, int nparts, int nq, int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, cudaStream_t s);
 int orb_launch_match_ratio(const int32_t* idx1, const int32_t* d1, const int32_t* d2, int nq, float nnratio, int th,
                            int32_t* match, int* d_count, cudaStream_t s);
 int orb_launch_grid_build(const orb_keypoint* kps, int n, int min_x, int max_x, int min_y, int max_y,

@@ -140,6 +140,24 @@ __global__ void k_knn2_merge(const int32_t* __restrict__ parts, int nparts, int 
     idx1[o] = bi; d1[o] = b1; d2[o] = b2;
 }
 
+// the same merge over parts that are separate buffers (one per rank; peer-device memory is read in place over NVLink)
+struct MergePtrs { const int32_t* p[ORB_COMM_MAX_RANKS]; };
+__global__ void k_knn2_merge_ptrs(MergePtrs parts, int nparts, int nq, int32_t* __restrict__ idx1, int32_t* __restrict__ d1, int32_t* __restrict__ d2)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    int b1 = INT_MAX, b2 = INT_MAX, bi = -1;
+#pragma unroll 1
+    for (int p = 0; p < nparts; p++) {
+        const int32_t* P = parts.p[p];
+        const int pi = P[i], pd1 = P[(size_t)nq + i], pd2 = P[(size_t)2 * nq + i];
+        if (pi < 0) continue;
+        if (pd1 < b1) { b2 = b1; b1 = pd1; bi = pi; } else if (pd1 < b2) b2 = pd1;
+        if (pd2 < b2) b2 = pd2;
+    }
+    idx1[i] = bi; d1[i] = b1; d2[i] = b2;
+}
+
 __global__ void k_match_ratio(const int32_t* __restrict__ idx1, const int32_t* __restrict__ d1, const int32_t* __restrict__ d2,
                               int nq, float nnratio, int th, int32_t* __restrict__ match, int* __restrict__ count)
 {
@@ -883,6 +901,16 @@ int orb_launch_knn2(orb_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_db,
 int orb_launch_knn2_merge(const int32_t* d_parts, int nparts, int nq, int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, cudaStream_t s)
 {
     k_knn2_merge<<<dim3((nq + 127) / 128, 1), 128, 0, s>>>(d_parts, nparts, nq, 1, d_idx1, d_d1, d_d2);
+    ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
+}
+
+int orb_launch_knn2_merge_ptrs(const int32_t* const* d_parts, int nparts, int nq, int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, cudaStream_t s)
+{
+    if (nparts < 1 || nparts > ORB_COMM_MAX_RANKS) return ORB_ERR_CAPACITY;
+    MergePtrs P;
+    for (int i = 0; i < ORB_COMM_MAX_RANKS; i++) P.p[i] = i < nparts ? d_parts[i] : nullptr;
+    k_knn2_merge_ptrs<<<(nq + 127) / 128, 128, 0, s>>>(P, nparts, nq, d_idx1, d_d1, d_d2);
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;
 }

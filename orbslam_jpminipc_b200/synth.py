@@ -180,3 +180,86 @@ def write_vocabulary_text(path, k, L, parent, desc, weight, scoring=0, weighting
         for i in range(1, n):
             f.write("%d %d %s %s%s" % (parent[i], 0 if has_child[i] else 1, " ".join(str(int(b)) for b in desc[i]), repr(float(weight[i])),
                                        "\n" if (trailing_newline or i + 1 < n) else ""))
+
+
+# ---- config 5: a keyframe-descriptor database that is the same at any GPU count ----
+# Counter-based: row r is a pure function of (seed, r), so a rank generates exactly its row range on its own device and rank 0
+# can regenerate everything for the single-scan check.  About 0.8 % of the rows in the upper half of the database are exact copies
+# of the row half a database below them: the two copies ALWAYS lie in different shards (contiguous ranges, 2+ ranks), so "lowest
+# global index wins, d2 == d1" is decided by the cross-shard merge, not inside one shard.  Even queries are planted next to such
+# duplicated rows (Binomial(256, 0.08) flipped bits), odd queries are random.
+_SM_GAMMA, _SM_M1, _SM_M2 = 0x9E3779B97F4A7C15, 0xBF58476D1CE4E5B9, 0x94D049BB133111EB
+_M64 = (1 << 64) - 1
+
+
+def _splitmix_np(x):
+    with np.errstate(over="ignore"):
+        z = (x.astype(np.uint64) + np.uint64(_SM_GAMMA))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(_SM_M1)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(_SM_M2)
+        return z ^ (z >> np.uint64(31))
+
+
+def db_is_dup_np(rows, ndb, seed):
+    rows = np.asarray(rows, np.uint64)
+    return (rows >= np.uint64(ndb // 2)) & ((_splitmix_np(rows ^ np.uint64((seed * 0x51ED27 + 0xABCD) & _M64)) & np.uint64(127)) == 0)
+
+
+def db_rows_np(rows, ndb, seed):
+    """descriptor rows (len(rows), 32) uint8 of the counter-based database, on the host"""
+    rows = np.asarray(rows, np.uint64)
+    eff = np.where(db_is_dup_np(rows, ndb, seed), rows - np.uint64(ndb // 2), rows)
+    with np.errstate(over="ignore"):
+        ctr = (eff[:, None] * np.uint64(4) + np.arange(4, dtype=np.uint64)[None, :]) + np.uint64((seed * 0x2545F491) & _M64)
+    return _splitmix_np(ctr).astype("<u8").view(np.uint8).reshape(len(rows), 32)
+
+
+def db_rows_torch(lo, hi, ndb, seed, device, chunk=1 << 20):
+    """the same rows [lo, hi) generated on `device` (torch int64 arithmetic wraps like uint64; shifts are made logical)"""
+    import torch
+
+    def s64(c):
+        c &= _M64
+        return c - (1 << 64) if c >= (1 << 63) else c
+
+    def lsr(z, k):
+        return (z >> k) & ((1 << (64 - k)) - 1)
+
+    def splitmix(x):
+        z = x + s64(_SM_GAMMA)
+        z = (z ^ lsr(z, 30)) * s64(_SM_M1)
+        z = (z ^ lsr(z, 27)) * s64(_SM_M2)
+        return z ^ lsr(z, 31)
+    out = torch.empty((hi - lo, 32), dtype=torch.uint8, device=device)
+    half = ndb // 2
+    for a in range(lo, hi, chunk):
+        b = min(a + chunk, hi)
+        r = torch.arange(a, b, dtype=torch.int64, device=device)
+        dup = (r >= half) & ((splitmix(r ^ s64(seed * 0x51ED27 + 0xABCD)) & 127) == 0)
+        eff = torch.where(dup, r - half, r)
+        ctr = eff[:, None] * 4 + torch.arange(4, dtype=torch.int64, device=device)[None, :] + s64(seed * 0x2545F491)
+        out[a - lo:b - lo] = splitmix(ctr).view(torch.uint8).reshape(b - a, 32)
+    return out
+
+
+def db_queries(nq, ndb, seed, seed_q=43, flip_p=0.08):
+    """queries for the counter-based database: even ones planted next to a DUPLICATED row (its two copies are half a database
+    apart), odd ones random.  Returns (q [nq,32] uint8, planted_row int64 [nq], -1 for random queries)."""
+    rq = np.random.default_rng(seed_q)
+    q = rq.integers(0, 256, (nq, 32), dtype=np.uint8)
+    planted = np.full(nq, -1, np.int64)
+    if ndb >= 4:
+        half = ndb // 2
+        cand = np.arange(half, ndb, dtype=np.uint64)
+        if len(cand) > (1 << 22):
+            cand = cand[rq.integers(0, len(cand), 1 << 22)]
+        dups = cand[db_is_dup_np(cand, ndb, seed)]
+        ne = (nq + 1) // 2
+        if len(dups):
+            src = dups[rq.integers(0, len(dups), ne)].astype(np.int64) - half          # the lower copy: the index that must win
+        else:
+            src = rq.integers(0, ndb, ne)
+        flips = np.packbits((rq.random((ne, 256)) < flip_p).astype(np.uint8), axis=1)
+        q[0::2] = db_rows_np(src, ndb, seed) ^ flips
+        planted[0::2] = src
+    return q, planted

@@ -82,7 +82,7 @@ def test_excess_epilogue_equals_strength_minus_threshold():
         assert np.array_equal(got, want)
 
 
-# ---- high-byte-lane NMS (the ORB_NMS_HIBYTE variant of k_fast_nms, compiled out by default) ---------------------------------
+# ---- high-byte-lane NMS (the default NMS lane layout of k_fast_nms; -DORB_NMS_LOBYTE selects the older PRMT-unpacking form) ---------------------------------
 # numpy restatement of the exact lane operations of that variant, compared with the plain definition of the masked strict
 # 8-neighbour test on tie-heavy random score words.
 U=np.uint32
