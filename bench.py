@@ -574,7 +574,6 @@ def run_matching(E):
             check(L.orb_hamming_knn2_device(ex._h, ptr(d_q5), NQ, ptr(whole), NDB, 1, 0, ptr(s[0]), ptr(s[1]), ptr(s[2]), C.c_void_p(stream)), "single scan")
             torch.cuda.synchronize()
             require(all(np.array_equal(a, b.cpu().numpy()) for a, b in zip(fin_h, s)), "config 5: merged sharded result differs from the single scan")
-            sub = np.arange(0, NQ, 97)                                     # and the oracle on a subset of queries against a DB slice they were planted in
             del whole
         merge_check = ("bit-exact vs single scan (%d shards, NCCL all-gather + k_knn2_merge in orb_knn2_sharded_device; all ranks agree)" % world) if world > 1 \
             else "1 shard: bit-exact vs the planted neighbours (lower copy wins, d2 == d1)"
@@ -823,7 +822,8 @@ def run_gpu(args):
                 "popc_peak_source": matching["popc_peak_source"],
                 "roofline": "POPC pipe: 8 POPC32 per descriptor pair (SURVEY.md §8d)"},
             "verified": (verified if args.verify else False), "merge_check": (matching or {}).get("db_sharded", {}).get("merge_check"),
-            "config1_752x480": config1, "single_frame_latency": latency, "matching": matching}
+            "config1_752x480": config1, "single_frame_latency": latency,
+            "tracking_extras": None if matching is None else {k: matching[k] for k in ("search_by_projection_1241x376", "vocabulary_transform_k10_L6") if k in matching}}
     if args.cpu_baseline:
         cores = os.cpu_count() or 1
         base = r0["_base"]
