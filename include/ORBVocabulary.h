@@ -9,12 +9,26 @@
 #ifndef ORBVOCABULARY_H
 #define ORBVOCABULARY_H
 
+#include <cstring>
 #include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
 #include "orb_b200.h"
 
+#ifdef ORB_B200_WITH_REFERENCE_TYPES
+// the reference's own containers (Frame.h / KeyFrame.h include them too), so that mBowVec / mFeatVec keep their types
+#include <opencv2/core/core.hpp>
+#include "Thirdparty/DBoW2/DBoW2/BowVector.h"
+#include "Thirdparty/DBoW2/DBoW2/FeatureVector.h"
+// The reference's headers name vector / list / set / pair unqualified (include/Frame.h:111, include/KeyFrame.h:139,
+// include/KeyFrameDatabase.h:66): they rely on the using-directive that the reference's ORBVocabulary.h leaks through
+// Thirdparty/DBoW2/DBoW2/FORB.h and TemplatedVocabulary.h.  A header that replaces it has to keep that (unfortunate) contract.
+#include <list>
+#include <set>
+#include <vector>
+using namespace std;
+#else
 namespace DBoW2
 {
 typedef unsigned int WordId;
@@ -23,6 +37,7 @@ typedef unsigned int NodeId;
 class BowVector : public std::map<WordId, WordValue> {};                         // Thirdparty/DBoW2/DBoW2/BowVector.h:56
 class FeatureVector : public std::map<NodeId, std::vector<unsigned int> > {};   // Thirdparty/DBoW2/DBoW2/FeatureVector.h:21
 }
+#endif
 
 namespace ORB_SLAM
 {
@@ -31,6 +46,11 @@ class ORBVocabulary
 {
 public:
     explicit ORBVocabulary(orb_ctx* context) : ctx(context), voc(nullptr) {}
+    // the reference's default constructor (src/main.cc:85: `ORBVocabulary Vocabulary;`): runs on the process-wide default context
+    ORBVocabulary() : ctx(orb_default_context()), voc(nullptr)
+    {
+        if (!ctx) throw std::runtime_error(std::string("ORBVocabulary: no context (") + orb_last_cuda_error() + ")");
+    }
     ~ORBVocabulary() { orb_vocab_destroy(voc); }
     ORBVocabulary(const ORBVocabulary&) = delete;
     ORBVocabulary& operator=(const ORBVocabulary&) = delete;
@@ -60,6 +80,25 @@ public:
         for (int j = 0; j < nf; j++)
             fv.insert(fv.end(), std::make_pair((DBoW2::NodeId)fn[j], std::vector<unsigned int>(fi.begin() + fs[j], fi.begin() + fs[j + 1])));
     }
+
+#ifdef ORB_B200_WITH_REFERENCE_TYPES
+    // the reference's call (src/Frame.cc:284-285, src/KeyFrame.cc:62-63): one 1 x 32 CV_8U row per feature
+    void transform(const std::vector<cv::Mat>& features, DBoW2::BowVector& v, DBoW2::FeatureVector& fv, int levelsup) const
+    {
+        std::vector<unsigned char> rows(features.size() * 32 + 32);
+        for (size_t i = 0; i < features.size(); i++) std::memcpy(&rows[i * 32], features[i].ptr<unsigned char>(), 32);
+        transform(rows.data(), (int)features.size(), v, fv, levelsup);
+    }
+    // transform(feature) -> word id, Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1197-1205
+    DBoW2::WordId transform(const cv::Mat& feature) const
+    {
+        int32_t w = 0, node = 0;
+        double weight = 0;
+        if (empty()) return 0;
+        check(orb_vocab_transform_features(ctx, voc, feature.ptr<unsigned char>(), 1, 0, &w, &weight, &node));
+        return (DBoW2::WordId)w;
+    }
+#endif
 
     // score(v1, v2), rounded to float as every caller stores it (float si = mpVoc->score(...))
     double score(const DBoW2::BowVector& v1, const DBoW2::BowVector& v2) const

@@ -16,6 +16,9 @@
 #include <string>
 #include <vector>
 #include "orb_b200.h"
+#if defined(ORB_B200_WITH_REFERENCE_TYPES) && !defined(ORB_B200_WITH_OPENCV)
+#define ORB_B200_WITH_OPENCV
+#endif
 #ifdef ORB_B200_WITH_OPENCV
 #include <opencv2/core/core.hpp>
 #include <opencv2/features2d/features2d.hpp>

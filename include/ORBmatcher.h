@@ -9,8 +9,11 @@
  *   SearchForInitialization (:598-713), SearchByProjection(KeyFrame*, Scw, ...) (:286-407), the scoring loops of Fuse
  *   (:1016-1265) and SearchBySim3 (:1267-1505), SearchForTriangulation (:852-1014)
  * plus the brute-force best/second-best + ratio test used for relocalisation-sized searches.
- * Frame / KeyFrame / MapPoint are the reference's own graph classes and stay on the host: the shim
- * takes the plain arrays those methods read (see INTEGRATION.md for the adapter code).
+ * Frame / KeyFrame / MapPoint are the reference's own graph classes and stay on the host.  Two forms:
+ *   - ORBmatcherArrays (below): the plain arrays those methods read, usable without any reference header;
+ *   - with -DORB_B200_WITH_REFERENCE_TYPES and the reference's include/ directory behind this one on the include path:
+ *     ORB_SLAM::ORBmatcher with the reference's exact constructor and method signatures (orb_b200_reftypes.h), so that the
+ *     reference's call sites compile unchanged (see INTEGRATION.md and oracle/Makefile target _ref/libref_dropin.so).
  */
 #ifndef ORBMATCHER_H
 #define ORBMATCHER_H
@@ -20,6 +23,9 @@
 #include <utility>
 #include <vector>
 #include "orb_b200.h"
+#if defined(ORB_B200_WITH_REFERENCE_TYPES) && !defined(ORB_B200_WITH_OPENCV)
+#define ORB_B200_WITH_OPENCV
+#endif
 
 namespace ORB_SLAM
 {
@@ -53,10 +59,15 @@ struct FrameArrays {
     }
 };
 
-class ORBmatcher
+// The matcher on plain arrays (always available).  Without ORB_B200_WITH_REFERENCE_TYPES it is also ORB_SLAM::ORBmatcher; with it,
+// ORB_SLAM::ORBmatcher is the reference-signature class of orb_b200_reftypes.h, which flattens Frame / KeyFrame / MapPoint and calls this.
+class ORBmatcherArrays
 {
 public:
-    ORBmatcher(orb_ctx* ctx, float nnratio = 0.6, bool checkOri = true) : ctx(ctx), mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+    ORBmatcherArrays(orb_ctx* ctx, float nnratio = 0.6, bool checkOri = true) : ctx(ctx), mfNNratio(nnratio), mbCheckOrientation(checkOri)
+    {
+        if (!ctx) throw std::runtime_error(std::string("ORBmatcher: no context (") + orb_last_cuda_error() + ")");
+    }
 
     // Computes the Hamming distance between two ORB descriptors (32-byte rows)
     static int DescriptorDistance(const unsigned char* a, const unsigned char* b) { return orb_descriptor_distance(a, b); }
@@ -307,6 +318,20 @@ protected:
     bool mbCheckOrientation;
 };
 
+#ifndef ORB_B200_WITH_REFERENCE_TYPES
+class ORBmatcher : public ORBmatcherArrays
+{
+public:
+    ORBmatcher(orb_ctx* ctx, float nnratio = 0.6, bool checkOri = true) : ORBmatcherArrays(ctx, nnratio, checkOri) {}
+    // the reference's constructor (include/ORBmatcher.h:41): runs on the process-wide default context
+    explicit ORBmatcher(float nnratio = 0.6, bool checkOri = true) : ORBmatcherArrays(orb_default_context(), nnratio, checkOri) {}
+};
+#endif
+
 } // namespace ORB_SLAM
+
+#ifdef ORB_B200_WITH_REFERENCE_TYPES
+#include "orb_b200_reftypes.h"
+#endif
 
 #endif

@@ -59,6 +59,11 @@ int         orb_abi_version(void);
 orb_ctx* orb_create(int device, int nfeatures, float scale_factor, int nlevels, int score_type,
                     int fast_th, int max_w, int max_h, int max_batch);
 void     orb_destroy(orb_ctx*);
+/* A process-wide matcher-only context on the current CUDA device (ORB_B200_DEVICE overrides), created on first use and kept until the
+ * process exits: what a reference-signature `ORBmatcher matcher(0.9, true);` on the stack (src/Tracking.cc:392,528,596,759,907,946,
+ * src/LocalMapping.cc:232,421, src/LoopClosing.cc:252,578) runs on.  Matcher calls on one context are safe from several threads
+ * (each call borrows its own stream and scratch), so Tracking, LocalMapping and LoopClosing share it.  NULL without a usable GPU. */
+orb_ctx* orb_default_context(void);
 int      orb_nlevels(const orb_ctx*);          /* ORBextractor::GetLevels()      include/ORBextractor.h:47 */
 float    orb_scale_factor(const orb_ctx*);     /* ORBextractor::GetScaleFactor() include/ORBextractor.h:50 */
 int      orb_keypoint_capacity(const orb_ctx*);/* rows to allocate per image: sum of per-level quotas */

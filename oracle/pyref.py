@@ -48,11 +48,14 @@ def lib():
         L.ref_frame_set_bowvec.argtypes = [vp, i, vp, vp]
         L.ref_detect_relocalisation_candidates.argtypes = [vp, vp, vp, i, vp, vp, vp]
         L.ref_frame_update_points.argtypes = [vp]
-        L.ref_search_by_projection_kf.argtypes = [vp, vp, vp, f, i, f, i, vp, vp]
-        L.ref_search_by_projection_sim3.argtypes = [vp, vp, vp, i, vp, vp, vp, vp, vp]
-        L.ref_fuse.argtypes = [vp, vp, f, vp, vp, vp, vp, vp]
-        L.ref_search_by_sim3.argtypes = [vp, vp, f, vp, vp, f, vp, vp, vp, vp, vp, vp, vp, vp, vp]
-        L.ref_fuse_sim3.argtypes = [vp, vp, vp, f, vp, vp, vp, vp, vp]
+        if hasattr(L, "ref_fuse"):                       # not in the drop-in flavour (oracle/pydropin.py): their projection stays with the caller
+            L.ref_search_by_projection_kf.argtypes = [vp, vp, vp, f, i, f, i, vp, vp]
+            L.ref_search_by_projection_sim3.argtypes = [vp, vp, vp, i, vp, vp, vp, vp, vp]
+            L.ref_fuse.argtypes = [vp, vp, f, vp, vp, vp, vp, vp]
+            L.ref_search_by_sim3.argtypes = [vp, vp, f, vp, vp, f, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+            L.ref_fuse_sim3.argtypes = [vp, vp, vp, f, vp, vp, vp, vp, vp]
+        L.ref_track_with_motion_model.argtypes = [vp, vp, vp, vp]
+        L.ref_glue_flavour.restype = C.c_char_p
         L.ref_descriptor_distance.argtypes = [vp, vp]
         L.ref_search_by_projection_ff.argtypes = [vp, vp, f, f, i, vp]
         L.ref_search_by_projection_mappoints.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, f, f, vp]
@@ -206,6 +209,17 @@ def search_by_projection(cur, last, th, nnratio=0.9, check_ori=True, match_cur=N
     m = np.full(cur.n, -1, np.int32) if match_cur is None else np.ascontiguousarray(match_cur, np.int32)
     n = _ok(lib().ref_search_by_projection_ff(cur._h, last._h, th, nnratio, int(check_ori), _p(m)), "SearchByProjection(F,F)")
     return n, m
+
+
+def track_with_motion_model(cur, last, velocity):
+    """the call sequence of Tracking::TrackWithMotionModel (src/Tracking.cc:594-606) -> (nmatches, match_cur)"""
+    V = np.ascontiguousarray(velocity, np.float32).reshape(16)
+    m = np.full(cur.n, -1, np.int32)
+    return _ok(lib().ref_track_with_motion_model(cur._h, last._h, _p(V), _p(m)), "TrackWithMotionModel"), m
+
+
+def flavour():
+    return lib().ref_glue_flavour().decode()
 
 
 def search_by_projection_mappoints(f, in_view, proj_x, proj_y, level, view_cos, mp_desc, th, nnratio, match_f=None):

@@ -547,6 +547,38 @@ void ref_frame_update_points(void* h)
     for (MapPoint* p : r->f.mvpMapPoints) if (p) p->UpdateNormalAndDepth();
 }
 
+/* The call sequence of Tracking::TrackWithMotionModel, src/Tracking.cc:594-606 (the pose optimisation that follows needs g2o and is
+ * not part of the path): matcher on the stack, motion-model pose, map points cleared, SearchByProjection(CurrentFrame, LastFrame, 15).
+ * velocity16 = mVelocity (4x4 row major).  match_cur[i2] out = last-frame feature whose map point the current keypoint received. */
+int ref_track_with_motion_model(void* cur_, void* last_, const float* velocity16, int32_t* match_cur)
+{
+    RefFrame *cur = (RefFrame*)cur_, *last = (RefFrame*)last_;
+    return guarded("TrackWithMotionModel", [&] {
+        cur->statics();
+        Frame &mCurrentFrame = cur->f, &mLastFrame = last->f;
+        cv::Mat mVelocity(4, 4, CV_32F);
+        std::memcpy(mVelocity.data, velocity16, 64);
+        ORBmatcher matcher(0.9, true);
+        mCurrentFrame.mTcw = mVelocity * mLastFrame.mTcw;
+        std::fill(mCurrentFrame.mvpMapPoints.begin(), mCurrentFrame.mvpMapPoints.end(), static_cast<MapPoint*>(NULL));
+        int nmatches = matcher.SearchByProjection(mCurrentFrame, mLastFrame, 15);
+        std::map<MapPoint*, int> idx;
+        index_of(mLastFrame.mvpMapPoints, idx);
+        for (int i = 0; i < mCurrentFrame.N; i++) match_cur[i] = mCurrentFrame.mvpMapPoints[i] ? idx.at(mCurrentFrame.mvpMapPoints[i]) : -1;
+        return nmatches;
+    });
+}
+/* which implementation of ORBextractor / ORBmatcher / ORBVocabulary this library was compiled against */
+const char* ref_glue_flavour(void)
+{
+#ifdef REF_GLUE_DROPIN
+    return "dropin: reference call sites + include/ORBextractor.h, ORBmatcher.h, ORBVocabulary.h of this repository (liborb_b200.so)";
+#else
+    return "reference: src/ORBextractor.cc, src/ORBmatcher.cc, DBoW2";
+#endif
+}
+
+#ifndef REF_GLUE_DROPIN      /* the four searches whose Sim3 / pose projection the drop-in header leaves to the caller (include/orb_b200_reftypes.h) */
 /* ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, th, ORBdist), :1622-1746.
  * already_found[i] != 0 puts the KeyFrame's point i into sAlreadyFound.  match_cur[i2] in: >= 0 -> the keypoint already carries some
  * other map point; out: KeyFrame feature index of the point assigned, the input value where it was occupied, else -1.
@@ -821,5 +853,6 @@ int ref_fuse_sim3(void* kf_, void* src_, const float* Scw16, float th, int32_t* 
     });
 }
 
+#endif /* REF_GLUE_DROPIN */
 } // extern "C"
 #endif /* REF_GLUE_EXTRACTOR_ONLY */

@@ -20,7 +20,7 @@ GRID_COLS, GRID_ROWS = 64, 48
 
 # every symbol include/orb_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "orb_error_string", "orb_last_cuda_error", "orb_abi_version", "orb_create", "orb_destroy", "orb_nlevels",
+    "orb_error_string", "orb_last_cuda_error", "orb_abi_version", "orb_create", "orb_default_context", "orb_destroy", "orb_nlevels",
     "orb_scale_factor", "orb_keypoint_capacity", "orb_set_descriptor_fma", "orb_extract", "orb_extract_batch", "orb_extract_batch_device", "orb_extract_batch_async", "orb_wait",
     "orb_last_launch_count", "orb_profile_enable", "orb_profile_read", "orb_profile_stage_name", "orb_debug_level_info", "orb_debug_level_plane", "orb_descriptor_distance",
     "orb_hamming_knn2", "orb_hamming_knn2_device", "orb_knn2_merge_device", "orb_match_ratio",
@@ -82,6 +82,8 @@ def lib():
     L.orb_create.restype = vp
     L.orb_create.argtypes = [i32, i32, f32, i32, i32, i32, i32, i32, i32]
     L.orb_destroy.argtypes = [vp]
+    L.orb_default_context.restype = vp
+    L.orb_default_context.argtypes = []
     L.orb_nlevels.argtypes = [vp]
     L.orb_scale_factor.restype = f32
     L.orb_scale_factor.argtypes = [vp]

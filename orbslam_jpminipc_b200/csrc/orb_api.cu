@@ -266,6 +266,20 @@ orb_ctx* orb_create(int device, int nfeatures, float scale_factor, int nlevels, 
     return c;
 }
 
+orb_ctx* orb_default_context(void)
+{
+    static std::mutex mu;
+    static orb_ctx* ctxs[64] = {};
+    int dev = 0;
+    if (const char* e = getenv("ORB_B200_DEVICE")) dev = atoi(e);
+    else if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    if (dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    // matcher-only: nothing of the extraction pipeline is allocated until an extract call arrives (there never is one here)
+    if (!ctxs[dev]) ctxs[dev] = orb_create(dev, 1000, 1.2f, 8, ORB_FAST_SCORE, 20, 64, 64, 1);
+    return ctxs[dev];
+}
+
 void orb_destroy(orb_ctx* c)
 {
     if (!c) return;
