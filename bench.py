@@ -440,6 +440,9 @@ def measure_extraction(E, w, h, steps, warmup, launches, full):
                                               % (world, h2d / 1e6, d2h / 1e6)}
         res["e2e"]["frac_of_copy_ceiling"] = e2e_value / ceil_fps
         res["e2e"]["frac_of_device_value"] = e2e_value / value
+        # what bounds the end-to-end number at this rank count: the kernels (device value) or the box's copy fabric (ceiling)
+        res["e2e"]["bound"] = "kernels (device-resident value)" if value < ceil_fps else "host<->device copies (copy_ceiling)"
+        res["e2e"]["frac_of_bound"] = e2e_value / min(value, ceil_fps)
 
     # ---- verification (after the timed regions, on what the timed calls wrote) ----
     if E.args.verify:

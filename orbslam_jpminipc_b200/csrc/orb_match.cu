@@ -46,6 +46,20 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 constexpr int KNN_THREADS = 256;      // one query per thread
 constexpr int KNN_TILE = 256;         // DB rows per shared-memory stage (8 KB)
 constexpr int KNN_STAGES = 3;
+constexpr int KNN_KEY_SHIFT = 22;     // packed key = distance << 22 | row within the chunk: chunks hold at most 2^22 rows (distance <= 256 fits above)
+
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xe8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
 
 struct Knn2Args {
     const uint8_t* q; const uint8_t* db;
@@ -87,6 +101,7 @@ k_knn2(Knn2Args A)
     };
     if (tid == 0) for (int t = 0; t < min(KNN_STAGES - 1, ntiles); t++) issue(t);
 
+#ifdef ORB_KNN_PLAIN      // the straightforward form: 8 XOR + 8 POPC + 7 adds per pair, POPC-pipe bound (16 lanes/clk/SM); kept for A/B timing
     int d1 = INT_MAX, d2 = INT_MAX, i1 = -1;
     for (int t = 0; t < ntiles; t++) {
         const int s = t % KNN_STAGES;
@@ -109,6 +124,42 @@ k_knn2(Knn2Args A)
             d1 = min(d1, d);
         }
     }
+#else
+    // POPC runs at a quarter of the ALU rate (16 vs 64 lanes/clk/SM), so the eight XOR words of a pair are first compressed by three
+    // carry-save adders (LOP3 0x96 = sum, 0xE8 = majority): x0..x7 -> two words of weight 1 (s3, x7) and three of weight 2
+    // (c1, c2, c3).  5 POPC + 14 LOP3 instead of 8 POPC + 8 LOP3 — the two pipes end up equally loaded (~40 clk per warp and row),
+    // exact like any adder tree.  The running best / second-best are two packed keys  distance << 22 | row-in-chunk  (strict '<'
+    // scan == minimum key: lowest row among equal distances; second order statistic == second smallest key):
+    //     m2 = min(m2, max(m1, key)),  m1 = min(m1, key)
+    // three min/max instead of compare + two selects + two min, and the key is assembled by two IMADs on the otherwise idle FMA pipe.
+    int m1 = INT_MAX, m2 = INT_MAX;
+    for (int t = 0; t < ntiles; t++) {
+        const int s = t % KNN_STAGES;
+        // the stage refilled now was consumed in iteration t-1; the barrier below orders that
+        __syncthreads();
+        if (tid == 0 && t + KNN_STAGES - 1 < ntiles) issue(t + KNN_STAGES - 1);
+        mbar_wait(&bar[s], (uint32_t)((t / KNN_STAGES) & 1));
+        const int rows = min(KNN_TILE, nrows - t * KNN_TILE);
+        const uint4* tp = &tile[s][0];
+        const int jbase = t * KNN_TILE;
+#pragma unroll 4
+        for (int r = 0; r < rows; r++) {
+            const uint4 a = tp[2 * r], b = tp[2 * r + 1];            // broadcast reads
+            const uint32_t x0 = qw[0] ^ a.x, x1 = qw[1] ^ a.y, x2 = qw[2] ^ a.z, x3 = qw[3] ^ a.w;
+            const uint32_t x4 = qw[4] ^ b.x, x5 = qw[5] ^ b.y, x6 = qw[6] ^ b.z, x7 = qw[7] ^ b.w;
+            const uint32_t s1 = xor3(x0, x1, x2), c1 = maj3(x0, x1, x2);
+            const uint32_t s2 = xor3(x3, x4, x5), c2 = maj3(x3, x4, x5);
+            const uint32_t s3 = xor3(s1, s2, x6), c3 = maj3(s1, s2, x6);
+            const int ones = __popc(s3) + __popc(x7);
+            const int twos = __popc(c1) + __popc(c2) + __popc(c3);
+            const int key = twos * (1 << (KNN_KEY_SHIFT + 1)) + (ones * (1 << KNN_KEY_SHIFT) + (jbase + r));
+            m2 = min(m2, max(m1, key));
+            m1 = min(m1, key);
+        }
+    }
+    const int d1 = m1 == INT_MAX ? INT_MAX : m1 >> KNN_KEY_SHIFT, d2 = m2 == INT_MAX ? INT_MAX : m2 >> KNN_KEY_SHIFT;
+    const int i1 = m1 == INT_MAX ? -1 : m1 & ((1 << KNN_KEY_SHIFT) - 1);
+#endif
     if (qi < A.nq) {
         const int gi = i1 < 0 ? -1 : (int)(row0 + i1) + A.idx_base;
         if (A.nchunks > 1) {
@@ -863,7 +914,7 @@ int orb_launch_knn2(orb_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_db,
     long long rows = (ndb + want_chunks - 1) / want_chunks;
     rows = std::max<long long>(rows, 4 * KNN_TILE);
     rows = ((rows + KNN_TILE - 1) / KNN_TILE) * KNN_TILE;
-    if (rows > (1 << 30)) rows = 1 << 30;
+    if (rows > (1 << KNN_KEY_SHIFT)) rows = 1 << KNN_KEY_SHIFT;       // the packed (distance, row) key of k_knn2
     const int nchunks = (int)((ndb + rows - 1) / rows);
     if (nchunks == 0) {          // empty DB: idx1 = -1, d1 = d2 = INT_MAX for every query
         k_knn2_merge<<<dim3((nq + 127) / 128, npairs), 128, 0, s>>>(nullptr, 0, nq, npairs, d_idx1, d_d1, d_d2);

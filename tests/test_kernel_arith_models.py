@@ -148,3 +148,39 @@ def test_nms_high_byte_lanes_model():
         ml, mr = mask_word(), mask_word()
         up, dn = rng.random(n) < 0.9, rng.random(n) < 0.9
         assert np.array_equal(hibyte_nms(*W, ml, mr, up, dn), direct(*W, ml, mr, up, dn)), trial
+
+
+# ---- k_knn2: carry-save compression of the eight XOR words + packed (distance, row) keys (csrc/orb_match.cu) -------------------------
+def test_knn2_carry_save_popcount_and_packed_key_model():
+    """numpy model of the default k_knn2 inner loop: three carry-save adders (LOP3 0x96 / 0xE8) turn 8 POPC into 5, and the running
+    best / second best are two packed keys with  m2 = min(m2, max(m1, key)); m1 = min(m1, key).  Checked against the plain
+    definition (sum of 8 popcounts; strict '<' scan: first minimum wins, d2 = second order statistic of the distance multiset)."""
+    rng = np.random.default_rng(12)
+    popc = lambda a: np.unpackbits(a.view(np.uint8).reshape(a.shape + (4,)), axis=-1).sum(-1).astype(np.int64)
+    maj = lambda a, b, c: (a & b) | (a & c) | (b & c)
+    for trial in range(20):
+        nrows = int(rng.integers(1, 700))
+        q = rng.integers(0, 2**32, 8, dtype=np.uint64).astype(np.uint32)
+        db = rng.integers(0, 2**32, (nrows, 8), dtype=np.uint64).astype(np.uint32)
+        if trial % 3 == 0:                                  # ties: copies of a few rows, and near copies of the query
+            db[rng.integers(0, nrows, nrows // 2 + 1)] = db[0]
+            db[rng.integers(0, nrows, 3)] = q ^ np.uint32(1 << int(rng.integers(0, 32)))
+        x = db ^ q[None, :]
+        s1, c1 = x[:, 0] ^ x[:, 1] ^ x[:, 2], maj(x[:, 0], x[:, 1], x[:, 2])
+        s2, c2 = x[:, 3] ^ x[:, 4] ^ x[:, 5], maj(x[:, 3], x[:, 4], x[:, 5])
+        s3, c3 = s1 ^ s2 ^ x[:, 6], maj(s1, s2, x[:, 6])
+        d = popc(s3) + popc(x[:, 7]) + 2 * (popc(c1) + popc(c2) + popc(c3))
+        assert np.array_equal(d, popc(x).sum(1))
+        m1 = m2 = 2**31 - 1
+        for r in range(nrows):
+            key = int(d[r]) * (1 << 22) + r
+            m2 = min(m2, max(m1, key))
+            m1 = min(m1, key)
+        e1, e2, ei = 2**31 - 1, 2**31 - 1, -1                # the reference scan, src/ORBmatcher.cc:197-222
+        for r in range(nrows):
+            if d[r] < e1:
+                e2, e1, ei = e1, int(d[r]), r
+            elif d[r] < e2:
+                e2 = int(d[r])
+        assert (m1 >> 22, m1 & (2**22 - 1)) == (e1, ei)
+        assert (2**31 - 1 if m2 == 2**31 - 1 else m2 >> 22) == e2
