@@ -156,7 +156,7 @@ def test_knn2_carry_save_popcount_and_packed_key_model():
     best / second best are two packed keys with  m2 = min(m2, max(m1, key)); m1 = min(m1, key).  Checked against the plain
     definition (sum of 8 popcounts; strict '<' scan: first minimum wins, d2 = second order statistic of the distance multiset)."""
     rng = np.random.default_rng(12)
-    popc = lambda a: np.unpackbits(a.view(np.uint8).reshape(a.shape + (4,)), axis=-1).sum(-1).astype(np.int64)
+    popc = lambda a: np.unpackbits(np.ascontiguousarray(a).view(np.uint8).reshape(a.shape + (4,)), axis=-1).sum(-1).astype(np.int64)
     maj = lambda a, b, c: (a & b) | (a & c) | (b & c)
     for trial in range(20):
         nrows = int(rng.integers(1, 700))
