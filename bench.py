@@ -558,6 +558,41 @@ def run_matching(E):
     ms5 = E.max_over_ranks(e0.elapsed_time(e1))
     pairs5 = reps5 * NQ * NDB / (ms5 * 1e-3)
     fin_h = [t.cpu().numpy() for t in fin]
+    # ---- A/B: the same two workloads on the tensor-core engine (csrc/orb_match_tc.cu: +-1 int8, tcgen05.mma kind::i8, accumulator in
+    #      TMEM).  Exact integer arithmetic, so the results must be bit-identical to the POPC engine's; any difference fails the run.
+    tensor = None
+    if E.args.tensor_ab:
+        check(L.orb_set_knn_engine(ex._h, 1), "orb_set_knn_engine")
+        popc4 = [t.clone() for t in o]
+        for _ in range(3):
+            knn_pairs()
+        E.barrier()
+        e0.record()
+        for _ in range(reps):
+            knn_pairs()
+        e1.record()
+        E.barrier()
+        tms4 = E.max_over_ranks(e0.elapsed_time(e1))
+        require(all(bool(torch.equal(a, b)) for a, b in zip(popc4, o)), "tensor-core kNN differs from the POPC engine on the 2000x2000 blocks")
+        for _ in range(2):
+            tfin = comm.knn2_sharded(d_q5, d_shard, lo, stream=stream)
+        E.barrier()
+        e0.record()
+        for _ in range(reps5):
+            tfin = comm.knn2_sharded(d_q5, d_shard, lo, stream=stream)
+        e1.record()
+        E.barrier()
+        tms5 = E.max_over_ranks(e0.elapsed_time(e1))
+        require(all(np.array_equal(a, b.cpu().numpy()) for a, b in zip(fin_h, tfin)), "tensor-core kNN differs from the POPC engine on the sharded database")
+        check(L.orb_set_knn_engine(ex._h, 0), "orb_set_knn_engine")
+        tp4, tp5 = world * reps * NPAIR * NQ * ND / (tms4 * 1e-3), reps5 * NQ * NDB / (tms5 * 1e-3)
+        # int8 tensor peak: nominal 4.5 POP/s dense per GPU (B200_PROFILING.md family figure: 2x the bf16 2.25 PFLOP/s); each pair is 256 MACs
+        tensor = {"engine": "ORB_KNN_TENSOR: descriptor bits as +-1 int8, tcgen05.mma kind::i8 M128 N256 K32 x 8, accumulator in TMEM, best/second-best scan on tcgen05.ld; Hamming = (256 - dot) / 2",
+                  "bit_exact_vs_popc_engine": True, "default": False,
+                  "pair_blocks_2000x2000": {"pairs_per_s": tp4, "speedup_vs_popc": tp4 / pairs4, "timed_ms": tms4},
+                  "db_sharded_10M": {"pairs_per_s": tp5, "ms_per_query_batch": tms5 / reps5, "speedup_vs_popc": tp5 / pairs5,
+                                     "int8_tensor_frac_nominal": tp5 / world * 512 / 4.5e15},
+                  "note": "experiment (VERDICT r1 item 9); the POPC engine stays the default because the path's contract (BASELINE.json north_star) names integer-pipe kernels"}
     merge_check = None
     if E.args.verify:
         # every rank holds the merged result: all ranks must agree, and rank 0 compares it with ONE scan over the whole database
@@ -593,6 +628,7 @@ def run_matching(E):
                                "popc_frac": pairs5 / world * 8 / pk, "popc_frac_theoretical": pairs5 / world * 8 / (POPC_THEORETICAL_GOPS * 1e9),
                                "merge": ("orb_knn2_sharded_device: k_knn2 + ncclAllGather (%s) + k_knn2_merge on one stream" % transport) if world > 1 else "none (1 shard)",
                                "merge_check": merge_check},
+                "tensor_core_experiment": tensor,
                 "verified": verified}
     return matching
 
@@ -821,6 +857,7 @@ def run_gpu(args):
             "matches_per_s": None if matching is None else {
                 "unit": "descriptor pairs/s (a 'match' = one query's best / second-best over the rows: queries_per_s)",
                 "pair_blocks_2000x2000": matching["pair_blocks_2000x2000"], "db_sharded_10M": matching["db_sharded"],
+                "tensor_core_experiment": matching["tensor_core_experiment"],
                 "popc_peak_gops_measured": matching["popc_peak_gops"], "popc_peak_gops_theoretical": POPC_THEORETICAL_GOPS,
                 "popc_peak_source": matching["popc_peak_source"],
                 "roofline": "POPC pipe: 8 POPC32 per descriptor pair (SURVEY.md §8d)"},
@@ -864,6 +901,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-verify", dest="verify", action="store_false")
     ap.add_argument("--skip-matching", action="store_true")
+    ap.add_argument("--no-tensor-ab", dest="tensor_ab", action="store_false", help="skip the tensor-core kNN A/B")
     ap.add_argument("--quick", action="store_true", help="headline measurement only (profiling runs): no 752x480 pass, no latency / tracking extras")
     ap.add_argument("--e2e-chunk", type=int, default=64)
     args = ap.parse_args()

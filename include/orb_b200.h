@@ -134,6 +134,11 @@ int orb_hamming_knn2(orb_ctx*, const uint8_t* q, int nq, const uint8_t* db, int6
  * device pointers, asynchronous.  idx_base is added to every idx1 >= 0 (global index of a DB shard). */
 int orb_hamming_knn2_device(orb_ctx*, const uint8_t* d_q, int nq, const uint8_t* d_db, int64_t ndb, int npairs,
                             int32_t idx_base, int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, void* stream);
+/* Which kernel computes the brute-force scan.  ORB_KNN_POPC (default, pinned by the path's contract): XOR + carry-save + POPC on the
+ * integer pipes.  ORB_KNN_TENSOR (experiment): descriptor bits as +-1 int8, tcgen05.mma kind::i8 with the accumulator in TMEM,
+ * Hamming = (256 - dot) / 2 — exact integer arithmetic, results bit-identical.  Also ORB_KNN_ENGINE=tensor|popc at orb_create. */
+enum { ORB_KNN_POPC = 0, ORB_KNN_TENSOR = 1 };
+int orb_set_knn_engine(orb_ctx*, int engine);
 /* Exact merge of per-shard results: parts[s] = (idx1, d1, d2) of shard s, each
  * nq int32 laid out as parts[(s*3+k)*nq + i].  best = lexicographic min of (d1, idx1);
  * second = 2nd smallest of the multiset union {d1_s, d2_s}.  Device pointers, asynchronous. */

@@ -23,7 +23,7 @@ EXPORTS = [
     "orb_error_string", "orb_last_cuda_error", "orb_abi_version", "orb_create", "orb_default_context", "orb_destroy", "orb_nlevels",
     "orb_scale_factor", "orb_keypoint_capacity", "orb_set_descriptor_fma", "orb_extract", "orb_extract_batch", "orb_extract_batch_device", "orb_extract_batch_async", "orb_wait",
     "orb_last_launch_count", "orb_profile_enable", "orb_profile_read", "orb_profile_stage_name", "orb_debug_level_info", "orb_debug_level_plane", "orb_descriptor_distance",
-    "orb_hamming_knn2", "orb_hamming_knn2_device", "orb_knn2_merge_device", "orb_match_ratio",
+    "orb_hamming_knn2", "orb_hamming_knn2_device", "orb_set_knn_engine", "orb_knn2_merge_device", "orb_match_ratio",
     "orb_frame_grid_build", "orb_search_by_projection", "orb_search_window", "orb_search_window_best", "orb_search_for_initialization", "orb_search_by_bow", "orb_search_by_bow_kf", "orb_search_for_triangulation", "orb_host_alloc", "orb_host_free",
     "orb_measure_popc_peak",
     "orb_distinctive_descriptors", "orb_cvt_gray", "orb_extract_batch_color", "orb_undistort_keypoints", "orb_image_bounds",
@@ -104,6 +104,7 @@ def lib():
     L.orb_descriptor_distance.argtypes = [vp, vp]
     L.orb_hamming_knn2.argtypes = [vp, vp, i32, vp, i64, vp, vp, vp]
     L.orb_hamming_knn2_device.argtypes = [vp, vp, i32, vp, i64, i32, i32, vp, vp, vp, vp]
+    L.orb_set_knn_engine.argtypes = [vp, i32]
     L.orb_knn2_merge_device.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
     L.orb_match_ratio.argtypes = [vp, vp, vp, vp, i32, f32, i32, vp, C.POINTER(C.c_int)]
     L.orb_frame_grid_build.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]

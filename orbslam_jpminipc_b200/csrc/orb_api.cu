@@ -233,6 +233,7 @@ orb_ctx* orb_create(int device, int nfeatures, float scale_factor, int nlevels, 
     c->score_type = score_type; c->fast_th = fast_th; c->max_w = max_w; c->max_h = max_h; c->max_batch = max_batch;
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (const char* e = getenv("ORB_GRAPH")) c->use_graph = atoi(e);
+    if (const char* e = getenv("ORB_KNN_ENGINE")) c->knn_engine = !strcmp(e, "tensor") ? ORB_KNN_TENSOR : ORB_KNN_POPC;
 #ifdef ORB_DEBUG                 // stage-skipping switch of tools/exposure.sh: only in a -DORB_DEBUG build, never in the shipped library
     if (const char* e = getenv("ORB_DEBUG_SKIP")) c->debug_skip = atoi(e);
 #endif
@@ -706,6 +707,13 @@ int orb_hamming_knn2(orb_ctx* c, const uint8_t* q, int nq, const uint8_t* db, in
         ORB_CUDA(cudaMemcpyAsync(d2, o2, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
     }
     ORB_CUDA(cudaStreamSynchronize(s));
+    return ORB_OK;
+}
+
+int orb_set_knn_engine(orb_ctx* c, int engine)
+{
+    if (!c || (engine != ORB_KNN_POPC && engine != ORB_KNN_TENSOR)) return ORB_ERR_INVALID;
+    c->knn_engine = engine;
     return ORB_OK;
 }
 

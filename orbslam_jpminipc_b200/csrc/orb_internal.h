@@ -189,6 +189,7 @@ struct orb_ctx {
     int rs_flex_width = 1;                                 // ORB_RESIZE_FLEX=0: fixed 128-column k_resize tiles (A/B timing)
     int rs_rows_pref = 8;                                  // ORB_RESIZE_ROWS: output rows per k_resize thread (tile height = 8 * rows at 128 columns)
     int select_serial = 0;                                 // ORB_SELECT_SERIAL=1: the thread-per-cell selection kernel (A/B timing)
+    int knn_engine = 0;                                    // ORB_KNN_POPC (default) / ORB_KNN_TENSOR: orb_set_knn_engine, ORB_KNN_ENGINE=tensor
     int use_graph = 1;                                     // ORB_GRAPH=0 switches the CUDA-graph replay off
     long long plan_gen = 0;                                // bumped whenever the plan (image shape) is rebuilt
     int fork_early = 0, fast_ctas = 6, blur_ctas = 8;      // stream-overlap tuning (ORB_FORK_EARLY / ORB_FAST_CTAS_FORK / ORB_BLUR_CTAS env)
@@ -226,6 +227,9 @@ int orb_resize_smem_setup(int max_bytes);
 // orb_match.cu
 int orb_launch_knn2(orb_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_db, int64_t ndb, int npairs, int32_t idx_base,
                     int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, cudaStream_t s);
+int orb_launch_knn2_tc(orb_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_db, int64_t ndb, int npairs, int32_t idx_base,
+                       int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, cudaStream_t s);      // orb_match_tc.cu
+int orb_launch_knn2_merge_pairs(const int32_t* d_parts, int nparts, int nq, int npairs, int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, cudaStream_t s);
 int orb_launch_knn2_merge(const int32_t* d_parts, int nparts, int nq, int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, cudaStream_t s);
 #define ORB_COMM_MAX_RANKS 16
 // the same merge with one pointer per part (parts may live on peer devices: orb_comm.cu, "p2p" transport)

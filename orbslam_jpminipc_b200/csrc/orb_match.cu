@@ -922,6 +922,7 @@ int orb_launch_knn2(orb_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_db,
         ORB_CUDA(cudaGetLastError());
         return ORB_OK;
     }
+    if (c->knn_engine == ORB_KNN_TENSOR) return orb_launch_knn2_tc(c, d_q, nq, d_db, ndb, npairs, idx_base, d_idx1, d_d1, d_d2, s);
     if (nchunks > 65535 || npairs > 65535 || qtiles > 65535) return ORB_ERR_CAPACITY;     // grid limits, before anything is allocated
     // global row indices are int32: a shard whose last row does not fit is refused instead of wrapping to negative indices
     // (which the merge would then drop as "empty")
@@ -952,6 +953,13 @@ int orb_launch_knn2(orb_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_db,
 int orb_launch_knn2_merge(const int32_t* d_parts, int nparts, int nq, int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, cudaStream_t s)
 {
     k_knn2_merge<<<dim3((nq + 127) / 128, 1), 128, 0, s>>>(d_parts, nparts, nq, 1, d_idx1, d_d1, d_d2);
+    ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
+}
+
+int orb_launch_knn2_merge_pairs(const int32_t* d_parts, int nparts, int nq, int npairs, int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, cudaStream_t s)
+{
+    k_knn2_merge<<<dim3((nq + 127) / 128, npairs), 128, 0, s>>>(d_parts, nparts, nq, npairs, d_idx1, d_d1, d_d2);
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;
 }

@@ -1,0 +1,293 @@
+// orb_match_tc.cu — EXPERIMENT: brute-force Hamming kNN-2 on the 5th-generation tensor cores.
+//
+// k_knn2 (orb_match.cu) is bound by the POPC / ALU pipes.  The same numbers come out of an exact integer contraction: map every
+// descriptor bit b to the int8 value 2b-1 in {-1,+1}; then for two 256-bit descriptors
+//       dot(q', d') = (#equal bits) - (#different bits) = 256 - 2 * Hamming(q, d)
+// so   Hamming = (256 - dot) / 2,  smallest distance = largest dot.  tcgen05.mma kind::i8 (s8 x s8 -> s32, exact) computes a
+// 128-query x 256-row block of dots per tile (8 instructions of K = 32), the accumulator lives in TMEM, and the CUDA cores only
+//   (1) expand the packed bits of the database tile into the canonical K-major shared-memory operand layout (one 2 KB lookup table:
+//       byte -> eight +-1 bytes), and
+//   (2) run the best / second-best scan on the accumulator read back with tcgen05.ld: per pair one IMAD (key = dot*256 + 255-col)
+//       and three integer min/max — against 5 POPC + 14 LOP3 + ... in k_knn2.
+// The MMA of tile t runs asynchronously (tcgen05.commit -> mbarrier) while the CUDA cores scan tile t-1 out of the other TMEM stage.
+// Results are bit-identical to k_knn2 (same scan semantics: lowest index wins, d2 = second order statistic); selected with
+// orb_set_knn_engine(ctx, ORB_KNN_TENSOR) or ORB_KNN_ENGINE=tensor, never by default (north_star pins the POPC path).
+#include "orb_internal.h"
+#include <algorithm>
+#include <climits>
+
+namespace {
+
+constexpr int TC_THREADS = 256;
+constexpr int TC_M = 128;             // queries per CTA = TMEM lanes
+constexpr int TC_N = 256;             // database rows per tile = accumulator columns of one TMEM stage
+constexpr int TC_KBYTES = 256;        // one int8 per descriptor bit
+constexpr int TC_LBO = 128;           // bytes between the two 16-byte K chunks of one core-matrix pair (K-major, no swizzle)
+constexpr int TC_SBO = 16 * 128;      // bytes between 8-row groups: 16 K-chunks of 128 bytes each
+constexpr int TC_A_BYTES = TC_M * TC_KBYTES;          // 32 KB
+constexpr int TC_B_BYTES = TC_N * TC_KBYTES;          // 64 KB per stage
+constexpr int TC_SMEM = TC_A_BYTES + 2 * TC_B_BYTES + 2048 /* lut */ + 2048 /* merge area + barriers */ + 1024 /* alignment slack */;
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits [0,14), leading byte offset >> 4 in [16,30),
+// stride byte offset >> 4 in [32,46), version 1 in [46,48), layout type SWIZZLE_NONE = 0 in [61,64)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr)
+{
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(TC_LBO >> 4) << 16) | ((uint64_t)(TC_SBO >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (c_format 2), A = B = signed 8 bit (format 1), both K-major,
+// N >> 3 in [17,23), M >> 4 in [24,29)
+constexpr uint32_t TC_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(TC_IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "TC_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra TC_DONE;\n\t"
+        "bra TC_WAIT;\n\t"
+        "TC_DONE:\n\t}" ::"r"(s_u32(bar)), "r"(parity) : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp receives lane (base + i), columns c .. c+31
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct Knn2TcArgs {
+    const uint8_t* q; const uint8_t* db;
+    int nq; long long ndb;
+    int rows_per_chunk, nchunks;
+    int32_t idx_base;
+    int32_t* out;                    // nchunks > 1: partials [pair][chunk][3][nq]
+    int32_t* o_idx1; int32_t* o_d1; int32_t* o_d2;
+};
+
+// one descriptor row (32 bytes in two uint4) -> 256 int8 in the canonical operand layout: chunk c (16 bytes = 16 bits of the row)
+// of row r lives at (r / 8) * SBO + c * LBO + (r % 8) * 16
+__device__ __forceinline__ void expand_row(uint8_t* op, int r, const uint4& lo, const uint4& hi, const uint2* lut)
+{
+    uint8_t* base = op + (r >> 3) * TC_SBO + (r & 7) * 16;
+    const uint32_t w[8] = { lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w };
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint2 e0 = lut[w[i] & 0xff], e1 = lut[(w[i] >> 8) & 0xff], e2 = lut[(w[i] >> 16) & 0xff], e3 = lut[w[i] >> 24];
+        *reinterpret_cast<uint4*>(base + (2 * i) * TC_LBO) = make_uint4(e0.x, e0.y, e1.x, e1.y);
+        *reinterpret_cast<uint4*>(base + (2 * i + 1) * TC_LBO) = make_uint4(e2.x, e2.y, e3.x, e3.y);
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_knn2_tc(Knn2TcArgs A)
+{
+    extern __shared__ uint8_t tc_raw[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>(((uintptr_t)tc_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = sm;
+    uint8_t* sB = sm + TC_A_BYTES;
+    uint2* lut = reinterpret_cast<uint2*>(sm + TC_A_BYTES + 2 * TC_B_BYTES);
+    int* s_merge = reinterpret_cast<int*>(sm + TC_A_BYTES + 2 * TC_B_BYTES + 2048);          // [128][3]: result of the upper column half
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(sm + TC_A_BYTES + 2 * TC_B_BYTES + 2048 + 128 * 3 * 4);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_full + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunk = blockIdx.x, mt = blockIdx.y, pair = blockIdx.z;
+    const long long row0 = (long long)chunk * A.rows_per_chunk;
+    const int nrows = (int)min((long long)A.rows_per_chunk, A.ndb - row0);
+    const uint8_t* db = A.db + ((size_t)pair * A.ndb + row0) * 32;
+    const int ntiles = (nrows + TC_N - 1) / TC_N;
+
+    // ---- one-time setup: TMEM (all 512 columns = two 256-column accumulator stages), barriers, lookup table, query operand ----
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s_u32(s_tmem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        tc_mbar_init(&bar_full[0], 1); tc_mbar_init(&bar_full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        uint32_t lo = 0, hi = 0;                                    // byte value tid -> eight int8: bit k set -> +1, clear -> -1
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            lo |= (((tid >> k) & 1) ? 0x01u : 0xffu) << (8 * k);
+            hi |= (((tid >> (k + 4)) & 1) ? 0x01u : 0xffu) << (8 * k);
+        }
+        lut[tid] = make_uint2(lo, hi);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *s_tmem;
+    if (tid < TC_M) {
+        const int qi = min(mt * TC_M + tid, A.nq - 1);              // rows past nq repeat the last query (never written back)
+        const uint4* qp = reinterpret_cast<const uint4*>(A.q + ((size_t)pair * A.nq + qi) * 32);
+        expand_row(sA, tid, __ldg(qp), __ldg(qp + 1), lut);
+    }
+
+    const uint64_t a_desc = smem_desc(s_u32(sA));
+    const int q4 = warp & 3, half = warp >> 2;                     // TMEM lane quarter this warp may read; column half it scans
+    const uint32_t t_lane = tmem + ((uint32_t)(q4 * 32) << 16);
+    int R1 = INT_MIN, R2 = INT_MIN, RI = -1;                        // running best dot, second-best dot, best row (chunk-relative)
+
+    auto scan_tile = [&](int t) {
+        const int s = t & 1;
+        tc_mbar_wait(&bar_full[s], (uint32_t)((t >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int valid = min(TC_N, nrows - t * TC_N);              // columns >= valid belong to rows past the chunk
+        int m1 = INT_MIN, m2 = INT_MIN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < TC_N / 2; c0 += 32) {
+            const int cbase = half * (TC_N / 2) + c0;
+            if (cbase >= valid) break;
+            int v[32];
+            tmem_ld32(t_lane + (uint32_t)(s * TC_N + cbase), v);
+            if (cbase + 32 <= valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const int key = v[j] * 256 + (255 - (cbase + j));
+                    m2 = max(m2, min(m1, key));
+                    m1 = max(m1, key);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const int key = (cbase + j < valid) ? v[j] * 256 + (255 - (cbase + j)) : INT_MIN;
+                    m2 = max(m2, min(m1, key));
+                    m1 = max(m1, key);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (m1 != INT_MIN) {                                        // fold the tile into the running result: earlier tiles hold lower rows
+            const int t1 = m1 >> 8, ti = t * TC_N + (255 - (m1 & 255));
+            const int t2 = m2 == INT_MIN ? INT_MIN : (m2 >> 8);
+            if (t1 > R1) { R2 = max(R1, t2); R1 = t1; RI = ti; }
+            else R2 = max(R2, t1);
+        }
+    };
+
+    uint4 nlo = make_uint4(0, 0, 0, 0), nhi = nlo;                  // this thread's database row of the next tile
+    if (tid < nrows) { const uint4* p = reinterpret_cast<const uint4*>(db + (size_t)tid * 32); nlo = __ldg(p); nhi = __ldg(p + 1); }
+    for (int t = 0; t < ntiles; t++) {
+        const int s = t & 1;
+        uint8_t* Bs = sB + s * TC_B_BYTES;
+        // stage s was last read by the MMAs of tile t-2, whose completion scan_tile(t-2) waited for
+        if (t * TC_N + tid < nrows) expand_row(Bs, tid, nlo, nhi, lut);
+        {
+            const long long nr = (long long)(t + 1) * TC_N + tid;
+            if (nr < nrows) { const uint4* p = reinterpret_cast<const uint4*>(db + (size_t)nr * 32); nlo = __ldg(p); nhi = __ldg(p + 1); }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy stores -> visible to the tensor core's async proxy
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t b_desc = smem_desc(s_u32(Bs));
+#pragma unroll
+            for (int k = 0; k < TC_KBYTES / 32; k++)                    // K = 32 int8 per instruction = two 16-byte chunks = 2 * LBO bytes
+                mma_i8(tmem + (uint32_t)(s * TC_N), a_desc + (uint64_t)((k * 2 * TC_LBO) >> 4), b_desc + (uint64_t)((k * 2 * TC_LBO) >> 4), k > 0);
+            mma_commit(&bar_full[s]);
+        }
+        if (t > 0) scan_tile(t - 1);                                    // CUDA cores scan tile t-1 while the tensor core computes tile t
+    }
+    scan_tile(ntiles - 1);
+
+    // ---- merge the two column halves of every query, convert dots to distances, write ----
+    __syncthreads();
+    const int row = q4 * 32 + lane;
+    if (half == 1) { s_merge[row * 3] = R1; s_merge[row * 3 + 1] = R2; s_merge[row * 3 + 2] = RI; }
+    __syncthreads();
+    if (half == 0) {
+        const int o1 = s_merge[row * 3], o2 = s_merge[row * 3 + 1], oi = s_merge[row * 3 + 2];
+        if (oi >= 0) {
+            if (RI < 0) { R1 = o1; R2 = o2; RI = oi; }
+            else if (o1 > R1 || (o1 == R1 && oi < RI)) { R2 = max(R1, o2); R1 = o1; RI = oi; }
+            else R2 = max(R2, o1);
+        }
+        const int qi = mt * TC_M + row;
+        if (qi < A.nq) {
+            const int d1 = RI < 0 ? INT_MAX : (256 - R1) >> 1, d2 = R2 == INT_MIN ? INT_MAX : (256 - R2) >> 1;
+            const int gi = RI < 0 ? -1 : (int)(row0 + RI) + A.idx_base;
+            if (A.nchunks > 1) {
+                int32_t* o = A.out + ((size_t)(pair * A.nchunks + chunk) * 3) * A.nq;
+                o[qi] = gi; o[A.nq + qi] = d1; o[2 * A.nq + qi] = d2;
+            } else {
+                const size_t o = (size_t)pair * A.nq + qi;
+                A.o_idx1[o] = gi; A.o_d1[o] = d1; A.o_d2[o] = d2;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+} // namespace
+
+int orb_launch_knn2_tc(orb_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_db, int64_t ndb, int npairs, int32_t idx_base,
+                       int32_t* d_idx1, int32_t* d_d1, int32_t* d_d2, cudaStream_t s)
+{
+    if (ndb <= 0) return ORB_ERR_INVALID;                      // the empty database is handled by the caller (orb_launch_knn2)
+    static int smem_set[64] = { 0 };
+    int dev = 0;
+    ORB_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !smem_set[dev]) {
+        ORB_CUDA(cudaFuncSetAttribute(k_knn2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+        smem_set[dev] = 1;
+    }
+    const int mtiles = (nq + TC_M - 1) / TC_M;
+    // one CTA per SM (shared memory + all of TMEM): as many chunks as fill one wave of SMs, chunks a multiple of the tile
+    long long want_chunks = std::max<long long>(1, (long long)c->num_sms / ((long long)mtiles * npairs));
+    long long rows = (ndb + want_chunks - 1) / want_chunks;
+    rows = std::max<long long>(rows, 8 * TC_N);
+    rows = ((rows + TC_N - 1) / TC_N) * TC_N;
+    if (rows > (1 << 22)) rows = 1 << 22;
+    const int nchunks = (int)((ndb + rows - 1) / rows);
+    if (nchunks > 65535 || npairs > 65535 || mtiles > 65535) return ORB_ERR_CAPACITY;
+    if (idx_base < 0) return ORB_ERR_INVALID;
+    if (ndb + (int64_t)idx_base > (int64_t)INT_MAX) return ORB_ERR_CAPACITY;
+    Knn2TcArgs A;
+    A.q = d_q; A.db = d_db; A.nq = nq; A.ndb = ndb; A.rows_per_chunk = (int)rows; A.nchunks = nchunks;
+    A.idx_base = idx_base; A.out = nullptr; A.o_idx1 = d_idx1; A.o_d1 = d_d1; A.o_d2 = d_d2;
+    int32_t* part = nullptr;
+    if (nchunks > 1) {
+        ORB_CUDA(cudaMallocFromPoolAsync((void**)&part, (size_t)npairs * nchunks * 3 * nq * sizeof(int32_t), c->pool, s));
+        A.out = part;
+    }
+    k_knn2_tc<<<dim3(nchunks, mtiles, npairs), TC_THREADS, TC_SMEM, s>>>(A);
+    c->last_launches = 1;
+    if (nchunks > 1) {
+        int rc = orb_launch_knn2_merge_pairs(part, nchunks, nq, npairs, d_idx1, d_d1, d_d2, s);
+        if (rc) return rc;
+        c->last_launches = 2;
+        ORB_CUDA(cudaFreeAsync(part, s));
+    }
+    ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
+}

@@ -559,3 +559,47 @@ def test_search_for_triangulation_vs_oracle(pkg, po, n1, n2, nnodes, ori, seed):
     assert rn > 3 and n == rn and np.array_equal(m12, rm12)
     assert len(pairs) == n and not has1[pairs[:, 0]].any() and not has2[pairs[:, 1]].any()
     assert len(np.unique(pairs[:, 1])) == len(pairs)       # a KF2 feature is matched once
+
+
+@pytest.mark.parametrize("nq,ndb", [(2000, 2000), (300, 5000), (1, 1), (257, 255), (2000, 70001), (5, 3), (129, 513), (128, 256), (640, 300000)])
+def test_knn2_tensor_core_engine_bit_exact(pkg, po, nq, ndb):
+    """ORB_KNN_TENSOR (csrc/orb_match_tc.cu): descriptor bits as +-1 int8 through tcgen05.mma kind::i8, Hamming = (256 - dot) / 2.
+    Exact integer arithmetic: (idx1, d1, d2) must equal the oracle's scan (and therefore the POPC engine) bit for bit."""
+    from orbslam_jpminipc_b200._lib import check, lib
+    from orbslam_jpminipc_b200.synth import synth_descriptors
+    m = pkg.ORBmatcher(0.6, True)
+    check(lib().orb_set_knn_engine(m._h, 1), "orb_set_knn_engine")
+    db, q = synth_descriptors(ndb, nq, dup_frac=0.02)
+    got = m.knn2(q, db)
+    ref = po.knn2(q, db)
+    assert all(np.array_equal(a, b) for a, b in zip(got, ref))
+    check(lib().orb_set_knn_engine(m._h, 0), "orb_set_knn_engine")
+    assert all(np.array_equal(a, b) for a, b in zip(m.knn2(q, db), ref))
+
+
+def test_knn2_tensor_core_engine_extremes(pkg, po):
+    """all-equal / all-different bits (dot = +256 / -256), ties across tiles and column halves, multi-pair launches"""
+    import ctypes as C
+    import torch
+    from orbslam_jpminipc_b200._lib import check, lib, ptr
+    L = lib()
+    m = pkg.ORBmatcher(0.6, True)
+    check(L.orb_set_knn_engine(m._h, 1), "orb_set_knn_engine")
+    rng = np.random.default_rng(3)
+    db = rng.integers(0, 256, (1500, 32), dtype=np.uint8)
+    db[700] = db[3]; db[1300] = db[3]; db[200] = ~db[5]; db[129] = db[128]
+    q = np.stack([db[3], ~db[3], db[5], db[128], np.zeros(32, np.uint8), np.full(32, 255, np.uint8)] + [db[i] for i in range(300, 420)])
+    assert all(np.array_equal(a, b) for a, b in zip(m.knn2(q, db), po.knn2(q, db)))
+    # several (query, database) blocks in one launch
+    npair, nq, nd = 5, 200, 700
+    qs = rng.integers(0, 256, (npair, nq, 32), dtype=np.uint8); ds = rng.integers(0, 256, (npair, nd, 32), dtype=np.uint8)
+    qs[:, ::2] = ds[:, :nq // 2] ^ np.packbits((rng.random((npair, nq // 2, 256)) < 0.05).astype(np.uint8), axis=2)
+    dev = torch.device("cuda", 0)
+    dq, dd = torch.from_numpy(qs).to(dev), torch.from_numpy(ds).to(dev)
+    o = [torch.zeros(npair * nq, dtype=torch.int32, device=dev) for _ in range(3)]
+    check(L.orb_hamming_knn2_device(m._h, ptr(dq), nq, ptr(dd), nd, npair, 0, ptr(o[0]), ptr(o[1]), ptr(o[2]),
+                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)), "knn2 pairs")
+    torch.cuda.synchronize()
+    for p in range(npair):
+        ref = po.knn2(qs[p], ds[p])
+        assert all(np.array_equal(o[k][p * nq:(p + 1) * nq].cpu().numpy(), ref[k]) for k in range(3)), p
