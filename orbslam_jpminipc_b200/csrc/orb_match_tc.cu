@@ -18,7 +18,9 @@
 
 namespace {
 
-constexpr int TC_THREADS = 256;
+constexpr int TC_SCAN_WARPS = 8;      // warps 0..7: best / second-best scan of the accumulator (TMEM lane quarter = warp & 3, column half = warp >> 2)
+constexpr int TC_PROD_WARPS = 4;      // warps 8..11: expand database bits into the int8 operand tile
+constexpr int TC_THREADS = (TC_SCAN_WARPS + TC_PROD_WARPS + 1) * 32;      // + warp 12: TMEM allocation and the MMA issuer
 constexpr int TC_M = 128;             // queries per CTA = TMEM lanes
 constexpr int TC_N = 256;             // database rows per tile = accumulator columns of one TMEM stage
 constexpr int TC_KBYTES = 256;        // one int8 per descriptor bit
@@ -26,7 +28,9 @@ constexpr int TC_LBO = 128;           // bytes between the two 16-byte K chunks 
 constexpr int TC_SBO = 16 * 128;      // bytes between 8-row groups: 16 K-chunks of 128 bytes each
 constexpr int TC_A_BYTES = TC_M * TC_KBYTES;          // 32 KB
 constexpr int TC_B_BYTES = TC_N * TC_KBYTES;          // 64 KB per stage
-constexpr int TC_SMEM = TC_A_BYTES + 2 * TC_B_BYTES + 2048 /* lut */ + 2048 /* merge area + barriers */ + 1024 /* alignment slack */;
+constexpr int TC_LUT_COPIES = 16;                     // lane pair j reads copy j: at most 2-way bank conflicts on the table
+constexpr int TC_LUT_BYTES = 256 * TC_LUT_COPIES * 8; // 32 KB
+constexpr int TC_SMEM = TC_A_BYTES + 2 * TC_B_BYTES + TC_LUT_BYTES + 2048 /* merge area + barriers */ + 1024 /* alignment slack */;
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -56,6 +60,10 @@ __device__ __forceinline__ void tc_mbar_init(uint64_t* bar, int count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity)
 {
     asm volatile(
@@ -66,7 +74,8 @@ __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity)
         "bra TC_WAIT;\n\t"
         "TC_DONE:\n\t}" ::"r"(s_u32(bar)), "r"(parity) : "memory");
 }
-// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp receives lane (base + i), columns c .. c+31
+// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp receives lane (base + i), columns c .. c+31.  Asynchronous: the
+// registers are valid after tmem_ld_wait().
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32])
 {
     asm volatile(
@@ -78,7 +87,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32])
           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// the loaded registers pass THROUGH the wait as in/out operands, so that no use of them can be scheduled ahead of it
+__device__ __forceinline__ void tmem_ld_wait(int (&v)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+          "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+          "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+          "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+        :: "memory");
 }
 
 struct Knn2TcArgs {
@@ -91,19 +109,27 @@ struct Knn2TcArgs {
 };
 
 // one descriptor row (32 bytes in two uint4) -> 256 int8 in the canonical operand layout: chunk c (16 bytes = 16 bits of the row)
-// of row r lives at (r / 8) * SBO + c * LBO + (r % 8) * 16
-__device__ __forceinline__ void expand_row(uint8_t* op, int r, const uint4& lo, const uint4& hi, const uint2* lut)
+// of row r lives at (r / 8) * SBO + c * LBO + (r % 8) * 16.  lutc = this lane's copy of the byte -> eight +-1 bytes table.
+__device__ __forceinline__ void expand_row(uint8_t* op, int r, const uint4& lo, const uint4& hi, const uint8_t* lutc)
 {
     uint8_t* base = op + (r >> 3) * TC_SBO + (r & 7) * 16;
     const uint32_t w[8] = { lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w };
+    constexpr int ES = TC_LUT_COPIES * 8;                            // bytes between consecutive table entries of one copy
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        const uint2 e0 = lut[w[i] & 0xff], e1 = lut[(w[i] >> 8) & 0xff], e2 = lut[(w[i] >> 16) & 0xff], e3 = lut[w[i] >> 24];
+        const uint2 e0 = *reinterpret_cast<const uint2*>(lutc + (w[i] & 0xffu) * ES);
+        const uint2 e1 = *reinterpret_cast<const uint2*>(lutc + ((w[i] >> 8) & 0xffu) * ES);
+        const uint2 e2 = *reinterpret_cast<const uint2*>(lutc + ((w[i] >> 16) & 0xffu) * ES);
+        const uint2 e3 = *reinterpret_cast<const uint2*>(lutc + (w[i] >> 24) * ES);
         *reinterpret_cast<uint4*>(base + (2 * i) * TC_LBO) = make_uint4(e0.x, e0.y, e1.x, e1.y);
         *reinterpret_cast<uint4*>(base + (2 * i + 1) * TC_LBO) = make_uint4(e2.x, e2.y, e3.x, e3.y);
     }
 }
 
+// Warp-specialised, three asynchronous stages joined by mbarriers (tile t uses stage s = t & 1, k-th use of a stage has parity k & 1):
+//   producers : wait full[s] of tile t-2 (its MMAs have read the stage)  -> expand tile t -> fence.proxy.async -> arrive ready[s]
+//   MMA issuer: wait ready[s], wait tfree[s] of tile t-2 (scanners done with the TMEM stage) -> 8 x tcgen05.mma -> commit -> full[s]
+//   scanners  : wait full[s] -> tcgen05.ld + min/max scan -> arrive tfree[s]
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_knn2_tc(Knn2TcArgs A)
 {
@@ -111,10 +137,11 @@ k_knn2_tc(Knn2TcArgs A)
     uint8_t* sm = reinterpret_cast<uint8_t*>(((uintptr_t)tc_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = sm;
     uint8_t* sB = sm + TC_A_BYTES;
-    uint2* lut = reinterpret_cast<uint2*>(sm + TC_A_BYTES + 2 * TC_B_BYTES);
-    int* s_merge = reinterpret_cast<int*>(sm + TC_A_BYTES + 2 * TC_B_BYTES + 2048);          // [128][3]: result of the upper column half
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(sm + TC_A_BYTES + 2 * TC_B_BYTES + 2048 + 128 * 3 * 4);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_full + 2);
+    uint8_t* lut = sm + TC_A_BYTES + 2 * TC_B_BYTES;
+    int* s_merge = reinterpret_cast<int*>(lut + TC_LUT_BYTES);                           // [128][3]: result of the upper column half
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lut + TC_LUT_BYTES + 128 * 3 * 4);
+    uint64_t *bar_ready = bars, *bar_full = bars + 2, *bar_tfree = bars + 4;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 6);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int chunk = blockIdx.x, mt = blockIdx.y, pair = blockIdx.z;
@@ -122,108 +149,138 @@ k_knn2_tc(Knn2TcArgs A)
     const int nrows = (int)min((long long)A.rows_per_chunk, A.ndb - row0);
     const uint8_t* db = A.db + ((size_t)pair * A.ndb + row0) * 32;
     const int ntiles = (nrows + TC_N - 1) / TC_N;
+    const bool scanner = warp < TC_SCAN_WARPS, producer = warp >= TC_SCAN_WARPS && warp < TC_SCAN_WARPS + TC_PROD_WARPS;
 
     // ---- one-time setup: TMEM (all 512 columns = two 256-column accumulator stages), barriers, lookup table, query operand ----
-    if (warp == 0) {
+    if (warp == TC_SCAN_WARPS + TC_PROD_WARPS) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s_u32(s_tmem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        tc_mbar_init(&bar_full[0], 1); tc_mbar_init(&bar_full[1], 1);
+        for (int i = 0; i < 2; i++) { tc_mbar_init(&bar_ready[i], TC_PROD_WARPS); tc_mbar_init(&bar_full[i], 1); tc_mbar_init(&bar_tfree[i], TC_SCAN_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    {
-        uint32_t lo = 0, hi = 0;                                    // byte value tid -> eight int8: bit k set -> +1, clear -> -1
+    for (int i = tid; i < 256 * TC_LUT_COPIES; i += TC_THREADS) {
+        const int b = i / TC_LUT_COPIES;
+        uint32_t lo = 0, hi = 0;                                    // byte value b -> eight int8: bit k set -> +1, clear -> -1
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            lo |= (((tid >> k) & 1) ? 0x01u : 0xffu) << (8 * k);
-            hi |= (((tid >> (k + 4)) & 1) ? 0x01u : 0xffu) << (8 * k);
+            lo |= (((b >> k) & 1) ? 0x01u : 0xffu) << (8 * k);
+            hi |= (((b >> (k + 4)) & 1) ? 0x01u : 0xffu) << (8 * k);
         }
-        lut[tid] = make_uint2(lo, hi);
+        reinterpret_cast<uint2*>(lut)[i] = make_uint2(lo, hi);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *s_tmem;
-    if (tid < TC_M) {
-        const int qi = min(mt * TC_M + tid, A.nq - 1);              // rows past nq repeat the last query (never written back)
+    const uint8_t* lutc = lut + (lane >> 1) * 8;
+    if (producer) {
+        const int r = tid - TC_SCAN_WARPS * 32;                     // 0..127: one query row per producer thread
+        const int qi = min(mt * TC_M + r, A.nq - 1);                // rows past nq repeat the last query (never written back)
         const uint4* qp = reinterpret_cast<const uint4*>(A.q + ((size_t)pair * A.nq + qi) * 32);
-        expand_row(sA, tid, __ldg(qp), __ldg(qp + 1), lut);
+        expand_row(sA, r, __ldg(qp), __ldg(qp + 1), lutc);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    __syncthreads();
 
-    const uint64_t a_desc = smem_desc(s_u32(sA));
-    const int q4 = warp & 3, half = warp >> 2;                     // TMEM lane quarter this warp may read; column half it scans
-    const uint32_t t_lane = tmem + ((uint32_t)(q4 * 32) << 16);
-    int R1 = INT_MIN, R2 = INT_MIN, RI = -1;                        // running best dot, second-best dot, best row (chunk-relative)
+    int R1 = INT_MIN, R2 = INT_MIN, RI = -1;                        // scanners: running best dot, second-best dot, best row (chunk-relative)
+    const int q4 = warp & 3, half = (warp >> 2) & 1;
 
-    auto scan_tile = [&](int t) {
-        const int s = t & 1;
-        tc_mbar_wait(&bar_full[s], (uint32_t)((t >> 1) & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int valid = min(TC_N, nrows - t * TC_N);              // columns >= valid belong to rows past the chunk
-        int m1 = INT_MIN, m2 = INT_MIN;
-#pragma unroll 1
-        for (int c0 = 0; c0 < TC_N / 2; c0 += 32) {
-            const int cbase = half * (TC_N / 2) + c0;
-            if (cbase >= valid) break;
-            int v[32];
-            tmem_ld32(t_lane + (uint32_t)(s * TC_N + cbase), v);
-            if (cbase + 32 <= valid) {
+    if (producer) {
+        const int p = tid - TC_SCAN_WARPS * 32;                     // rows p and p + 128 of every tile
+        uint4 r0lo = make_uint4(0, 0, 0, 0), r0hi = r0lo, r1lo = r0lo, r1hi = r0lo;
+        auto fetch = [&](int t) {
+            const long long a = (long long)t * TC_N + p, b = a + 128;
+            if (a < nrows) { const uint4* g = reinterpret_cast<const uint4*>(db + (size_t)a * 32); r0lo = __ldg(g); r0hi = __ldg(g + 1); }
+            if (b < nrows) { const uint4* g = reinterpret_cast<const uint4*>(db + (size_t)b * 32); r1lo = __ldg(g); r1hi = __ldg(g + 1); }
+        };
+        fetch(0);
+        for (int t = 0; t < ntiles; t++) {
+            const int s = t & 1;
+            uint8_t* Bs = sB + s * TC_B_BYTES;
+            if (t >= 2) tc_mbar_wait(&bar_full[s], (uint32_t)(((t - 2) >> 1) & 1));     // the MMAs of tile t-2 have consumed this stage
+            if ((long long)t * TC_N + p < nrows) expand_row(Bs, p, r0lo, r0hi, lutc);
+            if ((long long)t * TC_N + p + 128 < nrows) expand_row(Bs, p + 128, r1lo, r1hi, lutc);
+            if (t + 1 < ntiles) fetch(t + 1);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                // generic-proxy stores -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(&bar_ready[s]);
+        }
+    } else if (warp == TC_SCAN_WARPS + TC_PROD_WARPS) {
+        if (lane == 0) {
+            const uint64_t a_desc = smem_desc(s_u32(sA));
+            for (int t = 0; t < ntiles; t++) {
+                const int s = t & 1;
+                tc_mbar_wait(&bar_ready[s], (uint32_t)((t >> 1) & 1));
+                if (t >= 2) tc_mbar_wait(&bar_tfree[s], (uint32_t)(((t - 2) >> 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t b_desc = smem_desc(s_u32(sB + s * TC_B_BYTES));
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const int key = v[j] * 256 + (255 - (cbase + j));
-                    m2 = max(m2, min(m1, key));
-                    m1 = max(m1, key);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const int key = (cbase + j < valid) ? v[j] * 256 + (255 - (cbase + j)) : INT_MIN;
-                    m2 = max(m2, min(m1, key));
-                    m1 = max(m1, key);
-                }
+                for (int k = 0; k < TC_KBYTES / 32; k++)                // K = 32 int8 per instruction = two 16-byte chunks = 2 * LBO bytes
+                    mma_i8(tmem + (uint32_t)(s * TC_N), a_desc + (uint64_t)((k * 2 * TC_LBO) >> 4), b_desc + (uint64_t)((k * 2 * TC_LBO) >> 4), k > 0);
+                mma_commit(&bar_full[s]);
             }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        if (m1 != INT_MIN) {                                        // fold the tile into the running result: earlier tiles hold lower rows
-            const int t1 = m1 >> 8, ti = t * TC_N + (255 - (m1 & 255));
-            const int t2 = m2 == INT_MIN ? INT_MIN : (m2 >> 8);
-            if (t1 > R1) { R2 = max(R1, t2); R1 = t1; RI = ti; }
-            else R2 = max(R2, t1);
-        }
-    };
-
-    uint4 nlo = make_uint4(0, 0, 0, 0), nhi = nlo;                  // this thread's database row of the next tile
-    if (tid < nrows) { const uint4* p = reinterpret_cast<const uint4*>(db + (size_t)tid * 32); nlo = __ldg(p); nhi = __ldg(p + 1); }
-    for (int t = 0; t < ntiles; t++) {
-        const int s = t & 1;
-        uint8_t* Bs = sB + s * TC_B_BYTES;
-        // stage s was last read by the MMAs of tile t-2, whose completion scan_tile(t-2) waited for
-        if (t * TC_N + tid < nrows) expand_row(Bs, tid, nlo, nhi, lut);
-        {
-            const long long nr = (long long)(t + 1) * TC_N + tid;
-            if (nr < nrows) { const uint4* p = reinterpret_cast<const uint4*>(db + (size_t)nr * 32); nlo = __ldg(p); nhi = __ldg(p + 1); }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy stores -> visible to the tensor core's async proxy
-        __syncthreads();
-        if (tid == 0) {
+    } else {
+        const uint32_t t_lane = tmem + ((uint32_t)(q4 * 32) << 16);
+        for (int t = 0; t < ntiles; t++) {
+            const int s = t & 1;
+            tc_mbar_wait(&bar_full[s], (uint32_t)((t >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t b_desc = smem_desc(s_u32(Bs));
+            const int valid = min(TC_N, nrows - t * TC_N);              // columns >= valid belong to rows past the chunk
+            const int cb0 = half * (TC_N / 2);
+            const uint32_t tcol = t_lane + (uint32_t)(s * TC_N + cb0);
+            int m1 = INT_MIN, m2 = INT_MIN;
+            auto scan32 = [&](const int (&v)[32], int cbase) {
+                if (cbase + 32 <= valid) {
 #pragma unroll
-            for (int k = 0; k < TC_KBYTES / 32; k++)                    // K = 32 int8 per instruction = two 16-byte chunks = 2 * LBO bytes
-                mma_i8(tmem + (uint32_t)(s * TC_N), a_desc + (uint64_t)((k * 2 * TC_LBO) >> 4), b_desc + (uint64_t)((k * 2 * TC_LBO) >> 4), k > 0);
-            mma_commit(&bar_full[s]);
+                    for (int j = 0; j < 32; j++) {
+                        const int key = v[j] * 256 + (255 - (cbase + j));
+                        m2 = max(m2, min(m1, key));
+                        m1 = max(m1, key);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const int key = (cbase + j < valid) ? v[j] * 256 + (255 - (cbase + j)) : INT_MIN;
+                        m2 = max(m2, min(m1, key));
+                        m1 = max(m1, key);
+                    }
+                }
+            };
+            // two register buffers: the load of the next 32 columns is in flight while the current 32 are scanned
+            int va[32], vb[32];
+            tmem_ld32(tcol, va);
+            tmem_ld_wait(va);
+            tmem_ld32(tcol + 32, vb);
+            scan32(va, cb0);
+            tmem_ld_wait(vb);
+            tmem_ld32(tcol + 64, va);
+            scan32(vb, cb0 + 32);
+            tmem_ld_wait(va);
+            tmem_ld32(tcol + 96, vb);
+            scan32(va, cb0 + 64);
+            tmem_ld_wait(vb);
+            scan32(vb, cb0 + 96);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(&bar_tfree[s]);
+            if (m1 != INT_MIN) {                                        // fold the tile into the running result: earlier tiles hold lower rows
+                const int t1 = m1 >> 8, ti = t * TC_N + (255 - (m1 & 255));
+                const int t2 = m2 == INT_MIN ? INT_MIN : (m2 >> 8);
+                if (t1 > R1) { R2 = max(R1, t2); R1 = t1; RI = ti; }
+                else R2 = max(R2, t1);
+            }
         }
-        if (t > 0) scan_tile(t - 1);                                    // CUDA cores scan tile t-1 while the tensor core computes tile t
     }
-    scan_tile(ntiles - 1);
 
     // ---- merge the two column halves of every query, convert dots to distances, write ----
     __syncthreads();
     const int row = q4 * 32 + lane;
-    if (half == 1) { s_merge[row * 3] = R1; s_merge[row * 3 + 1] = R2; s_merge[row * 3 + 2] = RI; }
+    if (scanner && half == 1) { s_merge[row * 3] = R1; s_merge[row * 3 + 1] = R2; s_merge[row * 3 + 2] = RI; }
     __syncthreads();
-    if (half == 0) {
+    if (scanner && half == 0) {
         const int o1 = s_merge[row * 3], o2 = s_merge[row * 3 + 1], oi = s_merge[row * 3 + 2];
         if (oi >= 0) {
             if (RI < 0) { R1 = o1; R2 = o2; RI = oi; }
@@ -245,7 +302,7 @@ k_knn2_tc(Knn2TcArgs A)
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    if (warp == TC_SCAN_WARPS + TC_PROD_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
 } // namespace
