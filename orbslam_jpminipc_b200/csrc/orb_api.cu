@@ -142,7 +142,7 @@ static int prepare_ws(orb_ctx* c, WorkSet& W, int nimg)
     rc = ensure(W.d_ntotal, W.ntotal_bytes, B * (size_t)P.ncells * 4); if (rc) return rc;
     rc = ensure(W.d_lvl, W.lvl_bytes, B * (size_t)P.lvl_total * 8); if (rc) return rc;
     rc = ensure(W.d_nkept, W.nkept_bytes, B * ORB_MAX_LEVELS * sizeof(int)); if (rc) return rc;
-    rc = ensure(W.d_counters, W.counters_bytes, 32 * sizeof(int)); if (rc) return rc;
+    rc = ensure(W.d_counters, W.counters_bytes, (32 + B * ORB_MAX_LEVELS) * sizeof(int)); if (rc) return rc;     // tile queues + k_pyramid's (frame, level) counters
     if (!W.aux_stream) {
         ORB_CUDA(cudaStreamCreateWithFlags(&W.aux_stream, cudaStreamNonBlocking));
         ORB_CUDA(cudaEventCreateWithFlags(&W.ev_fork, cudaEventDisableTiming));
@@ -237,6 +237,7 @@ orb_ctx* orb_create(int device, int nfeatures, float scale_factor, int nlevels, 
 #ifdef ORB_DEBUG                 // stage-skipping switch of tools/exposure.sh: only in a -DORB_DEBUG build, never in the shipped library
     if (const char* e = getenv("ORB_DEBUG_SKIP")) c->debug_skip = atoi(e);
 #endif
+    if (const char* e = getenv("ORB_PYR_FUSED")) c->pyr_fused = atoi(e);
     if (const char* e = getenv("ORB_RESIZE_FLEX")) c->rs_flex_width = atoi(e) != 0;
     if (const char* e = getenv("ORB_RESIZE_ROWS")) c->rs_rows_pref = std::max(1, std::min(atoi(e), 32));
     if (const char* e = getenv("ORB_SELECT_SERIAL")) c->select_serial = atoi(e);

@@ -219,6 +219,188 @@ k_resize(const __grid_constant__ CUtensorMap tm, uint8_t* __restrict__ planes, s
     }
 }
 
+// ------------------------------------------------------------------ K1, fused
+// The whole resize cascade (levels 1 .. nlevels-1 of every frame) in ONE persistent launch instead of one launch per level: seven
+// serial launches cost seven ramp-ups and seven tails (levels 4..7 are only a few hundred tiles per 64 frames).  Work items are
+// numbered LEVEL-MAJOR over the batch (all tiles of level 1 of all frames, then level 2, ...) and handed out in that order by an
+// atomic counter; an item of level l >= 2 needs level l-1 of ITS frame complete, which is tracked by one counter of finished tiles
+// per (frame, level).  Every dependency of an item has a smaller item number, i.e. has been claimed by a running CTA before, and a
+// CTA publishes the completion of its current item BEFORE it blocks on the dependency of its next one, so the waits cannot form a
+// cycle (for a single frame they simply serialise the levels).  With a whole batch in flight the dependencies of an item were
+// finished thousands of items earlier and the wait is one acquire load.
+// Visibility: producers store with the generic proxy, __syncthreads, then thread 0 fences (gpu scope, cumulative) and bumps the
+// counter; the consumer's thread 0 acquires the counter and issues fence.proxy.async before the TMA (async proxy) read.
+struct PyrLevel { int tile_w, rows, box_w, box_h, tiles_x, ntiles, item_base, pad; };
+struct PyrParams { PyrLevel L[ORB_MAX_LEVELS]; int nlevels, total, buf_bytes, nimg; };
+
+__global__ void __launch_bounds__(ORB_RESIZE_THREADS)
+k_pyramid(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ planes, size_t fbytes, const Plan* __restrict__ plan,
+          const __grid_constant__ PyrParams P, const int2* __restrict__ xtab, const int2* __restrict__ ytab,
+          int* __restrict__ work_counter, int* __restrict__ done)
+{
+    extern __shared__ __align__(128) uint8_t rs_sm[];       // two source tiles of buf_bytes each
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ int s_next[2];
+    __shared__ int s_org[2][6];                             // x0, y0, frame, source origin x / y, level of the item in each buffer
+    const int tid = threadIdx.x;
+    const int buf_bytes = P.buf_bytes;
+    // thread 0 only: which level / frame / tile an item is, where its source footprint starts
+    auto decode = [&](int item, int buf) {
+        int l = 1;
+        while (l + 1 < P.nlevels && item >= P.L[l + 1].item_base) l++;
+        const PyrLevel& Q = P.L[l];
+        const int idx = item - Q.item_base;
+        const int fr = idx / Q.ntiles, ti = idx - fr * Q.ntiles;
+        const int by = ti / Q.tiles_x, bx = ti - by * Q.tiles_x;
+        const int RT_H = (ORB_RESIZE_THREADS / (Q.tile_w >> 2)) * Q.rows;
+        const int x0 = bx * Q.tile_w, y0 = by * RT_H;
+        const LevelGeom& D = plan->L[l];
+        const int sxo = (__ldg(&xtab[D.xtab_off + x0]).x & 0xffff) & ~15;   // 16-byte aligned TMA origin (ROI starts at padded x = 16)
+        const int syo = __ldg(&ytab[D.ytab_off + y0]).x & 0xffff;
+        s_org[buf][0] = x0; s_org[buf][1] = y0; s_org[buf][2] = fr; s_org[buf][3] = sxo; s_org[buf][4] = syo; s_org[buf][5] = l;
+    };
+    auto dep_ready = [&](int buf) -> bool {
+        const int l = s_org[buf][5];
+#ifdef ORB_PYR_NOSYNC
+        return true;
+#endif
+        if (l < 2) return true;                             // level 1 reads level 0, written by the previous kernel
+        int v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(done + s_org[buf][2] * ORB_MAX_LEVELS + (l - 1)) : "memory");
+        return v >= P.L[l - 1].ntiles;
+    };
+    auto issue = [&](int buf) {
+        const int l = s_org[buf][5];
+        const PyrLevel& Q = P.L[l];
+#ifndef ORB_PYR_NOSYNC
+        if (l >= 2) asm volatile("fence.proxy.async.global;" ::: "memory");    // other CTAs' generic-proxy stores (acquired above) before this async-proxy read
+#endif
+        mbar_expect_tx(&bar[buf], (uint32_t)(Q.box_w * Q.box_h));
+        tma_load_3d(rs_sm + (size_t)buf * buf_bytes, &tm.m[l], s_org[buf][3] + ORB_EDGE, s_org[buf][4] + ORB_EDGE, s_org[buf][2], &bar[buf]);
+    };
+    if (tid == 0) {
+        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // the FIRST item is claimed from the queue as well (not blockIdx.x): item numbers then follow the order in which CTAs actually
+    // start, so every dependency belongs to a CTA that is already running — no assumption about dispatch order or residency
+    if (tid == 0) {
+        const int first = atomicAdd(work_counter, 1);
+        s_next[1] = first;
+        if (first < P.total) {
+            decode(first, 0);
+            while (!dep_ready(0)) __nanosleep(64);
+            issue(0);
+        }
+    }
+    __syncthreads();
+    int item = s_next[1];
+    for (int it = 0; item < P.total; it++) {
+        const int buf = it & 1;
+        const int x0 = s_org[buf][0], y0 = s_org[buf][1], f = s_org[buf][2], sxo = s_org[buf][3], syo = s_org[buf][4], lvl = s_org[buf][5];
+        bool pending = false;
+        int nxt = P.total;
+        if (tid == 0) {
+            nxt = atomicAdd(work_counter, 1);
+            s_next[buf] = nxt;
+            if (nxt < P.total) {
+                decode(nxt, buf ^ 1);
+                if (dep_ready(buf ^ 1)) issue(buf ^ 1); else pending = true;     // never block here: the dependency may be THIS item
+            }
+        }
+        const PyrLevel& Q = P.L[lvl];
+        const LevelGeom& D = plan->L[lvl];
+        const int RT_W = Q.tile_w, RS_ROWS = Q.rows, box_w = Q.box_w;
+        const int ncg = RT_W >> 2;                              // column groups (4 columns each) per tile
+        const int2* xt = xtab + D.xtab_off;
+        const int2* yt = ytab + D.ytab_off;
+        const int Dw = D.w, Dh = D.h, Dstride = D.stride;
+        const int rg = tid / ncg, cgx = (tid - rg * ncg) * 4;
+        const int gx = x0 + cgx, ys = y0 + rg * RS_ROWS;
+        const bool active = gx < Dw && ys < Dh && rg < ORB_RESIZE_THREADS / ncg;     // tile widths that do not divide 1024 leave a few threads over
+        // horizontal taps of the thread's four columns (see k_resize)
+        int c0[4], c1[4];
+        uint32_t aw[4], sel[4];
+        bool fastp = true;
+        int wofs = 0, sh = 0;
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int2 e = __ldg(&xt[min(gx + k, Dw - 1)]);
+                c0[k] = (e.x & 0xffff) - sxo; c1[k] = (e.x >> 16) - sxo;
+                aw[k] = (uint32_t)e.y;                                  // a0 | a1 << 16, both in [0, 2048]
+            }
+            const int cb = c0[0];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int d0 = c0[k] - cb, d1 = c1[k] - cb;
+                fastp = fastp && d0 >= 0 && d1 >= 0 && d0 <= 7 && d1 <= 7;
+                sel[k] = (uint32_t)(d0 & 7) | ((uint32_t)(d1 & 7) << 4);
+            }
+            wofs = cb & ~3; sh = (cb & 3) * 8;
+        }
+        mbar_wait(&bar[buf], (uint32_t)((it >> 1) & 1));
+        if (active) {
+            const uint8_t* src = rs_sm + (size_t)buf * buf_bytes;
+            int id0 = -1, id1 = -1, G0[4], G1[4];                       // G = horizontal sum >> 4 of source rows id0 / id1
+            auto hrow = [&](int srow, int (&G)[4]) {
+                const uint8_t* r = src + srow * box_w;
+                if (fastp) {
+                    const uint32_t* rw = reinterpret_cast<const uint32_t*>(r + wofs);
+                    const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
+                    const uint32_t W0 = __funnelshift_r(w0, w1, sh), W1 = __funnelshift_r(w1, w2, sh);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) G[k] = (int)(__dp2a_lo(aw[k], __byte_perm(W0, W1, sel[k]), 0u) >> 4);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) G[k] = (int)((r[c0[k]] * (aw[k] & 0xffffu) + r[c1[k]] * (aw[k] >> 16)) >> 4);
+                }
+            };
+            uint8_t* drow = planes + (size_t)f * fbytes + D.plane_off + (size_t)(ys + ORB_EDGE) * Dstride + ORB_EDGE + gx;
+            const int yend = min(ys + RS_ROWS, Dh);
+            for (int y = ys; y < yend; y++, drow += Dstride) {
+                const int2 e = __ldg(&yt[y]);
+                const int s0 = (e.x & 0xffff) - syo, s1 = (e.x >> 16) - syo;
+                const int b0 = e.y & 0xffff, b1 = (int)((uint32_t)e.y >> 16);
+                if (s0 != id0) {
+                    if (s0 == id1) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) G0[k] = G1[k];
+                    } else hrow(s0, G0);
+                    id0 = s0;
+                }
+                if (s1 != id1) {
+                    if (s1 == id0) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) G1[k] = G0[k];
+                    } else hrow(s1, G1);
+                    id1 = s1;
+                }
+                uint32_t o[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) o[k] = (uint32_t)((((b0 * G0[k]) >> 16) + ((b1 * G1[k]) >> 16) + 2) >> 2);
+                *reinterpret_cast<uint32_t*>(drow) = (o[0] | (o[1] << 8)) | ((o[2] << 16) | (o[3] << 24));
+            }
+        }
+        __syncthreads();          // every store of this item is issued; the other buffer may be refilled
+        if (tid == 0) {
+            // release at gpu scope, cumulative over the CTA's stores (ordered before it by the barrier); nobody reads the last level here
+#ifndef ORB_PYR_NOSYNC
+            if (lvl + 1 < P.nlevels)
+#else
+            if (false)
+#endif
+                asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(done + f * ORB_MAX_LEVELS + lvl) : "memory");
+            if (pending) {                                              // own item published: now it is safe to block on the next one's level
+                while (!dep_ready(buf ^ 1)) __nanosleep(64);
+                issue(buf ^ 1);
+            }
+        }
+        item = s_next[buf];
+    }
+}
+
 // copyMakeBorder(..., 16, BORDER_REFLECT_101) for every level of every frame in one launch
 // (reference src/ORBextractor.cc:806,814).  Only blur and the descriptor sampler read the frame;
 // resize, FAST and IC_Angle stay inside the ROI.  One thread per 32-bit word of the frame region
@@ -1382,7 +1564,8 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         cudaEventRecord(e, s);
         c->prof_events.push_back(e);
     };
-    ORB_CUDA(cudaMemsetAsync(W.d_counters, 0, 32 * sizeof(int), s));      // every tile queue of this pass (FAST 1, blur 2, resize 4+l) in one node
+    // every tile queue of this pass (FAST 1, blur 2, resize 4+l) and the per-(frame, level) completion counters of k_pyramid in one node
+    ORB_CUDA(cudaMemsetAsync(W.d_counters, 0, (32 + (size_t)nimg * ORB_MAX_LEVELS) * sizeof(int), s));
     mark();
     {
         const LevelGeom& L = P.L[0];
@@ -1397,6 +1580,27 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         launches++;
     }
     mark();
+    if (c->pyr_fused && P.nlevels > 1) {
+        PyrParams Q;
+        memset(&Q, 0, sizeof Q);
+        Q.nlevels = P.nlevels; Q.nimg = nimg;
+        int total = 0, bufb = 1024;
+        for (int l = 1; l < P.nlevels; l++) {
+            const LevelGeom& D = P.L[l];
+            const int tw = c->rs_tile_w[l], rr = c->rs_rows[l], th = (4 * ORB_RESIZE_THREADS / tw) * rr;
+            Q.L[l].tile_w = tw; Q.L[l].rows = rr; Q.L[l].box_w = c->rs_box_w[l]; Q.L[l].box_h = c->rs_box_h[l];
+            Q.L[l].tiles_x = (D.w + tw - 1) / tw;
+            Q.L[l].ntiles = Q.L[l].tiles_x * ((D.h + th - 1) / th);
+            Q.L[l].item_base = total;
+            total += Q.L[l].ntiles * nimg;
+            bufb = std::max(bufb, (c->rs_box_w[l] * c->rs_box_h[l] + 127) & ~127);
+        }
+        Q.total = total; Q.buf_bytes = bufb;
+        const int grid = std::min(total, c->num_sms * ORB_RESIZE_CTAS);
+        k_pyramid<<<grid, ORB_RESIZE_THREADS, 2 * bufb + 16, s>>>(W.tm_resize, W.d_planes, fb, c->d_plan, Q, c->d_xtab, c->d_ytab,
+                                                                  W.d_counters + 4, W.d_counters + 32);
+        launches++;
+    } else
     for (int l = 1; l < P.nlevels; l++) {
         const LevelGeom& D = P.L[l];
         const int tw = c->rs_tile_w[l], rr = c->rs_rows[l], th = (4 * ORB_RESIZE_THREADS / tw) * rr;
@@ -1483,7 +1687,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
 static int raise_dyn_smem(const void* fn, int slot, int bytes)
 {
     static std::mutex mu;
-    static int cur[5][64] = {};
+    static int cur[6][64] = {};
     int dev = 0;
     ORB_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(mu);
@@ -1493,7 +1697,12 @@ static int raise_dyn_smem(const void* fn, int slot, int bytes)
     return ORB_OK;
 }
 
-int orb_resize_smem_setup(int max_bytes) { return raise_dyn_smem((const void*)k_resize, 0, max_bytes); }
+int orb_resize_smem_setup(int max_bytes)
+{
+    static_assert(sizeof(PyrParams) <= 1024, "k_pyramid parameter block");
+    int rc = raise_dyn_smem((const void*)k_resize, 0, max_bytes);
+    return rc ? rc : raise_dyn_smem((const void*)k_pyramid, 5, max_bytes);
+}
 
 int orb_select_smem_setup(int list_cap)     // list_cap: the largest per-level keypoint list (u64 records) of the plan
 {
