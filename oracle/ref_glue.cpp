@@ -578,7 +578,6 @@ const char* ref_glue_flavour(void)
 #endif
 }
 
-#ifndef REF_GLUE_DROPIN      /* the four searches whose Sim3 / pose projection the drop-in header leaves to the caller (include/orb_b200_reftypes.h) */
 /* ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, th, ORBdist), :1622-1746.
  * already_found[i] != 0 puts the KeyFrame's point i into sAlreadyFound.  match_cur[i2] in: >= 0 -> the keypoint already carries some
  * other map point; out: KeyFrame feature index of the point assigned, the input value where it was occupied, else -1.
@@ -853,6 +852,5 @@ int ref_fuse_sim3(void* kf_, void* src_, const float* Scw16, float th, int32_t* 
     });
 }
 
-#endif /* REF_GLUE_DROPIN */
 } // extern "C"
 #endif /* REF_GLUE_EXTRACTOR_ONLY */

@@ -98,6 +98,16 @@ def test_search_for_triangulation(po, pkg):
     assert _run_all(T.test_search_for_triangulation, po=po, pkg=pkg) == 4
 
 
+def test_back_end_searches_with_host_preamble(po):
+    """the five methods whose pose / Sim3 projection is host arithmetic in the reference: restated with the same cv:: expressions in
+    include/orb_b200_reftypes.h, scoring on the GPU, graph bookkeeping (Replace / AddObservation) on the host in the reference's order"""
+    assert _run_all(T.test_search_by_projection_keyframe, po=po) == 3          # SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist)
+    assert _run_all(T.test_search_by_projection_sim3, po=po) == 3              # SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th)
+    assert _run_all(T.test_fuse, po=po) == 3                                   # Fuse(KeyFrame*, vpMapPoints, th)
+    assert _run_all(T.test_search_by_sim3, po=po) == 3                         # SearchBySim3
+    assert _run_all(T.test_fuse_sim3, po=po) == 2                              # Fuse(KeyFrame*, Scw, vpPoints, th)
+
+
 def test_track_with_motion_model_equals_reference(po):
     """src/Tracking.cc:594-606 on both libraries: the reference's ORBmatcher.cc and the drop-in, same frames, same velocity"""
     for shape, nf in (((240, 320), 500), ((480, 752), 1000), ((376, 1241), 2000)):
