@@ -416,9 +416,10 @@ k_border(uint8_t* __restrict__ planes, uint8_t* __restrict__ blurred, size_t fby
     if (first >= L.border_items) return;
     const int w = L.w, h = L.h;
     const int wpr = L.stride >> 2;                      // words per padded row
-    const int band = ORB_EDGE * wpr;                    // words in the top (or bottom) band
+    const int band = ORB_RING * wpr;                    // words in the top (or bottom) band: ORB_RING rows next to the ROI
     const int rw0 = (ORB_EDGE + w) >> 2;                // first word that contains right-frame pixels
-    const int side = 4 + (wpr - rw0);                   // frame words per middle row
+    constexpr int LW = ORB_RING / 4;                    // words of the left ring
+    constexpr int side = LW + 2;                        // ring words per middle row: left ring + the two words covering [w, w + ORB_RING)
     const size_t poff = (size_t)f * fbytes + L.plane_off;
     auto fetch = [&](int item, size_t& o) -> uint32_t {
     int py, wx;
@@ -427,13 +428,14 @@ k_border(uint8_t* __restrict__ planes, uint8_t* __restrict__ blurred, size_t fby
         if (bi) item -= band;
         py = __float2int_rz(__fdividef((float)item + 0.5f, (float)wpr));
         wx = item - py * wpr;
-        if (bi) py += ORB_EDGE + h;
+        py += bi ? ORB_EDGE + h : ORB_EDGE - ORB_RING;
     } else {
         item -= 2 * band;
-        py = __float2int_rz(__fdividef((float)item + 0.5f, (float)side));
+        py = item / side;
         wx = item - py * side;
         py += ORB_EDGE;
-        if (wx >= 4) wx = rw0 + (wx - 4);
+        wx = wx < LW ? (ORB_EDGE - ORB_RING) / 4 + wx : rw0 + (wx - LW);
+        if (wx >= wpr) wx = wpr - 1;                    // a ROI that ends on the last word of the pitch: rewrite that word
     }
     int sy = py - ORB_EDGE;
     if (sy < 0) sy = -sy; else if (sy >= h) sy = 2 * h - 2 - sy;

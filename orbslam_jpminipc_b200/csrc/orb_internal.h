@@ -13,6 +13,12 @@
 #define ORB_MAX_GRID 96            // max grid cols / rows per level
 #define ORB_MAX_CELLS_LEVEL 256    // one select-CTA thread per cell
 #define ORB_EDGE 16                // EDGE_THRESHOLD, reference src/ORBextractor.cc:77
+// Width of the reflect-101 ring k_border actually writes around every level ROI.  The reference materialises all 16 pixels
+// (copyMakeBorder, :806,:814) but nothing on the path reads further out than 3: FAST, IC_Angle and HarrisResponses stay inside the ROI
+// (keypoints lie >= 16 px from its edge), GaussianBlur 7x7 reaches 3 px, and the rotated BRIEF pattern reaches
+// ceil(sqrt(13^2 + 13^2)) = 19 px from a keypoint, i.e. at most 3 px past the edge.  The outer 12 px of the padded planes are
+// never written and never read (orb_debug_level_plane returns them as they are).
+#define ORB_RING 4
 #ifndef ORB_TILE_W
 #define ORB_TILE_W 64            // FAST tile width (multiple of 64); measured 64x32 1.38 ms, 64x64 1.28, 128x64 1.25, 64x128 1.24 per 256 frames
 #endif

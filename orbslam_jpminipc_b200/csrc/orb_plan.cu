@@ -138,7 +138,9 @@ int orb_build_plan(orb_ctx* c, int w, int h)
             if (!fits) return ORB_ERR_CAPACITY;      // scale factors above ~3.7
         }
         L.border_base = border;
-        L.border_items = 2 * ORB_EDGE * (L.stride / 4) + L.h * (4 + L.stride / 4 - (ORB_EDGE + L.w) / 4);
+        // k_border work items (32-bit words): ORB_RING full rows above and below the ROI, and per ROI row the word left of it plus
+        // the two words that cover [w, w + ORB_RING) on the right
+        L.border_items = 2 * ORB_RING * (L.stride / 4) + L.h * (ORB_RING / 4 + 2);
         border += L.border_items;
         // cell grid (:531-547)
         L.nDesired = c->mnFeaturesPerLevel[l];

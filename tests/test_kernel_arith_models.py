@@ -184,3 +184,22 @@ def test_knn2_carry_save_popcount_and_packed_key_model():
                 e2 = int(d[r])
         assert (m1 >> 22, m1 & (2**22 - 1)) == (e1, ei)
         assert (2**31 - 1 if m2 == 2**31 - 1 else m2 >> 22) == e2
+
+
+def test_border_ring_covers_everything_the_path_reads():
+    """csrc/orb_internal.h ORB_RING = 4: k_border writes only a 4 px reflect-101 ring instead of the reference's 16 px frame.  That is
+    enough iff nothing reads further than 3 px past the ROI: keypoints lie >= 16 px inside (EDGE_THRESHOLD), the rotated rBRIEF pattern
+    reaches at most ceil(max |p|) px from a keypoint, GaussianBlur 7x7 reaches 3 px from a ROI pixel."""
+    import math
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "orbslam_jpminipc_b200", "csrc", "orb_internal.h")).read()
+    ring = int(re.search(r"#define ORB_RING (\d+)", hdr).group(1))
+    edge = int(re.search(r"#define ORB_EDGE (\d+)", hdr).group(1))
+    lines = [l for l in open(os.path.join(root, "orbslam_jpminipc_b200", "csrc", "orb_pattern.inc")) if not l.strip().startswith("//")]
+    nums = [int(x) for x in re.findall(r"-?\d+", " ".join(lines))]
+    assert len(nums) == 1024
+    reach = max(math.hypot(nums[i], nums[i + 1]) for i in range(0, 1024, 2))
+    # cvRound(x*b + y*a) of a point at distance r from the keypoint is at most round(r) away on either axis
+    assert round(reach) - edge <= ring - 1 and 3 <= ring - 1 + 0 and ring % 4 == 0
