@@ -7,8 +7,8 @@
 // 128-query x 256-row block of dots per tile (8 instructions of K = 32), the accumulator lives in TMEM, and the CUDA cores only
 //   (1) expand the packed bits of the database tile into the canonical K-major shared-memory operand layout (one 2 KB lookup table:
 //       byte -> eight +-1 bytes), and
-//   (2) run the best / second-best scan on the accumulator read back with tcgen05.ld: per pair one IMAD (key = dot*256 + 255-col)
-//       and three integer min/max — against 5 POPC + 14 LOP3 + ... in k_knn2.
+//   (2) run the best / second-best scan on the accumulator read back with tcgen05.ld: per pair one IMAD (key = (dot+256)*300 + 255-col,
+//       FMA pipe) and 2.5 integer min/max (ALU pipe) — against 5 POPC + 14 LOP3 + ... in k_knn2.
 // The MMA of tile t runs asynchronously (tcgen05.commit -> mbarrier) while the CUDA cores scan tile t-1 out of the other TMEM stage.
 // Results are bit-identical to k_knn2 (same scan semantics: lowest index wins, d2 = second order statistic); selected with
 // orb_set_knn_engine(ctx, ORB_KNN_TENSOR) or ORB_KNN_ENGINE=tensor, never by default (north_star pins the POPC path).
@@ -21,16 +21,18 @@ namespace {
 constexpr int TC_SCAN_WARPS = 8;      // warps 0..7: best / second-best scan of the accumulator (TMEM lane quarter = warp & 3, column half = warp >> 2)
 constexpr int TC_PROD_WARPS = 4;      // warps 8..11: expand database bits into the int8 operand tile
 constexpr int TC_THREADS = (TC_SCAN_WARPS + TC_PROD_WARPS + 1) * 32;      // + warp 12: TMEM allocation and the MMA issuer
-constexpr int TC_M = 128;             // queries per CTA = TMEM lanes
-constexpr int TC_N = 256;             // database rows per tile = accumulator columns of one TMEM stage
+constexpr int TC_M = 128;             // queries per M-tile = TMEM lanes
+constexpr int TC_MT = 2;              // M-tiles per CTA: one expanded database tile feeds two accumulators (256 queries)
+constexpr int TC_N = 128;             // database rows per tile = accumulator columns per (stage, M-tile): 2 stages x 2 M-tiles x 128 = all 512 TMEM columns
 constexpr int TC_KBYTES = 256;        // one int8 per descriptor bit
+constexpr int TC_KEYMUL = 300;        // scan key = (dot + 256) * 300 + (255 - column); see the scanner
 constexpr int TC_LBO = 128;           // bytes between the two 16-byte K chunks of one core-matrix pair (K-major, no swizzle)
 constexpr int TC_SBO = 16 * 128;      // bytes between 8-row groups: 16 K-chunks of 128 bytes each
-constexpr int TC_A_BYTES = TC_M * TC_KBYTES;          // 32 KB
-constexpr int TC_B_BYTES = TC_N * TC_KBYTES;          // 64 KB per stage
+constexpr int TC_A_BYTES = TC_M * TC_KBYTES;          // 32 KB per M-tile
+constexpr int TC_B_BYTES = TC_N * TC_KBYTES;          // 32 KB per stage
 constexpr int TC_LUT_COPIES = 16;                     // lane pair j reads copy j: at most 2-way bank conflicts on the table
 constexpr int TC_LUT_BYTES = 256 * TC_LUT_COPIES * 8; // 32 KB
-constexpr int TC_SMEM = TC_A_BYTES + 2 * TC_B_BYTES + TC_LUT_BYTES + 2048 /* merge area + barriers */ + 1024 /* alignment slack */;
+constexpr int TC_SMEM = TC_MT * TC_A_BYTES + 2 * TC_B_BYTES + TC_LUT_BYTES + 1024 /* barriers */ + 1024 /* alignment slack */;
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -63,6 +65,15 @@ __device__ __forceinline__ void tc_mbar_init(uint64_t* bar, int count)
 __device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool tc_mbar_test(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(s_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity)
 {
@@ -135,23 +146,22 @@ k_knn2_tc(Knn2TcArgs A)
 {
     extern __shared__ uint8_t tc_raw[];
     uint8_t* sm = reinterpret_cast<uint8_t*>(((uintptr_t)tc_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = sm;
-    uint8_t* sB = sm + TC_A_BYTES;
-    uint8_t* lut = sm + TC_A_BYTES + 2 * TC_B_BYTES;
-    int* s_merge = reinterpret_cast<int*>(lut + TC_LUT_BYTES);                           // [128][3]: result of the upper column half
-    uint64_t* bars = reinterpret_cast<uint64_t*>(lut + TC_LUT_BYTES + 128 * 3 * 4);
+    uint8_t* sA = sm;                                                                   // [TC_MT][32 KB]
+    uint8_t* sB = sm + TC_MT * TC_A_BYTES;                                              // [2 stages][32 KB]
+    uint8_t* lut = sB + 2 * TC_B_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lut + TC_LUT_BYTES);
     uint64_t *bar_ready = bars, *bar_full = bars + 2, *bar_tfree = bars + 4;
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 6);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int chunk = blockIdx.x, mt = blockIdx.y, pair = blockIdx.z;
+    const int chunk = blockIdx.x, mtp = blockIdx.y, pair = blockIdx.z;
     const long long row0 = (long long)chunk * A.rows_per_chunk;
     const int nrows = (int)min((long long)A.rows_per_chunk, A.ndb - row0);
     const uint8_t* db = A.db + ((size_t)pair * A.ndb + row0) * 32;
     const int ntiles = (nrows + TC_N - 1) / TC_N;
     const bool scanner = warp < TC_SCAN_WARPS, producer = warp >= TC_SCAN_WARPS && warp < TC_SCAN_WARPS + TC_PROD_WARPS;
 
-    // ---- one-time setup: TMEM (all 512 columns = two 256-column accumulator stages), barriers, lookup table, query operand ----
+    // ---- one-time setup: TMEM (all 512 columns), barriers, lookup table, the two query operand tiles ----
     if (warp == TC_SCAN_WARPS + TC_PROD_WARPS) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s_u32(s_tmem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -175,33 +185,28 @@ k_knn2_tc(Knn2TcArgs A)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *s_tmem;
     const uint8_t* lutc = lut + (lane >> 1) * 8;
-    if (producer) {
-        const int r = tid - TC_SCAN_WARPS * 32;                     // 0..127: one query row per producer thread
-        const int qi = min(mt * TC_M + r, A.nq - 1);                // rows past nq repeat the last query (never written back)
+    if (scanner) {                                                  // 256 threads = 256 query rows (rows past nq repeat the last query, never written back)
+        const int m = tid >> 7, r = tid & 127;
+        const int qi = min((mtp * TC_MT + m) * TC_M + r, A.nq - 1);
         const uint4* qp = reinterpret_cast<const uint4*>(A.q + ((size_t)pair * A.nq + qi) * 32);
-        expand_row(sA, r, __ldg(qp), __ldg(qp + 1), lutc);
+        expand_row(sA + m * TC_A_BYTES, r, __ldg(qp), __ldg(qp + 1), lutc);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
 
-    int R1 = INT_MIN, R2 = INT_MIN, RI = -1;                        // scanners: running best dot, second-best dot, best row (chunk-relative)
-    const int q4 = warp & 3, half = (warp >> 2) & 1;
-
     if (producer) {
-        const int p = tid - TC_SCAN_WARPS * 32;                     // rows p and p + 128 of every tile
-        uint4 r0lo = make_uint4(0, 0, 0, 0), r0hi = r0lo, r1lo = r0lo, r1hi = r0lo;
+        const int p = tid - TC_SCAN_WARPS * 32;                     // row p of every tile
+        uint4 rlo = make_uint4(0, 0, 0, 0), rhi = rlo;
         auto fetch = [&](int t) {
-            const long long a = (long long)t * TC_N + p, b = a + 128;
-            if (a < nrows) { const uint4* g = reinterpret_cast<const uint4*>(db + (size_t)a * 32); r0lo = __ldg(g); r0hi = __ldg(g + 1); }
-            if (b < nrows) { const uint4* g = reinterpret_cast<const uint4*>(db + (size_t)b * 32); r1lo = __ldg(g); r1hi = __ldg(g + 1); }
+            const long long a = (long long)t * TC_N + p;
+            if (a < nrows) { const uint4* g = reinterpret_cast<const uint4*>(db + (size_t)a * 32); rlo = __ldg(g); rhi = __ldg(g + 1); }
         };
         fetch(0);
         for (int t = 0; t < ntiles; t++) {
             const int s = t & 1;
             uint8_t* Bs = sB + s * TC_B_BYTES;
             if (t >= 2) tc_mbar_wait(&bar_full[s], (uint32_t)(((t - 2) >> 1) & 1));     // the MMAs of tile t-2 have consumed this stage
-            if ((long long)t * TC_N + p < nrows) expand_row(Bs, p, r0lo, r0hi, lutc);
-            if ((long long)t * TC_N + p + 128 < nrows) expand_row(Bs, p + 128, r1lo, r1hi, lutc);
+            if ((long long)t * TC_N + p < nrows) expand_row(Bs, p, rlo, rhi, lutc);
             if (t + 1 < ntiles) fetch(t + 1);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                // generic-proxy stores -> visible to the tensor core's async proxy
             __syncwarp();
@@ -209,7 +214,7 @@ k_knn2_tc(Knn2TcArgs A)
         }
     } else if (warp == TC_SCAN_WARPS + TC_PROD_WARPS) {
         if (lane == 0) {
-            const uint64_t a_desc = smem_desc(s_u32(sA));
+            const uint64_t a_desc0 = smem_desc(s_u32(sA)), a_desc1 = smem_desc(s_u32(sA + TC_A_BYTES));
             for (int t = 0; t < ntiles; t++) {
                 const int s = t & 1;
                 tc_mbar_wait(&bar_ready[s], (uint32_t)((t >> 1) & 1));
@@ -217,77 +222,89 @@ k_knn2_tc(Knn2TcArgs A)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint64_t b_desc = smem_desc(s_u32(sB + s * TC_B_BYTES));
 #pragma unroll
-                for (int k = 0; k < TC_KBYTES / 32; k++)                // K = 32 int8 per instruction = two 16-byte chunks = 2 * LBO bytes
-                    mma_i8(tmem + (uint32_t)(s * TC_N), a_desc + (uint64_t)((k * 2 * TC_LBO) >> 4), b_desc + (uint64_t)((k * 2 * TC_LBO) >> 4), k > 0);
+                for (int m = 0; m < TC_MT; m++)
+#pragma unroll
+                    for (int k = 0; k < TC_KBYTES / 32; k++)            // K = 32 int8 per instruction = two 16-byte chunks = 2 * LBO bytes
+                        mma_i8(tmem + (uint32_t)((s * TC_MT + m) * TC_N), (m ? a_desc1 : a_desc0) + (uint64_t)((k * 2 * TC_LBO) >> 4),
+                               b_desc + (uint64_t)((k * 2 * TC_LBO) >> 4), k > 0);
                 mma_commit(&bar_full[s]);
             }
         }
     } else {
+        // scanner warp w: M-tile w >> 2, TMEM lane quarter w & 3; one query row per thread, all 128 columns of its accumulator
+        const int m = warp >> 2, q4 = warp & 3;
         const uint32_t t_lane = tmem + ((uint32_t)(q4 * 32) << 16);
+        int R1 = INT_MIN, R2 = INT_MIN, RI = -1;                    // running best dot, second-best dot, best row (chunk-relative)
+        int va[32], vb[32];                                          // two register buffers: a load is in flight while the other buffer is scanned
+        bool early = false;                                         // the first load of this tile was already issued at the end of the previous one
         for (int t = 0; t < ntiles; t++) {
             const int s = t & 1;
-            tc_mbar_wait(&bar_full[s], (uint32_t)((t >> 1) & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int valid = min(TC_N, nrows - t * TC_N);              // columns >= valid belong to rows past the chunk
-            const int cb0 = half * (TC_N / 2);
-            const uint32_t tcol = t_lane + (uint32_t)(s * TC_N + cb0);
-            int m1 = INT_MIN, m2 = INT_MIN;
+            const uint32_t tcol = t_lane + (uint32_t)((s * TC_MT + m) * TC_N);
+            if (!early) {
+                tc_mbar_wait(&bar_full[s], (uint32_t)((t >> 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                tmem_ld32(tcol, va);
+            }
+            // key = (dot + 256) * TC_KEYMUL + (255 - col) >= 0: larger dot first, then lower column.  The multiplier is deliberately
+            // NOT a power of two: dot * 300 + constant is one IMAD on the (otherwise idle) FMA pipe, where dot * 256 + constant
+            // becomes a shift-add on the ALU pipe, which the scan saturates (ncu: ALU 84 %, FMA 3 %).  Two keys per step:
+            //   hi = max(a, b), lo = min(a, b);  m2 = max3(min(m1, hi), m2, lo);  m1 = max(m1, hi)      (5 ALU operations per 2 pairs)
+            // second largest of {m1 >= m2, hi >= lo}: hi <= m1 -> max(hi, m2) (lo <= hi adds nothing); hi > m1 -> max(m1, lo) (m2 <= m1).
+            int m1 = -1, m2 = -1;
             auto scan32 = [&](const int (&v)[32], int cbase) {
                 if (cbase + 32 <= valid) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const int key = v[j] * 256 + (255 - (cbase + j));
-                        m2 = max(m2, min(m1, key));
-                        m1 = max(m1, key);
+                    for (int j = 0; j < 32; j += 2) {
+                        const int a = v[j] * TC_KEYMUL + (256 * TC_KEYMUL + 255 - (cbase + j));
+                        const int b = v[j + 1] * TC_KEYMUL + (256 * TC_KEYMUL + 255 - (cbase + j + 1));
+                        const int hi = max(a, b), lo = min(a, b);
+                        m2 = __vimax3_s32(min(m1, hi), m2, lo);
+                        m1 = max(m1, hi);
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
-                        const int key = (cbase + j < valid) ? v[j] * 256 + (255 - (cbase + j)) : INT_MIN;
+                        const int key = (cbase + j < valid) ? v[j] * TC_KEYMUL + (256 * TC_KEYMUL + 255 - (cbase + j)) : -1;
                         m2 = max(m2, min(m1, key));
                         m1 = max(m1, key);
                     }
                 }
             };
-            // two register buffers: the load of the next 32 columns is in flight while the current 32 are scanned
-            int va[32], vb[32];
-            tmem_ld32(tcol, va);
             tmem_ld_wait(va);
             tmem_ld32(tcol + 32, vb);
-            scan32(va, cb0);
+            scan32(va, 0);
             tmem_ld_wait(vb);
             tmem_ld32(tcol + 64, va);
-            scan32(vb, cb0 + 32);
+            scan32(vb, 32);
             tmem_ld_wait(va);
             tmem_ld32(tcol + 96, vb);
-            scan32(va, cb0 + 64);
+            scan32(va, 64);
             tmem_ld_wait(vb);
-            scan32(vb, cb0 + 96);
+            // va is free: if the NEXT tile's accumulator is already complete (its MMAs do not depend on this scan), start its first load
+            // now so that its latency hides behind the last 32 columns of this tile.  The test must be warp-uniform: tcgen05.ld is .aligned.
+            early = false;
+            if (t + 1 < ntiles) {
+                const bool ready = tc_mbar_test(&bar_full[s ^ 1], (uint32_t)(((t + 1) >> 1) & 1));
+                if (__all_sync(0xffffffffu, ready)) {
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    tmem_ld32(t_lane + (uint32_t)(((s ^ 1) * TC_MT + m) * TC_N), va);
+                    early = true;
+                }
+            }
+            scan32(vb, 96);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) tc_mbar_arrive(&bar_tfree[s]);
-            if (m1 != INT_MIN) {                                        // fold the tile into the running result: earlier tiles hold lower rows
-                const int t1 = m1 >> 8, ti = t * TC_N + (255 - (m1 & 255));
-                const int t2 = m2 == INT_MIN ? INT_MIN : (m2 >> 8);
+            if (m1 >= 0) {                                              // fold the tile into the running result: earlier tiles hold lower rows
+                const int q1 = m1 / TC_KEYMUL, t1 = q1 - 256, ti = t * TC_N + (255 - (m1 - q1 * TC_KEYMUL));
+                const int t2 = m2 < 0 ? INT_MIN : m2 / TC_KEYMUL - 256;
                 if (t1 > R1) { R2 = max(R1, t2); R1 = t1; RI = ti; }
                 else R2 = max(R2, t1);
             }
         }
-    }
-
-    // ---- merge the two column halves of every query, convert dots to distances, write ----
-    __syncthreads();
-    const int row = q4 * 32 + lane;
-    if (scanner && half == 1) { s_merge[row * 3] = R1; s_merge[row * 3 + 1] = R2; s_merge[row * 3 + 2] = RI; }
-    __syncthreads();
-    if (scanner && half == 0) {
-        const int o1 = s_merge[row * 3], o2 = s_merge[row * 3 + 1], oi = s_merge[row * 3 + 2];
-        if (oi >= 0) {
-            if (RI < 0) { R1 = o1; R2 = o2; RI = oi; }
-            else if (o1 > R1 || (o1 == R1 && oi < RI)) { R2 = max(R1, o2); R1 = o1; RI = oi; }
-            else R2 = max(R2, o1);
-        }
-        const int qi = mt * TC_M + row;
+        // ---- dots -> distances, write ----
+        const int qi = (mtp * TC_MT + m) * TC_M + q4 * 32 + lane;
         if (qi < A.nq) {
             const int d1 = RI < 0 ? INT_MAX : (256 - R1) >> 1, d2 = R2 == INT_MIN ? INT_MAX : (256 - R2) >> 1;
             const int gi = RI < 0 ? -1 : (int)(row0 + RI) + A.idx_base;
@@ -318,7 +335,7 @@ int orb_launch_knn2_tc(orb_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_
         ORB_CUDA(cudaFuncSetAttribute(k_knn2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
         smem_set[dev] = 1;
     }
-    const int mtiles = (nq + TC_M - 1) / TC_M;
+    const int mtiles = (nq + TC_MT * TC_M - 1) / (TC_MT * TC_M);         // CTAs along the queries: 256 queries each
     // one CTA per SM (shared memory + all of TMEM): as many chunks as fill one wave of SMs, chunks a multiple of the tile
     long long want_chunks = std::max<long long>(1, (long long)c->num_sms / ((long long)mtiles * npairs));
     long long rows = (ndb + want_chunks - 1) / want_chunks;
