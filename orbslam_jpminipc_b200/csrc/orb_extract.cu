@@ -219,6 +219,122 @@ k_resize(const __grid_constant__ CUtensorMap tm, uint8_t* __restrict__ planes, s
     }
 }
 
+// ------------------------------------------------------------------ K1, unrolled form (round 2)
+// Same tiles, same TMA staging and the same arithmetic as k_resize, with the per-row overhead of that kernel removed: by its SASS
+// k_resize spends ~95 instructions per output row of 4 pixels against ~45 of arithmetic — a dependent global load of the row's table
+// entry, its decoding, 64-bit pointer stepping, four register moves whenever source row s1 becomes s0 (4 rows in 5 at 1.2), both
+// forms of the horizontal pass — and ~150 per item on decoding the column taps.  Here
+//   * ROWS is a compile-time constant and the row loop is fully unrolled: the ROWS table entries are fetched up front (independent
+//     loads), the row offsets are immediates;
+//   * the two horizontal-pass register sets swap roles every row (set B of row r is set A of row r + 1 when s0' == s1), so nothing
+//     is moved; a set is recomputed only when it does not already hold the source row it should (warp-uniform tests);
+//   * the column taps of a 4-column group come ready-made from a per-level table built with the plan (first source byte, the four
+//     PRMT selectors, the four weight pairs: two 128-bit loads);
+//   * only the packed horizontal pass exists (plan: every group's taps lie within 8 bytes, true for every scale factor <= 2);
+//     other levels keep k_resize.
+template <int ROWS>
+__global__ void __launch_bounds__(ORB_RESIZE_THREADS)
+k_resize_u(const __grid_constant__ CUtensorMap tm, uint8_t* __restrict__ planes, size_t fbytes, LevelGeom D,
+           const uint4* __restrict__ xgrp, const int2* __restrict__ ytab, int box_w, int box_h, int buf_bytes,
+           int nimg, int* __restrict__ work_counter, int RT_W)
+{
+    extern __shared__ __align__(128) uint8_t rs_sm[];       // two source tiles of buf_bytes each
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ int s_next[2];
+    __shared__ int s_org[2][5];                             // x0, y0, frame, source origin x / y of the item in each buffer
+    const int tid = threadIdx.x;
+    const int ncg = RT_W >> 2;
+    const int RT_H = (ORB_RESIZE_THREADS / ncg) * ROWS;
+    const int tiles_x = (D.w + RT_W - 1) / RT_W, tiles_y = (D.h + RT_H - 1) / RT_H;
+    const int ntiles = tiles_x * tiles_y, total = ntiles * nimg;
+    const int2* yt = ytab + D.ytab_off;
+    auto issue = [&](int item, int buf) {
+        const int ti = item % ntiles, fr = item / ntiles;
+        const int by = ti / tiles_x, bx = ti - by * tiles_x;
+        const int x0 = bx * RT_W, y0 = by * RT_H;
+        const int sxo = (int)__ldg(&xgrp[(x0 >> 2) * 2]).x & ~15;      // 16-byte aligned TMA origin (ROI starts at padded x = 16)
+        const int syo = __ldg(&yt[y0]).x & 0xffff;
+        s_org[buf][0] = x0; s_org[buf][1] = y0; s_org[buf][2] = fr; s_org[buf][3] = sxo; s_org[buf][4] = syo;
+        mbar_expect_tx(&bar[buf], (uint32_t)(box_w * box_h));
+        tma_load_3d(rs_sm + (size_t)buf * buf_bytes, &tm, sxo + ORB_EDGE, syo + ORB_EDGE, fr, &bar[buf]);
+    };
+    if (tid == 0) {
+        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int item = blockIdx.x;
+    if (tid == 0 && item < total) issue(item, 0);
+    __syncthreads();
+    const int rg = tid / ncg, cgx = (tid - rg * ncg) * 4;
+    const uint32_t sm_base = (uint32_t)__cvta_generic_to_shared(rs_sm);
+    for (int it = 0; item < total; it++) {
+        const int buf = it & 1;
+        const int x0 = s_org[buf][0], y0 = s_org[buf][1], f = s_org[buf][2], sxo = s_org[buf][3], syo = s_org[buf][4];
+        if (tid == 0) {
+            const int nxt = atomicAdd(work_counter, 1) + (int)gridDim.x;
+            s_next[buf] = nxt;
+            if (nxt < total) issue(nxt, buf ^ 1);
+        }
+        const int gx = x0 + cgx, ys = y0 + rg * ROWS;
+        const bool active = gx < D.w && ys < D.h && rg < ORB_RESIZE_THREADS / ncg;
+        uint4 ga = make_uint4(0, 0, 0, 0), gb = ga;
+        int2 ye[ROWS];
+        if (active) {
+            ga = __ldg(&xgrp[(gx >> 2) * 2]); gb = __ldg(&xgrp[(gx >> 2) * 2 + 1]);
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) ye[r] = __ldg(&yt[min(ys + r, D.h - 1)]);
+        }
+        mbar_wait(&bar[buf], (uint32_t)((it >> 1) & 1));
+        if (active) {
+            const int cb = (int)ga.x - sxo;
+            const uint32_t sh = (uint32_t)(cb & 3) * 8u;
+            const uint32_t row0 = sm_base + (uint32_t)(buf * buf_bytes + (cb & ~3) - syo * box_w);   // + srow_abs * box_w
+            const uint32_t sel0 = ga.y, sel1 = ga.y >> 16, sel2 = ga.z, sel3 = ga.z >> 16;
+            uint32_t GA[4], GB[4];
+            int idA = -1, idB = -1;
+            auto hrow = [&](int srow, uint32_t (&G)[4]) {
+                const uint32_t a = row0 + (uint32_t)(srow * box_w);
+                uint32_t w0, w1, w2;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(a));
+                asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(a));
+                asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(a));
+                const uint32_t W0 = __funnelshift_r(w0, w1, sh), W1 = __funnelshift_r(w1, w2, sh);
+                G[0] = __dp2a_lo(gb.x, __byte_perm(W0, W1, sel0), 0u) >> 4;
+                G[1] = __dp2a_lo(gb.y, __byte_perm(W0, W1, sel1), 0u) >> 4;
+                G[2] = __dp2a_lo(gb.z, __byte_perm(W0, W1, sel2), 0u) >> 4;
+                G[3] = __dp2a_lo(gb.w, __byte_perm(W0, W1, sel3), 0u) >> 4;
+            };
+            uint8_t* drow = planes + (size_t)f * fbytes + D.plane_off + (size_t)(ys + ORB_EDGE) * D.stride + ORB_EDGE + gx;
+            const int nrow = min(ROWS, D.h - ys);
+            auto out_row = [&](int r, const uint32_t (&G0)[4], const uint32_t (&G1)[4]) {
+                const uint32_t b0 = (uint32_t)ye[r].y & 0xffffu, b1 = (uint32_t)ye[r].y >> 16;
+                // (((b0*G0)>>16) + ((b1*G1)>>16) + 2) >> 2, the + 2 riding on the second product; weights sum to <= 2048: 0..255
+                uint32_t o[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) o[k] = (((b0 * G0[k]) >> 16) + ((b1 * G1[k] + 0x20000u) >> 16)) >> 2;
+                if (r < nrow)          // bytes past the right ROI edge fall into the border and are rewritten by k_border
+                    *reinterpret_cast<uint32_t*>(drow + (size_t)r * D.stride) = (o[0] | (o[1] << 8)) | ((o[2] << 16) | (o[3] << 24));
+            };
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+                const int s0 = ye[r].x & 0xffff, s1 = (int)((uint32_t)ye[r].x >> 16);
+                if ((r & 1) == 0) {            // even rows: A = s0, B = s1
+                    if (idA != s0) { hrow(s0, GA); idA = s0; }
+                    if (idB != s1) { hrow(s1, GB); idB = s1; }
+                    out_row(r, GA, GB);
+                } else {                       // odd rows: B = s0 (the previous row's s1 when the source advanced by one), A = s1
+                    if (idB != s0) { hrow(s0, GB); idB = s0; }
+                    if (idA != s1) { hrow(s1, GA); idA = s1; }
+                    out_row(r, GB, GA);
+                }
+            }
+        }
+        __syncthreads();          // the other buffer is refilled by the next iteration's prefetch
+        item = s_next[buf];
+    }
+}
+
 // ------------------------------------------------------------------ K1, fused
 // The whole resize cascade (levels 1 .. nlevels-1 of every frame) in ONE persistent launch instead of one launch per level: seven
 // serial launches cost seven ramp-ups and seven tails (levels 4..7 are only a few hundred tiles per 64 frames).  Work items are
@@ -558,6 +674,63 @@ __device__ __forceinline__ uint32_t excess2(uint32_t Mn, uint32_t Mx, uint32_t n
     return __viaddmax_s16x2_relu(~Mx, vm1, qb);
 }
 
+// ---- round 2: part of the arc network on the FMA pipe ----
+// ncu puts k_fast_nms at 87 % of the ALU pipe with the FMA pipe idle (4.6 %).  Both pipes issue a warp instruction every second
+// cycle per scheduler, so a 2-input min/max that leaves the ALU pipe frees it for two cycles even if it costs two FMA-pipe
+// instructions.  With a lane = 0x6400 | pixel (the fp16 number 1024 + pixel; positive halves order like their bit patterns, so
+// VIMNMX3.U16x2 keeps working on the same registers) and d = relu(a - b) = fma.rn.relu.f16x2(b, -1, a):
+//     max(a, b) = b + d        min(a, b) = a - d          (all values are integers below 2048: exact in fp16)
+// and the min tree and the max tree want max / min of the SAME pairs (r[k], r[k+9]) and (r[k+2], r[k+11]), so those share d:
+// 3 FMA-pipe instructions replace 2 ALU-pipe ones.  Per call 26 of the 68 operations move (ORB_FAST_HALF_LEVEL: 1 = the shared
+// pairs only, 2 = also max(eA, eB) / min(eA, eB) and the final combine).
+#ifndef ORB_FAST_HALF_LEVEL
+#define ORB_FAST_HALF_LEVEL 2
+#endif
+__device__ __forceinline__ uint32_t h2_relu_sub(uint32_t a, uint32_t b)       // relu(a - b) per fp16 lane
+{
+    uint32_t d;
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(b), "r"(0xBC00BC00u), "r"(a));
+    return d;
+}
+#ifdef ORB_FAST_HALF_FMAONLY
+__device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) { uint32_t r; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(0x3C003C00u), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t h2_sub(uint32_t a, uint32_t b) { uint32_t r; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(0xBC00BC00u), "r"(a)); return r; }
+#else
+__device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) { uint32_t r; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t h2_sub(uint32_t a, uint32_t b) { uint32_t r; asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+#endif
+__device__ __forceinline__ uint32_t h2_max(uint32_t a, uint32_t b) { return h2_add(b, h2_relu_sub(a, b)); }
+__device__ __forceinline__ uint32_t h2_min(uint32_t a, uint32_t b) { return h2_sub(a, h2_relu_sub(a, b)); }
+
+__device__ __forceinline__ void arc_minmax_h(const uint32_t (&r)[16], uint32_t& Mn, uint32_t& Mx)
+{
+    uint32_t g[4], h[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int k = 4 * q;
+#define R_(i) r[(k + (i)) & 15]
+        const uint32_t d09 = h2_relu_sub(R_(0), R_(9)), d211 = h2_relu_sub(R_(2), R_(11));
+        const uint32_t mx09 = h2_add(R_(9), d09), mn09 = h2_sub(R_(0), d09);
+        const uint32_t mx211 = h2_add(R_(11), d211), mn211 = h2_sub(R_(2), d211);
+        {
+            const uint32_t eA = __vimin3_u16x2(R_(1), R_(2), mx09);
+            const uint32_t eB = __vimin3_u16x2(R_(9), R_(10), mx211);
+            const uint32_t c1 = __vimin3_u16x2(R_(3), R_(4), R_(5)), c2 = __vimin3_u16x2(R_(6), R_(7), R_(8));
+            g[q] = __vimin3_u16x2(c1, c2, ORB_FAST_HALF_LEVEL >= 2 ? h2_max(eA, eB) : __vmaxu2(eA, eB));
+        }
+        {
+            const uint32_t eA = __vimax3_u16x2(R_(1), R_(2), mn09);
+            const uint32_t eB = __vimax3_u16x2(R_(9), R_(10), mn211);
+            const uint32_t c1 = __vimax3_u16x2(R_(3), R_(4), R_(5)), c2 = __vimax3_u16x2(R_(6), R_(7), R_(8));
+            h[q] = __vimax3_u16x2(c1, c2, ORB_FAST_HALF_LEVEL >= 2 ? h2_min(eA, eB) : __vminu2(eA, eB));
+        }
+#undef R_
+    }
+    const uint32_t a = __vimax3_u16x2(g[0], g[1], g[2]), b = __vimin3_u16x2(h[0], h[1], h[2]);
+    Mn = ORB_FAST_HALF_LEVEL >= 2 ? h2_max(a, g[3]) : __vmaxu2(a, g[3]);
+    Mx = ORB_FAST_HALF_LEVEL >= 2 ? h2_min(b, h[3]) : __vminu2(b, h[3]);
+}
+
 // Persistent kernel: each CTA walks (tile, frame) work items; the image tile of item i+1 is fetched by
 // TMA into the other shared-memory buffer while item i is being scored.
 __global__ void __launch_bounds__(FAST_THREADS, FAST_CTAS)
@@ -565,7 +738,7 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
            const Plan* __restrict__ plan, const Tile* __restrict__ tiles, int ntiles, int total, int* __restrict__ work_counter,
            const uint8_t* __restrict__ coltab, const int16_t* __restrict__ rowtab)
 {
-    __shared__ __align__(128) uint32_t img2[2][FI_H * FIW];
+    __shared__ __align__(128) uint32_t img2[2][(FI_H * FIW + 31) & ~31];      // each buffer 128-byte aligned (TMA destination) for any tile height
     __shared__ int s_next[2], s_ti[2], s_fr[2];             // next work item; tile index and frame of the item in each buffer
     __shared__ __align__(16) uint32_t sc[FS_H * FSW];
     __shared__ short rowcell[FS_H];
@@ -579,6 +752,8 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
     // like a non-corner, so the kernel may treat it as one
     const int th = max(plan->th_lo, 1);
     const uint32_t c1 = (uint32_t)((1 - th) & 0xffff) * 0x00010001u;       // (1 - th) in both lanes
+    // half lanes carry 0x6400 + value: the epilogue's lane constants absorb it (all sums stay inside a signed 16-bit lane)
+    const uint32_t c1n = (uint32_t)((1 - th - 0x6400) & 0xffff) * 0x00010001u, c1p = (uint32_t)((1 - th + 0x6400) & 0xffff) * 0x00010001u;
     const uint32_t th_m1 = (uint32_t)(th - 1);
     constexpr uint32_t TILE_BYTES = FI_H * FIW * 4;
 
@@ -652,8 +827,18 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
                 for (int q = 0; q < 7; q++) { w0[q] = ip[q * FIW]; w1[q] = ip[q * FIW + 1]; w2[q] = ip[q * FIW + 2]; }
                 // Ring sample k for pixels (x, x+1) resp. (x+2, x+3), packed as two u16 lanes holding value*257
                 // (byte duplicated): one PRMT straight from the two source words, order preserving.
+#ifdef ORB_FAST_INTLANES
 #define RPAIR(A, B, o, hi) __byte_perm(A, B, (hi) ? ((((o) + 3) << 12) | (((o) + 3) << 8) | (((o) + 2) << 4) | ((o) + 2)) \
                                                    : ((((o) + 1) << 12) | (((o) + 1) << 8) | ((o) << 4) | (o)))
+#else
+                // half lanes: 0x64 above the pixel byte.  Both bytes in one source word: one PRMT against the constant word;
+                // the pair (byte 3 of A, byte 0 of B) needs both words as PRMT sources and gets its 0x64 from a LOP3.
+                constexpr uint32_t K64 = 0x64646464u;
+#define RP_(i0) ((i0) + 1 <= 3 ? __byte_perm(A_, K64, 0x4040 | (((i0) + 1) << 8) | (i0))                               \
+                 : (i0) >= 4   ? __byte_perm(B_, K64, 0x4040 | (((i0) - 3) << 8) | ((i0) - 4))                         \
+                               : ((__byte_perm(A_, B_, 0x0403) & 0x00ff00ffu) | 0x64006400u))
+#define RPAIR(A, B, o, hi) ([&] { const uint32_t A_ = (A), B_ = (B); return RP_((o) + ((hi) ? 2 : 0)); }())
+#endif
 #define RING_ALL(hi, R)                                                                      \
                 R[0]  = RPAIR(w1[6], w2[6], 0, hi);  R[1]  = RPAIR(w1[6], w2[6], 1, hi);     \
                 R[2]  = RPAIR(w1[5], w2[5], 2, hi);  R[3]  = RPAIR(w1[4], w2[4], 3, hi);     \
@@ -671,27 +856,40 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
                 // corner needs one of them brighter than v+th or darker than v-th.  Flat areas leave here.
                 const uint32_t h0 = RPAIR(w1[6], w2[6], 0, 1), h4 = RPAIR(w1[3], w2[3], 3, 1);
                 const uint32_t h8 = RPAIR(w1[0], w2[0], 0, 1), h12 = RPAIR(w0[3], w1[3], 1, 1);
+#ifdef ORB_FAST_INTLANES
                 const uint32_t nvp_lo = __vadd2(~vlo, c1), vm1_lo = __vadd2(vlo, c1);      // -(v + th), v - th + 1
                 const uint32_t nvp_hi = __vadd2(~vhi, c1), vm1_hi = __vadd2(vhi, c1);
+#define LANEVAL(x) __byte_perm(x, 0, 0x4240)
+#define ARC_MINMAX arc_minmax
+#else
+                const uint32_t nvp_lo = __vadd2(~vlo, c1n), vm1_lo = __vadd2(vlo, c1p);    // -(v + th) - 0x6400, v - th + 1 + 0x6400
+                const uint32_t nvp_hi = __vadd2(~vhi, c1n), vm1_hi = __vadd2(vhi, c1p);
+#define LANEVAL(x) (x)
+#define ARC_MINMAX arc_minmax_h
+#endif
                 bool any;
                 {
                     const uint32_t bl = __vimax3_u16x2(ring[0], ring[4], __vmaxu2(ring[8], ring[12]));
                     const uint32_t dl = __vimin3_u16x2(ring[0], ring[4], __vminu2(ring[8], ring[12]));
                     const uint32_t bh = __vimax3_u16x2(h0, h4, __vmaxu2(h8, h12));
                     const uint32_t dh = __vimin3_u16x2(h0, h4, __vminu2(h8, h12));
-                    any = (excess2(__byte_perm(bl, 0, 0x4240), __byte_perm(dl, 0, 0x4240), nvp_lo, vm1_lo) |
-                           excess2(__byte_perm(bh, 0, 0x4240), __byte_perm(dh, 0, 0x4240), nvp_hi, vm1_hi)) != 0;
+                    any = (excess2(LANEVAL(bl), LANEVAL(dl), nvp_lo, vm1_lo) | excess2(LANEVAL(bh), LANEVAL(dh), nvp_hi, vm1_hi)) != 0;
                 }
                 if (any) {
-                    arc_minmax(ring, Mn, Mx);
-                    const uint32_t slo = excess2(__byte_perm(Mn, 0, 0x4240), __byte_perm(Mx, 0, 0x4240), nvp_lo, vm1_lo);
+                    ARC_MINMAX(ring, Mn, Mx);
+                    const uint32_t slo = excess2(LANEVAL(Mn), LANEVAL(Mx), nvp_lo, vm1_lo);
                     RING_ALL(1, ring)
-                    arc_minmax(ring, Mn, Mx);
-                    const uint32_t shi = excess2(__byte_perm(Mn, 0, 0x4240), __byte_perm(Mx, 0, 0x4240), nvp_hi, vm1_hi);
+                    ARC_MINMAX(ring, Mn, Mx);
+                    const uint32_t shi = excess2(LANEVAL(Mn), LANEVAL(Mx), nvp_hi, vm1_hi);
                     outw = __byte_perm(slo, shi, 0x6420) & cm;              // low byte of each of the four lanes
                 }
+#undef LANEVAL
+#undef ARC_MINMAX
 #undef RING_ALL
 #undef RPAIR
+#ifndef ORB_FAST_INTLANES
+#undef RP_
+#endif
             }
             sc[r * FSW + g] = outw;
         }
@@ -1612,6 +1810,10 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         const int tiles = ((D.w + tw - 1) / tw) * ((D.h + th - 1) / th) * nimg;
         const int bufb = (c->rs_box_w[l] * c->rs_box_h[l] + 127) & ~127;
         const int grid = std::min(tiles, c->num_sms * ORB_RESIZE_CTAS);
+        if (c->rs_unrolled && c->rs_packed[l] && rr == 8)
+            k_resize_u<8><<<grid, ORB_RESIZE_THREADS, 2 * bufb + 16, s>>>(W.tm_resize.m[l], W.d_planes, fb, D, reinterpret_cast<const uint4*>(c->d_xtab + c->rs_xg_off[l]),
+                                                                        c->d_ytab, c->rs_box_w[l], c->rs_box_h[l], bufb, nimg, W.d_counters + 4 + l, tw);
+        else
         k_resize<<<grid, ORB_RESIZE_THREADS, 2 * bufb + 16, s>>>(W.tm_resize.m[l], W.d_planes, fb, D, c->d_xtab, c->d_ytab, c->rs_box_w[l], c->rs_box_h[l],
                                                bufb, nimg, W.d_counters + 4 + l, tw, rr);
         launches++;
@@ -1692,7 +1894,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
 static int raise_dyn_smem(const void* fn, int slot, int bytes)
 {
     static std::mutex mu;
-    static int cur[6][64] = {};
+    static int cur[7][64] = {};
     int dev = 0;
     ORB_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(mu);
@@ -1706,6 +1908,7 @@ int orb_resize_smem_setup(int max_bytes)
 {
     static_assert(sizeof(PyrParams) <= 1024, "k_pyramid parameter block");
     int rc = raise_dyn_smem((const void*)k_resize, 0, max_bytes);
+    if (!rc) rc = raise_dyn_smem((const void*)k_resize_u<8>, 6, max_bytes);
     return rc ? rc : raise_dyn_smem((const void*)k_pyramid, 5, max_bytes);
 }
 

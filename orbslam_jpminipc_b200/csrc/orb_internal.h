@@ -194,6 +194,9 @@ struct orb_ctx {
     int debug_skip = 0;                                    // ORB_DEBUG_SKIP, honoured only by a -DORB_DEBUG build (timing experiments, results are wrong): 1 no blur, 2 no selection, 4 no describe
     int rs_flex_width = 1;                                 // ORB_RESIZE_FLEX=0: fixed 128-column k_resize tiles (A/B timing)
     int rs_rows_pref = 8;                                  // ORB_RESIZE_ROWS: output rows per k_resize thread (tile height = 8 * rows at 128 columns)
+    int rs_unrolled = 1;                                   // ORB_RESIZE_UNROLLED=0: k_resize for every level instead of k_resize_u (A/B timing)
+    int rs_packed[ORB_MAX_LEVELS] = { 0 };                 // every 4-column group's taps lie within 8 source bytes (k_resize_u's only form)
+    int rs_xg_off[ORB_MAX_LEVELS] = { 0 };                 // k_resize_u column-group table of the level: offset into xtab (int2 entries, 4 per group)
     int pyr_fused = 0;                                     // ORB_PYR_FUSED=0: one k_resize launch per level instead of the single k_pyramid launch (A/B timing)
     int select_serial = 0;                                 // ORB_SELECT_SERIAL=1: the thread-per-cell selection kernel (A/B timing)
     int knn_engine = 0;                                    // ORB_KNN_POPC (default) / ORB_KNN_TENSOR: orb_set_knn_engine, ORB_KNN_ENGINE=tensor

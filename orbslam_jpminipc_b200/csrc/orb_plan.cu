@@ -136,6 +136,27 @@ int orb_build_plan(orb_ctx* c, int w, int h)
             if (!fits && best_tw != 128) fits = try_tile(128, c->rs_rows_pref);
             if (!fits) fits = try_tile(64, 4);
             if (!fits) return ORB_ERR_CAPACITY;      // scale factors above ~3.7
+            // k_resize_u: per 4-column group the first source byte, the PRMT selectors of the four columns' tap pairs (byte offsets from
+            // that first byte, low nibble = tap 0, high nibble = tap 1; two selectors per word) and the four weight pairs
+            while (c->xtab.size() & 3) c->xtab.push_back(make_int2(0, 0));        // 32-byte aligned groups
+            c->rs_xg_off[l] = (int)c->xtab.size();
+            bool packed = true;
+            for (int gx = 0; gx < L.w; gx += 4) {
+                int2 e[4];
+                for (int k = 0; k < 4; k++) e[k] = c->xtab[L.xtab_off + std::min(gx + k, L.w - 1)];
+                const int cb = e[0].x & 0xffff;
+                unsigned sel[4];
+                for (int k = 0; k < 4; k++) {
+                    const int d0 = (e[k].x & 0xffff) - cb, d1 = (e[k].x >> 16) - cb;
+                    packed = packed && d0 >= 0 && d1 >= 0 && d0 <= 7 && d1 <= 7;
+                    sel[k] = (unsigned)(d0 & 7) | ((unsigned)(d1 & 7) << 4);
+                }
+                c->xtab.push_back(make_int2(cb, (int)(sel[0] | sel[1] << 16)));
+                c->xtab.push_back(make_int2((int)(sel[2] | sel[3] << 16), 0));
+                c->xtab.push_back(make_int2(e[0].y, e[1].y));
+                c->xtab.push_back(make_int2(e[2].y, e[3].y));
+            }
+            c->rs_packed[l] = packed;
         }
         L.border_base = border;
         // k_border work items (32-bit words): ORB_RING full rows above and below the ROI, and per ROI row the word left of it plus
