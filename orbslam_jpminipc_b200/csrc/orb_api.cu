@@ -238,6 +238,7 @@ orb_ctx* orb_create(int device, int nfeatures, float scale_factor, int nlevels, 
     if (const char* e = getenv("ORB_DEBUG_SKIP")) c->debug_skip = atoi(e);
 #endif
     if (const char* e = getenv("ORB_PYR_FUSED")) c->pyr_fused = atoi(e);
+    if (const char* e = getenv("ORB_FAST_ETILE")) c->fast_etile = atoi(e);
     if (const char* e = getenv("ORB_RESIZE_UNROLLED")) c->rs_unrolled = atoi(e);
     if (const char* e = getenv("ORB_RESIZE_FLEX")) c->rs_flex_width = atoi(e) != 0;
     if (const char* e = getenv("ORB_RESIZE_ROWS")) c->rs_rows_pref = std::max(1, std::min(atoi(e), 32));

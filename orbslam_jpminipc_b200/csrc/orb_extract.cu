@@ -709,9 +709,13 @@ __device__ __forceinline__ void arc_minmax_h(const uint32_t (&r)[16], uint32_t& 
     for (int q = 0; q < 4; q++) {
         const int k = 4 * q;
 #define R_(i) r[(k + (i)) & 15]
+#if ORB_FAST_HALF_LEVEL >= 1
         const uint32_t d09 = h2_relu_sub(R_(0), R_(9)), d211 = h2_relu_sub(R_(2), R_(11));
         const uint32_t mx09 = h2_add(R_(9), d09), mn09 = h2_sub(R_(0), d09);
         const uint32_t mx211 = h2_add(R_(11), d211), mn211 = h2_sub(R_(2), d211);
+#else
+        const uint32_t mx09 = __vmaxu2(R_(0), R_(9)), mn09 = __vminu2(R_(0), R_(9)), mx211 = __vmaxu2(R_(2), R_(11)), mn211 = __vminu2(R_(2), R_(11));
+#endif
         {
             const uint32_t eA = __vimin3_u16x2(R_(1), R_(2), mx09);
             const uint32_t eB = __vimin3_u16x2(R_(9), R_(10), mx211);
@@ -733,12 +737,20 @@ __device__ __forceinline__ void arc_minmax_h(const uint32_t (&r)[16], uint32_t& 
 
 // Persistent kernel: each CTA walks (tile, frame) work items; the image tile of item i+1 is fetched by
 // TMA into the other shared-memory buffer while item i is being scored.
-__global__ void __launch_bounds__(FAST_THREADS, FAST_CTAS)
+// ETILE (round 2, ORB_FAST_ETILE): the raw tile is first re-encoded into a tile of half lanes (one 16-bit lane 0x6400 | pixel per pixel,
+// columns x0-4 .. x0+67), so that a ring sample pair is an aligned 32-bit word of that tile when its first pixel is even and ONE
+// PRMT of two neighbouring words when it is odd: 18 PRMT per 4-pixel task instead of 42 + 10 LOP3, and the 0x64 comes out of
+// memory instead of out of an instruction.  The raw tile is then dead (the halo pass, which still reads it, runs before the score
+// pass), so ONE raw buffer suffices: the next item's TMA copy is issued after the re-encoding and lands during the score pass.
+constexpr int EW = FT_W / 2 + 4;        // 32-bit words per row of the half-lane tile (72 pixels)
+template <bool ETILE>
+__global__ void __launch_bounds__(FAST_THREADS, ETILE ? 5 : 6)      // residency is set by shared memory (42.6 / 36.1 KB per CTA), so the register cap may follow it
 k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_t* __restrict__ bitmap, size_t fbytes,
            const Plan* __restrict__ plan, const Tile* __restrict__ tiles, int ntiles, int total, int* __restrict__ work_counter,
            const uint8_t* __restrict__ coltab, const int16_t* __restrict__ rowtab)
 {
-    __shared__ __align__(128) uint32_t img2[2][(FI_H * FIW + 31) & ~31];      // each buffer 128-byte aligned (TMA destination) for any tile height
+    __shared__ __align__(128) uint32_t img2[ETILE ? 1 : 2][(FI_H * FIW + 31) & ~31];      // each buffer 128-byte aligned (TMA destination) for any tile height
+    __shared__ __align__(16) uint32_t et[ETILE ? FI_H * EW : 4];
     __shared__ int s_next[2], s_ti[2], s_fr[2];             // next work item; tile index and frame of the item in each buffer
     __shared__ __align__(16) uint32_t sc[FS_H * FSW];
     __shared__ short rowcell[FS_H];
@@ -761,8 +773,9 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
         const int ti = item % ntiles, fr = item / ntiles;
         const Tile t = tiles[ti];
         s_ti[buf] = ti; s_fr[buf] = fr;                     // decoded once here instead of by every thread
-        mbar_expect_tx(&bar[buf], TILE_BYTES);
-        tma_load_3d(&img2[buf][0], &tm.m[t.level], t.x0 - 16 + ORB_EDGE, t.y0 - 4 + ORB_EDGE, fr, &bar[buf]);
+        const int rb = ETILE ? 0 : buf;
+        mbar_expect_tx(&bar[rb], TILE_BYTES);
+        tma_load_3d(&img2[rb][0], &tm.m[t.level], t.x0 - 16 + ORB_EDGE, t.y0 - 4 + ORB_EDGE, fr, &bar[rb]);
     };
     if (tid == 0) {
         mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
@@ -783,7 +796,7 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
         if (tid == 0) {
             const int nxt = atomicAdd(work_counter, 1) + (int)gridDim.x;
             s_next[buf] = nxt;
-            if (nxt < total) issue(nxt, buf ^ 1);
+            if (!ETILE && nxt < total) issue(nxt, buf ^ 1);
         }
 
         // detection cells of the score tile's columns (as byte masks) and rows: copied from the per-level tables the host built
@@ -799,9 +812,9 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
                 } else rowcell[i - 3 * FSW] = __ldg(rt + (i - 3 * FSW));
             }
         }
-        if (tid < 32) mbar_wait(&bar[buf], (uint32_t)((it >> 1) & 1));      // image tile has landed; one warp polls, the rest sleep in the barrier
+        if (tid < 32) mbar_wait(&bar[ETILE ? 0 : buf], (uint32_t)((ETILE ? it : it >> 1) & 1));      // image tile has landed; one warp polls, the rest sleep in the barrier
         __syncthreads();
-        const uint32_t* img = img2[buf];
+        const uint32_t* img = img2[ETILE ? 0 : buf];
         // Tiles on the right / bottom edge of the detection region are only partly filled (8 % of the tile area at 752x480):
         // tasks are numbered over the filled part only, so that a narrow tile takes fewer rounds instead of idle lanes.
         // vw x vh = detection pixels of the tile; the NMS walks nq 16-pixel groups per row and reads one score word more on
@@ -820,6 +833,54 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
             const int r = FULL ? task / (FT_W / 4) : (int)(((uint32_t)(task >> 2) * inv_nq) >> 20), g = task - r * (FULL ? FT_W / 4 : nwi) + 1;
             const uint32_t cm = FULL ? 0xffffffffu : reinterpret_cast<const uint32_t*>(m_in)[g];   // every column of a full tile is a detection column
             uint32_t outw = 0;
+            if (ETILE) {
+              if (cm != 0 && rowcell[r] >= 0) {
+                // words 2g-2 .. 2g+3 of rows r..r+6 of the half-lane tile = pixels x-4 .. x+7 (x = first pixel of the task); the rows
+                // three and two away only need words 2g-1 .. 2g+2
+                const uint32_t* ep = et + r * EW + 2 * g;
+                uint32_t W[7][6];
+#pragma unroll
+                for (int q = 0; q < 7; q++) {
+                    const uint2 m = *reinterpret_cast<const uint2*>(ep + q * EW);
+                    W[q][2] = m.x; W[q][3] = m.y;
+                    if (q >= 2 && q <= 4) {
+                        const uint2 lo = *reinterpret_cast<const uint2*>(ep + q * EW - 2), hi = *reinterpret_cast<const uint2*>(ep + q * EW + 2);
+                        W[q][0] = lo.x; W[q][1] = lo.y; W[q][4] = hi.x; W[q][5] = hi.y;
+                    } else { W[q][0] = 0; W[q][1] = ep[q * EW - 1]; W[q][4] = ep[q * EW + 2]; W[q][5] = 0; }
+                }
+                // pixel pair starting s pixels from x in row q: a word of the tile for even s, the upper half of one and the lower half of the next for odd s
+#define S_(q, s) ((((s) + 4) & 1) == 0 ? W[q][((s) + 4) >> 1] : __byte_perm(W[q][((s) + 3) >> 1], W[q][((s) + 5) >> 1], 0x5432))
+#define RING_E(o, R)                                                                                                     \
+                R[0]  = S_(6, 0 + o);  R[1]  = S_(6, 1 + o);  R[2]  = S_(5, 2 + o);  R[3]  = S_(4, 3 + o);                  \
+                R[4]  = S_(3, 3 + o);  R[5]  = S_(2, 3 + o);  R[6]  = S_(1, 2 + o);  R[7]  = S_(0, 1 + o);                  \
+                R[8]  = S_(0, 0 + o);  R[9]  = S_(0, -1 + o); R[10] = S_(1, -2 + o); R[11] = S_(2, -3 + o);                 \
+                R[12] = S_(3, -3 + o); R[13] = S_(4, -3 + o); R[14] = S_(5, -2 + o); R[15] = S_(6, -1 + o);
+                const uint32_t vlo = W[3][2] & 0x00ff00ffu, vhi = W[3][3] & 0x00ff00ffu;
+                uint32_t ring[16], Mn, Mx;
+                RING_E(0, ring)
+                const uint32_t h0 = S_(6, 2), h4 = S_(3, 5), h8 = S_(0, 2), h12 = S_(3, -1);
+                const uint32_t nvp_lo = __vadd2(~vlo, c1n), vm1_lo = __vadd2(vlo, c1p);    // -(v + th) - 0x6400, v - th + 1 + 0x6400
+                const uint32_t nvp_hi = __vadd2(~vhi, c1n), vm1_hi = __vadd2(vhi, c1p);
+                bool any;
+                {
+                    const uint32_t bl = __vimax3_u16x2(ring[0], ring[4], __vmaxu2(ring[8], ring[12]));
+                    const uint32_t dl = __vimin3_u16x2(ring[0], ring[4], __vminu2(ring[8], ring[12]));
+                    const uint32_t bh = __vimax3_u16x2(h0, h4, __vmaxu2(h8, h12));
+                    const uint32_t dh = __vimin3_u16x2(h0, h4, __vminu2(h8, h12));
+                    any = (excess2(bl, dl, nvp_lo, vm1_lo) | excess2(bh, dh, nvp_hi, vm1_hi)) != 0;
+                }
+                if (any) {
+                    arc_minmax_h(ring, Mn, Mx);
+                    const uint32_t slo = excess2(Mn, Mx, nvp_lo, vm1_lo);
+                    RING_E(2, ring)
+                    arc_minmax_h(ring, Mn, Mx);
+                    const uint32_t shi = excess2(Mn, Mx, nvp_hi, vm1_hi);
+                    outw = __byte_perm(slo, shi, 0x6420) & cm;              // low byte of each of the four lanes
+                }
+#undef RING_E
+#undef S_
+              }
+            } else
             if (cm != 0 && rowcell[r] >= 0) {
                 const uint32_t* ip = img + r * FIW + g + 2;          // rows r..r+6 (y-3..y+3), words of cols x-4..x+7
                 uint32_t w0[7], w1[7], w2[7];
@@ -893,10 +954,13 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
             }
             sc[r * FSW + g] = outw;
         }
+        };
         // ---- halo columns: the NMS of the tile's first / last pixel column needs the strength of ONE pixel to the left (x0 - 1,
         //      byte 3 of score word 0) and to the right (x0 + 16 nq, byte 0 of score word 4 nq + 1).  Scoring those two words like
         //      the others would spend 2 of 18 tasks per row on 2 useful pixels of 8; here one task scores the pair (left, right)
         //      of a row in the two 16-bit lanes: 1 task per row instead of 2, and with 2 pixels instead of 4. ----
+        auto halo_pass = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
         const int nrh = FULL ? FS_H : nr, gr = (FULL ? FT_W / 4 : nwi) + 1;
         for (int r = tid; r < nrh; r += FAST_THREADS) {
             const uint32_t mL = m_in[3], mR = m_in[4 * gr];
@@ -929,7 +993,19 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
         }
         };
         const bool full = vw == FT_W && nr == FS_H;
+        if (ETILE) {
+            // re-encode the raw tile: raw word 3 + j of a row (columns x0-4+4j ..) -> words 2j, 2j+1 of the half-lane tile
+            for (int i = tid; i < FI_H * (EW / 2); i += FAST_THREADS) {
+                const int row = i / (EW / 2), j = i - row * (EW / 2);
+                const uint32_t rw = img[row * FIW + 3 + j];
+                *reinterpret_cast<uint2*>(et + row * EW + 2 * j) = make_uint2(__byte_perm(rw, 0x64646464u, 0x4140), __byte_perm(rw, 0x64646464u, 0x4342));
+            }
+            if (full) halo_pass(std::true_type{}); else halo_pass(std::false_type{});
+            __syncthreads();       // the raw tile is dead: fetch the next item's into the same buffer
+            if (tid == 0 && s_next[buf] < total) issue(s_next[buf], buf ^ 1);
+        }
         if (full) score_pass(std::true_type{}); else score_pass(std::false_type{});
+        if (!ETILE) { if (full) halo_pass(std::true_type{}); else halo_pass(std::false_type{}); }
         __syncthreads();
 
         // ---- NMS restricted to the pixel's own cell: one task = 16 output pixels (four words): one 128-bit store
@@ -1840,8 +1916,12 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
     {
         const int total = P.ntiles_fast * nimg;
         const int grid = std::min(total, c->num_sms * (fork && c->fork_early == 1 ? c->fast_ctas : FAST_CTAS));
-        k_fast_nms<<<grid, FAST_THREADS, 0, s>>>(W.tm_fast, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total, W.d_counters + 1,
-                                                     c->d_fast_coltab, c->d_fast_rowtab);
+        if (c->fast_etile)
+            k_fast_nms<true><<<grid, FAST_THREADS, 0, s>>>(W.tm_fast, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total, W.d_counters + 1,
+                                                           c->d_fast_coltab, c->d_fast_rowtab);
+        else
+            k_fast_nms<false><<<grid, FAST_THREADS, 0, s>>>(W.tm_fast, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total, W.d_counters + 1,
+                                                            c->d_fast_coltab, c->d_fast_rowtab);
     }
     if (fork && c->fork_early == 2) {     // blur starts behind FAST, next to compaction + selection
         ORB_CUDA(cudaEventRecord(W.ev_fork, s));

@@ -27,7 +27,7 @@
 #define ORB_RESIZE_CTAS 4
 #endif
 #ifndef ORB_TILE_H
-#define ORB_TILE_H 128
+#define ORB_TILE_H 112           // with the half-lane tile (k_fast_nms<true>) 112 rows keep six CTAs per SM resident: 2.888 -> 2.814 ms per 1024 frames against 128
 #endif
 #define ORB_BLUR_TILE_W 64
 #define ORB_BLUR_TILE_H 56
@@ -194,6 +194,7 @@ struct orb_ctx {
     int debug_skip = 0;                                    // ORB_DEBUG_SKIP, honoured only by a -DORB_DEBUG build (timing experiments, results are wrong): 1 no blur, 2 no selection, 4 no describe
     int rs_flex_width = 1;                                 // ORB_RESIZE_FLEX=0: fixed 128-column k_resize tiles (A/B timing)
     int rs_rows_pref = 8;                                  // ORB_RESIZE_ROWS: output rows per k_resize thread (tile height = 8 * rows at 128 columns)
+    int fast_etile = 1;                                    // ORB_FAST_ETILE=0: k_fast_nms<false> (ring samples by PRMT from the raw tile) instead of the half-lane tile (A/B timing)
     int rs_unrolled = 1;                                   // ORB_RESIZE_UNROLLED=0: k_resize for every level instead of k_resize_u (A/B timing)
     int rs_packed[ORB_MAX_LEVELS] = { 0 };                 // every 4-column group's taps lie within 8 source bytes (k_resize_u's only form)
     int rs_xg_off[ORB_MAX_LEVELS] = { 0 };                 // k_resize_u column-group table of the level: offset into xtab (int2 entries, 4 per group)
