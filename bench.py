@@ -355,24 +355,26 @@ def measure_extraction(E, w, h, steps, warmup, launches, full):
     out_d = np.zeros((B, cap, 32), np.uint8)
     out_c = np.zeros(B, np.int32)
     pk, pd, pc = (torch.from_numpy(a.view(np.uint8).reshape(-1)).pin_memory() for a in (out_k, out_d, out_c))
-    outs = [(pk, pd, pc), tuple(torch.empty_like(t_).pin_memory() for t_ in (pk, pd, pc))]
+    DEPTH = 3                      # calls in flight: launch i is enqueued before launch i-2 is waited for, each with its own pinned outputs
+    outs = [(pk, pd, pc)] + [tuple(torch.empty_like(t_).pin_memory() for t_ in (pk, pd, pc)) for _ in range(DEPTH - 1)]
     h2d, d2h = int(B * w * h), int(B * cap * 60 + B * 4)
 
-    # streaming form: launch i is enqueued (orb_extract_batch_async) before launch i-1 is waited for (orb_wait), with two sets of pinned
+    # streaming form: launch i is enqueued (orb_extract_batch_async) before launch i-2 is waited for (orb_wait), with three sets of pinned
     # output buffers, so the H2D of a launch overlaps the kernels of the previous one.  Every launch still copies its frames
     # host->device and its keypoints / descriptors / counts device->host inside the timed region.
     def run_stream(n):
-        prev = None
+        pending = []
         for i in range(n):
-            ok_, od_, oc_ = outs[i & 1]
+            ok_, od_, oc_ = outs[i % DEPTH]
             tk = C.c_longlong(-1)
             check(L.orb_extract_batch_async(ex._h, ptr(pin), B, w, h, w, w * h, C.c_void_p(ok_.data_ptr()), C.c_void_p(od_.data_ptr()),
                                             cap, C.c_void_p(oc_.data_ptr()), C.byref(tk)), "orb_extract_batch_async")
-            if prev is not None:
-                check(L.orb_wait(ex._h, prev), "orb_wait")
-            prev = tk.value
-        check(L.orb_wait(ex._h, prev), "orb_wait")
-    run_stream(4)
+            pending.append(tk.value)
+            if len(pending) == DEPTH:                    # the call that owns the pinned outputs the next launch will write
+                check(L.orb_wait(ex._h, pending.pop(0)), "orb_wait")
+        for tk_ in pending:
+            check(L.orb_wait(ex._h, tk_), "orb_wait")
+    run_stream(2 * DEPTH)
     E.barrier()
     e0.record()
     run_stream(launches * steps)
@@ -383,7 +385,7 @@ def measure_extraction(E, w, h, steps, warmup, launches, full):
     res["e2e"] = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * launches, "d2h_bytes_per_step": d2h * launches,
                   "ms_per_step": e2e_ms / steps, "gpu_launches_per_step": ex.last_launch_count() * launches,
                   "frames_per_call": B, "calls_per_step": launches,
-                  "api": "orb_extract_batch_async + orb_wait, two calls in flight (pinned host buffers in and out, calls alternate two work sets)"}
+                  "api": "orb_extract_batch_async + orb_wait, three calls in flight (pinned host buffers in and out, one output set per call in flight; calls alternate two device work sets, D2H on its own stream)"}
 
     if full:
         # one blocking call per launch, internally chunked (a context whose max_batch is a fraction of the call's batch makes

@@ -253,6 +253,8 @@ orb_ctx* orb_create(int device, int nfeatures, float scale_factor, int nlevels, 
               cudaMemset(c->d_status, 0, 32 * sizeof(int)) == cudaSuccess;
     for (int i = 0; i < 2 && ok; i++) {
         ok = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&c->out_streams[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_out_done[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming) == cudaSuccess;
     }
     ok = ok && cudaEventCreateWithFlags(&c->ev_user, cudaEventDisableTiming) == cudaSuccess &&
@@ -321,6 +323,8 @@ void orb_destroy(orb_ctx* c)
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) {
         if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+        if (c->out_streams[i]) cudaStreamDestroy(c->out_streams[i]);
+        if (c->ev_out_done[i]) cudaEventDestroy(c->ev_out_done[i]);
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
     }
     delete c;
@@ -491,15 +495,25 @@ int orb_extract_batch_async(orb_ctx* c, const uint8_t* imgs, int nimg, int w, in
             // B200, 256 frames 752x480 per step, streaming: chunk 256 chained 86.9 K frames/s, free 81.6 K; chunk 64 chained 67.4 K,
             // free 78.9 K (small grids do not fill the GPU and gain from overlapping), hence the size test.
             if (c->chain_chunks && c->kernels_pending && (double)n * w * h >= 40e6) ORB_CUDA(cudaStreamWaitEvent(s, c->ev_free[slot ^ 1], 0));
+            // the slot's output staging buffers are still being copied out by the chunk two back (its D2H runs on the slot's OUT
+            // stream, below): the kernels wait for that copy, the H2D copy above did not have to
+            if (!dev_out && c->out_pending[slot]) ORB_CUDA(cudaStreamWaitEvent(s, c->ev_out_done[slot], 0));
             rc = launch_extract(c, c->ws[slot], d_in, n, w, h, stride, frame_pitch, o_k, o_d, cap, o_c, s);
             if (rc != ORB_OK) return rc;
             launches += c->last_launches;
             ORB_CUDA(cudaEventRecord(c->ev_free[slot], s));
             c->kernels_pending = true;
             if (!dev_out) {
-                ORB_CUDA(cudaMemcpyAsync(kps + (size_t)f0 * cap, o_k, (size_t)n * cap * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, s));
-                ORB_CUDA(cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, o_d, (size_t)n * cap * 32, cudaMemcpyDeviceToHost, s));
-                ORB_CUDA(cudaMemcpyAsync(counts + f0, o_c, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+                // D2H on a stream of its own: on the slot's stream it sat between this chunk's kernels and the NEXT H2D copy of the
+                // slot, which then finished too late for its kernels to start when the other slot's end (7.1 instead of 6.4 ms per
+                // 1024 frames of 640x480: round 2, 148.6 K -> see DESIGN.md)
+                cudaStream_t os = c->out_streams[slot];
+                ORB_CUDA(cudaStreamWaitEvent(os, c->ev_free[slot], 0));
+                ORB_CUDA(cudaMemcpyAsync(kps + (size_t)f0 * cap, o_k, (size_t)n * cap * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, os));
+                ORB_CUDA(cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, o_d, (size_t)n * cap * 32, cudaMemcpyDeviceToHost, os));
+                ORB_CUDA(cudaMemcpyAsync(counts + f0, o_c, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, os));
+                ORB_CUDA(cudaEventRecord(c->ev_out_done[slot], os));
+                c->out_pending[slot] = true;
             }
             if (slot == 0) { c->last_n0 = n; c->last_n1 = 0; } else c->last_n1 = n;
         }
@@ -509,6 +523,7 @@ int orb_extract_batch_async(orb_ctx* c, const uint8_t* imgs, int nimg, int w, in
     ORB_CUDA(cudaEventRecord(t.b, c->streams[1]));
     ORB_CUDA(cudaStreamWaitEvent(c->done_stream, t.a, 0));
     ORB_CUDA(cudaStreamWaitEvent(c->done_stream, t.b, 0));
+    for (int i = 0; i < 2; i++) if (c->out_pending[i]) ORB_CUDA(cudaStreamWaitEvent(c->done_stream, c->ev_out_done[i], 0));     // latest D2H of either slot
     ORB_CUDA(cudaMemcpyAsync(t.h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->done_stream));
     ORB_CUDA(cudaEventRecord(t.done, c->done_stream));
     t.counts = counts; t.nimg = nimg; t.cap = cap; t.host_out = !dev_out; t.seq = c->next_seq;

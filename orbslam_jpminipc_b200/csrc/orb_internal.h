@@ -186,6 +186,9 @@ struct orb_ctx {
     uint8_t* d_desc[2] = { nullptr, nullptr };
     int32_t* d_counts[2] = { nullptr, nullptr };
     cudaStream_t streams[2] = { nullptr, nullptr };
+    cudaStream_t out_streams[2] = { nullptr, nullptr };   // device->host copies of a slot's results (host-buffer calls)
+    cudaEvent_t ev_out_done[2] = { nullptr, nullptr };
+    bool out_pending[2] = { false, false };
     cudaEvent_t ev_free[2] = { nullptr, nullptr };
     int last_launches = 0;
     int num_sms = 148;
