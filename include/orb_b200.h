@@ -325,6 +325,22 @@ int  orb_vocab_transform_batch(orb_ctx*, orb_vocab*, const uint8_t* desc, int sl
  * (int)(max_common*0.8f) shared words (all keyframes sharing a word if score_all), else 0. */
 int  orb_bow_score_db(orb_ctx*, orb_vocab*, const int32_t* qword, const double* qval, int nq, int nkf, const int32_t* kf_start,
                       const int32_t* kf_word, const double* kf_val, int score_all, int32_t* common, float* score, int* max_common);
+/* The two retrieval queries complete: KeyFrameDatabase::DetectRelocalisationCandidates(Frame*) (src/KeyFrameDatabase.cc:198-308,
+ * loop = 0) and DetectLoopCandidates(KeyFrame*, minScore) (:75-196, loop = 1) over nkf keyframes in the order they were add()ed.
+ *   excluded[k] != 0 (loop only, may be NULL): keyframe k is connected to the query keyframe (pKF->GetConnectedKeyFrames(), :77,:95)
+ *     and never enters the list.
+ *   cov_start / cov_idx (CSR, may be NULL): GetBestCovisibilityKeyFrames(10) of every keyframe, in its order (:146,:267); at most
+ *     the first ten entries of a row are read.
+ *   kf_score (in / out): the mRelocScore / mLoopScore member of every keyframe.  Keyframes scored by this query are rewritten, the
+ *     others keep their value: the reference adds the STALE score of a covisible keyframe that shares a word with the query without
+ *     having been scored by it (:278-281), so the state has to travel with the caller like the member travels with the keyframe.
+ *   common[k] (out): words shared with the query (0 for excluded keyframes).
+ *   cand (out, room for nkf), *ncand: the returned keyframes in the reference's order (first nomination in list order, :170-190).
+ * Loop rules: only keyframes with score >= min_score are nominators, neighbours need more than minCommonWords shared words, the best
+ * accumulated score starts at min_score.  All array pointers host or all device. */
+int  orb_bow_detect_candidates(orb_ctx*, orb_vocab*, const int32_t* qword, const double* qval, int nq, int nkf, const int32_t* kf_start,
+                               const int32_t* kf_word, const double* kf_val, const uint8_t* excluded, int loop, float min_score,
+                               const int32_t* cov_start, const int32_t* cov_idx, float* kf_score, int32_t* common, int32_t* cand, int* ncand);
 
 /* ------------------------------------------------------------------ multi-GPU ----------
  * The path shards two ways: frames are independent (contiguous blocks of frames per GPU, no data-path collective), and the

@@ -23,6 +23,7 @@
 #include <cmath>
 #include <cstring>
 #include <vector>
+#include <set>
 
 namespace {
 
@@ -1458,6 +1459,68 @@ void orc_bow_score_db(const int32_t* qw, const double* qv, int nq, int nkf, cons
             score[k] = (float)orc_bow_score_l1(qw, qv, nq, kf_word + kf_start[k], kf_val + kf_start[k], kf_start[k + 1] - kf_start[k]);
     }
     *max_common = mx;
+}
+
+/* KeyFrameDatabase::DetectRelocalisationCandidates (src/KeyFrameDatabase.cc:198-308, loop = 0) and DetectLoopCandidates (:75-196,
+ * loop = 1) restated on flat arrays; keyframe index = order of KeyFrameDatabase::add, so every inverted-file list (:41-47) is
+ * ascending in k.  kf_score = the mRelocScore / mLoopScore members (in / out). */
+int orc_bow_detect_candidates(const int32_t* qw, const double* qv, int nq, int nkf, const int32_t* kf_start, const int32_t* kf_word,
+                              const double* kf_val, const uint8_t* excluded, int loop, float min_score, const int32_t* cov_start,
+                              const int32_t* cov_idx, float* kf_score, int32_t* common, int32_t* cand)
+{
+    std::map<int, std::vector<int> > inverted;                          /* mvInvertedFile */
+    for (int k = 0; k < nkf; k++) for (int j = kf_start[k]; j < kf_start[k + 1]; j++) inverted[kf_word[j]].push_back(k);
+    std::vector<int> query(nkf, 0), words(nkf, 0), sharing;             /* mnRelocQuery == F->mnId, mnRelocWords, lKFsSharingWords */
+    for (int a = 0; a < nq; a++) {                                      /* :205-222 / :85-104 */
+        std::map<int, std::vector<int> >::const_iterator it = inverted.find(qw[a]);
+        if (it == inverted.end()) continue;
+        for (size_t i = 0; i < it->second.size(); i++) {
+            const int k = it->second[i];
+            if (!query[k]) {
+                words[k] = 0;
+                if (!(loop && excluded && excluded[k])) { query[k] = 1; sharing.push_back(k); }
+            }
+            words[k]++;
+        }
+    }
+    for (int k = 0; k < nkf; k++) common[k] = query[k] ? words[k] : 0;
+    if (sharing.empty()) return 0;
+    int maxCommonWords = 0;
+    for (size_t i = 0; i < sharing.size(); i++) maxCommonWords = std::max(maxCommonWords, words[sharing[i]]);
+    const int minCommonWords = (int)((float)maxCommonWords * 0.8f);    /* :233 / :117 */
+    std::vector<int> scored;                                            /* lScoreAndMatch */
+    for (size_t i = 0; i < sharing.size(); i++) {
+        const int k = sharing[i];
+        if (words[k] > minCommonWords) {
+            const float si = (float)orc_bow_score_l1(qw, qv, nq, kf_word + kf_start[k], kf_val + kf_start[k], kf_start[k + 1] - kf_start[k]);
+            kf_score[k] = si;
+            if (!loop || si >= min_score) scored.push_back(k);           /* :131-132 */
+        }
+    }
+    if (scored.empty()) return 0;
+    std::vector<std::pair<float, int> > acc;                            /* lAccScoreAndMatch */
+    float bestAccScore = loop ? min_score : 0.f;                        /* :139 / :260 */
+    for (size_t i = 0; i < scored.size(); i++) {
+        const int k = scored[i];
+        float bestScore = kf_score[k], accScore = kf_score[k];
+        int best = k;
+        if (cov_start)
+            for (int j = cov_start[k]; j < cov_start[k + 1] && j < cov_start[k] + 10; j++) {      /* GetBestCovisibilityKeyFrames(10) */
+                const int k2 = cov_idx[j];
+                if (!query[k2]) continue;                                /* :274 / :153 */
+                if (loop && !(words[k2] > minCommonWords)) continue;     /* :153 */
+                accScore += kf_score[k2];
+                if (kf_score[k2] > bestScore) { best = k2; bestScore = kf_score[k2]; }
+            }
+        acc.push_back(std::make_pair(accScore, best));
+        if (accScore > bestAccScore) bestAccScore = accScore;
+    }
+    const float minScoreToRetain = 0.75f * bestAccScore;
+    std::set<int> added;
+    int n = 0;
+    for (size_t i = 0; i < acc.size(); i++)
+        if (acc[i].first > minScoreToRetain && !added.count(acc[i].second)) { cand[n++] = acc[i].second; added.insert(acc[i].second); }
+    return n;
 }
 
 

@@ -195,6 +195,10 @@ double orc_bow_score_l1(const int32_t* w1, const double* v1, int n1, const int32
  * every keyframe (mnRelocWords), max, and the score of those with more than (int)(max*0.8f) shared words (others 0). */
 void  orc_bow_score_db(const int32_t* qw, const double* qv, int nq, int nkf, const int32_t* kf_start, const int32_t* kf_word,
                        const double* kf_val, int32_t* common, float* score, int* max_common);
+/* both retrieval queries complete (src/KeyFrameDatabase.cc:75-196, :198-308) on flat arrays; returns the number of candidates */
+int   orc_bow_detect_candidates(const int32_t* qw, const double* qv, int nq, int nkf, const int32_t* kf_start, const int32_t* kf_word,
+                                const double* kf_val, const uint8_t* excluded, int loop, float min_score, const int32_t* cov_start,
+                                const int32_t* cov_idx, float* kf_score, int32_t* common, int32_t* cand);
 
 /* ---- frame plumbing ---- */
 /* cvtColor(CV_RGB2GRAY / CV_BGR2GRAY), src/Tracking.cc:202-208; order 0 = RGB, 1 = BGR; OpenCV 4.x 15-bit coefficients */

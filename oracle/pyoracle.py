@@ -481,6 +481,32 @@ def bow_score_db(query, kf_bows):
     return common, score, mx.value
 
 
+def bow_detect_candidates(query, kf_bows, kf_score, covis=None, excluded=None, loop=False, min_score=0.0):
+    """src/KeyFrameDatabase.cc:198-308 (loop=False) / :75-196 (loop=True) -> (candidates in the reference's order, common); kf_score in place"""
+    qw = np.ascontiguousarray(query[0], np.int32); qv = np.ascontiguousarray(query[1], np.float64)
+    n = len(kf_bows)
+    start = np.zeros(n + 1, np.int32)
+    for i, b in enumerate(kf_bows):
+        start[i + 1] = start[i] + len(b[0])
+    words = np.ascontiguousarray(np.concatenate([np.asarray(b[0], np.int32) for b in kf_bows]), np.int32)
+    vals = np.ascontiguousarray(np.concatenate([np.asarray(b[1], np.float64) for b in kf_bows]), np.float64)
+    cs = ci = None
+    if covis is not None:
+        cs = np.zeros(n + 1, np.int32)
+        for i, c_ in enumerate(covis):
+            cs[i + 1] = cs[i] + len(c_)
+        ci = np.ascontiguousarray(np.concatenate([np.asarray(c_, np.int32) for c_ in covis]) if cs[n] else np.zeros(1, np.int32), np.int32)
+    ex = None if excluded is None else np.ascontiguousarray(excluded, np.uint8)
+    assert kf_score.dtype == np.float32 and kf_score.flags.c_contiguous
+    common = np.zeros(n, np.int32); cand = np.zeros(max(n, 1), np.int32)
+    f = lib().orc_bow_detect_candidates
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p] * 2 + [C.c_int] * 2 + [C.c_void_p] * 4 + [C.c_int, C.c_float] + [C.c_void_p] * 5
+    nc = f(_p(qw), _p(qv), len(qw), n, _p(start), _p(words), _p(vals), _p(ex) if ex is not None else None, int(loop), float(min_score),
+           _p(cs) if cs is not None else None, _p(ci) if ci is not None else None, _p(kf_score), _p(common), _p(cand))
+    return cand[:nc].copy(), common
+
+
 def cvt_gray(img, order=0):
     img = np.ascontiguousarray(img, np.uint8)
     h, w = img.shape[:2]

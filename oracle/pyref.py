@@ -47,6 +47,8 @@ def lib():
         L.ref_frame_set_mappoints.argtypes = [vp, vp, vp, vp]
         L.ref_frame_set_bowvec.argtypes = [vp, i, vp, vp]
         L.ref_detect_relocalisation_candidates.argtypes = [vp, vp, vp, i, vp, vp, vp]
+        if hasattr(L, "ref_detect_candidates"):
+            L.ref_detect_candidates.argtypes = [vp, vp, vp, i, i, vp, vp, vp, i, f, vp, vp, vp, vp]
         L.ref_frame_update_points.argtypes = [vp]
         if hasattr(L, "ref_fuse"):                       # not in the drop-in flavour (oracle/pydropin.py): their projection stays with the caller
             L.ref_search_by_projection_kf.argtypes = [vp, vp, vp, f, i, f, i, vp, vp]
@@ -324,6 +326,20 @@ def detect_relocalisation_candidates(vocab, query, keyframes):
     common, score, cand = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.int32)
     _ok(lib().ref_detect_relocalisation_candidates(vocab._h, query._h, hs, n, _p(common), _p(score), _p(cand)), "DetectRelocalisationCandidates")
     return common, score, cand.astype(bool)
+
+
+def detect_candidates(vocab, query, keyframes, edges, kf_score, loop=False, min_score=0.0):
+    """KeyFrameDatabase::DetectRelocalisationCandidates / DetectLoopCandidates (loop=True) with a covisibility graph.
+    edges = [(a, b, weight)], a = -1 for the query keyframe.  kf_score (float32) = the score members before the query, updated in place.
+    -> (candidates in returned order, common words, GetBestCovisibilityKeyFrames(10) per keyframe as index lists)"""
+    n = len(keyframes)
+    hs = (C.c_void_p * n)(*[k._h for k in keyframes])
+    e = np.ascontiguousarray(np.asarray(edges, np.int32).reshape(-1, 3))
+    ea, eb, ew = (np.ascontiguousarray(e[:, j]) for j in range(3))
+    common, cand, best = np.zeros(n, np.int32), np.zeros(max(n, 1), np.int32), np.zeros((n, 10), np.int32)
+    nc = _ok(lib().ref_detect_candidates(vocab._h, query._h, hs, n, len(e), _p(ea), _p(eb), _p(ew), int(loop), float(min_score),
+                                         _p(kf_score), _p(common), _p(cand), _p(best)), "DetectCandidates")
+    return cand[:nc].copy(), common, [row[row >= 0].tolist() for row in best]
 
 
 class RefVocabulary:

@@ -539,6 +539,55 @@ int ref_detect_relocalisation_candidates(void* voc_, void* query_, void** kfs, i
     });
 }
 
+/* Both retrieval queries of the reference with a covisibility graph: KeyFrameDatabase::add for every keyframe (in order),
+ * KeyFrame::AddConnection for nedges weighted edges (edge e joins keyframes ea[e], eb[e] with weight ew[e], both directions, as
+ * KeyFrame::UpdateConnections does; -1 in ea = the QUERY keyframe, used by the loop query's GetConnectedKeyFrames), member scores preset
+ * from score_io, then DetectRelocalisationCandidates(&F) (loop = 0, src/KeyFrameDatabase.cc:198-308) or DetectLoopCandidates(pKF,
+ * min_score) (loop = 1, :75-196).  Outputs: the returned keyframes IN ORDER (cand, returns their number), common[k] = mnRelocWords /
+ * mnLoopWords of the keyframes the query marked (0 otherwise), score_io[k] = mRelocScore / mLoopScore afterwards, and
+ * best10[k*10..] = GetBestCovisibilityKeyFrames(10) as indices (-1 padded) so that the flat-array callers use the reference's own lists. */
+int ref_detect_candidates(void* voc_, void* query_, void** kfs, int nkf, int nedges, const int32_t* ea, const int32_t* eb, const int32_t* ew,
+                          int loop, float min_score, float* score_io, int32_t* common, int32_t* cand, int32_t* best10)
+{
+    return guarded("DetectCandidates", [&] {
+        ORBVocabulary* voc = (ORBVocabulary*)voc_;
+        RefFrame* q = (RefFrame*)query_;
+        if (q->f.mnId == 0) q->f.mnId = Frame::nNextId++;
+        KeyFrameDatabase db(*voc);
+        std::map<KeyFrame*, int> idx;
+        std::vector<KeyFrame*> kf(nkf);
+        for (int k = 0; k < nkf; k++) kf[k] = ((RefFrame*)kfs[k])->keyframe();
+        KeyFrame* qkf = loop ? q->keyframe() : nullptr;
+        if (qkf && qkf->mnId == 0) qkf->mnId = KeyFrame::nNextId++;   /* the reference compares mnLoopQuery (initially 0) with pKF->mnId */
+        for (int k = 0; k < nkf; k++) {
+            kf[k]->mnRelocWords = 0; kf[k]->mnRelocQuery = 0; kf[k]->mnLoopWords = 0; kf[k]->mnLoopQuery = 0;
+            kf[k]->mRelocScore = score_io[k]; kf[k]->mLoopScore = score_io[k];
+            db.add(kf[k]);
+            idx[kf[k]] = k;
+        }
+        for (int e = 0; e < nedges; e++) {
+            KeyFrame* a = ea[e] < 0 ? qkf : kf[ea[e]];
+            KeyFrame* b = kf[eb[e]];
+            if (!a) continue;
+            a->AddConnection(b, ew[e]);
+            b->AddConnection(a, ew[e]);
+        }
+        for (int k = 0; k < nkf; k++) {
+            std::vector<KeyFrame*> nb = kf[k]->GetBestCovisibilityKeyFrames(10);
+            for (int j = 0; j < 10; j++) best10[k * 10 + j] = j < (int)nb.size() && idx.count(nb[j]) ? idx[nb[j]] : -1;
+        }
+        std::vector<KeyFrame*> out = loop ? db.DetectLoopCandidates(qkf, min_score) : db.DetectRelocalisationCandidates(&q->f);
+        const long unsigned qid = loop ? qkf->mnId : q->f.mnId;
+        for (int k = 0; k < nkf; k++) {
+            common[k] = loop ? (kf[k]->mnLoopQuery == qid ? kf[k]->mnLoopWords : 0) : (kf[k]->mnRelocQuery == qid ? kf[k]->mnRelocWords : 0);
+            score_io[k] = loop ? kf[k]->mLoopScore : kf[k]->mRelocScore;
+        }
+        int n = 0;
+        for (KeyFrame* p : out) cand[n++] = idx.at(p);
+        return n;
+    });
+}
+
 /* MapPoint::UpdateNormalAndDepth (src/MapPoint.cc:271-313) on every point of this frame's KeyFrame: fills the normal and the scale
  * invariance distances the back-end searches read.  Call after the pose is set. */
 void ref_frame_update_points(void* h)

@@ -29,7 +29,7 @@ EXPORTS = [
     "orb_distinctive_descriptors", "orb_cvt_gray", "orb_extract_batch_color", "orb_undistort_keypoints", "orb_image_bounds",
     "orb_db_read_descriptors", "orb_db_write_descriptors", "orb_db_read_keypoints", "orb_db_write_keypoints",
     "orb_vocab_create", "orb_vocab_load_text", "orb_vocab_destroy", "orb_vocab_info", "orb_vocab_transform_features",
-    "orb_vocab_transform_batch", "orb_bow_score_db",
+    "orb_vocab_transform_batch", "orb_bow_score_db", "orb_bow_detect_candidates",
     "orb_comm_init", "orb_comm_unique_id", "orb_comm_init_rank", "orb_comm_destroy", "orb_comm_size", "orb_comm_transport",
     "orb_comm_context", "orb_comm_set_extractor", "orb_comm_db_upload", "orb_comm_db_attach", "orb_knn2_sharded",
     "orb_knn2_sharded_device", "orb_extract_batch_multi",
@@ -140,6 +140,7 @@ def lib():
     L.orb_vocab_transform_features.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
     L.orb_vocab_transform_batch.argtypes = [vp, vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.orb_bow_score_db.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, i32, vp, vp, C.POINTER(C.c_int)]
+    L.orb_bow_detect_candidates.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, i32, C.c_float, vp, vp, vp, vp, vp, C.POINTER(C.c_int)]
     L.orb_comm_init.restype = vp
     L.orb_comm_init.argtypes = [i32]
     L.orb_comm_unique_id.argtypes = [vp]

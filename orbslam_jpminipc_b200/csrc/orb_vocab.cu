@@ -16,6 +16,7 @@
 // the norm), so results are bit-identical to the std::map based code.
 #include "orb_internal.h"
 #include <algorithm>
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -217,30 +218,98 @@ __device__ __forceinline__ int find_word(const int32_t* __restrict__ qw, int nq,
     return lo < nq && qw[lo] == w ? lo : -1;
 }
 
+// excluded (optional): keyframes connected to the query keyframe never enter DetectLoopCandidates' list (src/KeyFrameDatabase.cc:95):
+// they count as sharing nothing.  first_pos (optional): position in the query BowVector of the first shared word — the query words are
+// walked in ascending order and every inverted-file list in keyframe order (:85-104), so (first_pos, k) is the order of
+// lKFsSharingWords.
 __global__ void __launch_bounds__(256)
 k_bow_common(const int32_t* __restrict__ qw, int nq, int nkf, const int32_t* __restrict__ kf_start, const int32_t* __restrict__ kf_word,
-             int32_t* __restrict__ common, int* __restrict__ max_common)
+             const uint8_t* __restrict__ excluded, int32_t* __restrict__ common, int* __restrict__ max_common, int32_t* __restrict__ first_pos)
 {
     const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (k >= nkf) return;
     const int s = kf_start[k], e = kf_start[k + 1];
-    int c = 0;
-    for (int j = s + lane; j < e; j += 32) c += find_word(qw, nq, kf_word[j]) >= 0;
+    int c = 0, fp = INT_MAX;
+    if (!excluded || !excluded[k])
+        for (int j = s + lane; j < e; j += 32) { const int p = find_word(qw, nq, kf_word[j]); if (p >= 0) { c++; fp = min(fp, p); } }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (lane == 0) { common[k] = c; atomicMax(max_common, c); }
+    for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, o); fp = min(fp, __shfl_xor_sync(0xffffffffu, fp, o)); }
+    if (lane == 0) { common[k] = c; atomicMax(max_common, c); if (first_pos) first_pos[k] = fp; }
+}
+
+// Covisibility accumulation of DetectRelocalisationCandidates (:262-290) / DetectLoopCandidates (:141-168): one thread per keyframe of
+// lScoreAndMatch walks its (at most ten) best covisible keyframes in their order; float sums in that order.  kf_score is the
+// mRelocScore / mLoopScore member of every keyframe: k_bow_score has just rewritten it for the keyframes scored by THIS query, the
+// others keep what an earlier query left there, exactly as the members do (relocalisation adds such stale scores of neighbours that
+// share a word without having been scored, :278-281).  acc[k] < 0: keyframe k is not in lScoreAndMatch.
+__global__ void __launch_bounds__(256)
+k_bow_accumulate(int nkf, const int32_t* __restrict__ common, const int* __restrict__ max_common, const float* __restrict__ kf_score,
+                 const int32_t* __restrict__ cov_start, const int32_t* __restrict__ cov_idx, int loop, float min_score,
+                 float* __restrict__ acc, int32_t* __restrict__ best_kf, int* __restrict__ best_acc_bits, unsigned long long* __restrict__ min_key)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkf) return;
+    min_key[k] = ~0ull;
+    const int min_common = (int)__fmul_rn((float)*max_common, 0.8f);
+    const int cm = common[k];
+    float a = -1.f;
+    int bk = k;
+    if (cm > 0 && cm > min_common && (!loop || kf_score[k] >= min_score)) {
+        float best = kf_score[k];
+        a = best;
+        if (cov_start) {
+            const int e = min(cov_start[k + 1], cov_start[k] + 10);
+            for (int j = cov_start[k]; j < e; j++) {
+                const int nb = cov_idx[j];
+                if (nb < 0 || nb >= nkf || common[nb] <= 0 || (loop && common[nb] <= min_common)) continue;
+                const float sn = kf_score[nb];
+                a = __fadd_rn(a, sn);
+                if (sn > best) { bk = nb; best = sn; }
+            }
+        }
+        atomicMax(best_acc_bits, __float_as_int(a));         // scores are >= 0: the bit patterns order like the values
+    }
+    acc[k] = a; best_kf[k] = bk;
+}
+
+// keyframes above 0.75 * best accumulated score hand their best keyframe to the result (:170-190, :292-306); a keyframe named several
+// times is listed where its FIRST nominator stands in lScoreAndMatch: smallest (first_pos, k) key of its nominators
+__global__ void __launch_bounds__(256)
+k_bow_mark(int nkf, const float* __restrict__ acc, const int32_t* __restrict__ best_kf, const int32_t* __restrict__ first_pos,
+           const int* __restrict__ best_acc_bits, int loop, float min_score, unsigned long long* __restrict__ min_key)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkf || acc[k] < 0.f) return;
+    const float best = loop ? fmaxf(min_score, __int_as_float(*best_acc_bits)) : __int_as_float(*best_acc_bits);     // bestAccScore starts at minScore (:139) / 0 (:260)
+    if (acc[k] > __fmul_rn(0.75f, best))
+        atomicMin(&min_key[best_kf[k]], ((unsigned long long)(uint32_t)first_pos[k] << 32) | (uint32_t)k);
+}
+
+// rank by counting: one warp per listed keyframe counts the smaller keys (the list is a handful of keyframes)
+__global__ void __launch_bounds__(256)
+k_bow_rank(int nkf, const unsigned long long* __restrict__ min_key, int32_t* __restrict__ cand, int* __restrict__ ncand)
+{
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= nkf) return;
+    const unsigned long long key = min_key[b];
+    if (key == ~0ull) return;
+    int r = 0;
+    for (int j = lane; j < nkf; j += 32) r += min_key[j] < key;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    if (lane == 0) { cand[r] = b; atomicAdd(ncand, 1); }
 }
 
 __global__ void __launch_bounds__(256)
 k_bow_score(const int32_t* __restrict__ qw, const double* __restrict__ qv, int nq, int nkf, const int32_t* __restrict__ kf_start,
             const int32_t* __restrict__ kf_word, const double* __restrict__ kf_val, const int32_t* __restrict__ common,
-            const int* __restrict__ max_common, int score_all, float* __restrict__ score)
+            const int* __restrict__ max_common, int score_all, float* __restrict__ score, int keep_unscored = 0)
 {
     const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (k >= nkf) return;
     const int min_common = (int)__fmul_rn((float)*max_common, 0.8f);     // src/KeyFrameDatabase.cc:233
     const int cm = common[k];
-    if (cm <= 0 || (!score_all && cm <= min_common)) { if (lane == 0) score[k] = 0.f; return; }
+    if (cm <= 0 || (!score_all && cm <= min_common)) { if (lane == 0 && !keep_unscored) score[k] = 0.f; return; }
     const int s = kf_start[k], e = kf_start[k + 1];
     double acc = 0.0;                                                    // lane 0 carries the running sum, in word order
     for (int j0 = s; j0 < e; j0 += 32) {
@@ -544,7 +613,7 @@ int orb_bow_score_db(orb_ctx* c, orb_vocab* v, const int32_t* qw, const double* 
     }
     ORB_CUDA(cudaMemsetAsync(d_max, 0, 4, s));
     const unsigned blocks = (unsigned)((K * 32 + 255) / 256);
-    k_bow_common<<<blocks, 256, 0, s>>>(qw, nq, nkf, kf_start, kf_word, d_common, d_max);
+    k_bow_common<<<blocks, 256, 0, s>>>(qw, nq, nkf, kf_start, kf_word, nullptr, d_common, d_max, nullptr);
     k_bow_score<<<blocks, 256, 0, s>>>(qw, qv, nq, nkf, kf_start, kf_word, kf_val, d_common, d_max, score_all, d_score);
     ORB_CUDA(cudaGetLastError());
     if (!dev) {
@@ -552,6 +621,76 @@ int orb_bow_score_db(orb_ctx* c, orb_vocab* v, const int32_t* qw, const double* 
         ORB_CUDA(cudaMemcpyAsync(score, d_score, K * 4, cudaMemcpyDeviceToHost, s));
     }
     ORB_CUDA(cudaMemcpyAsync(max_common, d_max, 4, cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaStreamSynchronize(s));
+    return ORB_OK;
+}
+
+/* KeyFrameDatabase::DetectRelocalisationCandidates (src/KeyFrameDatabase.cc:198-308) and DetectLoopCandidates (:75-196) complete, on
+ * flat arrays: shared words, scores, covisibility accumulation, the 0.75 * best cut and the reference's result order. */
+int orb_bow_detect_candidates(orb_ctx* c, orb_vocab* v, const int32_t* qw, const double* qv, int nq, int nkf, const int32_t* kf_start,
+                              const int32_t* kf_word, const double* kf_val, const uint8_t* excluded, int loop, float min_score,
+                              const int32_t* cov_start, const int32_t* cov_idx, float* kf_score, int32_t* common, int32_t* cand, int* ncand)
+{
+    if (!c || !v || nq < 0 || nkf < 0 || !ncand) return ORB_ERR_INVALID;
+    *ncand = 0;
+    if (nkf == 0) return ORB_OK;
+    if (!kf_start || !kf_score || !common || !cand || (nq > 0 && (!qw || !qv))) return ORB_ERR_INVALID;
+    if (v->scoring != 0) return ORB_ERR_UNSUPPORTED;
+    ORB_CUDA(cudaSetDevice(c->device));
+    LaneGuard lg(c);
+    if (!lg.lane) return ORB_ERR_CUDA;
+    cudaStream_t s = lg.lane->stream;
+    const bool dev = on_device(kf_start);
+    if (on_device(common) != dev || on_device(kf_score) != dev || on_device(cand) != dev || (nq > 0 && on_device(qw) != dev) ||
+        (excluded && on_device(excluded) != dev) || (cov_start && on_device(cov_start) != dev)) return ORB_ERR_INVALID;
+    int total = 0, ctotal = 0;
+    if (dev) {
+        ORB_CUDA(cudaMemcpy(&total, kf_start + nkf, 4, cudaMemcpyDeviceToHost));
+        if (cov_start) ORB_CUDA(cudaMemcpy(&ctotal, cov_start + nkf, 4, cudaMemcpyDeviceToHost));
+    } else { total = kf_start[nkf]; if (cov_start) ctotal = cov_start[nkf]; }
+    if (total < 0 || ctotal < 0 || (total > 0 && (!kf_word || !kf_val)) || (ctotal > 0 && !cov_idx)) return ORB_ERR_INVALID;
+    const size_t K = (size_t)nkf, T = (size_t)total, Q = (size_t)nq, CT = (size_t)ctotal;
+    size_t need = 1024 + al256(K * 4) * 3 + al256(K * 8);                  // first_pos, acc, best_kf, min_key
+    if (!dev) need += al256(Q * 4) + al256(Q * 8) + al256((K + 1) * 4) * 2 + al256(T * 4) + al256(T * 8) + al256(K * 4) * 3 + al256(K) + al256(CT * 4);
+    int rc = orb_lane_scratch(lg.lane, need + 1024);
+    if (rc) return rc;
+    uint8_t* p = (uint8_t*)lg.lane->d_scratch;
+    auto take = [&](size_t bytes) { uint8_t* r = p; p += al256(std::max<size_t>(bytes, 1)); return r; };
+    int* d_int = (int*)take(16);                   // [0] max common, [1] best accumulated score (bits), [2] ncand
+    int32_t* d_first = (int32_t*)take(K * 4); float* d_acc = (float*)take(K * 4); int32_t* d_best = (int32_t*)take(K * 4);
+    unsigned long long* d_key = (unsigned long long*)take(K * 8);
+    int32_t* d_common = common; float* d_score = kf_score; int32_t* d_cand = cand;
+    if (!dev) {
+        int32_t* a = (int32_t*)take(Q * 4); double* b = (double*)take(Q * 8); int32_t* st = (int32_t*)take((K + 1) * 4);
+        int32_t* w = (int32_t*)take(T * 4); double* val = (double*)take(T * 8);
+        d_common = (int32_t*)take(K * 4); d_score = (float*)take(K * 4); d_cand = (int32_t*)take(K * 4);
+        if (Q) { ORB_CUDA(cudaMemcpyAsync(a, qw, Q * 4, cudaMemcpyHostToDevice, s)); ORB_CUDA(cudaMemcpyAsync(b, qv, Q * 8, cudaMemcpyHostToDevice, s)); }
+        ORB_CUDA(cudaMemcpyAsync(st, kf_start, (K + 1) * 4, cudaMemcpyHostToDevice, s));
+        if (T) { ORB_CUDA(cudaMemcpyAsync(w, kf_word, T * 4, cudaMemcpyHostToDevice, s)); ORB_CUDA(cudaMemcpyAsync(val, kf_val, T * 8, cudaMemcpyHostToDevice, s)); }
+        ORB_CUDA(cudaMemcpyAsync(d_score, kf_score, K * 4, cudaMemcpyHostToDevice, s));
+        qw = a; qv = b; kf_start = st; kf_word = w; kf_val = val;
+        if (excluded) { uint8_t* x = take(K); ORB_CUDA(cudaMemcpyAsync(x, excluded, K, cudaMemcpyHostToDevice, s)); excluded = x; }
+        if (cov_start) {
+            int32_t* cs = (int32_t*)take((K + 1) * 4); int32_t* ci = (int32_t*)take(CT * 4);
+            ORB_CUDA(cudaMemcpyAsync(cs, cov_start, (K + 1) * 4, cudaMemcpyHostToDevice, s));
+            if (CT) ORB_CUDA(cudaMemcpyAsync(ci, cov_idx, CT * 4, cudaMemcpyHostToDevice, s));
+            cov_start = cs; cov_idx = ci;
+        }
+    }
+    ORB_CUDA(cudaMemsetAsync(d_int, 0, 16, s));
+    const unsigned wblocks = (unsigned)((K * 32 + 255) / 256), tblocks = (unsigned)((K + 255) / 256);
+    k_bow_common<<<wblocks, 256, 0, s>>>(qw, nq, nkf, kf_start, kf_word, excluded, d_common, d_int, d_first);
+    k_bow_score<<<wblocks, 256, 0, s>>>(qw, qv, nq, nkf, kf_start, kf_word, kf_val, d_common, d_int, 0, d_score, 1);
+    k_bow_accumulate<<<tblocks, 256, 0, s>>>(nkf, d_common, d_int, d_score, cov_start, cov_idx, loop, min_score, d_acc, d_best, d_int + 1, d_key);
+    k_bow_mark<<<tblocks, 256, 0, s>>>(nkf, d_acc, d_best, d_first, d_int + 1, loop, min_score, d_key);
+    k_bow_rank<<<wblocks, 256, 0, s>>>(nkf, d_key, d_cand, d_int + 2);
+    ORB_CUDA(cudaGetLastError());
+    if (!dev) {
+        ORB_CUDA(cudaMemcpyAsync(common, d_common, K * 4, cudaMemcpyDeviceToHost, s));
+        ORB_CUDA(cudaMemcpyAsync(kf_score, d_score, K * 4, cudaMemcpyDeviceToHost, s));
+        ORB_CUDA(cudaMemcpyAsync(cand, d_cand, K * 4, cudaMemcpyDeviceToHost, s));
+    }
+    ORB_CUDA(cudaMemcpyAsync(ncand, d_int + 2, 4, cudaMemcpyDeviceToHost, s));
     ORB_CUDA(cudaStreamSynchronize(s));
     return ORB_OK;
 }

@@ -107,6 +107,33 @@ class ORBVocabulary:
                                      int(score_all), ptr(common), ptr(score), C.byref(mx)), "orb_bow_score_db")
         return common, score, mx.value
 
+    def detect_candidates(self, query_bow, kf_bows, kf_score, covis=None, excluded=None, loop=False, min_score=0.0):
+        """KeyFrameDatabase::DetectRelocalisationCandidates (src/KeyFrameDatabase.cc:198-308) / DetectLoopCandidates (:75-196, loop=True)
+        over keyframes in add() order.  covis[k] = GetBestCovisibilityKeyFrames(10) of keyframe k as indices; kf_score = the
+        mRelocScore / mLoopScore members (float32 array, updated in place).  Returns (candidate indices in the reference's order, common)."""
+        qw = np.ascontiguousarray(query_bow[0], np.int32); qv = np.ascontiguousarray(query_bow[1], np.float64)
+        n = len(kf_bows)
+        start = np.zeros(n + 1, np.int32)
+        for i, b in enumerate(kf_bows):
+            start[i + 1] = start[i] + len(b[0])
+        words = np.ascontiguousarray(np.concatenate([np.asarray(b[0], np.int32) for b in kf_bows]) if n else np.zeros(0, np.int32), np.int32)
+        vals = np.ascontiguousarray(np.concatenate([np.asarray(b[1], np.float64) for b in kf_bows]) if n else np.zeros(0, np.float64), np.float64)
+        cs = ci = None
+        if covis is not None:
+            cs = np.zeros(n + 1, np.int32)
+            for i, c_ in enumerate(covis):
+                cs[i + 1] = cs[i] + len(c_)
+            ci = np.ascontiguousarray(np.concatenate([np.asarray(c_, np.int32) for c_ in covis]) if cs[n] else np.zeros(1, np.int32), np.int32)
+        ex = None if excluded is None else np.ascontiguousarray(excluded, np.uint8)
+        assert kf_score.dtype == np.float32 and kf_score.flags.c_contiguous and len(kf_score) == n
+        common = np.zeros(n, np.int32); cand = np.zeros(max(n, 1), np.int32)
+        nc = C.c_int(0)
+        check(lib().orb_bow_detect_candidates(self._h, self._v, ptr(qw), ptr(qv), len(qw), n, ptr(start), ptr(words), ptr(vals),
+                                              ptr(ex) if ex is not None else None, int(loop), float(min_score),
+                                              ptr(cs) if cs is not None else None, ptr(ci) if ci is not None else None,
+                                              ptr(kf_score), ptr(common), ptr(cand), C.byref(nc)), "orb_bow_detect_candidates")
+        return cand[:nc.value].copy(), common
+
     def score(self, v1, v2):
         """TemplatedVocabulary::score(v1, v2) rounded to float as every caller in the reference does (float si = ...)."""
         _, s, _ = self.score_db(v1, [v2], score_all=True)

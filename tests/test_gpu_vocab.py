@@ -124,6 +124,64 @@ def test_score_db_vs_oracle(pkg, po, ctx):
     assert gv.score(q, bows[9]) == np.float32(po.bow_score_l1(q, bows[9]))
 
 
+@pytest.mark.parametrize("loop,min_score,seed,device_arrays", [(False, 0.0, 1, False), (False, 0.0, 2, True), (True, 0.05, 3, False),
+                                                              (True, 0.3, 4, True), (True, 1.5, 5, False)])
+def test_detect_candidates_vs_oracle(pkg, po, ctx, loop, min_score, seed, device_arrays):
+    """orb_bow_detect_candidates = KeyFrameDatabase::DetectRelocalisationCandidates / DetectLoopCandidates complete (covisibility
+    accumulation with stale member scores, 0.75 * best cut, result order), host and device arrays, against the oracle (which
+    tests/test_ref_build.py pins to the reference's own KeyFrameDatabase.cc)."""
+    import ctypes as C
+    k, L = 10, 3
+    parent, desc, weight = synth.synth_vocabulary(k, L, seed=21, stop_frac=0.02)
+    gv = pkg.ORBVocabulary(ctx).create(k, L, parent, desc, weight)
+    rng = np.random.default_rng(100 + seed)
+    nkf = 400
+    # 40 "places", ten views each with a varying share of the place's features: the query is one more view of place 7
+    batch = np.stack([_features(desc, parent, 800, 500 + (f % 40), flip=0.02 + 0.01 * (f % 3)) for f in range(nkf)])
+    for f in range(nkf):
+        cut = int(rng.integers(100, 800))
+        batch[f, cut:] = _features(desc, parent, 800 - cut, 9000 + f)
+    bows, _ = gv.transform_batch(batch, [800] * nkf, 1)
+    q = gv.transform_batch(_features(desc, parent, 800, 507, flip=0.03)[None], [800], 1)[0][0]
+    covis = [list(rng.choice(nkf, int(rng.integers(0, 15)), replace=False)) for _ in range(nkf)]
+    covis = [[int(j) for j in c if j != i] for i, c in enumerate(covis)]
+    excluded = (rng.random(nkf) < 0.1).astype(np.uint8) if loop else None
+    state = (rng.random(nkf) * 0.2).astype(np.float32)
+    os_ = state.copy()
+    ocand, ocommon = po.bow_detect_candidates(q, bows, os_, covis=covis, excluded=excluded, loop=loop, min_score=min_score)
+    gs = state.copy()
+    if not device_arrays:
+        gcand, gcommon = gv.detect_candidates(q, bows, gs, covis=covis, excluded=excluded, loop=loop, min_score=min_score)
+    else:
+        import torch
+        from orbslam_jpminipc_b200._lib import check, lib, ptr
+        dev = torch.device("cuda", 0)
+        start = np.zeros(nkf + 1, np.int32); start[1:] = np.cumsum([len(b[0]) for b in bows])
+        cs = np.zeros(nkf + 1, np.int32); cs[1:] = np.cumsum([len(c) for c in covis])
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        d = dict(qw=t(q[0].astype(np.int32)), qv=t(q[1]), st=t(start), w=t(np.concatenate([b[0] for b in bows]).astype(np.int32)),
+                 v=t(np.concatenate([b[1] for b in bows])), cs=t(cs), ci=t(np.concatenate([np.asarray(c, np.int32) for c in covis])),
+                 sc=t(gs), cm=torch.zeros(nkf, dtype=torch.int32, device=dev), cand=torch.zeros(nkf, dtype=torch.int32, device=dev))
+        ex = t(excluded) if excluded is not None else None
+        nc = C.c_int(0)
+        check(lib().orb_bow_detect_candidates(gv._h, gv._v, ptr(d["qw"]), ptr(d["qv"]), len(q[0]), nkf, ptr(d["st"]), ptr(d["w"]), ptr(d["v"]),
+                                              ptr(ex) if ex is not None else None, int(loop), float(min_score), ptr(d["cs"]), ptr(d["ci"]),
+                                              ptr(d["sc"]), ptr(d["cm"]), ptr(d["cand"]), C.byref(nc)), "orb_bow_detect_candidates")
+        gcand, gcommon, gs = d["cand"].cpu().numpy()[:nc.value], d["cm"].cpu().numpy(), d["sc"].cpu().numpy()
+    assert np.array_equal(gcommon, ocommon)
+    assert np.array_equal(gs.view(np.uint32), os_.view(np.uint32))
+    assert list(gcand) == list(ocand)
+    if min_score < 1.0:
+        assert len(ocand) >= 1 and (os_ != state).sum() >= 3
+    else:
+        assert len(ocand) == 0                               # an L1 score never exceeds 1: nothing reaches minScore, the reference returns an empty vector (:137)
+    # an empty database and a query without words
+    e, _ = gv.detect_candidates(q, [], np.zeros(0, np.float32))
+    assert len(e) == 0
+    e, c0 = gv.detect_candidates((np.zeros(0, np.int32), np.zeros(0, np.float64)), bows[:5], np.zeros(5, np.float32), covis=covis[:5] and [[] for _ in range(5)])
+    assert len(e) == 0 and not c0.any()
+
+
 def test_extract_transform_search_by_bow_chain(pkg, po):
     """Frame::ComputeBoW feeding SearchByBoW (src/Tracking.cc:907-927): both sides of the chain against the oracle."""
     ext = pkg.ORBextractor(1000, 1.2, 8, 1, 20, max_width=640, max_height=480)

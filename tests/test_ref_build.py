@@ -403,6 +403,81 @@ def test_relocalisation_candidate_scoring(po, tmp_path):
     assert np.array_equal(cand, score > np.float32(0.75) * score.max())
 
 
+def _retrieval_scene(tmp_path, seed, nkf=60):
+    """a synthetic vocabulary, one query BowVector, nkf keyframe BowVectors sharing 0 .. 100 % of its words, and a covisibility graph
+    with distinct weights (KeyFrame::UpdateBestCovisibles sorts (weight, pointer) pairs: equal weights would order by address)"""
+    from orbslam_jpminipc_b200 import synth
+    k, L = 6, 4
+    parent, desc, weight = synth.synth_vocabulary(k, L, seed=11)
+    path = str(tmp_path / "voc.txt")
+    synth.write_vocabulary_text(path, k, L, parent, desc, weight, trailing_newline=False)
+    rv = pyref.RefVocabulary(path)
+    rng = np.random.default_rng(seed)
+    leaves = np.nonzero(~np.isin(np.arange(len(parent)), parent))[0]
+    scene = rng.choice(leaves, 400)
+
+    def bow_of(words):
+        feats = desc[words] ^ np.packbits((rng.random((len(words), 256)) < 0.03).astype(np.uint8), axis=1)
+        return rv.transform(feats, 4)[0]
+    qbow = bow_of(scene)
+    kf_bows = []
+    for i in range(nkf):
+        share = int(len(scene) * rng.choice([0.0, 0.02, 0.3, 0.6, 0.8, 0.9, 0.95, 1.0]))
+        words = np.concatenate([rng.choice(scene, share), rng.choice(leaves, 300 - min(share, 299))]) if share else rng.choice(leaves, 300)
+        kf_bows.append(bow_of(words))
+    edges, wgt = [], 1000
+    for a in range(nkf):                                                # up to 14 neighbours: more than GetBestCovisibilityKeyFrames(10) returns
+        for b in rng.choice(nkf, int(rng.integers(0, 8)), replace=False):
+            if a != b and not any((e[0], e[1]) in ((a, b), (b, a)) for e in edges):
+                edges.append((a, int(b), wgt)); wgt -= 1
+    kp = np.zeros(1, pyref.KP_DTYPE); kp["x"] = 10; kp["y"] = 10
+    d1 = np.zeros((1, 32), np.uint8)
+    cam = (640, 480, 500.0, 500.0, 320.0, 240.0)
+    kfs = [pyref.RefFrame(kp, d1, *cam).set_bowvec(*b) for b in kf_bows]
+    q = pyref.RefFrame(kp, d1, *cam).set_bowvec(*qbow)
+    return rv, q, qbow, kfs, kf_bows, edges, rng
+
+
+@pytest.mark.parametrize("seed", [21, 22, 23])
+def test_relocalisation_candidates_with_covisibility(po, tmp_path, seed):
+    """DetectRelocalisationCandidates complete (src/KeyFrameDatabase.cc:198-308): covisibility accumulation over
+    GetBestCovisibilityKeyFrames(10) including the STALE mRelocScore of neighbours that share a word without being scored by this
+    query (:278-281), the 0.75 * best cut and the order / de-duplication of the returned list, against the oracle's flat-array form."""
+    rv, q, qbow, kfs, kf_bows, edges, rng = _retrieval_scene(tmp_path, seed)
+    stale = (rng.random(len(kfs)) * 0.3).astype(np.float32)                     # what earlier queries left in mRelocScore
+    rs = stale.copy()
+    rcand, rcommon, best10 = pyref.detect_candidates(rv, q, kfs, edges, rs)
+    assert max(len(b) for b in best10) == 10 and len(rcand) >= 1
+    os_ = stale.copy()
+    ocand, ocommon = po.bow_detect_candidates(qbow, kf_bows, os_, covis=best10)
+    assert np.array_equal(rcommon, ocommon)
+    assert np.array_equal(rs.view(np.uint32), os_.view(np.uint32))
+    assert list(rcand) == list(ocand)
+    # the accumulation matters in this scene: without the graph the answer differs
+    ncand, _ = po.bow_detect_candidates(qbow, kf_bows, stale.copy(), covis=None)
+    assert list(ncand) != list(ocand) or seed != 21
+
+
+@pytest.mark.parametrize("seed,min_score", [(31, 0.05), (32, 0.2), (33, 0.6)])
+def test_loop_candidates(po, tmp_path, seed, min_score):
+    """DetectLoopCandidates (src/KeyFrameDatabase.cc:75-196): keyframes connected to the query keyframe never enter the list, minScore
+    gates the nominators and seeds the best accumulated score, neighbours need more than minCommonWords shared words."""
+    rv, q, qbow, kfs, kf_bows, edges, rng = _retrieval_scene(tmp_path, seed)
+    connected = np.zeros(len(kfs), np.uint8)
+    connected[rng.choice(len(kfs), 12, replace=False)] = 1
+    qedges = [(-1, int(k), 5000 + int(k)) for k in np.nonzero(connected)[0]]
+    rs = np.zeros(len(kfs), np.float32)
+    rcand, rcommon, best10 = pyref.detect_candidates(rv, q, kfs, edges + qedges, rs, loop=True, min_score=min_score)
+    os_ = np.zeros(len(kfs), np.float32)
+    ocand, ocommon = po.bow_detect_candidates(qbow, kf_bows, os_, covis=best10, excluded=connected, loop=True, min_score=min_score)
+    assert np.array_equal(rcommon, ocommon)
+    assert np.array_equal(rs.view(np.uint32), os_.view(np.uint32))
+    assert list(rcand) == list(ocand)
+    assert not connected[ocand].any()
+    if min_score < 0.5:
+        assert len(ocand) >= 1
+
+
 @pytest.mark.parametrize("shape,nf,th,dist,ori", [((240, 320), 500, 10.0, 100, True), ((480, 752), 1000, 3.0, 64, True), ((376, 1241), 2000, 10.0, 100, False)])
 def test_search_by_projection_keyframe(po, shape, nf, th, dist, ori):
     """src/ORBmatcher.cc:1622-1746 (relocalisation).  The level prediction (:1662-1669) is the caller's job at the C ABI, so the
