@@ -135,6 +135,37 @@ def test_batch_equals_single_and_chunks(pkg, po):
     ex.close()
 
 
+def test_full_machine_batch_is_deterministic_and_exact(pkg, po):
+    """A batch large enough to keep every SM's resident CTAs busy for many work items (k_fast_nms re-uses ONE raw TMA buffer per CTA,
+    k_resize_u / k_blur two, all three draw items from atomic queues): sampled frames equal the oracle and ten repeats of the launch
+    give identical bytes, dense, sparse and flat frames mixed so that item costs differ widely."""
+    from orbslam_jpminipc_b200.synth import synth_frame
+    h, w, n = 480, 640, 192
+    rng = np.random.default_rng(77)
+    frames = []
+    for i in range(n):
+        kind = i % 4
+        if kind == 0: f = synth_frame(h, w, 6000 + i)
+        elif kind == 1: f = synth_frame(h, w, 6000 + i, quadrants=False)
+        elif kind == 2: f = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        else:
+            f = np.full((h, w), 90, np.uint8)
+            f[100:380, 150:500] = synth_frame(280, 350, 6000 + i)            # texture island in a flat frame: most tiles reject early
+        frames.append(f)
+    frames = np.stack(frames)
+    ex = pkg.ORBextractor(1000, 1.2, 8, 1, 20, max_width=w, max_height=h, max_batch=n)
+    orc = po.OracleExtractor(1000, 1.2, 8, 1, 20)
+    first = ex.extract_batch(frames)
+    for i in (0, 1, 2, 3, 95, 126, 190, 191):
+        rk, rd = orc(frames[i])
+        _same(first[i][0], first[i][1], rk, rd, ("full-machine batch", i))
+    for rep in range(10):
+        again = ex.extract_batch(frames)
+        for i in range(n):
+            assert np.array_equal(again[i][0].view(np.uint8), first[i][0].view(np.uint8)) and np.array_equal(again[i][1], first[i][1]), (rep, i)
+    ex.close()
+
+
 def test_other_parameters(pkg, po):
     from orbslam_jpminipc_b200.synth import synth_frame
     img = synth_frame(360, 480, 5000)
