@@ -223,7 +223,7 @@ orb_ctx* orb_create(int device, int nfeatures, float scale_factor, int nlevels, 
         cudaGetLastError();
         return nullptr;
     }
-    if ((score_type != ORB_FAST_SCORE && score_type != ORB_HARRIS_SCORE) || max_w < 1 || max_h < 1 || max_batch < 1 || fast_th < 1 || fast_th > 254) {
+    if ((score_type != ORB_FAST_SCORE && score_type != ORB_HARRIS_SCORE) || max_w < 1 || max_h < 1 || max_batch < 1 || fast_th < 0 || fast_th > 254) {     // fastTh 0 is valid for cv::FAST (k_fast_nms: a corner of strength 1 behaves like none)
         g_last_cuda_error = "orb_create: invalid argument";
         return nullptr;
     }

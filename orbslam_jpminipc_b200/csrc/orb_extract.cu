@@ -532,10 +532,11 @@ k_border(uint8_t* __restrict__ planes, uint8_t* __restrict__ blurred, size_t fby
     if (first >= L.border_items) return;
     const int w = L.w, h = L.h;
     const int wpr = L.stride >> 2;                      // words per padded row
-    const int band = ORB_RING * wpr;                    // words in the top (or bottom) band: ORB_RING rows next to the ROI
+    const int RING = L.ring;                            // ORB_RING, or the whole 16 px frame for a level whose cells reach past size - 16
+    const int band = RING * wpr;                        // words in the top (or bottom) band: RING rows next to the ROI
     const int rw0 = (ORB_EDGE + w) >> 2;                // first word that contains right-frame pixels
-    constexpr int LW = ORB_RING / 4;                    // words of the left ring
-    constexpr int side = LW + 2;                        // ring words per middle row: left ring + the two words covering [w, w + ORB_RING)
+    const int LW = RING >> 2;                           // words of the left ring
+    const int side = 2 * LW + 1;                        // ring words per middle row: left ring + the words covering [w, w + RING)
     const size_t poff = (size_t)f * fbytes + L.plane_off;
     auto fetch = [&](int item, size_t& o) -> uint32_t {
     int py, wx;
@@ -544,13 +545,13 @@ k_border(uint8_t* __restrict__ planes, uint8_t* __restrict__ blurred, size_t fby
         if (bi) item -= band;
         py = __float2int_rz(__fdividef((float)item + 0.5f, (float)wpr));
         wx = item - py * wpr;
-        py += bi ? ORB_EDGE + h : ORB_EDGE - ORB_RING;
+        py += bi ? ORB_EDGE + h : ORB_EDGE - RING;
     } else {
         item -= 2 * band;
         py = item / side;
         wx = item - py * side;
         py += ORB_EDGE;
-        wx = wx < LW ? (ORB_EDGE - ORB_RING) / 4 + wx : rw0 + (wx - LW);
+        wx = wx < LW ? (ORB_EDGE - RING) / 4 + wx : rw0 + (wx - LW);
         if (wx >= wpr) wx = wpr - 1;                    // a ROI that ends on the last word of the pitch: rewrite that word
     }
     int sy = py - ORB_EDGE;
@@ -819,7 +820,7 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
         // tasks are numbered over the filled part only, so that a narrow tile takes fewer rounds instead of idle lanes.
         // vw x vh = detection pixels of the tile; the NMS walks nq 16-pixel groups per row and reads one score word more on
         // either side, one row more above and below.  Score words outside [nr) x [nw) keep stale values and are never read.
-        const int vw = min(FT_W, L.w - ORB_EDGE - t.x0), vh = min(FT_H, L.h - ORB_EDGE - t.y0);
+        const int vw = min(FT_W, L.xend - t.x0), vh = min(FT_H, L.yend - t.y0);       // xend / yend: size - 16, or further where an inner cell of a degenerate grid reaches past it
         const int nq = (vw + 15) >> 4, nwi = 4 * nq, nr = min(FS_H, vh + 2);
         const uint32_t inv_nq = ((1u << 20) + nq - 1) / nq;   // floor(task / nq) = task * inv >> 20, exact for task < 4000, nq <= 66
 
@@ -1894,7 +1895,9 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
                                                bufb, nimg, W.d_counters + 4 + l, tw, rr);
         launches++;
     }
-    k_border<<<dim3((P.L[0].border_items + 511) / 512, nimg * P.nlevels), 256, 0, s>>>(W.d_planes, W.d_blur, fb, c->d_plan);
+    int border_max = 1;                 // a small level with the whole 16 px frame may hold more ring words than level 0 with its 4 px ring
+    for (int l = 0; l < P.nlevels; l++) border_max = std::max(border_max, P.L[l].border_items);
+    k_border<<<dim3((border_max + 511) / 512, nimg * P.nlevels), 256, 0, s>>>(W.d_planes, W.d_blur, fb, c->d_plan);
     launches++;
     // k_blur only needs the finished pyramid: outside profiling mode it runs on a second stream,
     // concurrently with FAST -> compaction -> selection (the selection kernel is latency bound and

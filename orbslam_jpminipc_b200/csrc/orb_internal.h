@@ -11,7 +11,7 @@
 
 #define ORB_MAX_LEVELS 16
 #define ORB_MAX_GRID 96            // max grid cols / rows per level
-#define ORB_MAX_CELLS_LEVEL 256    // one select-CTA thread per cell
+#define ORB_MAX_CELLS_LEVEL 1024   // cells of one level's grid (~5000 features on ONE level; 1000..2000 features over 8 levels need 45..90): shared arrays of the selection kernels
 #define ORB_EDGE 16                // EDGE_THRESHOLD, reference src/ORBextractor.cc:77
 // Width of the reflect-101 ring k_border actually writes around every level ROI.  The reference materialises all 16 pixels
 // (copyMakeBorder, :806,:814) but nothing on the path reads further out than 3: FAST, IC_Angle and HarrisResponses stay inside the ROI
@@ -52,6 +52,7 @@ struct LevelGeom {
     int ct_off, ct_len;    // k_fast_nms column masks: byte offset of this level's three arrays (in-region, left / right neighbour in the
                            // same cell; entry x + 4 for ROI column x) in the mask table, bytes per array (multiple of 4)
     int rt_off;            // k_fast_nms detection-cell row of ROI row y at rt_off + y + 1 of the row table (int16, -1 = outside)
+    int ring;              // width of the reflect-101 ring k_border writes around the ROI: ORB_RING, or ORB_EDGE when a detection cell reaches past [16, size - 16)
     int bm_off, bm_pitch;  // NMS-survivor bitmap of this level: byte offset in the frame's bitmap block, row pitch in bytes (bit i = ROI x 16+i)
 };
 

@@ -161,8 +161,7 @@ int orb_build_plan(orb_ctx* c, int w, int h)
         L.border_base = border;
         // k_border work items (32-bit words): ORB_RING full rows above and below the ROI, and per ROI row the word left of it plus
         // the two words that cover [w, w + ORB_RING) on the right
-        L.border_items = 2 * ORB_RING * (L.stride / 4) + L.h * (ORB_RING / 4 + 2);
-        border += L.border_items;
+        L.ring = ORB_RING; L.border_items = 0;       // set below, once the cell grid is known
         // cell grid (:531-547)
         L.nDesired = c->mnFeaturesPerLevel[l];
         L.cols = (int)sqrtf((float)L.nDesired / (5 * imageRatio));
@@ -188,12 +187,15 @@ int orb_build_plan(orb_ctx* c, int w, int h)
                 CellGeom g;
                 g.level = l; g.idx = i * L.cols + j;
                 g.inix = iniX; g.iniy = iniY; g.pad = 0;
-                g.skipped = (hX <= 0 || hY <= 0) ? 1 : 0;
-                if (hX <= 0 || hY <= 0) {                  // skipped cell (:570,:594): never produces keypoints
+                // only the LAST row / column is tested for an empty remainder and skipped (:570,:594); an inner cell of a level smaller
+                // than its margins (cellW or cellH <= -6) reaches Mat::rowRange / colRange with end < start, which throws like a
+                // cell that leaves the ROI does
+                const bool skip = (i == L.rows - 1 && hY <= 0) || (j == L.cols - 1 && hX <= 0);
+                g.skipped = skip ? 1 : 0;
+                if (skip) {                                // never produces keypoints and stays out of the quota loop's first pass
                     g.x0 = g.x1 = g.y0 = g.y1 = 0;
                 } else {
-                    // Mat::rowRange/colRange on the level ROI throws when the cell leaves it
-                    if (iniX < 0 || iniY < 0 || iniX + hX > L.w || iniY + hY > L.h) return ORB_ERR_GEOMETRY;
+                    if (hX < 0 || hY < 0 || iniX < 0 || iniY < 0 || iniX + hX > L.w || iniY + hY > L.h) return ORB_ERR_GEOMETRY;
                     g.x0 = iniX + 3; g.x1 = iniX + hX - 3; g.y0 = iniY + 3; g.y1 = iniY + hY - 3;
                     if (g.x1 < g.x0) g.x1 = g.x0;          // cell image narrower than 7 px: FAST finds nothing
                     if (g.y1 < g.y0) g.y1 = g.y0;
@@ -206,11 +208,27 @@ int orb_build_plan(orb_ctx* c, int w, int h)
                 c->cells.push_back(g);
             }
         }
+        // Degenerate grids (many features on a small level): cellW = ceil(W / cols), so the inner cells may reach up to cols - 1
+        // pixels past size - 16 — the reference detects there (:560-572,:591-596), and a keypoint closer than 16 px to the ROI edge
+        // makes IC_Angle and the descriptor pattern read up to 15 px of the reflect-101 frame instead of 3: such a level gets the
+        // reference's whole 16 px frame.
+        if (L.xend > maxBX || L.yend > maxBY) L.ring = ORB_EDGE;
+        L.border_items = 2 * L.ring * (L.stride / 4) + L.h * (L.ring / 2 + 1);   // ring rows above / below; per ROI row ring/4 words left, ring/4 + 1 right
+        border += L.border_items;
         L.bm_pitch = ((std::max(L.xend - ORB_EDGE, 0) + ORB_TILE_W - 1) / ORB_TILE_W) * (ORB_TILE_W / 8);   // whole FAST tiles
         L.bm_off = bm;
         bm += ((L.bm_pitch * std::max(((L.yend - ORB_EDGE + ORB_TILE_H - 1) / ORB_TILE_H) * ORB_TILE_H, 0) + 255) & ~255);
         L.lvl_base = lvl;
-        L.lvl_cap = L.nDesired + L.ncells + (L.ncells * L.ncells) / 2 + 64;
+        // Longest list the quota loop (src/ORBextractor.cc:622-670) can leave before the level's retainBest: ncells * nfCell + ncells.
+        // Proof: when an iteration starts with m open cells and deficit D, (retained by closed cells) + D <= (N - m) * (nfCell + 1)
+        // by induction (a cell that closes at quota nNew = nfCell + ceil(D / m) contributes its keys plus its own deficit = nNew, and
+        // the ceilings add at most one per closed cell); the open cells then receive m * nNew <= m * nfCell + D + m.  The quotas of
+        // cells that stay open are REPLACED, not accumulated, by the next iteration.  (Round 1 used ncells^2 / 2 for the ceilings,
+        // which refused e.g. 1092 features on one 298x495 level: 209 cells -> 23 K records > the selection kernel's shared memory.)
+        // tests/test_kernel_arith_models.py::test_quota_loop_bound checks the bound on adversarial key counts; the kernels still
+        // verify it at run time (status ORB_ERR_CAPACITY instead of an overrun).
+        L.lvl_cap = L.ncells * L.nfCell + L.ncells + 64;
+        if (L.lvl_cap < L.nDesired + 64) L.lvl_cap = L.nDesired + 64;
         lvl += L.lvl_cap;
         L.kp_base = kp;
         kp += L.nDesired;

@@ -178,6 +178,65 @@ def test_other_parameters(pkg, po):
         ex.close()
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_random_shapes_and_parameters(pkg, po, seed):
+    """Seeded sweep over image shapes, feature counts, scale factors, level counts and thresholds (six per seed): tile residues of every
+    kind at every level for k_resize_u (packed taps, role-swapping row sets), k_fast_nms<true> (112-row tiles, half-lane tile) and
+    k_blur; where the reference itself throws on a geometry, product and oracle must agree on that."""
+    from orbslam_jpminipc_b200.synth import synth_frame
+    rng = np.random.default_rng(9000 + seed)
+    for _ in range(6):
+        h, w = int(rng.integers(120, 700)), int(rng.integers(160, 900))
+        nf = int(rng.integers(100, 1500))
+        sf = float(rng.choice([1.1, 1.2, 1.2, 1.2, 1.25, 1.3, 1.44, 1.5, 2.0]))
+        nl = int(rng.integers(1, 9))
+        th = int(rng.choice([7, 9, 12, 20, 20, 25, 40]))
+        kind = int(rng.integers(0, 3))
+        if seed >= 6:                                          # wider ranges: very many features on few levels, fastTh 0, tiny levels
+            nf, th = int(rng.integers(50, 3000)), int(rng.choice([0, 1, 5, 20, 80]))
+        img = (synth_frame(h, w, 9100 + seed) if kind == 0 else synth_frame(h, w, 9200 + seed, quadrants=False) if kind == 1
+               else rng.integers(0, 256, (h, w), dtype=np.uint8))
+        what = (h, w, nf, sf, nl, th, kind)
+        ex = pkg.ORBextractor(nf, sf, nl, 1, th, max_width=w, max_height=h, max_batch=2)
+        try:
+            rk, rd = po.OracleExtractor(nf, sf, nl, 1, th)(img)
+        except RuntimeError:
+            with pytest.raises(pkg.OrbError):
+                ex(img)
+            ex.close()
+            continue
+        kps, desc = ex(img)
+        _same(kps, desc, rk, rd, what)
+        (k2, d2), (k3, d3) = ex.extract_batch(np.stack([img, img[::-1].copy()]))
+        _same(k2, d2, rk, rd, what + ("batch",))
+        rk3, rd3 = po.OracleExtractor(nf, sf, nl, 1, th)(img[::-1].copy())
+        _same(k3, d3, rk3, rd3, what + ("flipped",))
+        ex.close()
+
+
+@pytest.mark.parametrize("h,w,nf,scale,nlevels,fast_th", [
+    (261, 623, 1436, 1.5, 6, 9), (673, 239, 1436, 1.25, 1, 9), (206, 796, 1486, 1.3, 6, 40), (495, 298, 1092, 1.44, 1, 12),
+    (231, 698, 2278, 1.1, 1, 0), (360, 915, 2216, 1.7, 8, 1), (234, 523, 1597, 1.5, 8, 20)])
+def test_degenerate_grids(pkg, po, h, w, nf, scale, nlevels, fast_th):
+    """The configurations of tests/test_ref_build.py::test_extractor_degenerate_grids (oracle == the reference's own ORBextractor.cc
+    there): inner cells reaching past size - 16, keypoints that need the whole 16 px frame, 209 cells on one level, fastTh 0, and two
+    geometries the reference throws on."""
+    from orbslam_jpminipc_b200.synth import synth_frame
+    rng = np.random.default_rng(h * w)
+    ex = pkg.ORBextractor(nf, scale, nlevels, 1, fast_th, max_width=w, max_height=h, max_batch=2)
+    orc = po.OracleExtractor(nf, scale, nlevels, 1, fast_th)
+    for img in (synth_frame(h, w, 31, quadrants=False), rng.integers(0, 256, (h, w), dtype=np.uint8)):
+        try:
+            rk, rd = orc(img)
+        except RuntimeError:
+            with pytest.raises(pkg.OrbError):
+                ex(img)
+            continue
+        kps, desc = ex(img)
+        _same(kps, desc, rk, rd, (h, w, nf, scale, nlevels, fast_th))
+    ex.close()
+
+
 def test_strided_input_and_edge_cases(pkg, po):
     from orbslam_jpminipc_b200.synth import synth_frame
     big = synth_frame(300, 500, 6000)

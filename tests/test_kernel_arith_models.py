@@ -203,3 +203,64 @@ def test_border_ring_covers_everything_the_path_reads():
     reach = max(math.hypot(nums[i], nums[i + 1]) for i in range(0, 1024, 2))
     # cvRound(x*b + y*a) of a point at distance r from the keypoint is at most round(r) away on either axis
     assert round(reach) - edge <= ring - 1 and 3 <= ring - 1 + 0 and ring % 4 == 0
+
+
+def test_quota_loop_bound():
+    """orb_plan.cu sizes the per-level keypoint list as ncells * nfCell + ncells (+ margin): the quota redistribution of
+    src/ORBextractor.cc:622-670 never leaves more, whatever the per-cell key counts (random and adversarial), and the bound is tight
+    to within two records."""
+    import math
+    rng = np.random.default_rng(5)
+
+    def quota(t, q):
+        n = len(t)
+        retain = np.zeros(n, np.int64); closed = np.zeros(n, bool)
+        d = 0
+        for c in range(n):
+            if t[c] > q: retain[c] = q
+            else: retain[c] = t[c]; d += q - t[c]; closed[c] = True
+        while d > 0 and closed.sum() < n:
+            new = q + int(math.ceil(np.float32(d) / np.float32(n - closed.sum())))
+            d = 0
+            for c in range(n):
+                if closed[c]: continue
+                if t[c] > new: retain[c] = new
+                else: retain[c] = t[c]; d += new - t[c]; closed[c] = True
+        return int(retain.sum())
+    worst = -10 ** 9
+    for trial in range(4000):
+        n = int(rng.integers(1, 60)); nd = int(rng.integers(1, 600)); q = -(-nd // n)
+        mode = trial % 4
+        if mode == 0: t = rng.integers(0, 3 * q + 2, n)
+        elif mode == 1: t = rng.integers(0, 50 * q + 2, n) * (rng.random(n) < 0.3)
+        elif mode == 2: t = np.sort(rng.integers(0, q * n + 5, n))
+        else: t = (q + np.arange(n) * int(rng.integers(0, 4)) + rng.integers(-2, 3, n)).clip(0)
+        total = quota(t, q)
+        assert total <= n * q + n, (n, q, list(t))
+        worst = max(worst, total - n * q - n)
+    assert worst >= -4                       # tight: some input comes within a few records of the bound
+
+
+def test_half_lane_min_max_model():
+    """k_fast_nms round 2: a lane holds 0x6400 | pixel = the fp16 number 1024 + pixel.  (1) positive halves order like their bit
+    patterns, so the integer 16-bit min / max keep working; (2) d = relu(a - b), max = b + d, min = a - d are exact in fp16 for every
+    pixel pair; (3) the epilogue's lane constants absorb the 0x6400 without leaving a signed 16-bit lane."""
+    px = np.arange(256, dtype=np.uint16)
+    bits = (0x6400 | px).astype(np.uint16)
+    half = bits.view(np.float16)
+    assert np.array_equal(half.astype(np.float32), 1024.0 + px)
+    a, b = np.meshgrid(half, half, indexing="ij")
+    d = np.maximum((a - b).astype(np.float16), np.float16(0))                # fma.rn.relu.f16x2(b, -1, a): one rounding, exact here
+    assert np.array_equal((a.astype(np.float64) - b.astype(np.float64)).clip(0), d.astype(np.float64))
+    mx, mn = (b + d).astype(np.float16), (a - d).astype(np.float16)
+    assert np.array_equal(mx.view(np.uint16), np.maximum(a.view(np.uint16), b.view(np.uint16)))
+    assert np.array_equal(mn.view(np.uint16), np.minimum(a.view(np.uint16), b.view(np.uint16)))
+    # epilogue: q = max(Mn + nvp', ~Mx + vm1', 0) with nvp' = -(v + th) - 0x6400, vm1' = v - th + 1 + 0x6400 in int16 lanes
+    for th in (1, 7, 20, 255):
+        v, m = np.meshgrid(np.arange(256), np.arange(256), indexing="ij")
+        Mn = (0x6400 + m).astype(np.int32); Mx = Mn
+        nvp = (-(v + th) - 0x6400).astype(np.int32); vm1 = (v - th + 1 + 0x6400).astype(np.int32)
+        for term in (Mn + nvp, (-Mx - 1) + vm1):
+            assert term.min() >= -32768 and term.max() <= 32767 and nvp.min() >= -32768 and vm1.max() <= 32767
+        assert np.array_equal(np.maximum(Mn + nvp, 0), np.maximum(m - v - th, 0))
+        assert np.array_equal(np.maximum((-Mx - 1) + vm1, 0), np.maximum(v - m - th, 0))

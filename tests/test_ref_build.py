@@ -77,6 +77,36 @@ def test_extractor_degenerate_frames(po):
     assert len(ref(flat)[0]) == 0 and len(ref(noise)[0]) > 400
 
 
+@pytest.mark.parametrize("h,w,nf,scale,nlevels,fast_th,throws", [
+    (261, 623, 1436, 1.5, 6, 9, False),     # level 5 is 82x34: 4 cell rows of height 1 over a 2-row region, the third detects at y = 18 = h - 16
+    (673, 239, 1436, 1.25, 1, 9, False),    # 28 columns of width 8 over 207: columns 26 reaches 8 px past w - 16, column 27 is skipped
+    (206, 796, 1486, 1.3, 6, 40, False),    # keypoints closer than 16 px to the ROI edge: IC_Angle / rBRIEF read 15 px of the frame
+    (495, 298, 1092, 1.44, 1, 12, False),   # 209 cells on one level
+    (231, 698, 2278, 1.1, 1, 0, False),     # fastTh = 0
+    (360, 915, 2216, 1.7, 8, 1, True),      # a level smaller than its margins: an INNER cell row has negative height -> Mat::rowRange throws
+    (234, 523, 1597, 1.5, 8, 20, True),
+])
+def test_extractor_degenerate_grids(po, h, w, nf, scale, nlevels, fast_th, throws):
+    """Grids where cellW = ceil(W / cols) makes inner cells reach past [16, size - 16) or where a level is smaller than its margins
+    (found by the GPU fuzz sweep of round 2: the CUDA path cut detection at size - 16 and skipped what the reference throws on).  The
+    reference's own ORBextractor.cc decides; the oracle must agree, keypoint for keypoint or throw for throw."""
+    from orbslam_jpminipc_b200.synth import synth_frame
+    ref = pyref.RefExtractor(nf, scale, nlevels, 1, fast_th)
+    orc = po.OracleExtractor(nf, scale, nlevels, 1, fast_th)
+    rng = np.random.default_rng(h * w)
+    for img in (synth_frame(h, w, 31, quadrants=False), rng.integers(0, 256, (h, w), dtype=np.uint8)):
+        if throws:
+            with pytest.raises(RuntimeError):
+                ref(img)
+            with pytest.raises(RuntimeError):
+                orc(img)
+            continue
+        rk, rd = ref(img)
+        ok, od = orc(img)
+        _same_keypoints(rk, ok)
+        assert np.array_equal(rd, od) and len(rk) > 50
+
+
 # --------------------------------------------------------------------------------------------- Frame: undistortion, bounds, grid
 @pytest.mark.parametrize("dist", [(0, 0, 0, 0), (-0.28, 0.07, 0.0002, 0.00002), (0.1, -0.05, 0.001, -0.002)])
 def test_frame_constructor_equals_oracle(po, dist):

@@ -1,0 +1,47 @@
+"""Fuzz sweep of the extraction path against the CPU oracle (shapes, feature counts, scale factors, level counts, thresholds, frame kinds;
+where the reference throws on a geometry both must refuse):  gpurun -- 'python tools/fuzz_extract.py 0 400'
+Round 2: 1600 cases, 0 mismatches after the fixes it led to (detection past size - 16 in degenerate grids, the 16 px frame those levels
+need, inner cells of negative size, the list-capacity bound, 1024 cells per level, fastTh 0)."""
+import sys, numpy as np, time
+sys.path.insert(0, ".")
+import orbslam_jpminipc_b200 as pkg
+from oracle import pyoracle as po
+from orbslam_jpminipc_b200.synth import synth_frame
+bad = 0; n = 0; raised = 0; t0 = time.time()
+for seed in range(int(sys.argv[1]), int(sys.argv[2])):
+    rng = np.random.default_rng(70000 + seed)
+    h, w = int(rng.integers(100, 800)), int(rng.integers(120, 1000))
+    nf = int(rng.integers(50, 3000))
+    sf = float(rng.choice([1.05, 1.1, 1.2, 1.2, 1.25, 1.3, 1.44, 1.5, 1.7, 2.0, 2.3]))
+    nl = int(rng.integers(1, 9))
+    th = int(rng.choice([0, 1, 5, 7, 9, 12, 20, 20, 25, 40, 80]))
+    kind = int(rng.integers(0, 4))
+    if kind == 0: img = synth_frame(h, w, 100 + seed)
+    elif kind == 1: img = synth_frame(h, w, 200 + seed, quadrants=False)
+    elif kind == 2: img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    else:
+        img = np.full((h, w), int(rng.integers(0, 256)), np.uint8); hh, ww = h // 2, w // 2
+        img[h // 4:h // 4 + hh, w // 4:w // 4 + ww] = synth_frame(hh, ww, 300 + seed)
+    what = (h, w, nf, sf, nl, th, kind)
+    try:
+        ex = pkg.ORBextractor(nf, sf, nl, 1, th, max_width=w, max_height=h, max_batch=1)
+    except Exception as e:
+        print(what, "create raises", e); continue
+    n += 1
+    try:
+        rk, rd = po.OracleExtractor(nf, sf, nl, 1, th)(img)
+    except RuntimeError:
+        raised += 1
+        try:
+            ex(img); print(what, "oracle raises, GPU does not"); bad += 1
+        except pkg.OrbError:
+            pass
+        ex.close(); continue
+    try:
+        k, d = ex(img)
+    except Exception as e:
+        print(what, "GPU raises", e); bad += 1; ex.close(); continue
+    ok = len(k) == len(rk) and np.array_equal(d, rd) and np.array_equal(k.view(np.uint8), rk.view(np.uint8))
+    if not ok: bad += 1; print(what, "MISMATCH gpu %d oracle %d" % (len(k), len(rk)))
+    ex.close()
+print("cases", n, "oracle raised", raised, "bad", bad, "%.1f s" % (time.time() - t0))
