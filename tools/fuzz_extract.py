@@ -8,6 +8,7 @@ import orbslam_jpminipc_b200 as pkg
 from oracle import pyoracle as po
 from orbslam_jpminipc_b200.synth import synth_frame
 bad = 0; n = 0; raised = 0; t0 = time.time()
+HARRIS = len(sys.argv) > 3 and sys.argv[3] == "harris"        # half of the cases with scoreType = HARRIS_SCORE
 for seed in range(int(sys.argv[1]), int(sys.argv[2])):
     rng = np.random.default_rng(70000 + seed)
     h, w = int(rng.integers(100, 800)), int(rng.integers(120, 1000))
@@ -16,20 +17,21 @@ for seed in range(int(sys.argv[1]), int(sys.argv[2])):
     nl = int(rng.integers(1, 9))
     th = int(rng.choice([0, 1, 5, 7, 9, 12, 20, 20, 25, 40, 80]))
     kind = int(rng.integers(0, 4))
+    score = 0 if (HARRIS and rng.random() < 0.5) else 1
     if kind == 0: img = synth_frame(h, w, 100 + seed)
     elif kind == 1: img = synth_frame(h, w, 200 + seed, quadrants=False)
     elif kind == 2: img = rng.integers(0, 256, (h, w), dtype=np.uint8)
     else:
         img = np.full((h, w), int(rng.integers(0, 256)), np.uint8); hh, ww = h // 2, w // 2
         img[h // 4:h // 4 + hh, w // 4:w // 4 + ww] = synth_frame(hh, ww, 300 + seed)
-    what = (h, w, nf, sf, nl, th, kind)
+    what = (h, w, nf, sf, nl, th, kind, score)
     try:
-        ex = pkg.ORBextractor(nf, sf, nl, 1, th, max_width=w, max_height=h, max_batch=1)
+        ex = pkg.ORBextractor(nf, sf, nl, score, th, max_width=w, max_height=h, max_batch=1)
     except Exception as e:
         print(what, "create raises", e); continue
     n += 1
     try:
-        rk, rd = po.OracleExtractor(nf, sf, nl, 1, th)(img)
+        rk, rd = po.OracleExtractor(nf, sf, nl, score, th)(img)
     except RuntimeError:
         raised += 1
         try:
