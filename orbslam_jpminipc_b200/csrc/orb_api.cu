@@ -115,8 +115,8 @@ static int prepare(orb_ctx* c, int w, int h)
         ORB_CUDA(cudaMemcpy(c->d_fast_rowtab, c->fast_rowtab.data(), c->fast_rowtab.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
         int maxcap = 0;
         for (int l = 0; l < c->plan.nlevels; l++) maxcap = std::max(maxcap, c->plan.L[l].lvl_cap);
-        if ((size_t)maxcap * 8 > 170 * 1024) return ORB_ERR_CAPACITY;
-        rc = orb_select_smem_setup(maxcap); if (rc) return rc;
+        if ((size_t)maxcap * 8 + (size_t)c->plan.sel_cells_cap * 13 > 170 * 1024) return ORB_ERR_CAPACITY;
+        rc = orb_select_smem_setup(maxcap, c->plan.sel_cells_cap); if (rc) return rc;
         size_t rsm = 1024;
         for (int l = 1; l < c->plan.nlevels; l++) rsm = std::max(rsm, (size_t)2 * (((size_t)c->rs_box_w[l] * c->rs_box_h[l] + 127) & ~(size_t)127) + 16);
         rc = orb_resize_smem_setup((int)rsm); if (rc) return rc;

@@ -1317,8 +1317,9 @@ k_select_fast(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells,
               unsigned long long* __restrict__ cand64, const int* __restrict__ ntotal,
               unsigned long long* __restrict__ lvl, int* __restrict__ nkept, int* __restrict__ status, uint8_t* __restrict__ spare, size_t fbytes)
 {
-    extern __shared__ unsigned long long s_list[];            // sel_list_cap u64 | SEL_WARPS x SEL_WCAP u32 | SEL_WARPS x SEL_WCAP u16
-    __shared__ int s_total[ORB_MAX_CELLS_LEVEL], s_retain[ORB_MAX_CELLS_LEVEL], s_off[ORB_MAX_CELLS_LEVEL + 1];
+    // sel_list_cap u64 | SEL_WARPS x SEL_WCAP u32 | SEL_WARPS x SEL_WCAP u16 | per-cell tables sized for the plan's largest grid
+    // (sel_cells_cap: static arrays of ORB_MAX_CELLS_LEVEL entries cost 1 % of the whole pipeline in residency next to k_blur)
+    extern __shared__ unsigned long long s_list[];
     const int level = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const LevelGeom& L = plan->L[level];
     const int nCells = L.ncells;
@@ -1326,12 +1327,16 @@ k_select_fast(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells,
     const int* nt = ntotal + (size_t)f * plan->ncells + L.cell_base;
     uint32_t* s_wbuf = reinterpret_cast<uint32_t*>(s_list + plan->sel_list_cap);
     unsigned short* s_scr = reinterpret_cast<unsigned short*>(s_wbuf + SEL_WARPS * SEL_WCAP);
+    const int ccap = plan->sel_cells_cap;                      // multiple of 4
+    int* s_total = reinterpret_cast<int*>(s_scr + SEL_WARPS * SEL_WCAP);
+    int* s_retain = s_total + ccap;
+    int* s_off = s_retain + ccap;                              // ccap + 4 entries
+    unsigned char* noMore = reinterpret_cast<unsigned char*>(s_off + ccap + 4);
     for (int c = tid; c < nCells; c += blockDim.x) s_total[c] = nt[c];
     __syncthreads();
     if (tid == 0) {                                            // quota redistribution, src/ORBextractor.cc:622-670
         const int nfc = L.nfCell;
         int nNoMore = 0, nToDistribute = 0;
-        unsigned char noMore[ORB_MAX_CELLS_LEVEL];
         for (int c = 0; c < nCells; c++) {
             noMore[c] = 0; s_retain[c] = 0;
             if (cg[c].skipped) continue;                       // stays open with nTotal = 0
@@ -1939,7 +1944,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         if (c->fork_early == 0) { launch_blur(W.aux_stream); ORB_CUDA(cudaEventRecord(W.ev_join, W.aux_stream)); }
     }
     mark();
-    const size_t sel_smem = (size_t)P.sel_list_cap * 8 + (size_t)SEL_WARPS * SEL_WCAP * 6;
+    const size_t sel_smem = (size_t)P.sel_list_cap * 8 + (size_t)SEL_WARPS * SEL_WCAP * 6 + (size_t)P.sel_cells_cap * 13 + 16;
     uint8_t* sel_spare = (size_t)P.cand_total * 2 <= fb ? W.d_work : nullptr;
     if (P.harris) {
         k_harris<<<dim3((P.ncells + 7) / 8, nimg), 256, 0, s>>>(W.d_planes, fb, c->d_plan, c->d_cells, W.d_cand, W.d_ntotal, W.d_cand64);
@@ -1995,9 +2000,9 @@ int orb_resize_smem_setup(int max_bytes)
     return rc ? rc : raise_dyn_smem((const void*)k_pyramid, 5, max_bytes);
 }
 
-int orb_select_smem_setup(int list_cap)     // list_cap: the largest per-level keypoint list (u64 records) of the plan
+int orb_select_smem_setup(int list_cap, int cells_cap)     // the largest per-level keypoint list (u64 records) and cell grid of the plan
 {
-    const int serial = list_cap * 8 + SEL_STAGE * 4 + 1024, fast = list_cap * 8 + SEL_WARPS * SEL_WCAP * 6 + 1024;
+    const int serial = list_cap * 8 + SEL_STAGE * 4 + 1024, fast = list_cap * 8 + SEL_WARPS * SEL_WCAP * 6 + cells_cap * 13 + 1024;
     int rc = raise_dyn_smem((const void*)k_select<false>, 1, serial);
     if (!rc) rc = raise_dyn_smem((const void*)k_select<true>, 2, serial);
     if (!rc) rc = raise_dyn_smem((const void*)k_select_fast<true>, 4, fast);

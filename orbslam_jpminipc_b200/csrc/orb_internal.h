@@ -68,6 +68,7 @@ struct Plan {
     int ntiles_fast, ntiles_blur;
     int bm_total;          // bitmap bytes per frame
     int sel_list_cap;      // max lvl_cap over levels (k_select shared-memory list)
+    int sel_cells_cap;     // max ncells over levels, rounded up to a multiple of 4 (k_select_fast per-cell tables)
     int border_total;      // k_border work items (32-bit words of all frame regions) per image
     int desc_fma;          // descriptor rotation with the reference compiler's FMA contraction (orb_set_descriptor_fma)
     LevelGeom L[ORB_MAX_LEVELS];
@@ -237,7 +238,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
                        orb_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts, cudaStream_t s);
 int orb_upload_constants(const int* umax);
 int orb_build_tmaps(orb_ctx* c, WorkSet& W, int nframes);
-int orb_select_smem_setup(int max_bytes);
+int orb_select_smem_setup(int list_cap, int cells_cap);
 int orb_resize_smem_setup(int max_bytes);
 // orb_match.cu
 int orb_launch_knn2(orb_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_db, int64_t ndb, int npairs, int32_t idx_base,

@@ -268,7 +268,8 @@ int orb_build_plan(orb_ctx* c, int w, int h)
     P.border_total = border;
     P.bm_total = bm;
     P.sel_list_cap = 0;
-    for (int l = 0; l < P.nlevels; l++) P.sel_list_cap = std::max(P.sel_list_cap, P.L[l].lvl_cap);
+    P.sel_cells_cap = 4;
+    for (int l = 0; l < P.nlevels; l++) { P.sel_list_cap = std::max(P.sel_list_cap, P.L[l].lvl_cap); P.sel_cells_cap = std::max(P.sel_cells_cap, (P.L[l].ncells + 3) & ~3); }
     P.ntiles_fast = (int)c->tiles_fast.size();
     P.ntiles_blur = (int)c->tiles_blur.size();
     return ORB_OK;   // device upload happens in orb_api.cu
