@@ -293,7 +293,15 @@ def measure_extraction(E, w, h, steps, warmup, launches, full):
     cap = ex.capacity
     base = synth_frames(min(B, 32), h, w, 1000 + 100 * rank)            # 32 distinct frames per rank, tiled to the batch
     host = np.concatenate([base] * ((B + len(base) - 1) // len(base)))[:B].copy()
-    pin = torch.from_numpy(host).pin_memory()
+    if E.args.wc_input:
+        # write-combined pinned input (orb_host_alloc_input): the CPU only writes the frames, the copy engine reads them without cache snoops
+        base_ptr = L.orb_host_alloc_input(host.nbytes)
+        require(bool(base_ptr), "orb_host_alloc_input")
+        wc = np.ctypeslib.as_array(C.cast(base_ptr, C.POINTER(C.c_uint8)), shape=(host.nbytes,)).reshape(host.shape)
+        wc[...] = host
+        pin = torch.from_numpy(wc)
+    else:
+        pin = torch.from_numpy(host).pin_memory()
     d_img = pin.to(dev, non_blocking=False)
     d_kps = torch.zeros((B, cap, 7), dtype=torch.int32, device=dev)
     d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device=dev)
@@ -906,6 +914,7 @@ def main():
     ap.add_argument("--no-tensor-ab", dest="tensor_ab", action="store_false", help="skip the tensor-core kNN A/B")
     ap.add_argument("--quick", action="store_true", help="headline measurement only (profiling runs): no 752x480 pass, no latency / tracking extras")
     ap.add_argument("--e2e-chunk", type=int, default=64)
+    ap.add_argument("--wc-input", action="store_true", help="input frames in write-combined pinned memory (orb_host_alloc_input)")
     args = ap.parse_args()
     capture_stdout()
     if args.impl == "reference":

@@ -385,6 +385,8 @@ int orb_extract_batch_multi(orb_comm*, const uint8_t* imgs, int nimg, int w, int
 /* pinned host memory helpers (page-locked buffers make the host<->device copies asynchronous) */
 void* orb_host_alloc(size_t bytes);
 void  orb_host_free(void* p);
+/* the same, write-combined (cudaHostAllocWriteCombined): input frames that the CPU writes once and never reads */
+void* orb_host_alloc_input(size_t bytes);
 
 /* register-resident __popc micro-benchmark: measured POPC32 rate of this GPU in G ops/s
  * (the integer-pipe roofline denominator for the matcher) */

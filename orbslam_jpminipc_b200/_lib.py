@@ -24,7 +24,7 @@ EXPORTS = [
     "orb_scale_factor", "orb_keypoint_capacity", "orb_set_descriptor_fma", "orb_extract", "orb_extract_batch", "orb_extract_batch_device", "orb_extract_batch_async", "orb_wait",
     "orb_last_launch_count", "orb_profile_enable", "orb_profile_read", "orb_profile_stage_name", "orb_debug_level_info", "orb_debug_level_plane", "orb_descriptor_distance",
     "orb_hamming_knn2", "orb_hamming_knn2_device", "orb_set_knn_engine", "orb_knn2_merge_device", "orb_match_ratio",
-    "orb_frame_grid_build", "orb_search_by_projection", "orb_search_window", "orb_search_window_best", "orb_search_for_initialization", "orb_search_by_bow", "orb_search_by_bow_kf", "orb_search_for_triangulation", "orb_host_alloc", "orb_host_free",
+    "orb_frame_grid_build", "orb_search_by_projection", "orb_search_window", "orb_search_window_best", "orb_search_for_initialization", "orb_search_by_bow", "orb_search_by_bow_kf", "orb_search_for_triangulation", "orb_host_alloc", "orb_host_free", "orb_host_alloc_input",
     "orb_measure_popc_peak",
     "orb_distinctive_descriptors", "orb_cvt_gray", "orb_extract_batch_color", "orb_undistort_keypoints", "orb_image_bounds",
     "orb_db_read_descriptors", "orb_db_write_descriptors", "orb_db_read_keypoints", "orb_db_write_keypoints",
@@ -121,6 +121,8 @@ def lib():
                                                vp, C.POINTER(C.c_int)]
     L.orb_host_alloc.restype = vp
     L.orb_host_alloc.argtypes = [sz]
+    L.orb_host_alloc_input.restype = vp
+    L.orb_host_alloc_input.argtypes = [sz]
     L.orb_host_free.argtypes = [vp]
     L.orb_measure_popc_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.orb_distinctive_descriptors.argtypes = [vp, vp, vp, i32, vp, vp]

@@ -1227,5 +1227,13 @@ void* orb_host_alloc(size_t bytes)
     return p;
 }
 void orb_host_free(void* p) { if (p) cudaFreeHost(p); }
+/* page-locked AND write-combined: for input frames the CPU only ever writes (camera / decoder output).  The CPU caches are not
+ * snooped during the host->device copy; CPU reads of such memory are very slow. */
+void* orb_host_alloc_input(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocWriteCombined) != cudaSuccess) { orb_cuda_fail(cudaGetLastError(), "cudaHostAlloc"); return nullptr; }
+    return p;
+}
 
 } // extern "C"
