@@ -996,10 +996,22 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
         const bool full = vw == FT_W && nr == FS_H;
         if (ETILE) {
             // re-encode the raw tile: raw word 3 + j of a row (columns x0-4+4j ..) -> words 2j, 2j+1 of the half-lane tile
-            for (int i = tid; i < FI_H * (EW / 2); i += FAST_THREADS) {
-                const int row = i / (EW / 2), j = i - row * (EW / 2);
-                const uint32_t rw = img[row * FIW + 3 + j];
-                *reinterpret_cast<uint2*>(et + row * EW + 2 * j) = make_uint2(__byte_perm(rw, 0x64646464u, 0x4140), __byte_perm(rw, 0x64646464u, 0x4342));
+            // thread = (raw word column, row residue): no index arithmetic per word, compile-time row offsets (the flat form with a
+            // division per word was 7 % of the kernel's instructions)
+            {
+                constexpr int EC = EW / 2, ER = FAST_THREADS / EC;          // 18 word columns, 7 rows per pass
+                if (tid < EC * ER) {
+                    const int er0 = tid / EC, ej = tid - er0 * EC;
+                    const uint32_t* src = img + er0 * FIW + 3 + ej;
+                    uint32_t* dst = et + er0 * EW + 2 * ej;
+#pragma unroll
+                    for (int k = 0; k < (FI_H + ER - 1) / ER; k++) {
+                        if ((k + 1) * ER <= FI_H || er0 + k * ER < FI_H) {
+                            const uint32_t rw = src[k * ER * FIW];
+                            *reinterpret_cast<uint2*>(dst + k * ER * EW) = make_uint2(__byte_perm(rw, 0x64646464u, 0x4140), __byte_perm(rw, 0x64646464u, 0x4342));
+                        }
+                    }
+                }
             }
             if (full) halo_pass(std::true_type{}); else halo_pass(std::false_type{});
             __syncthreads();       // the raw tile is dead: fetch the next item's into the same buffer
