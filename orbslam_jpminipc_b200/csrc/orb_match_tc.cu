@@ -234,6 +234,88 @@ k_knn2_tc(Knn2TcArgs A)
         // scanner warp w: M-tile w >> 2, TMEM lane quarter w & 3; one query row per thread, all 128 columns of its accumulator
         const int m = warp >> 2, q4 = warp & 3;
         const uint32_t t_lane = tmem + ((uint32_t)(q4 * 32) << 16);
+#ifndef ORB_TC_SCAN32
+        // ---- 16-bit keys, two columns per register (default) ----
+        // key = distance * 128 + column = -64 * dot + 16384 + column fits a 16-bit lane (distance <= 256, 128 columns per tile), smaller is
+        // better and the lower column wins a tie.  Two columns are packed by two IMADs on the FMA pipe (no PRMT):
+        //   K = dot[j] * -64 + dot[j+1] * (-64 << 16) + constant          (modulo 2^32; every lane stays inside [0, 32895])
+        // and the scan keeps smallest / second smallest per lane (even / odd columns) with 5 ALU operations per FOUR keys,
+        //   lo = min(A, B), hi = max(A, B);  p2 = min3(max(p1, lo), p2, hi);  p1 = min(p1, lo)
+        // (second smallest of {p1 <= p2, lo <= hi}: lo < p1 -> min(p1, hi); lo >= p1 -> min(lo, p2)), against 5 per two 32-bit keys before.
+        int R1 = INT_MAX, R2 = INT_MAX, RI = -1;                    // running best distance, second-best distance, best row (chunk-relative)
+        int va[32], vb[32];                                          // two register buffers: a load is in flight while the other buffer is scanned
+        bool early = false;                                         // the first load of this tile was already issued at the end of the previous one
+        for (int t = 0; t < ntiles; t++) {
+            const int s = t & 1;
+            const int valid = min(TC_N, nrows - t * TC_N);              // columns >= valid belong to rows past the chunk
+            const uint32_t tcol = t_lane + (uint32_t)((s * TC_MT + m) * TC_N);
+            if (!early) {
+                tc_mbar_wait(&bar_full[s], (uint32_t)((t >> 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                tmem_ld32(tcol, va);
+            }
+            uint32_t p1 = 0xffffffffu, p2 = 0xffffffffu;
+            auto pack2 = [](int d0, int d1, int col) {               // keys of columns col, col + 1
+                const uint32_t cst = (uint32_t)(16384 + col) + ((uint32_t)(16384 + col + 1) << 16);
+                return (uint32_t)d1 * (uint32_t)(-64 * 65536) + ((uint32_t)d0 * (uint32_t)(-64) + cst);
+            };
+            auto scan32 = [&](const int (&v)[32], int cbase) {
+                if (cbase + 32 <= valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const uint32_t A2 = pack2(v[j], v[j + 1], cbase + j), B2 = pack2(v[j + 2], v[j + 3], cbase + j + 2);
+                        const uint32_t lo = __vminu2(A2, B2), hi = __vmaxu2(A2, B2);
+                        p2 = __vimin3_u16x2(__vmaxu2(p1, lo), p2, hi);
+                        p1 = __vminu2(p1, lo);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const uint32_t k0 = (cbase + j < valid) ? (uint32_t)(-64 * v[j] + 16384 + cbase + j) : 0xffffu;
+                        const uint32_t k1 = (cbase + j + 1 < valid) ? (uint32_t)(-64 * v[j + 1] + 16384 + cbase + j + 1) : 0xffffu;
+                        const uint32_t A2 = k0 | (k1 << 16);
+                        p2 = __vminu2(p2, __vmaxu2(p1, A2));
+                        p1 = __vminu2(p1, A2);
+                    }
+                }
+            };
+            tmem_ld_wait(va);
+            tmem_ld32(tcol + 32, vb);
+            scan32(va, 0);
+            tmem_ld_wait(vb);
+            tmem_ld32(tcol + 64, va);
+            scan32(vb, 32);
+            tmem_ld_wait(va);
+            tmem_ld32(tcol + 96, vb);
+            scan32(va, 64);
+            tmem_ld_wait(vb);
+            // va is free: if the NEXT tile's accumulator is already complete (its MMAs do not depend on this scan), start its first load
+            // now so that its latency hides behind the last 32 columns of this tile.  The test must be warp-uniform: tcgen05.ld is .aligned.
+            early = false;
+            if (t + 1 < ntiles) {
+                const bool ready = tc_mbar_test(&bar_full[s ^ 1], (uint32_t)(((t + 1) >> 1) & 1));
+                if (__all_sync(0xffffffffu, ready)) {
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    tmem_ld32(t_lane + (uint32_t)(((s ^ 1) * TC_MT + m) * TC_N), va);
+                    early = true;
+                }
+            }
+            scan32(vb, 96);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(&bar_tfree[s]);
+            // merge the even- and the odd-column lane, then fold the tile into the running result: earlier tiles hold lower rows
+            const uint32_t a1 = p1 & 0xffffu, b1 = p1 >> 16, a2 = p2 & 0xffffu, b2 = p2 >> 16;
+            const uint32_t best = min(a1, b1), second = min(max(a1, b1), min(a2, b2));
+            if (best != 0xffffu) {
+                const int t1 = (int)(best >> 7), ti = t * TC_N + (int)(best & 127u);
+                const int t2 = second == 0xffffu ? INT_MAX : (int)(second >> 7);
+                if (t1 < R1) { R2 = min(R1, t2); R1 = t1; RI = ti; }
+                else R2 = min(R2, t1);
+            }
+        }
+        const int d1f = R1, d2f = R2;
+#else
         int R1 = INT_MIN, R2 = INT_MIN, RI = -1;                    // running best dot, second-best dot, best row (chunk-relative)
         int va[32], vb[32];                                          // two register buffers: a load is in flight while the other buffer is scanned
         bool early = false;                                         // the first load of this tile was already issued at the end of the previous one
@@ -303,10 +385,12 @@ k_knn2_tc(Knn2TcArgs A)
                 else R2 = max(R2, t1);
             }
         }
+        const int d1f = RI < 0 ? INT_MAX : (256 - R1) >> 1, d2f = R2 == INT_MIN ? INT_MAX : (256 - R2) >> 1;
+#endif
         // ---- dots -> distances, write ----
         const int qi = (mtp * TC_MT + m) * TC_M + q4 * 32 + lane;
         if (qi < A.nq) {
-            const int d1 = RI < 0 ? INT_MAX : (256 - R1) >> 1, d2 = R2 == INT_MIN ? INT_MAX : (256 - R2) >> 1;
+            const int d1 = d1f, d2 = d2f;
             const int gi = RI < 0 ? -1 : (int)(row0 + RI) + A.idx_base;
             if (A.nchunks > 1) {
                 int32_t* o = A.out + ((size_t)(pair * A.nchunks + chunk) * 3) * A.nq;
