@@ -597,7 +597,7 @@ def run_matching(E):
         check(L.orb_set_knn_engine(ex._h, 0), "orb_set_knn_engine")
         tp4, tp5 = world * reps * NPAIR * NQ * ND / (tms4 * 1e-3), reps5 * NQ * NDB / (tms5 * 1e-3)
         # int8 tensor peak: nominal 4.5 POP/s dense per GPU (B200_PROFILING.md family figure: 2x the bf16 2.25 PFLOP/s); each pair is 256 MACs
-        tensor = {"engine": "ORB_KNN_TENSOR: descriptor bits as +-1 int8, tcgen05.mma kind::i8 M128 N256 K32 x 8, accumulator in TMEM, best/second-best scan on tcgen05.ld; Hamming = (256 - dot) / 2",
+        tensor = {"engine": "ORB_KNN_TENSOR: descriptor bits as +-1 int8, tcgen05.mma kind::i8 M128 N128 K32 x 8 for two query tiles per expanded database tile, accumulators in TMEM, best/second-best scan on tcgen05.ld with 16-bit packed keys; Hamming = (256 - dot) / 2",
                   "bit_exact_vs_popc_engine": True, "default": False,
                   "pair_blocks_2000x2000": {"pairs_per_s": tp4, "speedup_vs_popc": tp4 / pairs4, "timed_ms": tms4},
                   "db_sharded_10M": {"pairs_per_s": tp5, "ms_per_query_batch": tms5 / reps5, "speedup_vs_popc": tp5 / pairs5,

@@ -7,8 +7,9 @@
 // 128-query x 256-row block of dots per tile (8 instructions of K = 32), the accumulator lives in TMEM, and the CUDA cores only
 //   (1) expand the packed bits of the database tile into the canonical K-major shared-memory operand layout (one 2 KB lookup table:
 //       byte -> eight +-1 bytes), and
-//   (2) run the best / second-best scan on the accumulator read back with tcgen05.ld: per pair one IMAD (key = (dot+256)*300 + 255-col,
-//       FMA pipe) and 2.5 integer min/max (ALU pipe) — against 5 POPC + 14 LOP3 + ... in k_knn2.
+//   (2) run the best / second-best scan on the accumulator read back with tcgen05.ld: per pair one IMAD on the FMA pipe (16-bit key =
+//       distance*128 + column, two columns packed per register) and 1.25 16-bit SIMD min/max on the ALU pipe — against 5 POPC + 14 LOP3
+//       + ... in k_knn2 (-DORB_TC_SCAN32 keeps the earlier 32-bit keys: one IMAD + 2.5 min/max per pair).
 // The MMA of tile t runs asynchronously (tcgen05.commit -> mbarrier) while the CUDA cores scan tile t-1 out of the other TMEM stage.
 // Results are bit-identical to k_knn2 (same scan semantics: lowest index wins, d2 = second order statistic); selected with
 // orb_set_knn_engine(ctx, ORB_KNN_TENSOR) or ORB_KNN_ENGINE=tensor, never by default (north_star pins the POPC path).
