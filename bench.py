@@ -501,7 +501,7 @@ def roofline_of(res, w, h, B):
     return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
             "traffic": traffic, "traffic_source": (rec or {}).get("source") if k else None,
             "alu_pipe_pct_ncu": k.get("alu_pipe_pct") if k else None, "warp_inst_per_pixel_ncu": k.get("warp_inst_per_pixel") if k else None,
-            "note": "k_fast_nms is integer-ALU bound (ncu: ALU pipe ~88 % of peak, DRAM ~5 %); the HBM fraction is the required yardstick, not its limiter",
+            "note": "k_fast_nms is bound by instruction issue on the integer / half2 pipes (ncu figures in alu_pipe_pct_ncu / traffic_source: ALU pipe ~71 %, FMA pipe ~20 %, issue ~66 %, DRAM ~6 %); the HBM fraction is the required yardstick, not its limiter",
             "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_per_launch, "frames_per_launch": B,
             "kernel_ms_per_launch": stage[dom], "stage_ms_per_launch": stage, "stage_ms_per_step": stage, "profiled_ms_per_launch": res["profiled_ms_per_launch"],
             "pipeline_bytes_per_frame": algorithmic_bytes_per_frame(w, h, nkp)}
