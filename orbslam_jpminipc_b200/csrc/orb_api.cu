@@ -53,9 +53,9 @@ int orb_build_tmaps(orb_ctx* c, WorkSet& W, int nframes)
         CUresult r2 = enc(&W.tm_blur.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box_blur, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (l + 1 < P.nlevels && r1 == CUDA_SUCCESS) {       // source descriptor for the resize that produces level l+1
-            cuuint32_t box_rs[3] = { (cuuint32_t)c->rs_box_w[l + 1], (cuuint32_t)c->rs_box_h[l + 1], 1 };
-            r1 = enc(&W.tm_resize.m[l + 1], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box_rs, estr,
+        for (int v = 0; v < 2 && l + 1 < P.nlevels && r1 == CUDA_SUCCESS; v++) {       // source descriptors for the resize that produces level l+1 (both tilings)
+            cuuint32_t box_rs[3] = { (cuuint32_t)c->rs_box_w[v][l + 1], (cuuint32_t)c->rs_box_h[v][l + 1], 1 };
+            r1 = enc(&W.tm_resize[v].m[l + 1], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box_rs, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         }
@@ -118,7 +118,8 @@ static int prepare(orb_ctx* c, int w, int h)
         if ((size_t)maxcap * 8 + (size_t)c->plan.sel_cells_cap * 13 > 170 * 1024) return ORB_ERR_CAPACITY;
         rc = orb_select_smem_setup(maxcap, c->plan.sel_cells_cap); if (rc) return rc;
         size_t rsm = 1024;
-        for (int l = 1; l < c->plan.nlevels; l++) rsm = std::max(rsm, (size_t)2 * (((size_t)c->rs_box_w[l] * c->rs_box_h[l] + 127) & ~(size_t)127) + 16);
+        for (int v = 0; v < 2; v++)
+            for (int l = 1; l < c->plan.nlevels; l++) rsm = std::max(rsm, (size_t)2 * (((size_t)c->rs_box_w[v][l] * c->rs_box_h[v][l] + 127) & ~(size_t)127) + 16);
         rc = orb_resize_smem_setup((int)rsm); if (rc) return rc;
         c->plan_valid = true;
         c->plan_gen++;
@@ -157,9 +158,17 @@ static int prepare_ws(orb_ctx* c, WorkSet& W, int nimg)
 // time it comes by and replayed afterwards.  Not used on the legacy default stream (capture is not allowed there), in profiling mode,
 // or for large batches, where launch cost is noise.
 static int launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_in, int n, int w, int h, int stride, size_t pitch,
-                          orb_keypoint* o_k, uint8_t* o_d, int cap, int32_t* o_c, cudaStream_t s)
+                          orb_keypoint* o_k, uint8_t* o_d, int cap, int32_t* o_c, cudaStream_t s, bool host_in = false)
 {
-    const bool eligible = c->use_graph && !c->profile && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread &&
+    // Calls of at most pdl_frames frames whose input is already on the device are launched with programmatic dependent launch instead
+    // (orb_extract.cu, launch_k).  Measured on B200 for one 640x480 frame, blocking call, microseconds, graph replay | PDL launches:
+    // device in / device out 113 | 94, device in / pinned out 127 | 110; but pinned in / device out 102 | 107, pinned in / pinned out
+    // 123 | 129, pageable both 136 | 138 — behind a host-to-device copy the single submission of a graph wins, because the host then
+    // enqueues the whole pass while the copy is still in flight.  Both together are slower than either (a replayed graph with
+    // programmatic edges: 157 / 146 us pageable / pinned against 146 / 135), so it is one or the other.
+    const bool pdl = c->use_pdl && n <= c->pdl_frames && !host_in;
+    c->pdl_call = pdl;
+    const bool eligible = c->use_graph && !pdl && !c->profile && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread &&
                           (double)n * w * h <= 12e6;
     if (!eligible) return orb_launch_extract(c, W, d_in, n, w, h, stride, pitch, o_k, o_d, cap, o_c, s);
     WorkSet::GraphKey key;
@@ -242,7 +251,14 @@ orb_ctx* orb_create(int device, int nfeatures, float scale_factor, int nlevels, 
     if (const char* e = getenv("ORB_RESIZE_UNROLLED")) c->rs_unrolled = atoi(e);
     if (const char* e = getenv("ORB_RESIZE_FLEX")) c->rs_flex_width = atoi(e) != 0;
     if (const char* e = getenv("ORB_RESIZE_ROWS")) c->rs_rows_pref = std::max(1, std::min(atoi(e), 32));
+    if (const char* e = getenv("ORB_RESIZE_ROWS_SMALL")) c->rs_rows_small = std::max(1, std::min(atoi(e), 32));
+    if (const char* e = getenv("ORB_SMALL_CALL")) c->small_call_frames = std::max(0, atoi(e));
     if (const char* e = getenv("ORB_SELECT_SERIAL")) c->select_serial = atoi(e);
+    if (const char* e = getenv("ORB_SELECT_WIDE")) c->select_wide = atoi(e);
+    if (const char* e = getenv("ORB_COMPACT_WIDE")) c->compact_wide = atoi(e);
+    if (const char* e = getenv("ORB_PDL")) c->use_pdl = atoi(e);
+    if (const char* e = getenv("ORB_PDL_FRAMES")) c->pdl_frames = std::max(0, atoi(e));
+    if (const char* e = getenv("ORB_STAGE_SMALL")) c->stage_small = atoi(e);
     if (const char* e = getenv("ORB_FORK_EARLY")) c->fork_early = atoi(e);
     if (const char* e = getenv("ORB_FAST_CTAS_FORK")) c->fast_ctas = atoi(e);
     if (const char* e = getenv("ORB_BLUR_CTAS")) c->blur_ctas = atoi(e);
@@ -304,13 +320,14 @@ void orb_destroy(orb_ctx* c)
         if (t.a) cudaEventDestroy(t.a);
         if (t.b) cudaEventDestroy(t.b);
         if (t.h_status) cudaFreeHost(t.h_status);
+        if (t.h_stage) cudaFreeHost(t.h_stage);
     }
     if (c->done_stream) cudaStreamDestroy(c->done_stream);
     if (c->ev_dev_done) cudaEventDestroy(c->ev_dev_done);
     if (c->ev_user) cudaEventDestroy(c->ev_user);
     for (cudaEvent_t e : c->ev_half) if (e) cudaEventDestroy(e);
     void* ptrs[] = { c->d_plan, c->d_cells, c->d_tiles_fast, c->d_tiles_blur, c->d_xtab, c->d_ytab, c->d_fast_coltab, c->d_fast_rowtab, c->d_status, c->d_src[0], c->d_src[1], c->d_kps[0],
-                     c->d_kps[1], c->d_desc[0], c->d_desc[1], c->d_counts[0], c->d_counts[1] };
+                     c->d_kps[1], c->d_desc[0], c->d_desc[1], c->d_counts[0], c->d_counts[1], c->d_small[0], c->d_small[1] };
     for (int i = 0; i < c->nlanes; i++) {
         MatchLane& L = c->lanes[i];
         if (L.d_scratch) cudaFree(L.d_scratch);
@@ -381,6 +398,7 @@ int orb_extract_batch_device(orb_ctx* c, const uint8_t* d_imgs, int nimg, int w,
     c->last_n0 = n0; c->last_n1 = n1;
     if (!split) return launch_extract(c, c->ws[0], d_imgs, nimg, w, h, stride, frame_pitch, d_kps, d_desc, cap, d_counts, us);
     ORB_CUDA(cudaEventRecord(c->ev_user, us));
+    c->pdl_call = false;
     int launches = 0;
     for (int k = 0; k < 2; k++) {
         cudaStream_t s = c->streams[k];
@@ -417,6 +435,19 @@ int orb_wait(orb_ctx* c, long long seq)
         return st;
     }
     int rc = ORB_OK;                  // every entry is clamped before the error is reported: a caller that reads counts[i] rows stays inside its slots
+    if (t.staged) {                   // [keypoints n x cap | descriptors n x cap x 32 | counts n] in pinned staging -> the caller's buffers, valid rows only
+        const size_t cap = (size_t)t.cap;
+        const orb_keypoint* sk = reinterpret_cast<const orb_keypoint*>(t.h_stage);
+        const uint8_t* sd = t.h_stage + (size_t)t.nimg * cap * sizeof(orb_keypoint);
+        const int32_t* sc = reinterpret_cast<const int32_t*>(sd + (size_t)t.nimg * cap * 32);
+        for (int i = 0; i < t.nimg; i++) {
+            const size_t n = (size_t)std::max(0, std::min(sc[i], t.cap));
+            memcpy(t.u_kps + i * cap, sk + i * cap, n * sizeof(orb_keypoint));
+            memcpy(t.u_desc + i * cap * 32, sd + i * cap * 32, n * 32);
+            t.counts[i] = sc[i];
+        }
+        t.staged = false;
+    }
     if (t.host_out) for (int i = 0; i < t.nimg; i++) if (t.counts[i] > t.cap) { t.counts[i] = t.cap; rc = ORB_ERR_CAPACITY; }
     return rc;
 }
@@ -446,6 +477,7 @@ int orb_extract_batch_async(orb_ctx* c, const uint8_t* imgs, int nimg, int w, in
     }
     if (!c->done_stream) ORB_CUDA(cudaStreamCreateWithFlags(&c->done_stream, cudaStreamNonBlocking));
     *t.h_status = 0;
+    t.staged = false;
     int launches = 0;
     if (empty) {                                   // empty image: no keypoints (src/ORBextractor.cc:721-722)
         if (dev_out) { if (nimg) ORB_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * nimg, c->streams[0])); }
@@ -461,12 +493,31 @@ int orb_extract_batch_async(orb_ctx* c, const uint8_t* imgs, int nimg, int w, in
         int rc = prepare(c, w, h);
         if (rc != ORB_OK) return rc;
         const int B = std::min(nimg, c->max_batch);
+        // A call of a few frames into PAGEABLE output buffers (std::vector / cv::Mat of the reference's call site): three copies into
+        // pageable memory are three blocking, driver-staged transfers after the kernels; instead the slot's results form one device
+        // block that returns in ONE copy to pinned staging owned by the ticket, and orb_wait hands the valid rows to the caller.
+        size_t stage_bytes = 0;
+        if (c->stage_small && !dev_out && nimg <= B && nimg <= c->small_call_frames) {
+            cudaPointerAttributes pa;
+            if (cudaPointerGetAttributes(&pa, kps) == cudaSuccess && pa.type == cudaMemoryTypeUnregistered)
+                stage_bytes = (size_t)nimg * cap * (sizeof(orb_keypoint) + 32) + (size_t)nimg * sizeof(int32_t);
+            else cudaGetLastError();
+        }
+        if (stage_bytes) {
+            if (t.stage_bytes < stage_bytes) {
+                if (t.h_stage) { cudaFreeHost(t.h_stage); t.h_stage = nullptr; t.stage_bytes = 0; }
+                ORB_CUDA(cudaMallocHost((void**)&t.h_stage, stage_bytes));
+                t.stage_bytes = stage_bytes;
+            }
+            t.staged = true; t.u_kps = kps; t.u_desc = desc;
+        }
         if ((rc = prepare_ws(c, c->ws[0], B))) return rc;
         if ((nimg > B || !idle || c->chunk_parity) && (rc = prepare_ws(c, c->ws[1], B))) return rc;
         const size_t src_chunk = (size_t)B * frame_pitch;
         for (int i = 0; i < 2; i++) {
             if (!dev_in) { rc = ensure(c->d_src[i], c->src_bytes[i], src_chunk); if (rc) return rc; }
-            if (!dev_out) {
+            if (stage_bytes) { rc = ensure(c->d_small[i], c->small_bytes[i], stage_bytes); if (rc) return rc; }
+            else if (!dev_out) {
                 rc = ensure(c->d_kps[i], c->kps_bytes[i], (size_t)B * cap * sizeof(orb_keypoint)); if (rc) return rc;
                 rc = ensure(c->d_desc[i], c->desc_bytes[i], (size_t)B * cap * 32); if (rc) return rc;
                 rc = ensure(c->d_counts[i], c->counts_bytes[i], (size_t)B * sizeof(int32_t)); if (rc) return rc;
@@ -489,6 +540,11 @@ int orb_extract_batch_async(orb_ctx* c, const uint8_t* imgs, int nimg, int w, in
             orb_keypoint* o_k = dev_out ? kps + (size_t)f0 * cap : c->d_kps[slot];
             uint8_t* o_d = dev_out ? desc + (size_t)f0 * cap * 32 : c->d_desc[slot];
             int32_t* o_c = dev_out ? counts + f0 : c->d_counts[slot];
+            if (stage_bytes) {            // one chunk (nimg <= B): [keypoints | descriptors | counts]
+                o_k = reinterpret_cast<orb_keypoint*>(c->d_small[slot]);
+                o_d = c->d_small[slot] + (size_t)nimg * cap * sizeof(orb_keypoint);
+                o_c = reinterpret_cast<int32_t*>(o_d + (size_t)nimg * cap * 32);
+            }
             // a slot owns its staging and work buffers; stream order alone protects their reuse two chunks later.
             // Kernels of neighbouring LARGE chunks are chained (ORB_CHAIN_CHUNKS, default on): persistent grids of two streams that
             // become co-resident only steal each other's SMs, while the copies on either side still overlap freely.  Measured on
@@ -498,7 +554,7 @@ int orb_extract_batch_async(orb_ctx* c, const uint8_t* imgs, int nimg, int w, in
             // the slot's output staging buffers are still being copied out by the chunk two back (its D2H runs on the slot's OUT
             // stream, below): the kernels wait for that copy, the H2D copy above did not have to
             if (!dev_out && c->out_pending[slot]) ORB_CUDA(cudaStreamWaitEvent(s, c->ev_out_done[slot], 0));
-            rc = launch_extract(c, c->ws[slot], d_in, n, w, h, stride, frame_pitch, o_k, o_d, cap, o_c, s);
+            rc = launch_extract(c, c->ws[slot], d_in, n, w, h, stride, frame_pitch, o_k, o_d, cap, o_c, s, !dev_in);
             if (rc != ORB_OK) return rc;
             launches += c->last_launches;
             ORB_CUDA(cudaEventRecord(c->ev_free[slot], s));
@@ -509,9 +565,12 @@ int orb_extract_batch_async(orb_ctx* c, const uint8_t* imgs, int nimg, int w, in
                 // 1024 frames of 640x480: round 2, 148.6 K -> see DESIGN.md)
                 cudaStream_t os = c->out_streams[slot];
                 ORB_CUDA(cudaStreamWaitEvent(os, c->ev_free[slot], 0));
+                if (stage_bytes) ORB_CUDA(cudaMemcpyAsync(t.h_stage, c->d_small[slot], stage_bytes, cudaMemcpyDeviceToHost, os));
+                else {
                 ORB_CUDA(cudaMemcpyAsync(kps + (size_t)f0 * cap, o_k, (size_t)n * cap * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, os));
                 ORB_CUDA(cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, o_d, (size_t)n * cap * 32, cudaMemcpyDeviceToHost, os));
                 ORB_CUDA(cudaMemcpyAsync(counts + f0, o_c, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, os));
+                }
                 ORB_CUDA(cudaEventRecord(c->ev_out_done[slot], os));
                 c->out_pending[slot] = true;
             }

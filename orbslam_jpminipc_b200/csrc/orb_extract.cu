@@ -54,6 +54,14 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
                  ::"r"(smem_addr(dst)), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(smem_addr(bar)) : "memory");
 }
 
+// PDL (launch_k below): let the dependent grid start scheduling, then wait until the prerequisite grid has completed and its memory is
+// visible.  First statement of every kernel of the pass: all pipeline data is touched behind it; a no-op without the launch attribute.
+__device__ __forceinline__ void pdl_sync()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ K0
 // Level 0: copy the caller's image into the ROI of the padded plane (the 16-px reflect-101 frame
 // of every level is written afterwards by k_border).  4 pixels per thread.
@@ -61,6 +69,7 @@ __global__ void __launch_bounds__(256)
 k_level0(const uint8_t* __restrict__ src, int w, int h, int sstride, size_t spitch, int aligned4,
          uint8_t* __restrict__ planes, size_t fbytes, int pstride)
 {
+    pdl_sync();
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int f = blockIdx.z;
@@ -82,6 +91,7 @@ k_level0(const uint8_t* __restrict__ src, int w, int h, int sstride, size_t spit
 __global__ void __launch_bounds__(256)
 k_level0_v16(const uint8_t* __restrict__ src, int w, int h, int sstride, size_t spitch, uint8_t* __restrict__ planes, size_t fbytes, int pstride)
 {
+    pdl_sync();
     const int x16 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int f = blockIdx.z;
@@ -105,6 +115,7 @@ k_resize(const __grid_constant__ CUtensorMap tm, uint8_t* __restrict__ planes, s
          const int2* __restrict__ xtab, const int2* __restrict__ ytab, int box_w, int box_h, int buf_bytes,
          int nimg, int* __restrict__ work_counter, int RT_W, int RS_ROWS)
 {
+    pdl_sync();
     extern __shared__ __align__(128) uint8_t rs_sm[];       // two source tiles of buf_bytes each
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ int s_next[2];
@@ -238,6 +249,7 @@ k_resize_u(const __grid_constant__ CUtensorMap tm, uint8_t* __restrict__ planes,
            const uint4* __restrict__ xgrp, const int2* __restrict__ ytab, int box_w, int box_h, int buf_bytes,
            int nimg, int* __restrict__ work_counter, int RT_W)
 {
+    pdl_sync();
     extern __shared__ __align__(128) uint8_t rs_sm[];       // two source tiles of buf_bytes each
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ int s_next[2];
@@ -354,6 +366,7 @@ k_pyramid(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ planes, size
           const __grid_constant__ PyrParams P, const int2* __restrict__ xtab, const int2* __restrict__ ytab,
           int* __restrict__ work_counter, int* __restrict__ done)
 {
+    pdl_sync();
     extern __shared__ __align__(128) uint8_t rs_sm[];       // two source tiles of buf_bytes each
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ int s_next[2];
@@ -524,6 +537,7 @@ k_pyramid(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ planes, size
 __global__ void __launch_bounds__(256)
 k_border(uint8_t* __restrict__ planes, uint8_t* __restrict__ blurred, size_t fbytes, const Plan* __restrict__ plan)
 {
+    pdl_sync();
     // blockIdx.y = frame * nlevels + level; blockIdx.x walks the level's frame words (levels with fewer words exit).  Two words per
     // thread, both fetched before either is stored: the kernel is bound by load latency, not by instructions.
     const int l = blockIdx.y % plan->nlevels, f = blockIdx.y / plan->nlevels;
@@ -750,6 +764,7 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
            const Plan* __restrict__ plan, const Tile* __restrict__ tiles, int ntiles, int total, int* __restrict__ work_counter,
            const uint8_t* __restrict__ coltab, const int16_t* __restrict__ rowtab)
 {
+    pdl_sync();
     __shared__ __align__(128) uint32_t img2[ETILE ? 1 : 2][(FI_H * FIW + 31) & ~31];      // each buffer 128-byte aligned (TMA destination) for any tile height
     __shared__ __align__(16) uint32_t et[ETILE ? FI_H * EW : 4];
     __shared__ int s_next[2], s_ti[2], s_fr[2];             // next work item; tile index and frame of the item in each buffer
@@ -1132,6 +1147,7 @@ __global__ void __launch_bounds__(256, 8)      // 32 registers (20 bytes spilled
 k_cell_compact(const uint8_t* __restrict__ nms, const uint8_t* __restrict__ bitmap, size_t fbytes, const Plan* __restrict__ plan,
                const CellGeom* __restrict__ cells, uint32_t* __restrict__ cand, int* __restrict__ ntotal)
 {
+    pdl_sync();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= plan->ncells) return;
     const int f = blockIdx.y;
@@ -1200,6 +1216,124 @@ k_cell_compact(const uint8_t* __restrict__ nms, const uint8_t* __restrict__ bitm
     if (lane == 0) ntotal[(size_t)f * plan->ncells + warp] = count;
 }
 
+// Calls of a few frames (single-frame latency): one CTA per (frame, cell) instead of one warp.  A warp's serial walk over a whole
+// cell — a dependent bitmap load, then a dependent response load per survivor, per 32-word step — was 21 of the 116 us of one 640x480
+// frame.  Here the eight warps take an eighth of the cell's rows each and build their part of the list in shared memory; the
+// per-warp counts of survivors at fastTh and at 7 then give every warp its place in the cell's list (raster order = warp order), and
+// the fallback rule (:609-614) is applied while the parts are written out.  A part that overflows its segment (more than CCW_SEG
+// survivors in an eighth of a cell) sends the cell to the serial walk of the batch kernel, done by warp 0.
+constexpr int CCW_SEG = 512;
+__global__ void __launch_bounds__(256, 2)
+k_cell_compact_wide(const uint8_t* __restrict__ nms, const uint8_t* __restrict__ bitmap, size_t fbytes, const Plan* __restrict__ plan,
+                    const CellGeom* __restrict__ cells, uint32_t* __restrict__ cand, int* __restrict__ ntotal)
+{
+    pdl_sync();
+    __shared__ uint32_t seg[8][CCW_SEG];
+    __shared__ int s_cnt[8], s_nP[8], s_n7[8];
+    const int cell = blockIdx.x, f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const CellGeom g = cells[cell];
+    const LevelGeom& L = plan->L[g.level];
+    const uint8_t* map = nms + (size_t)f * fbytes + L.plane_off + (size_t)ORB_EDGE * L.stride + ORB_EDGE;
+    const uint32_t* bm = reinterpret_cast<const uint32_t*>(bitmap + (size_t)f * plan->bm_total + L.bm_off);
+    uint32_t* out = cand + (size_t)f * plan->cand_total + g.cand_off;
+    const int thP = plan->fast_th;
+    const int b0 = g.x0 - ORB_EDGE, b1 = g.x1 - ORB_EDGE;            // bit range [b0, b1) of a bitmap row
+    const int w0 = b0 >> 5, wpr = b1 > b0 ? ((b1 - 1) >> 5) - w0 + 1 : 0;
+    const int pitchw = L.bm_pitch >> 2;
+    const uint32_t lt = (1u << lane) - 1;
+    auto walk = [&](int ya, int yb, auto put) {                      // rows [ya, yb) in raster order; returns (count, nP, n7) summed over the warp
+        int count = 0, nP = 0, n7 = 0;
+        const int nitems = max(yb - ya, 0) * wpr;
+        for (int i0 = 0; i0 < nitems; i0 += 32) {
+            const int i = i0 + lane;
+            uint32_t word = 0;
+            int y = 0, xbase = 0;
+            if (i < nitems) {
+                const int rr = i / wpr, wi = i - rr * wpr;
+                y = ya + rr;
+                word = bm[(size_t)(y - ORB_EDGE) * pitchw + w0 + wi];
+                const int bit0 = (w0 + wi) << 5;
+                if (bit0 < b0) word &= 0xffffffffu << (b0 - bit0);
+                if (bit0 + 32 > b1) word &= 0xffffffffu >> (bit0 + 32 - b1);
+                xbase = bit0 + ORB_EDGE;
+            }
+            const int cnt = __popc(word);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int tv = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += tv; }
+            int pos = count + incl - cnt;
+            const uint8_t* row = map + (size_t)y * L.stride;
+            while (word) {
+                const int b = __ffs(word) - 1;
+                word &= word - 1;
+                const int x = xbase + b;
+                const uint32_t s = row[x];
+                nP += (int)s >= thP;
+                n7 += s >= 7;
+                put(pos++, (s << 24) | ((uint32_t)(y - g.iniy) << 12) | (uint32_t)(x - g.inix));
+            }
+            count += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        nP = __reduce_add_sync(0xffffffffu, nP);
+        n7 = __reduce_add_sync(0xffffffffu, n7);
+        return make_int3(count, nP, n7);
+    };
+    const int rows = g.y1 - g.y0, rpw = (rows + 7) >> 3;
+    {
+        const int ya = g.y0 + warp * rpw, yb = min(ya + rpw, g.y1);
+        uint32_t* sg = seg[warp];
+        const int3 r = walk(ya, yb, [&](int pos, uint32_t rec) { if (pos < CCW_SEG) sg[pos] = rec; });
+        if (lane == 0) { s_cnt[warp] = r.x; s_nP[warp] = r.y; s_n7[warp] = r.z; }
+    }
+    __syncthreads();
+    int nP = 0, n7 = 0, before = 0;
+    bool overflow = false;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { nP += s_nP[k]; n7 += s_n7[k]; overflow |= s_cnt[k] > CCW_SEG; }
+    const bool useP = nP > 3;
+    const int thr = useP ? thP : 7;
+    if (overflow) {                   // the batch kernel's walk and in-place fallback filter, by one warp
+        if (warp != 0) return;
+        const int3 r = walk(g.y0, g.y1, [&](int pos, uint32_t rec) { out[pos] = rec; });
+        int count = r.x;
+        const int want = useP ? r.y : r.z;
+        if (want < count) {
+            __syncwarp();
+            int w = 0;
+            for (int b = 0; b < count; b += 32) {
+                const int i = b + lane;
+                const uint32_t rec = i < count ? out[i] : 0u;
+                const bool k = i < count && (int)(rec >> 24) >= thr;
+                const uint32_t m = __ballot_sync(0xffffffffu, k);
+                __syncwarp();
+                if (k) out[w + __popc(m & lt)] = rec;
+                w += __popc(m);
+                __syncwarp();
+            }
+            count = w;
+        }
+        if (lane == 0) ntotal[(size_t)f * plan->ncells + cell] = count;
+        return;
+    }
+    // every record with a response >= thr stays (all of them when none is weaker: the serial form's want == count)
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (k < warp) before += useP ? s_nP[k] : s_n7[k];
+    {
+        const uint32_t* sg = seg[warp];
+        const int n = s_cnt[warp];
+        int w = before;
+        for (int b = 0; b < n; b += 32) {
+            const int i = b + lane;
+            const uint32_t rec = i < n ? sg[i] : 0u;
+            const bool k = i < n && (int)(rec >> 24) >= thr;
+            const uint32_t m = __ballot_sync(0xffffffffu, k);
+            if (k) out[w + __popc(m & lt)] = rec;
+            w += __popc(m);
+        }
+    }
+    if (threadIdx.x == 0) ntotal[(size_t)f * plan->ncells + cell] = useP ? nP : n7;
+}
+
 // ------------------------------------------------------------------ K4
 // One CTA per (frame, level).  Thread 0 replays the quota redistribution loop (:622-670); every
 // cell then runs retainBest (= libstdc++ introselect, first n survivors, see introselect.h) on
@@ -1215,6 +1349,7 @@ __global__ void __launch_bounds__(256)
 k_harris(const uint8_t* __restrict__ planes, size_t fbytes, const Plan* __restrict__ plan, const CellGeom* __restrict__ cells,
          const uint32_t* __restrict__ cand, const int* __restrict__ ntotal, unsigned long long* __restrict__ cand64)
 {
+    pdl_sync();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= plan->ncells) return;
     const int f = blockIdx.y;
@@ -1258,7 +1393,7 @@ constexpr int SEL_WCAP = 512;       // candidates one warp stages in shared memo
 #define ORB_SEL_WARPS 8
 #define ORB_SEL_SERIAL_BELOW 8
 #endif
-constexpr int SEL_WARPS = ORB_SEL_WARPS, SEL_SERIAL_BELOW = ORB_SEL_SERIAL_BELOW;   // below that range length lane 0 finishes alone
+constexpr int SEL_WARPS = ORB_SEL_WARPS, SEL_WARPS_WIDE = 32, SEL_SERIAL_BELOW = ORB_SEL_SERIAL_BELOW;   // below that range length lane 0 finishes alone
 
 template <typename T, typename C>
 __device__ __forceinline__ int warp_partition(T* v, int first, int last, C lt, unsigned short* scratch, int lane)
@@ -1323,13 +1458,16 @@ __device__ __forceinline__ void warp_nth_element(T* v, int n, int nth, C lt, uns
 }
 
 // Selection: CTA per (frame, level), warp per cell.  HARRIS: 64-bit records (float response | position) in global memory.
-template <bool HARRIS>
-__global__ void __launch_bounds__(SEL_WARPS * 32)
+// WARPS: 8 for batches (seven CTAs per SM stay resident); WARPS_WIDE for a handful of frames, where the (frame, level) CTAs do
+// not fill the machine and the kernel's time is the serial walk of one CTA's warps over the level's cells (single-frame latency).
+template <bool HARRIS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 k_select_fast(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells, uint32_t* __restrict__ cand,
               unsigned long long* __restrict__ cand64, const int* __restrict__ ntotal,
               unsigned long long* __restrict__ lvl, int* __restrict__ nkept, int* __restrict__ status, uint8_t* __restrict__ spare, size_t fbytes)
 {
-    // sel_list_cap u64 | SEL_WARPS x SEL_WCAP u32 | SEL_WARPS x SEL_WCAP u16 | per-cell tables sized for the plan's largest grid
+    pdl_sync();
+    // sel_list_cap u64 | WARPS x SEL_WCAP u32 | WARPS x SEL_WCAP u16 | per-cell tables sized for the plan's largest grid
     // (sel_cells_cap: static arrays of ORB_MAX_CELLS_LEVEL entries cost 1 % of the whole pipeline in residency next to k_blur)
     extern __shared__ unsigned long long s_list[];
     const int level = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1338,9 +1476,9 @@ k_select_fast(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells,
     const CellGeom* cg = cells + L.cell_base;
     const int* nt = ntotal + (size_t)f * plan->ncells + L.cell_base;
     uint32_t* s_wbuf = reinterpret_cast<uint32_t*>(s_list + plan->sel_list_cap);
-    unsigned short* s_scr = reinterpret_cast<unsigned short*>(s_wbuf + SEL_WARPS * SEL_WCAP);
+    unsigned short* s_scr = reinterpret_cast<unsigned short*>(s_wbuf + WARPS * SEL_WCAP);
     const int ccap = plan->sel_cells_cap;                      // multiple of 4
-    int* s_total = reinterpret_cast<int*>(s_scr + SEL_WARPS * SEL_WCAP);
+    int* s_total = reinterpret_cast<int*>(s_scr + WARPS * SEL_WCAP);
     int* s_retain = s_total + ccap;
     int* s_off = s_retain + ccap;                              // ccap + 4 entries
     unsigned char* noMore = reinterpret_cast<unsigned char*>(s_off + ccap + 4);
@@ -1377,7 +1515,7 @@ k_select_fast(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells,
     unsigned long long* gbase64 = HARRIS ? cand64 + (size_t)f * plan->cand_total : nullptr;
     const orbsel::KeyGreater<uint32_t, 24> lt32;
     const orbsel::FloatKeyGreater64 ltf;
-    for (int c = warp; c < nCells; c += SEL_WARPS) {           // retainBest per cell (:683-685)
+    for (int c = warp; c < nCells; c += WARPS) {           // retainBest per cell (:683-685)
         const int n = s_total[c], keep = s_retain[c];
         if (keep <= 0) continue;
         const int ix = cg[c].inix, iy = cg[c].iniy;
@@ -1423,7 +1561,7 @@ k_select_fast(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells,
     if (total > L.nDesired) {                                  // retainBest per level (:697-701)
         const orbsel::KeyGreater<unsigned long long, 32> lt64;
         if (warp == 0) {
-            if (total <= SEL_WARPS * SEL_WCAP) {
+            if (total <= WARPS * SEL_WCAP) {
                 if (HARRIS) warp_nth_element(s_list, total, L.nDesired - 1, ltf, s_scr, lane);
                 else warp_nth_element(s_list, total, L.nDesired - 1, lt64, s_scr, lane);
             } else if (lane == 0) {
@@ -1445,6 +1583,7 @@ k_select(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells, uint
          unsigned long long* __restrict__ cand64, const int* __restrict__ ntotal, unsigned long long* __restrict__ lvl,
          int* __restrict__ nkept, int* __restrict__ status)
 {
+    pdl_sync();
     extern __shared__ unsigned long long s_list[];            // lvl_cap records, then SEL_STAGE u32 records
     __shared__ int s_total[ORB_MAX_CELLS_LEVEL], s_retain[ORB_MAX_CELLS_LEVEL], s_off[ORB_MAX_CELLS_LEVEL + 1];
     __shared__ int s_coff[ORB_MAX_CELLS_LEVEL + 1];
@@ -1567,6 +1706,7 @@ __global__ void __launch_bounds__(BLUR_THREADS)
 k_blur(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ blurred, size_t fbytes,
        const Plan* __restrict__ plan, const Tile* __restrict__ tiles, int ntiles, int total, int* __restrict__ work_counter)
 {
+    pdl_sync();
     __shared__ __align__(128) uint8_t img2[2][BI_BUF];
     __shared__ __align__(16) float rowp[BI_H * BT_W];
     __shared__ __align__(8) uint64_t bar[2];
@@ -1732,6 +1872,7 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
            const Plan* __restrict__ plan, const unsigned long long* __restrict__ lvl, const int* __restrict__ nkept,
            orb_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int cap, int32_t* __restrict__ counts)
 {
+    pdl_sync();
     const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.y;
     const int nl = plan->nlevels;
@@ -1841,6 +1982,23 @@ int orb_upload_constants(const int* umax)
     return ORB_OK;
 }
 
+// Every kernel of the pass is launched with programmatic stream serialization (PDL): a kernel signals griddepcontrol.launch_dependents
+// at its top, so the NEXT kernel's CTAs are scheduled as soon as all CTAs of this one have started and SM resources free up, run their
+// prologue and park in griddepcontrol.wait until this grid has completed and its memory is visible.  Stream-order semantics are
+// unchanged (every access to pipeline data sits behind the wait); what disappears is the launch latency between dependent kernels:
+// the 14 launches of ONE frame cost about 4.7 us each, of which about half is launch.  ORB_PDL=0 switches it off (A/B timing).
+template <typename... KArgs, typename... Args>
+static inline void launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(std::forward<Args>(args))...);      // errors surface in cudaGetLastError at the end of the pass
+}
+
 #ifdef ORB_DEBUG
 #define ORB_SKIP(bit) (c->debug_skip & (bit))
 #else
@@ -1852,6 +2010,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
     const Plan& P = c->plan;
     const size_t fb = (size_t)P.frame_bytes;
     int launches = 0;
+    const bool pdl = c->pdl_call && !c->profile;      // chosen per call (orb_api.cu launch_extract): batches lose 1.6 % to parked CTAs (160.3 -> 157.8 K frames/s at 1024 frames)
     const dim3 blk(64, 4);
     auto mark = [&]() {           // stage boundary event (profiling mode only)
         if (!c->profile) return;
@@ -1871,12 +2030,13 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         const bool aligned16 = ((((uintptr_t)d_imgs | (uintptr_t)stride | (uintptr_t)frame_pitch | (uintptr_t)w) & 15) == 0) && (L.stride & 15) == 0 &&
                                (L.plane_off & 15) == 0 && (fb & 15) == 0 && ((uintptr_t)W.d_planes & 15) == 0;
         if (aligned16)
-            k_level0_v16<<<dim3((w / 16 + 15) / 16, (h + 15) / 16, nimg), dim3(16, 16), 0, s>>>(d_imgs, w, h, stride, frame_pitch, W.d_planes, fb, L.stride);
+            launch_k(pdl, k_level0_v16, dim3((w / 16 + 15) / 16, (h + 15) / 16, nimg), dim3(16, 16), 0, s, d_imgs, w, h, stride, frame_pitch, W.d_planes, fb, L.stride);
         else
-            k_level0<<<grid, blk, 0, s>>>(d_imgs, w, h, stride, frame_pitch, aligned4, W.d_planes, fb, L.stride);
+            launch_k(pdl, k_level0, grid, blk, 0, s, d_imgs, w, h, stride, frame_pitch, aligned4, W.d_planes, fb, L.stride);
         launches++;
     }
     mark();
+    const int rv = nimg <= c->small_call_frames ? 1 : 0;      // tiling of the resize cascade: calls of a few frames take the short tiles
     if (c->pyr_fused && P.nlevels > 1) {
         PyrParams Q;
         memset(&Q, 0, sizeof Q);
@@ -1884,37 +2044,44 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         int total = 0, bufb = 1024;
         for (int l = 1; l < P.nlevels; l++) {
             const LevelGeom& D = P.L[l];
-            const int tw = c->rs_tile_w[l], rr = c->rs_rows[l], th = (4 * ORB_RESIZE_THREADS / tw) * rr;
-            Q.L[l].tile_w = tw; Q.L[l].rows = rr; Q.L[l].box_w = c->rs_box_w[l]; Q.L[l].box_h = c->rs_box_h[l];
+            const int tw = c->rs_tile_w[rv][l], rr = c->rs_rows[rv][l], th = (4 * ORB_RESIZE_THREADS / tw) * rr;
+            Q.L[l].tile_w = tw; Q.L[l].rows = rr; Q.L[l].box_w = c->rs_box_w[rv][l]; Q.L[l].box_h = c->rs_box_h[rv][l];
             Q.L[l].tiles_x = (D.w + tw - 1) / tw;
             Q.L[l].ntiles = Q.L[l].tiles_x * ((D.h + th - 1) / th);
             Q.L[l].item_base = total;
             total += Q.L[l].ntiles * nimg;
-            bufb = std::max(bufb, (c->rs_box_w[l] * c->rs_box_h[l] + 127) & ~127);
+            bufb = std::max(bufb, (c->rs_box_w[rv][l] * c->rs_box_h[rv][l] + 127) & ~127);
         }
         Q.total = total; Q.buf_bytes = bufb;
         const int grid = std::min(total, c->num_sms * ORB_RESIZE_CTAS);
-        k_pyramid<<<grid, ORB_RESIZE_THREADS, 2 * bufb + 16, s>>>(W.tm_resize, W.d_planes, fb, c->d_plan, Q, c->d_xtab, c->d_ytab,
+        launch_k(pdl, k_pyramid, grid, ORB_RESIZE_THREADS, 2 * bufb + 16, s, W.tm_resize[rv], W.d_planes, fb, c->d_plan, Q, c->d_xtab, c->d_ytab,
                                                                   W.d_counters + 4, W.d_counters + 32);
         launches++;
     } else
     for (int l = 1; l < P.nlevels; l++) {
         const LevelGeom& D = P.L[l];
-        const int tw = c->rs_tile_w[l], rr = c->rs_rows[l], th = (4 * ORB_RESIZE_THREADS / tw) * rr;
+        const int tw = c->rs_tile_w[rv][l], rr = c->rs_rows[rv][l], th = (4 * ORB_RESIZE_THREADS / tw) * rr;
         const int tiles = ((D.w + tw - 1) / tw) * ((D.h + th - 1) / th) * nimg;
-        const int bufb = (c->rs_box_w[l] * c->rs_box_h[l] + 127) & ~127;
+        const int bufb = (c->rs_box_w[rv][l] * c->rs_box_h[rv][l] + 127) & ~127;
         const int grid = std::min(tiles, c->num_sms * ORB_RESIZE_CTAS);
-        if (c->rs_unrolled && c->rs_packed[l] && rr == 8)
-            k_resize_u<8><<<grid, ORB_RESIZE_THREADS, 2 * bufb + 16, s>>>(W.tm_resize.m[l], W.d_planes, fb, D, reinterpret_cast<const uint4*>(c->d_xtab + c->rs_xg_off[l]),
-                                                                        c->d_ytab, c->rs_box_w[l], c->rs_box_h[l], bufb, nimg, W.d_counters + 4 + l, tw);
+        const bool unrolled = c->rs_unrolled && c->rs_packed[l];
+        if (unrolled && rr == 2)
+            launch_k(pdl, k_resize_u<2>, grid, ORB_RESIZE_THREADS, 2 * bufb + 16, s, W.tm_resize[rv].m[l], W.d_planes, fb, D, reinterpret_cast<const uint4*>(c->d_xtab + c->rs_xg_off[l]),
+                                                                        c->d_ytab, c->rs_box_w[rv][l], c->rs_box_h[rv][l], bufb, nimg, W.d_counters + 4 + l, tw);
+        else if (unrolled && rr == 4)
+            launch_k(pdl, k_resize_u<4>, grid, ORB_RESIZE_THREADS, 2 * bufb + 16, s, W.tm_resize[rv].m[l], W.d_planes, fb, D, reinterpret_cast<const uint4*>(c->d_xtab + c->rs_xg_off[l]),
+                                                                        c->d_ytab, c->rs_box_w[rv][l], c->rs_box_h[rv][l], bufb, nimg, W.d_counters + 4 + l, tw);
+        else if (unrolled && rr == 8)
+            launch_k(pdl, k_resize_u<8>, grid, ORB_RESIZE_THREADS, 2 * bufb + 16, s, W.tm_resize[rv].m[l], W.d_planes, fb, D, reinterpret_cast<const uint4*>(c->d_xtab + c->rs_xg_off[l]),
+                                                                        c->d_ytab, c->rs_box_w[rv][l], c->rs_box_h[rv][l], bufb, nimg, W.d_counters + 4 + l, tw);
         else
-        k_resize<<<grid, ORB_RESIZE_THREADS, 2 * bufb + 16, s>>>(W.tm_resize.m[l], W.d_planes, fb, D, c->d_xtab, c->d_ytab, c->rs_box_w[l], c->rs_box_h[l],
+        launch_k(pdl, k_resize, grid, ORB_RESIZE_THREADS, 2 * bufb + 16, s, W.tm_resize[rv].m[l], W.d_planes, fb, D, c->d_xtab, c->d_ytab, c->rs_box_w[rv][l], c->rs_box_h[rv][l],
                                                bufb, nimg, W.d_counters + 4 + l, tw, rr);
         launches++;
     }
     int border_max = 1;                 // a small level with the whole 16 px frame may hold more ring words than level 0 with its 4 px ring
     for (int l = 0; l < P.nlevels; l++) border_max = std::max(border_max, P.L[l].border_items);
-    k_border<<<dim3((border_max + 511) / 512, nimg * P.nlevels), 256, 0, s>>>(W.d_planes, W.d_blur, fb, c->d_plan);
+    launch_k(pdl, k_border, dim3((border_max + 511) / 512, nimg * P.nlevels), 256, 0, s, W.d_planes, W.d_blur, fb, c->d_plan);
     launches++;
     // k_blur only needs the finished pyramid: outside profiling mode it runs on a second stream,
     // concurrently with FAST -> compaction -> selection (the selection kernel is latency bound and
@@ -1926,7 +2093,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
 #endif
         const int total = P.ntiles_blur * nimg;
         const int grid = std::min(total, c->num_sms * c->blur_ctas);
-        k_blur<<<grid, BLUR_THREADS, 0, bs>>>(W.tm_blur, W.d_blur, fb, c->d_plan, c->d_tiles_blur, P.ntiles_blur, total, W.d_counters + 2);
+        launch_k(false, k_blur, grid, BLUR_THREADS, 0, bs, W.tm_blur, W.d_blur, fb, c->d_plan, c->d_tiles_blur, P.ntiles_blur, total, W.d_counters + 2);
     };
     if (fork && c->fork_early == 1) {          // blur next to FAST: FAST saturates the ALU pipe and leaves the FMA pipe idle
         ORB_CUDA(cudaEventRecord(W.ev_fork, s));
@@ -1937,10 +2104,10 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         const int total = P.ntiles_fast * nimg;
         const int grid = std::min(total, c->num_sms * (fork && c->fork_early == 1 ? c->fast_ctas : FAST_CTAS));
         if (c->fast_etile)
-            k_fast_nms<true><<<grid, FAST_THREADS, 0, s>>>(W.tm_fast, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total, W.d_counters + 1,
+            launch_k(pdl, k_fast_nms<true>, grid, FAST_THREADS, 0, s, W.tm_fast, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total, W.d_counters + 1,
                                                            c->d_fast_coltab, c->d_fast_rowtab);
         else
-            k_fast_nms<false><<<grid, FAST_THREADS, 0, s>>>(W.tm_fast, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total, W.d_counters + 1,
+            launch_k(pdl, k_fast_nms<false>, grid, FAST_THREADS, 0, s, W.tm_fast, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total, W.d_counters + 1,
                                                             c->d_fast_coltab, c->d_fast_rowtab);
     }
     if (fork && c->fork_early == 2) {     // blur starts behind FAST, next to compaction + selection
@@ -1949,27 +2116,38 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
     }
     if (fork && (c->fork_early == 1 || c->fork_early == 2)) { launch_blur(W.aux_stream); ORB_CUDA(cudaEventRecord(W.ev_join, W.aux_stream)); }
     mark();
-    k_cell_compact<<<dim3((P.ncells + 7) / 8, nimg), 256, 0, s>>>(W.d_work, W.d_bitmap, fb, c->d_plan, c->d_cells, W.d_cand, W.d_ntotal);
+    if (c->compact_wide && nimg <= c->small_call_frames)
+        launch_k(pdl, k_cell_compact_wide, dim3(P.ncells, nimg), 256, 0, s, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_cells, W.d_cand, W.d_ntotal);
+    else
+    launch_k(pdl, k_cell_compact, dim3((P.ncells + 7) / 8, nimg), 256, 0, s, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_cells, W.d_cand, W.d_ntotal);
     if (fork && (c->fork_early == 0 || c->fork_early == 3)) {          // blur starts when compaction is done, i.e. next to the selection kernel
         ORB_CUDA(cudaEventRecord(W.ev_fork, s));
         ORB_CUDA(cudaStreamWaitEvent(W.aux_stream, W.ev_fork, 0));
         if (c->fork_early == 0) { launch_blur(W.aux_stream); ORB_CUDA(cudaEventRecord(W.ev_join, W.aux_stream)); }
     }
     mark();
-    const size_t sel_smem = (size_t)P.sel_list_cap * 8 + (size_t)SEL_WARPS * SEL_WCAP * 6 + (size_t)P.sel_cells_cap * 13 + 16;
+    // a handful of frames: 32 warps per (frame, level) CTA instead of 8 (one cell per warp in one trip; k_select was 36 of the 130 us of a
+    // single 640x480 frame), as long as the CTAs still fit the machine in one wave and the wider staging area fits its shared memory
+    auto sel_bytes = [&](int warps) { return (size_t)P.sel_list_cap * 8 + (size_t)warps * SEL_WCAP * 6 + (size_t)P.sel_cells_cap * 13 + 16; };
+    const bool sel_wide = c->select_wide && nimg * P.nlevels <= c->num_sms && sel_bytes(SEL_WARPS_WIDE) + 1024 <= 227 * 1024;
+    const size_t sel_smem = sel_bytes(sel_wide ? SEL_WARPS_WIDE : SEL_WARPS);
     uint8_t* sel_spare = (size_t)P.cand_total * 2 <= fb ? W.d_work : nullptr;
     if (P.harris) {
-        k_harris<<<dim3((P.ncells + 7) / 8, nimg), 256, 0, s>>>(W.d_planes, fb, c->d_plan, c->d_cells, W.d_cand, W.d_ntotal, W.d_cand64);
+        launch_k(pdl, k_harris, dim3((P.ncells + 7) / 8, nimg), 256, 0, s, W.d_planes, fb, c->d_plan, c->d_cells, W.d_cand, W.d_ntotal, W.d_cand64);
         if (c->select_serial)
-            k_select<true><<<dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s>>>(c->d_plan, c->d_cells, W.d_cand, W.d_cand64, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status);
+            launch_k(pdl, k_select<true>, dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s, c->d_plan, c->d_cells, W.d_cand, W.d_cand64, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status);
+        else if (sel_wide)
+            launch_k(pdl, k_select_fast<true, SEL_WARPS_WIDE>, dim3(P.nlevels, nimg), SEL_WARPS_WIDE * 32, sel_smem, s, c->d_plan, c->d_cells, W.d_cand, W.d_cand64, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status, sel_spare, fb);
         else
-            k_select_fast<true><<<dim3(P.nlevels, nimg), SEL_WARPS * 32, sel_smem, s>>>(c->d_plan, c->d_cells, W.d_cand, W.d_cand64, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status, sel_spare, fb);
+            launch_k(pdl, k_select_fast<true, SEL_WARPS>, dim3(P.nlevels, nimg), SEL_WARPS * 32, sel_smem, s, c->d_plan, c->d_cells, W.d_cand, W.d_cand64, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status, sel_spare, fb);
         launches++;
     } else if (!ORB_SKIP(2)) {
         if (c->select_serial)
-            k_select<false><<<dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s>>>(c->d_plan, c->d_cells, W.d_cand, nullptr, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status);
+            launch_k(pdl, k_select<false>, dim3(P.nlevels, nimg), 128, (size_t)P.sel_list_cap * 8 + SEL_STAGE * 4, s, c->d_plan, c->d_cells, W.d_cand, nullptr, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status);
+        else if (sel_wide)
+            launch_k(pdl, k_select_fast<false, SEL_WARPS_WIDE>, dim3(P.nlevels, nimg), SEL_WARPS_WIDE * 32, sel_smem, s, c->d_plan, c->d_cells, W.d_cand, nullptr, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status, sel_spare, fb);
         else
-            k_select_fast<false><<<dim3(P.nlevels, nimg), SEL_WARPS * 32, sel_smem, s>>>(c->d_plan, c->d_cells, W.d_cand, nullptr, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status, sel_spare, fb);
+            launch_k(pdl, k_select_fast<false, SEL_WARPS>, dim3(P.nlevels, nimg), SEL_WARPS * 32, sel_smem, s, c->d_plan, c->d_cells, W.d_cand, nullptr, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status, sel_spare, fb);
     }
     if (fork && c->fork_early == 3) {      // selection first: the latency-bound kernel takes the residency it needs, blur fills the rest
         launch_blur(W.aux_stream);
@@ -1980,7 +2158,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
     else launch_blur(s);
     mark();
     const int slots = std::min(cap, P.kp_cap);
-    if (!ORB_SKIP(4)) k_describe<<<dim3((std::max(slots, 1) + 7) / 8, nimg), 256, 0, s>>>(W.d_planes, W.d_blur, fb, c->d_plan, W.d_lvl, W.d_nkept,
+    if (!ORB_SKIP(4)) launch_k(pdl, k_describe, dim3((std::max(slots, 1) + 7) / 8, nimg), 256, 0, s, W.d_planes, W.d_blur, fb, c->d_plan, W.d_lvl, W.d_nkept,
                                                                     d_kps, d_desc, cap, d_counts);
     mark();
     launches += 5;
@@ -1994,7 +2172,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
 static int raise_dyn_smem(const void* fn, int slot, int bytes)
 {
     static std::mutex mu;
-    static int cur[7][64] = {};
+    static int cur[11][64] = {};
     int dev = 0;
     ORB_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(mu);
@@ -2009,6 +2187,8 @@ int orb_resize_smem_setup(int max_bytes)
     static_assert(sizeof(PyrParams) <= 1024, "k_pyramid parameter block");
     int rc = raise_dyn_smem((const void*)k_resize, 0, max_bytes);
     if (!rc) rc = raise_dyn_smem((const void*)k_resize_u<8>, 6, max_bytes);
+    if (!rc) rc = raise_dyn_smem((const void*)k_resize_u<4>, 9, max_bytes);
+    if (!rc) rc = raise_dyn_smem((const void*)k_resize_u<2>, 10, max_bytes);
     return rc ? rc : raise_dyn_smem((const void*)k_pyramid, 5, max_bytes);
 }
 
@@ -2017,6 +2197,12 @@ int orb_select_smem_setup(int list_cap, int cells_cap)     // the largest per-le
     const int serial = list_cap * 8 + SEL_STAGE * 4 + 1024, fast = list_cap * 8 + SEL_WARPS * SEL_WCAP * 6 + cells_cap * 13 + 1024;
     int rc = raise_dyn_smem((const void*)k_select<false>, 1, serial);
     if (!rc) rc = raise_dyn_smem((const void*)k_select<true>, 2, serial);
-    if (!rc) rc = raise_dyn_smem((const void*)k_select_fast<true>, 4, fast);
-    return rc ? rc : raise_dyn_smem((const void*)k_select_fast<false>, 3, fast);
+    if (!rc) rc = raise_dyn_smem((const void*)k_select_fast<true, SEL_WARPS>, 4, fast);
+    if (!rc) rc = raise_dyn_smem((const void*)k_select_fast<false, SEL_WARPS>, 3, fast);
+    const int wide = fast + (SEL_WARPS_WIDE - SEL_WARPS) * SEL_WCAP * 6;
+    if (wide <= 227 * 1024) {
+        if (!rc) rc = raise_dyn_smem((const void*)k_select_fast<true, SEL_WARPS_WIDE>, 7, wide);
+        if (!rc) rc = raise_dyn_smem((const void*)k_select_fast<false, SEL_WARPS_WIDE>, 8, wide);
+    }
+    return rc;
 }

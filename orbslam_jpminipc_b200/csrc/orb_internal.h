@@ -101,7 +101,7 @@ struct WorkSet {
     unsigned long long* d_lvl = nullptr; size_t lvl_bytes = 0;
     int* d_nkept = nullptr;       size_t nkept_bytes = 0;
     int* d_counters = nullptr;    size_t counters_bytes = 0;   // dynamic tile-queue counters (32 ints)
-    TmapSet tm_fast{}, tm_blur{}, tm_resize{};                 // boxes: FAST tile / blur tile / resize source footprint (map l reads level l-1)
+    TmapSet tm_fast{}, tm_blur{}, tm_resize[2]{};              // boxes: FAST tile / blur tile / resize source footprint (map l reads level l-1; [1] = the small-call tiling)
     const uint8_t* tm_base = nullptr; int tm_frames = 0, tm_w = 0, tm_h = 0;
     cudaStream_t aux_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // CUDA-graph replay of one extraction pass (orb_api.cu, launch_extract): captured the second time the same call shape and
@@ -154,8 +154,10 @@ struct orb_ctx {
     std::vector<int2> xtab, ytab;
     std::vector<uint8_t> fast_coltab;      // per level: in-region / left / right byte masks of every column (k_fast_nms)
     std::vector<int16_t> fast_rowtab;      // per level: detection-cell row of every row
-    int rs_box_w[ORB_MAX_LEVELS] = { 0 }, rs_box_h[ORB_MAX_LEVELS] = { 0 };   // k_resize TMA box (source footprint of one output tile)
-    int rs_tile_w[ORB_MAX_LEVELS] = { 0 }, rs_rows[ORB_MAX_LEVELS] = { 0 };   // k_resize tile width / rows per thread
+    // two tilings of the resize cascade: [0] for batches (8 rows per thread), [1] for calls of a few frames (rs_rows_small rows per
+    // thread: more, shorter CTAs — the seven dependent launches of ONE frame are bound by the run time of a single tile)
+    int rs_box_w[2][ORB_MAX_LEVELS] = { { 0 } }, rs_box_h[2][ORB_MAX_LEVELS] = { { 0 } };   // k_resize TMA box (source footprint of one output tile)
+    int rs_tile_w[2][ORB_MAX_LEVELS] = { { 0 } }, rs_rows[2][ORB_MAX_LEVELS] = { { 0 } };   // k_resize tile width / rows per thread
 
     // device tables (shared by both work sets)
     Plan* d_plan = nullptr;
@@ -174,7 +176,11 @@ struct orb_ctx {
     // asynchronous host-buffer calls (orb_extract_batch_async / orb_wait): a ring of completion records
     static constexpr int NTICKETS = 8;
     struct Ticket { cudaEvent_t done = nullptr, a = nullptr, b = nullptr; int* h_status = nullptr; int32_t* counts = nullptr;
-                    int nimg = 0, cap = 0; long long seq = -1; bool host_out = false; };
+                    int nimg = 0, cap = 0; long long seq = -1; bool host_out = false;
+                    // small call into pageable output buffers: the results come back as ONE block into pinned staging and orb_wait copies
+                    // counts[i] rows per frame to the caller (three copies into pageable memory are three blocking, staged transfers)
+                    uint8_t* h_stage = nullptr; size_t stage_bytes = 0; bool staged = false;
+                    orb_keypoint* u_kps = nullptr; uint8_t* u_desc = nullptr; };
     Ticket tickets[NTICKETS];
     cudaStream_t done_stream = nullptr;
     long long next_seq = 0, waited_seq = -1;   // tickets issued / highest ticket known complete
@@ -187,6 +193,8 @@ struct orb_ctx {
     orb_keypoint* d_kps[2] = { nullptr, nullptr };
     uint8_t* d_desc[2] = { nullptr, nullptr };
     int32_t* d_counts[2] = { nullptr, nullptr };
+    uint8_t* d_small[2] = { nullptr, nullptr };  size_t small_bytes[2] = { 0, 0 };   // [keypoints | descriptors | counts] of a staged small call
+    int stage_small = 1;                                   // ORB_STAGE_SMALL=0: always copy straight into the caller's buffers (A/B timing)
     cudaStream_t streams[2] = { nullptr, nullptr };
     cudaStream_t out_streams[2] = { nullptr, nullptr };   // device->host copies of a slot's results (host-buffer calls)
     cudaEvent_t ev_out_done[2] = { nullptr, nullptr };
@@ -197,7 +205,12 @@ struct orb_ctx {
     int split_device = 0;
     int desc_fma = 0;                                      // orb_set_descriptor_fma
     int debug_skip = 0;                                    // ORB_DEBUG_SKIP, honoured only by a -DORB_DEBUG build (timing experiments, results are wrong): 1 no blur, 2 no selection, 4 no describe
+    bool pdl_call = false;                                 // this call's kernels carry the PDL launch attribute (set by launch_extract)
+    int use_pdl = 1, pdl_frames = 4;                       // ORB_PDL=0: plain stream-ordered launches (A/B timing); ORB_PDL_FRAMES: largest call launched with PDL
+    int compact_wide = 1;                                  // ORB_COMPACT_WIDE=0: k_cell_compact (warp per cell) for small calls too (A/B timing)
+    int select_wide = 1;                                   // ORB_SELECT_WIDE=0: k_select_fast keeps 8 warps per CTA for small calls too (A/B timing)
     int rs_flex_width = 1;                                 // ORB_RESIZE_FLEX=0: fixed 128-column k_resize tiles (A/B timing)
+    int rs_rows_small = 2, small_call_frames = 4;          // ORB_RESIZE_ROWS_SMALL / ORB_SMALL_CALL: tiling [1] for calls of at most that many frames (0 = never)
     int rs_rows_pref = 8;                                  // ORB_RESIZE_ROWS: output rows per k_resize thread (tile height = 8 * rows at 128 columns)
     int fast_etile = 1;                                    // ORB_FAST_ETILE=0: k_fast_nms<false> (ring samples by PRMT from the raw tile) instead of the half-lane tile (A/B timing)
     int rs_unrolled = 1;                                   // ORB_RESIZE_UNROLLED=0: k_resize for every level instead of k_resize_u (A/B timing)

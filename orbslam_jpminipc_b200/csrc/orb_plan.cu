@@ -107,7 +107,7 @@ int orb_build_plan(orb_ctx* c, int w, int h)
             // A thread owns 4 columns x rr rows, a CTA tw columns x (1024 / tw) * rr rows.  Among the tile widths 64..128 the one
             // that leaves the fewest idle threads on this level's size wins (a fixed 128 wastes 18 % of the lanes on a 522-wide
             // level); 64x64 tiles with 4 rows per thread remain the fallback for scale factors whose footprint is too large.
-            auto try_tile = [&](int tw, int rr) {
+            auto try_tile = [&](int v, int tw, int rr) {
                 const int th = (4 * ORB_RESIZE_THREADS / tw) * rr;
                 int mw = 16, mr = 1;
                 for (int x0 = 0; x0 < L.w; x0 += tw) {
@@ -119,23 +119,26 @@ int orb_build_plan(orb_ctx* c, int w, int h)
                     const int y1 = std::min(y0 + th, L.h) - 1;
                     mr = std::max(mr, (c->ytab[L.ytab_off + y1].x >> 16) - (c->ytab[L.ytab_off + y0].x & 0xffff) + 1);
                 }
-                c->rs_box_w[l] = (mw + 15) & ~15; c->rs_box_h[l] = mr; c->rs_tile_w[l] = tw; c->rs_rows[l] = rr;
-                return c->rs_box_w[l] <= 256 && mr <= 256;
+                c->rs_box_w[v][l] = (mw + 15) & ~15; c->rs_box_h[v][l] = mr; c->rs_tile_w[v][l] = tw; c->rs_rows[v][l] = rr;
+                return c->rs_box_w[v][l] <= 256 && mr <= 256;
             };
-            int best_tw = 128;
-            if (c->rs_flex_width) {
-                double best = -1;
-                for (int tw = 64; tw <= 128; tw += 4) {
-                    const int th = (4 * ORB_RESIZE_THREADS / tw) * c->rs_rows_pref;
-                    const double ctas = (double)((L.w + tw - 1) / tw) * ((L.h + th - 1) / th);
-                    const double eff = (double)L.w * L.h / (ctas * ORB_RESIZE_THREADS * 4 * c->rs_rows_pref);
-                    if (eff >= best) { best = eff; best_tw = tw; }
+            for (int v = 0; v < 2; v++) {
+                const int rows_pref = v == 0 ? c->rs_rows_pref : std::min(c->rs_rows_small, c->rs_rows_pref);
+                int best_tw = 128;
+                if (c->rs_flex_width) {
+                    double best = -1;
+                    for (int tw = 64; tw <= 128; tw += 4) {
+                        const int th = (4 * ORB_RESIZE_THREADS / tw) * rows_pref;
+                        const double ctas = (double)((L.w + tw - 1) / tw) * ((L.h + th - 1) / th);
+                        const double eff = (double)L.w * L.h / (ctas * ORB_RESIZE_THREADS * 4 * rows_pref);
+                        if (eff >= best) { best = eff; best_tw = tw; }
+                    }
                 }
+                bool fits = try_tile(v, best_tw, rows_pref);
+                if (!fits && best_tw != 128) fits = try_tile(v, 128, rows_pref);
+                if (!fits) fits = try_tile(v, 64, std::min(4, rows_pref));
+                if (!fits) return ORB_ERR_CAPACITY;      // scale factors above ~3.7
             }
-            bool fits = try_tile(best_tw, c->rs_rows_pref);
-            if (!fits && best_tw != 128) fits = try_tile(128, c->rs_rows_pref);
-            if (!fits) fits = try_tile(64, 4);
-            if (!fits) return ORB_ERR_CAPACITY;      // scale factors above ~3.7
             // k_resize_u: per 4-column group the first source byte, the PRMT selectors of the four columns' tap pairs (byte offsets from
             // that first byte, low nibble = tap 0, high nibble = tap 1; two selectors per word) and the four weight pairs
             while (c->xtab.size() & 3) c->xtab.push_back(make_int2(0, 0));        // 32-byte aligned groups
