@@ -115,7 +115,7 @@ static int prepare(orb_ctx* c, int w, int h)
         ORB_CUDA(cudaMemcpy(c->d_fast_rowtab, c->fast_rowtab.data(), c->fast_rowtab.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
         int maxcap = 0;
         for (int l = 0; l < c->plan.nlevels; l++) maxcap = std::max(maxcap, c->plan.L[l].lvl_cap);
-        if ((size_t)maxcap * 8 + (size_t)c->plan.sel_cells_cap * 13 > 170 * 1024) return ORB_ERR_CAPACITY;
+        if ((size_t)maxcap * 8 + (size_t)c->plan.sel_cells_cap * 14 > 170 * 1024) return ORB_ERR_CAPACITY;
         rc = orb_select_smem_setup(maxcap, c->plan.sel_cells_cap); if (rc) return rc;
         size_t rsm = 1024;
         for (int v = 0; v < 2; v++)
@@ -158,17 +158,15 @@ static int prepare_ws(orb_ctx* c, WorkSet& W, int nimg)
 // time it comes by and replayed afterwards.  Not used on the legacy default stream (capture is not allowed there), in profiling mode,
 // or for large batches, where launch cost is noise.
 static int launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_in, int n, int w, int h, int stride, size_t pitch,
-                          orb_keypoint* o_k, uint8_t* o_d, int cap, int32_t* o_c, cudaStream_t s, bool host_in = false)
+                          orb_keypoint* o_k, uint8_t* o_d, int cap, int32_t* o_c, cudaStream_t s)
 {
-    // Calls of at most pdl_frames frames whose input is already on the device are launched with programmatic dependent launch instead
-    // (orb_extract.cu, launch_k).  Measured on B200 for one 640x480 frame, blocking call, microseconds, graph replay | PDL launches:
-    // device in / device out 113 | 94, device in / pinned out 127 | 110; but pinned in / device out 102 | 107, pinned in / pinned out
-    // 123 | 129, pageable both 136 | 138 — behind a host-to-device copy the single submission of a graph wins, because the host then
-    // enqueues the whole pass while the copy is still in flight.  Both together are slower than either (a replayed graph with
-    // programmatic edges: 157 / 146 us pageable / pinned against 146 / 135), so it is one or the other.
-    const bool pdl = c->use_pdl && n <= c->pdl_frames && !host_in;
-    c->pdl_call = pdl;
-    const bool eligible = c->use_graph && !pdl && !c->profile && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread &&
+    // Calls of at most pdl_frames frames also carry programmatic dependent launch edges (orb_extract.cu, launch_k), in the captured graph
+    // as well as in plain launches.  Measured on B200 for one 640x480 frame through the blocking call, microseconds, pageable / pinned
+    // / device buffers: graph replay alone 136 / 123 / 113, PDL launches alone 119 / 112 / 80, both 116 / 112 / 82.  (While the pass
+    // still began with a memset node the combination was SLOWER than either, 157 / 146: a programmatic edge behind a memset node
+    // costs a replayed graph more than all the edges gain — the counters are now cleared by the pass's first kernel.)
+    c->pdl_call = c->use_pdl && n <= c->pdl_frames;
+    const bool eligible = c->use_graph && !c->profile && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread &&
                           (double)n * w * h <= 12e6;
     if (!eligible) return orb_launch_extract(c, W, d_in, n, w, h, stride, pitch, o_k, o_d, cap, o_c, s);
     WorkSet::GraphKey key;
@@ -256,6 +254,7 @@ orb_ctx* orb_create(int device, int nfeatures, float scale_factor, int nlevels, 
     if (const char* e = getenv("ORB_SELECT_SERIAL")) c->select_serial = atoi(e);
     if (const char* e = getenv("ORB_SELECT_WIDE")) c->select_wide = atoi(e);
     if (const char* e = getenv("ORB_COMPACT_WIDE")) c->compact_wide = atoi(e);
+    if (const char* e = getenv("ORB_FAST_WIDE")) c->fast_wide = atoi(e);
     if (const char* e = getenv("ORB_PDL")) c->use_pdl = atoi(e);
     if (const char* e = getenv("ORB_PDL_FRAMES")) c->pdl_frames = std::max(0, atoi(e));
     if (const char* e = getenv("ORB_STAGE_SMALL")) c->stage_small = atoi(e);
@@ -554,7 +553,7 @@ int orb_extract_batch_async(orb_ctx* c, const uint8_t* imgs, int nimg, int w, in
             // the slot's output staging buffers are still being copied out by the chunk two back (its D2H runs on the slot's OUT
             // stream, below): the kernels wait for that copy, the H2D copy above did not have to
             if (!dev_out && c->out_pending[slot]) ORB_CUDA(cudaStreamWaitEvent(s, c->ev_out_done[slot], 0));
-            rc = launch_extract(c, c->ws[slot], d_in, n, w, h, stride, frame_pitch, o_k, o_d, cap, o_c, s, !dev_in);
+            rc = launch_extract(c, c->ws[slot], d_in, n, w, h, stride, frame_pitch, o_k, o_d, cap, o_c, s);
             if (rc != ORB_OK) return rc;
             launches += c->last_launches;
             ORB_CUDA(cudaEventRecord(c->ev_free[slot], s));

@@ -62,14 +62,27 @@ __device__ __forceinline__ void pdl_sync()
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// The tile queues of the later kernels (32 counters) and k_pyramid's per-(frame, level) completion counters start every pass at zero:
+// the first kernel of the pass clears them (first block of every frame) instead of a memset node in front of it — one dependent node
+// fewer per pass, and a pass that consists of kernels only.
+__device__ __forceinline__ void zero_counters(int* __restrict__ counters)
+{
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+        const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+        if (blockIdx.z == 0 && tid < 32) counters[tid] = 0;
+        if (tid < ORB_MAX_LEVELS) counters[32 + blockIdx.z * ORB_MAX_LEVELS + tid] = 0;
+    }
+}
+
 // ------------------------------------------------------------------ K0
 // Level 0: copy the caller's image into the ROI of the padded plane (the 16-px reflect-101 frame
 // of every level is written afterwards by k_border).  4 pixels per thread.
 __global__ void __launch_bounds__(256)
 k_level0(const uint8_t* __restrict__ src, int w, int h, int sstride, size_t spitch, int aligned4,
-         uint8_t* __restrict__ planes, size_t fbytes, int pstride)
+         uint8_t* __restrict__ planes, size_t fbytes, int pstride, int* __restrict__ counters)
 {
     pdl_sync();
+    zero_counters(counters);
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int f = blockIdx.z;
@@ -89,9 +102,11 @@ k_level0(const uint8_t* __restrict__ src, int w, int h, int sstride, size_t spit
 // the same copy, 16 bytes per thread, for sources whose base, row stride, frame pitch and width are multiples of 16 (640, 752, 1280,
 // 1920 ... wide frames): a quarter of the loads in flight per byte moved
 __global__ void __launch_bounds__(256)
-k_level0_v16(const uint8_t* __restrict__ src, int w, int h, int sstride, size_t spitch, uint8_t* __restrict__ planes, size_t fbytes, int pstride)
+k_level0_v16(const uint8_t* __restrict__ src, int w, int h, int sstride, size_t spitch, uint8_t* __restrict__ planes, size_t fbytes, int pstride,
+             int* __restrict__ counters)
 {
     pdl_sync();
+    zero_counters(counters);
     const int x16 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int f = blockIdx.z;
@@ -622,7 +637,7 @@ constexpr int FSW = FT_W / 4 + 2, FS_H = FT_H + 2;   // score tile: cols x0-4..x
 #define ORB_FAST_THREADS 128      // measured on B200: 320x3 1.75 ms, 256x4 1.56, 128x8 1.46, 64x16 1.43 per 256 frames
 #define ORB_FAST_CTAS 8
 #endif
-constexpr int FAST_THREADS = ORB_FAST_THREADS, FAST_CTAS = ORB_FAST_CTAS;
+constexpr int FAST_THREADS = ORB_FAST_THREADS, FAST_CTAS = ORB_FAST_CTAS, FAST_THREADS_SMALL = 512;
 
 __device__ __forceinline__ uint32_t lo16x2(uint32_t w) { return __byte_perm(w, 0, 0x4140); }   // bytes 0,1 -> u16 lanes
 __device__ __forceinline__ uint32_t hi16x2(uint32_t w) { return __byte_perm(w, 0, 0x4342); }   // bytes 2,3 -> u16 lanes
@@ -758,8 +773,10 @@ __device__ __forceinline__ void arc_minmax_h(const uint32_t (&r)[16], uint32_t& 
 // memory instead of out of an instruction.  The raw tile is then dead (the halo pass, which still reads it, runs before the score
 // pass), so ONE raw buffer suffices: the next item's TMA copy is issued after the re-encoding and lands during the score pass.
 constexpr int EW = FT_W / 2 + 4;        // 32-bit words per row of the half-lane tile (72 pixels)
-template <bool ETILE>
-__global__ void __launch_bounds__(FAST_THREADS, ETILE ? 5 : 6)      // residency is set by shared memory (42.6 / 36.1 KB per CTA), so the register cap may follow it
+// THREADS: 128 for batches; FAST_THREADS_SMALL for calls of a few frames, where every SM holds at most ONE tile and a tile's time is
+// the issue latency of the four warps that walk it (16.7 of the 115 us of one 640x480 frame)
+template <bool ETILE, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == FAST_THREADS ? (ETILE ? 5 : 6) : 1)      // residency is set by shared memory (42.6 / 36.1 KB per CTA), so the register cap may follow it
 k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_t* __restrict__ bitmap, size_t fbytes,
            const Plan* __restrict__ plan, const Tile* __restrict__ tiles, int ntiles, int total, int* __restrict__ work_counter,
            const uint8_t* __restrict__ coltab, const int16_t* __restrict__ rowtab)
@@ -821,7 +838,7 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
             const uint32_t* ct = reinterpret_cast<const uint32_t*>(coltab + L.ct_off) + (t.x0 >> 2);     // column x0 - 4 is entry x0
             const int16_t* rt = rowtab + L.rt_off + t.y0;                                                // row y0 - 1 is entry y0
             const int ctw = L.ct_len >> 2;
-            for (int i = tid; i < 3 * FSW + FS_H; i += FAST_THREADS) {
+            for (int i = tid; i < 3 * FSW + FS_H; i += THREADS) {
                 if (i < 3 * FSW) {
                     const int a = i / FSW;
                     mask3[i] = __ldg(ct + a * ctw + (i - a * FSW));
@@ -845,7 +862,7 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
         auto score_pass = [&](auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
         const int ntask = FULL ? FS_H * (FT_W / 4) : nr * nwi;
-        for (int task = tid; task < ntask; task += FAST_THREADS) {
+        for (int task = tid; task < ntask; task += THREADS) {
             const int r = FULL ? task / (FT_W / 4) : (int)(((uint32_t)(task >> 2) * inv_nq) >> 20), g = task - r * (FULL ? FT_W / 4 : nwi) + 1;
             const uint32_t cm = FULL ? 0xffffffffu : reinterpret_cast<const uint32_t*>(m_in)[g];   // every column of a full tile is a detection column
             uint32_t outw = 0;
@@ -978,7 +995,7 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
         auto halo_pass = [&](auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
         const int nrh = FULL ? FS_H : nr, gr = (FULL ? FT_W / 4 : nwi) + 1;
-        for (int r = tid; r < nrh; r += FAST_THREADS) {
+        for (int r = tid; r < nrh; r += THREADS) {
             const uint32_t mL = m_in[3], mR = m_in[4 * gr];
             uint32_t sL = 0, sR = 0;
             if (rowcell[r] >= 0 && (mL | mR) != 0) {
@@ -1014,7 +1031,7 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
             // thread = (raw word column, row residue): no index arithmetic per word, compile-time row offsets (the flat form with a
             // division per word was 7 % of the kernel's instructions)
             {
-                constexpr int EC = EW / 2, ER = FAST_THREADS / EC;          // 18 word columns, 7 rows per pass
+                constexpr int EC = EW / 2, ER = THREADS / EC;          // 18 word columns, 7 rows per pass
                 if (tid < EC * ER) {
                     const int er0 = tid / EC, ej = tid - er0 * EC;
                     const uint32_t* src = img + er0 * FIW + 3 + ej;
@@ -1043,7 +1060,7 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
         auto nms_pass = [&](auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
         const int ntask = FULL ? FT_H * (FT_W / 16) : vh * nq;
-        for (int task = tid; task < ntask; task += FAST_THREADS) {
+        for (int task = tid; task < ntask; task += THREADS) {
             const int ro = FULL ? task / (FT_W / 16) : (int)(((uint32_t)task * inv_nq) >> 20), q4 = task - ro * (FULL ? FT_W / 16 : nq);
             const int r = ro + 1;
             const int rc = rowcell[r];
@@ -1482,31 +1499,50 @@ k_select_fast(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells,
     int* s_retain = s_total + ccap;
     int* s_off = s_retain + ccap;                              // ccap + 4 entries
     unsigned char* noMore = reinterpret_cast<unsigned char*>(s_off + ccap + 4);
-    for (int c = tid; c < nCells; c += blockDim.x) s_total[c] = nt[c];
+    unsigned char* s_skip = noMore + ccap;                     // cg[c].skipped, fetched by all threads: thread 0's quota loop below would pay one global-load latency per cell
+    for (int c = tid; c < nCells; c += blockDim.x) { s_total[c] = nt[c]; s_skip[c] = (unsigned char)(cg[c].skipped != 0); }
     __syncthreads();
-    if (tid == 0) {                                            // quota redistribution, src/ORBextractor.cc:622-670
+    if (warp == 0) {                                           // quota redistribution, src/ORBextractor.cc:622-670
+        // by one WARP: every pass of the reference's loop treats the cells independently of each other given nNew, and what it carries
+        // from pass to pass are two integer sums — so the lanes take the cells and the sums are warp reductions (a single thread pays a
+        // shared-memory round trip per step: 5-9 us of the 24 us this kernel took for one frame)
         const int nfc = L.nfCell;
         int nNoMore = 0, nToDistribute = 0;
-        for (int c = 0; c < nCells; c++) {
-            noMore[c] = 0; s_retain[c] = 0;
-            if (cg[c].skipped) continue;                       // stays open with nTotal = 0
-            const int nKeys = s_total[c];
-            if (nKeys > nfc) { s_retain[c] = nfc; }
-            else { s_retain[c] = nKeys; nToDistribute += nfc - nKeys; noMore[c] = 1; nNoMore++; }
+        for (int c = lane; c < nCells; c += 32) {
+            int ret = 0; unsigned char nm = 0;
+            if (!s_skip[c]) {                                  // a skipped cell stays open with nTotal = 0
+                const int nKeys = s_total[c];
+                if (nKeys > nfc) ret = nfc;
+                else { ret = nKeys; nToDistribute += nfc - nKeys; nm = 1; nNoMore++; }
+            }
+            s_retain[c] = ret; noMore[c] = nm;
         }
+        nNoMore = __reduce_add_sync(0xffffffffu, nNoMore); nToDistribute = __reduce_add_sync(0xffffffffu, nToDistribute);
         while (nToDistribute > 0 && nNoMore < nCells) {
             const int nNew = nfc + (int)ceilf(__fdiv_rn((float)nToDistribute, (float)(nCells - nNoMore)));
-            nToDistribute = 0;
-            for (int c = 0; c < nCells; c++) {
+            int d = 0, m = 0;
+            for (int c = lane; c < nCells; c += 32) {
                 if (noMore[c]) continue;
-                if (s_total[c] > nNew) s_retain[c] = nNew;
-                else { s_retain[c] = s_total[c]; nToDistribute += nNew - s_total[c]; noMore[c] = 1; nNoMore++; }
+                const int nt_c = s_total[c];
+                if (nt_c > nNew) s_retain[c] = nNew;
+                else { s_retain[c] = nt_c; d += nNew - nt_c; noMore[c] = 1; m++; }
             }
+            nToDistribute = __reduce_add_sync(0xffffffffu, d); nNoMore += __reduce_add_sync(0xffffffffu, m);
         }
+        __syncwarp();
         int o = 0;
-        for (int c = 0; c < nCells; c++) { s_off[c] = o; o += s_retain[c]; }
-        s_off[nCells] = o;
-        if (o > L.lvl_cap) { atomicExch(status, ORB_ERR_CAPACITY); s_off[nCells] = -1; }
+        for (int c0 = 0; c0 < nCells; c0 += 32) {              // exclusive prefix of the quotas in cell order
+            const int c = c0 + lane, v = c < nCells ? s_retain[c] : 0;
+            int incl = v;
+#pragma unroll
+            for (int k = 1; k < 32; k <<= 1) { const int tv = __shfl_up_sync(0xffffffffu, incl, k); if (lane >= k) incl += tv; }
+            if (c < nCells) s_off[c] = o + incl - v;
+            o += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) {
+            s_off[nCells] = o;
+            if (o > L.lvl_cap) { atomicExch(status, ORB_ERR_CAPACITY); s_off[nCells] = -1; }
+        }
     }
     __syncthreads();
     int total = s_off[nCells];
@@ -2020,8 +2056,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         cudaEventRecord(e, s);
         c->prof_events.push_back(e);
     };
-    // every tile queue of this pass (FAST 1, blur 2, resize 4+l) and the per-(frame, level) completion counters of k_pyramid in one node
-    ORB_CUDA(cudaMemsetAsync(W.d_counters, 0, (32 + (size_t)nimg * ORB_MAX_LEVELS) * sizeof(int), s));
+    // every tile queue of this pass (FAST 1, blur 2, resize 4+l) and the per-(frame, level) completion counters of k_pyramid are cleared by k_level0
     mark();
     {
         const LevelGeom& L = P.L[0];
@@ -2030,9 +2065,9 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         const bool aligned16 = ((((uintptr_t)d_imgs | (uintptr_t)stride | (uintptr_t)frame_pitch | (uintptr_t)w) & 15) == 0) && (L.stride & 15) == 0 &&
                                (L.plane_off & 15) == 0 && (fb & 15) == 0 && ((uintptr_t)W.d_planes & 15) == 0;
         if (aligned16)
-            launch_k(pdl, k_level0_v16, dim3((w / 16 + 15) / 16, (h + 15) / 16, nimg), dim3(16, 16), 0, s, d_imgs, w, h, stride, frame_pitch, W.d_planes, fb, L.stride);
+            launch_k(pdl, k_level0_v16, dim3((w / 16 + 15) / 16, (h + 15) / 16, nimg), dim3(16, 16), 0, s, d_imgs, w, h, stride, frame_pitch, W.d_planes, fb, L.stride, W.d_counters);
         else
-            launch_k(pdl, k_level0, grid, blk, 0, s, d_imgs, w, h, stride, frame_pitch, aligned4, W.d_planes, fb, L.stride);
+            launch_k(pdl, k_level0, grid, blk, 0, s, d_imgs, w, h, stride, frame_pitch, aligned4, W.d_planes, fb, L.stride, W.d_counters);
         launches++;
     }
     mark();
@@ -2103,12 +2138,15 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
     {
         const int total = P.ntiles_fast * nimg;
         const int grid = std::min(total, c->num_sms * (fork && c->fork_early == 1 ? c->fast_ctas : FAST_CTAS));
-        if (c->fast_etile)
-            launch_k(pdl, k_fast_nms<true>, grid, FAST_THREADS, 0, s, W.tm_fast, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total, W.d_counters + 1,
-                                                           c->d_fast_coltab, c->d_fast_rowtab);
+        if (c->fast_etile && c->fast_wide && nimg <= c->small_call_frames)
+            launch_k(pdl, k_fast_nms<true, FAST_THREADS_SMALL>, std::min(total, c->num_sms), FAST_THREADS_SMALL, 0, s, W.tm_fast, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total,
+                     W.d_counters + 1, c->d_fast_coltab, c->d_fast_rowtab);
+        else if (c->fast_etile)
+            launch_k(pdl, k_fast_nms<true, FAST_THREADS>, grid, FAST_THREADS, 0, s, W.tm_fast, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total, W.d_counters + 1,
+                     c->d_fast_coltab, c->d_fast_rowtab);
         else
-            launch_k(pdl, k_fast_nms<false>, grid, FAST_THREADS, 0, s, W.tm_fast, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total, W.d_counters + 1,
-                                                            c->d_fast_coltab, c->d_fast_rowtab);
+            launch_k(pdl, k_fast_nms<false, FAST_THREADS>, grid, FAST_THREADS, 0, s, W.tm_fast, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total, W.d_counters + 1,
+                     c->d_fast_coltab, c->d_fast_rowtab);
     }
     if (fork && c->fork_early == 2) {     // blur starts behind FAST, next to compaction + selection
         ORB_CUDA(cudaEventRecord(W.ev_fork, s));
@@ -2128,7 +2166,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
     mark();
     // a handful of frames: 32 warps per (frame, level) CTA instead of 8 (one cell per warp in one trip; k_select was 36 of the 130 us of a
     // single 640x480 frame), as long as the CTAs still fit the machine in one wave and the wider staging area fits its shared memory
-    auto sel_bytes = [&](int warps) { return (size_t)P.sel_list_cap * 8 + (size_t)warps * SEL_WCAP * 6 + (size_t)P.sel_cells_cap * 13 + 16; };
+    auto sel_bytes = [&](int warps) { return (size_t)P.sel_list_cap * 8 + (size_t)warps * SEL_WCAP * 6 + (size_t)P.sel_cells_cap * 14 + 16; };
     const bool sel_wide = c->select_wide && nimg * P.nlevels <= c->num_sms && sel_bytes(SEL_WARPS_WIDE) + 1024 <= 227 * 1024;
     const size_t sel_smem = sel_bytes(sel_wide ? SEL_WARPS_WIDE : SEL_WARPS);
     uint8_t* sel_spare = (size_t)P.cand_total * 2 <= fb ? W.d_work : nullptr;
@@ -2194,7 +2232,7 @@ int orb_resize_smem_setup(int max_bytes)
 
 int orb_select_smem_setup(int list_cap, int cells_cap)     // the largest per-level keypoint list (u64 records) and cell grid of the plan
 {
-    const int serial = list_cap * 8 + SEL_STAGE * 4 + 1024, fast = list_cap * 8 + SEL_WARPS * SEL_WCAP * 6 + cells_cap * 13 + 1024;
+    const int serial = list_cap * 8 + SEL_STAGE * 4 + 1024, fast = list_cap * 8 + SEL_WARPS * SEL_WCAP * 6 + cells_cap * 14 + 1024;
     int rc = raise_dyn_smem((const void*)k_select<false>, 1, serial);
     if (!rc) rc = raise_dyn_smem((const void*)k_select<true>, 2, serial);
     if (!rc) rc = raise_dyn_smem((const void*)k_select_fast<true, SEL_WARPS>, 4, fast);
