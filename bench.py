@@ -731,23 +731,49 @@ def run_tracking_extras(E, matching):
     return cpu
 
 
-def frame_latency(E, base, w, h, graph):
+SMALL_CALL_OFF = {"ORB_SMALL_CALL": "0", "ORB_SELECT_WIDE": "0", "ORB_COMPACT_WIDE": "0", "ORB_FAST_WIDE": "0", "ORB_PDL": "0", "ORB_STAGE_SMALL": "0"}
+
+
+def frame_latency(E, base, w, h):
+    """Blocking single-frame calls (what the reference does once per camera frame, src/Frame.cc:60) through orb_extract: pageable and
+    pinned host buffers, the library's default against the same call with every small-call form switched off (the batch kernels and
+    launch scheme, i.e. where the round started); the variants are measured in interleaved rounds."""
+    import torch
     import orbslam_jpminipc_b200 as pkg
-    old = os.environ.get("ORB_GRAPH")
-    os.environ["ORB_GRAPH"] = "1" if graph else "0"
-    ex1 = pkg.ORBextractor(NFEAT, SCALE, NLEVELS, 1, FAST_TH, device=E.local, max_width=w, max_height=h, max_batch=1)
-    if old is None:
-        del os.environ["ORB_GRAPH"]
-    else:
-        os.environ["ORB_GRAPH"] = old
-    for i in range(10):
-        ex1(base[i % len(base)])
-    ts = []
-    for i in range(200):
-        t0 = time.perf_counter()
-        ex1(base[i % len(base)])
-        ts.append(time.perf_counter() - t0)
-    return {"median_ms": float(np.median(ts) * 1e3), "p90_ms": float(np.percentile(ts, 90) * 1e3)}
+    from orbslam_jpminipc_b200._lib import check, lib, ptr
+    L = lib()
+
+    def ctx(env):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            return pkg.ORBextractor(NFEAT, SCALE, NLEVELS, 1, FAST_TH, device=E.local, max_width=w, max_height=h, max_batch=1)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+
+    exs = {"default": ctx({}), "small_call_forms_off": ctx(SMALL_CALL_OFF)}
+    cap = exs["default"].capacity
+    n = C.c_int(0)
+    bufs = {"pageable": (np.stack(base[:8]), np.zeros(cap, pkg.KP_DTYPE), np.zeros((cap, 32), np.uint8)),
+            "pinned": (torch.from_numpy(np.stack(base[:8])).pin_memory(), torch.zeros((cap, 7), dtype=torch.int32).pin_memory(),
+                       torch.zeros((cap, 32), dtype=torch.uint8).pin_memory())}
+    T = {(a, b): [] for a in exs for b in bufs}
+    for rnd in range(5):
+        for a, ex in exs.items():
+            for b, (fr, k, d) in bufs.items():
+                for i in range(48):
+                    t0 = time.perf_counter()
+                    check(L.orb_extract(ex._h, ptr(fr[i % 8]), w, h, w, ptr(k), ptr(d), cap, C.byref(n)), "orb_extract")
+                    if i >= 8:
+                        T[a, b].append(time.perf_counter() - t0)
+    out = {a: {b: {"median_ms": float(np.median(T[a, b]) * 1e3), "p90_ms": float(np.percentile(T[a, b], 90) * 1e3)} for b in bufs} for a in exs}
+    for ex in exs.values():
+        ex.close()
+    return out
 
 
 def check_frame_sharding(E, res):
@@ -829,8 +855,9 @@ def run_gpu(args):
         verified["frame_sharding"] = check_frame_sharding(E, r0)
     latency = None
     if rank == 0 and not args.quick:
-        latency = {"api": "orb_extract (one 640x480 frame per blocking call, pageable host buffers, python ctypes caller)",
-                   "graph_replay": frame_latency(E, r0["_base"], W0, H0, True), "plain_launches": frame_latency(E, r0["_base"], W0, H0, False)}
+        latency = {"api": "orb_extract (one 640x480 frame per blocking call, python ctypes caller, 200 timed calls per variant in interleaved rounds)",
+                   "what": "default = the small-call forms of the pass (calls of <= 4 frames: short resize tiles, CTA-per-cell compaction, 32-warp selection, 512-thread FAST CTAs, programmatic dependent launch inside the replayed graph, one staged result block for pageable outputs); small_call_forms_off = the batch kernels and launch scheme for one frame",
+                   **frame_latency(E, r0["_base"], W0, H0)}
 
     # ---- configs[1]: 752x480 ----
     config1 = None

@@ -477,7 +477,7 @@ int orb_extract_batch_async(orb_ctx* c, const uint8_t* imgs, int nimg, int w, in
     if (!c->done_stream) ORB_CUDA(cudaStreamCreateWithFlags(&c->done_stream, cudaStreamNonBlocking));
     *t.h_status = 0;
     t.staged = false;
-    int launches = 0;
+    int launches = 0, simple_slot = -1;
     if (empty) {                                   // empty image: no keypoints (src/ORBextractor.cc:721-722)
         if (dev_out) { if (nimg) ORB_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * nimg, c->streams[0])); }
         else for (int i = 0; i < nimg; i++) counts[i] = 0;
@@ -574,8 +574,16 @@ int orb_extract_batch_async(orb_ctx* c, const uint8_t* imgs, int nimg, int w, in
                 c->out_pending[slot] = true;
             }
             if (slot == 0) { c->last_n0 = n; c->last_n1 = 0; } else c->last_n1 = n;
+            if (idle && nimg <= B) simple_slot = slot;       // one chunk on an idle pipeline: its own stream order already covers everything the ticket stands for
         }
     }
+    if (simple_slot >= 0) {
+        // the blocking single-chunk call (one frame per call in the reference): status and completion event ride on the stream that
+        // carries the call's last operation instead of a third stream behind three event waits
+        cudaStream_t ls = dev_out ? c->streams[simple_slot] : c->out_streams[simple_slot];
+        ORB_CUDA(cudaMemcpyAsync(t.h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, ls));
+        ORB_CUDA(cudaEventRecord(t.done, ls));
+    } else {
     // completion record on a third stream, so that the two work streams never wait for each other
     ORB_CUDA(cudaEventRecord(t.a, c->streams[0]));
     ORB_CUDA(cudaEventRecord(t.b, c->streams[1]));
@@ -584,6 +592,7 @@ int orb_extract_batch_async(orb_ctx* c, const uint8_t* imgs, int nimg, int w, in
     for (int i = 0; i < 2; i++) if (c->out_pending[i]) ORB_CUDA(cudaStreamWaitEvent(c->done_stream, c->ev_out_done[i], 0));     // latest D2H of either slot
     ORB_CUDA(cudaMemcpyAsync(t.h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->done_stream));
     ORB_CUDA(cudaEventRecord(t.done, c->done_stream));
+    }
     t.counts = counts; t.nimg = nimg; t.cap = cap; t.host_out = !dev_out; t.seq = c->next_seq;
     c->last_launches = launches;
     *ticket = c->next_seq++;
