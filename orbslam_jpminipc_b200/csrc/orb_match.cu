@@ -288,8 +288,40 @@ k_grid_build(const orb_keypoint* __restrict__ kps, int n, int min_x, int max_x, 
     }
     if (tid == 1023) cell_start[NC] = base;
     __syncthreads();
-    // stable placement in ascending keypoint index (the reference push_backs in index order): one warp walks the
-    // keypoints 32 at a time; lanes of the same cell rank themselves with match_any
+    // Placement in ascending keypoint index inside every cell (the reference push_backs in index order).  Usual case — no cell holds
+    // more than 32 keypoints (1000-2000 keypoints over 3072 cells): every thread drops its keypoints into their cells with an
+    // atomic counter, in whatever order, and the owner of a cell (three cells per thread, as in the scan above) then sorts the
+    // cell's few entries by index; ascending index IS insertion order.  The one-warp walk below did this in n / 32 serial trips of
+    // match_any (13 of the 18-32 us this kernel took) and remains for frames with a crowded cell.
+    __shared__ int s_big;
+    if (tid == 0) s_big = 0;
+    __syncthreads();
+    if (max(cnt[0], max(cnt[1], cnt[2])) > 32) s_big = 1;
+    __syncthreads();
+    if (!s_big) {
+        for (int i = tid; i < n; i += blockDim.x) {
+            const unsigned c = s_cell[i];
+            if (c != 0xffffu) cell_items[atomicAdd(&s_cnt[c], 1)] = i;
+        }
+        __syncthreads();
+        int start = incl - mine + ((tid >> 5) ? s_warp[(tid >> 5) - 1] : 0);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int m = cnt[k];
+            if (m > 1) {                                   // insertion sort of at most 32 indices, in registers' reach of L1
+                int32_t* v = cell_items + start;
+                for (int a = 1; a < m; a++) {
+                    const int x = v[a];
+                    int bpos = a - 1;
+                    while (bpos >= 0 && v[bpos] > x) { v[bpos + 1] = v[bpos]; bpos--; }
+                    v[bpos + 1] = x;
+                }
+            }
+            start += m;
+        }
+        return;
+    }
+    // crowded cell: one warp walks the keypoints 32 at a time; lanes of the same cell rank themselves with match_any
     if (tid < 32) {
         for (int i0 = 0; i0 < n; i0 += 32) {
             const int i = i0 + tid;
@@ -319,6 +351,7 @@ struct SbpArgs {
     float th;
     int cap;                          // candidate slots per query
     uint32_t* list; int* cnt;         // list[i*cap + pos] = dist<<22 | i2 ; cnt[i] = candidates found (-1: not searched)
+    const int32_t* prematch;          // match_cur as the caller passed it: keypoints that already carry a map point
 };
 
 __device__ __forceinline__ int hamming256(const uint32_t* q, const uint8_t* row)
@@ -353,6 +386,59 @@ __device__ void three_maxima(const int* hs, int& ind1, int& ind2, int& ind3)
     }
     if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
     else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
+}
+
+// Frame::GetFeaturesInArea (src/Frame.cc:200-265) for a whole warp, in the reference's scan order (ix outer, iy inner, insertion order).
+// The grid's CSR is indexed by cell id = ix * 48 + iy, so the cells iy = y0 .. y1 of ONE column ix are one contiguous run of cell_items:
+// the lanes fetch the run bounds of up to 32 columns at once (a cell-by-cell walk paid two dependent loads for each of the up to
+// 11 x 11 mostly empty cells of a window: 35 us per SearchByProjection), a warp prefix concatenates the runs and the items are visited 32 at
+// a time.  visit(valid, id) is called by all lanes together (it ballots); valid lanes carry consecutive items of the scan order.
+template <typename F>
+__device__ __forceinline__ void warp_window_walk(const orb_frame_view& fr, int x0, int x1, int y0, int y1, int lane, F visit)
+{
+    for (int c0 = x0; c0 <= x1; c0 += 32) {
+        const int c = c0 + lane;
+        int b = 0, e = 0;
+        if (c <= x1) { const int base = c * ORB_GRID_ROWS; b = fr.cell_start[base + y0]; e = fr.cell_start[base + y1 + 1]; }
+        const int len = e - b;
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int tv = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += tv; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int start = b - (incl - len);                      // item t of this trip's concatenation sits at start + t for the run that holds it
+        for (int t0 = 0; t0 < total; t0 += 32) {
+            const int t = t0 + lane;
+            int col = 0;                                         // number of runs that end at or before t = index of the run holding t
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) { const int v = __shfl_sync(0xffffffffu, incl, col + step - 1); if (v <= t) col += step; }
+            const int st = __shfl_sync(0xffffffffu, start, col & 31);
+            const bool valid = t < total;
+            visit(valid, valid ? fr.cell_items[st + t] : 0);
+        }
+    }
+}
+
+// Sorts a warp's candidate list (dist << 22 | id, in scan order) by (distance, scan position), in place: rank by counting.  With the
+// list in that order "the best candidate nobody earlier has claimed" is simply the FIRST unclaimed entry, and the second best of the
+// ratio tests the second one (the reference's strict '<' keeps the earlier of two equal distances, :1568, :466-473), so a round of
+// the resolution pass touches one or two entries per query instead of walking the whole list (27 -> 8 us per SearchByProjection).
+// Lists longer than SORT_MAX stay in scan order; the resolution pass walks those in full.
+constexpr int SORT_MAX = 256;
+__device__ __forceinline__ void warp_sort_candidates(uint32_t* __restrict__ list, int n, int lane)
+{
+    if (n < 2 || n > SORT_MAX) return;
+    __syncwarp();
+    uint32_t e[SORT_MAX / 32]; int rank[SORT_MAX / 32];
+#pragma unroll
+    for (int k = 0; k < SORT_MAX / 32; k++) { const int p = lane + 32 * k; e[k] = p < n ? list[p] : 0u; rank[k] = 0; }
+    for (int q = 0; q < n; q++) {
+        const uint32_t kq = ((list[q] >> 22) << 10) | (uint32_t)q;          // broadcast load (L1)
+#pragma unroll
+        for (int k = 0; k < SORT_MAX / 32; k++) rank[k] += kq < (((e[k] >> 22) << 10) | (uint32_t)(lane + 32 * k));
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < SORT_MAX / 32; k++) if (lane + 32 * k < n) list[rank[k]] = e[k];
 }
 
 // Pass 1, one warp per last-frame feature: project its map point (:1529-1537), gate on the image
@@ -401,29 +487,27 @@ k_sbp_candidates(SbpArgs A)
             const bool checkLevels = !(minLevel == -1 && maxLevel == -1);
             uint32_t* out = A.list + (size_t)i * A.cap;
             const uint32_t lt = (1u << lane) - 1;
-            for (int ix = x0; ix <= x1; ix++)
-                for (int iy = y0; iy <= y1; iy++) {
-                    const int cidx = ix * ORB_GRID_ROWS + iy;
-                    const int b = A.cur.cell_start[cidx], e = A.cur.cell_start[cidx + 1];
-                    for (int j0 = b; j0 < e; j0 += 32) {
-                        const int j = j0 + lane;
-                        bool ok = false; int id = 0;
-                        if (j < e) {
-                            id = A.cur.cell_items[j];
-                            const orb_keypoint kp = A.cur.kps[id];
-                            ok = true;
-                            if (checkLevels && !sameLevel) { if (kp.octave < minLevel || kp.octave > maxLevel) ok = false; }
-                            else if (sameLevel) { if (kp.octave != minLevel) ok = false; }
-                            if (fabsf(__fsub_rn(kp.x, u)) > r || fabsf(__fsub_rn(kp.y, v)) > r) ok = false;
-                        }
-                        const uint32_t m = __ballot_sync(0xffffffffu, ok);
-                        if (ok) {
-                            const int pos = total + __popc(m & lt);
-                            if (pos < A.cap) out[pos] = ((uint32_t)hamming256(q, A.cur.desc + (size_t)id * 32) << 22) | (uint32_t)id;
-                        }
-                        total += __popc(m);
-                    }
+            if (x1 >= x0 && y1 >= y0)
+            warp_window_walk(A.cur, x0, x1, y0, y1, lane, [&](bool valid, int id) {
+                bool ok = false;
+                if (valid) {
+                    const orb_keypoint kp = A.cur.kps[id];
+                    ok = true;
+                    if (checkLevels && !sameLevel) { if (kp.octave < minLevel || kp.octave > maxLevel) ok = false; }
+                    else if (sameLevel) { if (kp.octave != minLevel) ok = false; }
+                    if (fabsf(__fsub_rn(kp.x, u)) > r || fabsf(__fsub_rn(kp.y, v)) > r) ok = false;
+                    // CurrentFrame.mvpMapPoints[i2] set before the call (:1562): the keypoint can never be taken, whatever the claims
+                    // of pass 2 turn out to be, so it does not enter the list (the array is only written after the last round of pass 2)
+                    if (ok && A.prematch[id] >= 0) ok = false;
                 }
+                const uint32_t m = __ballot_sync(0xffffffffu, ok);
+                if (ok) {
+                    const int pos = total + __popc(m & lt);
+                    if (pos < A.cap) out[pos] = ((uint32_t)hamming256(q, A.cur.desc + (size_t)id * 32) << 22) | (uint32_t)id;
+                }
+                total += __popc(m);
+            });
+            if (total <= A.cap) warp_sort_candidates(out, total, lane);
         }
     }
     if (lane == 0) A.cnt[i] = total;
@@ -438,12 +522,20 @@ k_sbp_candidates(SbpArgs A)
 // and it takes 2-4 rounds in practice.  Then the rotation histogram filter (:1581-1617).
 // result[0] = nmatches, result[1] = error flag.
 __global__ void __launch_bounds__(1024)
-k_sbp_resolve(SbpArgs A, int check_ori, int32_t* __restrict__ match_cur, int8_t* __restrict__ bin_of, int* __restrict__ owner,
-              int* __restrict__ choice, int* __restrict__ result)
+k_sbp_resolve(SbpArgs A, int check_ori, int32_t* __restrict__ match_cur, int8_t* __restrict__ bin_of, int* owner,
+              int* choice, int* __restrict__ result, int use_smem_owner)
 {
+    // owner[] lives in shared memory when the frame's keypoints fit (the launch passes n2 * 4 bytes): every candidate of every round looks it up
+    extern __shared__ int s_owner[];
     __shared__ int hist[HISTO_LENGTH];
     __shared__ int s_changed, s_err, s_cnt, s_rounds;
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int* cnt = A.cnt;
+    if (use_smem_owner) {           // s_owner[n2] | choice[n1] | cnt[n1]: everything the rounds touch per query, except the lists themselves
+        owner = s_owner; choice = s_owner + A.cur.n; int* sc = choice + A.last.n;
+        for (int i = tid; i < A.last.n; i += nt) sc[i] = A.cnt[i];
+        cnt = sc;
+    }
     const int n1 = A.last.n, n2 = A.cur.n;
     if (tid < HISTO_LENGTH) hist[tid] = 0;
     if (tid == 0) { s_err = 0; s_cnt = 0; s_rounds = 0; }
@@ -457,16 +549,17 @@ k_sbp_resolve(SbpArgs A, int check_ori, int32_t* __restrict__ match_cur, int8_t*
         for (int i = tid; i < n1; i += nt) { const int c = choice[i]; if (c >= 0) atomicMin(&owner[c], i); }
         __syncthreads();
         for (int i = tid; i < n1; i += nt) {
-            const int n = A.cnt[i];
+            const int n = cnt[i];
             if (n <= 0) continue;
             if (n > A.cap) { s_err = 1; continue; }
             const uint32_t* L = A.list + (size_t)i * A.cap;
             uint32_t best = 0xffffffffu;          // dist<<22 | id ; scan position is the iteration order
+            const bool sorted = n <= SORT_MAX;    // list ordered by (distance, scan position): the first unclaimed entry is the answer
             for (int p = 0; p < n; p++) {
                 const uint32_t e = L[p];
                 const int id = (int)(e & 0x3fffff);
-                if (match_cur[id] >= 0) continue;                 // CurrentFrame.mvpMapPoints[i2] was set before the call (:1562)
                 if (owner[id] < i) continue;                      // claimed by an earlier feature
+                if (sorted) { best = e; break; }
                 if ((e >> 22) < (best >> 22)) best = e;           // strict '<': first in scan order wins
             }
             const int c = (best != 0xffffffffu && (int)(best >> 22) <= TH_HIGH) ? (int)(best & 0x3fffff) : -1;
@@ -526,6 +619,8 @@ struct WinArgs {
     const float* qangle;                        // query keypoint angles for the rotation histogram (may be NULL)
     int accept; float nnratio; int th_dist; int histogram;
     int cap; uint32_t* list; int* cnt;
+    int sort_lists;                             // k_win_resolve only: lists of at most SORT_MAX entries ordered by (distance, scan position)
+    const int32_t* prematch;                    // k_win_resolve only: the match array as passed in (NULL: no pre-existing matches to skip)
 };
 
 __global__ void __launch_bounds__(256)
@@ -573,29 +668,25 @@ k_win_candidates(WinArgs A)
             const bool sameLevel = checkLevels && minLevel == maxLevel;
             uint32_t* out = A.list + (size_t)i * A.cap;
             const uint32_t lt = (1u << lane) - 1;
-            for (int ix = x0; ix <= x1; ix++)
-                for (int iy = y0; iy <= y1; iy++) {
-                    const int cidx = ix * ORB_GRID_ROWS + iy;
-                    const int b = A.tgt.cell_start[cidx], e = A.tgt.cell_start[cidx + 1];
-                    for (int j0 = b; j0 < e; j0 += 32) {
-                        const int j = j0 + lane;
-                        bool ok = false; int id = 0;
-                        if (j < e) {
-                            id = A.tgt.cell_items[j];
-                            const orb_keypoint kp = A.tgt.kps[id];
-                            ok = true;
-                            if (checkLevels && !sameLevel) { if (kp.octave < minLevel || kp.octave > maxLevel) ok = false; }
-                            else if (sameLevel) { if (kp.octave != minLevel) ok = false; }
-                            if (fabsf(__fsub_rn(kp.x, u)) > r || fabsf(__fsub_rn(kp.y, v)) > r) ok = false;
-                        }
-                        const uint32_t m = __ballot_sync(0xffffffffu, ok);
-                        if (ok) {
-                            const int pos = total + __popc(m & lt);
-                            if (pos < A.cap) out[pos] = ((uint32_t)hamming256(q, A.tgt.desc + (size_t)id * 32) << 22) | (uint32_t)id;
-                        }
-                        total += __popc(m);
-                    }
+            if (x1 >= x0 && y1 >= y0)
+            warp_window_walk(A.tgt, x0, x1, y0, y1, lane, [&](bool valid, int id) {
+                bool ok = false;
+                if (valid) {
+                    const orb_keypoint kp = A.tgt.kps[id];
+                    ok = true;
+                    if (checkLevels && !sameLevel) { if (kp.octave < minLevel || kp.octave > maxLevel) ok = false; }
+                    else if (sameLevel) { if (kp.octave != minLevel) ok = false; }
+                    if (fabsf(__fsub_rn(kp.x, u)) > r || fabsf(__fsub_rn(kp.y, v)) > r) ok = false;
+                    if (ok && A.prematch && A.prematch[id] >= 0) ok = false;       // keypoint already carries a map point (k_win_resolve's rule, round-invariant)
                 }
+                const uint32_t m = __ballot_sync(0xffffffffu, ok);
+                if (ok) {
+                    const int pos = total + __popc(m & lt);
+                    if (pos < A.cap) out[pos] = ((uint32_t)hamming256(q, A.tgt.desc + (size_t)id * 32) << 22) | (uint32_t)id;
+                }
+                total += __popc(m);
+            });
+            if (A.sort_lists && total <= A.cap) warp_sort_candidates(out, total, lane);
         }
     }
     if (lane == 0) A.cnt[i] = total;
@@ -603,12 +694,20 @@ k_win_candidates(WinArgs A)
 
 // Same parallel fixed-point resolution as k_sbp_resolve, with the acceptance rules above.
 __global__ void __launch_bounds__(1024)
-k_win_resolve(WinArgs A, int32_t* __restrict__ match, int8_t* __restrict__ bin_of, int* __restrict__ owner,
-              int* __restrict__ choice, int* __restrict__ result)
+k_win_resolve(WinArgs A, int32_t* __restrict__ match, int8_t* __restrict__ bin_of, int* owner,
+              int* choice, int* __restrict__ result, int use_smem_owner)
 {
+    // owner[] lives in shared memory when the frame's keypoints fit (the launch passes n2 * 4 bytes): every candidate of every round looks it up
+    extern __shared__ int s_owner[];
     __shared__ int hist[HISTO_LENGTH];
     __shared__ int s_changed, s_err, s_cnt;
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int* cnt = A.cnt;
+    if (use_smem_owner) {           // s_owner[n2] | choice[n1] | cnt[n1]: everything the rounds touch per query, except the lists themselves
+        owner = s_owner; choice = s_owner + A.tgt.n; int* sc = choice + A.nq;
+        for (int i = tid; i < A.nq; i += nt) sc[i] = A.cnt[i];
+        cnt = sc;
+    }
     const int n1 = A.nq, n2 = A.tgt.n;
     if (tid < HISTO_LENGTH) hist[tid] = 0;
     if (tid == 0) { s_err = 0; s_cnt = 0; }
@@ -622,16 +721,21 @@ k_win_resolve(WinArgs A, int32_t* __restrict__ match, int8_t* __restrict__ bin_o
         for (int i = tid; i < n1; i += nt) { const int c = choice[i]; if (c >= 0) atomicMin(&owner[c], i); }
         __syncthreads();
         for (int i = tid; i < n1; i += nt) {
-            const int n = A.cnt[i];
+            const int n = cnt[i];
             if (n <= 0) continue;
             if (n > A.cap) { s_err = 1; continue; }
             const uint32_t* L = A.list + (size_t)i * A.cap;
             int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx = -1, bestLevel = -1, bestLevel2 = -1;
+            const bool sorted = A.sort_lists && n <= SORT_MAX;    // ordered by (distance, scan position): the first two unclaimed entries are best and second best
             for (int p = 0; p < n; p++) {
                 const uint32_t e = L[p];
                 const int id = (int)(e & 0x3fffff), dist = (int)(e >> 22);
-                if (match[id] >= 0) continue;                     // keypoint already carries a map point
                 if (owner[id] < i) continue;                      // claimed by an earlier query
+                if (sorted && bestIdx >= 0) {
+                    bestDist2 = dist;
+                    if (A.accept == WIN_ACCEPT_LEVEL_RATIO) bestLevel2 = A.tgt.kps[id].octave;
+                    break;
+                }
                 if (dist < bestDist) {
                     bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestIdx = id;
                     if (A.accept == WIN_ACCEPT_LEVEL_RATIO) bestLevel = A.tgt.kps[id].octave;
@@ -1028,7 +1132,7 @@ int orb_launch_search_by_projection(orb_ctx* c, const orb_frame_view* cur, const
     if (cur->nlevels < 1 || cur->nlevels > ORB_MAX_LEVELS) return ORB_ERR_INVALID;
     A.sf[0] = 1.0f;
     for (int i = 1; i < ORB_MAX_LEVELS; i++) A.sf[i] = i < cur->nlevels ? A.sf[i - 1] * cur->scale_factor : A.sf[i - 1];
-    A.th = th;
+    A.th = th; A.prematch = match_cur;
     if (cur->n >= (1 << 22)) return ORB_ERR_CAPACITY;
     // scratch: cnt[last.n] | choice[last.n] | owner[cur.n] | bin_of[cur.n] | list[last.n * cap]
     size_t off = 0;
@@ -1042,7 +1146,9 @@ int orb_launch_search_by_projection(orb_ctx* c, const orb_frame_view* cur, const
     A.list = (uint32_t*)(scratch + off);
     if (A.cap < 1) return ORB_ERR_CAPACITY;
     k_sbp_candidates<<<(last->n * 32 + 255) / 256, 256, 0, s>>>(A);
-    k_sbp_resolve<<<1, 1024, 0, s>>>(A, check_ori, match_cur, bin_of, owner, choice, d_result);
+    const size_t rs_bytes = ((size_t)cur->n + 2 * (size_t)last->n) * 4;
+    const int smem_owner = rs_bytes <= 40 * 1024;
+    k_sbp_resolve<<<1, 1024, smem_owner ? rs_bytes : 0, s>>>(A, check_ori, match_cur, bin_of, owner, choice, d_result, smem_owner);
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;
 }
@@ -1246,6 +1352,7 @@ int orb_launch_search_window(orb_ctx* c, const orb_frame_view* tgt, const orb_wi
     A.check_bounds = q->check_bounds; A.radius = q->radius; A.radius_const = q->radius_const;
     A.minl = q->min_level; A.maxl = q->max_level; A.qangle = q->angle;
     A.accept = accept; A.nnratio = nnratio; A.th_dist = th_dist; A.histogram = histogram && q->angle;
+    A.prematch = match; A.sort_lists = 1;
     if (tgt->n >= (1 << 22)) return ORB_ERR_CAPACITY;
     size_t off = 0;
     A.cnt = (int*)(scratch + off); off += ((size_t)q->n * 4 + 255) & ~(size_t)255;
@@ -1258,7 +1365,9 @@ int orb_launch_search_window(orb_ctx* c, const orb_frame_view* tgt, const orb_wi
     A.list = (uint32_t*)(scratch + off);
     if (A.cap < 1) return ORB_ERR_CAPACITY;
     k_win_candidates<<<(q->n * 32 + 255) / 256, 256, 0, s>>>(A);
-    k_win_resolve<<<1, 1024, 0, s>>>(A, match, bin_of, owner, choice, d_result);
+    const size_t rs_bytes = ((size_t)tgt->n + 2 * (size_t)q->n) * 4;
+    const int smem_owner = rs_bytes <= 40 * 1024;
+    k_win_resolve<<<1, 1024, smem_owner ? rs_bytes : 0, s>>>(A, match, bin_of, owner, choice, d_result, smem_owner);
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;
 }
@@ -1295,7 +1404,7 @@ int orb_launch_search_window_best(orb_ctx* c, const orb_frame_view* tgt, const o
     for (int i = 0; i < 16; i++) A.T[i] = (A.project && q->Tcw16) ? q->Tcw16[i] : 0.f;
     A.check_bounds = q->check_bounds; A.radius = q->radius; A.radius_const = q->radius_const;
     A.minl = q->min_level; A.maxl = q->max_level; A.qangle = nullptr;
-    A.accept = 0; A.nnratio = 0.f; A.th_dist = 256; A.histogram = 0;
+    A.accept = 0; A.nnratio = 0.f; A.th_dist = 256; A.histogram = 0; A.prematch = nullptr; A.sort_lists = 0;
     if (tgt->n >= (1 << 22)) return ORB_ERR_CAPACITY;
     size_t off = 0;
     A.cnt = (int*)(scratch + off); off += ((size_t)q->n * 4 + 255) & ~(size_t)255;
@@ -1396,7 +1505,7 @@ int orb_launch_search_for_initialization(orb_ctx* c, const orb_frame_view* f1, c
     A.tgt = *f2; A.nq = f1->n; A.active = d_active; A.qdesc = f1->desc; A.u = d_u; A.v = d_v; A.xyz = nullptr; A.project = 0;
     for (int i = 0; i < 16; i++) A.T[i] = 0.f;
     A.check_bounds = 0; A.radius = nullptr; A.radius_const = (float)window; A.minl = d_lv; A.maxl = d_lv; A.qangle = d_angle;
-    A.accept = 0; A.nnratio = nnratio; A.th_dist = TH_LOW; A.histogram = check_ori;
+    A.accept = 0; A.nnratio = nnratio; A.th_dist = TH_LOW; A.histogram = check_ori; A.prematch = nullptr; A.sort_lists = 0;
     A.cnt = (int*)take(n1 * 4);
     int* choice = (int*)take(n1 * 4);
     int* cdist = (int*)take(n1 * 4);

@@ -77,6 +77,26 @@ def test_frame_grid(pkg, po, matcher):
     assert np.array_equal(f.cell_start, o.cell_start)
     cnt = f.cell_start[-1]
     assert cnt < n and np.array_equal(f.cell_items[:cnt], o.cell_items[:cnt])
+    # crowded cells (more than 32 keypoints in one cell: the one-warp placement of k_grid_build), every keypoint in ONE cell, and
+    # cells of exactly 32 / 33 keypoints on either side of the switch
+    for kind in ("clustered", "one_cell", "edge32", "edge33"):
+        k2 = kps.copy()
+        if kind == "clustered":
+            k2["x"][:700] = rng.uniform(100, 130, 700).astype(np.float32); k2["y"][:700] = rng.uniform(200, 225, 700).astype(np.float32)
+        elif kind == "one_cell":
+            k2["x"] = rng.uniform(300, 305, n).astype(np.float32); k2["y"] = rng.uniform(100, 104, n).astype(np.float32)
+        else:
+            m = 32 if kind == "edge32" else 33
+            idx = rng.permutation(n)[:m]
+            k2["x"][idx] = np.float32(400.0); k2["y"][idx] = np.float32(300.0)
+            far = np.setdiff1d(np.arange(n), idx)
+            near = far[(np.abs(k2["x"][far] - 400.0) < 30) & (np.abs(k2["y"][far] - 300.0) < 30)]
+            k2["x"][near] = np.float32(20.0)                       # keep the neighbourhood of that cell empty otherwise
+        f2 = pkg.Frame(matcher, k2, np.zeros((n, 32), np.uint8), 752, 480, 500, 500, 376, 240)
+        o2 = po.OracleFrame(k2, np.zeros((n, 32), np.uint8), 752, 480, 500, 500, 376, 240)
+        c2 = o2.cell_start[-1]
+        assert np.array_equal(f2.cell_start, o2.cell_start), kind
+        assert np.array_equal(f2.cell_items[:c2], o2.cell_items[:c2]), kind
 
 
 # ---------------------------------------------------------------- SearchByProjection / SearchByBoW
