@@ -1,0 +1,42 @@
+"""Blocking orb_extract_batch calls of N = 1..32 frames (stereo / multi-camera rigs) with the small-call forms on (limit >= N) and off:
+where should `small_call_frames` / `pdl_frames` sit?   gpurun -- 'python tools/latency_small_batch.py'"""
+import os, sys, time, ctypes as C
+import numpy as np
+sys.path.insert(0, ".")
+import torch
+import orbslam_jpminipc_b200 as pkg
+from orbslam_jpminipc_b200._lib import check, lib, ptr
+from orbslam_jpminipc_b200.synth import synth_frames
+
+L = lib()
+H, W, NF = 480, 640, 1000
+frames = torch.from_numpy(np.stack(synth_frames(32, H, W, seed0=1000))).pin_memory()
+
+
+def ctx(env):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    ex = pkg.ORBextractor(NF, 1.2, 8, 1, 20, max_width=W, max_height=H, max_batch=32)
+    for k, v in old.items():
+        if v is None: del os.environ[k]
+        else: os.environ[k] = v
+    return ex
+
+
+variants = {"forms on (limit 64)": {"ORB_SMALL_CALL": "64", "ORB_PDL_FRAMES": "64"},
+            "kernels on, PDL off": {"ORB_SMALL_CALL": "64", "ORB_PDL_FRAMES": "0"},
+            "kernels off, PDL on": {"ORB_SMALL_CALL": "0", "ORB_PDL_FRAMES": "64", "ORB_SELECT_WIDE": "0"},
+            "forms off": {"ORB_SMALL_CALL": "0", "ORB_PDL_FRAMES": "0", "ORB_SELECT_WIDE": "0"}}
+exs = {k: ctx(v) for k, v in variants.items()}
+cap = exs["forms off"].capacity
+for n in (1, 2, 4, 6, 8, 12, 16, 32):
+    k = torch.zeros((n, cap, 7), dtype=torch.int32).pin_memory(); d = torch.zeros((n, cap, 32), dtype=torch.uint8).pin_memory()
+    c = torch.zeros(n, dtype=torch.int32).pin_memory()
+    T = {a: [] for a in exs}
+    for rnd in range(4):
+        for a, ex in exs.items():
+            for i in range(30):
+                t0 = time.perf_counter()
+                check(L.orb_extract_batch(ex._h, ptr(frames), n, W, H, W, W * H, ptr(k), ptr(d), cap, ptr(c)), "orb_extract_batch")
+                if i >= 5: T[a].append(time.perf_counter() - t0)
+    print("frames per call", n, "| " + " | ".join("%s: %.1f us" % (a, np.median(T[a]) * 1e6) for a in exs))
