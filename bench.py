@@ -856,7 +856,7 @@ def run_gpu(args):
     latency = None
     if rank == 0 and not args.quick:
         latency = {"api": "orb_extract (one 640x480 frame per blocking call, python ctypes caller, 200 timed calls per variant in interleaved rounds)",
-                   "what": "default = the small-call forms of the pass (calls of <= 4 frames: short resize tiles, CTA-per-cell compaction, 32-warp selection, 512-thread FAST CTAs, programmatic dependent launch inside the replayed graph, one staged result block for pageable outputs); small_call_forms_off = the batch kernels and launch scheme for one frame",
+                   "what": "default = the small-call forms of the pass (calls of <= 12 frames: short resize tiles, CTA-per-cell compaction, 32-warp selection, 512-thread FAST CTAs, programmatic dependent launch inside the replayed graph, one staged result block for pageable outputs); small_call_forms_off = the batch kernels and launch scheme for one frame",
                    **frame_latency(E, r0["_base"], W0, H0)}
 
     # ---- configs[1]: 752x480 ----

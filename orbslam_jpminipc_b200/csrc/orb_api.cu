@@ -496,7 +496,7 @@ int orb_extract_batch_async(orb_ctx* c, const uint8_t* imgs, int nimg, int w, in
         // pageable memory are three blocking, driver-staged transfers after the kernels; instead the slot's results form one device
         // block that returns in ONE copy to pinned staging owned by the ticket, and orb_wait hands the valid rows to the caller.
         size_t stage_bytes = 0;
-        if (c->stage_small && !dev_out && nimg <= B && nimg <= c->small_call_frames) {
+        if (c->stage_small && !dev_out && nimg <= B && nimg <= c->stage_frames) {
             cudaPointerAttributes pa;
             if (cudaPointerGetAttributes(&pa, kps) == cudaSuccess && pa.type == cudaMemoryTypeUnregistered)
                 stage_bytes = (size_t)nimg * cap * (sizeof(orb_keypoint) + 32) + (size_t)nimg * sizeof(int32_t);

@@ -427,7 +427,7 @@ def test_selection_ties_and_long_lists(pkg, po, kind, h, w, nf):
 
 @pytest.mark.parametrize("shape,nf,score", [((480, 640), 1000, 1), ((376, 1241), 2000, 1), ((240, 320), 300, 0)])
 def test_small_calls_take_the_latency_paths_and_agree(pkg, po, shape, nf, score):
-    """Calls of at most four frames (the reference's one frame per Frame::Frame, src/Frame.cc:60) run a latency-tuned form of the pass:
+    """Calls of a few frames (the reference's one frame per Frame::Frame, src/Frame.cc:60) run a latency-tuned form of the pass:
     short resize tiles, CTA-per-cell compaction, 32-warp selection, programmatic dependent launches and, for pageable outputs, one
     staged result block.  Every combination of call size (below / at / above the limit) and output memory kind must equal the oracle,
     and a context with all of it switched off must agree byte for byte."""
@@ -435,7 +435,7 @@ def test_small_calls_take_the_latency_paths_and_agree(pkg, po, shape, nf, score)
     from orbslam_jpminipc_b200._lib import check, lib, ptr
     from orbslam_jpminipc_b200.synth import synth_frames
     h, w = shape
-    frames = np.stack(synth_frames(6, h, w, seed0=8100 + nf))
+    frames = np.stack(synth_frames(14, h, w, seed0=8100 + nf))
     orc = po.OracleExtractor(nf, 1.2, 8, score, 20)
     want = [orc(f) for f in frames]
     off = {"ORB_SMALL_CALL": "0", "ORB_SELECT_WIDE": "0", "ORB_COMPACT_WIDE": "0", "ORB_PDL": "0", "ORB_STAGE_SMALL": "0"}
@@ -444,7 +444,7 @@ def test_small_calls_take_the_latency_paths_and_agree(pkg, po, shape, nf, score)
         old = {k: os.environ.get(k) for k in env}
         os.environ.update(env)
         try:
-            ex = pkg.ORBextractor(nf, 1.2, 8, score, 20, max_width=w, max_height=h, max_batch=6)
+            ex = pkg.ORBextractor(nf, 1.2, 8, score, 20, max_width=w, max_height=h, max_batch=14)
         finally:
             for k, v in old.items():
                 if v is None:
@@ -452,7 +452,7 @@ def test_small_calls_take_the_latency_paths_and_agree(pkg, po, shape, nf, score)
                 else:
                     os.environ[k] = v
         cap = ex.capacity
-        for n in (1, 2, 4, 5, 6, 1):
+        for n in (1, 2, 4, 5, 12, 13, 14, 1):          # PDL / staged results up to 4 frames, the kernel forms up to 12
             for pinned in (False, True):
                 k = torch.zeros((n, cap, 7), dtype=torch.int32); d = torch.full((n, cap, 32), 0xAB, dtype=torch.uint8)
                 c = torch.zeros(n, dtype=torch.int32)

@@ -40,3 +40,4 @@ for n in (1, 2, 4, 6, 8, 12, 16, 32):
                 check(L.orb_extract_batch(ex._h, ptr(frames), n, W, H, W, W * H, ptr(k), ptr(d), cap, ptr(c)), "orb_extract_batch")
                 if i >= 5: T[a].append(time.perf_counter() - t0)
     print("frames per call", n, "| " + " | ".join("%s: %.1f us" % (a, np.median(T[a]) * 1e6) for a in exs))
+for ex in exs.values(): ex.close()
