@@ -2154,7 +2154,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
     }
     if (fork && (c->fork_early == 1 || c->fork_early == 2)) { launch_blur(W.aux_stream); ORB_CUDA(cudaEventRecord(W.ev_join, W.aux_stream)); }
     mark();
-    if (c->compact_wide && nimg <= c->small_call_frames)
+    if (c->compact_wide == 2 || (c->compact_wide && nimg <= c->small_call_frames))       // ORB_COMPACT_WIDE=2: for every call size (A/B timing)
         launch_k(pdl, k_cell_compact_wide, dim3(P.ncells, nimg), 256, 0, s, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_cells, W.d_cand, W.d_ntotal);
     else
     launch_k(pdl, k_cell_compact, dim3((P.ncells + 7) / 8, nimg), 256, 0, s, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_cells, W.d_cand, W.d_ntotal);
