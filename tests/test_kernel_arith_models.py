@@ -264,3 +264,133 @@ def test_half_lane_min_max_model():
             assert term.min() >= -32768 and term.max() <= 32767 and nvp.min() >= -32768 and vm1.max() <= 32767
         assert np.array_equal(np.maximum(Mn + nvp, 0), np.maximum(m - v - th, 0))
         assert np.array_equal(np.maximum((-Mx - 1) + vm1, 0), np.maximum(v - m - th, 0))
+
+
+# ---------------------------------------------------------------- round 2, last session: matcher / small-call restructurings
+def test_grid_column_runs_equal_the_cell_by_cell_walk():
+    """warp_window_walk (orb_match.cu): Frame::GetFeaturesInArea scans ix outer, iy inner, insertion order (src/Frame.cc:233-259).  The
+    grid's CSR is indexed by cell id = ix * 48 + iy, so the cells iy = y0..y1 of one column are ONE contiguous run of cell_items and
+    the concatenation of the runs of columns x0..x1 is that scan order.  Also models the run lookup of the kernel: item t of the
+    concatenation lies in run #(number of inclusive prefix sums <= t) at start_run + t with start_run = b_run - exclusive prefix."""
+    rng = np.random.default_rng(11)
+    COLS, ROWS = 64, 48
+    for trial in range(200):
+        n = int(rng.integers(0, 3000))
+        cell = np.sort(rng.integers(0, COLS * ROWS, n)) if trial % 3 else np.sort(rng.integers(0, 40, n))   # crowded corner too
+        cell_start = np.searchsorted(cell, np.arange(COLS * ROWS + 1)).astype(np.int64)
+        items = rng.permutation(n)                                   # cell_items: any payload, the ORDER inside the CSR is what matters
+        x0, x1 = sorted(rng.integers(0, COLS, 2)); y0, y1 = sorted(rng.integers(0, ROWS, 2))
+        want = [items[j] for ix in range(x0, x1 + 1) for iy in range(y0, y1 + 1)
+                for j in range(cell_start[ix * ROWS + iy], cell_start[ix * ROWS + iy + 1])]
+        got = []
+        for c0 in range(x0, x1 + 1, 32):                              # one trip of the kernel: up to 32 columns, one per lane
+            cols = list(range(c0, min(c0 + 32, x1 + 1)))
+            b = np.array([cell_start[c * ROWS + y0] for c in cols] + [0] * (32 - len(cols)))
+            e = np.array([cell_start[c * ROWS + y1 + 1] for c in cols] + [0] * (32 - len(cols)))
+            ln = e - b
+            incl = np.cumsum(ln)
+            start = b - (incl - ln)
+            for t in range(int(incl[-1])):
+                col = 0
+                for step in (16, 8, 4, 2, 1):                         # the kernel's shuffle binary search
+                    if incl[col + step - 1] <= t:
+                        col += step
+                assert col == int(np.searchsorted(incl, t, side="right"))
+                got.append(items[start[col] + t])
+        assert got == want
+
+
+def test_sorted_candidate_list_gives_the_scan_order_best_and_second():
+    """warp_sort_candidates + the resolution passes (orb_match.cu): the reference scans a query's candidates in order and keeps
+    best / second best with strict '<' (src/ORBmatcher.cc:1559-1574, :466-473, :85-109), skipping claimed keypoints.  With the list
+    sorted by (distance, scan position) the FIRST unclaimed entry is that best and the second unclaimed one is the second best
+    (value and identity), for any set of claimed entries."""
+    rng = np.random.default_rng(12)
+    for trial in range(3000):
+        n = int(rng.integers(1, 40))
+        dist = rng.integers(0, 12, n) if trial % 2 else rng.integers(0, 257, n)      # tie-heavy and plain
+        ids = rng.permutation(1000)[:n]
+        claimed = rng.random(n) < rng.choice([0.0, 0.3, 0.8])
+        # reference loop
+        bd, bd2, bi, bi2 = 1 << 30, 1 << 30, -1, -1
+        for p in range(n):
+            if claimed[p]:
+                continue
+            if dist[p] < bd:
+                bd2, bi2 = bd, bi
+                bd, bi = dist[p], ids[p]
+            elif dist[p] < bd2:
+                bd2, bi2 = dist[p], ids[p]
+        # rank sort by key (dist << 10 | position), as the kernel does by counting smaller keys
+        key = (dist.astype(np.int64) << 10) | np.arange(n)
+        rank = np.array([(key < k).sum() for k in key])
+        assert sorted(rank) == list(range(n))
+        order = np.empty(n, np.int64); order[rank] = np.arange(n)
+        free = [p for p in order if not claimed[p]]
+        gd, gi = (dist[free[0]], ids[free[0]]) if free else (1 << 30, -1)
+        gd2, gi2 = (dist[free[1]], ids[free[1]]) if len(free) > 1 else (1 << 30, -1)
+        assert (gd, gi, gd2) == (bd, bi, bd2)
+        if len(free) > 1:
+            assert gi2 == bi2                                         # the level-ratio rule (:114-117) reads the second's octave
+
+
+def test_quota_redistribution_by_lanes_equals_the_serial_loop():
+    """k_select_fast: the reference's quota loop (src/ORBextractor.cc:622-670) walks the cells serially, but a pass treats every cell
+    independently given nNew and carries only two sums into the next pass; the kernel gives the cells to the 32 lanes and reduces
+    the sums.  Same retained counts and the same offsets for any cell counts, skipped cells included."""
+    import math
+    rng = np.random.default_rng(13)
+    for trial in range(2000):
+        ncells = int(rng.integers(1, 200)); nfc = int(rng.integers(1, 20))
+        total = rng.integers(0, 60, ncells) * (rng.random(ncells) < 0.8)
+        skipped = rng.random(ncells) < 0.1
+        total = np.where(skipped, 0, total)
+
+        def serial():
+            retain = np.zeros(ncells, np.int64); nomore = np.zeros(ncells, bool); nno = 0; ntd = 0
+            for c in range(ncells):
+                if skipped[c]:
+                    continue
+                if total[c] > nfc:
+                    retain[c] = nfc
+                else:
+                    retain[c] = total[c]; ntd += nfc - total[c]; nomore[c] = True; nno += 1
+            while ntd > 0 and nno < ncells:
+                nnew = nfc + int(math.ceil(np.float32(ntd) / np.float32(ncells - nno)))
+                ntd = 0
+                for c in range(ncells):
+                    if nomore[c]:
+                        continue
+                    if total[c] > nnew:
+                        retain[c] = nnew
+                    else:
+                        retain[c] = total[c]; ntd += nnew - total[c]; nomore[c] = True; nno += 1
+            return retain
+
+        def by_lanes():
+            retain = np.zeros(ncells, np.int64); nomore = np.zeros(ncells, bool)
+            part_no = np.zeros(32, np.int64); part_td = np.zeros(32, np.int64)
+            for lane in range(32):
+                for c in range(lane, ncells, 32):
+                    if skipped[c]:
+                        continue
+                    if total[c] > nfc:
+                        retain[c] = nfc
+                    else:
+                        retain[c] = total[c]; part_td[lane] += nfc - total[c]; nomore[c] = True; part_no[lane] += 1
+            nno, ntd = int(part_no.sum()), int(part_td.sum())
+            while ntd > 0 and nno < ncells:
+                nnew = nfc + int(math.ceil(np.float32(ntd) / np.float32(ncells - nno)))
+                d = np.zeros(32, np.int64); m = np.zeros(32, np.int64)
+                for lane in range(32):
+                    for c in range(lane, ncells, 32):
+                        if nomore[c]:
+                            continue
+                        if total[c] > nnew:
+                            retain[c] = nnew
+                        else:
+                            retain[c] = total[c]; d[lane] += nnew - total[c]; nomore[c] = True; m[lane] += 1
+                ntd = int(d.sum()); nno += int(m.sum())
+            return retain
+        a, b = serial(), by_lanes()
+        assert np.array_equal(a, b)
