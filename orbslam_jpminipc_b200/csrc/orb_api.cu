@@ -255,6 +255,7 @@ orb_ctx* orb_create(int device, int nfeatures, float scale_factor, int nlevels, 
     if (const char* e = getenv("ORB_SELECT_WIDE")) c->select_wide = atoi(e);
     if (const char* e = getenv("ORB_COMPACT_WIDE")) c->compact_wide = atoi(e);
     if (const char* e = getenv("ORB_FAST_WIDE")) c->fast_wide = atoi(e);
+    if (const char* e = getenv("ORB_SIDE_BORDER")) c->side_border = atoi(e);
     if (const char* e = getenv("ORB_PDL")) c->use_pdl = atoi(e);
     if (const char* e = getenv("ORB_PDL_FRAMES")) c->pdl_frames = std::max(0, atoi(e));
     if (const char* e = getenv("ORB_STAGE_SMALL")) c->stage_small = atoi(e);

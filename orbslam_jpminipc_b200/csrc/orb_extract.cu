@@ -56,10 +56,27 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
 
 // PDL (launch_k below): let the dependent grid start scheduling, then wait until the prerequisite grid has completed and its memory is
 // visible.  First statement of every kernel of the pass: all pipeline data is touched behind it; a no-op without the launch attribute.
-__device__ __forceinline__ void pdl_sync()
+#ifdef ORB_TIMELINE      // diagnostic build (tools/timeline.py): when did each kernel's first CTA arrive, and when did its dependency resolve
+__device__ unsigned long long g_tl[4 * 16];     // per kernel id: min arrival, min start (behind the wait), max arrival, max start
+__device__ __forceinline__ unsigned long long tl_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
+__device__ __forceinline__ void tl_stamp(int id)      // diagnostic build: latest time any CTA passed this point (slot 3 of the id)
 {
+#ifdef ORB_TIMELINE
+    if (threadIdx.x == 0 && threadIdx.y == 0) atomicMax(&g_tl[4 * id + 3], tl_now());
+#endif
+}
+__device__ __forceinline__ void pdl_sync(int id = 0)
+{
+#ifdef ORB_TIMELINE
+    const bool rec = threadIdx.x == 0 && threadIdx.y == 0;
+    if (rec) { const unsigned long long a = tl_now(); atomicMin(&g_tl[4 * id], a); atomicMax(&g_tl[4 * id + 2], a); }
+#endif
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef ORB_TIMELINE
+    if (rec) { const unsigned long long b = tl_now(); atomicMin(&g_tl[4 * id + 1], b); atomicMax(&g_tl[4 * id + 3], b); }
+#endif
 }
 
 // The tile queues of the later kernels (32 counters) and k_pyramid's per-(frame, level) completion counters start every pass at zero:
@@ -81,7 +98,7 @@ __global__ void __launch_bounds__(256)
 k_level0(const uint8_t* __restrict__ src, int w, int h, int sstride, size_t spitch, int aligned4,
          uint8_t* __restrict__ planes, size_t fbytes, int pstride, int* __restrict__ counters)
 {
-    pdl_sync();
+    pdl_sync(1);
     zero_counters(counters);
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -105,7 +122,7 @@ __global__ void __launch_bounds__(256)
 k_level0_v16(const uint8_t* __restrict__ src, int w, int h, int sstride, size_t spitch, uint8_t* __restrict__ planes, size_t fbytes, int pstride,
              int* __restrict__ counters)
 {
-    pdl_sync();
+    pdl_sync(1);
     zero_counters(counters);
     const int x16 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -130,7 +147,7 @@ k_resize(const __grid_constant__ CUtensorMap tm, uint8_t* __restrict__ planes, s
          const int2* __restrict__ xtab, const int2* __restrict__ ytab, int box_w, int box_h, int buf_bytes,
          int nimg, int* __restrict__ work_counter, int RT_W, int RS_ROWS)
 {
-    pdl_sync();
+    pdl_sync(2);
     extern __shared__ __align__(128) uint8_t rs_sm[];       // two source tiles of buf_bytes each
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ int s_next[2];
@@ -264,7 +281,7 @@ k_resize_u(const __grid_constant__ CUtensorMap tm, uint8_t* __restrict__ planes,
            const uint4* __restrict__ xgrp, const int2* __restrict__ ytab, int box_w, int box_h, int buf_bytes,
            int nimg, int* __restrict__ work_counter, int RT_W)
 {
-    pdl_sync();
+    pdl_sync(2);
     extern __shared__ __align__(128) uint8_t rs_sm[];       // two source tiles of buf_bytes each
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ int s_next[2];
@@ -381,7 +398,7 @@ k_pyramid(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ planes, size
           const __grid_constant__ PyrParams P, const int2* __restrict__ xtab, const int2* __restrict__ ytab,
           int* __restrict__ work_counter, int* __restrict__ done)
 {
-    pdl_sync();
+    pdl_sync(2);
     extern __shared__ __align__(128) uint8_t rs_sm[];       // two source tiles of buf_bytes each
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ int s_next[2];
@@ -552,7 +569,7 @@ k_pyramid(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ planes, size
 __global__ void __launch_bounds__(256)
 k_border(uint8_t* __restrict__ planes, uint8_t* __restrict__ blurred, size_t fbytes, const Plan* __restrict__ plan)
 {
-    pdl_sync();
+    pdl_sync(3);
     // blockIdx.y = frame * nlevels + level; blockIdx.x walks the level's frame words (levels with fewer words exit).  Two words per
     // thread, both fetched before either is stored: the kernel is bound by load latency, not by instructions.
     const int l = blockIdx.y % plan->nlevels, f = blockIdx.y / plan->nlevels;
@@ -781,7 +798,7 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
            const Plan* __restrict__ plan, const Tile* __restrict__ tiles, int ntiles, int total, int* __restrict__ work_counter,
            const uint8_t* __restrict__ coltab, const int16_t* __restrict__ rowtab)
 {
-    pdl_sync();
+    pdl_sync(4);
     __shared__ __align__(128) uint32_t img2[ETILE ? 1 : 2][(FI_H * FIW + 31) & ~31];      // each buffer 128-byte aligned (TMA destination) for any tile height
     __shared__ __align__(16) uint32_t et[ETILE ? FI_H * EW : 4];
     __shared__ int s_next[2], s_ti[2], s_fr[2];             // next work item; tile index and frame of the item in each buffer
@@ -1164,7 +1181,7 @@ __global__ void __launch_bounds__(256, 8)      // 32 registers (20 bytes spilled
 k_cell_compact(const uint8_t* __restrict__ nms, const uint8_t* __restrict__ bitmap, size_t fbytes, const Plan* __restrict__ plan,
                const CellGeom* __restrict__ cells, uint32_t* __restrict__ cand, int* __restrict__ ntotal)
 {
-    pdl_sync();
+    pdl_sync(5);
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= plan->ncells) return;
     const int f = blockIdx.y;
@@ -1244,7 +1261,7 @@ __global__ void __launch_bounds__(256, 2)
 k_cell_compact_wide(const uint8_t* __restrict__ nms, const uint8_t* __restrict__ bitmap, size_t fbytes, const Plan* __restrict__ plan,
                     const CellGeom* __restrict__ cells, uint32_t* __restrict__ cand, int* __restrict__ ntotal)
 {
-    pdl_sync();
+    pdl_sync(5);
     __shared__ uint32_t seg[8][CCW_SEG];
     __shared__ int s_cnt[8], s_nP[8], s_n7[8];
     const int cell = blockIdx.x, f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1366,7 +1383,7 @@ __global__ void __launch_bounds__(256)
 k_harris(const uint8_t* __restrict__ planes, size_t fbytes, const Plan* __restrict__ plan, const CellGeom* __restrict__ cells,
          const uint32_t* __restrict__ cand, const int* __restrict__ ntotal, unsigned long long* __restrict__ cand64)
 {
-    pdl_sync();
+    pdl_sync(6);
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= plan->ncells) return;
     const int f = blockIdx.y;
@@ -1483,7 +1500,7 @@ k_select_fast(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells,
               unsigned long long* __restrict__ cand64, const int* __restrict__ ntotal,
               unsigned long long* __restrict__ lvl, int* __restrict__ nkept, int* __restrict__ status, uint8_t* __restrict__ spare, size_t fbytes)
 {
-    pdl_sync();
+    pdl_sync(7);
     // sel_list_cap u64 | WARPS x SEL_WCAP u32 | WARPS x SEL_WCAP u16 | per-cell tables sized for the plan's largest grid
     // (sel_cells_cap: static arrays of ORB_MAX_CELLS_LEVEL entries cost 1 % of the whole pipeline in residency next to k_blur)
     extern __shared__ unsigned long long s_list[];
@@ -1545,6 +1562,7 @@ k_select_fast(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells,
         }
     }
     __syncthreads();
+    tl_stamp(10);
     int total = s_off[nCells];
     if (total < 0) { if (tid == 0) nkept[f * plan->nlevels + level] = 0; return; }
     uint32_t* gbase = cand + (size_t)f * plan->cand_total;
@@ -1594,6 +1612,7 @@ k_select_fast(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells,
         __syncwarp();
     }
     __syncthreads();
+    tl_stamp(11);
     if (total > L.nDesired) {                                  // retainBest per level (:697-701)
         const orbsel::KeyGreater<unsigned long long, 32> lt64;
         if (warp == 0) {
@@ -1608,9 +1627,11 @@ k_select_fast(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells,
         total = L.nDesired;
         __syncthreads();
     }
+    tl_stamp(12);
     unsigned long long* dst = lvl + (size_t)f * plan->lvl_total + L.lvl_base;
     for (int k = tid; k < total; k += blockDim.x) dst[k] = s_list[k];
     if (tid == 0) nkept[f * plan->nlevels + level] = total;
+    tl_stamp(13);
 }
 
 template <bool HARRIS>
@@ -1619,7 +1640,7 @@ k_select(const Plan* __restrict__ plan, const CellGeom* __restrict__ cells, uint
          unsigned long long* __restrict__ cand64, const int* __restrict__ ntotal, unsigned long long* __restrict__ lvl,
          int* __restrict__ nkept, int* __restrict__ status)
 {
-    pdl_sync();
+    pdl_sync(7);
     extern __shared__ unsigned long long s_list[];            // lvl_cap records, then SEL_STAGE u32 records
     __shared__ int s_total[ORB_MAX_CELLS_LEVEL], s_retain[ORB_MAX_CELLS_LEVEL], s_off[ORB_MAX_CELLS_LEVEL + 1];
     __shared__ int s_coff[ORB_MAX_CELLS_LEVEL + 1];
@@ -1742,7 +1763,7 @@ __global__ void __launch_bounds__(BLUR_THREADS)
 k_blur(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ blurred, size_t fbytes,
        const Plan* __restrict__ plan, const Tile* __restrict__ tiles, int ntiles, int total, int* __restrict__ work_counter)
 {
-    pdl_sync();
+    pdl_sync(8);
     __shared__ __align__(128) uint8_t img2[2][BI_BUF];
     __shared__ __align__(16) float rowp[BI_H * BT_W];
     __shared__ __align__(8) uint64_t bar[2];
@@ -1908,7 +1929,7 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
            const Plan* __restrict__ plan, const unsigned long long* __restrict__ lvl, const int* __restrict__ nkept,
            orb_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int cap, int32_t* __restrict__ counts)
 {
-    pdl_sync();
+    pdl_sync(9);
     const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.y;
     const int nl = plan->nlevels;
@@ -1993,9 +2014,24 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
         kp.response = plan->harris ? __int_as_float(score) : (float)score; kp.octave = level; kp.class_id = -1;
         kps[(size_t)f * cap + slot] = kp;
     }
+    tl_stamp(14);
 }
 
 } // namespace
+
+#ifdef ORB_TIMELINE
+extern "C" int orb_debug_timeline(unsigned long long* out, int reset)
+{
+    unsigned long long h[4 * 16];
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpyFromSymbol(h, g_tl, sizeof h) != cudaSuccess) return -1;
+    if (out) memcpy(out, h, sizeof h);
+    if (reset) {
+        for (int i = 0; i < 16; i++) { h[4 * i] = h[4 * i + 1] = ~0ull; h[4 * i + 2] = h[4 * i + 3] = 0ull; }
+        if (cudaMemcpyToSymbol(g_tl, h, sizeof h) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#endif
 
 int orb_upload_constants(const int* umax)
 {
@@ -2116,8 +2152,6 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
     }
     int border_max = 1;                 // a small level with the whole 16 px frame may hold more ring words than level 0 with its 4 px ring
     for (int l = 0; l < P.nlevels; l++) border_max = std::max(border_max, P.L[l].border_items);
-    launch_k(pdl, k_border, dim3((border_max + 511) / 512, nimg * P.nlevels), 256, 0, s, W.d_planes, W.d_blur, fb, c->d_plan);
-    launches++;
     // k_blur only needs the finished pyramid: outside profiling mode it runs on a second stream,
     // concurrently with FAST -> compaction -> selection (the selection kernel is latency bound and
     // leaves most of the machine idle); k_describe joins both.
@@ -2130,14 +2164,29 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         const int grid = std::min(total, c->num_sms * c->blur_ctas);
         launch_k(false, k_blur, grid, BLUR_THREADS, 0, bs, W.tm_blur, W.d_blur, fb, c->d_plan, c->d_tiles_blur, P.ntiles_blur, total, W.d_counters + 2);
     };
-    if (fork && c->fork_early == 1) {          // blur next to FAST: FAST saturates the ALU pipe and leaves the FMA pipe idle
+    // Small calls: the reflect-101 ring is read by k_blur (3 px) and k_describe only — FAST, IC_Angle and the compaction stay inside
+    // the ROI as long as every keypoint lies 16 px from the edge — so k_border leaves the critical path and runs, followed by k_blur,
+    // on the second stream beside FAST -> compaction -> selection (timeline of one frame, tools/timeline.py: k_border held FAST back
+    // by 4.7 of the pass's 60 us).  Not for HARRIS responses or levels whose cell grid reaches into the 16 px frame (LevelGeom::ring).
+    bool side_border = fork && c->side_border && nimg <= c->small_call_frames && !P.harris;
+    for (int l = 0; l < P.nlevels; l++) side_border = side_border && P.L[l].ring == ORB_RING;
+    if (side_border) {
+        ORB_CUDA(cudaEventRecord(W.ev_fork, s));
+        ORB_CUDA(cudaStreamWaitEvent(W.aux_stream, W.ev_fork, 0));
+        launch_k(false, k_border, dim3((border_max + 511) / 512, nimg * P.nlevels), 256, 0, W.aux_stream, W.d_planes, W.d_blur, fb, c->d_plan);
+        launch_blur(W.aux_stream);
+        ORB_CUDA(cudaEventRecord(W.ev_join, W.aux_stream));
+    } else
+    launch_k(pdl, k_border, dim3((border_max + 511) / 512, nimg * P.nlevels), 256, 0, s, W.d_planes, W.d_blur, fb, c->d_plan);
+    launches++;
+    if (fork && !side_border && c->fork_early == 1) {          // blur next to FAST: FAST saturates the ALU pipe and leaves the FMA pipe idle
         ORB_CUDA(cudaEventRecord(W.ev_fork, s));
         ORB_CUDA(cudaStreamWaitEvent(W.aux_stream, W.ev_fork, 0));
     }
     mark();
     {
         const int total = P.ntiles_fast * nimg;
-        const int grid = std::min(total, c->num_sms * (fork && c->fork_early == 1 ? c->fast_ctas : FAST_CTAS));
+        const int grid = std::min(total, c->num_sms * (fork && !side_border && c->fork_early == 1 ? c->fast_ctas : FAST_CTAS));
         if (c->fast_etile && c->fast_wide && nimg <= c->small_call_frames)
             launch_k(pdl, k_fast_nms<true, FAST_THREADS_SMALL>, std::min(total, c->num_sms), FAST_THREADS_SMALL, 0, s, W.tm_fast, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total,
                      W.d_counters + 1, c->d_fast_coltab, c->d_fast_rowtab);
@@ -2148,17 +2197,17 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
             launch_k(pdl, k_fast_nms<false, FAST_THREADS>, grid, FAST_THREADS, 0, s, W.tm_fast, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total, W.d_counters + 1,
                      c->d_fast_coltab, c->d_fast_rowtab);
     }
-    if (fork && c->fork_early == 2) {     // blur starts behind FAST, next to compaction + selection
+    if (fork && !side_border && c->fork_early == 2) {     // blur starts behind FAST, next to compaction + selection
         ORB_CUDA(cudaEventRecord(W.ev_fork, s));
         ORB_CUDA(cudaStreamWaitEvent(W.aux_stream, W.ev_fork, 0));
     }
-    if (fork && (c->fork_early == 1 || c->fork_early == 2)) { launch_blur(W.aux_stream); ORB_CUDA(cudaEventRecord(W.ev_join, W.aux_stream)); }
+    if (fork && !side_border && (c->fork_early == 1 || c->fork_early == 2)) { launch_blur(W.aux_stream); ORB_CUDA(cudaEventRecord(W.ev_join, W.aux_stream)); }
     mark();
     if (c->compact_wide == 2 || (c->compact_wide && nimg <= c->small_call_frames))       // ORB_COMPACT_WIDE=2: for every call size (A/B timing)
         launch_k(pdl, k_cell_compact_wide, dim3(P.ncells, nimg), 256, 0, s, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_cells, W.d_cand, W.d_ntotal);
     else
     launch_k(pdl, k_cell_compact, dim3((P.ncells + 7) / 8, nimg), 256, 0, s, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_cells, W.d_cand, W.d_ntotal);
-    if (fork && (c->fork_early == 0 || c->fork_early == 3)) {          // blur starts when compaction is done, i.e. next to the selection kernel
+    if (fork && !side_border && (c->fork_early == 0 || c->fork_early == 3)) {          // blur starts when compaction is done, i.e. next to the selection kernel
         ORB_CUDA(cudaEventRecord(W.ev_fork, s));
         ORB_CUDA(cudaStreamWaitEvent(W.aux_stream, W.ev_fork, 0));
         if (c->fork_early == 0) { launch_blur(W.aux_stream); ORB_CUDA(cudaEventRecord(W.ev_join, W.aux_stream)); }
@@ -2187,7 +2236,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         else
             launch_k(pdl, k_select_fast<false, SEL_WARPS>, dim3(P.nlevels, nimg), SEL_WARPS * 32, sel_smem, s, c->d_plan, c->d_cells, W.d_cand, nullptr, W.d_ntotal, W.d_lvl, W.d_nkept, c->d_status, sel_spare, fb);
     }
-    if (fork && c->fork_early == 3) {      // selection first: the latency-bound kernel takes the residency it needs, blur fills the rest
+    if (fork && !side_border && c->fork_early == 3) {      // selection first: the latency-bound kernel takes the residency it needs, blur fills the rest
         launch_blur(W.aux_stream);
         ORB_CUDA(cudaEventRecord(W.ev_join, W.aux_stream));
     }
