@@ -206,7 +206,7 @@ struct orb_ctx {
     int desc_fma = 0;                                      // orb_set_descriptor_fma
     int debug_skip = 0;                                    // ORB_DEBUG_SKIP, honoured only by a -DORB_DEBUG build (timing experiments, results are wrong): 1 no blur, 2 no selection, 4 no describe
     bool pdl_call = false;                                 // this call's kernels carry the PDL launch attribute (set by launch_extract)
-    int use_pdl = 1, pdl_frames = 4;                       // ORB_PDL=0: plain stream-ordered launches (A/B timing); ORB_PDL_FRAMES: largest call launched with PDL
+    int use_pdl = 1, pdl_frames = 2;                       // ORB_PDL=0: plain stream-ordered launches (A/B timing); ORB_PDL_FRAMES: largest call launched with PDL (1 frame 93 against 102 us, 2: 108 / 111, 4: 149 / 139)
     int side_border = 1;                                   // ORB_SIDE_BORDER=0: k_border stays on the main stream for small calls too (A/B timing)
     int fast_wide = 1;                                     // ORB_FAST_WIDE=0: 128-thread k_fast_nms CTAs for small calls too (A/B timing)
     int compact_wide = 1;                                  // ORB_COMPACT_WIDE=0: k_cell_compact (warp per cell) for small calls too (A/B timing)
