@@ -165,7 +165,7 @@ static int launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_in, int n, in
     // / device buffers: graph replay alone 136 / 123 / 113, PDL launches alone 119 / 112 / 80, both 116 / 112 / 82.  (While the pass
     // still began with a memset node the combination was SLOWER than either, 157 / 146: a programmatic edge behind a memset node
     // costs a replayed graph more than all the edges gain — the counters are now cleared by the pass's first kernel.)
-    c->pdl_call = c->use_pdl && n <= c->pdl_frames;
+    c->pdl_call = c->use_pdl && n <= c->pdl_frames && (double)n * w * h <= 1e6;     // one 1080p frame: 236 us with the edges, 220 without (parked CTAs of its larger grids)
     const bool eligible = c->use_graph && !c->profile && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread &&
                           (double)n * w * h <= 12e6;
     if (!eligible) return orb_launch_extract(c, W, d_in, n, w, h, stride, pitch, o_k, o_d, cap, o_c, s);

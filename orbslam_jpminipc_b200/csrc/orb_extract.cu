@@ -2107,7 +2107,18 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
         launches++;
     }
     mark();
-    const int rv = nimg <= c->small_call_frames ? 1 : 0;      // tiling of the resize cascade: calls of a few frames take the short tiles
+    // Which small-call forms a call takes.  ORB_SMALL_CALL = 0 switches all of them off; otherwise every form has the limit at which it
+    // stopped paying on B200 (tools/latency_small_batch.py --forms4 / --each [--hd] [--noise]: blocking calls, pinned buffers, us):
+    //   short resize tiles        up to 8 frames   (VGA 1 frame 93 against 102, 4: 140 / 149, 8: 195 / 195; 1080p 1 frame 211 / 223, dense noise 598 / 641)
+    //   512-thread FAST CTAs      up to 2 frames, up to 4 while the call's tiles number at most 4 per SM
+    //                             (VGA 1: 93 / 115, 2: 109 / 131, 4: 140 / 149, 6: 177 / 168, 16: 317 / 293; 1080p 1: 211 / 237, 2: 306 / 320, 4: 478 / 437)
+    //   CTA-per-cell compaction   up to 32 frames  (VGA 16: 318 / 332, 32: 577 / 587; 1080p 1: 237 / 355; 1024 frames 0.68 / 0.32 ms)
+    //   border on the side stream up to small_call_frames (VGA 8: 202 / 215; 1080p 1: 237 / 265)
+    const bool small_on = c->small_call_frames > 0;
+    const bool sm_resize = small_on && nimg <= 8;
+    const bool sm_fast = small_on && (c->fast_wide == 2 || nimg <= 2 || (nimg <= 4 && P.ntiles_fast * nimg <= 4 * c->num_sms));   // ORB_FAST_WIDE=2: always (A/B timing)
+    const bool sm_compact = small_on && nimg <= 32;
+    const int rv = sm_resize ? 1 : 0;      // tiling of the resize cascade
     if (c->pyr_fused && P.nlevels > 1) {
         PyrParams Q;
         memset(&Q, 0, sizeof Q);
@@ -2187,7 +2198,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
     {
         const int total = P.ntiles_fast * nimg;
         const int grid = std::min(total, c->num_sms * (fork && !side_border && c->fork_early == 1 ? c->fast_ctas : FAST_CTAS));
-        if (c->fast_etile && c->fast_wide && nimg <= c->small_call_frames)
+        if (c->fast_etile && c->fast_wide && sm_fast)
             launch_k(pdl, k_fast_nms<true, FAST_THREADS_SMALL>, std::min(total, c->num_sms), FAST_THREADS_SMALL, 0, s, W.tm_fast, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_tiles_fast, P.ntiles_fast, total,
                      W.d_counters + 1, c->d_fast_coltab, c->d_fast_rowtab);
         else if (c->fast_etile)
@@ -2203,7 +2214,7 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
     }
     if (fork && !side_border && (c->fork_early == 1 || c->fork_early == 2)) { launch_blur(W.aux_stream); ORB_CUDA(cudaEventRecord(W.ev_join, W.aux_stream)); }
     mark();
-    if (c->compact_wide == 2 || (c->compact_wide && nimg <= c->small_call_frames))       // ORB_COMPACT_WIDE=2: for every call size (A/B timing)
+    if (c->compact_wide == 2 || (c->compact_wide && sm_compact))       // ORB_COMPACT_WIDE=2: for every call size (A/B timing)
         launch_k(pdl, k_cell_compact_wide, dim3(P.ncells, nimg), 256, 0, s, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_cells, W.d_cand, W.d_ntotal);
     else
     launch_k(pdl, k_cell_compact, dim3((P.ncells + 7) / 8, nimg), 256, 0, s, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_cells, W.d_cand, W.d_ntotal);

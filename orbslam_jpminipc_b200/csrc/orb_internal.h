@@ -212,9 +212,8 @@ struct orb_ctx {
     int compact_wide = 1;                                  // ORB_COMPACT_WIDE=0: k_cell_compact (warp per cell) for small calls too (A/B timing)
     int select_wide = 1;                                   // ORB_SELECT_WIDE=0: k_select_fast keeps 8 warps per CTA for small calls too (A/B timing)
     int rs_flex_width = 1;                                 // ORB_RESIZE_FLEX=0: fixed 128-column k_resize tiles (A/B timing)
-    // ORB_RESIZE_ROWS_SMALL / ORB_SMALL_CALL: the small-call kernel forms for calls of at most that many frames (0 = never).  Measured on
-    // B200, blocking 640x480 calls with pinned buffers, forms on | off: 1 frame 101 | 138 us, 2: 115 | 147, 4: 150 | 174, 8: 208 | 222,
-    // 12: 270 | 278, 16: 338 | 327, 32: 589 | 538 (tools/latency_small_batch.py) — the crossover sits between 12 and 16 frames.
+    // ORB_RESIZE_ROWS_SMALL / ORB_SMALL_CALL: rows per thread of the small-call resize tiling; the largest call (frames) that still counts
+    // as small (0 = no small-call forms at all).  The individual forms have their own limits (orb_extract.cu, orb_launch_extract).
     int rs_rows_small = 2, small_call_frames = 12;
     int stage_frames = 4;                                  // largest call whose pageable outputs return through the staged block (its rows are copied once more by the host)
     int rs_rows_pref = 8;                                  // ORB_RESIZE_ROWS: output rows per k_resize thread (tile height = 8 * rows at 128 columns)
