@@ -63,3 +63,26 @@ for (h, w, nf) in [(480, 640, 1000), (376, 1241, 2000)]:
         t0 = time.perf_counter(); call_dev(); ts.append(time.perf_counter() - t0)
     print((h, w, nf), "| device views (incl. a torch fill + the result read-back):", med(ts))
     ex.close()
+
+# ---- ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:49-125): the local-map search of
+# Tracking::SearchReferencePointsInFrustum, once per tracked frame: ~1500 projected map points against one 640x480 frame
+h, w, nf = 480, 640, 1000
+ex = pkg.ORBextractor(nf, 1.2, 8, 1, 20, max_width=w, max_height=h, max_batch=2)
+fa = synth_frame(h, w, 9000, quadrants=False)
+fb = shifted_frame(fa, 3, 2, 9001)
+(ka, da), (kb, db_) = ex.extract_batch(np.stack([fa, fb]))
+m = pkg.ORBmatcher(0.8, True, extractor=ex)
+F = pkg.Frame(m, kb, db_, w, h, 500.0, 500.0, w / 2, h / 2)
+rng = np.random.default_rng(1)
+NMP = 1500
+src = rng.integers(0, len(ka), NMP)
+px = (ka["x"][src] + 3 + rng.normal(0, 1.5, NMP)).astype(np.float32); py = (ka["y"][src] + 2 + rng.normal(0, 1.5, NMP)).astype(np.float32)
+lvl = ka["octave"][src].astype(np.int32)
+in_view = ((px > 0) & (px < w) & (py > 0) & (py < h)).astype(np.uint8)
+vcos = rng.uniform(0.9, 1.0, NMP).astype(np.float32)
+n1, mt1 = m.SearchByProjectionMapPoints(F, in_view, px, py, lvl, vcos, da[src], 3.0)
+ts = []
+for _ in range(REPS):
+    t0 = time.perf_counter(); m.SearchByProjectionMapPoints(F, in_view, px, py, lvl, vcos, da[src], 3.0); ts.append(time.perf_counter() - t0)
+print("SearchByProjection(F, %d map points, th 3) on a 640x480 / %d-keypoint frame: matches %d | host buffers (python wrapper): %s" % (NMP, F.N, n1, med(ts)))
+ex.close()
