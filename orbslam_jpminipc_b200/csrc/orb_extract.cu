@@ -1924,7 +1924,32 @@ __device__ __forceinline__ int rint_magic(float v)
 
 // One warp per output keypoint slot.  Lanes 0..30 own patch column u = lane-15 for the moments;
 // lane i then owns descriptor byte i (8 tests, 16 rotated samples).
-__global__ void __launch_bounds__(256, 8)      // 32 registers: the kernel is bound by gather latency, 0.262 -> 0.248 ms per 256 frames against 40 registers
+// ORB_DESC_STAGE (default): the 512 rotated samples of a keypoint are a gather over a 37x37 window of the blurred level (the pattern's
+// largest radius is 18.4, so a rotated coordinate rounds to at most 18): taken straight from global memory every sample instruction
+// touches about 25 sectors, and those L1 wavefronts were 0.37 of the kernel's 0.95 ms per 1024 frames (measured by collapsing the
+// addresses).  The warp therefore copies the window into shared memory first — 13 four-byte cp.async per lane, three rows of ten aligned
+// words per instruction, issued before IC_Angle so that their latency hides behind the moments — and samples it with LDS.U8.
+#ifndef ORB_DESC_STAGE
+#define ORB_DESC_STAGE 1
+#endif
+constexpr int DS_R = 18, DS_ROWS = 2 * DS_R + 1, DS_WORDS = 10, DS_PITCH = 44;      // window radius / rows, aligned words fetched per row, row pitch in shared memory (bytes)
+constexpr int DS_WARP_BYTES = (DS_ROWS * DS_PITCH + 15) & ~15;
+constexpr int IS_R = 15, IS_ROWS = 2 * IS_R + 1, IS_WORDS = 9, IS_PITCH = 36;       // the same for IC_Angle's 31x31 patch of the un-blurred level
+constexpr int IS_WARP_BYTES = (IS_ROWS * IS_PITCH + 15) & ~15;
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void* g)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+#ifndef ORB_DESC_MINB
+#define ORB_DESC_MINB 8
+#endif
+__global__ void __launch_bounds__(256, ORB_DESC_MINB)      // 32 registers: the kernel is bound by gather latency, 0.262 -> 0.248 ms per 256 frames against 40 registers
 k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurred, size_t fbytes,
            const Plan* __restrict__ plan, const unsigned long long* __restrict__ lvl, const int* __restrict__ nkept,
            orb_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int cap, int32_t* __restrict__ counts)
@@ -1948,10 +1973,61 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
     const int stride = L.stride;
     const unsigned long long rec = lvl[(size_t)f * plan->lvl_total + L.lvl_base + idx];
     const int x = (int)(rec & 0xffff), y = (int)((rec >> 16) & 0xffff), score = (int)(rec >> 32);
+#if !ORB_DESC_STAGE
     const size_t poff = (size_t)f * fbytes + L.plane_off + (size_t)(ORB_EDGE + y) * stride + ORB_EDGE + x;
     const uint8_t* center = planes + poff;                  // un-blurred plane: orientation
     const uint8_t* bcenter = blurred + poff;                // blurred ROI + un-blurred frame: descriptor
+#endif
 
+#if ORB_DESC_STAGE
+    __shared__ __align__(16) uint8_t s_patch[8][DS_WARP_BYTES + IS_WARP_BYTES];
+    const int xa = ORB_EDGE + x - DS_R;                      // padded column of the descriptor window's first byte; the copy starts at the aligned word below it
+    const int xi = ORB_EDGE + x - IS_R;                      // the same for the orientation patch
+    const uint32_t s_ic = (uint32_t)__cvta_generic_to_shared(&s_patch[threadIdx.x >> 5][0]), s_win = s_ic + IS_WARP_BYTES;
+    {
+        const size_t lev_off = (size_t)f * fbytes + L.plane_off;       // byte offset of the level inside either buffer
+        {   // un-blurred 31x31 patch: three rows of nine words per instruction (lanes 27..31 idle)
+            const int rg = lane >= 18 ? 2 : lane >= 9 ? 1 : 0, wd = lane - IS_WORDS * rg;
+            const uint8_t* gp = planes + lev_off + (size_t)(ORB_EDGE + y - IS_R + rg) * stride + (xi & ~3) + 4 * wd;
+            const uint32_t sw = s_ic + rg * IS_PITCH + 4 * wd;
+#pragma unroll
+            for (int i = 0; i < (IS_ROWS + 2) / 3; i++, gp += 3 * stride)
+                if (lane < 3 * IS_WORDS && 3 * i + rg < IS_ROWS) cp_async4(sw + i * 3 * IS_PITCH, gp);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        {   // blurred 37x37 window: three rows of ten words per instruction (lanes 30, 31 idle)
+            const int rg = lane >= 20 ? 2 : lane >= 10 ? 1 : 0, wd = lane - DS_WORDS * rg;
+            const uint8_t* gp = blurred + lev_off + (size_t)(ORB_EDGE + y - DS_R + rg) * stride + (xa & ~3) + 4 * wd;
+            const uint32_t sw = s_win + rg * DS_PITCH + 4 * wd;
+#pragma unroll
+            for (int i = 0; i < (DS_ROWS + 2) / 3; i++, gp += 3 * stride)
+                if (lane < 3 * DS_WORDS && 3 * i + rg < DS_ROWS) cp_async4(sw + i * 3 * DS_PITCH, gp);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    }
+    // IC_Angle (:124-151): m10 = sum u*I, m01 = sum v*I over the radius-15 disc; lane = column u.  Rows +v and -v of a column are inside
+    // the disc together (one predicate), and both sums ride in one register: acc = colsum * 2^19 + sum v*I  (|sum v*I| <= 255 * 240 < 2^18,
+    // colsum <= 31 * 255 < 2^13), so a pixel costs one LDS.U8 with an immediate row offset and one IMAD with an immediate multiplier.
+    int m10, m01;
+    {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        const uint32_t rows = g_rowmask[lane];              // bit (v+15): |u| <= umax[|v|]; symmetric in v; lane 31 holds 0
+        const uint32_t sp = s_ic + (uint32_t)(xi & 3) + lane;
+        uint32_t acc = 0;
+        if ((rows >> 15) & 1) acc = lds_u8(sp + IS_R * IS_PITCH) << 19;
+#pragma unroll
+        for (int v = 1; v <= IS_R; v++)
+            if ((rows >> (15 + v)) & 1) {
+                acc += lds_u8(sp + (IS_R + v) * IS_PITCH) * ((1u << 19) + (uint32_t)v);
+                acc += lds_u8(sp + (IS_R - v) * IS_PITCH) * ((1u << 19) - (uint32_t)v);
+            }
+        const int mv = ((int)(acc << 13)) >> 13;            // sign-extended low 19 bits
+        const int colsum = (int)((acc - (uint32_t)mv) >> 19);
+        m10 = __reduce_add_sync(0xffffffffu, (lane - 15) * colsum);
+        m01 = __reduce_add_sync(0xffffffffu, mv);
+    }
+#else
     // IC_Angle (:124-151): m10 = sum u*I, m01 = sum v*I over the radius-15 disc; lane = column u
     int m10 = 0, m01 = 0;
     {
@@ -1970,6 +2046,7 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
+#endif
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
     // computeOrbDescriptor (:155-194); cos/sin pinned to correctly rounded FP32 via double
@@ -1981,7 +2058,14 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
     const float2* pat = g_pattern_t + lane;
     const bool fma_form = plan->desc_fma != 0;
     // offset = cvRound(y')*stride + cvRound(x'); the 1.5*2^23 magic add leaves the rounded integer in the mantissa
+#if ORB_DESC_STAGE
+    // the same in the staged window: byte (ry + 18) * pitch + (rx + 18 + alignment offset) of the warp's copy
+    const uint32_t stage_fix = s_win + (uint32_t)(DS_R * DS_PITCH + DS_R + (xa & 3)) - 0x4B400000u * (uint32_t)(DS_PITCH + 1);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+#else
     const uint32_t magic_fix = 0u - 0x4B400000u * (uint32_t)(stride + 1);      // modulo-2^32 arithmetic, exact for the in-range result
+#endif
     // x*b + y*a and x*a - y*b (:166-167): two roundings each as written, or, when the reference is built with its own
     // -O3 -march=native on an FMA host, GCC's contraction fma(x, b, y*a) / fma(x, a, -(y*b)) (orb_set_descriptor_fma).  The flag is
     // uniform, so the choice is made once around the loop instead of per sample.
@@ -1998,7 +2082,11 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
                 const float rx = FMA ? __fmaf_rn(p.x, a, -__fmul_rn(p.y, b)) : __fsub_rn(__fmul_rn(p.x, a), __fmul_rn(p.y, b));
                 const uint32_t yb = __float_as_uint(__fadd_rn(ry, 12582912.0f));
                 const uint32_t xb = __float_as_uint(__fadd_rn(rx, 12582912.0f));
+#if ORB_DESC_STAGE
+                t[e] = (int)lds_u8(yb * (uint32_t)DS_PITCH + xb + stage_fix);
+#else
                 t[e] = bcenter[(int)(yb * (uint32_t)stride + xb + magic_fix)];
+#endif
             }
             bits |= (t[0] < t[1]) << k;
         }
