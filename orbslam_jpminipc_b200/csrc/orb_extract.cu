@@ -1888,10 +1888,11 @@ k_blur(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ blurred, size_t
 const int8_t h_pattern[1024] = {
 #include "orb_pattern.inc"
 };
-// rBRIEF pattern transposed for the warp: entry [(2*k+e)*32 + lane] = sample e of test k of descriptor byte `lane`
-__device__ float2 g_pattern_t[16 * 32];
+// rBRIEF pattern transposed for the warp
+__device__ float4 g_pattern_t[8 * 32];    // entry [k * 32 + lane] = both sample points of test k of descriptor byte `lane`: one 128-bit load per test
 __device__ uint32_t g_rowmask[32];      // IC_Angle disc: bit (v+15) of entry `lane` set iff |lane-15| <= umax[|v|]
 __constant__ int c_umax[16];
+__device__ uint4 g_icmask[32 * 3];        // IC_Angle by rows: entry [r * 3 + q], q < 2: byte (u+15) of the 32 bytes = 0xff iff |u| <= umax[|r-15|]; row 31 and q = 2 are zero
 
 // cv::fastAtan2 (degrees), every operation individually rounded to FP32 (no contraction)
 __device__ __forceinline__ float fast_atan2_deg(float y, float x)
@@ -1932,10 +1933,38 @@ __device__ __forceinline__ int rint_magic(float v)
 #ifndef ORB_DESC_STAGE
 #define ORB_DESC_STAGE 1
 #endif
-constexpr int DS_R = 18, DS_ROWS = 2 * DS_R + 1, DS_WORDS = 10, DS_PITCH = 44;      // window radius / rows, aligned words fetched per row, row pitch in shared memory (bytes)
+#ifndef ORB_DESC_WIDE
+#define ORB_DESC_WIDE 0       // 1: the descriptor window as four 16-byte chunks per row (eight rows per cp.async instruction, 64-byte pitch) instead of ten words:
+#endif                        // 5 instead of 13 copies, but 0.945 against 0.835 ms per 1024 frames — more bytes per row and a pitch of 16 banks doubles the gather's conflicts
+#if ORB_DESC_WIDE
+constexpr int DS_R = 18, DS_ROWS = 2 * DS_R + 1, DS_PITCH = 64, DS_AMASK = 15;
+#else
+constexpr int DS_R = 18, DS_ROWS = 2 * DS_R + 1, DS_WORDS = 10, DS_PITCH = 44, DS_AMASK = 3;      // window radius / rows, aligned words fetched per row, row pitch in shared memory (bytes)
+#endif
 constexpr int DS_WARP_BYTES = (DS_ROWS * DS_PITCH + 15) & ~15;
+// ORB_DESC_ROWS (default): the orientation patch is copied as three 16-byte chunks per row (ten rows per cp.async instruction) and a lane
+// owns a ROW: three LDS.128 (a 48-byte pitch is conflict free for them), the row's bytes moved to u = -15..16 by funnel shifts (the word
+// part of the alignment is warp-uniform: a switch), the disc applied as a byte mask from a 1.5 KB table in shared memory, and the row's
+// two sums taken by IDP.4A against immediate weights: 5 shared-memory loads and ~45 instructions per keypoint instead of 31 and ~85.
+#ifndef ORB_DESC_ROWS
+#define ORB_DESC_ROWS 1
+#endif
+#if ORB_DESC_ROWS
+constexpr int IS_R = 15, IS_ROWS = 2 * IS_R + 1, IS_CHUNKS = 3, IS_PITCH = 16 * IS_CHUNKS;
+#else
 constexpr int IS_R = 15, IS_ROWS = 2 * IS_R + 1, IS_WORDS = 9, IS_PITCH = 36;       // the same for IC_Angle's 31x31 patch of the un-blurred level
+#endif
 constexpr int IS_WARP_BYTES = (IS_ROWS * IS_PITCH + 15) & ~15;
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t saddr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
 __device__ __forceinline__ void cp_async4(uint32_t saddr, const void* g)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(saddr), "l"(g) : "memory");
@@ -1947,13 +1976,18 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
     return v;
 }
 #ifndef ORB_DESC_MINB
-#define ORB_DESC_MINB 8
+#define ORB_DESC_MINB 6
 #endif
 __global__ void __launch_bounds__(256, ORB_DESC_MINB)      // 32 registers: the kernel is bound by gather latency, 0.262 -> 0.248 ms per 256 frames against 40 registers
 k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurred, size_t fbytes,
            const Plan* __restrict__ plan, const unsigned long long* __restrict__ lvl, const int* __restrict__ nkept,
            orb_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int cap, int32_t* __restrict__ counts)
 {
+#if ORB_DESC_STAGE && ORB_DESC_ROWS
+    __shared__ __align__(16) uint4 s_icmask[32 * 3];
+    if (threadIdx.x < 32 * 3) s_icmask[threadIdx.x] = g_icmask[threadIdx.x];      // written at context creation: may be read ahead of the dependency wait
+    __syncthreads();
+#endif
     pdl_sync(9);
     const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.y;
@@ -1986,6 +2020,17 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
     const uint32_t s_ic = (uint32_t)__cvta_generic_to_shared(&s_patch[threadIdx.x >> 5][0]), s_win = s_ic + IS_WARP_BYTES;
     {
         const size_t lev_off = (size_t)f * fbytes + L.plane_off;       // byte offset of the level inside either buffer
+#if ORB_DESC_ROWS
+        {   // un-blurred 31x31 patch: ten rows of three 16-byte chunks per instruction (lanes 30, 31 idle)
+            const int rg = (lane * 11) >> 5, ch = lane - 3 * rg;           // lane / 3, lane % 3
+            const uint8_t* gp = planes + lev_off + (size_t)(ORB_EDGE + y - IS_R + rg) * stride + (xi & ~15) + 16 * ch;
+            const uint32_t sw = s_ic + rg * IS_PITCH + 16 * ch;
+#pragma unroll
+            for (int i = 0; i < (IS_ROWS + 9) / 10; i++, gp += 10 * stride)
+                if (lane < 30 && 10 * i + rg < IS_ROWS) cp_async16(sw + i * 10 * IS_PITCH, gp);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+#else
         {   // un-blurred 31x31 patch: three rows of nine words per instruction (lanes 27..31 idle)
             const int rg = lane >= 18 ? 2 : lane >= 9 ? 1 : 0, wd = lane - IS_WORDS * rg;
             const uint8_t* gp = planes + lev_off + (size_t)(ORB_EDGE + y - IS_R + rg) * stride + (xi & ~3) + 4 * wd;
@@ -1995,6 +2040,18 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
                 if (lane < 3 * IS_WORDS && 3 * i + rg < IS_ROWS) cp_async4(sw + i * 3 * IS_PITCH, gp);
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
+#endif
+#if ORB_DESC_WIDE
+        {   // blurred 37x37 window: eight rows of four 16-byte chunks per instruction
+            const int rg = lane >> 2, ch = lane & 3;
+            const uint8_t* gp = blurred + lev_off + (size_t)(ORB_EDGE + y - DS_R + rg) * stride + (xa & ~15) + 16 * ch;
+            const uint32_t sw = s_win + rg * DS_PITCH + 16 * ch;
+#pragma unroll
+            for (int i = 0; i < (DS_ROWS + 7) / 8; i++, gp += 8 * stride)
+                if (8 * i + rg < DS_ROWS) cp_async16(sw + i * 8 * DS_PITCH, gp);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+#else
         {   // blurred 37x37 window: three rows of ten words per instruction (lanes 30, 31 idle)
             const int rg = lane >= 20 ? 2 : lane >= 10 ? 1 : 0, wd = lane - DS_WORDS * rg;
             const uint8_t* gp = blurred + lev_off + (size_t)(ORB_EDGE + y - DS_R + rg) * stride + (xa & ~3) + 4 * wd;
@@ -2004,6 +2061,7 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
                 if (lane < 3 * DS_WORDS && 3 * i + rg < DS_ROWS) cp_async4(sw + i * 3 * DS_PITCH, gp);
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
+#endif
     }
     // IC_Angle (:124-151): m10 = sum u*I, m01 = sum v*I over the radius-15 disc; lane = column u.  Rows +v and -v of a column are inside
     // the disc together (one predicate), and both sums ride in one register: acc = colsum * 2^19 + sum v*I  (|sum v*I| <= 255 * 240 < 2^18,
@@ -2012,6 +2070,33 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
     {
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
+#if ORB_DESC_ROWS
+        // lane = row v = lane - 15 (lane 31: its mask row is zero).  w[] = the row's 48 bytes; the patch starts at byte xi & 15.
+        const uint32_t ra = s_ic + lane * IS_PITCH;
+        const uint4 q0 = lds_u128(ra), q1 = lds_u128(ra + 16), q2 = lds_u128(ra + 32);
+        const uint32_t ma = (uint32_t)__cvta_generic_to_shared(s_icmask) + lane * 48;
+        const uint4 k0 = lds_u128(ma), k1 = lds_u128(ma + 16);
+        const uint32_t w[12] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w };
+        const uint32_t mk[8] = { k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w };
+        const uint32_t sh = 8u * (uint32_t)(xi & 3);
+        uint32_t d[8];
+        switch ((xi >> 2) & 3) {                               // warp-uniform word offset of the patch inside the row
+#define ORB_IC_ALIGN(K) _Pragma("unroll") for (int i = 0; i < 8; i++) d[i] = __funnelshift_r(w[K + i], w[K + i + 1], sh) & mk[i];
+        case 0: ORB_IC_ALIGN(0) break;
+        case 1: ORB_IC_ALIGN(1) break;
+        case 2: ORB_IC_ALIGN(2) break;
+        default: ORB_IC_ALIGN(3) break;
+#undef ORB_IC_ALIGN
+        }
+        uint32_t rowsum = 0, wsum = 0;                         // sum I and sum (u + 15) * I over the row's part of the disc
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            rowsum = __dp4a(d[i], 0x01010101u, rowsum);
+            wsum = __dp4a(d[i], 0x03020100u + 0x04040404u * (uint32_t)i, wsum);
+        }
+        m10 = __reduce_add_sync(0xffffffffu, (int)wsum - 15 * (int)rowsum);
+        m01 = __reduce_add_sync(0xffffffffu, (lane - 15) * (int)rowsum);
+#else
         const uint32_t rows = g_rowmask[lane];              // bit (v+15): |u| <= umax[|v|]; symmetric in v; lane 31 holds 0
         const uint32_t sp = s_ic + (uint32_t)(xi & 3) + lane;
         uint32_t acc = 0;
@@ -2026,6 +2111,7 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
         const int colsum = (int)((acc - (uint32_t)mv) >> 19);
         m10 = __reduce_add_sync(0xffffffffu, (lane - 15) * colsum);
         m01 = __reduce_add_sync(0xffffffffu, mv);
+#endif
     }
 #else
     // IC_Angle (:124-151): m10 = sum u*I, m01 = sum v*I over the radius-15 disc; lane = column u
@@ -2055,12 +2141,12 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
     float a, b;
     if (lane == 0) { double sd, cd; sincos((double)arad, &sd, &cd); a = (float)cd; b = (float)sd; }
     a = __shfl_sync(0xffffffffu, a, 0); b = __shfl_sync(0xffffffffu, b, 0);
-    const float2* pat = g_pattern_t + lane;
+    const float4* pat = g_pattern_t + lane;
     const bool fma_form = plan->desc_fma != 0;
     // offset = cvRound(y')*stride + cvRound(x'); the 1.5*2^23 magic add leaves the rounded integer in the mantissa
 #if ORB_DESC_STAGE
     // the same in the staged window: byte (ry + 18) * pitch + (rx + 18 + alignment offset) of the warp's copy
-    const uint32_t stage_fix = s_win + (uint32_t)(DS_R * DS_PITCH + DS_R + (xa & 3)) - 0x4B400000u * (uint32_t)(DS_PITCH + 1);
+    const uint32_t stage_fix = s_win + (uint32_t)(DS_R * DS_PITCH + DS_R + (xa & DS_AMASK)) - 0x4B400000u * (uint32_t)(DS_PITCH + 1);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
 #else
@@ -2075,9 +2161,10 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             int t[2];
+            const float4 pp = __ldg(pat + k * 32);
 #pragma unroll
             for (int e = 0; e < 2; e++) {
-                const float2 p = __ldg(pat + (2 * k + e) * 32);
+                const float2 p = e ? make_float2(pp.z, pp.w) : make_float2(pp.x, pp.y);
                 const float ry = FMA ? __fmaf_rn(p.x, b, __fmul_rn(p.y, a)) : __fadd_rn(__fmul_rn(p.x, b), __fmul_rn(p.y, a));
                 const float rx = FMA ? __fmaf_rn(p.x, a, -__fmul_rn(p.y, b)) : __fsub_rn(__fmul_rn(p.x, a), __fmul_rn(p.y, b));
                 const uint32_t yb = __float_as_uint(__fadd_rn(ry, 12582912.0f));
@@ -2124,13 +2211,12 @@ extern "C" int orb_debug_timeline(unsigned long long* out, int reset)
 int orb_upload_constants(const int* umax)
 {
     ORB_CUDA(cudaMemcpyToSymbol(c_umax, umax, sizeof(int) * 16));
-    float2 t[16 * 32];
+    float4 t[8 * 32];
     for (int lane = 0; lane < 32; lane++)
-        for (int k = 0; k < 8; k++)
-            for (int e = 0; e < 2; e++) {
-                const int8_t* p = h_pattern + lane * 32 + 4 * k + 2 * e;
-                t[(2 * k + e) * 32 + lane] = make_float2((float)p[0], (float)p[1]);
-            }
+        for (int k = 0; k < 8; k++) {
+            const int8_t* p = h_pattern + lane * 32 + 4 * k;
+            t[k * 32 + lane] = make_float4((float)p[0], (float)p[1], (float)p[2], (float)p[3]);
+        }
     ORB_CUDA(cudaMemcpyToSymbol(g_pattern_t, t, sizeof t));
     uint32_t rm[32];
     for (int lane = 0; lane < 32; lane++) {
@@ -2139,6 +2225,13 @@ int orb_upload_constants(const int* umax)
         for (int v = -15; v <= 15; v++) if (au <= umax[v < 0 ? -v : v]) rm[lane] |= 1u << (v + 15);
     }
     ORB_CUDA(cudaMemcpyToSymbol(g_rowmask, rm, sizeof rm));
+    uint8_t im[32 * 48];
+    memset(im, 0, sizeof im);
+    for (int r = 0; r < 31; r++) {
+        const int av = r > 15 ? r - 15 : 15 - r;
+        for (int u = -15; u <= 15; u++) if ((u < 0 ? -u : u) <= umax[av]) im[r * 48 + u + 15] = 0xff;
+    }
+    ORB_CUDA(cudaMemcpyToSymbol(g_icmask, im, sizeof im));
     return ORB_OK;
 }
 
