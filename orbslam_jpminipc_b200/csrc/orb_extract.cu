@@ -1927,9 +1927,9 @@ __device__ __forceinline__ int rint_magic(float v)
 // lane i then owns descriptor byte i (8 tests, 16 rotated samples).
 // ORB_DESC_STAGE (default): the 512 rotated samples of a keypoint are a gather over a 37x37 window of the blurred level (the pattern's
 // largest radius is 18.4, so a rotated coordinate rounds to at most 18): taken straight from global memory every sample instruction
-// touches about 25 sectors, and those L1 wavefronts were 0.37 of the kernel's 0.95 ms per 1024 frames (measured by collapsing the
-// addresses).  The warp therefore copies the window into shared memory first — 13 four-byte cp.async per lane, three rows of ten aligned
-// words per instruction, issued before IC_Angle so that their latency hides behind the moments — and samples it with LDS.U8.
+// touches about 22 different 128-byte lines (~350 L1 wavefronts per keypoint against ~80 for copying the window once).  The warp therefore
+// copies the window into shared memory first — 13 four-byte cp.async per lane, three rows of ten aligned words per instruction, issued
+// ahead of IC_Angle — and samples it with LDS.U8.
 #ifndef ORB_DESC_STAGE
 #define ORB_DESC_STAGE 1
 #endif
