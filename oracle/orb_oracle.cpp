@@ -247,14 +247,49 @@ float ic_angle(const uint8_t* center, int step, const int* umax)
     return fast_atan2((float)m_01, (float)m_10);
 }
 
-/* computeOrbDescriptor, src/ORBextractor.cc:155-194.  cos/sin: the reference's
- * cosf/sinf (libm-variant dependent in the last bit) are pinned to correctly
- * rounded single precision computed through double. */
+/* cosf / sinf as the reference calls them at src/ORBextractor.cc:160 (`cos(angle)` on a float with `using namespace std`).  The algorithm
+ * is glibc's (libm >= 2.28, the image has 2.39; not part of /root/reference): sysdeps/ieee754/flt-32/s_sinf.c, s_cosf.c, sincosf.h — the
+ * argument in double, n = round(x * 2/pi) by a scaled truncation, x - n * pi/2, a degree-7 sine or degree-8 cosine polynomial, one rounding
+ * to float.  Restated for 0 <= y < 120 in plain double operations; orb_oracle_trig_mismatches() compares it with the host's own cosf / sinf
+ * (tests/test_oracle_golden.py, strided over every binade of [0, 360] degrees; tools/cpp/sincos_exhaustive.cu does all 1 135 869 953 angles). */
+static float trig_poly(double x, double x2, bool neg_cos, int n)
+{
+    if ((n & 1) == 0) {
+        const double s0 = -0x1.555545995a603p-3, s1 = 0x1.1107605230bc4p-7, s2 = -0x1.994eb3774cf24p-13;
+        double x3 = x * x2, t1 = s1 + x2 * s2, x7 = x3 * x2, s = x + x3 * s0;
+        return (float)(s + x7 * t1);
+    }
+    const double sg = neg_cos ? -1.0 : 1.0;
+    const double c0 = sg, c1 = sg * -0x1.ffffffd0c621cp-2, c2 = sg * 0x1.55553e1068f19p-5, c3 = sg * -0x1.6c087e89a359dp-10, c4 = sg * 0x1.99343027bf8c3p-16;
+    double x4 = x2 * x2, q2 = c3 + x2 * c4, q1 = c0 + x2 * c1, x6 = x4 * x2, c = q1 + x4 * c2;
+    return (float)(c + x6 * q2);
+}
+static void ref_sincosf(float y, float* sn, float* cs)
+{
+    uint32_t bits; memcpy(&bits, &y, 4);
+    const uint32_t top = (bits >> 20) & 0x7ff;
+    double x = (double)y;
+    if (top < 0x3f4) {
+        if (top < 0x398) { *cs = 1.0f; *sn = y; return; }
+        double x2 = x * x;
+        *sn = trig_poly(x, x2, false, 0); *cs = trig_poly(x, x2, false, 1);
+        return;
+    }
+    double r = x * 0x1.45F306DC9C883p+23;
+    int n = ((int32_t)r + 0x800000) >> 24;
+    x = x - n * 0x1.921FB54442D18p0;
+    const bool neg = (n & 2) != 0;
+    double xs = ((n + 1) & 2) ? -x : x, x2 = x * x;
+    *sn = trig_poly(xs, x2, neg, n); *cs = trig_poly(xs, x2, neg, n ^ 1);
+}
+
+/* computeOrbDescriptor, src/ORBextractor.cc:155-194. */
 void rbrief(const uint8_t* center, int step, float angle_deg, uint8_t* desc, bool fma_form = false)
 {
     const float factorPI = (float)(M_PI / 180.f);        /* :154 */
     float angle = angle_deg * factorPI;                   /* :159 */
-    float a = (float)cos((double)angle), b = (float)sin((double)angle);
+    float a, b;
+    ref_sincosf(angle, &b, &a);                            /* :160 */
     const int8_t* pat = kPattern;
     for (int i = 0; i < 32; ++i, pat += 32) {
         int val = 0;
@@ -352,6 +387,23 @@ struct orc_extractor {
 };
 
 extern "C" {
+
+/* The restatement of cosf / sinf above against the HOST's libm on the angles with bit patterns lo, lo + step, .. <= hi (degrees, as
+ * kpt.angle): the number of angles on which cos or sin differ.  Test infrastructure for tests/test_oracle_golden.py. */
+long long orc_trig_mismatches(uint32_t lo, uint32_t hi, uint32_t step)
+{
+    const float factorPI = (float)(M_PI / 180.f);
+    long long bad = 0;
+    for (uint64_t u = lo; u <= hi; u += step) {
+        uint32_t b32 = (uint32_t)u; float deg; memcpy(&deg, &b32, 4);
+        volatile float rad = deg * factorPI;
+        float sn, cs;
+        ref_sincosf(rad, &sn, &cs);
+        const float hc = cosf(rad), hs = sinf(rad);
+        bad += memcmp(&cs, &hc, 4) != 0 || memcmp(&sn, &hs, 4) != 0;
+    }
+    return bad;
+}
 
 orc_extractor* orc_extractor_create(int nfeatures, float scale_factor, int nlevels,
                                     int score_type, int fast_th, int blur_variant)

@@ -35,6 +35,8 @@ typedef struct orc_extractor orc_extractor;
 orc_extractor* orc_extractor_create(int nfeatures, float scale_factor, int nlevels,
                                     int score_type, int fast_th, int blur_variant);
 void orc_extractor_destroy(orc_extractor*);
+/* restated cosf / sinf of the descriptor rotation vs the host's libm on angle bit patterns lo, lo + step, .. <= hi: number of differing angles */
+long long orc_trig_mismatches(uint32_t lo, uint32_t hi, uint32_t step);
 /* descriptor rotation x*b + y*a (src/ORBextractor.cc:166-167) as GCC contracts it under the reference's own -O3 -march=native on an
  * FMA host: fma(x, b, y*a) / fma(x, a, -(y*b)).  Default 0 = as written (two roundings). */
 void orc_extractor_set_descriptor_fma(orc_extractor*, int on);

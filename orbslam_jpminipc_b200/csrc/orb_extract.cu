@@ -13,6 +13,7 @@
 // Integer stages are bit-exact by construction; the two floating-point stages (blur, angle /
 // rotation) spell out every rounding with __f*_rn / fmaf so the compiler cannot contract them.
 #include "orb_internal.h"
+#include "orb_trig.h"
 #include <mutex>
 #include <type_traits>
 #include <climits>
@@ -2135,12 +2136,16 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
 #endif
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    // computeOrbDescriptor (:155-194); cos/sin pinned to correctly rounded FP32 via double
+    // computeOrbDescriptor (:155-194); cos / sin = glibc's cosf / sinf restated in orb_trig.h (pinned on every float angle)
     const float factorPI = (float)(3.14159265358979323846 / 180.f);
     const float arad = __fmul_rn(angle, factorPI);
     float a, b;
+#ifdef ORB_DESC_TRIG_CR       // the earlier pin: correctly rounded through double (differs from glibc's cosf / sinf by one ulp on 0.13 % of all angles)
     if (lane == 0) { double sd, cd; sincos((double)arad, &sd, &cd); a = (float)cd; b = (float)sd; }
     a = __shfl_sync(0xffffffffu, a, 0); b = __shfl_sync(0xffffffffu, b, 0);
+#else
+    orbtrig::sincosf_glibc(arad, b, a);                    // glibc's cosf / sinf, the reference's own calls (orb_trig.h); every lane computes it (~35 instructions, no shuffle)
+#endif
     const float4* pat = g_pattern_t + lane;
     const bool fma_form = plan->desc_fma != 0;
     // offset = cvRound(y')*stride + cvRound(x'); the 1.5*2^23 magic add leaves the rounded integer in the mantissa

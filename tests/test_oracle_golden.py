@@ -140,3 +140,19 @@ def test_gemm_projection_pin(prim):
             t0 = np.float32(t0 + np.float32(T[i, r, 2] * X[i, 2, 0]))
             v = np.float32(float(t0) + float(T[i, r, 3]))
             assert v.view(np.uint32) == Y[i, r]
+
+
+def test_descriptor_trig_equals_host_libm():
+    """The oracle restates glibc's cosf / sinf (the reference's calls at src/ORBextractor.cc:160) instead of calling libm, so that the pin does
+    not move with the host.  Here the restatement is compared with this host's own cosf / sinf on every 89th float angle of [0, 360] degrees
+    (12.8 M angles over all binades) and on two dense runs; tools/cpp/sincos_exhaustive.cu covers all 1 135 869 953 angles on the GPU box."""
+    import ctypes as C
+    L = po.lib()
+    L.orc_trig_mismatches.restype = C.c_longlong
+    L.orc_trig_mismatches.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+    last = int(np.float32(360.0).view(np.uint32))
+    assert L.orc_trig_mismatches(0, last, 89) == 0
+    lo = int(np.float32(0.1).view(np.uint32))                       # where glibc's sinf is most often one ulp from the correctly rounded value
+    assert L.orc_trig_mismatches(lo, lo + 2_000_000, 1) == 0
+    lo = int(np.float32(44.9).view(np.uint32))                      # across the pi/4 switch of the argument reduction
+    assert L.orc_trig_mismatches(lo, lo + 2_000_000, 1) == 0
