@@ -250,7 +250,7 @@ float ic_angle(const uint8_t* center, int step, const int* umax)
 /* cosf / sinf as the reference calls them at src/ORBextractor.cc:160 (`cos(angle)` on a float with `using namespace std`).  The algorithm
  * is glibc's (libm >= 2.28, the image has 2.39; not part of /root/reference): sysdeps/ieee754/flt-32/s_sinf.c, s_cosf.c, sincosf.h — the
  * argument in double, n = round(x * 2/pi) by a scaled truncation, x - n * pi/2, a degree-7 sine or degree-8 cosine polynomial, one rounding
- * to float.  Restated for 0 <= y < 120 in plain double operations; orb_oracle_trig_mismatches() compares it with the host's own cosf / sinf
+ * to float.  Restated for 0 <= y < 120 in plain double operations; orc_trig_mismatches() compares it with the host's own cosf / sinf
  * (tests/test_oracle_golden.py, strided over every binade of [0, 360] degrees; tools/cpp/sincos_exhaustive.cu does all 1 135 869 953 angles). */
 static float trig_poly(double x, double x2, bool neg_cos, int n)
 {
