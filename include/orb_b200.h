@@ -70,7 +70,9 @@ int      orb_keypoint_capacity(const orb_ctx*);/* rows to allocate per image: su
 /* Which reference BUILD the descriptors reproduce.  The rotation of the sampling pattern, `x*b + y*a` / `x*a - y*b`
  * (src/ORBextractor.cc:166-167), is written with two roundings per expression; the reference's own flags (-O3 -march=native,
  * CMakeLists.txt:12-13) let GCC contract it to fma(x, b, y*a) / fma(x, a, -(y*b)) on an FMA-capable host, which changes about 2
- * descriptor bits per 40 000 keypoints.  on = 0 (default): as written; on = 1: the contracted form.  Keypoints are unaffected. */
+ * descriptor bits per 40 000 keypoints.  on = 0 (default): as written; on = 1: the contracted form.  Keypoints are unaffected.
+ * The rotation factors themselves, `a = (float)cos(angle), b = (float)sin(angle)` (:160, libm's cosf / sinf on a float), are glibc's
+ * (>= 2.28) cosf / sinf bit for bit on every float angle (csrc/orb_trig.h, tools/cpp/sincos_exhaustive.cu). */
 int      orb_set_descriptor_fma(orb_ctx*, int on);
 
 /* ORBextractor::operator()(image, mask, keypoints, descriptors), src/ORBextractor.cc:718-779.
