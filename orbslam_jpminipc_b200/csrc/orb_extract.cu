@@ -1945,7 +1945,7 @@ constexpr int DS_R = 18, DS_ROWS = 2 * DS_R + 1, DS_WORDS = 10, DS_PITCH = 44, D
 constexpr int DS_WARP_BYTES = (DS_ROWS * DS_PITCH + 15) & ~15;
 // ORB_DESC_ROWS (default): the orientation patch is copied as three 16-byte chunks per row (ten rows per cp.async instruction) and a lane
 // owns a ROW: three LDS.128 (a 48-byte pitch is conflict free for them), the row's bytes moved to u = -15..16 by funnel shifts (the word
-// part of the alignment is warp-uniform: a switch), the disc applied as a byte mask from a 1.5 KB table in shared memory, and the row's
+// part of the alignment is warp-uniform: a switch), the disc applied as a byte mask from a 1.5 KB table (L1-resident), and the row's
 // two sums taken by IDP.4A against immediate weights: 5 shared-memory loads and ~45 instructions per keypoint instead of 31 and ~85.
 #ifndef ORB_DESC_ROWS
 #define ORB_DESC_ROWS 1
@@ -1984,11 +1984,6 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
            const Plan* __restrict__ plan, const unsigned long long* __restrict__ lvl, const int* __restrict__ nkept,
            orb_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int cap, int32_t* __restrict__ counts)
 {
-#if ORB_DESC_STAGE && ORB_DESC_ROWS
-    __shared__ __align__(16) uint4 s_icmask[32 * 3];
-    if (threadIdx.x < 32 * 3) s_icmask[threadIdx.x] = g_icmask[threadIdx.x];      // written at context creation: may be read ahead of the dependency wait
-    __syncthreads();
-#endif
     pdl_sync(9);
     const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.y;
@@ -2075,8 +2070,9 @@ k_describe(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ blurr
         // lane = row v = lane - 15 (lane 31: its mask row is zero).  w[] = the row's 48 bytes; the patch starts at byte xi & 15.
         const uint32_t ra = s_ic + lane * IS_PITCH;
         const uint4 q0 = lds_u128(ra), q1 = lds_u128(ra + 16), q2 = lds_u128(ra + 32);
-        const uint32_t ma = (uint32_t)__cvta_generic_to_shared(s_icmask) + lane * 48;
-        const uint4 k0 = lds_u128(ma), k1 = lds_u128(ma + 16);
+        // the disc as byte masks of this lane's row, straight from the 1.5 KB table in global memory (L1-resident): a copy of the table in
+        // shared memory cost a CTA barrier in front of everything else — 0.828 against 0.792 ms per 1024 frames
+        const uint4 k0 = __ldg(g_icmask + lane * 3), k1 = __ldg(g_icmask + lane * 3 + 1);
         const uint32_t w[12] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w };
         const uint32_t mk[8] = { k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w };
         const uint32_t sh = 8u * (uint32_t)(xi & 3);
