@@ -466,3 +466,17 @@ def test_small_calls_take_the_latency_paths_and_agree(pkg, po, shape, nf, score)
                         rk, rd = want[i]
                         _same(kk[i, :int(c[i])], d.numpy()[i, :int(c[i])], rk, rd, (env != {}, n, pinned, rep, i))
         ex.close()
+
+
+def test_rotation_factors_equal_libm_on_every_angle():
+    """cosf / sinf of the descriptor rotation (reference src/ORBextractor.cc:160): the device function k_describe calls (csrc/orb_trig.h)
+    against this host's libm on EVERY float angle in [0, 360] degrees, 1 135 869 953 arguments (tools/cpp/sincos_exhaustive.cu, built by
+    __graft_entry__.build(); a few seconds).  Exit code 1 = some angle differs."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(G), os.pardir, "tools", "cpp", "build", "sincos_ex")
+    if not os.path.exists(exe):
+        pytest.skip("tools/cpp/build/sincos_ex not built")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    tail = r.stdout.strip().splitlines()[-5:]
+    assert r.returncode == 0, tail
+    assert any("the function k_describe calls" in l and "differs from the host's cosf / sinf: 0 of" in l for l in tail), tail
