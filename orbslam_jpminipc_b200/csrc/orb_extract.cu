@@ -1178,20 +1178,37 @@ k_fast_nms(const __grid_constant__ TmapSet tm, uint8_t* __restrict__ nms, uint8_
 // threshold 7 (src/ORBextractor.cc:609-614) — both sets are sub-sequences of the th_lo list
 // ("one-pass fallback").
 // record = score<<24 | y_local<<12 | x_local   (cell-image coordinates, as cv::FAST reports)
+// A warp's life here is short (one or two steps over a cell) and mostly a chain of dependent memory round trips: cell count -> cell geometry ->
+// level geometry -> bitmap word -> response.  The plan's part of it (ORB_COMPACT_ARGS, default) travels in the kernel's parameter block instead,
+// which leaves three round trips.
+#ifndef ORB_COMPACT_ARGS
+#define ORB_COMPACT_ARGS 1
+#endif
+struct CompactGeom { int plane_off[ORB_MAX_LEVELS], stride[ORB_MAX_LEVELS], bm_off[ORB_MAX_LEVELS], bm_pitch[ORB_MAX_LEVELS]; int ncells, bm_total, cand_total, fast_th; };
 __global__ void __launch_bounds__(256, 8)      // 32 registers (20 bytes spilled): latency bound, 0.128 -> 0.108 ms per 256 frames against 47 registers
 k_cell_compact(const uint8_t* __restrict__ nms, const uint8_t* __restrict__ bitmap, size_t fbytes, const Plan* __restrict__ plan,
-               const CellGeom* __restrict__ cells, uint32_t* __restrict__ cand, int* __restrict__ ntotal)
+               const CellGeom* __restrict__ cells, uint32_t* __restrict__ cand, int* __restrict__ ntotal, const __grid_constant__ CompactGeom cg)
 {
     pdl_sync(5);
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= plan->ncells) return;
+#if ORB_COMPACT_ARGS
+    const int ncells = cg.ncells;
+    if (warp >= ncells) return;
+    const int f = blockIdx.y;
+    const CellGeom g = cells[warp];
+    struct { int plane_off, stride, bm_off, bm_pitch; } L = { cg.plane_off[g.level], cg.stride[g.level], cg.bm_off[g.level], cg.bm_pitch[g.level] };
+    const int bm_total = cg.bm_total, cand_total = cg.cand_total, thP = cg.fast_th;
+#else
+    const int ncells = plan->ncells;
+    if (warp >= ncells) return;
     const int f = blockIdx.y;
     const CellGeom g = cells[warp];
     const LevelGeom& L = plan->L[g.level];
+    const int bm_total = plan->bm_total, cand_total = plan->cand_total, thP = plan->fast_th;
+#endif
     const uint8_t* map = nms + (size_t)f * fbytes + L.plane_off + (size_t)ORB_EDGE * L.stride + ORB_EDGE;
-    const uint32_t* bm = reinterpret_cast<const uint32_t*>(bitmap + (size_t)f * plan->bm_total + L.bm_off);
-    uint32_t* out = cand + (size_t)f * plan->cand_total + g.cand_off;
-    const int thP = plan->fast_th;
+    const uint32_t* bm = reinterpret_cast<const uint32_t*>(bitmap + (size_t)f * bm_total + L.bm_off);
+    uint32_t* out = cand + (size_t)f * cand_total + g.cand_off;
     int count = 0, nP = 0, n7 = 0;
     // The rectangle is walked as (row, 32-pixel bitmap word) items in raster order; a lane owns one item per step.
     const int b0 = g.x0 - ORB_EDGE, b1 = g.x1 - ORB_EDGE;            // bit range [b0, b1) of a bitmap row
@@ -1248,7 +1265,7 @@ k_cell_compact(const uint8_t* __restrict__ nms, const uint8_t* __restrict__ bitm
         }
         count = w;
     }
-    if (lane == 0) ntotal[(size_t)f * plan->ncells + warp] = count;
+    if (lane == 0) ntotal[(size_t)f * ncells + warp] = count;
 }
 
 // Calls of a few frames (single-frame latency): one CTA per (frame, cell) instead of one warp.  A warp's serial walk over a whole
@@ -2399,7 +2416,13 @@ int orb_launch_extract(orb_ctx* c, WorkSet& W, const uint8_t* d_imgs, int nimg, 
     if (c->compact_wide == 2 || (c->compact_wide && sm_compact))       // ORB_COMPACT_WIDE=2: for every call size (A/B timing)
         launch_k(pdl, k_cell_compact_wide, dim3(P.ncells, nimg), 256, 0, s, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_cells, W.d_cand, W.d_ntotal);
     else
-    launch_k(pdl, k_cell_compact, dim3((P.ncells + 7) / 8, nimg), 256, 0, s, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_cells, W.d_cand, W.d_ntotal);
+    {
+        CompactGeom cg;
+        memset(&cg, 0, sizeof cg);
+        for (int l = 0; l < P.nlevels; l++) { cg.plane_off[l] = P.L[l].plane_off; cg.stride[l] = P.L[l].stride; cg.bm_off[l] = P.L[l].bm_off; cg.bm_pitch[l] = P.L[l].bm_pitch; }
+        cg.ncells = P.ncells; cg.bm_total = P.bm_total; cg.cand_total = P.cand_total; cg.fast_th = P.fast_th;
+        launch_k(pdl, k_cell_compact, dim3((P.ncells + 7) / 8, nimg), 256, 0, s, W.d_work, W.d_bitmap, fb, c->d_plan, c->d_cells, W.d_cand, W.d_ntotal, cg);
+    }
     if (fork && !side_border && (c->fork_early == 0 || c->fork_early == 3)) {          // blur starts when compaction is done, i.e. next to the selection kernel
         ORB_CUDA(cudaEventRecord(W.ev_fork, s));
         ORB_CUDA(cudaStreamWaitEvent(W.aux_stream, W.ev_fork, 0));
