@@ -1963,7 +1963,7 @@ constexpr int DS_WARP_BYTES = (DS_ROWS * DS_PITCH + 15) & ~15;
 // ORB_DESC_ROWS (default): the orientation patch is copied as three 16-byte chunks per row (ten rows per cp.async instruction) and a lane
 // owns a ROW: three LDS.128 (a 48-byte pitch is conflict free for them), the row's bytes moved to u = -15..16 by funnel shifts (the word
 // part of the alignment is warp-uniform: a switch), the disc applied as a byte mask from a 1.5 KB table (L1-resident), and the row's
-// two sums taken by IDP.4A against immediate weights: 5 shared-memory loads and ~45 instructions per keypoint instead of 31 and ~85.
+// two sums taken by IDP.4A against immediate weights: three shared-memory and two table loads and ~45 instructions per keypoint instead of 31 loads and ~85.
 #ifndef ORB_DESC_ROWS
 #define ORB_DESC_ROWS 1
 #endif
