@@ -156,3 +156,17 @@ def test_descriptor_trig_equals_host_libm():
     assert L.orc_trig_mismatches(lo, lo + 2_000_000, 1) == 0
     lo = int(np.float32(44.9).view(np.uint32))                      # across the pi/4 switch of the argument reduction
     assert L.orc_trig_mismatches(lo, lo + 2_000_000, 1) == 0
+
+
+def test_trig_constants_shared_by_kernel_and_oracle():
+    """csrc/orb_trig.h (device) and oracle/orb_oracle.cpp (checker) restate the same libm algorithm: their hexadecimal float constants
+    (reduction factor, pi/2, polynomial coefficients) and the two argument-range thresholds must be the same set."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dev = open(os.path.join(root, "orbslam_jpminipc_b200", "csrc", "orb_trig.h")).read()
+    ora = open(os.path.join(root, "oracle", "orb_oracle.cpp")).read()
+    ora = ora[ora.index("static float trig_poly"):ora.index("/* computeOrbDescriptor, src/ORBextractor.cc:155-194. */")]
+    hexf = lambda s: sorted(set(float.fromhex(m) for m in re.findall(r"0x1(?:\.[0-9a-fA-F]+)?p[+-]?\d+", s)))
+    assert hexf(dev) == hexf(ora) and len(hexf(dev)) == 9      # 2/pi * 2^24, pi/2, four cosine and three sine coefficients (c0 = 1 is spelled as the sign)
+    for t in ("0x3f4", "0x398", "0x800000"):
+        assert t in dev and t in ora
